@@ -1,0 +1,200 @@
+/*
+ * nbslice_b200.h -- C ABI of the B200-native SlicedNonbondedForce hot path.
+ *
+ * This is the drop-in boundary below the plugin's CalcSlicedNonbondedForceKernel
+ * interface (reference: openmmapi/include/NonbondedSlicingKernels.h:27-85).  The C++
+ * platform kernel in openmm-nonbonded-slicing_b200/platform/ subclasses that interface and
+ * forwards to the entry points declared here; nothing in these signatures depends on
+ * OpenMM, torch or C++ types -- plain pointers, sizes and status codes only.
+ *
+ * Mapping to the reference interface (file:line relative to the reference checkout):
+ *
+ *   nbs_create              <- CalcSlicedNonbondedForceKernel::initialize
+ *                              (NonbondedSlicingKernels.h:48; what the Reference platform
+ *                              collects from the Force in ReferenceNonbondedSlicingKernels.cpp:59-185)
+ *   nbs_execute             <- CalcSlicedNonbondedForceKernel::execute
+ *                              (NonbondedSlicingKernels.h:59; ReferenceNonbondedSlicingKernels.cpp:187-268)
+ *   nbs_update_parameters   <- CalcSlicedNonbondedForceKernel::copyParametersToContext
+ *                              (NonbondedSlicingKernels.h:66; ReferenceNonbondedSlicingKernels.cpp:270-319)
+ *   nbs_get_pme_parameters  <- CalcSlicedNonbondedForceKernel::getPMEParameters
+ *                              (NonbondedSlicingKernels.h:75; ReferenceNonbondedSlicingKernels.cpp:321-328)
+ *   nbs_set_lambdas /
+ *   nbs_set_global_parameters
+ *                           <- the per-evaluation reads of Context parameters in
+ *                              ReferenceNonbondedSlicingKernels.cpp:339-392 (computeParameters)
+ *   nbs_destroy             <- KernelImpl destructor
+ *   nbs_last_error          <- the OpenMMException messages the adapter rethrows
+ *                              (SURVEY 8b "Errors")
+ *
+ * Conventions (reference: SURVEY Appendix A):
+ *   units nm, kJ/mol, e;  slice(i,j) = max*(max+1)/2 + min  (SlicedNonbondedForce.h:22);
+ *   term index 0 = Coulomb, 1 = van der Waals (ReferenceNonbondedSlicingKernels.h:76-77);
+ *   slice energies are UNSCALED by lambda; forces are lambda-scaled
+ *   (ReferenceSlicedLJCoulombIxn.cpp:435-444).
+ *
+ * All functions return NBS_OK (0) or a negative status; the message for the calling
+ * thread's last failure is available from nbs_last_error().  There is no CPU fallback:
+ * every compute entry point fails with NBS_ERR_CUDA if no usable sm_100 device exists.
+ */
+#ifndef NBSLICE_B200_H_
+#define NBSLICE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NBS_ABI_VERSION 1
+
+/* status codes */
+#define NBS_OK                 0
+#define NBS_ERR_INVALID       -1   /* bad argument / inconsistent description            */
+#define NBS_ERR_UNSUPPORTED   -2   /* valid for the reference, not implemented on device */
+#define NBS_ERR_CUDA          -3   /* CUDA runtime failure, or no sm_100 device          */
+#define NBS_ERR_BOX           -4   /* periodic box smaller than twice the cutoff
+                                      (ReferenceNonbondedSlicingKernels.cpp:202-204)     */
+#define NBS_ERR_CAPACITY      -5   /* internal list overflow that could not be regrown   */
+
+/* nonbonded methods: values of CalcSlicedNonbondedForceKernel::NonbondedMethod
+ * (NonbondedSlicingKernels.h:29-36) */
+#define NBS_METHOD_NOCUTOFF            0
+#define NBS_METHOD_CUTOFF_NONPERIODIC  1
+#define NBS_METHOD_CUTOFF_PERIODIC     2
+#define NBS_METHOD_EWALD               3
+#define NBS_METHOD_PME                 4
+#define NBS_METHOD_LJPME               5
+
+/* nbs_system_desc.flags */
+#define NBS_FLAG_DETERMINISTIC   0x1u  /* fixed-point PME spreading (DeterministicForces)   */
+#define NBS_FLAG_PROFILE         0x2u  /* record CUDA events around every kernel            */
+#define NBS_FLAG_NO_GRAPH        0x4u  /* plain stream launches instead of a CUDA graph     */
+
+/* memory spaces / layouts for positions and forces */
+#define NBS_MEM_HOST    0
+#define NBS_MEM_DEVICE  1
+
+#define NBS_POS_F64_XYZ   0   /* double[N][3]  -- the Reference platform's vector<Vec3>          */
+#define NBS_POS_F32_XYZW  1   /* float[N][4]   -- OpenMM CUDA posq (w ignored), device only      */
+
+#define NBS_FORCE_F64_XYZ      0   /* double[N][3], added to (accumulate=1) or overwritten       */
+#define NBS_FORCE_I64_FIXED    1   /* long long[3][padded_atoms], value*2^32, always ADDED;
+                                      OpenMM CUDA's getLongForceBuffer layout (pme.cc:382-388)   */
+
+/*
+ * Everything the Reference platform's initialize() reads from the Force and System
+ * (ReferenceNonbondedSlicingKernels.cpp:59-185).  All arrays are host memory and are
+ * copied; the caller keeps ownership.
+ */
+typedef struct nbs_system_desc {
+    int32_t struct_size;                  /* = sizeof(nbs_system_desc)                         */
+    int32_t num_particles;
+    int32_t num_subsets;
+    int32_t method;                       /* NBS_METHOD_*                                       */
+    const int32_t* subsets;               /* [N] getParticleSubset                              */
+    const double*  charges;               /* [N] base charge                                    */
+    const double*  sigmas;                /* [N] base sigma                                     */
+    const double*  epsilons;              /* [N] base epsilon                                   */
+    int32_t num_exceptions;               /* ALL exceptions; each one is also an exclusion      */
+    int32_t num_global_params;            /* values supplied through nbs_set_global_parameters  */
+    const int32_t* exception_particles;   /* [nE][2]                                            */
+    const double*  exception_params;      /* [nE][3] chargeProd, sigma, epsilon (base)          */
+    int32_t num_particle_offsets;
+    int32_t num_exception_offsets;
+    const int32_t* particle_offset_indices;   /* [nPO][2] (global parameter index, particle)    */
+    const double*  particle_offset_scales;    /* [nPO][3] chargeScale, sigmaScale, epsilonScale */
+    const int32_t* exception_offset_indices;  /* [nEO][2] (global parameter index, exception)   */
+    const double*  exception_offset_scales;   /* [nEO][3]                                       */
+    double cutoff;
+    double switching_distance;
+    double rf_dielectric;
+    double ewald_alpha;                   /* from calcPMEParameters (explicit)       */
+    int32_t pme_grid[3];
+    int32_t use_switching_function;
+    int32_t exceptions_use_periodic;
+    int32_t device_index;
+    uint32_t flags;                       /* NBS_FLAG_*                                         */
+    int32_t reserved0;
+    const double* dispersion_coefficients;/* [nSl] from SlicedNonbondedForceImpl::
+                                             calcDispersionCorrections, or NULL for zeros       */
+} nbs_system_desc;
+
+/* One evaluation == one CalcSlicedNonbondedForceKernel::execute call. */
+typedef struct nbs_exec_args {
+    int32_t struct_size;                  /* = sizeof(nbs_exec_args)                           */
+    int32_t positions_format;             /* NBS_POS_*                                          */
+    int32_t positions_space;              /* NBS_MEM_*                                          */
+    int32_t forces_format;                /* NBS_FORCE_*                                        */
+    int32_t forces_space;                 /* NBS_MEM_*                                          */
+    int32_t forces_accumulate;            /* F64 only: 1 = add into the buffer (Reference
+                                             semantics, forces += ...), 0 = overwrite           */
+    const void* positions;
+    void* forces;                         /* may be NULL: energies only                         */
+    int64_t padded_num_atoms;             /* I64_FIXED: stride between the x, y and z planes    */
+    const int32_t* atom_index;            /* optional device int[N]: slot -> particle index of
+                                             the caller's (re-ordered) position/force buffers   */
+    double box[9];                        /* periodic box vectors a, b, c (rows)                */
+    int32_t include_forces;               /* ignored, like the Reference platform               */
+    int32_t include_energy;               /* only affects the adapter's return value            */
+    int32_t include_direct;
+    int32_t include_reciprocal;
+    double* slice_energies;               /* host double[nSl][2] (Coulomb, vdW), overwritten;
+                                             includes self, background and dispersion terms     */
+    void* stream;                         /* cudaStream_t the work is ordered on (0 = default)  */
+} nbs_exec_args;
+
+typedef struct nbs_context nbs_context;
+
+/* library-level */
+int         nbs_abi_version(void);
+const char* nbs_last_error(void);
+int         nbs_device_count(void);
+
+/* life cycle */
+int nbs_create(const nbs_system_desc* desc, nbs_context** out);
+int nbs_destroy(nbs_context* ctx);
+int nbs_update_parameters(nbs_context* ctx, const nbs_system_desc* desc);
+
+/* per-evaluation state */
+int nbs_set_lambdas(nbs_context* ctx, const double* lambdas /* [nSl][2] (Coulomb, vdW) */);
+int nbs_set_global_parameters(nbs_context* ctx, const double* values /* [num_global_params] */);
+int nbs_execute(nbs_context* ctx, const nbs_exec_args* args);
+
+/* queries */
+int nbs_get_pme_parameters(const nbs_context* ctx, double* alpha, int32_t* nx, int32_t* ny, int32_t* nz);
+int nbs_get_num_slices(const nbs_context* ctx, int32_t* num_slices);
+
+/*
+ * Parity diagnostics for the neighbour list of the LAST nbs_execute with include_direct:
+ * the set of interacting pairs (r^2 <= cutoff^2, not excluded), as particle indices with
+ * first < second.  `count` and the order-independent `hash` (sum over pairs of
+ * nbs_pair_hash(first, second), mod 2^64) are always written; `pairs` (host int32[capacity][2])
+ * receives the pairs themselves when non-NULL and large enough.
+ */
+int nbs_get_pair_set(nbs_context* ctx, int64_t capacity, int32_t* pairs, int64_t* count, uint64_t* hash);
+/* the exclusion set the device uses, as sorted unique (first < second) pairs */
+int nbs_get_exclusion_set(nbs_context* ctx, int64_t capacity, int32_t* pairs, int64_t* count);
+
+/*
+ * Per-kernel timing of the last nbs_execute (requires NBS_FLAG_PROFILE).  Writes up to
+ * `capacity` entries; names are static strings.  Returns the number of entries in *count.
+ */
+int nbs_get_kernel_times(nbs_context* ctx, int32_t capacity, const char** names, float* milliseconds, int32_t* count);
+/* number of kernels launched by this library on behalf of ctx since creation */
+int nbs_get_launch_count(const nbs_context* ctx, int64_t* launches);
+/* neighbour-list statistics of the last evaluation: [0] i-blocks, [1] j entries, [2] tiles,
+ * [3] candidate pair evaluations (tiles*1024), [4] exclusion-list entries */
+int nbs_get_nlist_stats(nbs_context* ctx, int64_t stats[8]);
+
+static inline uint64_t nbs_pair_hash(uint32_t first, uint32_t second) {
+    uint64_t x = ((uint64_t) first << 32) | second;       /* splitmix64 finaliser */
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NBSLICE_B200_H_ */

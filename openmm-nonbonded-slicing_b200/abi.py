@@ -1,0 +1,187 @@
+"""ctypes view of include/nbslice_b200.h (the C ABI of the CUDA library).
+
+The structures here must match the header field for field; ``struct_size`` is checked by the
+library on every call, so a drift fails loudly instead of corrupting memory.  There is no
+fallback: if ``csrc/libnbslice_b200.so`` is missing or cannot be loaded, importing the product
+path raises (the oracle under ``oracle/`` is test infrastructure and is never used from here).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+NBS_OK = 0
+NBS_ERR_INVALID = -1
+NBS_ERR_UNSUPPORTED = -2
+NBS_ERR_CUDA = -3
+NBS_ERR_BOX = -4
+NBS_ERR_CAPACITY = -5
+
+NBS_FLAG_DETERMINISTIC = 0x1
+NBS_FLAG_PROFILE = 0x2
+NBS_FLAG_NO_GRAPH = 0x4
+
+NBS_MEM_HOST = 0
+NBS_MEM_DEVICE = 1
+NBS_POS_F64_XYZ = 0
+NBS_POS_F32_XYZW = 1
+NBS_FORCE_F64_XYZ = 0
+NBS_FORCE_I64_FIXED = 1
+
+_i32p = C.POINTER(C.c_int32)
+_f64p = C.POINTER(C.c_double)
+
+
+class SystemDesc(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_int32),
+        ("num_particles", C.c_int32),
+        ("num_subsets", C.c_int32),
+        ("method", C.c_int32),
+        ("subsets", _i32p),
+        ("charges", _f64p),
+        ("sigmas", _f64p),
+        ("epsilons", _f64p),
+        ("num_exceptions", C.c_int32),
+        ("num_global_params", C.c_int32),
+        ("exception_particles", _i32p),
+        ("exception_params", _f64p),
+        ("num_particle_offsets", C.c_int32),
+        ("num_exception_offsets", C.c_int32),
+        ("particle_offset_indices", _i32p),
+        ("particle_offset_scales", _f64p),
+        ("exception_offset_indices", _i32p),
+        ("exception_offset_scales", _f64p),
+        ("cutoff", C.c_double),
+        ("switching_distance", C.c_double),
+        ("rf_dielectric", C.c_double),
+        ("ewald_alpha", C.c_double),
+        ("pme_grid", C.c_int32*3),
+        ("use_switching_function", C.c_int32),
+        ("exceptions_use_periodic", C.c_int32),
+        ("device_index", C.c_int32),
+        ("flags", C.c_uint32),
+        ("reserved0", C.c_int32),
+        ("dispersion_coefficients", _f64p),
+    ]
+
+
+class ExecArgs(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_int32),
+        ("positions_format", C.c_int32),
+        ("positions_space", C.c_int32),
+        ("forces_format", C.c_int32),
+        ("forces_space", C.c_int32),
+        ("forces_accumulate", C.c_int32),
+        ("positions", C.c_void_p),
+        ("forces", C.c_void_p),
+        ("padded_num_atoms", C.c_int64),
+        ("atom_index", C.c_void_p),
+        ("box", C.c_double*9),
+        ("include_forces", C.c_int32),
+        ("include_energy", C.c_int32),
+        ("include_direct", C.c_int32),
+        ("include_reciprocal", C.c_int32),
+        ("slice_energies", _f64p),
+        ("stream", C.c_void_p),
+    ]
+
+
+def _ptr(array, ctype):
+    if array is None or array.size == 0:
+        return C.cast(None, C.POINTER(ctype))
+    return array.ctypes.data_as(C.POINTER(ctype))
+
+
+class DescArrays:
+    """Owns the numpy arrays a SystemDesc points into (keeps them alive, C-contiguous, typed)."""
+
+    def __init__(self, **fields):
+        self.arrays = {}
+        self.desc = SystemDesc()
+        self.desc.struct_size = C.sizeof(SystemDesc)
+        for name, value in fields.items():
+            ftype = dict(SystemDesc._fields_)[name]
+            if ftype is _i32p:
+                arr = np.ascontiguousarray(value, dtype=np.int32)
+                self.arrays[name] = arr
+                setattr(self.desc, name, _ptr(arr, C.c_int32))
+            elif ftype is _f64p:
+                if value is None:
+                    setattr(self.desc, name, C.cast(None, _f64p))
+                else:
+                    arr = np.ascontiguousarray(value, dtype=np.float64)
+                    self.arrays[name] = arr
+                    setattr(self.desc, name, _ptr(arr, C.c_double))
+            elif name == "pme_grid":
+                self.desc.pme_grid[:] = [int(v) for v in value]
+            else:
+                setattr(self.desc, name, value)
+
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libnbslice_b200.so")
+_lib = None
+
+# every symbol include/nbslice_b200.h declares
+EXPORTS = [
+    "nbs_abi_version", "nbs_last_error", "nbs_device_count", "nbs_create", "nbs_destroy",
+    "nbs_update_parameters", "nbs_set_lambdas", "nbs_set_global_parameters", "nbs_execute",
+    "nbs_get_pme_parameters", "nbs_get_num_slices", "nbs_get_pair_set", "nbs_get_exclusion_set",
+    "nbs_get_kernel_times", "nbs_get_launch_count", "nbs_get_nlist_stats",
+]
+
+
+class NbsError(Exception):
+    def __init__(self, status, message):
+        super().__init__(message)
+        self.status = status
+
+
+def load_library():
+    """Load the CUDA library; raises if it has not been built (no CPU fallback exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `make -C {os.path.dirname(LIB_PATH)}` "
+            "(or __graft_entry__.build()); this package has no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    lib.nbs_abi_version.restype = C.c_int
+    lib.nbs_last_error.restype = C.c_char_p
+    lib.nbs_device_count.restype = C.c_int
+    lib.nbs_create.argtypes = [C.POINTER(SystemDesc), C.POINTER(C.c_void_p)]
+    lib.nbs_destroy.argtypes = [C.c_void_p]
+    lib.nbs_update_parameters.argtypes = [C.c_void_p, C.POINTER(SystemDesc)]
+    lib.nbs_set_lambdas.argtypes = [C.c_void_p, _f64p]
+    lib.nbs_set_global_parameters.argtypes = [C.c_void_p, _f64p]
+    lib.nbs_execute.argtypes = [C.c_void_p, C.POINTER(ExecArgs)]
+    lib.nbs_get_pme_parameters.argtypes = [C.c_void_p, _f64p, _i32p, _i32p, _i32p]
+    lib.nbs_get_num_slices.argtypes = [C.c_void_p, _i32p]
+    lib.nbs_get_pair_set.argtypes = [C.c_void_p, C.c_int64, _i32p, C.POINTER(C.c_int64), C.POINTER(C.c_uint64)]
+    lib.nbs_get_exclusion_set.argtypes = [C.c_void_p, C.c_int64, _i32p, C.POINTER(C.c_int64)]
+    lib.nbs_get_kernel_times.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_char_p), C.POINTER(C.c_float), _i32p]
+    lib.nbs_get_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+    lib.nbs_get_nlist_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+    for name in EXPORTS:
+        getattr(lib, name)
+    if lib.nbs_abi_version() != 1:
+        raise ImportError("libnbslice_b200.so has an unexpected ABI version")
+    _lib = lib
+    return lib
+
+
+def check(status):
+    if status != NBS_OK:
+        raise NbsError(status, load_library().nbs_last_error().decode())
+
+
+def pair_hash(first, second):
+    """nbs_pair_hash of include/nbslice_b200.h, vectorised (uint64 wrap-around arithmetic)."""
+    with np.errstate(over="ignore"):
+        x = (np.asarray(first, dtype=np.uint64) << np.uint64(32)) | np.asarray(second, dtype=np.uint64)
+        x = x + np.uint64(0x9E3779B97F4A7C15)
+        x = (x ^ (x >> np.uint64(30)))*np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27)))*np.uint64(0x94D049BB133111EB)
+        return x ^ (x >> np.uint64(31))

@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""bench.py -- force+energy evaluations per second of the SlicedNonbondedForce hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C3] [--impl reference]
+
+One "step" is one complete evaluation (neighbour list, direct space, exceptions, PME, all slice
+energies delivered to the host) of one synthetic system:
+  * N = 1 : C3, the DHFR-size system BASELINE.json's target is quoted on (override with --workload);
+  * N > 1 : C5, the STMV-size system, strong scaling -- direct-space i-blocks and PME subset grids are
+            split across ranks, forces/energies combined with an NCCL all-reduce.
+Prints ONE JSON line (contract in the task statement): `value` is device-resident throughput timed
+with CUDA events (L2 flushed between steps, outside the events), `e2e` the same metric through the
+host-buffer API (host->device copy of positions and device->host copy of forces + energies inside
+the timed region), `roofline` the FP32-pipe fraction of the pair kernel, `cpu_baseline` the
+reference's own Reference-platform arithmetic (oracle/_ref) on this box's host cores.
+
+`--impl reference` times that CPU implementation instead (rank 0 only).
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_PAIR = 72            # FP32-equivalent flops per interacting pair
+FS_PER_STEP = 2.0             # ns/day figure assumes one evaluation per 2 fs step
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--workload", default=None, help="C1..C5 (default: C3 at 1 GPU, C5 at N > 1)")
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--cpu-baseline-seconds", type=float, default=15.0)
+    return p.parse_args()
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.samples, self.stop, self.index = [], threading.Event(), index
+        self.thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop.wait(0.1)
+
+    def __enter__(self):
+        self.thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self.stop.set()
+        self.thread.join(timeout=10)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(s) > 3+k and s[3+k].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm)//2] if sm else None, "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def ns_per_day(evals_per_s, fs=FS_PER_STEP):
+    return evals_per_s*86400*fs*1e-6
+
+
+def load_workload(name):
+    systems = importlib.import_module("openmm-nonbonded-slicing_b200.systems")
+    return systems.make_system(name)
+
+
+def run_reference(args, workload_name):
+    """The reference's own CPU implementation of the path (oracle/_ref), all host threads it can use."""
+    from oracle import oracle
+    nbs = importlib.import_module("openmm-nonbonded-slicing_b200")
+    kind = "reference" if oracle.available("reference") else "port"
+    s = load_workload(workload_name)
+    desc = nbs.build_desc(s.system, s.force)
+    lam = np.ones((s.force.getNumSlices(), 2))
+    times = []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        res = oracle.evaluate(desc, s.positions, s.box, lam, kind=kind)
+        dt = time.perf_counter()-t0
+        if it >= args.warmup:
+            times.append(dt)
+    ms = 1e3*float(np.mean(times))
+    value = 1e3/ms
+    line = {
+        "impl": "reference", "metric": "force+energy evals/s", "value": value, "unit": "evals/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{workload_name}: {s.description}", "ns_per_day_2fs": ns_per_day(value)},
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": os.cpu_count(), "kind": kind,
+                         "sample": "full evaluation per step (neighbour list + direct + PME); single-threaded except pocketfft",
+                         "breakdown_s": {k: float(v) for k, v in res.timings.items()}},
+        "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def cpu_baseline(workload_name, s, desc, seconds):
+    from oracle import oracle
+    kind = "reference" if oracle.available("reference") else "port"
+    lam = np.ones((s.force.getNumSlices(), 2))
+    t_start, times, last = time.perf_counter(), [], None
+    while True:
+        t0 = time.perf_counter()
+        last = oracle.evaluate(desc, s.positions, s.box, lam, kind=kind)
+        times.append(time.perf_counter()-t0)
+        if time.perf_counter()-t_start > seconds or len(times) >= 20:
+            break
+    value = 1.0/float(np.mean(times))
+    return {"value": value, "unit": "evals/s", "cores": os.cpu_count(), "kind": kind,
+            "sample": f"{len(times)} full evaluation(s) of {workload_name} (neighbour list + direct + PME)",
+            "threads": "1 (pocketfft may use all cores)",
+            "breakdown_s": {k: float(v) for k, v in last.timings.items()}}, last
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    workload_name = args.workload or ("C3" if args.gpus == 1 else "C5")
+    if args.impl == "reference":
+        if rank == 0:
+            run_reference(args, workload_name)
+        return
+    import torch
+    nbs = importlib.import_module("openmm-nonbonded-slicing_b200")
+    abi = nbs.abi
+    if world > 1:
+        from importlib import import_module
+        multi = import_module("openmm-nonbonded-slicing_b200.multigpu")
+        return multi.bench_main(args, workload_name)
+
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda:0")
+    s = load_workload(workload_name)
+    n = s.force.getNumParticles()
+    nsl = s.force.getNumSlices()
+    lam = np.ones((nsl, 2))
+
+    # ---- device-resident throughput ------------------------------------------------------------
+    kernel = nbs.B200CalcSlicedNonbondedForceKernel(nbs.Platform())
+    kernel.initialize(s.system, s.force)
+    pos_dev = torch.tensor(s.positions, dtype=torch.float64, device=dev).contiguous()
+    frc_dev = torch.zeros((n, 3), dtype=torch.float64, device=dev)
+    flush = torch.empty(256*1024*1024, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step_device():
+        return kernel.execute_device(pos_dev.data_ptr(), s.box, frc_dev.data_ptr(), lam, stream=stream)
+
+    for _ in range(args.warmup):
+        step_device()
+    torch.cuda.synchronize()
+    launches_before = kernel.getLaunchCount()
+    per_step = []
+    with ClockSampler() as clocks:
+        t_wall0 = time.perf_counter()
+        for _ in range(args.steps):
+            flush.fill_(1)
+            start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            start.record()
+            energies = step_device()
+            end.record()
+            torch.cuda.synchronize()
+            per_step.append(start.elapsed_time(end))
+        t_wall = time.perf_counter()-t_wall0
+    launches = kernel.getLaunchCount()-launches_before
+    ms = float(np.mean(per_step))
+    value = 1e3/ms
+
+    # ---- end to end through the host-buffer API (what a plugin user calls) ---------------------
+    pos_host = torch.tensor(s.positions, dtype=torch.float64).pin_memory()
+    frc_host = torch.zeros((n, 3), dtype=torch.float64).pin_memory()
+    pos_np, frc_np = pos_host.numpy(), frc_host.numpy()
+    e2e_times = []
+    for it in range(args.warmup + args.steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        frc_np[:] = 0
+        e_host = kernel._evaluate(pos_np, s.box, lam, np.zeros(0), True, True, frc_np)
+        dt = time.perf_counter()-t0
+        if it >= args.warmup:
+            e2e_times.append(dt)
+    e2e_value = 1.0/float(np.mean(e2e_times))
+
+    # ---- per-kernel durations (CUDA events around every kernel, separate profiled context) ------
+    prof = nbs.B200CalcSlicedNonbondedForceKernel(nbs.Platform(flags=abi.NBS_FLAG_PROFILE))
+    prof.initialize(s.system, s.force)
+    acc = {}
+    reps = 10
+    for it in range(3 + reps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        prof.execute_device(pos_dev.data_ptr(), s.box, frc_dev.data_ptr(), lam, stream=stream)
+        if it >= 3:
+            for name, t in prof.getKernelTimes():
+                acc[name] = acc.get(name, 0.0) + t/reps
+    pair_count, _, _ = prof.getPairSet(with_pairs=False)
+    stats = prof.getNlistStats()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    fp32_peak = 148*128*2*float(peaks.get("sm_max_mhz", 1965.0))*1e6/1e12
+    pair_ms = acc.get("pair", float("nan"))
+    achieved = FLOP_PER_PAIR*pair_count/(pair_ms*1e-3)/1e12
+    grid = s.force.getPMEParameters()[1]
+    G = grid**3
+    pme_bytes = 32*s.force.getNumSubsets()*G + 52*n
+    pme_ms = sum(acc.get(k, 0.0) for k in ("spread", "fft_conv", "gather"))
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    roofline = {"bound": "fp32", "kernel": "k_pair", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+                "frac": achieved/fp32_peak, "traffic": None,
+                "peak_source": "148 SM x 128 lanes x 2 x sm_max_mhz of MEASURED_PEAKS.json (no measured FP32 figure in that file)",
+                "algorithmic": f"{FLOP_PER_PAIR} flop x {pair_count} interacting pairs", "kernel_ms": pair_ms,
+                "tile_efficiency": pair_count/max(stats[3], 1)}
+    roofline_pme = {"bound": "hbm", "kernels": "k_spread + 5 FFT/convolution kernels + k_gather", "achieved": pme_bytes/(pme_ms*1e-3)/1e9,
+                    "peak": hbm_peak, "unit": "GB/s", "frac": pme_bytes/(pme_ms*1e-3)/1e9/hbm_peak,
+                    "peak_source": "hbm_gbs of MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+                    "algorithmic": f"32*nS*G + 52*N = {pme_bytes} bytes", "kernel_ms": pme_ms, "traffic": None}
+
+    line = {
+        "metric": "force+energy evals/s", "value": value, "unit": "evals/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{workload_name}: {s.description}", "atoms": n, "subsets": s.force.getNumSubsets(),
+                   "pme_grid": grid, "cutoff_nm": 1.0, "ns_per_day_2fs": ns_per_day(value), "ns_per_day_4fs": ns_per_day(value, 4.0),
+                   "l2": "256 MiB buffer written between steps, outside the per-step CUDA events",
+                   "neighbour_list": "rebuilt from scratch every step", "interacting_pairs": pair_count,
+                   "wall_s_timed_loop": t_wall},
+        "clocks": clocks.summary(),
+        "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(pos_np.nbytes),
+                "d2h_bytes_per_step": int(frc_np.nbytes + 8*2*36 + 64), "ns_per_day_2fs": ns_per_day(e2e_value)},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "roofline_pme": roofline_pme,
+        "kernel_ms": {k: round(v, 5) for k, v in acc.items()},
+        "slice_energy_checksum": float(np.abs(energies).sum()),
+    }
+    if not args.no_cpu_baseline:
+        desc = kernel.desc
+        base, ref = cpu_baseline(workload_name, s, desc, args.cpu_baseline_seconds)
+        line["cpu_baseline"] = base
+        scale = np.maximum(np.abs(ref.slice_energies), 1.0)
+        frc_check = frc_dev.cpu().numpy()
+        line["parity_vs_cpu_baseline"] = {
+            "force_rel_rms": float(np.sqrt(((frc_check-ref.forces)**2).sum()/(ref.forces**2).sum())),
+            "max_energy_err_over_max_absE_1": float(np.max(np.abs(e_host-ref.slice_energies)/scale)),
+        }
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,194 @@
+// k_nlist.cu -- tile neighbour list with exclusion masks, rebuilt every evaluation.
+//
+// Replaces what the reference gets from OpenMM: computeNeighborListVoxelHash + the exclusion sets
+// on the Reference platform (ReferenceNonbondedSlicingKernels.cpp:101-106, 197) and
+// NonbondedUtilities' block list / exclusion tiles on CUDA (CommonNonbondedSlicingKernels.cpp:721).
+//
+// One CTA per i-block (<= 32 sorted atoms of one column).  Its warps walk the neighbouring columns;
+// for every column the interacting atoms are ONE contiguous range of the sorted arrays (z-bin range
+// of the column, per periodic image), read in coalesced 32-atom chunks.  A candidate j survives if
+// it is within cutoff of the i-block's bounding box.  Survivors are compacted with warp ballots into
+// shared memory, then copied out as one dense list per i-block:
+//   jlist : atoms that have no masked pair with this block             (fast tiles)
+//   xlist : atoms of the block itself (pairs i >= j masked) and atoms that share an exclusion with
+//           any atom of the block, each with the 32-bit mask of excluded i lanes
+// Half list: a pair is owned by the block of the atom with the LOWER sorted index, whatever the
+// periodic image, so columns before the block's own column are skipped outright.
+#include "nbs_internal.h"
+#include "nbs_device.cuh"
+
+namespace nbs {
+
+constexpr int JBUF = 1536;     // per-warp staging capacity (entries)
+constexpr int XBUF = 192;
+
+struct BuildArgs {
+    int N, maxBlocks, capJ, capX;
+    int ncx, ncy, nzb;
+    float colWx, colWy, binH;
+    float Lx, Ly, Lz;
+    float sx, sy, sz;          // nm per fixed-point unit
+    float reach;               // cutoff + margin
+    const int* counters;
+    const int* blkFirst; const int* blkCount; const uint4* blkLo; const uint4* blkHi;
+    const int* binStart;
+    const uint4* posq; const float4* par;
+    const int2* exclRange; const int* exclStart; const int* exclList; const int* origToSorted;
+    int* jlist; int* jcount; int* xlist; unsigned* xmask; int* xcount;
+    int* overflow;             // counters + 1
+};
+
+__global__ void __launch_bounds__(BUILD_WARPS*32) k_build_lists(BuildArgs a) {
+    const int b = blockIdx.x;
+    if (b >= a.counters[0]) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ int jbuf[BUILD_WARPS][JBUF];
+    __shared__ int xbuf[BUILD_WARPS][XBUF];
+    __shared__ unsigned xmbuf[BUILD_WARPS][XBUF];
+    __shared__ int counts[2][BUILD_WARPS];
+
+    const int first = a.blkFirst[b], count = a.blkCount[b];
+    const uint4 lo = a.blkLo[b], hi = a.blkHi[b];
+    const int colI = (int) lo.w;
+    const int cx = colI/a.ncy, cy = colI - cx*a.ncy;
+    // bounding box in nm (absolute coordinates; only used for the conservative column/range walk)
+    const float lox = lo.x*a.sx, loy = lo.y*a.sy, loz = lo.z*a.sz;
+    const float hix = hi.x*a.sx, hiy = hi.y*a.sy, hiz = hi.z*a.sz;
+    const float ex = (float) (hi.x - lo.x)*a.sx, ey = (float) (hi.y - lo.y)*a.sy, ez = (float) (hi.z - lo.z)*a.sz;
+    const float R = a.reach, R2 = R*R;
+    const int uxLo = (int) floorf((lox - R)/a.colWx), uxHi = (int) floorf((hix + R)/a.colWx);
+    const int uyLo = (int) floorf((loy - R)/a.colWy), uyHi = (int) floorf((hiy + R)/a.colWy);
+    const int nuy = uyHi - uyLo + 1;
+    const int nCand = (uxHi - uxLo + 1)*nuy;
+
+    int nj = 0, nx = 0;
+    bool overflow = false;
+    for (int cand = warp; cand < nCand; cand += BUILD_WARPS) {
+        const int ux = uxLo + cand/nuy, uy = uyLo + cand % nuy;
+        const int kx = (ux >= a.ncx) - (ux < 0), ky = (uy >= a.ncy) - (uy < 0);
+        const int wx = ux - kx*a.ncx, wy = uy - ky*a.ncy;
+        if (wx < 0 || wx >= a.ncx || wy < 0 || wy >= a.ncy) continue;      // more than one box away: cannot interact
+        const int colJ = wx*a.ncy + wy;
+        if (colJ < colI) continue;                                         // owned by the other block
+        const float gx = fmaxf(0.f, fmaxf(ux*a.colWx - hix, lox - (ux+1)*a.colWx));
+        const float gy = fmaxf(0.f, fmaxf(uy*a.colWy - hiy, loy - (uy+1)*a.colWy));
+        const float d2 = gx*gx + gy*gy;
+        if (d2 > R2) continue;
+        const float dz = sqrtf(R2 - d2) + 1e-4f;
+        const float zlo = loz - dz, zhi = hiz + dz;
+        for (int kz = -1; kz <= 1; kz++) {
+            const float segLo = fmaxf(zlo, kz*a.Lz) - kz*a.Lz, segHi = fminf(zhi, (kz+1)*a.Lz) - kz*a.Lz;
+            if (segHi < segLo) continue;
+            const int zb0 = max(0, min(a.nzb-1, (int) floorf(segLo/a.binH)));
+            const int zb1 = max(0, min(a.nzb-1, (int) floorf(segHi/a.binH)));
+            int s = a.binStart[colJ*a.nzb + zb0];
+            const int e = a.binStart[colJ*a.nzb + zb1 + 1];
+            if (colJ == colI) s = max(s, first);                           // j must not precede the block
+            const long long shx = (long long) kx << 32, shy = (long long) ky << 32, shz = (long long) kz << 32;
+            const int code = ((kx+1) + 3*(ky+1) + 9*(kz+1)) << J_SHIFT_BITS;
+            for (int j0 = s; j0 < e; j0 += 32) {
+                const int j = j0 + lane;
+                bool pass = false;
+                unsigned imask = 0;
+                if (j < e) {
+                    const uint4 q = a.posq[j];
+                    const float rx = (float) ((long long) q.x + shx - (long long) lo.x)*a.sx;
+                    const float ry = (float) ((long long) q.y + shy - (long long) lo.y)*a.sy;
+                    const float rz = (float) ((long long) q.z + shz - (long long) lo.z)*a.sz;
+                    const float ddx = fmaxf(0.f, fmaxf(-rx, rx - ex));
+                    const float ddy = fmaxf(0.f, fmaxf(-ry, ry - ey));
+                    const float ddz = fmaxf(0.f, fmaxf(-rz, rz - ez));
+                    pass = ddx*ddx + ddy*ddy + ddz*ddz <= R2;
+                    if (pass) {
+                        const int rel = j - first;
+                        if (rel >= 0 && rel < count) imask = 0xffffffffu << rel;      // own block: keep i < j only
+                        const int2 range = a.exclRange[j];
+                        if (range.y >= first && range.x < first + count) {
+                            const int p = __float_as_int(a.par[j].w);
+                            for (int k = a.exclStart[p]; k < a.exclStart[p+1]; k++) {
+                                const int d = a.origToSorted[a.exclList[k]] - first;
+                                if (d >= 0 && d < count) imask |= 1u << d;
+                            }
+                        }
+                    }
+                }
+                const unsigned mJ = __ballot_sync(FULL_MASK, pass && imask == 0);
+                const unsigned mX = __ballot_sync(FULL_MASK, pass && imask != 0);
+                const unsigned below = (1u << lane) - 1u;
+                if (pass) {
+                    if (imask == 0) {
+                        const int slot = nj + __popc(mJ & below);
+                        if (slot < JBUF) jbuf[warp][slot] = code | j;
+                    }
+                    else {
+                        const int slot = nx + __popc(mX & below);
+                        if (slot < XBUF) { xbuf[warp][slot] = code | j; xmbuf[warp][slot] = imask; }
+                    }
+                }
+                nj += __popc(mJ);
+                nx += __popc(mX);
+            }
+        }
+    }
+    if (nj > JBUF || nx > XBUF) { overflow = true; nj = min(nj, JBUF); nx = min(nx, XBUF); }
+    if (lane == 0) { counts[0][warp] = nj; counts[1][warp] = nx; }
+    __syncthreads();
+    int offJ = 0, offX = 0, totJ = 0, totX = 0;
+#pragma unroll
+    for (int w = 0; w < BUILD_WARPS; w++) {
+        if (w < warp) { offJ += counts[0][w]; offX += counts[1][w]; }
+        totJ += counts[0][w];
+        totX += counts[1][w];
+    }
+    if (totJ > a.capJ - 32 || totX > a.capX - 32) overflow = true;
+    totJ = min(totJ, a.capJ - 32);
+    totX = min(totX, a.capX - 32);
+    int* jl = a.jlist + (size_t) b*a.capJ;
+    int* xl = a.xlist + (size_t) b*a.capX;
+    unsigned* xm = a.xmask + (size_t) b*a.capX;
+    for (int k = lane; k < nj; k += 32) if (offJ + k < totJ) jl[offJ + k] = jbuf[warp][k];
+    for (int k = lane; k < nx; k += 32) if (offX + k < totX) { xl[offX + k] = xbuf[warp][k]; xm[offX + k] = xmbuf[warp][k]; }
+    // pad the last tile of each list with invalid entries
+    const int t = threadIdx.x;
+    if (t < 32) {
+        int padJ = ((totJ + 31) & ~31) - totJ;
+        if (t < padJ) jl[totJ + t] = -1;
+    }
+    else if (t < 64) {
+        int padX = ((totX + 31) & ~31) - totX;
+        if (t-32 < padX) { xl[totX + t-32] = -1; xm[totX + t-32] = 0xffffffffu; }
+    }
+    if (t == 0) {
+        a.jcount[b] = totJ;
+        a.xcount[b] = totX;
+    }
+    if (overflow && lane == 0) atomicOr(a.overflow, 1);
+}
+
+int launchExclRange(Context& c);
+
+int launchBuildLists(Context& c) {
+    const CellGeom& g = c.geom;
+    int status = launchExclRange(c);
+    if (status != NBS_OK) return status;
+    BuildArgs a;
+    a.N = c.N; a.maxBlocks = c.maxBlocks; a.capJ = c.capJ; a.capX = c.capX;
+    a.ncx = g.ncx; a.ncy = g.ncy; a.nzb = g.nzb;
+    a.colWx = g.colW[0]; a.colWy = g.colW[1]; a.binH = g.binH;
+    a.Lx = (float) g.box[0]; a.Ly = (float) g.box[1]; a.Lz = (float) g.box[2];
+    a.sx = g.scale[0]; a.sy = g.scale[1]; a.sz = g.scale[2];
+    a.reach = (float) c.cutoff + 2e-4f;
+    a.counters = c.dCounters.d;
+    a.blkFirst = c.dBlkFirst.d; a.blkCount = c.dBlkCount.d; a.blkLo = c.dBlkLo.d; a.blkHi = c.dBlkHi.d;
+    a.binStart = c.dBinStart.d;
+    a.posq = c.dPosq.d; a.par = c.dPar.d;
+    a.exclRange = c.dExclRange.d; a.exclStart = c.dExclStart.d; a.exclList = c.dExclList.d; a.origToSorted = c.dOrigToSorted.d;
+    a.jlist = c.dJList.d; a.jcount = c.dJCount.d; a.xlist = c.dXList.d; a.xmask = c.dXMask.d; a.xcount = c.dXCount.d;
+    a.overflow = c.dCounters.d + 1;
+    k_build_lists<<<c.maxBlocks, BUILD_WARPS*32, 0, c.stream>>>(a);
+    c.launches++;
+    timerMark(c, "build_lists");
+    return NBS_OK;
+}
+
+} // namespace nbs

@@ -1,0 +1,291 @@
+// k_sort.cu -- positions -> fixed-point fractional coordinates -> cell sort -> i-blocks.
+//
+// This stage has no counterpart in the reference's source: the plugin's platforms take their
+// neighbour list from OpenMM ([external] computeNeighborListVoxelHash on the Reference platform,
+// ReferenceNonbondedSlicingKernels.cpp:197; NonbondedUtilities on CUDA, CommonNonbondedSlicingKernels.cpp:721).
+// It is rebuilt from scratch on every evaluation, like the Reference platform does.
+//
+// All kernels here are HBM/latency bound integer work: one coalesced pass over the atoms each.
+#include "nbs_internal.h"
+#include "nbs_device.cuh"
+
+namespace nbs {
+
+// ---------------------------------------------------------------------------------------------
+// k_prep: one thread per input slot.  Wraps the position into the box, converts to 32-bit
+// fixed-point fractional coordinates and counts the atom into its (column, z-bin).
+// ---------------------------------------------------------------------------------------------
+__global__ void k_prep(int N, const double* __restrict__ pos64, const float4* __restrict__ pos32,
+                       const int* __restrict__ atomIndex, double3 invBox, int ncx, int ncy, int nzb,
+                       uint4* __restrict__ fix, int* __restrict__ binCount) {
+    int slot = blockIdx.x*blockDim.x + threadIdx.x;
+    if (slot >= N) return;
+    double x, y, z;
+    if (pos64) { x = pos64[3*slot]; y = pos64[3*slot+1]; z = pos64[3*slot+2]; }
+    else { float4 p = pos32[slot]; x = p.x; y = p.y; z = p.z; }
+    int particle = atomIndex ? atomIndex[slot] : slot;
+    double fx = x*invBox.x, fy = y*invBox.y, fz = z*invBox.z;
+    fx -= floor(fx); fy -= floor(fy); fz -= floor(fz);
+    unsigned ux = (unsigned) (__double2ull_rd(fx*4294967296.0) & 0xffffffffull);
+    unsigned uy = (unsigned) (__double2ull_rd(fy*4294967296.0) & 0xffffffffull);
+    unsigned uz = (unsigned) (__double2ull_rd(fz*4294967296.0) & 0xffffffffull);
+    int bin = (__umulhi(ux, ncx)*ncy + __umulhi(uy, ncy))*nzb + __umulhi(uz, nzb);
+    fix[particle] = make_uint4(ux, uy, uz, (unsigned) bin);
+    atomicAdd(&binCount[bin], 1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Exclusive scan (int), out[n] = total.  Small inputs: one CTA walks the array with a carry.
+// Large inputs: three passes with 4096-element tiles.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int blockExclusiveScan(int v, int* warpSums, int& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warpSums[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int w = lane < nw ? warpSums[lane] : 0;
+        int winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        warpSums[lane] = winc - w;               // exclusive offsets of the warps
+        if (lane == 31) warpSums[32] = winc;     // block total
+    }
+    __syncthreads();
+    int result = warpSums[warp] + inc - v;
+    total = warpSums[32];
+    __syncthreads();
+    return result;
+}
+
+__global__ void __launch_bounds__(1024) k_scan_single(const int* __restrict__ in, int* __restrict__ out, int n) {
+    __shared__ int warpSums[33];
+    int carry = 0;
+    for (int base = 0; base < n; base += 1024) {
+        int i = base + threadIdx.x;
+        int v = i < n ? in[i] : 0;
+        int total;
+        int ex = blockExclusiveScan(v, warpSums, total);
+        if (i < n) out[i] = carry + ex;
+        carry += total;
+    }
+    if (threadIdx.x == 0) out[n] = carry;
+}
+
+__global__ void __launch_bounds__(1024) k_scan_tiles(const int* __restrict__ in, int* __restrict__ out, int n, int* __restrict__ tileSums) {
+    __shared__ int warpSums[33];
+    int base = blockIdx.x*4096 + threadIdx.x*4;
+    int v[4], s = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { v[k] = base+k < n ? in[base+k] : 0; s += v[k]; }
+    int total;
+    int ex = blockExclusiveScan(s, warpSums, total);
+#pragma unroll
+    for (int k = 0; k < 4; k++) { if (base+k < n) out[base+k] = ex; ex += v[k]; }
+    if (threadIdx.x == 0) tileSums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) k_scan_add(int* __restrict__ out, int n, const int* __restrict__ tileOffsets) {
+    int base = blockIdx.x*4096 + threadIdx.x*4;
+    int off = tileOffsets[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < 4; k++) if (base+k < n) out[base+k] += off;
+    if (blockIdx.x == gridDim.x-1 && threadIdx.x == 0) out[n] = tileOffsets[gridDim.x];
+}
+
+static int scanExclusive(Context& c, const int* in, int* out, int n) {
+    if (n <= 32768) {
+        k_scan_single<<<1, 1024, 0, c.stream>>>(in, out, n);
+        c.launches++;
+        return NBS_OK;
+    }
+    int tiles = (n + 4095)/4096;
+    NBS_CUDA_CHECK(c.dScanTmp.ensure(2*(size_t) tiles + 2));
+    int* sums = c.dScanTmp.d;
+    int* offsets = c.dScanTmp.d + tiles + 1;
+    k_scan_tiles<<<tiles, 1024, 0, c.stream>>>(in, out, n, sums);
+    k_scan_single<<<1, 1024, 0, c.stream>>>(sums, offsets, tiles);
+    k_scan_add<<<tiles, 1024, 0, c.stream>>>(out, n, offsets);
+    c.launches += 3;
+    return NBS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_scatter: slot of every particle inside its bin (order inside a bin is fixed up next).
+// ---------------------------------------------------------------------------------------------
+__global__ void k_scatter(int N, const uint4* __restrict__ fix, const int* __restrict__ binStart,
+                          int* __restrict__ binCursor, int* __restrict__ sortedToOrig) {
+    int p = blockIdx.x*blockDim.x + threadIdx.x;
+    if (p >= N) return;
+    int bin = (int) fix[p].w;
+    int slot = binStart[bin] + atomicAdd(&binCursor[bin], 1);
+    sortedToOrig[slot] = p;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_bin_finalize: one thread per bin.  Orders the bin's particles by particle index (so that the
+// sorted order, and with it every floating-point sum downstream, is reproducible) and gathers the
+// sorted per-atom records.
+// ---------------------------------------------------------------------------------------------
+__device__ void heapSort(int* a, int n) {
+    for (int start = n/2-1; start >= 0; start--) {
+        int root = start;
+        for (;;) {
+            int child = 2*root+1;
+            if (child >= n) break;
+            if (child+1 < n && a[child] < a[child+1]) child++;
+            if (a[root] >= a[child]) break;
+            int t = a[root]; a[root] = a[child]; a[child] = t;
+            root = child;
+        }
+    }
+    for (int end = n-1; end > 0; end--) {
+        int t = a[0]; a[0] = a[end]; a[end] = t;
+        int root = 0;
+        for (;;) {
+            int child = 2*root+1;
+            if (child >= end) break;
+            if (child+1 < end && a[child] < a[child+1]) child++;
+            if (a[root] >= a[child]) break;
+            int u = a[root]; a[root] = a[child]; a[child] = u;
+            root = child;
+        }
+    }
+}
+
+__global__ void k_bin_finalize(int nBins, const int* __restrict__ binStart, int* __restrict__ sortedToOrig,
+                               int* __restrict__ origToSorted, const uint4* __restrict__ fix,
+                               const float* __restrict__ chargeF, const float2* __restrict__ sigEps,
+                               const int* __restrict__ subset, uint4* __restrict__ posq, float4* __restrict__ par) {
+    int bin = blockIdx.x*blockDim.x + threadIdx.x;
+    if (bin >= nBins) return;
+    int s = binStart[bin], e = binStart[bin+1];
+    int n = e - s;
+    if (n > 1) {
+        if (n <= 24) {
+            for (int i = s+1; i < e; i++) {
+                int v = sortedToOrig[i], j = i-1;
+                while (j >= s && sortedToOrig[j] > v) { sortedToOrig[j+1] = sortedToOrig[j]; j--; }
+                sortedToOrig[j+1] = v;
+            }
+        }
+        else
+            heapSort(sortedToOrig + s, n);
+    }
+    for (int slot = s; slot < e; slot++) {
+        int p = sortedToOrig[slot];
+        uint4 f = fix[p];
+        float2 se = sigEps[p];
+        posq[slot] = make_uint4(f.x, f.y, f.z, __float_as_uint(chargeF[p]));
+        par[slot] = make_float4(se.x, se.y, __int_as_float(subset[p]), __int_as_float(p));
+        origToSorted[p] = slot;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// i-blocks: <= 32 consecutive sorted atoms of one column.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_col_blocks(int nCols, int nzb, const int* __restrict__ binStart, int* __restrict__ colBlocks) {
+    int col = blockIdx.x*blockDim.x + threadIdx.x;
+    if (col >= nCols) return;
+    int cnt = binStart[(col+1)*nzb] - binStart[col*nzb];
+    colBlocks[col] = (cnt + 31) >> 5;
+}
+
+__global__ void k_blocks(int nCols, int nzb, int maxBlocks, const int* __restrict__ binStart,
+                         const int* __restrict__ colBlockStart, const uint4* __restrict__ posq,
+                         int* __restrict__ blkFirst, int* __restrict__ blkCount, uint4* __restrict__ blkLo,
+                         uint4* __restrict__ blkHi, int* __restrict__ counters) {
+    const int lane = threadIdx.x & 31;
+    int b = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
+    const int nBlocks = colBlockStart[nCols];
+    if (b == 0 && lane == 0) counters[0] = nBlocks;
+    if (b >= nBlocks || b >= maxBlocks) return;
+    int lo = 0, hi = nCols;                       // last column with colBlockStart[col] <= b
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (colBlockStart[mid] <= b) lo = mid; else hi = mid;
+    }
+    int col = lo;
+    int colBegin = binStart[col*nzb], colEnd = binStart[(col+1)*nzb];
+    int first = colBegin + 32*(b - colBlockStart[col]);
+    int count = min(32, colEnd - first);
+    uint4 p = posq[first + min(lane, count-1)];
+    unsigned xl = p.x, xh = p.x, yl = p.y, yh = p.y, zl = p.z, zh = p.z;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        xl = min(xl, __shfl_xor_sync(0xffffffffu, xl, o)); xh = max(xh, __shfl_xor_sync(0xffffffffu, xh, o));
+        yl = min(yl, __shfl_xor_sync(0xffffffffu, yl, o)); yh = max(yh, __shfl_xor_sync(0xffffffffu, yh, o));
+        zl = min(zl, __shfl_xor_sync(0xffffffffu, zl, o)); zh = max(zh, __shfl_xor_sync(0xffffffffu, zh, o));
+    }
+    if (lane == 0) {
+        blkFirst[b] = first;
+        blkCount[b] = count;
+        blkLo[b] = make_uint4(xl, yl, zl, (unsigned) col);
+        blkHi[b] = make_uint4(xh, yh, zh, 0u);
+    }
+}
+
+// For every sorted atom: the range of sorted indices its exclusion partners fall in (lets the list
+// builder skip the per-atom exclusion walk for almost every (i-block, j) candidate).
+__global__ void k_excl_range(int N, const float4* __restrict__ par, const int* __restrict__ exclStart,
+                             const int* __restrict__ exclList, const int* __restrict__ origToSorted,
+                             int2* __restrict__ exclRange) {
+    int j = blockIdx.x*blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    int p = __float_as_int(par[j].w);
+    int lo = 0x7fffffff, hi = -1;
+    for (int k = exclStart[p]; k < exclStart[p+1]; k++) {
+        int s = origToSorted[exclList[k]];
+        lo = min(lo, s);
+        hi = max(hi, s);
+    }
+    exclRange[j] = make_int2(lo, hi);
+}
+
+int launchSort(Context& c, const PosInput& in) {
+    const CellGeom& g = c.geom;
+    const int N = c.N;
+    cudaStream_t st = c.stream;
+    NBS_CUDA_CHECK(cudaMemsetAsync(c.dBinCount.d, 0, sizeof(int)*(g.nBins+1), st));
+    NBS_CUDA_CHECK(cudaMemsetAsync(c.dBinCursor.d, 0, sizeof(int)*(g.nBins+1), st));
+    const int T = 256;
+    k_prep<<<(N+T-1)/T, T, 0, st>>>(N, in.format == NBS_POS_F64_XYZ ? (const double*) in.ptr : nullptr,
+                                    in.format == NBS_POS_F32_XYZW ? (const float4*) in.ptr : nullptr, in.atomIndex,
+                                    make_double3(g.invBox[0], g.invBox[1], g.invBox[2]), g.ncx, g.ncy, g.nzb,
+                                    c.dFix.d, c.dBinCount.d);
+    c.launches++;
+    timerMark(c, "prep");
+    int status = scanExclusive(c, c.dBinCount.d, c.dBinStart.d, g.nBins);
+    if (status != NBS_OK) return status;
+    k_scatter<<<(N+T-1)/T, T, 0, st>>>(N, c.dFix.d, c.dBinStart.d, c.dBinCursor.d, c.dSortedToOrig.d);
+    k_bin_finalize<<<(g.nBins+T-1)/T, T, 0, st>>>(g.nBins, c.dBinStart.d, c.dSortedToOrig.d, c.dOrigToSorted.d, c.dFix.d,
+                                                  c.dChargeF.d, c.dSigEps.d, c.dSubset.d, c.dPosq.d, c.dPar.d);
+    // dBinCount is reused for the per-column block counts
+    k_col_blocks<<<(g.nCols+T-1)/T, T, 0, st>>>(g.nCols, g.nzb, c.dBinStart.d, c.dBinCount.d);
+    c.launches += 3;
+    status = scanExclusive(c, c.dBinCount.d, c.dColBlockStart.d, g.nCols);
+    if (status != NBS_OK) return status;
+    k_blocks<<<(c.maxBlocks*32+T-1)/T, T, 0, st>>>(g.nCols, g.nzb, c.maxBlocks, c.dBinStart.d, c.dColBlockStart.d, c.dPosq.d,
+                                                  c.dBlkFirst.d, c.dBlkCount.d, c.dBlkLo.d, c.dBlkHi.d, c.dCounters.d);
+    c.launches++;
+    timerMark(c, "sort");
+    return NBS_OK;
+}
+
+int launchExclRange(Context& c) {
+    const int T = 256;
+    k_excl_range<<<(c.N+T-1)/T, T, 0, c.stream>>>(c.N, c.dPar.d, c.dExclStart.d, c.dExclList.d, c.dOrigToSorted.d, c.dExclRange.d);
+    c.launches++;
+    return NBS_OK;
+}
+
+} // namespace nbs

@@ -1,0 +1,656 @@
+// nbs_api.cu -- the C ABI (include/nbslice_b200.h) and the host-side sequencing of one evaluation.
+//
+// Host logic mirrors what the reference's Reference-platform kernel does around its arithmetic:
+//   nbs_create / nbs_update_parameters  <- ReferenceCalcSlicedNonbondedForceKernel::initialize /
+//        copyParametersToContext (ReferenceNonbondedSlicingKernels.cpp:59-185, 270-319)
+//   applyParameters()                   <- computeParameters (:339-392): offsets, (sigma/2, 2 sqrt(eps), q),
+//        exception (sigma, 4 eps, qq), "1-4" selection (:107)
+//   nbs_execute                         <- execute (:187-268) minus the lambda-weighted sum, which is the
+//        adapter's job (it owns the scaling-parameter names)
+// There is no CPU fallback anywhere in this file: every path ends in CUDA kernels or an error code.
+#include "nbs_internal.h"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <set>
+
+namespace nbs {
+
+static thread_local std::string gLastError;
+void setError(const std::string& message) { gLastError = message; }
+
+void timerMark(Context& c, const char* name) {
+    if (!c.profiling) return;
+    cudaEvent_t ev;
+    cudaEventCreate(&ev);
+    cudaEventRecord(ev, c.stream);
+    c.timer.names.push_back(name);
+    c.timer.events.push_back(ev);
+}
+
+static void timerReset(Context& c) {
+    for (cudaEvent_t ev : c.timer.events) cudaEventDestroy(ev);
+    c.timer.events.clear();
+    c.timer.names.clear();
+}
+
+static int fail(int status, const std::string& message) {
+    setError(message);
+    return status;
+}
+
+// ---- description -> host arrays ---------------------------------------------------------------
+static int readDescription(Context& c, const nbs_system_desc& d, bool creating) {
+    if (d.struct_size != (int32_t) sizeof(nbs_system_desc)) return fail(NBS_ERR_INVALID, "nbs_system_desc.struct_size mismatch");
+    if (d.num_particles <= 0) return fail(NBS_ERR_INVALID, "num_particles must be positive");
+    if (d.num_subsets < 1 || d.num_subsets > MAX_SUBSETS)
+        return fail(NBS_ERR_UNSUPPORTED, "num_subsets must be between 1 and 8");
+    if (!creating) {
+        // ReferenceNonbondedSlicingKernels.cpp:271-272
+        if (d.num_particles != c.N) return fail(NBS_ERR_INVALID, "updateParametersInContext: The number of particles has changed");
+    }
+    if (d.num_particles > J_INDEX_MASK) return fail(NBS_ERR_UNSUPPORTED, "too many particles");
+    const int N = d.num_particles;
+    std::vector<int> subsets(d.subsets, d.subsets + N);
+    for (int s : subsets)
+        if (s < 0 || s >= d.num_subsets) return fail(NBS_ERR_INVALID, "particle subset out of range");
+    for (int i = 0; i < d.num_exceptions; i++)
+        for (int k = 0; k < 2; k++) {
+            int p = d.exception_particles[2*i+k];
+            if (p < 0 || p >= N) return fail(NBS_ERR_INVALID, "SlicedNonbondedForce: Illegal particle index for an exception: " + std::to_string(p));
+        }
+    for (int i = 0; i < d.num_particle_offsets; i++) {
+        if (d.particle_offset_indices[2*i] < 0 || d.particle_offset_indices[2*i] >= d.num_global_params ||
+            d.particle_offset_indices[2*i+1] < 0 || d.particle_offset_indices[2*i+1] >= N)
+            return fail(NBS_ERR_INVALID, "SlicedNonbondedForce: Illegal index for a particle parameter offset");
+    }
+    for (int i = 0; i < d.num_exception_offsets; i++) {
+        if (d.exception_offset_indices[2*i] < 0 || d.exception_offset_indices[2*i] >= d.num_global_params ||
+            d.exception_offset_indices[2*i+1] < 0 || d.exception_offset_indices[2*i+1] >= d.num_exceptions)
+            return fail(NBS_ERR_INVALID, "SlicedNonbondedForce: Illegal index for an exception parameter offset");
+    }
+    // count the "1-4" exceptions (:88-111) -- base values or an attached offset
+    std::set<int> withOffsets;
+    for (int i = 0; i < d.num_exception_offsets; i++) withOffsets.insert(d.exception_offset_indices[2*i+1]);
+    int num14 = 0;
+    for (int i = 0; i < d.num_exceptions; i++)
+        if (d.exception_params[3*i] != 0.0 || d.exception_params[3*i+2] != 0.0 || withOffsets.count(i)) num14++;
+    if (!creating && num14 != c.num14)
+        return fail(NBS_ERR_INVALID, "updateParametersInContext: The number of non-excluded exceptions has changed");
+
+    c.N = N;
+    c.nS = d.num_subsets;
+    c.nSl = c.nS*(c.nS+1)/2;
+    c.num14 = num14;
+    c.subsets = subsets;
+    c.baseQ.assign(d.charges, d.charges + N);
+    c.baseSig.assign(d.sigmas, d.sigmas + N);
+    c.baseEps.assign(d.epsilons, d.epsilons + N);
+    c.nExc = d.num_exceptions;
+    c.excPairs.assign(d.exception_particles, d.exception_particles + 2*(size_t) c.nExc);
+    c.excParams.assign(d.exception_params, d.exception_params + 3*(size_t) c.nExc);
+    c.pOffIdx.assign(d.particle_offset_indices, d.particle_offset_indices + 2*(size_t) d.num_particle_offsets);
+    c.pOffScale.assign(d.particle_offset_scales, d.particle_offset_scales + 3*(size_t) d.num_particle_offsets);
+    c.eOffIdx.assign(d.exception_offset_indices, d.exception_offset_indices + 2*(size_t) d.num_exception_offsets);
+    c.eOffScale.assign(d.exception_offset_scales, d.exception_offset_scales + 3*(size_t) d.num_exception_offsets);
+    if (creating) {
+        c.nGlobals = d.num_global_params;
+        c.globals.assign(c.nGlobals, 0.0);
+        c.lambdas.assign(2*(size_t) c.nSl, 1.0);
+        c.method = d.method;
+        c.cutoff = d.cutoff;
+        c.alpha = d.ewald_alpha;
+        c.switchDist = d.switching_distance;
+        c.rfDielectric = d.rf_dielectric;
+        c.useSwitch = d.method != NBS_METHOD_NOCUTOFF && d.use_switching_function != 0;
+        c.excPeriodic = (d.method == NBS_METHOD_NOCUTOFF || d.method == NBS_METHOD_CUTOFF_NONPERIODIC) ? false : d.exceptions_use_periodic != 0;
+        for (int k = 0; k < 3; k++) c.grid[k] = d.pme_grid[k];
+        c.flags = d.flags;
+        c.device = d.device_index;
+    }
+    c.dispersion.assign(c.nSl, 0.0);
+    if (d.dispersion_coefficients)
+        for (int s = 0; s < c.nSl; s++) c.dispersion[s] = d.dispersion_coefficients[s];
+    c.paramsDirty = true;
+    return NBS_OK;
+}
+
+// computeParameters (:339-392) + upload
+static int applyParameters(Context& c) {
+    const int N = c.N;
+    std::vector<double> q(c.baseQ), sig(c.baseSig), eps(c.baseEps);
+    for (size_t i = 0; i < c.pOffIdx.size()/2; i++) {
+        const double value = c.globals[c.pOffIdx[2*i]];
+        const int index = c.pOffIdx[2*i+1];
+        q[index] += value*c.pOffScale[3*i];
+        sig[index] += value*c.pOffScale[3*i+1];
+        eps[index] += value*c.pOffScale[3*i+2];
+    }
+    std::vector<float> chargeF(N);
+    std::vector<float2> sigEps(N);
+    const double sqrtK = std::sqrt(kOne4PiEps0);
+    c.subsetQ.assign(c.nS, 0.0);
+    c.subsetQ2.assign(c.nS, 0.0);
+    for (int i = 0; i < N; i++) {
+        chargeF[i] = (float) (q[i]*sqrtK);
+        sigEps[i] = make_float2((float) (0.5*sig[i]), (float) (2.0*std::sqrt(eps[i])));
+        c.subsetQ[c.subsets[i]] += q[i];
+        c.subsetQ2[c.subsets[i]] += q[i]*q[i];
+    }
+    std::vector<double> eq(c.nExc), es(c.nExc), ee(c.nExc);
+    std::vector<char> is14(c.nExc, 0);
+    for (int i = 0; i < c.nExc; i++) {
+        eq[i] = c.excParams[3*i]; es[i] = c.excParams[3*i+1]; ee[i] = c.excParams[3*i+2];
+        is14[i] = (eq[i] != 0.0 || ee[i] != 0.0) ? 1 : 0;
+    }
+    for (size_t i = 0; i < c.eOffIdx.size()/2; i++) {
+        const double value = c.globals[c.eOffIdx[2*i]];
+        const int index = c.eOffIdx[2*i+1];
+        is14[index] = 1;
+        eq[index] += value*c.eOffScale[3*i];
+        es[index] += value*c.eOffScale[3*i+1];
+        ee[index] += value*c.eOffScale[3*i+2];
+    }
+    std::vector<double4> excParam(c.nExc);
+    std::vector<int2> excPair(c.nExc);
+    std::vector<int> excSlice(c.nExc);
+    for (int i = 0; i < c.nExc; i++) {
+        excParam[i] = make_double4(es[i], 4.0*ee[i], kOne4PiEps0*eq[i], is14[i] ? 1.0 : 0.0);
+        excPair[i] = make_int2(c.excPairs[2*i], c.excPairs[2*i+1]);
+        const int s1 = c.subsets[excPair[i].x], s2 = c.subsets[excPair[i].y];
+        excSlice[i] = s1 > s2 ? s1*(s1+1)/2 + s2 : s2*(s2+1)/2 + s1;
+    }
+    // exclusion lists (every exception is an exclusion, :101-106), CSR over particles, partners sorted
+    std::vector<int> exclStart(N+1, 0);
+    for (int i = 0; i < c.nExc; i++) { exclStart[excPair[i].x+1]++; exclStart[excPair[i].y+1]++; }
+    for (int i = 0; i < N; i++) exclStart[i+1] += exclStart[i];
+    std::vector<int> exclList(std::max<size_t>(1, 2*(size_t) c.nExc)), cursor(exclStart.begin(), exclStart.end()-1);
+    for (int i = 0; i < c.nExc; i++) {
+        exclList[cursor[excPair[i].x]++] = excPair[i].y;
+        exclList[cursor[excPair[i].y]++] = excPair[i].x;
+    }
+    for (int i = 0; i < N; i++) std::sort(exclList.begin() + exclStart[i], exclList.begin() + exclStart[i+1]);
+
+    NBS_CUDA_CHECK(c.dSubset.ensure(N));
+    NBS_CUDA_CHECK(c.dChargeF.ensure(N));
+    NBS_CUDA_CHECK(c.dSigEps.ensure(N));
+    NBS_CUDA_CHECK(c.dCharge.ensure(N));
+    NBS_CUDA_CHECK(c.dExclStart.ensure(N+1));
+    NBS_CUDA_CHECK(c.dExclList.ensure(exclList.size()));
+    NBS_CUDA_CHECK(c.dExcPair.ensure(std::max(1, c.nExc)));
+    NBS_CUDA_CHECK(c.dExcParam.ensure(std::max(1, c.nExc)));
+    NBS_CUDA_CHECK(c.dExcSlice.ensure(std::max(1, c.nExc)));
+    NBS_CUDA_CHECK(cudaMemcpy(c.dSubset.d, c.subsets.data(), sizeof(int)*N, cudaMemcpyHostToDevice));
+    NBS_CUDA_CHECK(cudaMemcpy(c.dChargeF.d, chargeF.data(), sizeof(float)*N, cudaMemcpyHostToDevice));
+    NBS_CUDA_CHECK(cudaMemcpy(c.dSigEps.d, sigEps.data(), sizeof(float2)*N, cudaMemcpyHostToDevice));
+    NBS_CUDA_CHECK(cudaMemcpy(c.dCharge.d, q.data(), sizeof(double)*N, cudaMemcpyHostToDevice));
+    NBS_CUDA_CHECK(cudaMemcpy(c.dExclStart.d, exclStart.data(), sizeof(int)*(N+1), cudaMemcpyHostToDevice));
+    NBS_CUDA_CHECK(cudaMemcpy(c.dExclList.d, exclList.data(), sizeof(int)*exclList.size(), cudaMemcpyHostToDevice));
+    if (c.nExc > 0) {
+        NBS_CUDA_CHECK(cudaMemcpy(c.dExcPair.d, excPair.data(), sizeof(int2)*c.nExc, cudaMemcpyHostToDevice));
+        NBS_CUDA_CHECK(cudaMemcpy(c.dExcParam.d, excParam.data(), sizeof(double4)*c.nExc, cudaMemcpyHostToDevice));
+        NBS_CUDA_CHECK(cudaMemcpy(c.dExcSlice.d, excSlice.data(), sizeof(int)*c.nExc, cudaMemcpyHostToDevice));
+    }
+    c.paramsDirty = false;
+    return NBS_OK;
+}
+
+// B-spline moduli: pme_calculate_bsplines_moduli, ReferencePME.cpp:88-183 (order 5), and FFT twiddles.
+static void bsplineModuli(int ngrid, double* moduli) {
+    const int order = PME_ORDER;
+    double data[PME_ORDER];
+    data[order-1] = 0; data[1] = 0; data[0] = 1;
+    for (int k = 3; k < order; k++) {
+        double div = 1.0/(k-1.0);
+        data[k-1] = 0;
+        for (int l = 1; l < (k-1); l++) data[k-l-1] = div*(l*data[k-l-2] + (k-l)*data[k-l-1]);
+        data[0] = div*data[0];
+    }
+    double div = 1.0/(order-1);
+    data[order-1] = 0;
+    for (int l = 1; l < (order-1); l++) data[order-l-1] = div*(l*data[order-l-2] + (order-l)*data[order-l-1]);
+    data[0] = div*data[0];
+    std::vector<double> bsp(std::max(ngrid, order+1), 0.0);
+    for (int i = 1; i <= order; i++) bsp[i] = data[i-1];
+    for (int i = 0; i < ngrid; i++) {
+        double sc = 0, ss = 0;
+        for (int j = 0; j < ngrid; j++) {
+            double arg = (2.0*M_PI*i*j)/ngrid;
+            sc += bsp[j]*cos(arg);
+            ss += bsp[j]*sin(arg);
+        }
+        moduli[i] = sc*sc + ss*ss;
+    }
+    for (int i = 0; i < ngrid; i++)
+        if (moduli[i] < 1.0e-7) moduli[i] = (moduli[(i-1+ngrid)%ngrid] + moduli[(i+1)%ngrid])/2;
+}
+
+int uploadPmeTables(Context& c) {
+    const int nx = c.grid[0], ny = c.grid[1], nz = c.grid[2];
+    const int total = nx + ny + nz;
+    c.hModuli.assign(total, 0.0);
+    bsplineModuli(nx, c.hModuli.data());
+    bsplineModuli(ny, c.hModuli.data() + nx);
+    bsplineModuli(nz, c.hModuli.data() + nx + ny);
+    std::vector<float2> tw(total);
+    int off = 0;
+    for (int n : {nx, ny, nz}) {
+        for (int k = 0; k < n; k++) {
+            double ang = -2.0*kPi*k/n;
+            tw[off+k] = make_float2((float) cos(ang), (float) sin(ang));
+        }
+        off += n;
+    }
+    NBS_CUDA_CHECK(c.dModuli.ensure(total));
+    NBS_CUDA_CHECK(c.dTwiddle.ensure(total));
+    NBS_CUDA_CHECK(cudaMemcpy(c.dModuli.d, c.hModuli.data(), sizeof(double)*total, cudaMemcpyHostToDevice));
+    NBS_CUDA_CHECK(cudaMemcpy(c.dTwiddle.d, tw.data(), sizeof(float2)*total, cudaMemcpyHostToDevice));
+    const size_t G = (size_t) nx*ny*nz, Gh = (size_t) nx*ny*(nz/2+1);
+    NBS_CUDA_CHECK(c.dGrid.ensure(G*c.nS));
+    NBS_CUDA_CHECK(c.dGridC.ensure(Gh*c.nS));
+    return NBS_OK;
+}
+
+// cell geometry for this box: columns whose 32-atom blocks are roughly cubic, fine z-bins for sorting
+static int setupGeometry(Context& c, const double box[9]) {
+    CellGeom& g = c.geom;
+    const double L[3] = {box[0], box[4], box[8]};
+    const double volume = L[0]*L[1]*L[2];
+    const double density = c.N/volume;
+    double side = std::cbrt(32.0/density);
+    side = std::max(side, 0.3*c.cutoff);
+    for (int k = 0; k < 3; k++) {
+        g.box[k] = L[k];
+        g.invBox[k] = 1.0/L[k];
+        g.scale[k] = (float) (L[k]/4294967296.0);
+    }
+    g.ncx = std::max(1, std::min(512, (int) std::lround(L[0]/side)));
+    g.ncy = std::max(1, std::min(512, (int) std::lround(L[1]/side)));
+    g.nzb = std::max(1, std::min(8192, (int) std::ceil(L[2]/(side/8))));
+    while ((long long) g.ncx*g.ncy*g.nzb > 8000000LL && g.nzb > 1) g.nzb /= 2;
+    g.nCols = g.ncx*g.ncy;
+    g.nBins = g.nCols*g.nzb;
+    g.colW[0] = (float) (L[0]/g.ncx);
+    g.colW[1] = (float) (L[1]/g.ncy);
+    g.binH = (float) (L[2]/g.nzb);
+    const int N = c.N;
+    c.Npad = ((N + 31)/32)*32 + 32;
+    c.maxBlocks = N/32 + g.nCols + 1;
+    NBS_CUDA_CHECK(c.dFix.ensure(N));
+    NBS_CUDA_CHECK(c.dBinCount.ensure(g.nBins + 2));
+    NBS_CUDA_CHECK(c.dBinStart.ensure(g.nBins + 2));
+    NBS_CUDA_CHECK(c.dBinCursor.ensure(g.nBins + 2));
+    NBS_CUDA_CHECK(c.dSortedToOrig.ensure(N));
+    NBS_CUDA_CHECK(c.dOrigToSorted.ensure(N));
+    NBS_CUDA_CHECK(c.dPosq.ensure(c.Npad));
+    NBS_CUDA_CHECK(c.dPar.ensure(c.Npad));
+    NBS_CUDA_CHECK(c.dExclRange.ensure(c.Npad));
+    NBS_CUDA_CHECK(c.dColBlockStart.ensure(g.nCols + 2));
+    NBS_CUDA_CHECK(c.dBlkFirst.ensure(c.maxBlocks));
+    NBS_CUDA_CHECK(c.dBlkCount.ensure(c.maxBlocks));
+    NBS_CUDA_CHECK(c.dBlkLo.ensure(c.maxBlocks));
+    NBS_CUDA_CHECK(c.dBlkHi.ensure(c.maxBlocks));
+    NBS_CUDA_CHECK(c.dJCount.ensure(c.maxBlocks));
+    NBS_CUDA_CHECK(c.dXCount.ensure(c.maxBlocks));
+    NBS_CUDA_CHECK(c.dJList.ensure((size_t) c.maxBlocks*c.capJ));
+    NBS_CUDA_CHECK(c.dXList.ensure((size_t) c.maxBlocks*c.capX));
+    NBS_CUDA_CHECK(c.dXMask.ensure((size_t) c.maxBlocks*c.capX));
+    NBS_CUDA_CHECK(c.dForce.ensure(3*(size_t) c.Npad));
+    return NBS_OK;
+}
+
+static int checkDevice(int device) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(NBS_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    }
+    if (device < 0 || device >= count) return fail(NBS_ERR_CUDA, "device_index out of range");
+    cudaDeviceProp prop;
+    NBS_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(NBS_ERR_CUDA, std::string("device '") + prop.name + "' is not sm_100: this library is built for B200 only");
+    NBS_CUDA_CHECK(cudaSetDevice(device));
+    return NBS_OK;
+}
+
+static void releaseAll(Context& c) {
+    timerReset(c);
+    c.dSubset.release(); c.dChargeF.release(); c.dSigEps.release(); c.dCharge.release();
+    c.dExclStart.release(); c.dExclList.release(); c.dExcPair.release(); c.dExcParam.release(); c.dExcSlice.release();
+    c.dPosIn.release(); c.dForceOut.release(); c.dFix.release(); c.dBinCount.release(); c.dBinStart.release();
+    c.dBinCursor.release(); c.dScanTmp.release(); c.dSortedToOrig.release(); c.dOrigToSorted.release();
+    c.dPosq.release(); c.dPar.release(); c.dColBlockStart.release(); c.dBlkFirst.release(); c.dBlkCount.release();
+    c.dBlkLo.release(); c.dBlkHi.release(); c.dExclRange.release(); c.dJList.release(); c.dJCount.release();
+    c.dXList.release(); c.dXCount.release(); c.dXMask.release(); c.dCounters.release(); c.dForce.release();
+    c.dEnergy.release(); c.dGrid.release(); c.dGridC.release(); c.dEterm.release(); c.dModuli.release();
+    c.dTwiddle.release(); c.dPairStats.release(); c.dPairDump.release();
+    if (c.hCounters) cudaFreeHost(c.hCounters);
+    if (c.hEnergy) cudaFreeHost(c.hEnergy);
+    if (c.hForce) cudaFreeHost(c.hForce);
+    c.hCounters = nullptr; c.hEnergy = nullptr; c.hForce = nullptr;
+}
+
+} // namespace nbs
+
+using namespace nbs;
+
+struct nbs_context { Context c; };
+
+extern "C" {
+
+int nbs_abi_version(void) { return NBS_ABI_VERSION; }
+
+const char* nbs_last_error(void) { return gLastError.c_str(); }
+
+int nbs_device_count(void) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return count;
+}
+
+int nbs_create(const nbs_system_desc* desc, nbs_context** out) {
+    if (!desc || !out) return fail(NBS_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (desc->struct_size != (int32_t) sizeof(nbs_system_desc)) return fail(NBS_ERR_INVALID, "nbs_system_desc.struct_size mismatch");
+    switch (desc->method) {
+        case NBS_METHOD_PME: case NBS_METHOD_CUTOFF_PERIODIC: break;
+        case NBS_METHOD_NOCUTOFF: case NBS_METHOD_CUTOFF_NONPERIODIC:
+            return fail(NBS_ERR_UNSUPPORTED, "non-periodic nonbonded methods are not implemented on this platform yet");
+        case NBS_METHOD_EWALD: case NBS_METHOD_LJPME:
+            return fail(NBS_ERR_UNSUPPORTED, "Ewald and LJPME are not implemented on this platform (PME only)");
+        default: return fail(NBS_ERR_INVALID, "illegal nonbonded method");
+    }
+    if (desc->cutoff <= 0) return fail(NBS_ERR_INVALID, "cutoff must be positive");
+    int status = checkDevice(desc->device_index);
+    if (status != NBS_OK) return status;
+    nbs_context* ctx = new nbs_context();
+    Context& c = ctx->c;
+    status = readDescription(c, *desc, true);
+    if (status != NBS_OK) { delete ctx; return status; }
+    if (c.method == NBS_METHOD_PME) {
+        if (c.alpha <= 0 || c.grid[0] < PME_ORDER+1 || c.grid[1] < PME_ORDER+1 || c.grid[2] < PME_ORDER+1) {
+            delete ctx;
+            return fail(NBS_ERR_INVALID, "PME needs ewald_alpha > 0 and a grid of at least 6 points per dimension");
+        }
+    }
+    c.capJ = 2048;
+    c.capX = 256;
+    c.profiling = (c.flags & NBS_FLAG_PROFILE) != 0;
+    cudaError_t e = cudaSuccess;
+    if ((e = c.dCounters.ensure(16)) != cudaSuccess || (e = c.dEnergy.ensure(2*MAX_SLICES)) != cudaSuccess ||
+        (e = c.dPairStats.ensure(4)) != cudaSuccess || (e = c.dPairDump.ensure(1)) != cudaSuccess ||
+        (e = cudaMallocHost((void**) &c.hCounters, 16*sizeof(int))) != cudaSuccess ||
+        (e = cudaMallocHost((void**) &c.hEnergy, 2*MAX_SLICES*sizeof(double))) != cudaSuccess) {
+        releaseAll(c);
+        delete ctx;
+        return fail(NBS_ERR_CUDA, std::string("allocation failed: ") + cudaGetErrorString(e));
+    }
+    if (c.method == NBS_METHOD_PME) {
+        status = uploadPmeTables(c);
+        if (status != NBS_OK) { releaseAll(c); delete ctx; return status; }
+    }
+    *out = ctx;
+    return NBS_OK;
+}
+
+int nbs_destroy(nbs_context* ctx) {
+    if (!ctx) return NBS_OK;
+    cudaSetDevice(ctx->c.device);
+    releaseAll(ctx->c);
+    delete ctx;
+    return NBS_OK;
+}
+
+int nbs_update_parameters(nbs_context* ctx, const nbs_system_desc* desc) {
+    if (!ctx || !desc) return fail(NBS_ERR_INVALID, "null argument");
+    cudaSetDevice(ctx->c.device);
+    return readDescription(ctx->c, *desc, false);
+}
+
+int nbs_set_lambdas(nbs_context* ctx, const double* lambdas) {
+    if (!ctx || !lambdas) return fail(NBS_ERR_INVALID, "null argument");
+    ctx->c.lambdas.assign(lambdas, lambdas + 2*(size_t) ctx->c.nSl);
+    return NBS_OK;
+}
+
+int nbs_set_global_parameters(nbs_context* ctx, const double* values) {
+    if (!ctx) return fail(NBS_ERR_INVALID, "null argument");
+    Context& c = ctx->c;
+    if (c.nGlobals == 0) return NBS_OK;
+    if (!values) return fail(NBS_ERR_INVALID, "null argument");
+    bool changed = false;
+    for (int k = 0; k < c.nGlobals; k++)
+        if (c.globals[k] != values[k]) { c.globals[k] = values[k]; changed = true; }
+    // only parameters that feed an offset change the per-particle data (CommonNonbondedSlicingKernels.cpp:1152-1163)
+    if (changed && (!c.pOffIdx.empty() || !c.eOffIdx.empty())) c.paramsDirty = true;
+    return NBS_OK;
+}
+
+int nbs_execute(nbs_context* ctx, const nbs_exec_args* args) {
+    if (!ctx || !args) return fail(NBS_ERR_INVALID, "null argument");
+    if (args->struct_size != (int32_t) sizeof(nbs_exec_args)) return fail(NBS_ERR_INVALID, "nbs_exec_args.struct_size mismatch");
+    Context& c = ctx->c;
+    NBS_CUDA_CHECK(cudaSetDevice(c.device));
+    const double* box = args->box;
+    if (box[1] != 0 || box[2] != 0 || box[3] != 0 || box[5] != 0 || box[6] != 0 || box[7] != 0)
+        return fail(NBS_ERR_UNSUPPORTED, "triclinic boxes are not implemented on this platform yet");
+    // ReferenceNonbondedSlicingKernels.cpp:200-204
+    const double minAllowedSize = 1.999999*c.cutoff;
+    if (box[0] < minAllowedSize || box[4] < minAllowedSize || box[8] < minAllowedSize)
+        return fail(NBS_ERR_BOX, "The periodic box size has decreased to less than twice the nonbonded cutoff.");
+    if (!args->positions) return fail(NBS_ERR_INVALID, "positions is null");
+    if (args->positions_format == NBS_POS_F32_XYZW && args->positions_space != NBS_MEM_DEVICE)
+        return fail(NBS_ERR_INVALID, "float4 positions must be device memory");
+    if (args->forces_format == NBS_FORCE_I64_FIXED && (args->forces_space != NBS_MEM_DEVICE || args->padded_num_atoms < c.N))
+        return fail(NBS_ERR_INVALID, "fixed-point forces need device memory and padded_num_atoms >= num_particles");
+    if (args->atom_index && args->positions_format == NBS_POS_F64_XYZ && args->positions_space == NBS_MEM_HOST)
+        return fail(NBS_ERR_INVALID, "atom_index requires device-resident positions");
+    c.stream = (cudaStream_t) args->stream;
+    cudaStream_t st = c.stream;
+    const bool pme = c.method == NBS_METHOD_PME;
+    const bool wantEnergy = args->slice_energies != nullptr;
+    const bool direct = args->include_direct != 0;
+    const bool recip = args->include_reciprocal != 0 && pme;
+    const int N = c.N;
+    int status;
+    if (c.paramsDirty && (status = applyParameters(c)) != NBS_OK) return status;
+
+    for (int attempt = 0; attempt < 6; attempt++) {
+        if ((status = setupGeometry(c, box)) != NBS_OK) return status;
+        timerReset(c);
+        timerMark(c, "begin");
+        // positions
+        PosInput in;
+        in.format = args->positions_format;
+        in.atomIndex = args->atom_index;
+        const double* dPos64 = nullptr;
+        if (args->positions_space == NBS_MEM_HOST) {
+            NBS_CUDA_CHECK(c.dPosIn.ensure(3*(size_t) N));
+            NBS_CUDA_CHECK(cudaMemcpyAsync(c.dPosIn.d, args->positions, sizeof(double)*3*N, cudaMemcpyHostToDevice, st));
+            in.ptr = c.dPosIn.d;
+            dPos64 = c.dPosIn.d;
+        }
+        else {
+            in.ptr = args->positions;
+            if (args->positions_format == NBS_POS_F64_XYZ) dPos64 = (const double*) args->positions;
+        }
+        NBS_CUDA_CHECK(cudaMemsetAsync(c.dForce.d, 0, sizeof(unsigned long long)*3*c.Npad, st));
+        NBS_CUDA_CHECK(cudaMemsetAsync(c.dEnergy.d, 0, sizeof(double)*2*MAX_SLICES, st));
+        NBS_CUDA_CHECK(cudaMemsetAsync(c.dCounters.d, 0, sizeof(int)*16, st));
+        timerMark(c, "h2d_zero");
+        if ((status = launchSort(c, in)) != NBS_OK) return status;
+        if (direct) {
+            if ((status = launchBuildLists(c)) != NBS_OK) return status;
+            if ((status = launchPairs(c, wantEnergy, 0)) != NBS_OK) return status;
+            if (c.nExc > 0) {
+                if (!dPos64) return fail(NBS_ERR_UNSUPPORTED, "exceptions need double-precision positions in this version");
+                if ((status = launchBonded(c, dPos64, true)) != NBS_OK) return status;
+            }
+        }
+        if (recip && (status = launchPme(c, wantEnergy)) != NBS_OK) return status;
+        // forces out
+        if (args->forces) {
+            if (args->forces_space == NBS_MEM_DEVICE) {
+                if ((status = launchFinalize(c, args->forces, args->forces_format, args->padded_num_atoms,
+                                             args->forces_accumulate, args->atom_index)) != NBS_OK) return status;
+            }
+            else {
+                NBS_CUDA_CHECK(c.dForceOut.ensure(3*(size_t) N));
+                if ((status = launchFinalize(c, c.dForceOut.d, NBS_FORCE_F64_XYZ, 0, 0, nullptr)) != NBS_OK) return status;
+                if (args->forces_accumulate) {
+                    if (c.hForceCap < 3*(size_t) N) {
+                        if (c.hForce) cudaFreeHost(c.hForce);
+                        NBS_CUDA_CHECK(cudaMallocHost((void**) &c.hForce, sizeof(double)*3*N));
+                        c.hForceCap = 3*(size_t) N;
+                    }
+                    NBS_CUDA_CHECK(cudaMemcpyAsync(c.hForce, c.dForceOut.d, sizeof(double)*3*N, cudaMemcpyDeviceToHost, st));
+                }
+                else
+                    NBS_CUDA_CHECK(cudaMemcpyAsync(args->forces, c.dForceOut.d, sizeof(double)*3*N, cudaMemcpyDeviceToHost, st));
+            }
+        }
+        NBS_CUDA_CHECK(cudaMemcpyAsync(c.hEnergy, c.dEnergy.d, sizeof(double)*2*MAX_SLICES, cudaMemcpyDeviceToHost, st));
+        NBS_CUDA_CHECK(cudaMemcpyAsync(c.hCounters, c.dCounters.d, sizeof(int)*16, cudaMemcpyDeviceToHost, st));
+        timerMark(c, "d2h");
+        NBS_CUDA_CHECK(cudaStreamSynchronize(st));
+        NBS_CUDA_CHECK(cudaGetLastError());
+        if (c.hCounters[1] == 0) break;
+        // neighbour-list capacity overflow: grow and redo the evaluation
+        if (c.capJ >= 65536) return fail(NBS_ERR_CAPACITY, "neighbour list capacity exceeded (system too dense for the tile list)");
+        c.capJ *= 2;
+        c.capX *= 2;
+        if (attempt == 5) return fail(NBS_ERR_CAPACITY, "neighbour list capacity exceeded");
+    }
+    c.nBlocksLast = c.hCounters[0];
+    c.haveLast = true;
+    c.lastDirect = direct;
+    std::memcpy(c.lastBox, box, sizeof(double)*9);
+    if (args->forces && args->forces_space == NBS_MEM_HOST && args->forces_accumulate) {
+        double* out = (double*) args->forces;
+        for (size_t k = 0; k < 3*(size_t) N; k++) out[k] += c.hForce[k];
+    }
+    if (wantEnergy) {
+        double* E = args->slice_energies;
+        for (int k = 0; k < 2*c.nSl; k++) E[k] = c.hEnergy[k];
+        const double volume = box[0]*box[4]*box[8];
+        if (recip) {
+            // self energy and neutralising background, ReferenceSlicedLJCoulombIxn.cpp:203-222
+            const double selfFactor = kOne4PiEps0*c.alpha/std::sqrt(kPi);
+            const double factor = (-1/(4*c.alpha*c.alpha))/(2*kEpsilon0*volume);
+            for (int i = 0; i < c.nS; i++) {
+                E[2*(i*(i+3)/2)] -= selfFactor*c.subsetQ2[i];
+                for (int j = i; j < c.nS; j++)
+                    E[2*(j*(j+1)/2+i)] += (i == j ? 1 : 2)*c.subsetQ[i]*c.subsetQ[j]*factor;
+            }
+        }
+        if (direct)   // dispersion correction, ReferenceNonbondedSlicingKernels.cpp:244-249
+            for (int s = 0; s < c.nSl; s++) E[2*s+1] += c.dispersion[s]/volume;
+    }
+    return NBS_OK;
+}
+
+int nbs_get_pme_parameters(const nbs_context* ctx, double* alpha, int32_t* nx, int32_t* ny, int32_t* nz) {
+    if (!ctx) return fail(NBS_ERR_INVALID, "null argument");
+    if (ctx->c.method != NBS_METHOD_PME && ctx->c.method != NBS_METHOD_LJPME)
+        return fail(NBS_ERR_INVALID, "getPMEParametersInContext: This Context is not using PME or LJPME");
+    *alpha = ctx->c.alpha; *nx = ctx->c.grid[0]; *ny = ctx->c.grid[1]; *nz = ctx->c.grid[2];
+    return NBS_OK;
+}
+
+int nbs_get_num_slices(const nbs_context* ctx, int32_t* num_slices) {
+    if (!ctx || !num_slices) return fail(NBS_ERR_INVALID, "null argument");
+    *num_slices = ctx->c.nSl;
+    return NBS_OK;
+}
+
+int nbs_get_pair_set(nbs_context* ctx, int64_t capacity, int32_t* pairs, int64_t* count, uint64_t* hash) {
+    if (!ctx || !count || !hash) return fail(NBS_ERR_INVALID, "null argument");
+    Context& c = ctx->c;
+    if (!c.haveLast || !c.lastDirect) return fail(NBS_ERR_INVALID, "no direct-space evaluation to inspect");
+    NBS_CUDA_CHECK(cudaSetDevice(c.device));
+    c.stream = nullptr;
+    const bool dump = pairs != nullptr && capacity > 0;
+    if (dump) NBS_CUDA_CHECK(c.dPairDump.ensure((size_t) capacity));
+    NBS_CUDA_CHECK(cudaMemset(c.dPairStats.d, 0, sizeof(unsigned long long)*4));
+    const bool saved = c.profiling;
+    c.profiling = false;
+    int status = launchPairs(c, false, dump ? 2 : 1);
+    c.profiling = saved;
+    if (status != NBS_OK) return status;
+    unsigned long long stats[4];
+    NBS_CUDA_CHECK(cudaMemcpy(stats, c.dPairStats.d, sizeof(stats), cudaMemcpyDeviceToHost));
+    *count = (int64_t) stats[0];
+    *hash = stats[1];
+    if (dump) {
+        if ((int64_t) stats[0] > capacity) return fail(NBS_ERR_CAPACITY, "pair buffer too small");
+        NBS_CUDA_CHECK(cudaMemcpy(pairs, c.dPairDump.d, sizeof(int2)*stats[0], cudaMemcpyDeviceToHost));
+    }
+    return NBS_OK;
+}
+
+int nbs_get_exclusion_set(nbs_context* ctx, int64_t capacity, int32_t* pairs, int64_t* count) {
+    if (!ctx || !count) return fail(NBS_ERR_INVALID, "null argument");
+    Context& c = ctx->c;
+    NBS_CUDA_CHECK(cudaSetDevice(c.device));
+    int status;
+    if (c.paramsDirty && (status = applyParameters(c)) != NBS_OK) return status;
+    // read back what the device actually uses
+    std::vector<int> start(c.N+1), list(std::max<size_t>(1, 2*(size_t) c.nExc));
+    NBS_CUDA_CHECK(cudaMemcpy(start.data(), c.dExclStart.d, sizeof(int)*(c.N+1), cudaMemcpyDeviceToHost));
+    NBS_CUDA_CHECK(cudaMemcpy(list.data(), c.dExclList.d, sizeof(int)*list.size(), cudaMemcpyDeviceToHost));
+    int64_t n = 0;
+    for (int i = 0; i < c.N; i++)
+        for (int k = start[i]; k < start[i+1]; k++)
+            if (list[k] > i && (k == start[i] || list[k] != list[k-1])) {
+                if (pairs && n < capacity) { pairs[2*n] = i; pairs[2*n+1] = list[k]; }
+                n++;
+            }
+    *count = n;
+    return NBS_OK;
+}
+
+int nbs_get_kernel_times(nbs_context* ctx, int32_t capacity, const char** names, float* milliseconds, int32_t* count) {
+    if (!ctx || !count) return fail(NBS_ERR_INVALID, "null argument");
+    Context& c = ctx->c;
+    int n = 0;
+    for (size_t k = 1; k < c.timer.events.size(); k++) {
+        if (n >= capacity) break;
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, c.timer.events[k-1], c.timer.events[k]) != cudaSuccess) { cudaGetLastError(); ms = -1; }
+        names[n] = c.timer.names[k];
+        milliseconds[n] = ms;
+        n++;
+    }
+    *count = n;
+    return NBS_OK;
+}
+
+int nbs_get_launch_count(const nbs_context* ctx, int64_t* launches) {
+    if (!ctx || !launches) return fail(NBS_ERR_INVALID, "null argument");
+    *launches = ctx->c.launches;
+    return NBS_OK;
+}
+
+int nbs_get_nlist_stats(nbs_context* ctx, int64_t stats[8]) {
+    if (!ctx || !stats) return fail(NBS_ERR_INVALID, "null argument");
+    Context& c = ctx->c;
+    for (int k = 0; k < 8; k++) stats[k] = 0;
+    if (!c.haveLast || !c.lastDirect) return NBS_OK;
+    NBS_CUDA_CHECK(cudaSetDevice(c.device));
+    const int nb = c.nBlocksLast;
+    std::vector<int> jc(nb), xc(nb);
+    NBS_CUDA_CHECK(cudaMemcpy(jc.data(), c.dJCount.d, sizeof(int)*nb, cudaMemcpyDeviceToHost));
+    NBS_CUDA_CHECK(cudaMemcpy(xc.data(), c.dXCount.d, sizeof(int)*nb, cudaMemcpyDeviceToHost));
+    long long entries = 0, tiles = 0, xentries = 0;
+    for (int b = 0; b < nb; b++) {
+        entries += jc[b] + xc[b];
+        xentries += xc[b];
+        tiles += (jc[b]+31)/32 + (xc[b]+31)/32;
+    }
+    stats[0] = nb; stats[1] = entries; stats[2] = tiles; stats[3] = tiles*1024; stats[4] = xentries;
+    stats[5] = c.capJ; stats[6] = c.geom.nCols; stats[7] = c.geom.nBins;
+    return NBS_OK;
+}
+
+} // extern "C"

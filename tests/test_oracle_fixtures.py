@@ -1,0 +1,171 @@
+"""CPU tests: the restated oracle against (a) the committed golden fixtures that oracle/make_golden.py
+produced with the reference's own compiled TUs, (b) that compiled reference itself on random systems
+(when oracle/_ref exists), and (c) the slicing identities of tests/TestSlicedNonbondedForce.h:1031-1457."""
+import importlib
+import os
+
+import numpy as np
+import pytest
+
+from helpers import assert_equal_tol, force_rel_rms
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def systems():
+    return importlib.import_module("openmm-nonbonded-slicing_b200.systems")
+
+
+@pytest.mark.parametrize("name", ["C1", "C2"])
+def test_port_matches_reference_fixture(nbs, oracle, systems, name):
+    g = np.load(os.path.join(GOLDEN, f"{name}_reference.npz"))
+    s = systems.make_system(name)
+    # the generator is deterministic: same positions as when the fixture was made
+    assert np.allclose([s.positions.sum(), (s.positions**2).sum()], g["positions_checksum"], rtol=1e-13)
+    desc = nbs.build_desc(s.system, s.force)
+    for tag, (direct, recip) in {"full": (True, True), "direct": (True, False), "recip": (False, True)}.items():
+        r = oracle.evaluate(desc, s.positions, s.box, g["lambdas"], None, direct, recip, kind="port")
+        assert force_rel_rms(r.forces, g[f"{tag}_forces"]) < 1e-12
+        assert np.allclose(r.slice_energies, g[f"{tag}_energies"], rtol=1e-11, atol=1e-9)
+        if direct:
+            assert r.pair_count == int(g["pair_count"][0])
+            assert r.pair_hash == int(g["pair_hash"][0])
+
+
+def random_system(nbs, rng, n=300, nsub=3, L=2.6, grid=(20, 20, 20), with_offsets=True, net_charge=True):
+    system = nbs.System()
+    force = nbs.SlicedNonbondedForce(nsub)
+    force.setNonbondedMethod(force.PME)
+    force.setCutoffDistance(1.0)
+    force.setPMEParameters(2.8, *grid)
+    system.setDefaultPeriodicBoxVectors([L, 0, 0], [0, L, 0], [0, 0, L])
+    side = int(np.ceil(n**(1/3)))
+    sites = np.array([(i, j, k) for i in range(side) for j in range(side) for k in range(side)][:n], dtype=float)
+    positions = (sites+0.5)*L/side + rng.uniform(-0.05, 0.05, size=(n, 3))
+    positions += rng.integers(-2, 3, size=(n, 3))*L          # unwrapped coordinates must work too
+    charges = rng.uniform(-0.8, 0.8, size=n)
+    if not net_charge:
+        charges -= charges.mean()
+    for i in range(n):
+        system.addParticle(1.0)
+        force.addParticle(charges[i], rng.uniform(0.15, 0.3), rng.uniform(0.1, 1.0))
+        force.setParticleSubset(i, int(rng.integers(0, nsub)))
+    bonds = [(i, i+1) for i in range(0, n-1) if i % 5 != 4]
+    force.createExceptionsFromBonds(bonds, 1/1.2, 0.5)
+    if with_offsets:
+        force.addGlobalParameter("off", 0.3)
+        force.addParticleParameterOffset("off", 3, 0.5, 0.01, 0.2)
+        force.addExceptionParameterOffset("off", 2, 0.2, 0.01, 0.1)
+    force.addGlobalParameter("lc", 0.7)
+    force.addGlobalParameter("lv", 0.4)
+    force.addScalingParameter("lc", 0, 1, True, False)
+    force.addScalingParameter("lv", 0, 1, False, True)
+    force.addEnergyParameterDerivative("lc")
+    force.addEnergyParameterDerivative("lv")
+    system.addForce(force)
+    return system, force, positions
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_port_matches_compiled_reference(nbs, oracle, seed):
+    if not oracle.available("reference"):
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(seed)
+    system, force, positions = random_system(nbs, rng)
+    states = []
+    for kind in ("port", "reference"):
+        ctx = nbs.Context(system, oracle.OraclePlatform(kind))
+        ctx.setPositions(positions)
+        ctx.setParameter("off", 0.45)
+        states.append(ctx.getState(getEnergy=True, getForces=True, getParameterDerivatives=True))
+    a, b = states
+    assert force_rel_rms(a.getForces(), b.getForces()) < 1e-12
+    assert_equal_tol(b.getPotentialEnergy(), a.getPotentialEnergy(), 1e-12)
+    for name, value in b.getEnergyParameterDerivatives().items():
+        assert_equal_tol(value, a.getEnergyParameterDerivatives()[name], 1e-12)
+
+
+def test_dispersion_coefficients_agree(nbs, oracle, systems):
+    """The host mirror of calcDispersionCorrections (product side) equals the oracle's restatement."""
+    s = systems.make_system("C2")
+    host = nbs.SlicedNonbondedForceImpl.calcDispersionCorrections(s.system, s.force)
+    desc = nbs.build_desc(s.system, s.force)
+    ref = oracle.dispersion_coefficients(desc, np.array([g[1] for g in s.force._globalParams]))
+    assert np.allclose(host, ref, rtol=1e-12)
+    assert np.any(np.asarray(host) != 0)
+
+
+def test_slicing_equals_rescaled_parameters(nbs, oracle):
+    """testNonbondedSlicing (:1031-1318): scaling slice (0,1) and (1,1) by lambda equals a one-subset
+    force whose subset-1 charges are scaled (Coulomb case); sum of all slice derivatives = energy."""
+    rng = np.random.default_rng(7)
+    n, L = 200, 7.0
+    system1, system2 = nbs.System(), nbs.System()
+    plain = nbs.SlicedNonbondedForce(1)
+    plain.setNonbondedMethod(plain.PME)
+    plain.setCutoffDistance(3.0)
+    plain.setPMEParameters(1.1, 24, 24, 24)
+    plain.setUseDispersionCorrection(True)
+    positions = rng.uniform(0, L, size=(n, 3))
+    # keep particles apart
+    side = 6
+    sites = np.array([(i, j, k) for i in range(side) for j in range(side) for k in range(side)][:n], dtype=float)
+    positions = (sites+0.5)*L/side + rng.uniform(-0.1, 0.1, size=(n, 3))
+    charges = np.array([1-2*(k % 2) for k in range(n)], dtype=float)
+    for k in range(n):
+        system1.addParticle(1.0)
+        system2.addParticle(1.0)
+        plain.addParticle(charges[k], 0.5, 1.0)
+    for k in range(0, n, 2):
+        plain.addException(k, k+1, charges[k]*charges[k+1], 0.5, 1.0)
+    for sysm in (system1, system2):
+        sysm.setDefaultPeriodicBoxVectors([L, 0, 0], [0, L, 0], [0, 0, L])
+    sliced = nbs.SlicedNonbondedForce(plain, 2)
+    in1 = rng.random(n) < 0.5
+    for k in range(n):
+        if in1[k]:
+            sliced.setParticleSubset(k, 1)
+    sliced.addGlobalParameter("lambda", 1)
+    sliced.addScalingParameter("lambda", 0, 1, True, False)
+    sliced.addGlobalParameter("lambdaSq", 1)
+    sliced.addScalingParameter("lambdaSq", 1, 1, True, False)
+    system1.addForce(plain)
+    system2.addForce(sliced)
+    platform = oracle.OraclePlatform("port")
+    ctx2 = nbs.Context(system2, platform)
+    ctx2.setPositions(positions)
+    energies = {}
+    for lam in (1.0, 0.0, 0.5):
+        for k in range(n):
+            plain.setParticleParameters(k, charges[k]*(lam if in1[k] else 1.0), 0.5, 1.0)
+        for e in range(plain.getNumExceptions()):
+            p1, p2 = plain.getExceptionParameters(e)[:2]
+            scale = 1.0
+            if in1[p1] != in1[p2]:
+                scale = lam
+            elif in1[p1]:
+                scale = lam*lam
+            plain.setExceptionParameters(e, p1, p2, charges[p1]*charges[p2]*scale, 0.5, 1.0)
+        ctx1 = nbs.Context(system1, platform)
+        ctx1.setPositions(positions)
+        ctx2.setParameter("lambda", lam)
+        ctx2.setParameter("lambdaSq", lam*lam)
+        for groups in (0xFFFFFFFF,):
+            s1 = ctx1.getState(getEnergy=True, getForces=True, groups=groups)
+            s2 = ctx2.getState(getEnergy=True, getForces=True, groups=groups)
+            assert_equal_tol(s1.getPotentialEnergy(), s2.getPotentialEnergy(), 1e-9)
+            assert force_rel_rms(s2.getForces(), s1.getForces()) < 1e-9
+        energies[lam] = s2.getPotentialEnergy()
+    # derivatives (:1279-1317)
+    sliced.addEnergyParameterDerivative("lambda")
+    sliced.addEnergyParameterDerivative("lambdaSq")
+    sliced.addGlobalParameter("remainderC", 1.0)
+    sliced.addScalingParameter("remainderC", 0, 0, True, False)
+    sliced.addEnergyParameterDerivative("remainderC")
+    ctx2.reinitialize(True)
+    ctx2.setParameter("lambda", 1.0)
+    ctx2.setParameter("lambdaSq", 1.0)
+    d = ctx2.getState(getEnergy=True, getParameterDerivatives=True)
+    derivs = d.getEnergyParameterDerivatives()
+    assert_equal_tol(energies[1.0]-energies[0.0], derivs["lambda"]+derivs["lambdaSq"], 1e-9)

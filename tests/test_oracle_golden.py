@@ -1,0 +1,485 @@
+"""Pins the CPU oracles against the analytic known answers of the reference's own test suite
+(tests/TestSlicedNonbondedForce.h; line ranges cited per test).  Runs on both oracle backends:
+the restatement ("port") and -- when oracle/_ref was built from /root/reference -- the reference's
+unmodified TUs ("reference")."""
+import math
+
+import numpy as np
+import pytest
+
+from helpers import TOL, assert_equal_tol, assert_equal_vec
+
+
+def _kinds(oracle):
+    return ["port"] + (["reference"] if oracle.available("reference") else [])
+
+
+@pytest.fixture(params=["port", "reference"])
+def platform(request, oracle):
+    if request.param == "reference" and not oracle.available("reference"):
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    return oracle.OraclePlatform(request.param)
+
+
+def test_coulomb(nbs, platform):
+    """testCoulomb :87-109"""
+    system = nbs.System()
+    system.addParticle(1.0)
+    system.addParticle(1.0)
+    ff = nbs.SlicedNonbondedForce(1)
+    ff.addParticle(0.5, 1, 0)
+    ff.addParticle(-1.5, 1, 0)
+    system.addForce(ff)
+    assert not ff.usesPeriodicBoundaryConditions()
+    assert not system.usesPeriodicBoundaryConditions()
+    context = nbs.Context(system, platform)
+    context.setPositions([[0, 0, 0], [2, 0, 0]])
+    state = context.getState(getForces=True, getEnergy=True)
+    force = nbs.ONE_4PI_EPS0*(-0.75)/4.0
+    assert_equal_vec([-force, 0, 0], state.getForces()[0], TOL)
+    assert_equal_vec([force, 0, 0], state.getForces()[1], TOL)
+    assert_equal_tol(nbs.ONE_4PI_EPS0*(-0.75)/2.0, state.getPotentialEnergy(), TOL)
+
+
+def test_lj(nbs, platform):
+    """testLJ :111-135"""
+    system = nbs.System()
+    system.addParticle(1.0)
+    system.addParticle(1.0)
+    ff = nbs.SlicedNonbondedForce(1)
+    ff.addParticle(0, 1.2, 1)
+    ff.addParticle(0, 1.4, 2)
+    system.addForce(ff)
+    context = nbs.Context(system, platform)
+    context.setPositions([[0, 0, 0], [2, 0, 0]])
+    state = context.getState(getForces=True, getEnergy=True)
+    x = 1.3/2.0
+    eps = math.sqrt(2.0)
+    force = 4.0*eps*(12*x**12-6*x**6)/2.0
+    assert_equal_vec([-force, 0, 0], state.getForces()[0], TOL)
+    assert_equal_vec([force, 0, 0], state.getForces()[1], TOL)
+    assert_equal_tol(4.0*eps*(x**12-x**6), state.getPotentialEnergy(), TOL)
+
+
+def _chain_force(nbs, method=None, cutoff=None, eps=None):
+    system = nbs.System()
+    sliced = nbs.SlicedNonbondedForce(1)
+    if method is not None:
+        sliced.setNonbondedMethod(method)
+    for _ in range(5):
+        system.addParticle(1.0)
+        sliced.addParticle(0, 1.5, 0)
+    if cutoff is not None:
+        sliced.setCutoffDistance(cutoff)
+        sliced.setReactionFieldDielectric(eps)
+    sliced.createExceptionsFromBonds([(0, 1), (1, 2), (2, 3), (3, 4)], 0.0, 0.0)
+    first14 = second14 = None
+    for i in range(sliced.getNumExceptions()):
+        p1, p2 = sliced.getExceptionParameters(i)[:2]
+        if {p1, p2} == {0, 3}:
+            first14 = i
+        if {p1, p2} == {1, 4}:
+            second14 = i
+    system.addForce(sliced)
+    return system, sliced, first14, second14
+
+
+def test_exclusions_and_14(nbs, platform):
+    """testExclusionsAnd14 :137-222"""
+    system, sliced, first14, second14 = _chain_force(nbs)
+    context = nbs.Context(system, platform)
+    for i in range(1, 5):
+        r = 1.0
+        positions = [[0, j, 0] for j in range(5)]
+        for j in range(5):
+            sliced.setParticleParameters(j, 0, 1.5, 0)
+        sliced.setParticleParameters(0, 0, 1.5, 1)
+        sliced.setParticleParameters(i, 0, 1.5, 1)
+        sliced.setExceptionParameters(first14, 0, 3, 0, 1.5, 0.5 if i == 3 else 0.0)
+        sliced.setExceptionParameters(second14, 1, 4, 0, 1.5, 0.0)
+        positions[i] = [r, 0, 0]
+        context.reinitialize()
+        context.setPositions(positions)
+        state = context.getState(getForces=True, getEnergy=True)
+        x = 1.5/r
+        force = 4.0*(12*x**12-6*x**6)/r
+        energy = 4.0*(x**12-x**6)
+        if i == 3:
+            force *= 0.5
+            energy *= 0.5
+        if i < 3:
+            force = energy = 0
+        assert_equal_vec([-force, 0, 0], state.getForces()[0], TOL)
+        assert_equal_vec([force, 0, 0], state.getForces()[i], TOL)
+        assert_equal_tol(energy, state.getPotentialEnergy(), TOL)
+        # Coulomb
+        sliced.setParticleParameters(0, 2, 1.5, 0)
+        sliced.setParticleParameters(i, 2, 1.5, 0)
+        sliced.setExceptionParameters(first14, 0, 3, 4/1.2 if i == 3 else 0, 1.5, 0)
+        sliced.setExceptionParameters(second14, 1, 4, 0, 1.5, 0)
+        context.reinitialize()
+        context.setPositions(positions)
+        state = context.getState(getForces=True, getEnergy=True)
+        force = nbs.ONE_4PI_EPS0*4/(r*r)
+        energy = nbs.ONE_4PI_EPS0*4/r
+        if i == 3:
+            force /= 1.2
+            energy /= 1.2
+        if i < 3:
+            force = energy = 0
+        assert_equal_vec([-force, 0, 0], state.getForces()[0], TOL)
+        assert_equal_vec([force, 0, 0], state.getForces()[i], TOL)
+        assert_equal_tol(energy, state.getPotentialEnergy(), TOL)
+
+
+def test_cutoff(nbs, platform):
+    """testCutoff :224-260"""
+    system = nbs.System()
+    ff = nbs.SlicedNonbondedForce(1)
+    for _ in range(3):
+        system.addParticle(1.0)
+        ff.addParticle(1.0, 1, 0)
+    ff.setNonbondedMethod(ff.CutoffNonPeriodic)
+    cutoff, eps = 2.9, 50.0
+    ff.setCutoffDistance(cutoff)
+    ff.setReactionFieldDielectric(eps)
+    system.addForce(ff)
+    context = nbs.Context(system, platform)
+    context.setPositions([[0, 0, 0], [0, 2, 0], [0, 3, 0]])
+    state = context.getState(getForces=True, getEnergy=True)
+    K = nbs.ONE_4PI_EPS0
+    krf = (1.0/cutoff**3)*(eps-1.0)/(2.0*eps+1.0)
+    crf = (1.0/cutoff)*(3.0*eps)/(2.0*eps+1.0)
+    force1 = K*(0.25-2.0*krf*2.0)
+    force2 = K*(1.0-2.0*krf*1.0)
+    forces = state.getForces()
+    assert_equal_vec([0, -force1, 0], forces[0], TOL)
+    assert_equal_vec([0, force1-force2, 0], forces[1], TOL)
+    assert_equal_vec([0, force2, 0], forces[2], TOL)
+    assert_equal_tol(K*(0.5+krf*4.0-crf) + K*(1.0+krf*1.0-crf), state.getPotentialEnergy(), TOL)
+
+
+def test_cutoff14(nbs, platform):
+    """testCutoff14 :262-356"""
+    cutoff, eps = 3.5, 30.0
+    system, sliced, first14, second14 = _chain_force(nbs, nbs.SlicedNonbondedForce.CutoffNonPeriodic, cutoff, eps)
+    context = nbs.Context(system, platform)
+    positions = [[float(k), 0, 0] for k in range(5)]
+    context.setPositions(positions)
+    for i in range(1, 5):
+        sliced.setParticleParameters(0, 0, 1.5, 1)
+        for j in range(1, 5):
+            sliced.setParticleParameters(j, 0, 1.5, 0)
+        sliced.setParticleParameters(i, 0, 1.5, 1)
+        sliced.setExceptionParameters(first14, 0, 3, 0, 1.5, 0.5 if i == 3 else 0.0)
+        sliced.setExceptionParameters(second14, 1, 4, 0, 1.5, 0.0)
+        context.reinitialize(True)
+        state = context.getState(getForces=True, getEnergy=True)
+        r = positions[i][0]
+        x = 1.5/r
+        force = 4.0*(12*x**12-6*x**6)/r
+        energy = 4.0*(x**12-x**6)
+        if i == 3:
+            force *= 0.5
+            energy *= 0.5
+        if i < 3 or r > cutoff:
+            force = energy = 0
+        assert_equal_vec([-force, 0, 0], state.getForces()[0], TOL)
+        assert_equal_vec([force, 0, 0], state.getForces()[i], TOL)
+        assert_equal_tol(energy, state.getPotentialEnergy(), TOL)
+        q = 0.7
+        sliced.setParticleParameters(0, q, 1.5, 0)
+        sliced.setParticleParameters(i, q, 1.5, 0)
+        sliced.setExceptionParameters(first14, 0, 3, q*q/1.2 if i == 3 else 0, 1.5, 0)
+        sliced.setExceptionParameters(second14, 1, 4, 0, 1.5, 0)
+        context.reinitialize(True)
+        state = context.getState(getForces=True, getEnergy=True)
+        force = nbs.ONE_4PI_EPS0*q*q/(r*r)
+        energy = nbs.ONE_4PI_EPS0*q*q/r
+        if i == 3:
+            force /= 1.2
+            energy /= 1.2
+        if i < 3 or r > cutoff:
+            force = energy = 0
+        assert_equal_vec([-force, 0, 0], state.getForces()[0], TOL)
+        assert_equal_vec([force, 0, 0], state.getForces()[i], TOL)
+        assert_equal_tol(energy, state.getPotentialEnergy(), TOL)
+
+
+def test_periodic(nbs, platform):
+    """testPeriodic :358-392"""
+    system = nbs.System()
+    sliced = nbs.SlicedNonbondedForce(1)
+    for _ in range(3):
+        system.addParticle(1.0)
+        sliced.addParticle(1.0, 1, 0)
+    sliced.addException(0, 1, 0.0, 1.0, 0.0)
+    sliced.setNonbondedMethod(sliced.CutoffPeriodic)
+    cutoff = 2.0
+    sliced.setCutoffDistance(cutoff)
+    system.setDefaultPeriodicBoxVectors([4, 0, 0], [0, 4, 0], [0, 0, 4])
+    system.addForce(sliced)
+    assert sliced.usesPeriodicBoundaryConditions() and system.usesPeriodicBoundaryConditions()
+    context = nbs.Context(system, platform)
+    context.setPositions([[0, 0, 0], [2, 0, 0], [3, 0, 0]])
+    state = context.getState(getForces=True, getEnergy=True)
+    eps = 78.3
+    krf = (1.0/cutoff**3)*(eps-1.0)/(2.0*eps+1.0)
+    crf = (1.0/cutoff)*(3.0*eps)/(2.0*eps+1.0)
+    force = nbs.ONE_4PI_EPS0*(1.0-2.0*krf*1.0)
+    forces = state.getForces()
+    assert_equal_vec([force, 0, 0], forces[0], TOL)
+    assert_equal_vec([-force, 0, 0], forces[1], TOL)
+    assert_equal_vec([0, 0, 0], forces[2], TOL)
+    assert_equal_tol(2*nbs.ONE_4PI_EPS0*(1.0+krf*1.0-crf), state.getPotentialEnergy(), TOL)
+
+
+def test_periodic_exceptions(nbs, platform):
+    """testPeriodicExceptions :394-430"""
+    system = nbs.System()
+    sliced = nbs.SlicedNonbondedForce(1)
+    for _ in range(2):
+        system.addParticle(1.0)
+        sliced.addParticle(1.0, 1, 0)
+    sliced.addException(0, 1, 1.0, 1.0, 0.0)
+    sliced.setNonbondedMethod(sliced.CutoffPeriodic)
+    sliced.setCutoffDistance(2.0)
+    system.setDefaultPeriodicBoxVectors([4, 0, 0], [0, 4, 0], [0, 0, 4])
+    system.addForce(sliced)
+    context = nbs.Context(system, platform)
+    context.setPositions([[0, 0, 0], [3, 0, 0]])
+    state = context.getState(getForces=True, getEnergy=True)
+    force = nbs.ONE_4PI_EPS0/9
+    assert_equal_vec([-force, 0, 0], state.getForces()[0], TOL)
+    assert_equal_vec([force, 0, 0], state.getForces()[1], TOL)
+    assert_equal_tol(nbs.ONE_4PI_EPS0/3, state.getPotentialEnergy(), TOL)
+    sliced.setExceptionsUsePeriodicBoundaryConditions(True)
+    context.reinitialize(True)
+    state = context.getState(getForces=True, getEnergy=True)
+    force = nbs.ONE_4PI_EPS0
+    assert_equal_vec([force, 0, 0], state.getForces()[0], TOL)
+    assert_equal_vec([-force, 0, 0], state.getForces()[1], TOL)
+    assert_equal_tol(nbs.ONE_4PI_EPS0, state.getPotentialEnergy(), TOL)
+
+
+def test_triclinic(nbs, platform):
+    """testTriclinic :432-492 (positions from numpy's RNG instead of SFMT; the check is analytic)"""
+    system = nbs.System()
+    a, b, c = np.array([3.1, 0, 0]), np.array([0.4, 3.5, 0]), np.array([-0.1, -0.5, 4.0])
+    system.setDefaultPeriodicBoxVectors(a, b, c)
+    sliced = nbs.SlicedNonbondedForce(1)
+    for _ in range(2):
+        system.addParticle(1.0)
+        sliced.addParticle(1.0, 1, 0)
+    sliced.setNonbondedMethod(sliced.CutoffPeriodic)
+    cutoff = 1.5
+    sliced.setCutoffDistance(cutoff)
+    system.addForce(sliced)
+    context = nbs.Context(system, platform)
+    rng = np.random.default_rng(0)
+    eps = 78.3
+    krf = (1.0/cutoff**3)*(eps-1.0)/(2.0*eps+1.0)
+    crf = (1.0/cutoff)*(3.0*eps)/(2.0*eps+1.0)
+    for _ in range(50):
+        u = rng.random((2, 3))
+        positions = [a*u[k, 0] + b*u[k, 1] + c*u[k, 2] for k in range(2)]
+        context.setPositions(positions)
+        best, delta = 100.0, None
+        for i in (-1, 0, 1):
+            for j in (-1, 0, 1):
+                for k in (-1, 0, 1):
+                    d = positions[1]-positions[0]+a*i+b*j+c*k
+                    if d.dot(d) < best:
+                        best, delta = d.dot(d), d
+        distance = math.sqrt(best)
+        state = context.getState(getForces=True, getEnergy=True)
+        if distance >= cutoff:
+            assert state.getPotentialEnergy() == 0.0
+            assert np.all(state.getForces() == 0)
+        else:
+            force = delta*nbs.ONE_4PI_EPS0*(-1.0/distance**3+2.0*krf)
+            assert_equal_tol(nbs.ONE_4PI_EPS0*(1.0/distance+krf*distance*distance-crf), state.getPotentialEnergy(), 1e-4)
+            assert_equal_vec(force, state.getForces()[0], 1e-4)
+            assert_equal_vec(-force, state.getForces()[1], 1e-4)
+
+
+def test_dispersion_correction(nbs, platform):
+    """testDispersionCorrection :614-681"""
+    gridSize = 5
+    numParticles = gridSize**3
+    boxSize = gridSize*0.7
+    cutoff = boxSize/3
+    system = nbs.System()
+    sliced = nbs.SlicedNonbondedForce(1)
+    positions = []
+    for i in range(gridSize):
+        for j in range(gridSize):
+            for k in range(gridSize):
+                system.addParticle(1.0)
+                sliced.addParticle(0, 1.1, 0.5)
+                positions.append([i*boxSize/gridSize, j*boxSize/gridSize, k*boxSize/gridSize])
+    sliced.setNonbondedMethod(sliced.CutoffPeriodic)
+    sliced.setCutoffDistance(cutoff)
+    system.setDefaultPeriodicBoxVectors([boxSize, 0, 0], [0, boxSize, 0], [0, 0, boxSize])
+    system.addForce(sliced)
+    context = nbs.Context(system, platform)
+    context.setPositions(positions)
+    energy1 = context.getState(getEnergy=True).getPotentialEnergy()
+    sliced.setUseDispersionCorrection(False)
+    context.reinitialize()
+    context.setPositions(positions)
+    energy2 = context.getState(getEnergy=True).getPotentialEnergy()
+    term1 = (0.5*1.1**12/cutoff**9)/9
+    term2 = (0.5*1.1**6/cutoff**3)/3
+    expected = 8*math.pi*numParticles*numParticles*(term1-term2)/boxSize**3
+    assert_equal_tol(expected, energy1-energy2, TOL)
+    numType2 = 0
+    for i in range(0, numParticles, 2):
+        sliced.setParticleParameters(i, 0, 1, 1)
+        numType2 += 1
+    numType1 = numParticles-numType2
+    sliced.updateParametersInContext(context)
+    energy2 = context.getState(getEnergy=True).getPotentialEnergy()
+    sliced.setUseDispersionCorrection(True)
+    context.reinitialize()
+    context.setPositions(positions)
+    energy1 = context.getState(getEnergy=True).getPotentialEnergy()
+    term1 = ((numType1*(numType1+1))//2)*(0.5*1.1**12/cutoff**9)/9
+    term2 = ((numType1*(numType1+1))//2)*(0.5*1.1**6/cutoff**3)/3
+    term1 += ((numType2*(numType2+1))//2)*(1*1.0**12/cutoff**9)/9
+    term2 += ((numType2*(numType2+1))//2)*(1*1.0**6/cutoff**3)/3
+    combinedSigma = 0.5*(1+1.1)
+    combinedEpsilon = math.sqrt(1*0.5)
+    term1 += (numType1*numType2)*(combinedEpsilon*combinedSigma**12/cutoff**9)/9
+    term2 += (numType1*numType2)*(combinedEpsilon*combinedSigma**6/cutoff**3)/3
+    term1 /= (numParticles*(numParticles+1))//2
+    term2 /= (numParticles*(numParticles+1))//2
+    expected = 8*math.pi*numParticles*numParticles*(term1-term2)/boxSize**3
+    assert_equal_tol(expected, energy1-energy2, TOL)
+
+
+def test_switching_function(nbs, platform):
+    """testSwitchingFunction :760-813 (CutoffNonPeriodic leg)"""
+    system = nbs.System()
+    system.addParticle(1.0)
+    system.addParticle(1.0)
+    ff = nbs.SlicedNonbondedForce(1)
+    ff.addParticle(0, 1.2, 1)
+    ff.addParticle(0, 1.4, 2)
+    ff.setNonbondedMethod(ff.CutoffNonPeriodic)
+    ff.setCutoffDistance(2.0)
+    ff.setUseSwitchingFunction(True)
+    ff.setSwitchingDistance(1.5)
+    ff.setUseDispersionCorrection(False)
+    system.addForce(ff)
+    context = nbs.Context(system, platform)
+    eps = math.sqrt(2.0)
+    r = 1.0
+    while r < 2.5:
+        context.setPositions([[0, 0, 0], [r, 0, 0]])
+        state = context.getState(getForces=True, getEnergy=True)
+        x = 1.3/r
+        expectedEnergy = 4.0*eps*(x**12-x**6)
+        switchValue = 1.0
+        if r > 1.5:
+            t = (r-1.5)/0.5
+            switchValue = 1+t*t*t*(-10+t*(15-t*6))
+        if r >= 2.0:
+            switchValue = 0.0
+        assert_equal_tol(switchValue*expectedEnergy, state.getPotentialEnergy(), TOL)
+        delta = 1e-3
+        context.setPositions([[0, 0, 0], [r-delta, 0, 0]])
+        e1 = context.getState(getEnergy=True).getPotentialEnergy()
+        context.setPositions([[0, 0, 0], [r+delta, 0, 0]])
+        e2 = context.getState(getEnergy=True).getPotentialEnergy()
+        assert_equal_tol((e2-e1)/(2*delta), state.getForces()[0][0], 1e-3)
+        r += 0.1
+
+
+def test_parameter_offsets(nbs, platform):
+    """testParameterOffsets :883-945"""
+    system = nbs.System()
+    for _ in range(4):
+        system.addParticle(1.0)
+    force = nbs.SlicedNonbondedForce(1)
+    force.addParticle(0.0, 1.0, 0.5)
+    force.addParticle(1.0, 0.5, 0.6)
+    force.addParticle(-1.0, 2.0, 0.7)
+    force.addParticle(0.5, 2.0, 0.8)
+    force.addException(0, 3, 0.0, 1.0, 0.0)
+    force.addException(2, 3, 0.5, 1.0, 1.5)
+    force.addException(0, 1, 1.0, 1.5, 1.0)
+    force.addGlobalParameter("p1", 0.0)
+    force.addGlobalParameter("p2", 1.0)
+    force.addParticleParameterOffset("p1", 0, 3.0, 0.5, 0.5)
+    force.addParticleParameterOffset("p2", 1, 1.0, 1.0, 2.0)
+    force.addExceptionParameterOffset("p1", 1, 0.5, 0.5, 1.5)
+    system.addForce(force)
+    context = nbs.Context(system, platform)
+    context.setPositions([[i, 0, 0] for i in range(4)])
+    assert len(context.getParameters()) == 2
+    assert context.getParameter("p1") == 0.0 and context.getParameter("p2") == 1.0
+    context.setParameter("p1", 0.5)
+    context.setParameter("p2", 1.5)
+    q = [0.0+3.0*0.5, 1.0+1.0*1.5, -1.0, 0.5]
+    sg = [1.0+0.5*0.5, 0.5+1.0*1.5, 2.0, 2.0]
+    ep = [0.5+0.5*0.5, 0.6+2.0*1.5, 0.7, 0.8]
+    qq, ss, ee = {}, {}, {}
+    for i in range(4):
+        for j in range(i+1, 4):
+            qq[i, j], ss[i, j], ee[i, j] = q[i]*q[j], 0.5*(sg[i]+sg[j]), math.sqrt(ep[i]*ep[j])
+    qq[0, 3], ss[0, 3], ee[0, 3] = 0.0, 1.0, 0.0
+    qq[2, 3], ss[2, 3], ee[2, 3] = 0.5+0.5*0.5, 1.0+0.5*0.5, 1.5+1.5*0.5
+    qq[0, 1], ss[0, 1], ee[0, 1] = 1.0, 1.5, 1.0
+    energy = 0.0
+    for (i, j) in qq:
+        dist = j-i
+        x = ss[i, j]/dist
+        energy += nbs.ONE_4PI_EPS0*qq[i, j]/dist + 4.0*ee[i, j]*(x**12-x**6)
+    assert_equal_tol(energy, context.getState(getEnergy=True).getPotentialEnergy(), 1e-4)
+
+
+def test_direct_and_reciprocal(nbs, platform):
+    """testDirectAndReciprocal :987-1029"""
+    system = nbs.System()
+    for _ in range(4):
+        system.addParticle(1.0)
+    system.setDefaultPeriodicBoxVectors([2, 0, 0], [0, 2, 0], [0, 0, 2])
+    force = nbs.SlicedNonbondedForce(1)
+    system.addForce(force)
+    force.setNonbondedMethod(force.PME)
+    force.setCutoffDistance(1.0)
+    force.setReciprocalSpaceForceGroup(1)
+    force.addParticle(1.0, 0.5, 1.0)
+    force.addParticle(1.0, 0.5, 1.0)
+    force.addParticle(-1.0, 0.5, 1.0)
+    force.addParticle(-1.0, 0.5, 1.0)
+    force.addException(0, 2, -2.0, 0.5, 3.0)
+    context = nbs.Context(system, platform)
+    context.setPositions([[0, 0, 0], [1.5, 0, 0], [0, 0.5, 0.5], [0.2, 1.3, 0]])
+    e1 = context.getState(getEnergy=True).getPotentialEnergy()
+    e2 = context.getState(getEnergy=True, groups=1 << 0).getPotentialEnergy()
+    e3 = context.getState(getEnergy=True, groups=1 << 1).getPotentialEnergy()
+    assert_equal_tol(e1, e2+e3, 1e-4)
+    assert e2 != 0 and e3 != 0
+    force.setIncludeDirectSpace(False)
+    context.reinitialize(True)
+    e4 = context.getState(getEnergy=True).getPotentialEnergy()
+    assert_equal_tol(e3, e4, 1e-4)
+
+
+def test_parameter_clash(nbs, platform):
+    """python/tests/TestSlicedNonbondedForce.py:51-67 and SlicedNonbondedForceImpl.cpp:114-131"""
+    system = nbs.System()
+    system.setDefaultPeriodicBoxVectors([4, 0, 0], [0, 4, 0], [0, 0, 4])
+    system.addParticle(1.0)
+    system.addParticle(1.0)
+    force = nbs.SlicedNonbondedForce(1)
+    force.addParticle(1.5, 1, 0)
+    force.addParticle(-1.5, 1, 0)
+    force.addGlobalParameter("param", 1)
+    force.addScalingParameter("param", 0, 0, True, True)
+    force.addParticleParameterOffset("param", 0, 1, 1, 0)
+    system.addForce(force)
+    with pytest.raises(Exception):
+        nbs.Context(system, platform)

@@ -23,37 +23,47 @@ namespace nbs {
 constexpr int FFT_MAX_N = 512;
 
 struct FftPlan {           // factorisation of one dimension
-    int n, nf;
+    int n, nf, nq;         // nq = butterflies per lane of the widest pass = ceil(max_R (n/R) / 32)
     int f[12];
+    unsigned long long packed;   // the factors, 4 bits each, first pass in the low bits, 0-terminated
 };
 
 static bool makePlan(int n, FftPlan& p) {
-    p.n = n; p.nf = 0;
+    p.n = n; p.nf = 0; p.nq = 1;
     int m = n;
     while (m % 4 == 0) { p.f[p.nf++] = 4; m /= 4; }
     const int radices[] = {2, 3, 5, 7, 11, 13};
     for (int r : radices)
         while (m % r == 0) { p.f[p.nf++] = r; m /= r; }
+    p.packed = 0;
+    for (int k = 0; k < p.nf; k++) {
+        if (p.f[k] <= 7) p.nq = std::max(p.nq, (n/p.f[k] + 31)/32);      // radix 11/13 passes are rolled loops
+        p.packed |= (unsigned long long) p.f[k] << (4*k);
+    }
     return m == 1 && n <= FFT_MAX_N;
 }
+
+// complex helpers, generic in precision
+template <typename T> struct Cx;
+template <> struct Cx<float> { typedef float2 type; };
+template <> struct Cx<double> { typedef double2 type; };
+__device__ __forceinline__ float2 mk(float x, float y) { return make_float2(x, y); }
+__device__ __forceinline__ double2 mk(double x, double y) { return make_double2(x, y); }
+template <typename C> __device__ __forceinline__ C cmul(C a, C b) { return mk(a.x*b.x - a.y*b.y, a.x*b.y + a.y*b.x); }
 
 // ---------------------------------------------------------------------------------------------
 // One Stockham pass of radix R over a line of length n in shared memory, executed by one warp.
 // Inputs are staged through registers, so the pass is in place (read all, sync, write all).
+// NQ = butterflies per lane the instantiation is unrolled for.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-    return make_float2(a.x*b.x - a.y*b.y, a.x*b.y + a.y*b.x);
-}
-
-template <int R>
-__device__ __forceinline__ void fftPass(float2* line, int n, int Ns, const float2* tw, int lane) {
-    constexpr int MAXB = (FFT_MAX_N/R + 31)/32;
+template <int R, int NQ, typename C>
+__device__ __forceinline__ void fftPass(C* line, int n, int Ns, const C* tw, int lane) {
     const int nb = n/R;
     const int tstep = n/(Ns*R);
     const int rstep = n/R;
-    float2 v[MAXB][R];
+    C v[NQ][R];
 #pragma unroll
-    for (int q = 0; q < MAXB; q++) {
+    for (int q = 0; q < NQ; q++) {
         const int j = lane + 32*q;
         if (j < nb) {
 #pragma unroll
@@ -62,7 +72,7 @@ __device__ __forceinline__ void fftPass(float2* line, int n, int Ns, const float
     }
     __syncwarp();
 #pragma unroll
-    for (int q = 0; q < MAXB; q++) {
+    for (int q = 0; q < NQ; q++) {
         const int j = lane + 32*q;
         if (j < nb) {
             const int k = j % Ns;
@@ -70,27 +80,27 @@ __device__ __forceinline__ void fftPass(float2* line, int n, int Ns, const float
             for (int t = 1; t < R; t++) v[q][t] = cmul(v[q][t], tw[t*k*tstep]);
             const int j0 = (j/Ns)*Ns*R + k;
             if (R == 2) {
-                line[j0] = make_float2(v[q][0].x + v[q][1].x, v[q][0].y + v[q][1].y);
-                line[j0 + Ns] = make_float2(v[q][0].x - v[q][1].x, v[q][0].y - v[q][1].y);
+                line[j0] = mk(v[q][0].x + v[q][1].x, v[q][0].y + v[q][1].y);
+                line[j0 + Ns] = mk(v[q][0].x - v[q][1].x, v[q][0].y - v[q][1].y);
             }
             else if (R == 4) {
-                const float2 a0 = make_float2(v[q][0].x + v[q][2].x, v[q][0].y + v[q][2].y);
-                const float2 a1 = make_float2(v[q][0].x - v[q][2].x, v[q][0].y - v[q][2].y);
-                const float2 a2 = make_float2(v[q][1].x + v[q][3].x, v[q][1].y + v[q][3].y);
-                const float2 a3 = make_float2(v[q][1].x - v[q][3].x, v[q][1].y - v[q][3].y);
+                const C a0 = mk(v[q][0].x + v[q][2].x, v[q][0].y + v[q][2].y);
+                const C a1 = mk(v[q][0].x - v[q][2].x, v[q][0].y - v[q][2].y);
+                const C a2 = mk(v[q][1].x + v[q][3].x, v[q][1].y + v[q][3].y);
+                const C a3 = mk(v[q][1].x - v[q][3].x, v[q][1].y - v[q][3].y);
                 // forward transform: multiply a3 by -i
-                line[j0] = make_float2(a0.x + a2.x, a0.y + a2.y);
-                line[j0 + Ns] = make_float2(a1.x + a3.y, a1.y - a3.x);
-                line[j0 + 2*Ns] = make_float2(a0.x - a2.x, a0.y - a2.y);
-                line[j0 + 3*Ns] = make_float2(a1.x - a3.y, a1.y + a3.x);
+                line[j0] = mk(a0.x + a2.x, a0.y + a2.y);
+                line[j0 + Ns] = mk(a1.x + a3.y, a1.y - a3.x);
+                line[j0 + 2*Ns] = mk(a0.x - a2.x, a0.y - a2.y);
+                line[j0 + 3*Ns] = mk(a1.x - a3.y, a1.y + a3.x);
             }
             else {
 #pragma unroll
                 for (int o = 0; o < R; o++) {
-                    float2 acc = v[q][0];
+                    C acc = v[q][0];
 #pragma unroll
                     for (int t = 1; t < R; t++) {
-                        const float2 w = tw[((o*t) % R)*rstep];
+                        const C w = tw[((o*t) % R)*rstep];
                         acc.x += v[q][t].x*w.x - v[q][t].y*w.y;
                         acc.y += v[q][t].x*w.y + v[q][t].y*w.x;
                     }
@@ -102,19 +112,51 @@ __device__ __forceinline__ void fftPass(float2* line, int n, int Ns, const float
     __syncwarp();
 }
 
+// Radix 11 / 13 (rare grid sizes): rolled loops over small local arrays -- slow but register-light,
+// so the common radices keep their occupancy.  n <= 512 means at most 46 butterflies, i.e. at most two
+// per lane; both are read before anything is written (the pass is in place).
+template <typename C>
+__device__ __noinline__ void fftPassLarge(C* line, int n, int R, int Ns, const C* tw, int lane) {
+    const int nb = n/R, tstep = n/(Ns*R), rstep = n/R;
+    C v[2][13];
+    for (int q = 0; q < 2; q++) {
+        const int j = lane + 32*q;
+        if (j < nb)
+            for (int t = 0; t < R; t++) v[q][t] = line[j + t*nb];
+    }
+    __syncwarp();
+    for (int q = 0; q < 2; q++) {
+        const int j = lane + 32*q;
+        if (j >= nb) continue;
+        const int k = j % Ns;
+        for (int t = 1; t < R; t++) v[q][t] = cmul(v[q][t], tw[t*k*tstep]);
+        const int j0 = (j/Ns)*Ns*R + k;
+        for (int o = 0; o < R; o++) {
+            C acc = v[q][0];
+            for (int t = 1; t < R; t++) {
+                const C z = tw[((o*t) % R)*rstep];
+                acc.x += v[q][t].x*z.x - v[q][t].y*z.y;
+                acc.y += v[q][t].x*z.y + v[q][t].y*z.x;
+            }
+            line[j0 + o*Ns] = acc;
+        }
+    }
+    __syncwarp();
+}
+
 // Forward (e^{-i...}) unnormalised FFT of one shared-memory line by one warp.
-__device__ __forceinline__ void warpFft(float2* line, const FftPlan& plan, const float2* tw, int lane) {
+template <int NQ, typename C>
+__device__ __forceinline__ void warpFft(C* line, int n, unsigned long long factors, const C* tw, int lane) {
     int Ns = 1;
-    for (int f = 0; f < plan.nf; f++) {
-        const int R = plan.f[f];
+    for (; factors != 0; factors >>= 4) {
+        const int R = (int) (factors & 15);
         switch (R) {
-            case 2: fftPass<2>(line, plan.n, Ns, tw, lane); break;
-            case 3: fftPass<3>(line, plan.n, Ns, tw, lane); break;
-            case 4: fftPass<4>(line, plan.n, Ns, tw, lane); break;
-            case 5: fftPass<5>(line, plan.n, Ns, tw, lane); break;
-            case 7: fftPass<7>(line, plan.n, Ns, tw, lane); break;
-            case 11: fftPass<11>(line, plan.n, Ns, tw, lane); break;
-            default: fftPass<13>(line, plan.n, Ns, tw, lane); break;
+            case 2: fftPass<2, NQ>(line, n, Ns, tw, lane); break;
+            case 3: fftPass<3, NQ>(line, n, Ns, tw, lane); break;
+            case 4: fftPass<4, NQ>(line, n, Ns, tw, lane); break;
+            case 5: fftPass<5, NQ>(line, n, Ns, tw, lane); break;
+            case 7: fftPass<7, NQ>(line, n, Ns, tw, lane); break;
+            default: fftPassLarge(line, n, R, Ns, tw, lane); break;
         }
         Ns *= R;
     }
@@ -123,22 +165,25 @@ __device__ __forceinline__ void warpFft(float2* line, const FftPlan& plan, const
 // ---------------------------------------------------------------------------------------------
 // Spreading: one warp per (sorted) atom; lanes 0..24 own an (ix, iy) offset and walk the 5 z points.
 // Reference: pme_grid_spread_charge, ReferencePME.cpp:320-396 (forward-only spreading, :375-394).
+// T = float for force-only evaluations, double when slice energies are requested (cross-subset
+// structure-factor products cancel to ~1e-6 of their terms; see DESIGN.md "Precision").
 // ---------------------------------------------------------------------------------------------
 struct PmeArgs {
     int N, Npad, nS, nx, ny, nz, nzh;
     const uint4* posq; const float4* par;
-    float* grid; float2* gridC; const float* eterm;
-    unsigned long long* force; double* energy;
+    void* grid; const float* pot;
+    unsigned long long* force;
     float fscale[3];             // n_d / L_d
-    LambdaTable lam;
 };
 
-__device__ __forceinline__ void gridCoord(unsigned fixed, int n, int& index, float& frac) {
+template <typename T>
+__device__ __forceinline__ void gridCoord(unsigned fixed, int n, int& index, T& frac) {
     const unsigned long long t = (unsigned long long) fixed*(unsigned) n;     // frac * n in 32.32 fixed point
     index = (int) (t >> 32);
-    frac = (float) (unsigned) (t & 0xffffffffull)*(1.0f/4294967296.0f);
+    frac = (T) (unsigned) (t & 0xffffffffull)*(T) (1.0/4294967296.0);
 }
 
+template <typename T>
 __global__ void __launch_bounds__(256) k_spread(const PmeArgs a) {
     const int lane = threadIdx.x & 31;
     const int j = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
@@ -148,24 +193,24 @@ __global__ void __launch_bounds__(256) k_spread(const PmeArgs a) {
     const float q = __uint_as_float(p.w);
     // lanes 0-4 x, 5-9 y, 10-14 z: each lane keeps the weight lane%5 of "its" dimension
     const int dim = min(lane/5, 2), kk = lane % 5;
-    int index; float frac;
-    gridCoord(dim == 0 ? p.x : (dim == 1 ? p.y : p.z), dim == 0 ? a.nx : (dim == 1 ? a.ny : a.nz), index, frac);
-    float th[5], dth[5];
+    int index; T frac;
+    gridCoord<T>(dim == 0 ? p.x : (dim == 1 ? p.y : p.z), dim == 0 ? a.nx : (dim == 1 ? a.ny : a.nz), index, frac);
+    T th[5], dth[5];
     bspline5(frac, th, dth);
-    float mine = th[0];
+    T mine = th[0];
 #pragma unroll
     for (int k = 1; k < 5; k++) mine = kk == k ? th[k] : mine;
     const int ix0 = __shfl_sync(FULL_MASK, index, 0), iy0 = __shfl_sync(FULL_MASK, index, 5), iz0 = __shfl_sync(FULL_MASK, index, 10);
     const int ox = lane/5, oy = lane % 5;
-    const float tx = __shfl_sync(FULL_MASK, mine, min(ox, 4)), ty = __shfl_sync(FULL_MASK, mine, 5 + oy);
-    float tz[5];
+    const T tx = __shfl_sync(FULL_MASK, mine, min(ox, 4)), ty = __shfl_sync(FULL_MASK, mine, 5 + oy);
+    T tz[5];
 #pragma unroll
     for (int k = 0; k < 5; k++) tz[k] = __shfl_sync(FULL_MASK, mine, 10 + k);
     if (lane >= 25 || q == 0.f) return;
     int x = ix0 + ox; x -= x >= a.nx ? a.nx : 0;
     int y = iy0 + oy; y -= y >= a.ny ? a.ny : 0;
-    float* row = a.grid + (((size_t) subset*a.nx + x)*a.ny + y)*a.nz;
-    const float w = q*tx*ty;
+    T* row = (T*) a.grid + (((size_t) subset*a.nx + x)*a.ny + y)*a.nz;
+    const T w = (T) q*tx*ty;
 #pragma unroll
     for (int k = 0; k < 5; k++) {
         int z = iz0 + k; z -= z >= a.nz ? a.nz : 0;
@@ -178,96 +223,108 @@ __global__ void __launch_bounds__(256) k_spread(const PmeArgs a) {
 // ---------------------------------------------------------------------------------------------
 struct FftArgs {
     int nS, nx, ny, nz, nzh;
-    FftPlan plan;
-    const float2* tw;            // twiddles of this dimension: exp(-2 pi i k / n)
-    float* grid; float2* gridC; const float* eterm;
+    int n;                       // length of the dimension this launch transforms
+    unsigned long long factors;  // its radices, 4 bits each
+    const void* tw;              // twiddles of this dimension: exp(-2 pi i k / n), precision T
+    void* grid; void* gridC; const void* eterm;
+    float* pot;                  // real-space potential grid (always float; read by the gather)
     double* energy;
     int wantEnergy;
     LambdaTable lam;
 };
 
+template <typename T, int NQ>
 __global__ void __launch_bounds__(256) k_fft_z_fwd(const FftArgs a) {
-    extern __shared__ float2 sm[];
+    typedef typename Cx<T>::type C;
+    extern __shared__ double2 smRaw[];
+    C* sm = (C*) smRaw;
     const int n = a.nz, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float2* tw = sm;
-    float2* line = sm + n + (size_t) warp*n;
-    for (int k = threadIdx.x; k < n; k += blockDim.x) tw[k] = a.tw[k];
+    C* tw = sm;
+    C* line = sm + n + (size_t) warp*n;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) tw[k] = ((const C*) a.tw)[k];
     __syncthreads();
     const int halfY = (a.ny + 1) >> 1;
     const int pair = blockIdx.x*8 + warp;
     if (pair >= a.nS*a.nx*halfY) return;
     const int sx = pair/halfY, y0 = 2*(pair - sx*halfY), y1 = y0 + 1;
-    const float* r0 = a.grid + ((size_t) sx*a.ny + y0)*n;
-    const float* r1 = r0 + n;
-    for (int z = lane; z < n; z += 32) line[z] = make_float2(r0[z], y1 < a.ny ? r1[z] : 0.f);
+    const T* r0 = (const T*) a.grid + ((size_t) sx*a.ny + y0)*n;
+    const T* r1 = r0 + n;
+    for (int z = lane; z < n; z += 32) line[z] = mk(r0[z], y1 < a.ny ? r1[z] : (T) 0);
     __syncwarp();
-    warpFft(line, a.plan, tw, lane);
-    float2* o0 = a.gridC + ((size_t) sx*a.ny + y0)*a.nzh;
-    float2* o1 = o0 + a.nzh;
+    warpFft<NQ>(line, a.n, a.factors, tw, lane);
+    C* o0 = (C*) a.gridC + ((size_t) sx*a.ny + y0)*a.nzh;
+    C* o1 = o0 + a.nzh;
+    const T half = (T) 0.5;
     for (int k = lane; k < a.nzh; k += 32) {
-        const float2 zk = line[k], zn = line[k == 0 ? 0 : n - k];
-        o0[k] = make_float2(0.5f*(zk.x + zn.x), 0.5f*(zk.y - zn.y));
-        if (y1 < a.ny) o1[k] = make_float2(0.5f*(zk.y + zn.y), -0.5f*(zk.x - zn.x));
+        const C zk = line[k], zn = line[k == 0 ? 0 : n - k];
+        o0[k] = mk(half*(zk.x + zn.x), half*(zk.y - zn.y));
+        if (y1 < a.ny) o1[k] = mk(half*(zk.y + zn.y), -half*(zk.x - zn.x));
     }
 }
 
-// z transform, half complex -> real (inverse, unnormalised), two lines per complex FFT.
+// z transform, half complex -> real (inverse, unnormalised), two lines per complex FFT; writes the
+// float potential grid the gather reads.
+template <typename T, int NQ>
 __global__ void __launch_bounds__(256) k_fft_z_inv(const FftArgs a) {
-    extern __shared__ float2 sm[];
+    typedef typename Cx<T>::type C;
+    extern __shared__ double2 smRaw[];
+    C* sm = (C*) smRaw;
     const int n = a.nz, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float2* tw = sm;
-    float2* line = sm + n + (size_t) warp*n;
-    for (int k = threadIdx.x; k < n; k += blockDim.x) tw[k] = a.tw[k];
+    C* tw = sm;
+    C* line = sm + n + (size_t) warp*n;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) tw[k] = ((const C*) a.tw)[k];
     __syncthreads();
     const int halfY = (a.ny + 1) >> 1;
     const int pair = blockIdx.x*8 + warp;
     if (pair >= a.nS*a.nx*halfY) return;
     const int sx = pair/halfY, y0 = 2*(pair - sx*halfY), y1 = y0 + 1;
-    const float2* i0 = a.gridC + ((size_t) sx*a.ny + y0)*a.nzh;
-    const float2* i1 = i0 + a.nzh;
+    const C* i0 = (const C*) a.gridC + ((size_t) sx*a.ny + y0)*a.nzh;
+    const C* i1 = i0 + a.nzh;
     for (int k = lane; k < a.nzh; k += 32) {
-        const float2 A = i0[k], B = y1 < a.ny ? i1[k] : make_float2(0.f, 0.f);
-        line[k] = make_float2(A.x - B.y, -(A.y + B.x));                 // conj(A + iB)
-        if (k > 0 && 2*k < n) line[n - k] = make_float2(A.x + B.y, A.y - B.x);   // conj(conj(A) + i conj(B))
+        const C A = i0[k], B = y1 < a.ny ? i1[k] : mk((T) 0, (T) 0);
+        line[k] = mk(A.x - B.y, -(A.y + B.x));                          // conj(A + iB)
+        if (k > 0 && 2*k < n) line[n - k] = mk(A.x + B.y, A.y - B.x);   // conj(conj(A) + i conj(B))
     }
     __syncwarp();
-    warpFft(line, a.plan, tw, lane);
-    float* r0 = a.grid + ((size_t) sx*a.ny + y0)*n;
+    warpFft<NQ>(line, a.n, a.factors, tw, lane);
+    float* r0 = a.pot + ((size_t) sx*a.ny + y0)*n;
     float* r1 = r0 + n;
     for (int z = lane; z < n; z += 32) {
-        const float2 w = line[z];
-        r0[z] = w.x;
-        if (y1 < a.ny) r1[z] = -w.y;
+        const C w = line[z];
+        r0[z] = (float) w.x;
+        if (y1 < a.ny) r1[z] = (float) -w.y;
     }
 }
 
 // y transform on the half spectrum, in place.  CTA = one (subset, x) plane x 16 consecutive kz.
-template <bool INVERSE>
+template <typename T, int NQ, bool INVERSE>
 __global__ void __launch_bounds__(512) k_fft_y(const FftArgs a) {
-    extern __shared__ float2 sm[];
+    typedef typename Cx<T>::type C;
+    extern __shared__ double2 smRaw[];
+    C* sm = (C*) smRaw;
     const int n = a.ny, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int stride = n + 1;
-    float2* tw = sm;
-    float2* lines = sm + n;
-    for (int k = threadIdx.x; k < n; k += blockDim.x) tw[k] = a.tw[k];
+    C* tw = sm;
+    C* lines = sm + n;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) tw[k] = ((const C*) a.tw)[k];
     const int chunks = (a.nzh + 15) >> 4;
     const int sx = blockIdx.x/chunks, k0 = (blockIdx.x - sx*chunks)*16;
-    float2* base = a.gridC + (size_t) sx*n*a.nzh;
+    C* base = (C*) a.gridC + (size_t) sx*n*a.nzh;
     for (int idx = threadIdx.x; idx < n*16; idx += blockDim.x) {
         const int l = idx & 15, y = idx >> 4;
         if (k0 + l < a.nzh) {
-            float2 v = base[(size_t) y*a.nzh + k0 + l];
+            C v = base[(size_t) y*a.nzh + k0 + l];
             if (INVERSE) v.y = -v.y;
             lines[l*stride + y] = v;
         }
     }
     __syncthreads();
-    if (k0 + warp < a.nzh) warpFft(lines + warp*stride, a.plan, tw, lane);
+    if (k0 + warp < a.nzh) warpFft<NQ>(lines + warp*stride, a.n, a.factors, tw, lane);
     __syncthreads();
     for (int idx = threadIdx.x; idx < n*16; idx += blockDim.x) {
         const int l = idx & 15, y = idx >> 4;
         if (k0 + l < a.nzh) {
-            float2 v = lines[l*stride + y];
+            C v = lines[l*stride + y];
             if (INVERSE) v.y = -v.y;
             base[(size_t) y*a.nzh + k0 + l] = v;
         }
@@ -280,27 +337,30 @@ __global__ void __launch_bounds__(512) k_fft_y(const FftArgs a) {
 // half spectrum counts twice except on the kz = 0 and kz = nz/2 planes).  The reference then scales
 // every subset grid by eterm and lets the gather mix subsets with lambda (:681-687); here the mix
 // happens in k space.
-template <int NS>
+template <typename T, int NQ, int NS>
 __global__ void __launch_bounds__(256) k_fft_x_conv(const FftArgs a) {
-    extern __shared__ float2 sm[];
+    typedef typename Cx<T>::type C;
+    extern __shared__ double2 smRaw[];
+    C* sm = (C*) smRaw;
     __shared__ double shE[MAX_SLICES];
     const int n = a.nx, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int stride = n + 1;
-    float2* tw = sm;
-    float2* lines = sm + n;                       // [s][l][x]
-    for (int k = threadIdx.x; k < n; k += blockDim.x) tw[k] = a.tw[k];
+    C* tw = sm;
+    C* lines = sm + n;                       // [s][l][x]
+    for (int k = threadIdx.x; k < n; k += blockDim.x) tw[k] = ((const C*) a.tw)[k];
     if (threadIdx.x < MAX_SLICES) shE[threadIdx.x] = 0.0;
     const int chunks = (a.nzh + 7) >> 3;
     const int y = blockIdx.x/chunks, k0 = (blockIdx.x - y*chunks)*8;
     const int nS = a.nS;
+    C* gridC = (C*) a.gridC;
     for (int idx = threadIdx.x; idx < nS*n*8; idx += blockDim.x) {
         const int l = idx & 7, x = (idx >> 3) % n, s = idx/(8*n);
         if (k0 + l < a.nzh)
-            lines[(s*8 + l)*stride + x] = a.gridC[(((size_t) s*n + x)*a.ny + y)*a.nzh + k0 + l];
+            lines[(s*8 + l)*stride + x] = gridC[(((size_t) s*n + x)*a.ny + y)*a.nzh + k0 + l];
     }
     __syncthreads();
     for (int L = warp; L < nS*8; L += 8)
-        if (k0 + (L & 7) < a.nzh) warpFft(lines + L*stride, a.plan, tw, lane);
+        if (k0 + (L & 7) < a.nzh) warpFft<NQ>(lines + L*stride, a.n, a.factors, tw, lane);
     __syncthreads();
     double e[NS*(NS+1)/2];
 #pragma unroll
@@ -308,43 +368,43 @@ __global__ void __launch_bounds__(256) k_fft_x_conv(const FftArgs a) {
     for (int idx = threadIdx.x; idx < n*8; idx += blockDim.x) {
         const int l = idx & 7, x = idx >> 3, k = k0 + l;
         if (k >= a.nzh) continue;
-        const float et = a.eterm[((size_t) x*a.ny + y)*a.nzh + k];
-        float2 S[NS];
+        const T et = ((const T*) a.eterm)[((size_t) x*a.ny + y)*a.nzh + k];
+        C S[NS];
 #pragma unroll
-        for (int s = 0; s < NS; s++) S[s] = s < nS ? lines[(s*8 + l)*stride + x] : make_float2(0.f, 0.f);
+        for (int s = 0; s < NS; s++) S[s] = s < nS ? lines[(s*8 + l)*stride + x] : mk((T) 0, (T) 0);
         if (a.wantEnergy) {
-            const float w = (k == 0 || 2*k == a.nz) ? 1.f : 2.f;
+            const T w = (k == 0 || 2*k == a.nz) ? (T) 1 : (T) 2;
 #pragma unroll
             for (int sb = 0; sb < NS; sb++)
 #pragma unroll
                 for (int sa = 0; sa <= sb; sa++) {
-                    const float prod = S[sa].x*S[sb].x + S[sa].y*S[sb].y;
-                    e[sb*(sb+1)/2 + sa] += (double) ((sa == sb ? 0.5f : 1.f)*w*et*prod);
+                    const T prod = S[sa].x*S[sb].x + S[sa].y*S[sb].y;
+                    e[sb*(sb+1)/2 + sa] += (double) ((sa == sb ? (T) 0.5 : (T) 1)*w*et*prod);
                 }
         }
 #pragma unroll
         for (int si = 0; si < NS; si++) {
             if (si >= nS) break;
-            float gx = 0.f, gy = 0.f;
+            T gx = 0, gy = 0;
 #pragma unroll
             for (int sj = 0; sj < NS; sj++) {
-                const float lam = a.lam.c[triSlice(si, sj)];
-                gx = fmaf(lam, S[sj].x, gx);
-                gy = fmaf(lam, S[sj].y, gy);
+                const T lam = (T) a.lam.c[triSlice(si, sj)];
+                gx += lam*S[sj].x;
+                gy += lam*S[sj].y;
             }
-            lines[(si*8 + l)*stride + x] = make_float2(et*gx, -et*gy);      // conjugated for the inverse pass
+            lines[(si*8 + l)*stride + x] = mk(et*gx, -et*gy);      // conjugated for the inverse pass
         }
     }
     __syncthreads();
     for (int L = warp; L < nS*8; L += 8)
-        if (k0 + (L & 7) < a.nzh) warpFft(lines + L*stride, a.plan, tw, lane);
+        if (k0 + (L & 7) < a.nzh) warpFft<NQ>(lines + L*stride, a.n, a.factors, tw, lane);
     __syncthreads();
     for (int idx = threadIdx.x; idx < nS*n*8; idx += blockDim.x) {
         const int l = idx & 7, x = (idx >> 3) % n, s = idx/(8*n);
         if (k0 + l < a.nzh) {
-            float2 v = lines[(s*8 + l)*stride + x];
+            C v = lines[(s*8 + l)*stride + x];
             v.y = -v.y;
-            a.gridC[(((size_t) s*n + x)*a.ny + y)*a.nzh + k0 + l] = v;
+            gridC[(((size_t) s*n + x)*a.ny + y)*a.nzh + k0 + l] = v;
         }
     }
     if (a.wantEnergy) {
@@ -373,7 +433,7 @@ __global__ void __launch_bounds__(256) k_gather(const PmeArgs a) {
     const int subset = __float_as_int(a.par[j].z);
     const int dim = min(lane/5, 2), kk = lane % 5;
     int index; float frac;
-    gridCoord(dim == 0 ? p.x : (dim == 1 ? p.y : p.z), dim == 0 ? a.nx : (dim == 1 ? a.ny : a.nz), index, frac);
+    gridCoord<float>(dim == 0 ? p.x : (dim == 1 ? p.y : p.z), dim == 0 ? a.nx : (dim == 1 ? a.ny : a.nz), index, frac);
     float th[5], dth[5];
     bspline5(frac, th, dth);
     float mine = th[0], dmine = dth[0];
@@ -390,7 +450,7 @@ __global__ void __launch_bounds__(256) k_gather(const PmeArgs a) {
     if (lane < 25) {
         int x = ix0 + ox; x -= x >= a.nx ? a.nx : 0;
         int y = iy0 + oy; y -= y >= a.ny ? a.ny : 0;
-        const float* row = a.grid + (((size_t) subset*a.nx + x)*a.ny + y)*a.nz;
+        const float* row = a.pot + (((size_t) subset*a.nx + x)*a.ny + y)*a.nz;
         float s0 = 0.f, s1 = 0.f;
 #pragma unroll
         for (int k = 0; k < 5; k++) {
@@ -415,18 +475,19 @@ __global__ void __launch_bounds__(256) k_gather(const PmeArgs a) {
 // Influence function eterm(k) = exp(-pi^2 m^2 / alpha^2) / (pi V m^2 Bx By Bz), ReferencePME.cpp:426-471
 // (without ONE_4PI_EPS0, which the charges carry).  Recomputed only when the box changes.
 // ---------------------------------------------------------------------------------------------
+template <typename T>
 __global__ void k_eterm(int nx, int ny, int nz, int nzh, double3 invBox, double volume, double alpha,
-                        const double* __restrict__ moduli, float* __restrict__ eterm) {
+                        const double* __restrict__ moduli, T* __restrict__ eterm) {
     const size_t idx = (size_t) blockIdx.x*blockDim.x + threadIdx.x;
     if (idx >= (size_t) nx*ny*nzh) return;
     const int kz = (int) (idx % nzh), ky = (int) ((idx/nzh) % ny), kx = (int) (idx/((size_t) nzh*ny));
-    if (kx == 0 && ky == 0 && kz == 0) { eterm[idx] = 0.f; return; }
+    if (kx == 0 && ky == 0 && kz == 0) { eterm[idx] = (T) 0; return; }
     const double mx = (kx < (nx+1)/2 ? kx : kx - nx)*invBox.x;
     const double my = (ky < (ny+1)/2 ? ky : ky - ny)*invBox.y;
     const double mz = (kz < (nz+1)/2 ? kz : kz - nz)*invBox.z;
     const double m2 = mx*mx + my*my + mz*mz;
     const double denom = m2*kPi*volume*moduli[kx]*moduli[nx + ky]*moduli[nx + ny + kz];
-    eterm[idx] = (float) (exp(-kPi*kPi*m2/(alpha*alpha))/denom);
+    eterm[idx] = (T) (exp(-kPi*kPi*m2/(alpha*alpha))/denom);
 }
 
 int prepareEterm(Context& c) {
@@ -435,14 +496,60 @@ int prepareEterm(Context& c) {
     const int nx = c.grid[0], ny = c.grid[1], nz = c.grid[2], nzh = nz/2 + 1;
     const size_t total = (size_t) nx*ny*nzh;
     NBS_CUDA_CHECK(c.dEterm.ensure(total));
-    k_eterm<<<(unsigned) ((total + 255)/256), 256, 0, c.stream>>>(nx, ny, nz, nzh, make_double3(g.invBox[0], g.invBox[1], g.invBox[2]),
-                                                                  g.box[0]*g.box[1]*g.box[2], c.alpha, c.dModuli.d, c.dEterm.d);
-    c.launches++;
+    NBS_CUDA_CHECK(c.dEtermD.ensure(total));
+    const double3 inv = make_double3(g.invBox[0], g.invBox[1], g.invBox[2]);
+    const double volume = g.box[0]*g.box[1]*g.box[2];
+    k_eterm<float><<<(unsigned) ((total + 255)/256), 256, 0, c.stream>>>(nx, ny, nz, nzh, inv, volume, c.alpha, c.dModuli.d, c.dEterm.d);
+    k_eterm<double><<<(unsigned) ((total + 255)/256), 256, 0, c.stream>>>(nx, ny, nz, nzh, inv, volume, c.alpha, c.dModuli.d, c.dEtermD.d);
+    c.launches += 2;
     for (int k = 0; k < 3; k++) c.etermBox[k] = g.box[k];
     return NBS_OK;
 }
 
-int launchPme(Context& c, bool wantEnergy) {
+template <typename T, int NQ>
+static void launchFftChain(Context& c, FftArgs f, const FftPlan& px, const FftPlan& py, const FftPlan& pz,
+                           size_t smX, size_t smY, size_t smZ) {
+    typedef typename Cx<T>::type C;
+    cudaStream_t st = c.stream;
+    const int nx = c.grid[0], ny = c.grid[1], nz = c.grid[2], nzh = nz/2 + 1;
+    const C* tw = (const C*) (sizeof(T) == 8 ? (const void*) c.dTwiddleD.d : (const void*) c.dTwiddle.d);
+    const int pairs = c.nS*nx*((ny + 1)/2);
+    const int yCtas = c.nS*nx*((nzh + 15)/16), xCtas = ny*((nzh + 7)/8);
+    static bool attr = false;
+    if (!attr) {
+        const int big = 200*1024;
+        cudaFuncSetAttribute(k_fft_z_fwd<T, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(k_fft_z_inv<T, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(k_fft_y<T, NQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(k_fft_y<T, NQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(k_fft_x_conv<T, NQ, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(k_fft_x_conv<T, NQ, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(k_fft_x_conv<T, NQ, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(k_fft_x_conv<T, NQ, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(k_fft_x_conv<T, NQ, MAX_SUBSETS>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        attr = true;
+    }
+    f.n = pz.n; f.factors = pz.packed; f.tw = tw + nx + ny;
+    k_fft_z_fwd<T, NQ><<<(pairs + 7)/8, 256, smZ, st>>>(f);
+    f.n = py.n; f.factors = py.packed; f.tw = tw + nx;
+    k_fft_y<T, NQ, false><<<yCtas, 512, smY, st>>>(f);
+    f.n = px.n; f.factors = px.packed; f.tw = tw;
+    switch (c.nS) {
+        case 1: k_fft_x_conv<T, NQ, 1><<<xCtas, 256, smX, st>>>(f); break;
+        case 2: k_fft_x_conv<T, NQ, 2><<<xCtas, 256, smX, st>>>(f); break;
+        case 3: k_fft_x_conv<T, NQ, 3><<<xCtas, 256, smX, st>>>(f); break;
+        case 4: k_fft_x_conv<T, NQ, 4><<<xCtas, 256, smX, st>>>(f); break;
+        default: k_fft_x_conv<T, NQ, MAX_SUBSETS><<<xCtas, 256, smX, st>>>(f); break;
+    }
+    f.n = py.n; f.factors = py.packed; f.tw = tw + nx;
+    k_fft_y<T, NQ, true><<<yCtas, 512, smY, st>>>(f);
+    f.n = pz.n; f.factors = pz.packed; f.tw = tw + nx + ny;
+    k_fft_z_inv<T, NQ><<<(pairs + 7)/8, 256, smZ, st>>>(f);
+    c.launches += 5;
+}
+
+template <typename T>
+static int launchPmeT(Context& c, bool wantEnergy) {
     const int nx = c.grid[0], ny = c.grid[1], nz = c.grid[2], nzh = nz/2 + 1;
     const size_t G = (size_t) nx*ny*nz;
     cudaStream_t st = c.stream;
@@ -453,71 +560,49 @@ int launchPme(Context& c, bool wantEnergy) {
     }
     int status = prepareEterm(c);
     if (status != NBS_OK) return status;
-    NBS_CUDA_CHECK(cudaMemsetAsync(c.dGrid.d, 0, sizeof(float)*G*c.nS, st));
+    NBS_CUDA_CHECK(cudaMemsetAsync(c.dGrid.d, 0, sizeof(T)*G*c.nS, st));
     PmeArgs p;
     p.N = c.N; p.Npad = c.Npad; p.nS = c.nS; p.nx = nx; p.ny = ny; p.nz = nz; p.nzh = nzh;
-    p.posq = c.dPosq.d; p.par = c.dPar.d; p.grid = c.dGrid.d; p.gridC = c.dGridC.d; p.eterm = c.dEterm.d;
-    p.force = c.dForce.d; p.energy = c.dEnergy.d;
+    p.posq = c.dPosq.d; p.par = c.dPar.d; p.grid = c.dGrid.d; p.pot = c.dPot.d;
+    p.force = c.dForce.d;
     for (int k = 0; k < 3; k++) p.fscale[k] = (float) (c.grid[k]*c.geom.invBox[k]);
-    for (int s = 0; s < MAX_SLICES; s++) {
-        p.lam.c[s] = s < c.nSl ? (float) c.lambdas[2*s] : 1.f;
-        p.lam.v[s] = s < c.nSl ? (float) c.lambdas[2*s+1] : 1.f;
-    }
     const int atomCtas = (c.N + 7)/8;
-    k_spread<<<atomCtas, 256, 0, st>>>(p);
+    k_spread<T><<<atomCtas, 256, 0, st>>>(p);
     c.launches++;
     timerMark(c, "spread");
 
     FftArgs f;
     f.nS = c.nS; f.nx = nx; f.ny = ny; f.nz = nz; f.nzh = nzh;
-    f.grid = c.dGrid.d; f.gridC = c.dGridC.d; f.eterm = c.dEterm.d; f.energy = c.dEnergy.d;
+    f.grid = c.dGrid.d; f.gridC = c.dGridC.d; f.pot = c.dPot.d; f.energy = c.dEnergy.d;
+    f.eterm = sizeof(T) == 8 ? (const void*) c.dEtermD.d : (const void*) c.dEterm.d;
     f.wantEnergy = wantEnergy ? 1 : 0;
-    f.lam = p.lam;
-    const int pairs = c.nS*nx*((ny + 1)/2);
-    // z forward
-    f.plan = pz; f.tw = c.dTwiddle.d + nx + ny;
-    const size_t smZ = sizeof(float2)*(size_t) nz*9;
-    // y
-    const size_t smY = sizeof(float2)*((size_t) ny + 16*((size_t) ny + 1));
-    const size_t smX = sizeof(float2)*((size_t) nx + (size_t) c.nS*8*((size_t) nx + 1));
-    if (!c.fftAttrSet) {
-        cudaFuncSetAttribute(k_fft_z_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 200*1024);
-        cudaFuncSetAttribute(k_fft_z_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, 200*1024);
-        cudaFuncSetAttribute(k_fft_y<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200*1024);
-        cudaFuncSetAttribute(k_fft_y<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200*1024);
-        cudaFuncSetAttribute(k_fft_x_conv<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200*1024);
-        cudaFuncSetAttribute(k_fft_x_conv<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200*1024);
-        cudaFuncSetAttribute(k_fft_x_conv<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200*1024);
-        cudaFuncSetAttribute(k_fft_x_conv<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200*1024);
-        cudaFuncSetAttribute(k_fft_x_conv<MAX_SUBSETS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200*1024);
-        c.fftAttrSet = true;
+    for (int s = 0; s < MAX_SLICES; s++) {
+        f.lam.c[s] = s < c.nSl ? (float) c.lambdas[2*s] : 1.f;
+        f.lam.v[s] = s < c.nSl ? (float) c.lambdas[2*s+1] : 1.f;
     }
+    const size_t cs = 2*sizeof(T);
+    const size_t smZ = cs*(size_t) nz*9;
+    const size_t smY = cs*((size_t) ny + 16*((size_t) ny + 1));
+    const size_t smX = cs*((size_t) nx + (size_t) c.nS*8*((size_t) nx + 1));
     if (smX > 200*1024 || smY > 200*1024 || smZ > 200*1024) {
         setError("PME grid too large for the shared-memory FFT");
         return NBS_ERR_UNSUPPORTED;
     }
-    k_fft_z_fwd<<<(pairs + 7)/8, 256, smZ, st>>>(f);
-    f.plan = py; f.tw = c.dTwiddle.d + nx;
-    k_fft_y<false><<<c.nS*nx*((nzh + 15)/16), 512, smY, st>>>(f);
-    f.plan = px; f.tw = c.dTwiddle.d;
-    const int xCtas = ny*((nzh + 7)/8);
-    switch (c.nS) {
-        case 1: k_fft_x_conv<1><<<xCtas, 256, smX, st>>>(f); break;
-        case 2: k_fft_x_conv<2><<<xCtas, 256, smX, st>>>(f); break;
-        case 3: k_fft_x_conv<3><<<xCtas, 256, smX, st>>>(f); break;
-        case 4: k_fft_x_conv<4><<<xCtas, 256, smX, st>>>(f); break;
-        default: k_fft_x_conv<MAX_SUBSETS><<<xCtas, 256, smX, st>>>(f); break;
-    }
-    f.plan = py; f.tw = c.dTwiddle.d + nx;
-    k_fft_y<true><<<c.nS*nx*((nzh + 15)/16), 512, smY, st>>>(f);
-    f.plan = pz; f.tw = c.dTwiddle.d + nx + ny;
-    k_fft_z_inv<<<(pairs + 7)/8, 256, smZ, st>>>(f);
-    c.launches += 5;
+    const int nq = std::max(px.nq, std::max(py.nq, pz.nq));
+    if (nq <= 1) launchFftChain<T, 1>(c, f, px, py, pz, smX, smY, smZ);
+    else if (nq <= 2) launchFftChain<T, 2>(c, f, px, py, pz, smX, smY, smZ);
+    else if (nq <= 4) launchFftChain<T, 4>(c, f, px, py, pz, smX, smY, smZ);
+    else launchFftChain<T, 8>(c, f, px, py, pz, smX, smY, smZ);
     timerMark(c, "fft_conv");
     k_gather<<<atomCtas, 256, 0, st>>>(p);
     c.launches++;
     timerMark(c, "gather");
     return NBS_OK;
+}
+
+// Energies requested -> double-precision grids and transforms; forces only -> single precision.
+int launchPme(Context& c, bool wantEnergy) {
+    return wantEnergy ? launchPmeT<double>(c, true) : launchPmeT<float>(c, false);
 }
 
 } // namespace nbs

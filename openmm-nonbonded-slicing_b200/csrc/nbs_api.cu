@@ -233,11 +233,13 @@ int uploadPmeTables(Context& c) {
     bsplineModuli(ny, c.hModuli.data() + nx);
     bsplineModuli(nz, c.hModuli.data() + nx + ny);
     std::vector<float2> tw(total);
+    std::vector<double2> twD(total);
     int off = 0;
     for (int n : {nx, ny, nz}) {
         for (int k = 0; k < n; k++) {
             double ang = -2.0*kPi*k/n;
             tw[off+k] = make_float2((float) cos(ang), (float) sin(ang));
+            twD[off+k] = make_double2(cos(ang), sin(ang));
         }
         off += n;
     }
@@ -245,9 +247,12 @@ int uploadPmeTables(Context& c) {
     NBS_CUDA_CHECK(c.dTwiddle.ensure(total));
     NBS_CUDA_CHECK(cudaMemcpy(c.dModuli.d, c.hModuli.data(), sizeof(double)*total, cudaMemcpyHostToDevice));
     NBS_CUDA_CHECK(cudaMemcpy(c.dTwiddle.d, tw.data(), sizeof(float2)*total, cudaMemcpyHostToDevice));
+    NBS_CUDA_CHECK(c.dTwiddleD.ensure(total));
+    NBS_CUDA_CHECK(cudaMemcpy(c.dTwiddleD.d, twD.data(), sizeof(double2)*total, cudaMemcpyHostToDevice));
     const size_t G = (size_t) nx*ny*nz, Gh = (size_t) nx*ny*(nz/2+1);
     NBS_CUDA_CHECK(c.dGrid.ensure(G*c.nS));
     NBS_CUDA_CHECK(c.dGridC.ensure(Gh*c.nS));
+    NBS_CUDA_CHECK(c.dPot.ensure(G*c.nS));
     return NBS_OK;
 }
 
@@ -324,6 +329,7 @@ static void releaseAll(Context& c) {
     c.dBlkLo.release(); c.dBlkHi.release(); c.dExclRange.release(); c.dJList.release(); c.dJCount.release();
     c.dXList.release(); c.dXCount.release(); c.dXMask.release(); c.dCounters.release(); c.dForce.release();
     c.dEnergy.release(); c.dGrid.release(); c.dGridC.release(); c.dEterm.release(); c.dModuli.release();
+    c.dPot.release(); c.dEtermD.release(); c.dTwiddleD.release();
     c.dTwiddle.release(); c.dPairStats.release(); c.dPairDump.release();
     if (c.hCounters) cudaFreeHost(c.hCounters);
     if (c.hEnergy) cudaFreeHost(c.hEnergy);

@@ -46,18 +46,19 @@ __device__ __forceinline__ unsigned long long pairHash(unsigned first, unsigned 
 
 // Order-5 cardinal B-spline weights and derivatives for fractional offset w, following the Darden
 // recursion the reference uses (ReferencePME.cpp:280-314), in single precision.
-__device__ __forceinline__ void bspline5(float dr, float* data, float* ddata) {
-    data[4] = 0.f; data[1] = dr; data[0] = 1.f - dr;
+template <typename T>
+__device__ __forceinline__ void bspline5(T dr, T* data, T* ddata) {
+    data[4] = (T) 0; data[1] = dr; data[0] = (T) 1 - dr;
     // k = 3
-    data[2] = 0.5f*dr*data[1];
-    data[1] = 0.5f*((dr+1.f)*data[0] + (2.f-dr)*data[1]);
-    data[0] = 0.5f*(1.f-dr)*data[0];
+    data[2] = (T) 0.5*dr*data[1];
+    data[1] = (T) 0.5*((dr+(T) 1)*data[0] + ((T) 2-dr)*data[1]);
+    data[0] = (T) 0.5*((T) 1-dr)*data[0];
     // k = 4
-    const float third = 1.f/3.f;
+    const T third = (T) (1.0/3.0);
     data[3] = third*dr*data[2];
-    data[2] = third*((dr+1.f)*data[1] + (3.f-dr)*data[2]);
-    data[1] = third*((dr+2.f)*data[0] + (2.f-dr)*data[1]);
-    data[0] = third*(1.f-dr)*data[0];
+    data[2] = third*((dr+(T) 1)*data[1] + ((T) 3-dr)*data[2]);
+    data[1] = third*((dr+(T) 2)*data[0] + ((T) 2-dr)*data[1]);
+    data[0] = third*((T) 1-dr)*data[0];
     // differentiate
     ddata[0] = -data[0];
     ddata[1] = data[0] - data[1];
@@ -65,11 +66,11 @@ __device__ __forceinline__ void bspline5(float dr, float* data, float* ddata) {
     ddata[3] = data[2] - data[3];
     ddata[4] = data[3] - data[4];
     // k = 5
-    data[4] = 0.25f*dr*data[3];
-    data[3] = 0.25f*((dr+1.f)*data[2] + (4.f-dr)*data[3]);
-    data[2] = 0.25f*((dr+2.f)*data[1] + (3.f-dr)*data[2]);
-    data[1] = 0.25f*((dr+3.f)*data[0] + (2.f-dr)*data[1]);
-    data[0] = 0.25f*(1.f-dr)*data[0];
+    data[4] = (T) 0.25*dr*data[3];
+    data[3] = (T) 0.25*((dr+(T) 1)*data[2] + ((T) 4-dr)*data[3]);
+    data[2] = (T) 0.25*((dr+(T) 2)*data[1] + ((T) 3-dr)*data[2]);
+    data[1] = (T) 0.25*((dr+(T) 3)*data[0] + ((T) 2-dr)*data[1]);
+    data[0] = (T) 0.25*((T) 1-dr)*data[0];
 }
 
 } // namespace nbs

@@ -124,9 +124,12 @@ struct Context {
     Buf<int> dCounters;                      // [0] nBlocks, [1] overflow flags, [2..] stats
     Buf<unsigned long long> dForce;          // [3][Npad]
     Buf<double> dEnergy;                     // [MAX_SLICES][2]
-    Buf<float> dGrid;
-    Buf<float2> dGridC;
+    Buf<double> dGrid;                       // charge grid [nS][nx][ny][nz] (double or float view)
+    Buf<double2> dGridC;                     // half spectrum [nS][nx][ny][nz/2+1] (double2 or float2 view)
+    Buf<float> dPot;                         // potential grid read by the gather
     Buf<float> dEterm;
+    Buf<double> dEtermD;
+    Buf<double2> dTwiddleD;
     Buf<double> dModuli;                     // [nx+ny+nz]
     Buf<float2> dTwiddle;                    // [nx+ny+nz]
     Buf<unsigned long long> dPairStats;      // [0] count, [1] hash

@@ -59,8 +59,9 @@ def random_system(nbs, rng, n=300, nsub=3, L=2.6, grid=(20, 20, 20), with_offset
         force.addExceptionParameterOffset("off", 2, 0.2, 0.01, 0.1)
     force.addGlobalParameter("lc", 0.7)
     force.addGlobalParameter("lv", 0.4)
-    force.addScalingParameter("lc", 0, 1, True, False)
-    force.addScalingParameter("lv", 0, 1, False, True)
+    other = 1 if nsub > 1 else 0
+    force.addScalingParameter("lc", 0, other, True, False)
+    force.addScalingParameter("lv", 0, other, False, True)
     force.addEnergyParameterDerivative("lc")
     force.addEnergyParameterDerivative("lv")
     system.addForce(force)

@@ -590,7 +590,7 @@ class CalcSlicedNonbondedForceKernel:
         raise NotImplementedError
 
 
-def build_desc(system, force, flags=0, device_index=0):
+def build_desc(system, force, flags=0, device_index=0, legal_grid=False):
     """Everything ReferenceCalcSlicedNonbondedForceKernel::initialize reads from the Force
     (platforms/reference/src/ReferenceNonbondedSlicingKernels.cpp:59-185), flattened into an
     nbs_system_desc.  Returns the abi.DescArrays that own the memory."""
@@ -603,6 +603,8 @@ def build_desc(system, force, flags=0, device_index=0):
     if method in (force.PME, force.LJPME):
         alpha, nx, ny, nz = SlicedNonbondedForceImpl.calcPMEParameters(system, force, False)
         grid = (nx, ny, nz)
+        if legal_grid:
+            grid = tuple(findLegalFFTDimension(g) for g in grid)
     dispersion = None
     if force.getUseDispersionCorrection():
         dispersion = SlicedNonbondedForceImpl.calcDispersionCorrections(system, force)
@@ -715,6 +717,21 @@ class SlicedKernelBase(CalcSlicedNonbondedForceKernel):
         raise OpenMMException("LJPME is not supported by this platform")
 
 
+def findLegalFFTDimension(minimum):
+    """Smallest size >= minimum whose prime factors are all <= 13 -- what the plugin's GPU platforms do
+    with the PME grid (platforms/common/include/FFT3DFactory.h:31-47, used at
+    CommonNonbondedSlicingKernels.cpp:441-443); the Reference platform keeps the size as given."""
+    n = max(int(minimum), 1)
+    while True:
+        m = n
+        for f in (2, 3, 5, 7, 11, 13):
+            while m % f == 0:
+                m //= f
+        if m == 1:
+            return n
+        n += 1
+
+
 class B200CalcSlicedNonbondedForceKernel(SlicedKernelBase):
     """The kernel of the "B200" platform: forwards to the CUDA library through the C ABI."""
 
@@ -724,7 +741,7 @@ class B200CalcSlicedNonbondedForceKernel(SlicedKernelBase):
         self.lib = abi.load_library()
 
     def _desc_options(self):
-        return {"flags": self.platform.flags, "device_index": self.platform.deviceIndex}
+        return {"flags": self.platform.flags, "device_index": self.platform.deviceIndex, "legal_grid": True}
 
     def _create(self):
         handle = C.c_void_p()

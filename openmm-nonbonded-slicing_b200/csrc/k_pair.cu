@@ -14,8 +14,12 @@
 //     floats relative to the i-block's corner, so the cutoff test sees ~1e-7 nm resolution at any box
 //     size, and a pair that lands within 2e-5 nm^2 of the cutoff is re-tested exactly in double from
 //     the integers -- this is what makes the interacting-pair set bit-exact against the oracle;
-//   * per-slice energies: 2*NS float accumulators per lane (the lane's own subset is fixed), folded
-//     with warp shuffles into doubles once per CTA.
+//   * per-slice energies (EMODE 2, the default): the in-cutoff pairs of a tile are compacted with warp
+//     ballots into a small shared-memory queue and their energies are evaluated in DOUBLE precision
+//     from the exact integer coordinates, 32 real pairs at a time (no lane is wasted on pairs beyond the
+//     cutoff).  Slice energies are sums of ~10^4..10^8 pair terms of both signs; single precision
+//     cannot deliver 1e-5 of a small net value (DESIGN.md "Precision").  EMODE 1 keeps the cheaper
+//     single-precision energies (2*NS float accumulators per lane), EMODE 0 computes forces only.
 // Bound: FP32 pipe (no tensor-core shaped work here).
 #include "nbs_internal.h"
 #include "nbs_device.cuh"
@@ -29,7 +33,8 @@ struct PairArgs {
     float rc2, alpha, krf, crf;
     float rswitch, rcut;
     int useSwitch;
-    double rc2d;
+    double rc2d, alphaD, krfD, crfD;
+    const double* q64;                   // sorted charges * sqrt(ONE_4PI_EPS0), double
     const int* counters;
     const int* blkFirst; const int* blkCount; const uint4* blkLo;
     const uint4* posq; const float4* par;
@@ -58,6 +63,63 @@ __device__ __forceinline__ float erfcxPoly(float t) {
     return p;
 }
 
+// erfc(x)*exp(x^2), x in [0, 6], in double: degree-14 polynomial in u = (8 t - 5)/3, t = 1/(1 + x/2);
+// relative error 1e-11 (fit against scipy.special.erfcx).
+__device__ __forceinline__ double erfcxPolyD(double t) {
+    const double u = fma(t, 2.6666666666666665, -1.6666666666666667);
+    double p = 6.52049290501760624e-09;
+    p = fma(p, u, 5.91610931414778049e-08);
+    p = fma(p, u, -2.22270786854985114e-07);
+    p = fma(p, u, -2.43147204892178188e-07);
+    p = fma(p, u, 2.86160851006960621e-06);
+    p = fma(p, u, -4.29950666125027918e-06);
+    p = fma(p, u, -2.27129828446940741e-05);
+    p = fma(p, u, 1.00552837184801405e-04);
+    p = fma(p, u, 1.33588067694989746e-04);
+    p = fma(p, u, -1.66536651372469141e-03);
+    p = fma(p, u, -1.67024495580285893e-03);
+    p = fma(p, u, 3.29934296618579967e-02);
+    p = fma(p, u, 1.69407590984921058e-01);
+    p = fma(p, u, 4.22187583608948647e-01);
+    p = fma(p, u, 3.78537416928964254e-01);
+    return p;
+}
+
+// Energy of one pair in double precision from the exact fixed-point coordinates (the wrapped integer
+// difference IS the minimum image for any pair inside the cutoff).  Formulas: ReferenceSlicedLJCoulombIxn.cpp
+// :376-396, 443-444 (PME) and :598-624 (reaction field), switch :380-384, 428-431.
+template <bool IS_PME>
+__device__ __forceinline__ void pairEnergyD(const uint4 fi, const uint4 fj, double qi, double qj, float sigi, float sigj,
+                                            float epsi, float epsj, const PairArgs& a, double& ec, double& ev) {
+    const double dx = (double) (int) (fj.x - fi.x)*a.dsx;
+    const double dy = (double) (int) (fj.y - fi.y)*a.dsy;
+    const double dz = (double) (int) (fj.z - fi.z)*a.dsz;
+    const double r2 = dx*dx + dy*dy + dz*dz;
+    double y = (double) rsqrtf((float) r2);
+    y = y*fma(-0.5*r2*y, y, 1.5);
+    y = y*fma(-0.5*r2*y, y, 1.5);
+    const double r = r2*y;
+    double s2 = ((double) sigi + (double) sigj)*y;
+    s2 *= s2;
+    const double s6 = s2*s2*s2;
+    ev = (double) epsi*(double) epsj*(s6 - 1.0)*s6;
+    if (a.useSwitch && r > (double) a.rswitch) {
+        const double u = (r - (double) a.rswitch)/((double) a.rcut - (double) a.rswitch);
+        ev *= 1.0 + u*u*u*(-10.0 + u*(15.0 - u*6.0));
+    }
+    const double qq = qi*qj;
+    if (IS_PME) {
+        const double x = a.alphaD*r;
+        const double d = fma(0.5, x, 1.0);
+        double t = (double) __frcp_rn((float) d);
+        t = t*fma(-d, t, 2.0);
+        t = t*fma(-d, t, 2.0);
+        ec = qq*y*exp(-x*x)*erfcxPolyD(t);
+    }
+    else
+        ec = qq*(y + a.krfD*r2 - a.crfD);
+}
+
 template <int NS>
 __device__ __forceinline__ float pick(const float (&v)[NS], int s) {
     float r = v[0];
@@ -67,8 +129,10 @@ __device__ __forceinline__ float pick(const float (&v)[NS], int s) {
 }
 
 // MODE 0: forces (+ energies when ENERGY); MODE 1: count + hash the interacting pairs; MODE 2: also dump them.
-template <int NS, bool ENERGY, bool IS_PME, int MODE>
+template <int NS, int EMODE, bool IS_PME, int MODE>
 __global__ void __launch_bounds__(PAIR_WARPS*32) k_pair(const PairArgs a) {
+    constexpr bool ENERGY = EMODE == 1;          // single-precision energies in the main loop
+    constexpr int NE = NS*(NS+1);                // 2 * number of slices
     const int b = blockIdx.x;
     if (b >= a.counters[0]) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -76,6 +140,13 @@ __global__ void __launch_bounds__(PAIR_WARPS*32) k_pair(const PairArgs a) {
     __shared__ float4 shPar[PAIR_WARPS][32];
     __shared__ float shF[PAIR_WARPS][3][32];
     __shared__ double shE[MAX_SLICES*2];
+    // double-precision energy path: the i-block's exact coordinates / charges, the tile's, and the queue
+    __shared__ uint4 shIFix[EMODE == 2 ? 32 : 1];
+    __shared__ double shIQ[EMODE == 2 ? 32 : 1];
+    __shared__ float2 shISE[EMODE == 2 ? 32 : 1];
+    __shared__ uint4 shJFix[EMODE == 2 ? PAIR_WARPS : 1][32];
+    __shared__ double shJQ[EMODE == 2 ? PAIR_WARPS : 1][32];
+    __shared__ unsigned short shQueue[EMODE == 2 ? PAIR_WARPS : 1][64];
 
     const int first = a.blkFirst[b], cnt = a.blkCount[b];
     const uint4 lo = a.blkLo[b];
@@ -91,6 +162,35 @@ __global__ void __launch_bounds__(PAIR_WARPS*32) k_pair(const PairArgs a) {
     float lamC[NS], lamV[NS];
 #pragma unroll
     for (int s = 0; s < NS; s++) { int sl = triSlice(si, s); lamC[s] = a.lam.c[sl]; lamV[s] = a.lam.v[sl]; }
+
+    double acc[NE];                               // EMODE 2: [slice][term], dynamically indexed
+    int qn = 0;
+    if (EMODE == 2) {
+#pragma unroll
+        for (int k = 0; k < NE; k++) acc[k] = 0.0;
+        if (warp == 0) {
+            shIFix[lane] = make_uint4(pi.x, pi.y, pi.z, (unsigned) si);
+            shIQ[lane] = iValid ? a.q64[first + lane] : 0.0;
+            shISE[lane] = make_float2(sigi, epsi);
+        }
+        __syncthreads();
+    }
+    const unsigned below = (1u << lane) - 1u;
+    // evaluate `count` queued pairs (one per lane) in double and add them to the lane's slice table
+    auto drainQueue = [&](int count) {
+        if (lane < count) {
+            const unsigned e = shQueue[warp][lane];
+            const int il = e >> 5, js = e & 31;
+            const uint4 fi = shIFix[il], fj = shJFix[warp][js];
+            const float2 sei = shISE[il];
+            const float4 prj = shPar[warp][js];
+            double ec, ev;
+            pairEnergyD<IS_PME>(fi, fj, shIQ[il], shJQ[warp][js], sei.x, prj.x, sei.y, prj.y, a, ec, ev);
+            const int sl = triSlice((int) fi.w, (int) fj.w);
+            acc[2*sl] += ec;
+            acc[2*sl+1] += ev;
+        }
+    };
 
     float fix = 0.f, fiy = 0.f, fiz = 0.f;
     float eC[NS], eV[NS];
@@ -126,6 +226,17 @@ __global__ void __launch_bounds__(PAIR_WARPS*32) k_pair(const PairArgs a) {
         __syncwarp();
         shPos[warp][lane] = pj;
         shPar[warp][lane] = parj;
+        if (EMODE == 2) {
+            uint4 fj = make_uint4(0u, 0u, 0u, 0u);
+            double qj = 0.0;
+            if (entry >= 0) {
+                const uint4 q = a.posq[jIndex];
+                fj = make_uint4(q.x, q.y, q.z, (unsigned) __float_as_int(parj.z));
+                qj = a.q64[jIndex];
+            }
+            shJFix[warp][lane] = fj;
+            shJQ[warp][lane] = qj;
+        }
         __syncwarp();
         unsigned excluded = 0;                 // bit s: the pair (this lane's i, j slot s) is masked
         if (isX) {
@@ -157,6 +268,22 @@ __global__ void __launch_bounds__(PAIR_WARPS*32) k_pair(const PairArgs a) {
                 }
             }
             if (isX) in = in && !((excluded >> js) & 1u);
+            if (EMODE == 2 && MODE == 0) {
+                const unsigned m = __ballot_sync(FULL_MASK, in);
+                if (m) {
+                    if (in) shQueue[warp][qn + __popc(m & below)] = (unsigned short) ((lane << 5) | js);
+                    qn += __popc(m);
+                    if (qn >= 32) {
+                        __syncwarp();
+                        drainQueue(32);
+                        const int rest = qn - 32;
+                        const unsigned short moved = lane < rest ? shQueue[warp][32 + lane] : (unsigned short) 0;
+                        __syncwarp();
+                        if (lane < rest) shQueue[warp][lane] = moved;
+                        qn = rest;
+                    }
+                }
+            }
             if (MODE != 0) {
                 if (in) {
                     const unsigned origJ = (unsigned) __float_as_int(pr.w);
@@ -223,6 +350,12 @@ __global__ void __launch_bounds__(PAIR_WARPS*32) k_pair(const PairArgs a) {
             fjy = __shfl_sync(FULL_MASK, fjy, src);
             fjz = __shfl_sync(FULL_MASK, fjz, src);
         }
+        if (EMODE == 2 && MODE == 0) {              // the queue refers to this tile's shared-memory slots
+            __syncwarp();
+            drainQueue(qn);
+            qn = 0;
+            __syncwarp();
+        }
         if (MODE == 0 && entry >= 0) {
             atomicAdd(a.force + jIndex, toFixed(fjx));
             atomicAdd(a.force + a.Npad + jIndex, toFixed(fjy));
@@ -243,7 +376,7 @@ __global__ void __launch_bounds__(PAIR_WARPS*32) k_pair(const PairArgs a) {
 
     // fold the i forces of the CTA's warps in a fixed order, then one fixed-point atomic per atom
     shF[warp][0][lane] = fix; shF[warp][1][lane] = fiy; shF[warp][2][lane] = fiz;
-    if (ENERGY && threadIdx.x < MAX_SLICES*2) shE[threadIdx.x] = 0.0;
+    if (EMODE != 0 && threadIdx.x < MAX_SLICES*2) shE[threadIdx.x] = 0.0;
     __syncthreads();
     if (threadIdx.x < 96) {
         const int comp = threadIdx.x >> 5;
@@ -272,18 +405,31 @@ __global__ void __launch_bounds__(PAIR_WARPS*32) k_pair(const PairArgs a) {
         __syncthreads();
         if (threadIdx.x < NS*(NS+1)) atomicAdd(a.energy + threadIdx.x, shE[threadIdx.x]);
     }
-}
-
-template <int NS, bool ENERGY, bool IS_PME>
-static void launchPairT(Context& c, const PairArgs& a, int mode) {
-    dim3 grid(c.maxBlocks), block(PAIR_WARPS*32);
-    if (mode == 0) k_pair<NS, ENERGY, IS_PME, 0><<<grid, block, 0, c.stream>>>(a);
+    if (EMODE == 2) {
+#pragma unroll
+        for (int k = 0; k < NE; k++) {
+            const double v = warpSum(acc[k]);
+            if (lane == 0 && v != 0.0) atomicAdd(&shE[k], v);
+        }
+        __syncthreads();
+        if (threadIdx.x < NE && shE[threadIdx.x] != 0.0) atomicAdd(a.energy + threadIdx.x, shE[threadIdx.x]);
+    }
 }
 
 template <int NS>
-static void launchPairNS(Context& c, const PairArgs& a, bool energy, bool pme) {
-    if (energy) { if (pme) launchPairT<NS, true, true>(c, a, 0); else launchPairT<NS, true, false>(c, a, 0); }
-    else { if (pme) launchPairT<NS, false, true>(c, a, 0); else launchPairT<NS, false, false>(c, a, 0); }
+static void launchPairNS(Context& c, const PairArgs& a, int emode, bool pme) {
+    dim3 grid(c.maxBlocks), block(PAIR_WARPS*32);
+    cudaStream_t st = c.stream;
+    if (pme) {
+        if (emode == 0) k_pair<NS, 0, true, 0><<<grid, block, 0, st>>>(a);
+        else if (emode == 1) k_pair<NS, 1, true, 0><<<grid, block, 0, st>>>(a);
+        else k_pair<NS, 2, true, 0><<<grid, block, 0, st>>>(a);
+    }
+    else {
+        if (emode == 0) k_pair<NS, 0, false, 0><<<grid, block, 0, st>>>(a);
+        else if (emode == 1) k_pair<NS, 1, false, 0><<<grid, block, 0, st>>>(a);
+        else k_pair<NS, 2, false, 0><<<grid, block, 0, st>>>(a);
+    }
 }
 
 int launchPairs(Context& c, bool wantEnergy, int mode) {
@@ -294,6 +440,10 @@ int launchPairs(Context& c, bool wantEnergy, int mode) {
     a.dsx = g.box[0]/4294967296.0; a.dsy = g.box[1]/4294967296.0; a.dsz = g.box[2]/4294967296.0;
     a.rc2 = (float) (c.cutoff*c.cutoff);
     a.rc2d = c.cutoff*c.cutoff;
+    a.alphaD = c.alpha;
+    a.krfD = pow(c.cutoff, -3.0)*(c.rfDielectric - 1.0)/(2.0*c.rfDielectric + 1.0);
+    a.crfD = (1.0/c.cutoff)*(3.0*c.rfDielectric)/(2.0*c.rfDielectric + 1.0);
+    a.q64 = c.dQ64.d;
     a.alpha = (float) c.alpha;
     // ReferenceSlicedLJCoulombIxn::setUseCutoff, ReferenceSlicedLJCoulombIxn.cpp:60-68
     a.krf = (float) (pow(c.cutoff, -3.0)*(c.rfDielectric - 1.0)/(2.0*c.rfDielectric + 1.0));
@@ -316,15 +466,16 @@ int launchPairs(Context& c, bool wantEnergy, int mode) {
     }
     const bool pme = c.method == NBS_METHOD_PME;
     dim3 grid(c.maxBlocks), block(PAIR_WARPS*32);
-    if (mode == 1) k_pair<1, false, true, 1><<<grid, block, 0, c.stream>>>(a);
-    else if (mode == 2) k_pair<1, false, true, 2><<<grid, block, 0, c.stream>>>(a);
+    const int emode = !wantEnergy ? 0 : ((c.flags & NBS_FLAG_FP32_ENERGY) ? 1 : 2);
+    if (mode == 1) k_pair<1, 0, true, 1><<<grid, block, 0, c.stream>>>(a);
+    else if (mode == 2) k_pair<1, 0, true, 2><<<grid, block, 0, c.stream>>>(a);
     else {
         switch (c.nS) {
-            case 1: launchPairNS<1>(c, a, wantEnergy, pme); break;
-            case 2: launchPairNS<2>(c, a, wantEnergy, pme); break;
-            case 3: launchPairNS<3>(c, a, wantEnergy, pme); break;
-            case 4: launchPairNS<4>(c, a, wantEnergy, pme); break;
-            default: launchPairNS<MAX_SUBSETS>(c, a, wantEnergy, pme); break;
+            case 1: launchPairNS<1>(c, a, emode, pme); break;
+            case 2: launchPairNS<2>(c, a, emode, pme); break;
+            case 3: launchPairNS<3>(c, a, emode, pme); break;
+            case 4: launchPairNS<4>(c, a, emode, pme); break;
+            default: launchPairNS<MAX_SUBSETS>(c, a, emode, pme); break;
         }
     }
     c.launches++;

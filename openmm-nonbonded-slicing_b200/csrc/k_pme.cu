@@ -602,7 +602,8 @@ static int launchPmeT(Context& c, bool wantEnergy) {
 
 // Energies requested -> double-precision grids and transforms; forces only -> single precision.
 int launchPme(Context& c, bool wantEnergy) {
-    return wantEnergy ? launchPmeT<double>(c, true) : launchPmeT<float>(c, false);
+    const bool fp64 = wantEnergy && !(c.flags & NBS_FLAG_FP32_ENERGY);
+    return fp64 ? launchPmeT<double>(c, true) : launchPmeT<float>(c, wantEnergy);
 }
 
 } // namespace nbs

@@ -164,7 +164,8 @@ __device__ void heapSort(int* a, int n) {
 __global__ void k_bin_finalize(int nBins, const int* __restrict__ binStart, int* __restrict__ sortedToOrig,
                                int* __restrict__ origToSorted, const uint4* __restrict__ fix,
                                const float* __restrict__ chargeF, const float2* __restrict__ sigEps,
-                               const int* __restrict__ subset, uint4* __restrict__ posq, float4* __restrict__ par) {
+                               const int* __restrict__ subset, const double* __restrict__ charge, double sqrtK,
+                               uint4* __restrict__ posq, float4* __restrict__ par, double* __restrict__ q64) {
     int bin = blockIdx.x*blockDim.x + threadIdx.x;
     if (bin >= nBins) return;
     int s = binStart[bin], e = binStart[bin+1];
@@ -186,6 +187,7 @@ __global__ void k_bin_finalize(int nBins, const int* __restrict__ binStart, int*
         float2 se = sigEps[p];
         posq[slot] = make_uint4(f.x, f.y, f.z, __float_as_uint(chargeF[p]));
         par[slot] = make_float4(se.x, se.y, __int_as_float(subset[p]), __int_as_float(p));
+        q64[slot] = charge[p]*sqrtK;
         origToSorted[p] = slot;
     }
 }
@@ -268,7 +270,8 @@ int launchSort(Context& c, const PosInput& in) {
     if (status != NBS_OK) return status;
     k_scatter<<<(N+T-1)/T, T, 0, st>>>(N, c.dFix.d, c.dBinStart.d, c.dBinCursor.d, c.dSortedToOrig.d);
     k_bin_finalize<<<(g.nBins+T-1)/T, T, 0, st>>>(g.nBins, c.dBinStart.d, c.dSortedToOrig.d, c.dOrigToSorted.d, c.dFix.d,
-                                                  c.dChargeF.d, c.dSigEps.d, c.dSubset.d, c.dPosq.d, c.dPar.d);
+                                                  c.dChargeF.d, c.dSigEps.d, c.dSubset.d, c.dCharge.d, sqrt(kOne4PiEps0),
+                                                  c.dPosq.d, c.dPar.d, c.dQ64.d);
     // dBinCount is reused for the per-column block counts
     k_col_blocks<<<(g.nCols+T-1)/T, T, 0, st>>>(g.nCols, g.nzb, c.dBinStart.d, c.dBinCount.d);
     c.launches += 3;

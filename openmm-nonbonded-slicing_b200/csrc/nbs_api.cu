@@ -289,6 +289,7 @@ static int setupGeometry(Context& c, const double box[9]) {
     NBS_CUDA_CHECK(c.dOrigToSorted.ensure(N));
     NBS_CUDA_CHECK(c.dPosq.ensure(c.Npad));
     NBS_CUDA_CHECK(c.dPar.ensure(c.Npad));
+    NBS_CUDA_CHECK(c.dQ64.ensure(c.Npad));
     NBS_CUDA_CHECK(c.dExclRange.ensure(c.Npad));
     NBS_CUDA_CHECK(c.dColBlockStart.ensure(g.nCols + 2));
     NBS_CUDA_CHECK(c.dBlkFirst.ensure(c.maxBlocks));
@@ -325,7 +326,7 @@ static void releaseAll(Context& c) {
     c.dExclStart.release(); c.dExclList.release(); c.dExcPair.release(); c.dExcParam.release(); c.dExcSlice.release();
     c.dPosIn.release(); c.dForceOut.release(); c.dFix.release(); c.dBinCount.release(); c.dBinStart.release();
     c.dBinCursor.release(); c.dScanTmp.release(); c.dSortedToOrig.release(); c.dOrigToSorted.release();
-    c.dPosq.release(); c.dPar.release(); c.dColBlockStart.release(); c.dBlkFirst.release(); c.dBlkCount.release();
+    c.dPosq.release(); c.dPar.release(); c.dQ64.release(); c.dColBlockStart.release(); c.dBlkFirst.release(); c.dBlkCount.release();
     c.dBlkLo.release(); c.dBlkHi.release(); c.dExclRange.release(); c.dJList.release(); c.dJCount.release();
     c.dXList.release(); c.dXCount.release(); c.dXMask.release(); c.dCounters.release(); c.dForce.release();
     c.dEnergy.release(); c.dGrid.release(); c.dGridC.release(); c.dEterm.release(); c.dModuli.release();

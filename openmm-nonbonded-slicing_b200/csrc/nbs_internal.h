@@ -114,6 +114,7 @@ struct Context {
     Buf<int> dScanTmp;
     Buf<int> dSortedToOrig, dOrigToSorted;
     Buf<uint4> dPosq;
+    Buf<double> dQ64;                        // sorted charges * sqrt(ONE_4PI_EPS0) in double (energy path)
     Buf<float4> dPar;
     Buf<int> dColBlockStart;                 // [nCols+1]
     Buf<int> dBlkFirst, dBlkCount;

@@ -5,12 +5,11 @@ Tolerances (BASELINE.json north_star):
   * interacting-pair set and exclusion set: bit-exact (count + order-independent 64-bit hash, and the
     sorted pair lists themselves on the smaller systems);
   * forces: relative RMS error sqrt(sum |F-Fref|^2 / sum |Fref|^2) <= 1e-5;
-  * per-slice energies and dE/dlambda: |E - Eref| <= 1e-5 * max(|Eref|, 1) for a direct-only and for a
-    reciprocal-only evaluation (the floor of 1 is the reference tests' own assertion semantics,
-    AssertionUtilities.h:20-27); for a FULL evaluation, whose slice energy is the sum of those two
-    independently computed parts, the bound is 1e-5 * max(|E_direct,ref| + |E_recip,ref|, 1) -- a
-    slice such as protein-ligand Coulomb in C3 is +12.98 - 9.36 = 3.62 kJ/mol and single-precision
-    pair terms cannot resolve 1e-5 of the difference ("Precision").
+  * per-slice energies and dE/dlambda: |E - Eref| <= 1e-5 * max(|Eref|, 1) for every slice and term, in
+    direct-only, reciprocal-only and full evaluations (the floor of 1 kJ/mol is the reference tests' own
+    assertion semantics, AssertionUtilities.h:20-27).  Slice energies are small differences of large
+    sums (protein-ligand Coulomb in C3: +12.98 - 9.36 = 3.62 kJ/mol out of ~10^4 of pair terms), which
+    is why every energy term is evaluated in double precision on the device ("Precision").
 """
 import importlib
 import os
@@ -56,10 +55,7 @@ def three_way(kernel, desc, s_positions, box, lam, oracle_eval):
         ref_e, ref_f, pair_count, pair_hash = oracle_eval(tag, direct, recip)
         parts[tag] = ref_e
         assert force_rel_rms(forces, ref_f) <= F_TOL, tag
-        if tag == "full":
-            check_energies(e, ref_e, np.abs(parts["direct"]) + np.abs(parts["recip"]))
-        else:
-            check_energies(e, ref_e)
+        check_energies(e, ref_e)
         if direct:
             count, h, _ = kernel.getPairSet(with_pairs=False)
             assert (count, h) == (pair_count, pair_hash), f"pair set differs ({count} vs {pair_count})"
@@ -131,9 +127,10 @@ def test_random_systems(nbs, platform, oracle, seed, nsub, grid, n):
             assert force_rel_rms(a.getForces(), b.getForces()) <= F_TOL
             ea = ctx.impls[0].kernel.lastSliceEnergies
             eb = ref.impls[0].kernel.lastSliceEnergies
-            scale = np.maximum(np.abs(eb), 1e-3*np.abs(eb).max())
-            check_energies(ea, eb, scale)
             k, r = ctx.impls[0].kernel, ref.impls[0].kernel.lastResult
+            check_energies(ea, eb)
+            for name, value in b.getEnergyParameterDerivatives().items():
+                assert_equal_tol(value, a.getEnergyParameterDerivatives()[name], E_TOL)
             count, h, _ = k.getPairSet(with_pairs=False)
             assert (count, h) == (r.pair_count, r.pair_hash)
     # offsets change through setParameter only (no re-initialisation)
@@ -174,7 +171,9 @@ def test_tiny_and_degenerate_systems(nbs, platform, oracle):
             c.setPositions(positions)
         a = ctx.getState(getEnergy=True, getForces=True)
         b = ref.getState(getEnergy=True, getForces=True)
-        assert force_rel_rms(a.getForces(), b.getForces()) <= F_TOL
+        # two charges: the force is ~1 kJ/mol/nm, so use the reference tests' floor-1 vector comparison
+        for k in range(2):
+            assert_equal_vec(b.getForces()[k], a.getForces()[k], TOL)
         assert_equal_tol(b.getPotentialEnergy(), a.getPotentialEnergy(), 1e-5)
 
 

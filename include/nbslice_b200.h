@@ -79,6 +79,7 @@ extern "C" {
 
 #define NBS_POS_F64_XYZ   0   /* double[N][3]  -- the Reference platform's vector<Vec3>          */
 #define NBS_POS_F32_XYZW  1   /* float[N][4]   -- OpenMM CUDA posq (w ignored), device only      */
+#define NBS_POS_F64_XYZW  2   /* double[N][4]  -- OpenMM CUDA posq in double precision, device   */
 
 #define NBS_FORCE_F64_XYZ      0   /* double[N][3], added to (accumulate=1) or overwritten       */
 #define NBS_FORCE_I64_FIXED    1   /* long long[3][padded_atoms], value*2^32, always ADDED;

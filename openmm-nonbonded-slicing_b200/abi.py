@@ -26,6 +26,7 @@ NBS_MEM_HOST = 0
 NBS_MEM_DEVICE = 1
 NBS_POS_F64_XYZ = 0
 NBS_POS_F32_XYZW = 1
+NBS_POS_F64_XYZW = 2
 NBS_FORCE_F64_XYZ = 0
 NBS_FORCE_I64_FIXED = 1
 

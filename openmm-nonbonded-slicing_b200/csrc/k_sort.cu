@@ -16,14 +16,19 @@ namespace nbs {
 // fixed-point fractional coordinates and counts the atom into its (column, z-bin).
 // ---------------------------------------------------------------------------------------------
 __global__ void k_prep(int N, const double* __restrict__ pos64, const float4* __restrict__ pos32,
-                       const int* __restrict__ atomIndex, double3 invBox, int ncx, int ncy, int nzb,
-                       uint4* __restrict__ fix, int* __restrict__ binCount) {
+                       const double4* __restrict__ pos64w, const int* __restrict__ atomIndex, double3 invBox,
+                       int ncx, int ncy, int nzb, uint4* __restrict__ fix, int* __restrict__ binCount,
+                       double* __restrict__ pos64out) {
     int slot = blockIdx.x*blockDim.x + threadIdx.x;
     if (slot >= N) return;
     double x, y, z;
     if (pos64) { x = pos64[3*slot]; y = pos64[3*slot+1]; z = pos64[3*slot+2]; }
+    else if (pos64w) { double4 p = pos64w[slot]; x = p.x; y = p.y; z = p.z; }
     else { float4 p = pos32[slot]; x = p.x; y = p.y; z = p.z; }
     int particle = atomIndex ? atomIndex[slot] : slot;
+    if (pos64out) {          // particle-ordered, unwrapped, double: what the exception kernel reads
+        pos64out[3*particle] = x; pos64out[3*particle+1] = y; pos64out[3*particle+2] = z;
+    }
     double fx = x*invBox.x, fy = y*invBox.y, fz = z*invBox.z;
     fx -= floor(fx); fy -= floor(fy); fz -= floor(fz);
     unsigned ux = (unsigned) (__double2ull_rd(fx*4294967296.0) & 0xffffffffull);
@@ -261,9 +266,10 @@ int launchSort(Context& c, const PosInput& in) {
     NBS_CUDA_CHECK(cudaMemsetAsync(c.dBinCursor.d, 0, sizeof(int)*(g.nBins+1), st));
     const int T = 256;
     k_prep<<<(N+T-1)/T, T, 0, st>>>(N, in.format == NBS_POS_F64_XYZ ? (const double*) in.ptr : nullptr,
-                                    in.format == NBS_POS_F32_XYZW ? (const float4*) in.ptr : nullptr, in.atomIndex,
+                                    in.format == NBS_POS_F32_XYZW ? (const float4*) in.ptr : nullptr,
+                                    in.format == NBS_POS_F64_XYZW ? (const double4*) in.ptr : nullptr, in.atomIndex,
                                     make_double3(g.invBox[0], g.invBox[1], g.invBox[2]), g.ncx, g.ncy, g.nzb,
-                                    c.dFix.d, c.dBinCount.d);
+                                    c.dFix.d, c.dBinCount.d, in.pos64out);
     c.launches++;
     timerMark(c, "prep");
     int status = scanExclusive(c, c.dBinCount.d, c.dBinStart.d, g.nBins);

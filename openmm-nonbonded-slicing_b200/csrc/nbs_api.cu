@@ -447,11 +447,13 @@ int nbs_execute(nbs_context* ctx, const nbs_exec_args* args) {
     if (box[0] < minAllowedSize || box[4] < minAllowedSize || box[8] < minAllowedSize)
         return fail(NBS_ERR_BOX, "The periodic box size has decreased to less than twice the nonbonded cutoff.");
     if (!args->positions) return fail(NBS_ERR_INVALID, "positions is null");
-    if (args->positions_format == NBS_POS_F32_XYZW && args->positions_space != NBS_MEM_DEVICE)
-        return fail(NBS_ERR_INVALID, "float4 positions must be device memory");
+    if (args->positions_format != NBS_POS_F64_XYZ && args->positions_space != NBS_MEM_DEVICE)
+        return fail(NBS_ERR_INVALID, "xyzw positions must be device memory");
+    if (args->positions_format < 0 || args->positions_format > NBS_POS_F64_XYZW)
+        return fail(NBS_ERR_INVALID, "illegal positions_format");
     if (args->forces_format == NBS_FORCE_I64_FIXED && (args->forces_space != NBS_MEM_DEVICE || args->padded_num_atoms < c.N))
         return fail(NBS_ERR_INVALID, "fixed-point forces need device memory and padded_num_atoms >= num_particles");
-    if (args->atom_index && args->positions_format == NBS_POS_F64_XYZ && args->positions_space == NBS_MEM_HOST)
+    if (args->atom_index && args->positions_space == NBS_MEM_HOST)
         return fail(NBS_ERR_INVALID, "atom_index requires device-resident positions");
     c.stream = (cudaStream_t) args->stream;
     cudaStream_t st = c.stream;
@@ -471,6 +473,7 @@ int nbs_execute(nbs_context* ctx, const nbs_exec_args* args) {
         PosInput in;
         in.format = args->positions_format;
         in.atomIndex = args->atom_index;
+        in.pos64out = nullptr;
         const double* dPos64 = nullptr;
         if (args->positions_space == NBS_MEM_HOST) {
             NBS_CUDA_CHECK(c.dPosIn.ensure(3*(size_t) N));
@@ -480,7 +483,12 @@ int nbs_execute(nbs_context* ctx, const nbs_exec_args* args) {
         }
         else {
             in.ptr = args->positions;
-            if (args->positions_format == NBS_POS_F64_XYZ) dPos64 = (const double*) args->positions;
+            if (args->positions_format == NBS_POS_F64_XYZ && !args->atom_index) dPos64 = (const double*) args->positions;
+            else if (c.nExc > 0 && direct) {     // particle-ordered double copy for the exception kernel
+                NBS_CUDA_CHECK(c.dPosIn.ensure(3*(size_t) N));
+                in.pos64out = c.dPosIn.d;
+                dPos64 = c.dPosIn.d;
+            }
         }
         NBS_CUDA_CHECK(cudaMemsetAsync(c.dForce.d, 0, sizeof(unsigned long long)*3*c.Npad, st));
         NBS_CUDA_CHECK(cudaMemsetAsync(c.dEnergy.d, 0, sizeof(double)*2*MAX_SLICES, st));

@@ -157,7 +157,7 @@ struct Context {
 };
 
 // ---- launch wrappers (each counts its launches in ctx.launches) ----
-struct PosInput { const void* ptr; int format; const int* atomIndex; };
+struct PosInput { const void* ptr; int format; const int* atomIndex; double* pos64out; };
 
 int launchSort(Context& c, const PosInput& in);                 // fixed-point conversion, binning, cell sort, blocks
 int launchBuildLists(Context& c);

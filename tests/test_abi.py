@@ -109,3 +109,15 @@ def _non_pme_system(nbs):
     force.addParticle(0.0, 1.0, 0.0)
     system.addForce(force)
     return system
+
+
+def test_cpp_adapter_compiles_against_plugin_interface():
+    """The C++ platform kernel (platform/) must keep compiling against the plugin's UNCHANGED headers
+    (NonbondedSlicingKernels.h, SlicedNonbondedForce.h, SlicedNonbondedForceImpl.h)."""
+    import subprocess
+    if not os.path.isdir("/root/reference/openmmapi/include"):
+        pytest.skip("reference tree not present on this box")
+    out = subprocess.run(["make", "-C", os.path.join(ROOT, "openmm-nonbonded-slicing_b200", "platform"), "check"],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "adapter compiles" in out.stdout

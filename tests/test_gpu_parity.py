@@ -325,3 +325,51 @@ def test_stmv_size_properties(nbs, platform, systems):
     e3 = kernel._evaluate(shifted, s.box, lam2, np.zeros(0), True, True, f3)
     assert force_rel_rms(f3, f2) < 1e-5
     assert np.allclose(e3, e2, rtol=1e-5, atol=1e-2)
+
+
+def test_openmm_cuda_buffer_layouts(nbs, platform, systems, oracle):
+    """The layouts the C++ adapter hands over (platform/B200NonbondedSlicingKernels.cpp): OpenMM CUDA's posq
+    as float4 / double4 in a permuted, padded atom order + the atomIndex array, and its long-long
+    fixed-point force buffer [3][paddedNumAtoms] (pme.cc:382-388), all device resident."""
+    import ctypes as C
+    import torch
+    abi = nbs.abi
+    s = systems.make_system("C2")
+    n = s.force.getNumParticles()
+    kernel = nbs.B200CalcSlicedNonbondedForceKernel(platform)
+    kernel.initialize(s.system, s.force)
+    lam = np.random.default_rng(9).uniform(0.3, 1.0, size=(s.force.getNumSlices(), 2))
+    ref = oracle.evaluate(kernel.desc, s.positions, s.box, lam, None, True, True, kind="port")
+    rng = np.random.default_rng(4)
+    order = rng.permutation(n).astype(np.int32)              # slot -> particle
+    padded = ((n + 31)//32)*32 + 64
+    for fmt, dtype in ((abi.NBS_POS_F64_XYZW, torch.float64), (abi.NBS_POS_F32_XYZW, torch.float32)):
+        posq = torch.zeros((padded, 4), dtype=dtype, device="cuda")
+        posq[:n, :3] = torch.tensor(s.positions[order], dtype=dtype, device="cuda")
+        index = torch.tensor(order, dtype=torch.int32, device="cuda")
+        forces = torch.zeros((3, padded), dtype=torch.int64, device="cuda")
+        kernel._push_parameters(lam, np.zeros(0))
+        args = abi.ExecArgs()
+        args.struct_size = C.sizeof(abi.ExecArgs)
+        args.positions_format, args.positions_space = fmt, abi.NBS_MEM_DEVICE
+        args.forces_format, args.forces_space = abi.NBS_FORCE_I64_FIXED, abi.NBS_MEM_DEVICE
+        args.positions, args.forces = posq.data_ptr(), forces.data_ptr()
+        args.padded_num_atoms = padded
+        args.atom_index = index.data_ptr()
+        args.box[:] = list(s.box.reshape(9))
+        args.include_forces = args.include_energy = args.include_direct = args.include_reciprocal = 1
+        energies = np.zeros((s.force.getNumSlices(), 2))
+        args.slice_energies = energies.ctypes.data_as(C.POINTER(C.c_double))
+        args.stream = torch.cuda.current_stream().cuda_stream
+        for _ in range(2):                                   # the buffer is accumulated into, like OpenMM's
+            abi.check(kernel.lib.nbs_execute(kernel.handle, C.byref(args)))
+        torch.cuda.synchronize()
+        f = np.zeros((n, 3))
+        f[order] = (forces.cpu().numpy().astype(np.float64)/2**32).T[:n]/2
+        if fmt == abi.NBS_POS_F64_XYZW:
+            assert force_rel_rms(f, ref.forces) <= F_TOL
+            check_energies(energies, ref.slice_energies)
+            count, h, _ = kernel.getPairSet(with_pairs=False)
+            assert (count, h) == (ref.pair_count, ref.pair_hash)
+        else:       # float32 coordinates are OpenMM's single-precision mode: positions themselves are rounded
+            assert force_rel_rms(f, ref.forces) <= 2e-4

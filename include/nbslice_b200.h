@@ -55,6 +55,9 @@ extern "C" {
 #define NBS_ERR_BOX           -4   /* periodic box smaller than twice the cutoff
                                       (ReferenceNonbondedSlicingKernels.cpp:202-204)     */
 #define NBS_ERR_CAPACITY      -5   /* internal list overflow that could not be regrown   */
+#define NBS_RETRY              1   /* nbs_execute_finish only: an internal list was too small (on
+                                      this or another rank); it has been grown -- repeat the
+                                      evaluation from nbs_execute_begin                      */
 
 /* nonbonded methods: values of CalcSlicedNonbondedForceKernel::NonbondedMethod
  * (NonbondedSlicingKernels.h:29-36) */
@@ -163,6 +166,46 @@ int nbs_update_parameters(nbs_context* ctx, const nbs_system_desc* desc);
 int nbs_set_lambdas(nbs_context* ctx, const double* lambdas /* [nSl][2] (Coulomb, vdW) */);
 int nbs_set_global_parameters(nbs_context* ctx, const double* values /* [num_global_params] */);
 int nbs_execute(nbs_context* ctx, const nbs_exec_args* args);
+
+/*
+ * Multi-GPU evaluation: one process (and one nbs_context) per GPU, every rank holding ALL positions.
+ * The reference has no counterpart -- its only multi-device path is OpenMM's per-device work split with
+ * reciprocal space on device 0 (platforms/cuda/src/CudaParallelNonbondedSlicingKernels.cpp:35-53,
+ * CommonNonbondedSlicingKernels.cpp:416, 465, 643-646).  Work is split where it shards naturally:
+ *   direct space : i-block b belongs to the rank with (b % block_period) in [block_offset,
+ *                  block_offset + block_width); exceptions are dealt round-robin;
+ *   PME          : a rank owns the charge grids of subsets [subset_begin, subset_end) -- spreading,
+ *                  FFTs and gather of those subsets; an empty range means no reciprocal work.
+ * The caller (torch.distributed / NCCL) performs the two exchanges between the phases:
+ *   nbs_execute_begin -> broadcast each owned half spectrum to the ranks that own grids
+ *   nbs_execute_convolve -> all-reduce(sum) `forces` (int64) and `energies` (double)
+ *   nbs_execute_finish   (returns NBS_RETRY on every rank if any rank overflowed a list)
+ * nbs_execute == begin + convolve + finish on an unsharded context.
+ */
+typedef struct nbs_exchange_buffers {
+    int32_t struct_size;                  /* = sizeof(nbs_exchange_buffers)                    */
+    int32_t spectrum_is_double;           /* element type of `spectra`: double2 (1) or float2   */
+    void*   spectra;                      /* device [num_subsets][nx][ny][nz/2+1] half spectra  */
+    int64_t spectrum_bytes_per_subset;
+    void*   forces;                       /* device int64[force_words]: fixed-point (x 2^32)
+                                             accumulators [3][padded] in cell-sorted order, which
+                                             is identical on every rank                          */
+    int64_t force_words;
+    void*   energies;                     /* device double[energy_words]: slice table + flags    */
+    int64_t energy_words;
+} nbs_exchange_buffers;
+
+int nbs_set_shard(nbs_context* ctx, int32_t rank, int32_t num_ranks, int32_t block_period, int32_t block_offset,
+                  int32_t block_width, int32_t subset_begin, int32_t subset_end);
+int nbs_execute_begin(nbs_context* ctx, const nbs_exec_args* args);
+int nbs_execute_convolve(nbs_context* ctx, const nbs_exec_args* args);
+int nbs_execute_finish(nbs_context* ctx, const nbs_exec_args* args);
+/* valid between nbs_execute_begin and nbs_execute_finish of the evaluation in flight */
+int nbs_get_exchange_buffers(nbs_context* ctx, nbs_exchange_buffers* out);
+
+/* test hook: initial per-block capacities of the neighbour lists (they grow on demand; a tiny value
+ * forces the NBS_RETRY path) */
+int nbs_debug_set_list_capacity(nbs_context* ctx, int32_t j_capacity, int32_t x_capacity);
 
 /* queries */
 int nbs_get_pme_parameters(const nbs_context* ctx, double* alpha, int32_t* nx, int32_t* ny, int32_t* nz);

@@ -16,6 +16,7 @@ NBS_ERR_UNSUPPORTED = -2
 NBS_ERR_CUDA = -3
 NBS_ERR_BOX = -4
 NBS_ERR_CAPACITY = -5
+NBS_RETRY = 1
 
 NBS_FLAG_DETERMINISTIC = 0x1
 NBS_FLAG_PROFILE = 0x2
@@ -90,6 +91,19 @@ class ExecArgs(C.Structure):
     ]
 
 
+class ExchangeBuffers(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_int32),
+        ("spectrum_is_double", C.c_int32),
+        ("spectra", C.c_void_p),
+        ("spectrum_bytes_per_subset", C.c_int64),
+        ("forces", C.c_void_p),
+        ("force_words", C.c_int64),
+        ("energies", C.c_void_p),
+        ("energy_words", C.c_int64),
+    ]
+
+
 def _ptr(array, ctype):
     if array is None or array.size == 0:
         return C.cast(None, C.POINTER(ctype))
@@ -131,6 +145,8 @@ EXPORTS = [
     "nbs_update_parameters", "nbs_set_lambdas", "nbs_set_global_parameters", "nbs_execute",
     "nbs_get_pme_parameters", "nbs_get_num_slices", "nbs_get_pair_set", "nbs_get_exclusion_set",
     "nbs_get_kernel_times", "nbs_get_launch_count", "nbs_get_nlist_stats",
+    "nbs_set_shard", "nbs_execute_begin", "nbs_execute_convolve", "nbs_execute_finish", "nbs_get_exchange_buffers",
+    "nbs_debug_set_list_capacity",
 ]
 
 
@@ -166,6 +182,11 @@ def load_library():
     lib.nbs_get_kernel_times.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_char_p), C.POINTER(C.c_float), _i32p]
     lib.nbs_get_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
     lib.nbs_get_nlist_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+    lib.nbs_set_shard.argtypes = [C.c_void_p] + [C.c_int32]*7
+    for name in ("nbs_execute_begin", "nbs_execute_convolve", "nbs_execute_finish"):
+        getattr(lib, name).argtypes = [C.c_void_p, C.POINTER(ExecArgs)]
+    lib.nbs_debug_set_list_capacity.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+    lib.nbs_get_exchange_buffers.argtypes = [C.c_void_p, C.POINTER(ExchangeBuffers)]
     for name in EXPORTS:
         getattr(lib, name)
     if lib.nbs_abi_version() != 1:

@@ -14,6 +14,7 @@ namespace nbs {
 
 struct BondedArgs {
     int nExc, Npad;
+    int rank, nRanks;                // exception e belongs to rank e % nRanks
     int doExclusionCorrection;       // PME only
     int periodic;                    // exceptionsUsePeriodic
     double3 box, invBox;
@@ -30,7 +31,7 @@ __global__ void k_bonded(const BondedArgs a) {
     const int lane = threadIdx.x & 31;
     int slice = -1;
     double eCoul = 0.0, eVdw = 0.0;
-    if (e < a.nExc) {
+    if (e < a.nExc && e % a.nRanks == a.rank) {
         const int2 pr = a.pairs[e];
         const int s1 = a.slotOf ? a.slotOf[pr.x] : pr.x, s2 = a.slotOf ? a.slotOf[pr.y] : pr.y;
         double dx = a.pos[3*s1] - a.pos[3*s2], dy = a.pos[3*s1+1] - a.pos[3*s2+1], dz = a.pos[3*s1+2] - a.pos[3*s2+2];
@@ -97,6 +98,7 @@ int launchBonded(Context& c, const double* dPos, bool periodicBox) {
     if (c.nExc == 0) return NBS_OK;
     BondedArgs a;
     a.nExc = c.nExc; a.Npad = c.Npad;
+    a.rank = c.rank; a.nRanks = c.nRanks;
     a.doExclusionCorrection = c.method == NBS_METHOD_PME ? 1 : 0;
     a.periodic = (c.excPeriodic && periodicBox) ? 1 : 0;
     a.box = make_double3(c.geom.box[0], c.geom.box[1], c.geom.box[2]);

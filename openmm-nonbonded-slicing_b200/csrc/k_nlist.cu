@@ -24,6 +24,7 @@ constexpr int XBUF = 192;
 
 struct BuildArgs {
     int N, maxBlocks, capJ, capX;
+    int blockPeriod, blockOffset, blockWidth;   // this rank's share of the i-blocks
     int ncx, ncy, nzb;
     float colWx, colWy, binH;
     float Lx, Ly, Lz;
@@ -36,10 +37,12 @@ struct BuildArgs {
     const int2* exclRange; const int* exclStart; const int* exclList; const int* origToSorted;
     int* jlist; int* jcount; int* xlist; unsigned* xmask; int* xcount;
     int* overflow;             // counters + 1
+    double* overflowFlag;      // energy[2*MAX_SLICES]: the same flag as a double, so that it all-reduces
 };
 
 __global__ void __launch_bounds__(BUILD_WARPS*32) k_build_lists(BuildArgs a) {
-    const int b = blockIdx.x;
+    const int lb = blockIdx.x;                  // rank-local block index (lists are stored there)
+    const int b = localToGlobalBlock(lb, a.blockPeriod, a.blockOffset, a.blockWidth);
     if (b >= a.counters[0]) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     __shared__ int jbuf[BUILD_WARPS][JBUF];
@@ -143,9 +146,9 @@ __global__ void __launch_bounds__(BUILD_WARPS*32) k_build_lists(BuildArgs a) {
     if (totJ > a.capJ - 32 || totX > a.capX - 32) overflow = true;
     totJ = min(totJ, a.capJ - 32);
     totX = min(totX, a.capX - 32);
-    int* jl = a.jlist + (size_t) b*a.capJ;
-    int* xl = a.xlist + (size_t) b*a.capX;
-    unsigned* xm = a.xmask + (size_t) b*a.capX;
+    int* jl = a.jlist + (size_t) lb*a.capJ;
+    int* xl = a.xlist + (size_t) lb*a.capX;
+    unsigned* xm = a.xmask + (size_t) lb*a.capX;
     for (int k = lane; k < nj; k += 32) if (offJ + k < totJ) jl[offJ + k] = jbuf[warp][k];
     for (int k = lane; k < nx; k += 32) if (offX + k < totX) { xl[offX + k] = xbuf[warp][k]; xm[offX + k] = xmbuf[warp][k]; }
     // pad the last tile of each list with invalid entries
@@ -159,20 +162,20 @@ __global__ void __launch_bounds__(BUILD_WARPS*32) k_build_lists(BuildArgs a) {
         if (t-32 < padX) { xl[totX + t-32] = -1; xm[totX + t-32] = 0xffffffffu; }
     }
     if (t == 0) {
-        a.jcount[b] = totJ;
-        a.xcount[b] = totX;
+        a.jcount[lb] = totJ;
+        a.xcount[lb] = totX;
     }
-    if (overflow && lane == 0) atomicOr(a.overflow, 1);
+    if (overflow && lane == 0) { atomicOr(a.overflow, 1); a.overflowFlag[0] = 1.0; }
 }
-
-int launchExclRange(Context& c);
 
 int launchBuildLists(Context& c) {
     const CellGeom& g = c.geom;
+    if (c.blockWidth == 0) return NBS_OK;          // this rank has no direct-space share
     int status = launchExclRange(c);
     if (status != NBS_OK) return status;
     BuildArgs a;
     a.N = c.N; a.maxBlocks = c.maxBlocks; a.capJ = c.capJ; a.capX = c.capX;
+    a.blockPeriod = c.blockPeriod; a.blockOffset = c.blockOffset; a.blockWidth = c.blockWidth;
     a.ncx = g.ncx; a.ncy = g.ncy; a.nzb = g.nzb;
     a.colWx = g.colW[0]; a.colWy = g.colW[1]; a.binH = g.binH;
     a.Lx = (float) g.box[0]; a.Ly = (float) g.box[1]; a.Lz = (float) g.box[2];
@@ -185,7 +188,8 @@ int launchBuildLists(Context& c) {
     a.exclRange = c.dExclRange.d; a.exclStart = c.dExclStart.d; a.exclList = c.dExclList.d; a.origToSorted = c.dOrigToSorted.d;
     a.jlist = c.dJList.d; a.jcount = c.dJCount.d; a.xlist = c.dXList.d; a.xmask = c.dXMask.d; a.xcount = c.dXCount.d;
     a.overflow = c.dCounters.d + 1;
-    k_build_lists<<<c.maxBlocks, BUILD_WARPS*32, 0, c.stream>>>(a);
+    a.overflowFlag = c.dEnergy.d + 2*MAX_SLICES;
+    k_build_lists<<<c.maxLocalBlocks, BUILD_WARPS*32, 0, c.stream>>>(a);
     c.launches++;
     timerMark(c, "build_lists");
     return NBS_OK;

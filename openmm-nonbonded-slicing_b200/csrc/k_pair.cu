@@ -28,6 +28,7 @@ namespace nbs {
 
 struct PairArgs {
     int capJ, capX, Npad;
+    int blockPeriod, blockOffset, blockWidth;   // this rank's share of the i-blocks
     float sx, sy, sz;
     double dsx, dsy, dsz;
     float rc2, alpha, krf, crf;
@@ -133,7 +134,8 @@ template <int NS, int EMODE, bool IS_PME, int MODE>
 __global__ void __launch_bounds__(PAIR_WARPS*32) k_pair(const PairArgs a) {
     constexpr bool ENERGY = EMODE == 1;          // single-precision energies in the main loop
     constexpr int NE = NS*(NS+1);                // 2 * number of slices
-    const int b = blockIdx.x;
+    const int lb = blockIdx.x;                  // rank-local block index
+    const int b = localToGlobalBlock(lb, a.blockPeriod, a.blockOffset, a.blockWidth);
     if (b >= a.counters[0]) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     __shared__ float4 shPos[PAIR_WARPS][32];
@@ -198,11 +200,11 @@ __global__ void __launch_bounds__(PAIR_WARPS*32) k_pair(const PairArgs a) {
     for (int s = 0; s < NS; s++) { eC[s] = 0.f; eV[s] = 0.f; }
     unsigned long long nPairs = 0, hPairs = 0;
 
-    const int nJ = a.jcount[b], nX = a.xcount[b];
+    const int nJ = a.jcount[lb], nX = a.xcount[lb];
     const int tJ = (nJ + 31) >> 5, tX = (nX + 31) >> 5;
-    const int* jl = a.jlist + (size_t) b*a.capJ;
-    const int* xl = a.xlist + (size_t) b*a.capX;
-    const unsigned* xm = a.xmask + (size_t) b*a.capX;
+    const int* jl = a.jlist + (size_t) lb*a.capJ;
+    const int* xl = a.xlist + (size_t) lb*a.capX;
+    const unsigned* xm = a.xmask + (size_t) lb*a.capX;
     const float TWO_OVER_SQRT_PI = 1.1283791670955126f;
 
     for (int t = warp; t < tJ + tX; t += PAIR_WARPS) {
@@ -418,7 +420,7 @@ __global__ void __launch_bounds__(PAIR_WARPS*32) k_pair(const PairArgs a) {
 
 template <int NS>
 static void launchPairNS(Context& c, const PairArgs& a, int emode, bool pme) {
-    dim3 grid(c.maxBlocks), block(PAIR_WARPS*32);
+    dim3 grid(c.maxLocalBlocks), block(PAIR_WARPS*32);
     cudaStream_t st = c.stream;
     if (pme) {
         if (emode == 0) k_pair<NS, 0, true, 0><<<grid, block, 0, st>>>(a);
@@ -433,9 +435,11 @@ static void launchPairNS(Context& c, const PairArgs& a, int emode, bool pme) {
 }
 
 int launchPairs(Context& c, bool wantEnergy, int mode) {
+    if (c.blockWidth == 0) return NBS_OK;          // this rank has no direct-space share
     const CellGeom& g = c.geom;
     PairArgs a;
     a.capJ = c.capJ; a.capX = c.capX; a.Npad = c.Npad;
+    a.blockPeriod = c.blockPeriod; a.blockOffset = c.blockOffset; a.blockWidth = c.blockWidth;
     a.sx = g.scale[0]; a.sy = g.scale[1]; a.sz = g.scale[2];
     a.dsx = g.box[0]/4294967296.0; a.dsy = g.box[1]/4294967296.0; a.dsz = g.box[2]/4294967296.0;
     a.rc2 = (float) (c.cutoff*c.cutoff);
@@ -465,7 +469,7 @@ int launchPairs(Context& c, bool wantEnergy, int mode) {
         a.lam.v[s] = s < c.nSl ? (float) c.lambdas[2*s+1] : 1.f;
     }
     const bool pme = c.method == NBS_METHOD_PME;
-    dim3 grid(c.maxBlocks), block(PAIR_WARPS*32);
+    dim3 grid(c.maxLocalBlocks), block(PAIR_WARPS*32);
     const int emode = !wantEnergy ? 0 : ((c.flags & NBS_FLAG_FP32_ENERGY) ? 1 : 2);
     if (mode == 1) k_pair<1, 0, true, 1><<<grid, block, 0, c.stream>>>(a);
     else if (mode == 2) k_pair<1, 0, true, 2><<<grid, block, 0, c.stream>>>(a);

@@ -170,6 +170,7 @@ __device__ __forceinline__ void warpFft(C* line, int n, unsigned long long facto
 // ---------------------------------------------------------------------------------------------
 struct PmeArgs {
     int N, Npad, nS, nx, ny, nz, nzh;
+    int ownLo, ownHi;            // this rank spreads / gathers the atoms of subsets [ownLo, ownHi)
     const uint4* posq; const float4* par;
     void* grid; const float* pot;
     unsigned long long* force;
@@ -206,7 +207,7 @@ __global__ void __launch_bounds__(256) k_spread(const PmeArgs a) {
     T tz[5];
 #pragma unroll
     for (int k = 0; k < 5; k++) tz[k] = __shfl_sync(FULL_MASK, mine, 10 + k);
-    if (lane >= 25 || q == 0.f) return;
+    if (lane >= 25 || q == 0.f || subset < a.ownLo || subset >= a.ownHi) return;
     int x = ix0 + ox; x -= x >= a.nx ? a.nx : 0;
     int y = iy0 + oy; y -= y >= a.ny ? a.ny : 0;
     T* row = (T*) a.grid + (((size_t) subset*a.nx + x)*a.ny + y)*a.nz;
@@ -223,6 +224,7 @@ __global__ void __launch_bounds__(256) k_spread(const PmeArgs a) {
 // ---------------------------------------------------------------------------------------------
 struct FftArgs {
     int nS, nx, ny, nz, nzh;
+    int ownLo, ownHi;            // x_conv: subsets whose mixed potential this rank produces
     int n;                       // length of the dimension this launch transforms
     unsigned long long factors;  // its radices, 4 bits each
     const void* tw;              // twiddles of this dimension: exp(-2 pi i k / n), precision T
@@ -378,13 +380,15 @@ __global__ void __launch_bounds__(256) k_fft_x_conv(const FftArgs a) {
             for (int sb = 0; sb < NS; sb++)
 #pragma unroll
                 for (int sa = 0; sa <= sb; sa++) {
+                    if (sa < a.ownLo || sa >= a.ownHi) continue;     // a slice belongs to the owner of its lower subset
                     const T prod = S[sa].x*S[sb].x + S[sa].y*S[sb].y;
                     e[sb*(sb+1)/2 + sa] += (double) ((sa == sb ? (T) 0.5 : (T) 1)*w*et*prod);
                 }
         }
 #pragma unroll
         for (int si = 0; si < NS; si++) {
-            if (si >= nS) break;
+            if (si >= a.ownHi) break;
+            if (si < a.ownLo) continue;
             T gx = 0, gy = 0;
 #pragma unroll
             for (int sj = 0; sj < NS; sj++) {
@@ -396,11 +400,12 @@ __global__ void __launch_bounds__(256) k_fft_x_conv(const FftArgs a) {
         }
     }
     __syncthreads();
-    for (int L = warp; L < nS*8; L += 8)
+    const int nOwn = a.ownHi - a.ownLo;
+    for (int L = a.ownLo*8 + warp; L < a.ownHi*8; L += 8)
         if (k0 + (L & 7) < a.nzh) warpFft<NQ>(lines + L*stride, a.n, a.factors, tw, lane);
     __syncthreads();
-    for (int idx = threadIdx.x; idx < nS*n*8; idx += blockDim.x) {
-        const int l = idx & 7, x = (idx >> 3) % n, s = idx/(8*n);
+    for (int idx = threadIdx.x; idx < nOwn*n*8; idx += blockDim.x) {
+        const int l = idx & 7, x = (idx >> 3) % n, s = a.ownLo + idx/(8*n);
         if (k0 + l < a.nzh) {
             C v = lines[(s*8 + l)*stride + x];
             v.y = -v.y;
@@ -431,6 +436,7 @@ __global__ void __launch_bounds__(256) k_gather(const PmeArgs a) {
     const float q = __uint_as_float(p.w);
     if (q == 0.f) return;
     const int subset = __float_as_int(a.par[j].z);
+    if (subset < a.ownLo || subset >= a.ownHi) return;
     const int dim = min(lane/5, 2), kk = lane % 5;
     int index; float frac;
     gridCoord<float>(dim == 0 ? p.x : (dim == 1 ? p.y : p.z), dim == 0 ? a.nx : (dim == 1 ? a.ny : a.nz), index, frac);
@@ -506,17 +512,21 @@ int prepareEterm(Context& c) {
     return NBS_OK;
 }
 
+// The chain is split where a multi-rank evaluation exchanges spectra: `half` 0 = z and y forward
+// transforms of this rank's own subsets, `half` 1 = fused x pass (all subsets in, own subsets out),
+// inverse y and z of the own subsets.
 template <typename T, int NQ>
 static void launchFftChain(Context& c, FftArgs f, const FftPlan& px, const FftPlan& py, const FftPlan& pz,
-                           size_t smX, size_t smY, size_t smZ) {
+                           size_t smX, size_t smY, size_t smZ, int half) {
     typedef typename Cx<T>::type C;
     cudaStream_t st = c.stream;
     const int nx = c.grid[0], ny = c.grid[1], nz = c.grid[2], nzh = nz/2 + 1;
     const C* tw = (const C*) (sizeof(T) == 8 ? (const void*) c.dTwiddleD.d : (const void*) c.dTwiddle.d);
-    const int pairs = c.nS*nx*((ny + 1)/2);
-    const int yCtas = c.nS*nx*((nzh + 15)/16), xCtas = ny*((nzh + 7)/8);
-    static bool attr = false;
-    if (!attr) {
+    const int nOwn = c.ownHi - c.ownLo;
+    const int pairs = nOwn*nx*((ny + 1)/2);
+    const int yCtas = nOwn*nx*((nzh + 15)/16), xCtas = ny*((nzh + 7)/8);
+    static bool attr[64] = {false};
+    if (!attr[c.device & 63]) {
         const int big = 200*1024;
         cudaFuncSetAttribute(k_fft_z_fwd<T, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
         cudaFuncSetAttribute(k_fft_z_inv<T, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
@@ -527,12 +537,22 @@ static void launchFftChain(Context& c, FftArgs f, const FftPlan& px, const FftPl
         cudaFuncSetAttribute(k_fft_x_conv<T, NQ, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
         cudaFuncSetAttribute(k_fft_x_conv<T, NQ, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
         cudaFuncSetAttribute(k_fft_x_conv<T, NQ, MAX_SUBSETS>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-        attr = true;
+        attr[c.device & 63] = true;
     }
-    f.n = pz.n; f.factors = pz.packed; f.tw = tw + nx + ny;
-    k_fft_z_fwd<T, NQ><<<(pairs + 7)/8, 256, smZ, st>>>(f);
-    f.n = py.n; f.factors = py.packed; f.tw = tw + nx;
-    k_fft_y<T, NQ, false><<<yCtas, 512, smY, st>>>(f);
+    // the per-subset kernels see only the own slabs: offset the base pointers, nS = own count
+    FftArgs own = f;
+    own.nS = nOwn;
+    own.grid = (T*) f.grid + (size_t) c.ownLo*nx*ny*nz;
+    own.gridC = (C*) f.gridC + (size_t) c.ownLo*nx*ny*nzh;
+    own.pot = f.pot + (size_t) c.ownLo*nx*ny*nz;
+    if (half == 0) {
+        own.n = pz.n; own.factors = pz.packed; own.tw = tw + nx + ny;
+        k_fft_z_fwd<T, NQ><<<(pairs + 7)/8, 256, smZ, st>>>(own);
+        own.n = py.n; own.factors = py.packed; own.tw = tw + nx;
+        k_fft_y<T, NQ, false><<<yCtas, 512, smY, st>>>(own);
+        c.launches += 2;
+        return;
+    }
     f.n = px.n; f.factors = px.packed; f.tw = tw;
     switch (c.nS) {
         case 1: k_fft_x_conv<T, NQ, 1><<<xCtas, 256, smX, st>>>(f); break;
@@ -541,38 +561,43 @@ static void launchFftChain(Context& c, FftArgs f, const FftPlan& px, const FftPl
         case 4: k_fft_x_conv<T, NQ, 4><<<xCtas, 256, smX, st>>>(f); break;
         default: k_fft_x_conv<T, NQ, MAX_SUBSETS><<<xCtas, 256, smX, st>>>(f); break;
     }
-    f.n = py.n; f.factors = py.packed; f.tw = tw + nx;
-    k_fft_y<T, NQ, true><<<yCtas, 512, smY, st>>>(f);
-    f.n = pz.n; f.factors = pz.packed; f.tw = tw + nx + ny;
-    k_fft_z_inv<T, NQ><<<(pairs + 7)/8, 256, smZ, st>>>(f);
-    c.launches += 5;
+    own.n = py.n; own.factors = py.packed; own.tw = tw + nx;
+    k_fft_y<T, NQ, true><<<yCtas, 512, smY, st>>>(own);
+    own.n = pz.n; own.factors = pz.packed; own.tw = tw + nx + ny;
+    k_fft_z_inv<T, NQ><<<(pairs + 7)/8, 256, smZ, st>>>(own);
+    c.launches += 3;
 }
 
 template <typename T>
-static int launchPmeT(Context& c, bool wantEnergy) {
+static int launchPmeT(Context& c, bool wantEnergy, int half) {
     const int nx = c.grid[0], ny = c.grid[1], nz = c.grid[2], nzh = nz/2 + 1;
     const size_t G = (size_t) nx*ny*nz;
     cudaStream_t st = c.stream;
+    if (c.ownHi <= c.ownLo) return NBS_OK;            // this rank owns no subset grid
     FftPlan px, py, pz;
     if (!makePlan(nx, px) || !makePlan(ny, py) || !makePlan(nz, pz)) {
         setError("PME grid dimensions must be <= 512 and factor into 2, 3, 5, 7, 11, 13");
         return NBS_ERR_UNSUPPORTED;
     }
-    int status = prepareEterm(c);
-    if (status != NBS_OK) return status;
-    NBS_CUDA_CHECK(cudaMemsetAsync(c.dGrid.d, 0, sizeof(T)*G*c.nS, st));
     PmeArgs p;
     p.N = c.N; p.Npad = c.Npad; p.nS = c.nS; p.nx = nx; p.ny = ny; p.nz = nz; p.nzh = nzh;
+    p.ownLo = c.ownLo; p.ownHi = c.ownHi;
     p.posq = c.dPosq.d; p.par = c.dPar.d; p.grid = c.dGrid.d; p.pot = c.dPot.d;
     p.force = c.dForce.d;
     for (int k = 0; k < 3; k++) p.fscale[k] = (float) (c.grid[k]*c.geom.invBox[k]);
     const int atomCtas = (c.N + 7)/8;
-    k_spread<T><<<atomCtas, 256, 0, st>>>(p);
-    c.launches++;
-    timerMark(c, "spread");
+    if (half == 0) {
+        int status = prepareEterm(c);
+        if (status != NBS_OK) return status;
+        NBS_CUDA_CHECK(cudaMemsetAsync((T*) c.dGrid.d + (size_t) c.ownLo*G, 0, sizeof(T)*G*(c.ownHi - c.ownLo), st));
+        k_spread<T><<<atomCtas, 256, 0, st>>>(p);
+        c.launches++;
+        timerMark(c, "spread");
+    }
 
     FftArgs f;
     f.nS = c.nS; f.nx = nx; f.ny = ny; f.nz = nz; f.nzh = nzh;
+    f.ownLo = c.ownLo; f.ownHi = c.ownHi;
     f.grid = c.dGrid.d; f.gridC = c.dGridC.d; f.pot = c.dPot.d; f.energy = c.dEnergy.d;
     f.eterm = sizeof(T) == 8 ? (const void*) c.dEtermD.d : (const void*) c.dEterm.d;
     f.wantEnergy = wantEnergy ? 1 : 0;
@@ -589,21 +614,24 @@ static int launchPmeT(Context& c, bool wantEnergy) {
         return NBS_ERR_UNSUPPORTED;
     }
     const int nq = std::max(px.nq, std::max(py.nq, pz.nq));
-    if (nq <= 1) launchFftChain<T, 1>(c, f, px, py, pz, smX, smY, smZ);
-    else if (nq <= 2) launchFftChain<T, 2>(c, f, px, py, pz, smX, smY, smZ);
-    else if (nq <= 4) launchFftChain<T, 4>(c, f, px, py, pz, smX, smY, smZ);
-    else launchFftChain<T, 8>(c, f, px, py, pz, smX, smY, smZ);
-    timerMark(c, "fft_conv");
-    k_gather<<<atomCtas, 256, 0, st>>>(p);
-    c.launches++;
-    timerMark(c, "gather");
+    if (nq <= 1) launchFftChain<T, 1>(c, f, px, py, pz, smX, smY, smZ, half);
+    else if (nq <= 2) launchFftChain<T, 2>(c, f, px, py, pz, smX, smY, smZ, half);
+    else if (nq <= 4) launchFftChain<T, 4>(c, f, px, py, pz, smX, smY, smZ, half);
+    else launchFftChain<T, 8>(c, f, px, py, pz, smX, smY, smZ, half);
+    timerMark(c, half == 0 ? "fft_fwd" : "fft_conv_inv");
+    if (half == 1) {
+        k_gather<<<atomCtas, 256, 0, st>>>(p);
+        c.launches++;
+        timerMark(c, "gather");
+    }
     return NBS_OK;
 }
 
 // Energies requested -> double-precision grids and transforms; forces only -> single precision.
-int launchPme(Context& c, bool wantEnergy) {
+// half 0: spread + forward z/y transforms of the own subsets; half 1: x pass + convolution, inverse, gather.
+int launchPme(Context& c, bool wantEnergy, int half) {
     const bool fp64 = wantEnergy && !(c.flags & NBS_FLAG_FP32_ENERGY);
-    return fp64 ? launchPmeT<double>(c, true) : launchPmeT<float>(c, wantEnergy);
+    return fp64 ? launchPmeT<double>(c, true, half) : launchPmeT<float>(c, wantEnergy, half);
 }
 
 } // namespace nbs

@@ -281,6 +281,7 @@ static int setupGeometry(Context& c, const double box[9]) {
     const int N = c.N;
     c.Npad = ((N + 31)/32)*32 + 32;
     c.maxBlocks = N/32 + g.nCols + 1;
+    c.maxLocalBlocks = std::max(1, ((c.maxBlocks + c.blockPeriod - 1)/c.blockPeriod)*c.blockWidth);
     NBS_CUDA_CHECK(c.dFix.ensure(N));
     NBS_CUDA_CHECK(c.dBinCount.ensure(g.nBins + 2));
     NBS_CUDA_CHECK(c.dBinStart.ensure(g.nBins + 2));
@@ -296,11 +297,11 @@ static int setupGeometry(Context& c, const double box[9]) {
     NBS_CUDA_CHECK(c.dBlkCount.ensure(c.maxBlocks));
     NBS_CUDA_CHECK(c.dBlkLo.ensure(c.maxBlocks));
     NBS_CUDA_CHECK(c.dBlkHi.ensure(c.maxBlocks));
-    NBS_CUDA_CHECK(c.dJCount.ensure(c.maxBlocks));
-    NBS_CUDA_CHECK(c.dXCount.ensure(c.maxBlocks));
-    NBS_CUDA_CHECK(c.dJList.ensure((size_t) c.maxBlocks*c.capJ));
-    NBS_CUDA_CHECK(c.dXList.ensure((size_t) c.maxBlocks*c.capX));
-    NBS_CUDA_CHECK(c.dXMask.ensure((size_t) c.maxBlocks*c.capX));
+    NBS_CUDA_CHECK(c.dJCount.ensure(c.maxLocalBlocks));
+    NBS_CUDA_CHECK(c.dXCount.ensure(c.maxLocalBlocks));
+    NBS_CUDA_CHECK(c.dJList.ensure((size_t) c.maxLocalBlocks*c.capJ));
+    NBS_CUDA_CHECK(c.dXList.ensure((size_t) c.maxLocalBlocks*c.capX));
+    NBS_CUDA_CHECK(c.dXMask.ensure((size_t) c.maxLocalBlocks*c.capX));
     NBS_CUDA_CHECK(c.dForce.ensure(3*(size_t) c.Npad));
     return NBS_OK;
 }
@@ -336,6 +337,10 @@ static void releaseAll(Context& c) {
     if (c.hEnergy) cudaFreeHost(c.hEnergy);
     if (c.hForce) cudaFreeHost(c.hForce);
     c.hCounters = nullptr; c.hEnergy = nullptr; c.hForce = nullptr;
+    if (c.directStream) cudaStreamDestroy(c.directStream);
+    if (c.evSorted) cudaEventDestroy(c.evSorted);
+    if (c.evDirectDone) cudaEventDestroy(c.evDirectDone);
+    c.directStream = nullptr; c.evSorted = nullptr; c.evDirectDone = nullptr;
 }
 
 } // namespace nbs
@@ -382,13 +387,17 @@ int nbs_create(const nbs_system_desc* desc, nbs_context** out) {
         }
     }
     c.capJ = 2048;
+    c.ownLo = 0; c.ownHi = c.nS;
     c.capX = 256;
     c.profiling = (c.flags & NBS_FLAG_PROFILE) != 0;
     cudaError_t e = cudaSuccess;
-    if ((e = c.dCounters.ensure(16)) != cudaSuccess || (e = c.dEnergy.ensure(2*MAX_SLICES)) != cudaSuccess ||
+    if ((e = c.dCounters.ensure(16)) != cudaSuccess || (e = c.dEnergy.ensure(ENERGY_WORDS)) != cudaSuccess ||
         (e = c.dPairStats.ensure(4)) != cudaSuccess || (e = c.dPairDump.ensure(1)) != cudaSuccess ||
         (e = cudaMallocHost((void**) &c.hCounters, 16*sizeof(int))) != cudaSuccess ||
-        (e = cudaMallocHost((void**) &c.hEnergy, 2*MAX_SLICES*sizeof(double))) != cudaSuccess) {
+        (e = cudaMallocHost((void**) &c.hEnergy, ENERGY_WORDS*sizeof(double))) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&c.directStream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&c.evSorted, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&c.evDirectDone, cudaEventDisableTiming)) != cudaSuccess) {
         releaseAll(c);
         delete ctx;
         return fail(NBS_ERR_CUDA, std::string("allocation failed: ") + cudaGetErrorString(e));
@@ -434,11 +443,17 @@ int nbs_set_global_parameters(nbs_context* ctx, const double* values) {
     return NBS_OK;
 }
 
-int nbs_execute(nbs_context* ctx, const nbs_exec_args* args) {
-    if (!ctx || !args) return fail(NBS_ERR_INVALID, "null argument");
+// ---- one evaluation, in three phases --------------------------------------------------------------
+// A single-rank evaluation (nbs_execute) runs them back to back.  A multi-rank evaluation (one process
+// per GPU) interleaves two exchanges that the caller performs on the same stream:
+//   begin    : sort, neighbour list + pair kernel + exceptions for this rank's i-blocks (on an internal
+//              stream, concurrent with PME), spreading + forward z/y FFT of this rank's subset grids
+//   [exchange: every rank that owns grids receives the other subsets' half spectra]
+//   convolve : fused x pass (cross-subset products per slice, lambda mixing), inverse FFT, force gather
+//   [exchange: all-reduce of the fixed-point force accumulators and of the slice-energy table]
+//   finish   : forces to the caller's layout, energies to the host, host-side constants
+static int validateExec(Context& c, const nbs_exec_args* args) {
     if (args->struct_size != (int32_t) sizeof(nbs_exec_args)) return fail(NBS_ERR_INVALID, "nbs_exec_args.struct_size mismatch");
-    Context& c = ctx->c;
-    NBS_CUDA_CHECK(cudaSetDevice(c.device));
     const double* box = args->box;
     if (box[1] != 0 || box[2] != 0 || box[3] != 0 || box[5] != 0 || box[6] != 0 || box[7] != 0)
         return fail(NBS_ERR_UNSUPPORTED, "triclinic boxes are not implemented on this platform yet");
@@ -455,101 +470,150 @@ int nbs_execute(nbs_context* ctx, const nbs_exec_args* args) {
         return fail(NBS_ERR_INVALID, "fixed-point forces need device memory and padded_num_atoms >= num_particles");
     if (args->atom_index && args->positions_space == NBS_MEM_HOST)
         return fail(NBS_ERR_INVALID, "atom_index requires device-resident positions");
+    return NBS_OK;
+}
+
+static int phaseBegin(Context& c, const nbs_exec_args* args) {
+    int status = validateExec(c, args);
+    if (status != NBS_OK) return status;
+    NBS_CUDA_CHECK(cudaSetDevice(c.device));
+    const double* box = args->box;
     c.stream = (cudaStream_t) args->stream;
     cudaStream_t st = c.stream;
     const bool pme = c.method == NBS_METHOD_PME;
-    const bool wantEnergy = args->slice_energies != nullptr;
-    const bool direct = args->include_direct != 0;
-    const bool recip = args->include_reciprocal != 0 && pme;
+    c.phaseEnergy = args->slice_energies != nullptr;
+    c.phaseDirect = args->include_direct != 0;
+    c.phaseRecip = args->include_reciprocal != 0 && pme;
+    c.phase = 0;
     const int N = c.N;
-    int status;
     if (c.paramsDirty && (status = applyParameters(c)) != NBS_OK) return status;
-
-    for (int attempt = 0; attempt < 6; attempt++) {
-        if ((status = setupGeometry(c, box)) != NBS_OK) return status;
-        timerReset(c);
-        timerMark(c, "begin");
-        // positions
-        PosInput in;
-        in.format = args->positions_format;
-        in.atomIndex = args->atom_index;
-        in.pos64out = nullptr;
-        const double* dPos64 = nullptr;
-        if (args->positions_space == NBS_MEM_HOST) {
+    if ((status = setupGeometry(c, box)) != NBS_OK) return status;
+    timerReset(c);
+    timerMark(c, "begin");
+    // positions
+    PosInput in;
+    in.format = args->positions_format;
+    in.atomIndex = args->atom_index;
+    in.pos64out = nullptr;
+    const double* dPos64 = nullptr;
+    if (args->positions_space == NBS_MEM_HOST) {
+        NBS_CUDA_CHECK(c.dPosIn.ensure(3*(size_t) N));
+        NBS_CUDA_CHECK(cudaMemcpyAsync(c.dPosIn.d, args->positions, sizeof(double)*3*N, cudaMemcpyHostToDevice, st));
+        in.ptr = c.dPosIn.d;
+        dPos64 = c.dPosIn.d;
+    }
+    else {
+        in.ptr = args->positions;
+        if (args->positions_format == NBS_POS_F64_XYZ && !args->atom_index) dPos64 = (const double*) args->positions;
+        else if (c.nExc > 0 && c.phaseDirect) {     // particle-ordered double copy for the exception kernel
             NBS_CUDA_CHECK(c.dPosIn.ensure(3*(size_t) N));
-            NBS_CUDA_CHECK(cudaMemcpyAsync(c.dPosIn.d, args->positions, sizeof(double)*3*N, cudaMemcpyHostToDevice, st));
-            in.ptr = c.dPosIn.d;
+            in.pos64out = c.dPosIn.d;
             dPos64 = c.dPosIn.d;
         }
+    }
+    NBS_CUDA_CHECK(cudaMemsetAsync(c.dForce.d, 0, sizeof(unsigned long long)*3*c.Npad, st));
+    NBS_CUDA_CHECK(cudaMemsetAsync(c.dEnergy.d, 0, sizeof(double)*ENERGY_WORDS, st));
+    NBS_CUDA_CHECK(cudaMemsetAsync(c.dCounters.d, 0, sizeof(int)*16, st));
+    timerMark(c, "h2d_zero");
+    if ((status = launchSort(c, in)) != NBS_OK) return status;
+    if (c.phaseDirect) {
+        // direct space on its own stream so that it overlaps the PME chain (serial when profiling)
+        const bool overlap = !c.profiling && c.phaseRecip && c.directStream != nullptr;
+        if (overlap) {
+            NBS_CUDA_CHECK(cudaEventRecord(c.evSorted, st));
+            NBS_CUDA_CHECK(cudaStreamWaitEvent(c.directStream, c.evSorted, 0));
+            c.stream = c.directStream;
+        }
+        status = launchBuildLists(c);
+        if (status == NBS_OK) status = launchPairs(c, c.phaseEnergy, 0);
+        if (status == NBS_OK && c.nExc > 0) {
+            if (!dPos64) status = fail(NBS_ERR_UNSUPPORTED, "exceptions need double-precision positions in this version");
+            else status = launchBonded(c, dPos64, true);
+        }
+        c.directOverlapped = overlap;
+        if (overlap) {
+            cudaEventRecord(c.evDirectDone, c.directStream);
+            c.stream = st;
+            if (status != NBS_OK) cudaStreamWaitEvent(st, c.evDirectDone, 0);
+        }
+        if (status != NBS_OK) return status;
+    }
+    else c.directOverlapped = false;
+    if (c.phaseRecip && (status = launchPme(c, c.phaseEnergy, 0)) != NBS_OK) {
+        if (c.directOverlapped) cudaStreamWaitEvent(st, c.evDirectDone, 0);
+        return status;
+    }
+    c.phase = 1;
+    return NBS_OK;
+}
+
+static int phaseConvolve(Context& c, const nbs_exec_args* args) {
+    if (c.phase != 1) return fail(NBS_ERR_INVALID, "nbs_execute_convolve called without nbs_execute_begin");
+    NBS_CUDA_CHECK(cudaSetDevice(c.device));
+    cudaStream_t st = c.stream;
+    int status = NBS_OK;
+    if (c.phaseRecip) status = launchPme(c, c.phaseEnergy, 1);
+    if (c.directOverlapped) NBS_CUDA_CHECK(cudaStreamWaitEvent(st, c.evDirectDone, 0));   // join the direct-space stream
+    if (status != NBS_OK) { c.phase = 0; return status; }
+    c.phase = 2;
+    return NBS_OK;
+}
+
+// Returns NBS_OK, an error, or NBS_RETRY: the neighbour-list capacity was exceeded (on this or any
+// other rank), it has been doubled, and the whole evaluation must be repeated.
+static int phaseFinish(Context& c, const nbs_exec_args* args) {
+    if (c.phase != 2) return fail(NBS_ERR_INVALID, "nbs_execute_finish called without nbs_execute_convolve");
+    c.phase = 0;
+    NBS_CUDA_CHECK(cudaSetDevice(c.device));
+    cudaStream_t st = c.stream;
+    const int N = c.N;
+    const double* box = args->box;
+    int status;
+    if (args->forces) {
+        if (args->forces_space == NBS_MEM_DEVICE) {
+            if ((status = launchFinalize(c, args->forces, args->forces_format, args->padded_num_atoms,
+                                         args->forces_accumulate, args->atom_index)) != NBS_OK) return status;
+        }
         else {
-            in.ptr = args->positions;
-            if (args->positions_format == NBS_POS_F64_XYZ && !args->atom_index) dPos64 = (const double*) args->positions;
-            else if (c.nExc > 0 && direct) {     // particle-ordered double copy for the exception kernel
-                NBS_CUDA_CHECK(c.dPosIn.ensure(3*(size_t) N));
-                in.pos64out = c.dPosIn.d;
-                dPos64 = c.dPosIn.d;
-            }
-        }
-        NBS_CUDA_CHECK(cudaMemsetAsync(c.dForce.d, 0, sizeof(unsigned long long)*3*c.Npad, st));
-        NBS_CUDA_CHECK(cudaMemsetAsync(c.dEnergy.d, 0, sizeof(double)*2*MAX_SLICES, st));
-        NBS_CUDA_CHECK(cudaMemsetAsync(c.dCounters.d, 0, sizeof(int)*16, st));
-        timerMark(c, "h2d_zero");
-        if ((status = launchSort(c, in)) != NBS_OK) return status;
-        if (direct) {
-            if ((status = launchBuildLists(c)) != NBS_OK) return status;
-            if ((status = launchPairs(c, wantEnergy, 0)) != NBS_OK) return status;
-            if (c.nExc > 0) {
-                if (!dPos64) return fail(NBS_ERR_UNSUPPORTED, "exceptions need double-precision positions in this version");
-                if ((status = launchBonded(c, dPos64, true)) != NBS_OK) return status;
-            }
-        }
-        if (recip && (status = launchPme(c, wantEnergy)) != NBS_OK) return status;
-        // forces out
-        if (args->forces) {
-            if (args->forces_space == NBS_MEM_DEVICE) {
-                if ((status = launchFinalize(c, args->forces, args->forces_format, args->padded_num_atoms,
-                                             args->forces_accumulate, args->atom_index)) != NBS_OK) return status;
-            }
-            else {
-                NBS_CUDA_CHECK(c.dForceOut.ensure(3*(size_t) N));
-                if ((status = launchFinalize(c, c.dForceOut.d, NBS_FORCE_F64_XYZ, 0, 0, nullptr)) != NBS_OK) return status;
-                if (args->forces_accumulate) {
-                    if (c.hForceCap < 3*(size_t) N) {
-                        if (c.hForce) cudaFreeHost(c.hForce);
-                        NBS_CUDA_CHECK(cudaMallocHost((void**) &c.hForce, sizeof(double)*3*N));
-                        c.hForceCap = 3*(size_t) N;
-                    }
-                    NBS_CUDA_CHECK(cudaMemcpyAsync(c.hForce, c.dForceOut.d, sizeof(double)*3*N, cudaMemcpyDeviceToHost, st));
+            NBS_CUDA_CHECK(c.dForceOut.ensure(3*(size_t) N));
+            if ((status = launchFinalize(c, c.dForceOut.d, NBS_FORCE_F64_XYZ, 0, 0, nullptr)) != NBS_OK) return status;
+            if (args->forces_accumulate) {
+                if (c.hForceCap < 3*(size_t) N) {
+                    if (c.hForce) cudaFreeHost(c.hForce);
+                    NBS_CUDA_CHECK(cudaMallocHost((void**) &c.hForce, sizeof(double)*3*N));
+                    c.hForceCap = 3*(size_t) N;
                 }
-                else
-                    NBS_CUDA_CHECK(cudaMemcpyAsync(args->forces, c.dForceOut.d, sizeof(double)*3*N, cudaMemcpyDeviceToHost, st));
+                NBS_CUDA_CHECK(cudaMemcpyAsync(c.hForce, c.dForceOut.d, sizeof(double)*3*N, cudaMemcpyDeviceToHost, st));
             }
+            else
+                NBS_CUDA_CHECK(cudaMemcpyAsync(args->forces, c.dForceOut.d, sizeof(double)*3*N, cudaMemcpyDeviceToHost, st));
         }
-        NBS_CUDA_CHECK(cudaMemcpyAsync(c.hEnergy, c.dEnergy.d, sizeof(double)*2*MAX_SLICES, cudaMemcpyDeviceToHost, st));
-        NBS_CUDA_CHECK(cudaMemcpyAsync(c.hCounters, c.dCounters.d, sizeof(int)*16, cudaMemcpyDeviceToHost, st));
-        timerMark(c, "d2h");
-        NBS_CUDA_CHECK(cudaStreamSynchronize(st));
-        NBS_CUDA_CHECK(cudaGetLastError());
-        if (c.hCounters[1] == 0) break;
-        // neighbour-list capacity overflow: grow and redo the evaluation
+    }
+    NBS_CUDA_CHECK(cudaMemcpyAsync(c.hEnergy, c.dEnergy.d, sizeof(double)*ENERGY_WORDS, cudaMemcpyDeviceToHost, st));
+    NBS_CUDA_CHECK(cudaMemcpyAsync(c.hCounters, c.dCounters.d, sizeof(int)*16, cudaMemcpyDeviceToHost, st));
+    timerMark(c, "d2h");
+    NBS_CUDA_CHECK(cudaStreamSynchronize(st));
+    NBS_CUDA_CHECK(cudaGetLastError());
+    if (c.hCounters[1] != 0 || c.hEnergy[2*MAX_SLICES] != 0.0) {
+        // neighbour-list capacity overflow (here or, after the all-reduce, on any rank): grow and redo
         if (c.capJ >= 65536) return fail(NBS_ERR_CAPACITY, "neighbour list capacity exceeded (system too dense for the tile list)");
         c.capJ *= 2;
         c.capX *= 2;
-        if (attempt == 5) return fail(NBS_ERR_CAPACITY, "neighbour list capacity exceeded");
+        return NBS_RETRY;
     }
     c.nBlocksLast = c.hCounters[0];
     c.haveLast = true;
-    c.lastDirect = direct;
+    c.lastDirect = c.phaseDirect;
     std::memcpy(c.lastBox, box, sizeof(double)*9);
     if (args->forces && args->forces_space == NBS_MEM_HOST && args->forces_accumulate) {
         double* out = (double*) args->forces;
         for (size_t k = 0; k < 3*(size_t) N; k++) out[k] += c.hForce[k];
     }
-    if (wantEnergy) {
+    if (c.phaseEnergy) {
         double* E = args->slice_energies;
         for (int k = 0; k < 2*c.nSl; k++) E[k] = c.hEnergy[k];
         const double volume = box[0]*box[4]*box[8];
-        if (recip) {
+        if (c.phaseRecip) {
             // self energy and neutralising background, ReferenceSlicedLJCoulombIxn.cpp:203-222
             const double selfFactor = kOne4PiEps0*c.alpha/std::sqrt(kPi);
             const double factor = (-1/(4*c.alpha*c.alpha))/(2*kEpsilon0*volume);
@@ -559,9 +623,77 @@ int nbs_execute(nbs_context* ctx, const nbs_exec_args* args) {
                     E[2*(j*(j+1)/2+i)] += (i == j ? 1 : 2)*c.subsetQ[i]*c.subsetQ[j]*factor;
             }
         }
-        if (direct)   // dispersion correction, ReferenceNonbondedSlicingKernels.cpp:244-249
+        if (c.phaseDirect)   // dispersion correction, ReferenceNonbondedSlicingKernels.cpp:244-249
             for (int s = 0; s < c.nSl; s++) E[2*s+1] += c.dispersion[s]/volume;
     }
+    return NBS_OK;
+}
+
+int nbs_execute(nbs_context* ctx, const nbs_exec_args* args) {
+    if (!ctx || !args) return fail(NBS_ERR_INVALID, "null argument");
+    Context& c = ctx->c;
+    if (c.nRanks != 1) return fail(NBS_ERR_INVALID, "a sharded context is driven through nbs_execute_begin/convolve/finish");
+    for (int attempt = 0; attempt < 7; attempt++) {
+        int status = phaseBegin(c, args);
+        if (status == NBS_OK) status = phaseConvolve(c, args);
+        if (status == NBS_OK) status = phaseFinish(c, args);
+        if (status != NBS_RETRY) return status;
+    }
+    return fail(NBS_ERR_CAPACITY, "neighbour list capacity exceeded");
+}
+
+int nbs_execute_begin(nbs_context* ctx, const nbs_exec_args* args) {
+    if (!ctx || !args) return fail(NBS_ERR_INVALID, "null argument");
+    return phaseBegin(ctx->c, args);
+}
+
+int nbs_execute_convolve(nbs_context* ctx, const nbs_exec_args* args) {
+    if (!ctx || !args) return fail(NBS_ERR_INVALID, "null argument");
+    return phaseConvolve(ctx->c, args);
+}
+
+int nbs_execute_finish(nbs_context* ctx, const nbs_exec_args* args) {
+    if (!ctx || !args) return fail(NBS_ERR_INVALID, "null argument");
+    return phaseFinish(ctx->c, args);
+}
+
+int nbs_set_shard(nbs_context* ctx, int32_t rank, int32_t num_ranks, int32_t block_period, int32_t block_offset,
+                  int32_t block_width, int32_t subset_begin, int32_t subset_end) {
+    if (!ctx) return fail(NBS_ERR_INVALID, "null argument");
+    Context& c = ctx->c;
+    if (num_ranks < 1 || rank < 0 || rank >= num_ranks) return fail(NBS_ERR_INVALID, "illegal rank / num_ranks");
+    if (block_period < 1 || block_width < 0 || block_offset < 0 || block_offset + block_width > block_period)
+        return fail(NBS_ERR_INVALID, "illegal i-block share: need 0 <= offset, offset + width <= period");
+    if (subset_begin < 0 || subset_end > c.nS || subset_begin > subset_end)
+        return fail(NBS_ERR_INVALID, "illegal subset range");
+    c.rank = rank; c.nRanks = num_ranks;
+    c.blockPeriod = block_period; c.blockOffset = block_offset; c.blockWidth = block_width;
+    c.ownLo = subset_begin; c.ownHi = subset_end;
+    c.haveLast = false;
+    return NBS_OK;
+}
+
+int nbs_debug_set_list_capacity(nbs_context* ctx, int32_t j_capacity, int32_t x_capacity) {
+    if (!ctx || j_capacity < 64 || x_capacity < 64 || j_capacity % 32 || x_capacity % 32)
+        return fail(NBS_ERR_INVALID, "capacities must be multiples of 32, at least 64");
+    ctx->c.capJ = j_capacity;
+    ctx->c.capX = x_capacity;
+    return NBS_OK;
+}
+
+int nbs_get_exchange_buffers(nbs_context* ctx, nbs_exchange_buffers* out) {
+    if (!ctx || !out) return fail(NBS_ERR_INVALID, "null argument");
+    Context& c = ctx->c;
+    if (out->struct_size != (int32_t) sizeof(nbs_exchange_buffers)) return fail(NBS_ERR_INVALID, "nbs_exchange_buffers.struct_size mismatch");
+    const bool fp64 = c.phaseEnergy && !(c.flags & NBS_FLAG_FP32_ENERGY);
+    const size_t Gh = (size_t) c.grid[0]*c.grid[1]*(c.grid[2]/2 + 1);
+    out->spectra = c.dGridC.d;
+    out->spectrum_bytes_per_subset = (int64_t) (Gh*(fp64 ? sizeof(double2) : sizeof(float2)));
+    out->spectrum_is_double = fp64 ? 1 : 0;
+    out->forces = c.dForce.d;
+    out->force_words = 3*(int64_t) c.Npad;
+    out->energies = c.dEnergy.d;
+    out->energy_words = ENERGY_WORDS;
     return NBS_OK;
 }
 
@@ -651,9 +783,11 @@ int nbs_get_nlist_stats(nbs_context* ctx, int64_t stats[8]) {
     if (!ctx || !stats) return fail(NBS_ERR_INVALID, "null argument");
     Context& c = ctx->c;
     for (int k = 0; k < 8; k++) stats[k] = 0;
-    if (!c.haveLast || !c.lastDirect) return NBS_OK;
+    if (!c.haveLast || !c.lastDirect || c.blockWidth == 0) return NBS_OK;
     NBS_CUDA_CHECK(cudaSetDevice(c.device));
-    const int nb = c.nBlocksLast;
+    int nb = 0;                                   // rank-local blocks that exist
+    while (nb < c.maxLocalBlocks && localToGlobalBlock(nb, c.blockPeriod, c.blockOffset, c.blockWidth) < c.nBlocksLast) nb++;
+    if (nb == 0) return NBS_OK;
     std::vector<int> jc(nb), xc(nb);
     NBS_CUDA_CHECK(cudaMemcpy(jc.data(), c.dJCount.d, sizeof(int)*nb, cudaMemcpyDeviceToHost));
     NBS_CUDA_CHECK(cudaMemcpy(xc.data(), c.dXCount.d, sizeof(int)*nb, cudaMemcpyDeviceToHost));

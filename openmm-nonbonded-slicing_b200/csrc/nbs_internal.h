@@ -154,16 +154,37 @@ struct Context {
     size_t hForceCap = 0;
     cudaStream_t stream = nullptr;           // stream of the current nbs_execute
     long long stats[8] = {0};
+    // ---- sharding across ranks (one process per GPU; see DESIGN.md "Multi-GPU") ----
+    // Direct space: global i-block b belongs to this rank iff (b % blockPeriod) lies in
+    // [blockOffset, blockOffset + blockWidth).  Lists are stored at the rank-local block index.
+    // PME: this rank owns the charge grids of subsets [ownLo, ownHi).
+    int rank = 0, nRanks = 1;
+    int blockPeriod = 1, blockOffset = 0, blockWidth = 1;
+    int ownLo = 0, ownHi = 0;                // set to [0, nS) at creation
+    int maxLocalBlocks = 0;
+    // ---- phase state of the evaluation in flight ----
+    cudaStream_t directStream = nullptr;     // direct space runs here, concurrently with PME on `stream`
+    cudaEvent_t evSorted = nullptr, evDirectDone = nullptr;
+    bool phaseDirect = false, phaseRecip = false, phaseEnergy = false, directOverlapped = false;
+    const double* phasePos64 = nullptr;
+    int phase = 0;                           // 0 idle, 1 begun, 2 convolved
 };
+
+constexpr int ENERGY_WORDS = 2*MAX_SLICES + 8;   // slice table + [2*MAX_SLICES] = list-overflow flag (as a double, so it all-reduces)
+
+__host__ __device__ inline int localToGlobalBlock(int local, int period, int offset, int width) {
+    return (local/width)*period + offset + local % width;
+}
 
 // ---- launch wrappers (each counts its launches in ctx.launches) ----
 struct PosInput { const void* ptr; int format; const int* atomIndex; double* pos64out; };
 
 int launchSort(Context& c, const PosInput& in);                 // fixed-point conversion, binning, cell sort, blocks
 int launchBuildLists(Context& c);
+int launchExclRange(Context& c);
 int launchPairs(Context& c, bool wantEnergy, int mode);         // mode 0: forces+energy, 1: count/hash pairs, 2: dump pairs
 int launchBonded(Context& c, const double* dPos, bool periodicBox);
-int launchPme(Context& c, bool wantEnergy);
+int launchPme(Context& c, bool wantEnergy, int half);    // half 0: spread..y forward; 1: x/conv..gather
 int launchFinalize(Context& c, void* dOut, int format, long long paddedAtoms, int accumulate, const int* atomIndex);
 int prepareEterm(Context& c);
 int uploadPmeTables(Context& c);

@@ -1,0 +1,424 @@
+"""Multi-GPU evaluation of the SlicedNonbondedForce hot path: one process per GPU.
+
+The reference has no collective anywhere; its only multi-device path is OpenMM's per-device split of
+the direct-space tiles with reciprocal space pinned to device 0
+(platforms/cuda/src/CudaParallelNonbondedSlicingKernels.cpp:35-53;
+platforms/common/src/CommonNonbondedSlicingKernels.cpp:416, 465, 643-646, 725-728).  Here the path is
+sharded where it shards naturally:
+
+  * positions are replicated; every rank sorts them identically (the sort is deterministic), so
+    "sorted atom k" means the same atom everywhere;
+  * direct space: i-blocks are dealt to the ranks in an interleaved pattern (``ShardPlan.block_share``),
+    exceptions round-robin; ranks that own PME grids get a smaller share;
+  * PME: subset grids are assigned to ranks as contiguous ranges (``ShardPlan.subset_range``); spreading,
+    FFTs and gather of a grid happen on its owner.  The sliced convolution needs every subset's
+    spectrum at the same k, so the owners exchange half spectra once (NCCL broadcast inside the group
+    of grid owners);
+  * forces (64-bit fixed point -- integer sums are exact and order independent, so every rank ends up
+    with bit-identical forces) and the slice-energy table are combined with NCCL all-reduce.
+
+``torch.distributed`` is plumbing: the compute is the C ABI's three phases (include/nbslice_b200.h:
+nbs_execute_begin / _convolve / _finish), and the collectives are issued on the same CUDA stream in
+between.  The choreography is written against a small backend protocol so that the CPU tests can run
+it under ``gloo`` with a NumPy stand-in for the kernels (tests/test_multigpu_cpu.py).
+"""
+import ctypes as C
+import json
+import os
+import time
+
+import numpy as np
+
+from . import abi
+from .api import B200CalcSlicedNonbondedForceKernel
+
+PATTERN_PERIOD = 64     # i-blocks are dealt in periods of this many consecutive blocks
+
+
+class ShardPlan:
+    """Which rank does what.  Pure integer logic, identical on every rank."""
+
+    def __init__(self, world_size, num_subsets, direct_share=None, period=PATTERN_PERIOD):
+        if world_size < 1 or num_subsets < 1:
+            raise ValueError("world_size and num_subsets must be positive")
+        self.world_size = world_size
+        self.num_subsets = num_subsets
+        self.num_pme_ranks = min(world_size, num_subsets)
+        self.period = max(period, world_size)
+        if direct_share is None:
+            direct_share = [1.0]*world_size
+        if len(direct_share) != world_size or min(direct_share) < 0 or sum(direct_share) <= 0:
+            raise ValueError("direct_share needs one non-negative entry per rank and a positive sum")
+        self.widths = self._apportion(direct_share, self.period)
+
+    @staticmethod
+    def _apportion(share, total):
+        """Largest-remainder apportionment of `total` slots proportional to `share`."""
+        s = float(sum(share))
+        exact = [total*x/s for x in share]
+        widths = [int(np.floor(e)) for e in exact]
+        order = sorted(range(len(share)), key=lambda r: (-(exact[r]-widths[r]), r))
+        for r in order[:total-sum(widths)]:
+            widths[r] += 1
+        return widths
+
+    def subset_range(self, rank):
+        """Contiguous range [lo, hi) of subsets whose PME grids `rank` owns (empty for rank >= num_pme_ranks)."""
+        if rank >= self.num_pme_ranks:
+            return (0, 0)
+        n, p = self.num_subsets, self.num_pme_ranks
+        return (rank*n//p, (rank+1)*n//p)
+
+    def subset_owner(self, subset):
+        for r in range(self.num_pme_ranks):
+            lo, hi = self.subset_range(r)
+            if lo <= subset < hi:
+                return r
+        raise ValueError("subset out of range")
+
+    def pme_ranks(self):
+        return list(range(self.num_pme_ranks))
+
+    def block_share(self, rank):
+        """(period, offset, width): i-block b is this rank's iff offset <= b % period < offset + width."""
+        return (self.period, sum(self.widths[:rank]), self.widths[rank])
+
+    def block_owner(self, block):
+        k = block % self.period
+        for r in range(self.world_size):
+            _, off, w = self.block_share(r)
+            if off <= k < off+w:
+                return r
+        raise AssertionError
+
+    @classmethod
+    def balanced(cls, world_size, num_subsets, direct_ms, pme_ms_per_rank, period=PATTERN_PERIOD):
+        """Shares that equalise  share_r * direct_ms + pme_ms_per_rank[r]  (all times of ONE rank doing
+        that work alone): share_r = (T - pme_r)/direct_ms with T chosen so the shares sum to 1."""
+        pme = list(pme_ms_per_rank) + [0.0]*(world_size-len(pme_ms_per_rank))
+        active = list(range(world_size))
+        share = [0.0]*world_size
+        while active:
+            T = (direct_ms + sum(pme[r] for r in active))/len(active)
+            negative = [r for r in active if T - pme[r] < 0]
+            if not negative:
+                for r in active:
+                    share[r] = (T - pme[r])/direct_ms
+                break
+            for r in negative:          # this rank is busy with PME alone for longer than the others need
+                active.remove(r)
+        if sum(share) <= 0:
+            share = [1.0]*world_size
+        return cls(world_size, num_subsets, share, period)
+
+    def describe(self):
+        return {"world_size": self.world_size, "pme_ranks": self.num_pme_ranks,
+                "subset_ranges": [self.subset_range(r) for r in range(self.world_size)],
+                "block_pattern": {"period": self.period, "widths": self.widths}}
+
+
+# ---------------------------------------------------------------------------------------------------
+# Choreography (backend-agnostic).  A backend provides, for ONE rank:
+#   begin()                    -> None
+#   spectrum_slabs()           -> list of per-subset tensors (views of the backend's spectra buffer)
+#   convolve()                 -> None
+#   reduce_tensors()           -> list of tensors to all-reduce (sum) in place
+#   finish()                   -> result, or RETRY
+# ---------------------------------------------------------------------------------------------------
+RETRY = object()
+
+
+def exchange_spectra(plan, rank, slabs, dist, group):
+    """Every grid owner receives every other owner's half spectra (one broadcast per subset)."""
+    if plan.num_pme_ranks <= 1 or rank >= plan.num_pme_ranks:
+        return
+    works = []
+    for subset, slab in enumerate(slabs):
+        works.append(dist.broadcast(slab, src=plan.subset_owner(subset), group=group, async_op=True))
+    for w in works:
+        w.wait()
+
+
+def evaluate_distributed(plan, rank, backend, dist, pme_group, max_attempts=7):
+    """One evaluation of this rank's shard, exchanges included.  Collective: every rank must call it."""
+    for _ in range(max_attempts):
+        backend.begin()
+        exchange_spectra(plan, rank, backend.spectrum_slabs(), dist, pme_group)
+        backend.convolve()
+        if plan.world_size > 1:
+            for t in backend.reduce_tensors():
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        result = backend.finish()
+        if result is not RETRY:
+            return result
+    raise RuntimeError("neighbour list capacity exceeded")
+
+
+def evaluate_lockstep(plan, backends, max_attempts=7):
+    """The same choreography for all ranks inside ONE process (several shards on one device, or NumPy
+    stand-ins): collectives are emulated with tensor copies and sums.  Used by the tests to exercise
+    the sharded kernels without a second GPU."""
+    import torch
+    for _ in range(max_attempts):
+        for b in backends:
+            b.begin()
+        slabs = [b.spectrum_slabs() for b in backends]
+        for subset in range(plan.num_subsets):
+            owner = plan.subset_owner(subset)
+            for r in plan.pme_ranks():
+                if r != owner and slabs[r]:
+                    slabs[r][subset].copy_(slabs[owner][subset])
+        for b in backends:
+            b.convolve()
+        tensors = [b.reduce_tensors() for b in backends]
+        for k in range(len(tensors[0])):
+            total = tensors[0][k].clone()
+            for r in range(1, len(backends)):
+                total += tensors[r][k]
+            for r in range(len(backends)):
+                tensors[r][k].copy_(total)
+        if hasattr(torch, "cuda") and torch.cuda.is_available():
+            torch.cuda.synchronize()
+        results = [b.finish() for b in backends]
+        if not any(r is RETRY for r in results):
+            return results
+        assert all(r is RETRY for r in results), "the overflow flag must reach every rank"
+    raise RuntimeError("neighbour list capacity exceeded")
+
+
+# ---------------------------------------------------------------------------------------------------
+# The CUDA backend: one shard of a B200 kernel
+# ---------------------------------------------------------------------------------------------------
+class _DeviceMemory:
+    """Raw device memory exposed through __cuda_array_interface__ so torch can alias it."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def _alias(ptr, shape, typestr, device):
+    import torch
+    return torch.as_tensor(_DeviceMemory(ptr, shape, typestr), device=device)
+
+
+class ShardedB200Kernel(B200CalcSlicedNonbondedForceKernel):
+    """A B200 kernel that evaluates one rank's shard.  `initialize` as usual, then `set_plan`."""
+
+    def set_plan(self, plan, rank):
+        self.plan, self.rank = plan, rank
+        period, offset, width = plan.block_share(rank)
+        lo, hi = plan.subset_range(rank)
+        abi.check(self.lib.nbs_set_shard(self.handle, rank, plan.world_size, period, offset, width, lo, hi))
+
+    # -- backend protocol ---------------------------------------------------------------------------
+    def prepare(self, positions_ptr, box, forces_ptr, lambdas, stream=0, want_energies=True,
+                includeDirect=True, includeReciprocal=True):
+        import torch
+        self._push_parameters(np.asarray(lambdas, dtype=np.float64), np.zeros(0))
+        args = abi.ExecArgs()
+        args.struct_size = C.sizeof(abi.ExecArgs)
+        args.positions_format = abi.NBS_POS_F64_XYZ
+        args.positions_space = abi.NBS_MEM_DEVICE
+        args.forces_format = abi.NBS_FORCE_F64_XYZ
+        args.forces_space = abi.NBS_MEM_DEVICE
+        args.forces_accumulate = 0
+        args.positions = positions_ptr
+        args.forces = forces_ptr
+        args.box[:] = list(np.asarray(box, dtype=np.float64).reshape(9))
+        args.include_forces = 1
+        args.include_energy = 1
+        args.include_direct = int(includeDirect)
+        args.include_reciprocal = int(includeReciprocal)
+        self._energies = np.zeros((self.numSlices, 2)) if want_energies else None
+        args.slice_energies = self._energies.ctypes.data_as(C.POINTER(C.c_double)) if want_energies else None
+        args.stream = stream
+        self._args = args
+        self._device = torch.device("cuda", self.platform.deviceIndex)
+
+    def begin(self):
+        abi.check(self.lib.nbs_execute_begin(self.handle, C.byref(self._args)))
+        ex = abi.ExchangeBuffers()
+        ex.struct_size = C.sizeof(abi.ExchangeBuffers)
+        abi.check(self.lib.nbs_get_exchange_buffers(self.handle, C.byref(ex)))
+        self._ex = ex
+
+    def spectrum_slabs(self):
+        if self.plan.num_pme_ranks <= 1 or self.rank >= self.plan.num_pme_ranks or not self._args.include_reciprocal:
+            return []
+        ex = self._ex
+        words = ex.spectrum_bytes_per_subset//(8 if ex.spectrum_is_double else 4)
+        typestr = "<f8" if ex.spectrum_is_double else "<f4"
+        whole = _alias(ex.spectra, (self.numSubsets, words), typestr, self._device)
+        return [whole[s] for s in range(self.numSubsets)]
+
+    def convolve(self):
+        abi.check(self.lib.nbs_execute_convolve(self.handle, C.byref(self._args)))
+
+    def reduce_tensors(self):
+        ex = self._ex
+        return [_alias(ex.forces, (ex.force_words,), "<i8", self._device),
+                _alias(ex.energies, (ex.energy_words,), "<f8", self._device)]
+
+    def finish(self):
+        status = self.lib.nbs_execute_finish(self.handle, C.byref(self._args))
+        if status == abi.NBS_RETRY:
+            return RETRY
+        abi.check(status)
+        return self._energies
+
+
+def calibrate_plan(kernel_factory, world_size, num_subsets, run_once):
+    """Measure (on this rank, alone) the direct-space time and the PME time of each grid owner's share,
+    and derive a balanced plan.  `kernel_factory(flags)` makes an initialised ShardedB200Kernel and
+    `run_once(kernel)` evaluates it; returns the plan and the measurements (identical inputs on every
+    rank give near-identical plans, but callers broadcast rank 0's to be exact)."""
+    base = ShardPlan(world_size, num_subsets)
+    k = kernel_factory(abi.NBS_FLAG_PROFILE)
+    direct_ms, pme_ms = 0.0, []
+    for r in range(base.num_pme_ranks):
+        # a rank that does all of direct space and subset range r
+        lo, hi = base.subset_range(r)
+        abi.check(k.lib.nbs_set_shard(k.handle, 0, 1, 1, 0, 1, lo, hi))
+        k.plan, k.rank = ShardPlan(1, num_subsets), 0
+        for _ in range(3):
+            run_once(k)
+        times = dict()
+        for name, ms in k.getKernelTimes():
+            times[name] = times.get(name, 0.0) + ms
+        direct_ms = sum(times.get(n, 0.0) for n in ("build_lists", "pair", "bonded"))
+        pme_ms.append(sum(times.get(n, 0.0) for n in ("spread", "fft_fwd", "fft_conv_inv", "gather")))
+    del k
+    plan = ShardPlan.balanced(world_size, num_subsets, direct_ms, pme_ms)
+    return plan, {"direct_ms": direct_ms, "pme_ms_per_owner": pme_ms}
+
+
+# ---------------------------------------------------------------------------------------------------
+# bench.py --gpus N (N > 1): strong scaling of one evaluation of the STMV-size system
+# ---------------------------------------------------------------------------------------------------
+def bench_main(args, workload_name):
+    import importlib
+    import torch
+    import torch.distributed as dist
+    bench = importlib.import_module("bench")
+    systems = importlib.import_module(__package__ + ".systems")
+    from .api import Platform
+
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    s = systems.make_system(workload_name)
+    n, nsl, ns = s.force.getNumParticles(), s.force.getNumSlices(), s.force.getNumSubsets()
+    lam = np.ones((nsl, 2))
+    pos_dev = torch.tensor(s.positions, dtype=torch.float64, device=dev).contiguous()
+    frc_dev = torch.zeros((n, 3), dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def factory(flags):
+        k = ShardedB200Kernel(Platform(deviceIndex=local, flags=flags))
+        k.initialize(s.system, s.force)
+        return k
+
+    def run_alone(k):
+        k.prepare(pos_dev.data_ptr(), s.box, frc_dev.data_ptr(), lam, stream=stream)
+        return evaluate_distributed(ShardPlan(1, ns), 0, k, dist, None)
+
+    # rank 0 calibrates, everybody adopts its plan
+    payload = [None]
+    if rank == 0:
+        plan, calibration = calibrate_plan(factory, world, ns, run_alone)
+        payload = [(plan.widths, calibration)]
+    dist.broadcast_object_list(payload, src=0)
+    widths, calibration = payload[0]
+    plan = ShardPlan(world, ns, [float(w) for w in widths])
+    pme_group = dist.new_group(plan.pme_ranks()) if plan.num_pme_ranks > 1 else None
+
+    kernel = factory(0)
+    kernel.set_plan(plan, rank)
+    flush = torch.empty(256*1024*1024, dtype=torch.uint8, device=dev)
+
+    def step():
+        kernel.prepare(pos_dev.data_ptr(), s.box, frc_dev.data_ptr(), lam, stream=stream)
+        return evaluate_distributed(plan, rank, kernel, dist, pme_group)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    launches0 = kernel.getLaunchCount()
+    sampler = bench.ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.__enter__()
+    # device-resident throughput: per-step CUDA events, L2 flushed between steps outside the events
+    per_step = []
+    for _ in range(args.steps):
+        flush.fill_(1)
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        start.record()
+        energies = step()
+        end.record()
+        torch.cuda.synchronize()
+        per_step.append(start.elapsed_time(end))
+    if sampler:
+        sampler.__exit__()
+    launches = kernel.getLaunchCount()-launches0
+    t = torch.tensor(per_step, dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)               # max over ranks, step by step
+    ms = float(t.mean().item())
+    value = 1e3/ms
+
+    # end to end: host positions in, host forces + energies out, every step
+    pos_host = torch.tensor(s.positions, dtype=torch.float64).pin_memory()
+    frc_host = torch.zeros((n, 3), dtype=torch.float64).pin_memory()
+    e2e = []
+    for it in range(args.warmup + args.steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        pos_dev.copy_(pos_host, non_blocking=True)
+        step()
+        frc_host.copy_(frc_dev, non_blocking=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter()-t0
+        if it >= args.warmup:
+            e2e.append(dt)
+    te = torch.tensor(e2e, dtype=torch.float64, device=dev)
+    dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = 1.0/float(te.mean().item())
+
+    pairs = torch.tensor([kernel.getPairSet(with_pairs=False)[0]], dtype=torch.int64, device=dev)
+    dist.all_reduce(pairs)
+    checksum = float(np.abs(energies).sum())
+    fsum = frc_dev.abs().sum().reshape(1)
+    fmin, fmax = fsum.clone(), fsum.clone()
+    dist.all_reduce(fmin, op=dist.ReduceOp.MIN)
+    dist.all_reduce(fmax, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        grid = s.force.getPMEParameters()[1]
+        line = {
+            "metric": "force+energy evals/s", "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{workload_name}: {s.description}", "atoms": n, "subsets": ns, "pme_grid": grid,
+                       "cutoff_nm": 1.0, "ns_per_day_2fs": bench.ns_per_day(value),
+                       "l2": "256 MiB buffer written between steps, outside the per-step CUDA events",
+                       "neighbour_list": "rebuilt from scratch every step on every rank",
+                       "interacting_pairs": int(pairs.item()), "plan": plan.describe(), "calibration": calibration,
+                       "timing": "CUDA events per step on each rank, max over ranks per step, mean over steps"},
+            "clocks": sampler.summary(),
+            "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(pos_host.numel()*8),
+                    "d2h_bytes_per_step": int(frc_host.numel()*8 + 8*2*nsl), "ns_per_day_2fs": bench.ns_per_day(e2e_value),
+                    "note": "per rank: every rank uploads all positions and downloads all forces"},
+            "gpu_launches": int(launches),
+            "collectives_per_step": {"spectrum_broadcasts": ns if plan.num_pme_ranks > 1 else 0, "all_reduces": 2},
+            "slice_energy_checksum": checksum,
+            "forces_identical_on_all_ranks": bool(fmin.item() == fmax.item()),
+        }
+        print(json.dumps(line))
+    dist.barrier()
+    dist.destroy_process_group()

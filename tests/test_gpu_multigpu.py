@@ -1,0 +1,170 @@
+"""Sharded evaluation on the GPU (run with -m gpu).
+
+* `test_shards_in_lockstep_*`: K shards of one system evaluated by K contexts on ONE device, the two
+  exchanges emulated with tensor copies / sums (multigpu.evaluate_lockstep) -- exercises every sharded
+  kernel path (interleaved i-blocks, round-robin exceptions, own-subset spreading / FFT / gather, owner-
+  of-the-lower-subset slice energies, the split x pass) and must reproduce the unsharded evaluation:
+  forces BIT-exactly where only integer sums differ, i.e. the fixed-point accumulators agree exactly
+  for direct space; PME goes through float atomics, so forces are compared to 1e-6 relative RMS and
+  energies to 1e-9 relative.
+* `test_nccl_two_ranks`: the same through torch.distributed + NCCL on two GPUs (skipped on a 1-GPU box).
+"""
+import importlib
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from helpers import force_rel_rms
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def multigpu():
+    return importlib.import_module("openmm-nonbonded-slicing_b200.multigpu")
+
+
+@pytest.fixture(scope="module")
+def systems():
+    return importlib.import_module("openmm-nonbonded-slicing_b200.systems")
+
+
+def unsharded(nbs, s, lam, direct=True, recip=True):
+    kernel = nbs.B200CalcSlicedNonbondedForceKernel(nbs.Platform())
+    kernel.initialize(s.system, s.force)
+    forces = np.zeros_like(s.positions)
+    e = kernel._evaluate(s.positions, s.box, lam, np.zeros(0), direct, recip, forces)
+    count, h, _ = kernel.getPairSet(with_pairs=False) if direct else (0, 0, None)
+    return forces, e, count, h
+
+
+def run_lockstep(nbs, multigpu, s, lam, plan, direct=True, recip=True):
+    import torch
+    dev = torch.device("cuda:0")
+    pos = torch.tensor(s.positions, dtype=torch.float64, device=dev)
+    shards, outs = [], []
+    for r in range(plan.world_size):
+        k = multigpu.ShardedB200Kernel(nbs.Platform())
+        k.initialize(s.system, s.force)
+        k.set_plan(plan, r)
+        out = torch.zeros_like(pos)
+        k.prepare(pos.data_ptr(), s.box, out.data_ptr(), lam, stream=torch.cuda.current_stream().cuda_stream,
+                  includeDirect=direct, includeReciprocal=recip)
+        shards.append(k)
+        outs.append(out)
+    energies = multigpu.evaluate_lockstep(plan, shards)
+    torch.cuda.synchronize()
+    pairs = [k.getPairSet(with_pairs=False) for k in shards] if direct else []
+    return [o.cpu().numpy() for o in outs], energies, pairs
+
+
+@pytest.mark.parametrize("name,world,share", [("C1", 2, None), ("C2", 3, [1, 2, 2]), ("C3", 2, [1, 3]), ("C3", 4, [0, 1, 2, 2])])
+def test_shards_in_lockstep_match_unsharded(nbs, multigpu, systems, name, world, share):
+    s = systems.make_system(name)
+    ns = s.force.getNumSubsets()
+    lam = np.random.default_rng(5).uniform(0.2, 1.0, size=(s.force.getNumSlices(), 2))
+    for direct, recip in ((True, False), (False, True), (True, True)):
+        ref_f, ref_e, ref_count, ref_hash = unsharded(nbs, s, lam, direct, recip)
+        plan = multigpu.ShardPlan(world, ns, share)
+        forces, energies, pairs = run_lockstep(nbs, multigpu, s, lam, plan, direct, recip)
+        for f, e in zip(forces, energies):
+            assert np.array_equal(f, forces[0])                 # every rank holds the same reduced forces
+            if recip:
+                assert force_rel_rms(f, ref_f) <= 1e-6
+            else:
+                assert np.array_equal(f, ref_f)                 # integer accumulation: bit-exact
+            assert np.allclose(e, ref_e, rtol=1e-9, atol=1e-9)
+        if direct:
+            # the ranks' pair sets are disjoint and their union is the unsharded set
+            assert sum(p[0] for p in pairs) == ref_count
+            assert sum(p[1] for p in pairs) % 2**64 == ref_hash
+
+
+def test_capacity_retry_is_collective(nbs, multigpu, systems):
+    """A dense system overflows the initial list capacity: every shard must retry together."""
+    s = systems.make_system("C2")
+    lam = np.ones((s.force.getNumSlices(), 2))
+    import ctypes as C
+    plan = multigpu.ShardPlan(2, s.force.getNumSubsets())
+    ref_f, ref_e, _, _ = unsharded(nbs, s, lam)
+    import torch
+    dev = torch.device("cuda:0")
+    pos = torch.tensor(s.positions, dtype=torch.float64, device=dev)
+    shards, outs = [], []
+    for r in range(2):
+        k = multigpu.ShardedB200Kernel(nbs.Platform())
+        k.initialize(s.system, s.force)
+        k.set_plan(plan, r)
+        if r == 1:
+            nbs.abi.check(k.lib.nbs_debug_set_list_capacity(k.handle, 256, 64))    # far too small: forces a retry
+        out = torch.zeros_like(pos)
+        k.prepare(pos.data_ptr(), s.box, out.data_ptr(), lam, stream=torch.cuda.current_stream().cuda_stream)
+        shards.append(k)
+        outs.append(out)
+    energies = multigpu.evaluate_lockstep(plan, shards)
+    torch.cuda.synchronize()
+    for o, e in zip(outs, energies):
+        assert force_rel_rms(o.cpu().numpy(), ref_f) <= 1e-6
+        assert np.allclose(e, ref_e, rtol=1e-9, atol=1e-9)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _nccl_worker(rank, world, port, name, out):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        nbs = importlib.import_module("openmm-nonbonded-slicing_b200")
+        multigpu = importlib.import_module("openmm-nonbonded-slicing_b200.multigpu")
+        systems = importlib.import_module("openmm-nonbonded-slicing_b200.systems")
+        s = systems.make_system(name)
+        lam = np.random.default_rng(5).uniform(0.2, 1.0, size=(s.force.getNumSlices(), 2))
+        plan = multigpu.ShardPlan(world, s.force.getNumSubsets())
+        group = dist.new_group(plan.pme_ranks()) if plan.num_pme_ranks > 1 else None
+        k = multigpu.ShardedB200Kernel(nbs.Platform(deviceIndex=rank))
+        k.initialize(s.system, s.force)
+        k.set_plan(plan, rank)
+        pos = torch.tensor(s.positions, dtype=torch.float64, device=dev)
+        frc = torch.zeros_like(pos)
+        k.prepare(pos.data_ptr(), s.box, frc.data_ptr(), lam, stream=torch.cuda.current_stream().cuda_stream)
+        e = multigpu.evaluate_distributed(plan, rank, k, dist, group)
+        torch.cuda.synchronize()
+        out.put((rank, frc.cpu().numpy(), e.copy()))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_nccl_two_ranks(nbs, multigpu, systems):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, "C3", out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = sorted([out.get(timeout=600) for _ in range(2)], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    s = systems.make_system("C3")
+    lam = np.random.default_rng(5).uniform(0.2, 1.0, size=(s.force.getNumSlices(), 2))
+    ref_f, ref_e, _, _ = unsharded(nbs, s, lam)
+    assert np.array_equal(results[0][1], results[1][1])
+    for _, f, e in results:
+        assert force_rel_rms(f, ref_f) <= 1e-6
+        assert np.allclose(e, ref_e, rtol=1e-9, atol=1e-9)

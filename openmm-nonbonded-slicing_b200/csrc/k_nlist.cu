@@ -16,6 +16,7 @@
 // periodic image, so columns before the block's own column are skipped outright.
 #include "nbs_internal.h"
 #include "nbs_device.cuh"
+#include <algorithm>
 
 namespace nbs {
 
@@ -37,6 +38,9 @@ struct BuildArgs {
     const int2* exclRange; const int* exclStart; const int* exclList; const int* origToSorted;
     int* jlist; int* jcount; int* xlist; unsigned* xmask; int* xcount;
     int* overflow;             // counters + 1
+    int* itemCount;            // counters + 2
+    int2* items;               // work items of the pair kernel: (local block, first tile)
+    int chunkTiles, maxItems;
     double* overflowFlag;      // energy[2*MAX_SLICES]: the same flag as a double, so that it all-reduces
 };
 
@@ -164,6 +168,12 @@ __global__ void __launch_bounds__(BUILD_WARPS*32) k_build_lists(BuildArgs a) {
     if (t == 0) {
         a.jcount[lb] = totJ;
         a.xcount[lb] = totX;
+        // work items for the pair kernel: the block's tiles (J tiles, then X tiles) in chunks
+        const int tiles = ((totJ + 31) >> 5) + ((totX + 31) >> 5);
+        const int n = (tiles + a.chunkTiles - 1)/a.chunkTiles;
+        const int base = atomicAdd(a.itemCount, n);
+        for (int k = 0; k < n; k++)
+            if (base + k < a.maxItems) a.items[base + k] = make_int2(lb, k*a.chunkTiles);
     }
     if (overflow && lane == 0) { atomicOr(a.overflow, 1); a.overflowFlag[0] = 1.0; }
 }
@@ -189,6 +199,10 @@ int launchBuildLists(Context& c) {
     a.jlist = c.dJList.d; a.jcount = c.dJCount.d; a.xlist = c.dXList.d; a.xmask = c.dXMask.d; a.xcount = c.dXCount.d;
     a.overflow = c.dCounters.d + 1;
     a.overflowFlag = c.dEnergy.d + 2*MAX_SLICES;
+    a.itemCount = c.dCounters.d + 2;
+    a.items = c.dItems.d;
+    a.chunkTiles = c.chunkTiles;
+    a.maxItems = (int) std::min<size_t>(c.dItems.cap, 0x7fffffff);
     k_build_lists<<<c.maxLocalBlocks, BUILD_WARPS*32, 0, c.stream>>>(a);
     c.launches++;
     timerMark(c, "build_lists");

@@ -4,31 +4,40 @@
 // ReferenceSlicedLJCoulombIxn.cpp:367-445 for PME; :571-631 for the reaction-field cutoff) --
 // per-slice energies are accumulated UNSCALED, forces are scaled by (lambda_vdW, lambda_Coulomb)
 // of the pair's slice.  The structure is not the reference's (which injects a per-pair snippet into
-// OpenMM's tile loop, platforms/common/src/kernels/coulombLennardJones.cc):
-//   * one CTA per i-block, its warps share the block's tile list round-robin;
-//   * a tile = 32 i atoms (one per lane, registers) x 32 j atoms staged in shared memory as
-//     float4 (tile-relative position, charge) + float4 (sigma/2, 2 sqrt(eps), subset);
-//   * lane l meets j slot (l + k) & 31 at step k, so both the i and the j force accumulate in
-//     registers; the j accumulators rotate by one lane per step (3 shuffles);
-//   * positions are 32-bit fixed-point fractional coordinates; each tile converts them once into
-//     floats relative to the i-block's corner, so the cutoff test sees ~1e-7 nm resolution at any box
-//     size, and a pair that lands within 2e-5 nm^2 of the cutoff is re-tested exactly in double from
-//     the integers -- this is what makes the interacting-pair set bit-exact against the oracle;
-//   * per-slice energies (EMODE 2, the default): the in-cutoff pairs of a tile are compacted with warp
-//     ballots into a small shared-memory queue and their energies are evaluated in DOUBLE precision
-//     from the exact integer coordinates, 32 real pairs at a time (no lane is wasted on pairs beyond the
-//     cutoff).  Slice energies are sums of ~10^4..10^8 pair terms of both signs; single precision
-//     cannot deliver 1e-5 of a small net value (DESIGN.md "Precision").  EMODE 1 keeps the cheaper
-//     single-precision energies (2*NS float accumulators per lane), EMODE 0 computes forces only.
-// Bound: FP32 pipe (no tensor-core shaped work here).
+// OpenMM's 32x32 tile loop, platforms/common/src/kernels/coulombLennardJones.cc, and pays the full
+// pair arithmetic for every one of the 1024 pairs of a tile although only ~30% are inside the cutoff):
+//
+//   * WORK ITEMS, PERSISTENT WARPS.  The list builder emits items (i-block, first tile, <= chunk tiles);
+//     every warp of a persistent grid pulls items from a global cursor, so there is no CTA-wide barrier,
+//     no tail of idle warps, and small systems (818 i-blocks at DHFR size) still fill 148 SMs.
+//   * TWO PHASES PER TILE.  Phase A ("cull"): 32 i atoms (one per lane) x 32 j atoms staged in shared
+//     memory as float4; lane l meets j slot (l + k) & 31 at step k; only the squared distance is computed
+//     (~18 instructions per pair) and the pairs inside the cutoff are compacted with a warp ballot into a
+//     per-warp queue.  Phase B ("evaluate"): the queue is drained 32 REAL pairs at a time -- every lane of
+//     every pass does useful arithmetic.  Forces are fp32; with slice energies requested the same pass
+//     evaluates the pair's energies in DOUBLE precision from the exact fixed-point coordinates
+//     (slice energies are sums of 10^4..10^8 terms of both signs; DESIGN.md "Precision").
+//   * Phase B scatters into per-warp shared-memory accumulators with a plain read-modify-write; lanes of
+//     one pass that hit the same atom are found with match.any and take turns in lane order, so the
+//     summation order is fixed -- forces are bit-reproducible.  Per tile (j) and per item (i) the float
+//     sums are converted to 64-bit fixed point and added to the global accumulators (integer adds
+//     commute).
+//   * positions are 32-bit fixed-point fractional coordinates; each tile converts them once into floats
+//     relative to the i-block's corner (~1e-7 nm resolution at any box size); a pair whose fp32 r^2 lands
+//     within 2e-5 nm^2 of the cutoff is re-tested exactly in double from the integers -- this is what
+//     makes the interacting-pair set bit-exact against the oracle.
+// Bound: FP32 / issue rate (no tensor-core shaped work here).
 #include "nbs_internal.h"
 #include "nbs_device.cuh"
+#include <algorithm>
 
 namespace nbs {
 
 struct PairArgs {
     int capJ, capX, Npad;
     int blockPeriod, blockOffset, blockWidth;   // this rank's share of the i-blocks
+    int chunkTiles;                             // tiles per work item
+    int nE;                                     // 2 * number of slices
     float sx, sy, sz;
     double dsx, dsy, dsz;
     float rc2, alpha, krf, crf;
@@ -36,7 +45,8 @@ struct PairArgs {
     int useSwitch;
     double rc2d, alphaD, krfD, crfD;
     const double* q64;                   // sorted charges * sqrt(ONE_4PI_EPS0), double
-    const int* counters;
+    int* counters;                       // [2] number of work items, [3] cursor
+    const int2* items;                   // (local block, first tile)
     const int* blkFirst; const int* blkCount; const uint4* blkLo;
     const uint4* posq; const float4* par;
     const int* jlist; const int* jcount; const int* xlist; const unsigned* xmask; const int* xcount;
@@ -47,6 +57,26 @@ struct PairArgs {
     long long dumpCapacity;
     LambdaTable lam;
 };
+
+// per-warp shared memory
+struct __align__(16) WarpScratch {
+    float4 iPos[32];      // i-block: position relative to the block corner, charge*sqrt(K)
+    float4 iPar[32];      // sigma/2, 2 sqrt(eps), subset, particle index
+    float4 jPos[32];      // current tile
+    float4 jPar[32];
+    float4 fi[32];        // force accumulators (float, one item / one tile)
+    float4 fj[32];
+    uint4 iFix[32];       // exact coordinates, w = subset
+    uint4 jFix[32];
+    double iQ[32];        // charges in double (energy path)
+    double jQ[32];
+    unsigned jMask[32];   // exclusion-list tiles: bit l set = pair (i lane l, this j) is masked
+    unsigned short queue[1024 + 32];
+};
+
+__device__ __forceinline__ float rsqrtFast(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcpFast(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float ex2Fast(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
 // erfc(x)*exp(x^2) for x in [0, 6]: degree-9 polynomial in t = 1/(1 + x/2), relative error 2.7e-7 in
 // fp32 Horner form (fit and verified against scipy.special.erfcx).
@@ -86,6 +116,30 @@ __device__ __forceinline__ double erfcxPolyD(double t) {
     return p;
 }
 
+// exp(-z) for z in [0, 60], double, ~3e-16 relative: 2^n * e^h with a degree-11 Taylor polynomial on
+// |h| <= ln(2)/2 -- the library exp() minus the special cases this kernel cannot hit.
+__device__ __forceinline__ double expNegD(double z) {
+    const double u = -z*1.4426950408889634074;                 // log2(e)
+    const double shifter = 6755399441055744.0;                  // 1.5 * 2^52: rounds to nearest integer
+    const double n = (u + shifter) - shifter;
+    const double g = fma(n, -0.693147180559945286, -z);        // -z - n ln2 (hi part of ln2)
+    const double h = fma(n, -2.31904681384629956e-17, g);      // ... lo part
+    double p = 2.50521083854417188e-08;                          // 1/11!
+    p = fma(p, h, 2.75573192239858907e-07);
+    p = fma(p, h, 2.75573192239858907e-06);
+    p = fma(p, h, 2.48015873015873016e-05);
+    p = fma(p, h, 1.98412698412698413e-04);
+    p = fma(p, h, 1.38888888888888894e-03);
+    p = fma(p, h, 8.33333333333333322e-03);
+    p = fma(p, h, 4.16666666666666644e-02);
+    p = fma(p, h, 1.66666666666666657e-01);
+    p = fma(p, h, 0.5);
+    p = fma(p, h, 1.0);
+    p = fma(p, h, 1.0);
+    const int ni = (int) n;
+    return __hiloint2double(__double2hiint(p) + (ni << 20), __double2loint(p));
+}
+
 // Energy of one pair in double precision from the exact fixed-point coordinates (the wrapped integer
 // difference IS the minimum image for any pair inside the cutoff).  Formulas: ReferenceSlicedLJCoulombIxn.cpp
 // :376-396, 443-444 (PME) and :598-624 (reaction field), switch :380-384, 428-431.
@@ -96,9 +150,11 @@ __device__ __forceinline__ void pairEnergyD(const uint4 fi, const uint4 fj, doub
     const double dy = (double) (int) (fj.y - fi.y)*a.dsy;
     const double dz = (double) (int) (fj.z - fi.z)*a.dsz;
     const double r2 = dx*dx + dy*dy + dz*dz;
-    double y = (double) rsqrtf((float) r2);
-    y = y*fma(-0.5*r2*y, y, 1.5);
-    y = y*fma(-0.5*r2*y, y, 1.5);
+    const float r2f = (float) r2;
+    float yf = rsqrtFast(r2f);
+    yf = yf*fmaf(-0.5f*r2f*yf, yf, 1.5f);              // fp32 Newton step: ~1e-7
+    double y = (double) yf;
+    y = y*fma(-0.5*r2*y, y, 1.5);                       // double Newton step: ~1e-14
     const double r = r2*y;
     double s2 = ((double) sigi + (double) sigj)*y;
     s2 *= s2;
@@ -112,256 +168,248 @@ __device__ __forceinline__ void pairEnergyD(const uint4 fi, const uint4 fj, doub
     if (IS_PME) {
         const double x = a.alphaD*r;
         const double d = fma(0.5, x, 1.0);
-        double t = (double) __frcp_rn((float) d);
-        t = t*fma(-d, t, 2.0);
-        t = t*fma(-d, t, 2.0);
-        ec = qq*y*exp(-x*x)*erfcxPolyD(t);
+        const float df = (float) d;
+        float tf = rcpFast(df);
+        tf = tf*fmaf(-df, tf, 2.f);                     // fp32 Newton step
+        double t = (double) tf;
+        t = t*fma(-d, t, 2.0);                          // double Newton step
+        ec = qq*y*expNegD(x*x)*erfcxPolyD(t);
     }
     else
         ec = qq*(y + a.krfD*r2 - a.crfD);
 }
 
-template <int NS>
-__device__ __forceinline__ float pick(const float (&v)[NS], int s) {
-    float r = v[0];
-#pragma unroll
-    for (int k = 1; k < NS; k++) r = (s == k) ? v[k] : r;
-    return r;
-}
-
-// MODE 0: forces (+ energies when ENERGY); MODE 1: count + hash the interacting pairs; MODE 2: also dump them.
-template <int NS, int EMODE, bool IS_PME, int MODE>
-__global__ void __launch_bounds__(PAIR_WARPS*32) k_pair(const PairArgs a) {
-    constexpr bool ENERGY = EMODE == 1;          // single-precision energies in the main loop
-    constexpr int NE = NS*(NS+1);                // 2 * number of slices
-    const int lb = blockIdx.x;                  // rank-local block index
-    const int b = localToGlobalBlock(lb, a.blockPeriod, a.blockOffset, a.blockWidth);
-    if (b >= a.counters[0]) return;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    __shared__ float4 shPos[PAIR_WARPS][32];
-    __shared__ float4 shPar[PAIR_WARPS][32];
-    __shared__ float shF[PAIR_WARPS][3][32];
+// MODE 0: forces (+ energies per EMODE); MODE 1: count + hash the interacting pairs; MODE 2: also dump them.
+// EMODE 0: forces only; 1: single-precision energies; 2: double-precision energies.
+template <int EMODE, bool IS_PME, int MODE>
+__global__ void __launch_bounds__(PAIR_WARPS*32, 2) k_pair(const PairArgs a) {
+    extern __shared__ __align__(16) unsigned char smemRaw[];
+    __shared__ float2 shLam[MAX_SLICES];
     __shared__ double shE[MAX_SLICES*2];
-    // double-precision energy path: the i-block's exact coordinates / charges, the tile's, and the queue
-    __shared__ uint4 shIFix[EMODE == 2 ? 32 : 1];
-    __shared__ double shIQ[EMODE == 2 ? 32 : 1];
-    __shared__ float2 shISE[EMODE == 2 ? 32 : 1];
-    __shared__ uint4 shJFix[EMODE == 2 ? PAIR_WARPS : 1][32];
-    __shared__ double shJQ[EMODE == 2 ? PAIR_WARPS : 1][32];
-    __shared__ unsigned short shQueue[EMODE == 2 ? PAIR_WARPS : 1][64];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpScratch& w = reinterpret_cast<WarpScratch*>(smemRaw)[warp];
+    if (threadIdx.x < MAX_SLICES) shLam[threadIdx.x] = make_float2(a.lam.c[threadIdx.x], a.lam.v[threadIdx.x]);
+    if (threadIdx.x < MAX_SLICES*2) shE[threadIdx.x] = 0.0;
+    __syncthreads();
 
-    const int first = a.blkFirst[b], cnt = a.blkCount[b];
-    const uint4 lo = a.blkLo[b];
-    const bool iValid = lane < cnt;
-    const uint4 pi = iValid ? a.posq[first + lane] : lo;
-    const float4 pari = iValid ? a.par[first + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
-    float xi = (float) (pi.x - lo.x)*a.sx, yi = (float) (pi.y - lo.y)*a.sy, zi = (float) (pi.z - lo.z)*a.sz;
-    if (!iValid) xi = 1.0e8f;
-    const float qi = iValid ? __uint_as_float(pi.w) : 0.f;
-    const float sigi = pari.x, epsi = pari.y;
-    const int si = __float_as_int(pari.z);
-    const unsigned origI = (unsigned) __float_as_int(pari.w);
-    float lamC[NS], lamV[NS];
-#pragma unroll
-    for (int s = 0; s < NS; s++) { int sl = triSlice(si, s); lamC[s] = a.lam.c[sl]; lamV[s] = a.lam.v[sl]; }
-
-    double acc[NE];                               // EMODE 2: [slice][term], dynamically indexed
-    int qn = 0;
-    if (EMODE == 2) {
-#pragma unroll
-        for (int k = 0; k < NE; k++) acc[k] = 0.0;
-        if (warp == 0) {
-            shIFix[lane] = make_uint4(pi.x, pi.y, pi.z, (unsigned) si);
-            shIQ[lane] = iValid ? a.q64[first + lane] : 0.0;
-            shISE[lane] = make_float2(sigi, epsi);
-        }
-        __syncthreads();
-    }
     const unsigned below = (1u << lane) - 1u;
-    // evaluate `count` queued pairs (one per lane) in double and add them to the lane's slice table
-    auto drainQueue = [&](int count) {
-        if (lane < count) {
-            const unsigned e = shQueue[warp][lane];
-            const int il = e >> 5, js = e & 31;
-            const uint4 fi = shIFix[il], fj = shJFix[warp][js];
-            const float2 sei = shISE[il];
-            const float4 prj = shPar[warp][js];
-            double ec, ev;
-            pairEnergyD<IS_PME>(fi, fj, shIQ[il], shJQ[warp][js], sei.x, prj.x, sei.y, prj.y, a, ec, ev);
-            const int sl = triSlice((int) fi.w, (int) fj.w);
-            acc[2*sl] += ec;
-            acc[2*sl+1] += ev;
-        }
-    };
-
-    float fix = 0.f, fiy = 0.f, fiz = 0.f;
-    float eC[NS], eV[NS];
+    const int nItems = a.counters[2];
+    const float TWO_OVER_SQRT_PI = 1.1283791670955126f;
+    double acc[MAX_SLICES*2];                     // [slice][term], dynamically indexed (local memory, L1-resident)
+    if (EMODE != 0) {
 #pragma unroll
-    for (int s = 0; s < NS; s++) { eC[s] = 0.f; eV[s] = 0.f; }
+        for (int k = 0; k < MAX_SLICES*2; k++) acc[k] = 0.0;
+    }
     unsigned long long nPairs = 0, hPairs = 0;
 
-    const int nJ = a.jcount[lb], nX = a.xcount[lb];
-    const int tJ = (nJ + 31) >> 5, tX = (nX + 31) >> 5;
-    const int* jl = a.jlist + (size_t) lb*a.capJ;
-    const int* xl = a.xlist + (size_t) lb*a.capX;
-    const unsigned* xm = a.xmask + (size_t) lb*a.capX;
-    const float TWO_OVER_SQRT_PI = 1.1283791670955126f;
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(a.counters + 3, 1);
+        item = __shfl_sync(FULL_MASK, item, 0);
+        if (item >= nItems) break;
+        const int2 it = a.items[item];
+        const int lb = it.x;
+        const int b = localToGlobalBlock(lb, a.blockPeriod, a.blockOffset, a.blockWidth);
+        const int first = a.blkFirst[b], cnt = a.blkCount[b];
+        const uint4 lo = a.blkLo[b];
+        const bool iValid = lane < cnt;
+        const uint4 pi = iValid ? a.posq[first + lane] : lo;
+        const float4 pari = iValid ? a.par[first + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+        float xi = (float) (pi.x - lo.x)*a.sx;
+        const float yi = (float) (pi.y - lo.y)*a.sy, zi = (float) (pi.z - lo.z)*a.sz;
+        if (!iValid) xi = 1.0e8f;
+        __syncwarp();
+        w.iPos[lane] = make_float4(xi, yi, zi, iValid ? __uint_as_float(pi.w) : 0.f);
+        w.iPar[lane] = pari;
+        w.fi[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+        w.iFix[lane] = make_uint4(pi.x, pi.y, pi.z, (unsigned) __float_as_int(pari.z));
+        if (EMODE == 2) w.iQ[lane] = iValid ? a.q64[first + lane] : 0.0;
 
-    for (int t = warp; t < tJ + tX; t += PAIR_WARPS) {
-        const bool isX = t >= tJ;
-        const int* list = isX ? xl + (t - tJ)*32 : jl + t*32;
-        const int entry = list[lane];
-        unsigned imask = isX ? xm[(t - tJ)*32 + lane] : 0u;
-        float4 pj = make_float4(-1.0e8f, 0.f, 0.f, 0.f), parj = make_float4(0.f, 0.f, 0.f, 0.f);
-        int jIndex = 0;
-        if (entry >= 0) {
-            jIndex = entry & J_INDEX_MASK;
-            const int code = entry >> J_SHIFT_BITS;
-            const int kx = code % 3 - 1, ky = (code/3) % 3 - 1, kz = code/9 - 1;
-            const uint4 q = a.posq[jIndex];
-            parj = a.par[jIndex];
-            pj.x = (float) ((long long) q.x + ((long long) kx << 32) - (long long) lo.x)*a.sx;
-            pj.y = (float) ((long long) q.y + ((long long) ky << 32) - (long long) lo.y)*a.sy;
-            pj.z = (float) ((long long) q.z + ((long long) kz << 32) - (long long) lo.z)*a.sz;
-            pj.w = __uint_as_float(q.w);
-        }
-        __syncwarp();
-        shPos[warp][lane] = pj;
-        shPar[warp][lane] = parj;
-        if (EMODE == 2) {
-            uint4 fj = make_uint4(0u, 0u, 0u, 0u);
-            double qj = 0.0;
+        const int nJ = a.jcount[lb], nX = a.xcount[lb];
+        const int tJ = (nJ + 31) >> 5, tX = (nX + 31) >> 5;
+        const int tEnd = min(it.y + a.chunkTiles, tJ + tX);
+        const int* jl = a.jlist + (size_t) lb*a.capJ;
+        const int* xl = a.xlist + (size_t) lb*a.capX;
+        const unsigned* xm = a.xmask + (size_t) lb*a.capX;
+
+        for (int t = it.y; t < tEnd; t++) {
+            const bool isX = t >= tJ;
+            const int entry = isX ? xl[(t - tJ)*32 + lane] : jl[t*32 + lane];
+            float4 pj = make_float4(-1.0e8f, 0.f, 0.f, 0.f), parj = make_float4(0.f, 0.f, 0.f, 0.f);
+            uint4 fixj = make_uint4(0u, 0u, 0u, 0u);
+            int jIndex = 0;
             if (entry >= 0) {
+                jIndex = entry & J_INDEX_MASK;
+                const int code = entry >> J_SHIFT_BITS;
+                const int kx = code % 3 - 1, ky = (code/3) % 3 - 1, kz = code/9 - 1;
                 const uint4 q = a.posq[jIndex];
-                fj = make_uint4(q.x, q.y, q.z, (unsigned) __float_as_int(parj.z));
-                qj = a.q64[jIndex];
+                parj = a.par[jIndex];
+                pj.x = (float) ((long long) q.x + ((long long) kx << 32) - (long long) lo.x)*a.sx;
+                pj.y = (float) ((long long) q.y + ((long long) ky << 32) - (long long) lo.y)*a.sy;
+                pj.z = (float) ((long long) q.z + ((long long) kz << 32) - (long long) lo.z)*a.sz;
+                pj.w = __uint_as_float(q.w);
+                fixj = make_uint4(q.x, q.y, q.z, (unsigned) __float_as_int(parj.z));
             }
-            shJFix[warp][lane] = fj;
-            shJQ[warp][lane] = qj;
-        }
-        __syncwarp();
-        unsigned excluded = 0;                 // bit s: the pair (this lane's i, j slot s) is masked
-        if (isX) {
+            __syncwarp();
+            w.jPos[lane] = pj;
+            w.jPar[lane] = parj;
+            w.jFix[lane] = fixj;
+            w.fj[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (EMODE == 2) w.jQ[lane] = entry >= 0 ? a.q64[jIndex] : 0.0;
+            if (isX) w.jMask[lane] = xm[(t - tJ)*32 + lane];
+            __syncwarp();
+
+            // ---- phase A: cull.  Queue entry = (i lane << 5) | j slot ----
+            int qn = 0;
 #pragma unroll 4
-            for (int bit = 0; bit < 32; bit++) {
-                unsigned m = __ballot_sync(FULL_MASK, (imask >> bit) & 1u);
-                if (lane == bit) excluded = m;
-            }
-        }
-        float fjx = 0.f, fjy = 0.f, fjz = 0.f;
-#pragma unroll 2
-        for (int k = 0; k < 32; k++) {
-            const int js = (lane + k) & 31;
-            const float4 p = shPos[warp][js];
-            const float4 pr = shPar[warp][js];
-            const float dx = xi - p.x, dy = yi - p.y, dz = zi - p.z;
-            const float r2 = fmaf(dx, dx, fmaf(dy, dy, dz*dz));
-            bool in = r2 <= a.rc2;
-            if (fabsf(r2 - a.rc2) < 2.0e-5f) {
-                // borderline: decide from the exact integer coordinates, in double
-                const int e2 = list[js];
-                if (e2 >= 0 && iValid) {
-                    const int code = e2 >> J_SHIFT_BITS;
-                    const uint4 q = a.posq[e2 & J_INDEX_MASK];
-                    const double ex = (double) ((long long) q.x + ((long long) (code % 3 - 1) << 32) - (long long) pi.x)*a.dsx;
-                    const double ey = (double) ((long long) q.y + ((long long) ((code/3) % 3 - 1) << 32) - (long long) pi.y)*a.dsy;
-                    const double ez = (double) ((long long) q.z + ((long long) (code/9 - 1) << 32) - (long long) pi.z)*a.dsz;
+            for (int k = 0; k < 32; k++) {
+                const int js = (lane + k) & 31;
+                const float4 p = w.jPos[js];
+                const float dx = xi - p.x, dy = yi - p.y, dz = zi - p.z;
+                const float r2 = fmaf(dx, dx, fmaf(dy, dy, dz*dz));
+                bool in = r2 <= a.rc2;
+                if (fabsf(r2 - a.rc2) < 2.0e-5f) {
+                    // borderline: decide from the exact integer coordinates, in double
+                    const uint4 fj = w.jFix[js];
+                    const double ex = (double) (int) (fj.x - pi.x)*a.dsx;
+                    const double ey = (double) (int) (fj.y - pi.y)*a.dsy;
+                    const double ez = (double) (int) (fj.z - pi.z)*a.dsz;
                     in = ex*ex + ey*ey + ez*ez <= a.rc2d;
                 }
-            }
-            if (isX) in = in && !((excluded >> js) & 1u);
-            if (EMODE == 2 && MODE == 0) {
+                if (isX) in = in && !((w.jMask[js] >> lane) & 1u);
                 const unsigned m = __ballot_sync(FULL_MASK, in);
-                if (m) {
-                    if (in) shQueue[warp][qn + __popc(m & below)] = (unsigned short) ((lane << 5) | js);
-                    qn += __popc(m);
-                    if (qn >= 32) {
-                        __syncwarp();
-                        drainQueue(32);
-                        const int rest = qn - 32;
-                        const unsigned short moved = lane < rest ? shQueue[warp][32 + lane] : (unsigned short) 0;
-                        __syncwarp();
-                        if (lane < rest) shQueue[warp][lane] = moved;
-                        qn = rest;
-                    }
-                }
+                if (in) w.queue[qn + __popc(m & below)] = (unsigned short) ((lane << 5) | js);
+                qn += __popc(m);
             }
+            __syncwarp();
+
             if (MODE != 0) {
-                if (in) {
-                    const unsigned origJ = (unsigned) __float_as_int(pr.w);
-                    const unsigned f = min(origI, origJ), s = max(origI, origJ);
-                    nPairs++;
-                    hPairs += pairHash(f, s);
-                    if (MODE == 2) {
-                        unsigned long long slot = atomicAdd(a.pairStats + 2, 1ull);
-                        if ((long long) slot < a.dumpCapacity) a.pairDump[slot] = make_int2((int) f, (int) s);
+                // the interacting-pair set itself (parity diagnostics)
+                for (int base = 0; base < qn; base += 32) {
+                    if (base + lane < qn) {
+                        const unsigned e = w.queue[base + lane];
+                        const unsigned oi = (unsigned) __float_as_int(w.iPar[e >> 5].w), oj = (unsigned) __float_as_int(w.jPar[e & 31].w);
+                        const unsigned f = min(oi, oj), s = max(oi, oj);
+                        nPairs++;
+                        hPairs += pairHash(f, s);
+                        if (MODE == 2) {
+                            unsigned long long slot = atomicAdd(a.pairStats + 2, 1ull);
+                            if ((long long) slot < a.dumpCapacity) a.pairDump[slot] = make_int2((int) f, (int) s);
+                        }
                     }
                 }
                 continue;
             }
-            float invR = rsqrtf(r2);
-            invR = invR*fmaf(-0.5f*r2*invR, invR, 1.5f);            // one Newton step
-            const float r = r2*invR;
-            const float qq = qi*p.w;
-            const float sig = sigi + pr.x;
-            float s2 = sig*invR;
-            s2 *= s2;
-            const float s6 = s2*s2*s2;
-            const float eps = epsi*pr.y;
-            const float invR2 = invR*invR;
-            float ev = eps*(s6 - 1.f)*s6;
-            float fv = eps*fmaf(12.f, s6, -6.f)*s6*invR2;
-            float ec, fc;
-            if (IS_PME) {
-                const float ar = a.alpha*r;
-                const float ex = __expf(-ar*ar);
-                const float tt = __fdividef(1.f, fmaf(0.5f, ar, 1.f));
-                const float erfcv = ex*erfcxPoly(tt);
-                const float qr = qq*invR;
-                ec = qr*erfcv;
-                fc = qr*invR2*fmaf(TWO_OVER_SQRT_PI*ar, ex, erfcv);
-            }
-            else {
-                ec = qq*(invR + a.krf*r2 - a.crf);
-                fc = qq*invR2*(invR - 2.f*a.krf*r2);
-            }
-            if (a.useSwitch && r > a.rswitch) {
-                const float w = 1.f/(a.rcut - a.rswitch);
-                const float u = (r - a.rswitch)*w;
-                const float sv = 1.f + u*u*u*(-10.f + u*(15.f - u*6.f));
-                const float sd = u*u*(-30.f + u*(60.f - u*30.f))*w;
-                fv = sv*fv - ev*sd*invR;
-                ev *= sv;
-            }
-            const int sj = __float_as_int(pr.z);
-            float dEdR = pick<NS>(lamV, sj)*fv + pick<NS>(lamC, sj)*fc;
-            dEdR = in ? dEdR : 0.f;
-            fix = fmaf(dEdR, dx, fix); fiy = fmaf(dEdR, dy, fiy); fiz = fmaf(dEdR, dz, fiz);
-            fjx = fmaf(-dEdR, dx, fjx); fjy = fmaf(-dEdR, dy, fjy); fjz = fmaf(-dEdR, dz, fjz);
-            if (ENERGY) {
-                ec = in ? ec : 0.f;
-                ev = in ? ev : 0.f;
-#pragma unroll
-                for (int s = 0; s < NS; s++) {
-                    eC[s] += (sj == s) ? ec : 0.f;
-                    eV[s] += (sj == s) ? ev : 0.f;
+
+            // ---- phase B: evaluate, 32 real pairs per pass ----
+            for (int base = 0; base < qn; base += 32) {
+                const bool active = base + lane < qn;
+                int il = 32 + lane, js = 32 + lane;            // unique dummies for idle lanes
+                float fx = 0.f, fy = 0.f, fz = 0.f;
+                if (active) {
+                    const unsigned e = w.queue[base + lane];
+                    il = e >> 5; js = e & 31;
+                    const float4 p1 = w.iPos[il], q1 = w.iPar[il], p2 = w.jPos[js], q2 = w.jPar[js];
+                    const float dx = p1.x - p2.x, dy = p1.y - p2.y, dz = p1.z - p2.z;
+                    const float r2 = fmaf(dx, dx, fmaf(dy, dy, dz*dz));
+                    float invR = rsqrtFast(r2);
+                    invR = invR*fmaf(-0.5f*r2*invR, invR, 1.5f);            // one Newton step
+                    const float r = r2*invR;
+                    const float qq = p1.w*p2.w;
+                    const float sig = q1.x + q2.x;
+                    float s2 = sig*invR;
+                    s2 *= s2;
+                    const float s6 = s2*s2*s2;
+                    const float eps = q1.y*q2.y;
+                    const float invR2 = invR*invR;
+                    float ev = eps*(s6 - 1.f)*s6;
+                    float fv = eps*fmaf(12.f, s6, -6.f)*s6*invR2;
+                    float ec, fc;
+                    if (IS_PME) {
+                        const float ar = a.alpha*r;
+                        const float ex = ex2Fast(-1.4426950408889634f*ar*ar);
+                        const float tt = rcpFast(fmaf(0.5f, ar, 1.f));
+                        const float erfcv = ex*erfcxPoly(tt);
+                        const float qr = qq*invR;
+                        ec = qr*erfcv;
+                        fc = qr*invR2*fmaf(TWO_OVER_SQRT_PI*ar, ex, erfcv);
+                    }
+                    else {
+                        ec = qq*(invR + a.krf*r2 - a.crf);
+                        fc = qq*invR2*(invR - 2.f*a.krf*r2);
+                    }
+                    if (a.useSwitch && r > a.rswitch) {
+                        const float wd = 1.f/(a.rcut - a.rswitch);
+                        const float u = (r - a.rswitch)*wd;
+                        const float sv = 1.f + u*u*u*(-10.f + u*(15.f - u*6.f));
+                        const float sd = u*u*(-30.f + u*(60.f - u*30.f))*wd;
+                        fv = sv*fv - ev*sd*invR;
+                        ev *= sv;
+                    }
+                    const int sl = triSlice(__float_as_int(q1.z), __float_as_int(q2.z));
+                    const float2 lam = shLam[sl];
+                    const float dEdR = lam.y*fv + lam.x*fc;
+                    fx = dEdR*dx; fy = dEdR*dy; fz = dEdR*dz;
+                    if (EMODE == 1) {
+                        acc[2*sl] += (double) ec;
+                        acc[2*sl+1] += (double) ev;
+                    }
+                    if (EMODE == 2) {
+                        double ecd, evd;
+                        pairEnergyD<IS_PME>(w.iFix[il], w.jFix[js], w.iQ[il], w.jQ[js], q1.x, q2.x, q1.y, q2.y, a, ecd, evd);
+                        acc[2*sl] += ecd;
+                        acc[2*sl+1] += evd;
+                    }
+                }
+                // scatter: lanes that share an atom take turns in lane order (fixed summation order)
+                {
+                    const unsigned peers = __match_any_sync(FULL_MASK, il);
+                    const int rank = __popc(peers & below);
+                    unsigned pending = __ballot_sync(FULL_MASK, active);
+                    for (int round = 0; pending; round++) {
+                        if (active && rank == round) {
+                            float4 f = w.fi[il];
+                            f.x += fx; f.y += fy; f.z += fz;
+                            w.fi[il] = f;
+                        }
+                        __syncwarp();
+                        pending = __ballot_sync(FULL_MASK, active && rank > round);
+                    }
+                }
+                {
+                    const unsigned peers = __match_any_sync(FULL_MASK, js);
+                    const int rank = __popc(peers & below);
+                    unsigned pending = __ballot_sync(FULL_MASK, active);
+                    for (int round = 0; pending; round++) {
+                        if (active && rank == round) {
+                            float4 f = w.fj[js];
+                            f.x -= fx; f.y -= fy; f.z -= fz;
+                            w.fj[js] = f;
+                        }
+                        __syncwarp();
+                        pending = __ballot_sync(FULL_MASK, active && rank > round);
+                    }
                 }
             }
-            const int src = (lane + 1) & 31;
-            fjx = __shfl_sync(FULL_MASK, fjx, src);
-            fjy = __shfl_sync(FULL_MASK, fjy, src);
-            fjz = __shfl_sync(FULL_MASK, fjz, src);
+            // j forces of this tile -> global fixed point
+            if (entry >= 0) {
+                const float4 f = w.fj[lane];
+                if (f.x != 0.f || f.y != 0.f || f.z != 0.f) {
+                    atomicAdd(a.force + jIndex, toFixed(f.x));
+                    atomicAdd(a.force + a.Npad + jIndex, toFixed(f.y));
+                    atomicAdd(a.force + 2*(size_t) a.Npad + jIndex, toFixed(f.z));
+                }
+            }
         }
-        if (EMODE == 2 && MODE == 0) {              // the queue refers to this tile's shared-memory slots
+        // i forces of this item -> global fixed point
+        if (MODE == 0) {
             __syncwarp();
-            drainQueue(qn);
-            qn = 0;
-            __syncwarp();
-        }
-        if (MODE == 0 && entry >= 0) {
-            atomicAdd(a.force + jIndex, toFixed(fjx));
-            atomicAdd(a.force + a.Npad + jIndex, toFixed(fjy));
-            atomicAdd(a.force + 2*(size_t) a.Npad + jIndex, toFixed(fjz));
+            if (iValid) {
+                const float4 f = w.fi[lane];
+                atomicAdd(a.force + first + lane, toFixed(f.x));
+                atomicAdd(a.force + a.Npad + first + lane, toFixed(f.y));
+                atomicAdd(a.force + 2*(size_t) a.Npad + first + lane, toFixed(f.z));
+            }
         }
     }
 
@@ -375,63 +423,33 @@ __global__ void __launch_bounds__(PAIR_WARPS*32) k_pair(const PairArgs a) {
         }
         return;
     }
-
-    // fold the i forces of the CTA's warps in a fixed order, then one fixed-point atomic per atom
-    shF[warp][0][lane] = fix; shF[warp][1][lane] = fiy; shF[warp][2][lane] = fiz;
-    if (EMODE != 0 && threadIdx.x < MAX_SLICES*2) shE[threadIdx.x] = 0.0;
-    __syncthreads();
-    if (threadIdx.x < 96) {
-        const int comp = threadIdx.x >> 5;
-        float sum = 0.f;
-#pragma unroll
-        for (int w = 0; w < PAIR_WARPS; w++) sum += shF[w][comp][lane];
-        if (lane < cnt) atomicAdd(a.force + (size_t) comp*a.Npad + first + lane, toFixed(sum));
-    }
-    if (ENERGY) {
-        // slice(sa, sb) gets eX[sb] of lanes whose atom is in sa, and eX[sa] of lanes in sb (sa != sb)
-#pragma unroll
-        for (int sa = 0; sa < NS; sa++)
-#pragma unroll
-            for (int sb = sa; sb < NS; sb++) {
-                double c = 0.0, v = 0.0;
-                if (si == sa) { c += eC[sb]; v += eV[sb]; }
-                if (sa != sb && si == sb) { c += eC[sa]; v += eV[sa]; }
-                c = warpSum(c);
-                v = warpSum(v);
-                if (lane == 0) {
-                    const int sl = sb*(sb+1)/2 + sa;
-                    atomicAdd(&shE[2*sl], c);
-                    atomicAdd(&shE[2*sl+1], v);
-                }
-            }
-        __syncthreads();
-        if (threadIdx.x < NS*(NS+1)) atomicAdd(a.energy + threadIdx.x, shE[threadIdx.x]);
-    }
-    if (EMODE == 2) {
-#pragma unroll
-        for (int k = 0; k < NE; k++) {
+    if (EMODE != 0) {
+        for (int k = 0; k < a.nE; k++) {
             const double v = warpSum(acc[k]);
             if (lane == 0 && v != 0.0) atomicAdd(&shE[k], v);
         }
         __syncthreads();
-        if (threadIdx.x < NE && shE[threadIdx.x] != 0.0) atomicAdd(a.energy + threadIdx.x, shE[threadIdx.x]);
+        if (threadIdx.x < MAX_SLICES*2 && shE[threadIdx.x] != 0.0) atomicAdd(a.energy + threadIdx.x, shE[threadIdx.x]);
     }
 }
 
-template <int NS>
-static void launchPairNS(Context& c, const PairArgs& a, int emode, bool pme) {
-    dim3 grid(c.maxLocalBlocks), block(PAIR_WARPS*32);
-    cudaStream_t st = c.stream;
-    if (pme) {
-        if (emode == 0) k_pair<NS, 0, true, 0><<<grid, block, 0, st>>>(a);
-        else if (emode == 1) k_pair<NS, 1, true, 0><<<grid, block, 0, st>>>(a);
-        else k_pair<NS, 2, true, 0><<<grid, block, 0, st>>>(a);
+template <int EMODE, bool IS_PME, int MODE>
+static int launchPairT(Context& c, const PairArgs& a) {
+    static bool attr[64] = {false};
+    const size_t smem = sizeof(WarpScratch)*PAIR_WARPS;
+    if (!attr[c.device & 63]) {
+        NBS_CUDA_CHECK(cudaFuncSetAttribute(k_pair<EMODE, IS_PME, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        attr[c.device & 63] = true;
     }
-    else {
-        if (emode == 0) k_pair<NS, 0, false, 0><<<grid, block, 0, st>>>(a);
-        else if (emode == 1) k_pair<NS, 1, false, 0><<<grid, block, 0, st>>>(a);
-        else k_pair<NS, 2, false, 0><<<grid, block, 0, st>>>(a);
+    // persistent grid: as many CTAs as are resident at once
+    static int perSM[64] = {0};
+    if (perSM[c.device & 63] == 0) {
+        int n = 0;
+        NBS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_pair<EMODE, IS_PME, MODE>, PAIR_WARPS*32, smem));
+        perSM[c.device & 63] = std::max(1, n);
     }
+    k_pair<EMODE, IS_PME, MODE><<<perSM[c.device & 63]*c.numSMs, PAIR_WARPS*32, smem, c.stream>>>(a);
+    return NBS_OK;
 }
 
 int launchPairs(Context& c, bool wantEnergy, int mode) {
@@ -440,6 +458,8 @@ int launchPairs(Context& c, bool wantEnergy, int mode) {
     PairArgs a;
     a.capJ = c.capJ; a.capX = c.capX; a.Npad = c.Npad;
     a.blockPeriod = c.blockPeriod; a.blockOffset = c.blockOffset; a.blockWidth = c.blockWidth;
+    a.chunkTiles = c.chunkTiles;
+    a.nE = 2*c.nSl;
     a.sx = g.scale[0]; a.sy = g.scale[1]; a.sz = g.scale[2];
     a.dsx = g.box[0]/4294967296.0; a.dsy = g.box[1]/4294967296.0; a.dsz = g.box[2]/4294967296.0;
     a.rc2 = (float) (c.cutoff*c.cutoff);
@@ -456,6 +476,7 @@ int launchPairs(Context& c, bool wantEnergy, int mode) {
     a.rswitch = (float) c.switchDist;
     a.rcut = (float) c.cutoff;
     a.counters = c.dCounters.d;
+    a.items = c.dItems.d;
     a.blkFirst = c.dBlkFirst.d; a.blkCount = c.dBlkCount.d; a.blkLo = c.dBlkLo.d;
     a.posq = c.dPosq.d; a.par = c.dPar.d;
     a.jlist = c.dJList.d; a.jcount = c.dJCount.d; a.xlist = c.dXList.d; a.xmask = c.dXMask.d; a.xcount = c.dXCount.d;
@@ -469,19 +490,15 @@ int launchPairs(Context& c, bool wantEnergy, int mode) {
         a.lam.v[s] = s < c.nSl ? (float) c.lambdas[2*s+1] : 1.f;
     }
     const bool pme = c.method == NBS_METHOD_PME;
-    dim3 grid(c.maxLocalBlocks), block(PAIR_WARPS*32);
     const int emode = !wantEnergy ? 0 : ((c.flags & NBS_FLAG_FP32_ENERGY) ? 1 : 2);
-    if (mode == 1) k_pair<1, 0, true, 1><<<grid, block, 0, c.stream>>>(a);
-    else if (mode == 2) k_pair<1, 0, true, 2><<<grid, block, 0, c.stream>>>(a);
-    else {
-        switch (c.nS) {
-            case 1: launchPairNS<1>(c, a, emode, pme); break;
-            case 2: launchPairNS<2>(c, a, emode, pme); break;
-            case 3: launchPairNS<3>(c, a, emode, pme); break;
-            case 4: launchPairNS<4>(c, a, emode, pme); break;
-            default: launchPairNS<MAX_SUBSETS>(c, a, emode, pme); break;
-        }
+    int status;
+    if (mode != 0) {
+        NBS_CUDA_CHECK(cudaMemsetAsync(c.dCounters.d + 3, 0, sizeof(int), c.stream));      // rewind the work cursor
+        status = mode == 1 ? launchPairT<0, true, 1>(c, a) : launchPairT<0, true, 2>(c, a);
     }
+    else if (pme) status = emode == 0 ? launchPairT<0, true, 0>(c, a) : (emode == 1 ? launchPairT<1, true, 0>(c, a) : launchPairT<2, true, 0>(c, a));
+    else status = emode == 0 ? launchPairT<0, false, 0>(c, a) : (emode == 1 ? launchPairT<1, false, 0>(c, a) : launchPairT<2, false, 0>(c, a));
+    if (status != NBS_OK) return status;
     c.launches++;
     timerMark(c, mode == 0 ? "pair" : "pair_set");
     return NBS_OK;

@@ -73,16 +73,15 @@ __device__ __forceinline__ int blockExclusiveScan(int v, int* warpSums, int& tot
 
 __global__ void __launch_bounds__(1024) k_scan_single(const int* __restrict__ in, int* __restrict__ out, int n) {
     __shared__ int warpSums[33];
-    int carry = 0;
-    for (int base = 0; base < n; base += 1024) {
-        int i = base + threadIdx.x;
-        int v = i < n ? in[i] : 0;
-        int total;
-        int ex = blockExclusiveScan(v, warpSums, total);
-        if (i < n) out[i] = carry + ex;
-        carry += total;
-    }
-    if (threadIdx.x == 0) out[n] = carry;
+    // every thread owns a contiguous run of `per` elements: one block-wide scan in total
+    const int per = (n + 1023) >> 10;
+    const int begin = min(n, (int) threadIdx.x*per), end = min(n, begin + per);
+    int sum = 0;
+    for (int i = begin; i < end; i++) sum += in[i];
+    int total;
+    int ex = blockExclusiveScan(sum, warpSums, total);
+    for (int i = begin; i < end; i++) { const int v = in[i]; out[i] = ex; ex += v; }
+    if (threadIdx.x == 0) out[n] = total;
 }
 
 __global__ void __launch_bounds__(1024) k_scan_tiles(const int* __restrict__ in, int* __restrict__ out, int n, int* __restrict__ tileSums) {
@@ -136,65 +135,30 @@ __global__ void k_scatter(int N, const uint4* __restrict__ fix, const int* __res
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_bin_finalize: one thread per bin.  Orders the bin's particles by particle index (so that the
-// sorted order, and with it every floating-point sum downstream, is reproducible) and gathers the
-// sorted per-atom records.
+// k_place: one thread per scattered slot.  The final position of a particle inside its bin is its
+// rank by particle index among the bin's members (so the sorted order -- and with it every
+// floating-point sum downstream -- is reproducible whatever order the scatter's atomics ran in);
+// the thread then writes the particle's sorted records.  Bins hold a handful of atoms (1/8 of a
+// block height), so the rank is a short scan of the bin.
 // ---------------------------------------------------------------------------------------------
-__device__ void heapSort(int* a, int n) {
-    for (int start = n/2-1; start >= 0; start--) {
-        int root = start;
-        for (;;) {
-            int child = 2*root+1;
-            if (child >= n) break;
-            if (child+1 < n && a[child] < a[child+1]) child++;
-            if (a[root] >= a[child]) break;
-            int t = a[root]; a[root] = a[child]; a[child] = t;
-            root = child;
-        }
-    }
-    for (int end = n-1; end > 0; end--) {
-        int t = a[0]; a[0] = a[end]; a[end] = t;
-        int root = 0;
-        for (;;) {
-            int child = 2*root+1;
-            if (child >= end) break;
-            if (child+1 < end && a[child] < a[child+1]) child++;
-            if (a[root] >= a[child]) break;
-            int u = a[root]; a[root] = a[child]; a[child] = u;
-            root = child;
-        }
-    }
-}
-
-__global__ void k_bin_finalize(int nBins, const int* __restrict__ binStart, int* __restrict__ sortedToOrig,
-                               int* __restrict__ origToSorted, const uint4* __restrict__ fix,
-                               const float* __restrict__ chargeF, const float2* __restrict__ sigEps,
-                               const int* __restrict__ subset, const double* __restrict__ charge, double sqrtK,
-                               uint4* __restrict__ posq, float4* __restrict__ par, double* __restrict__ q64) {
-    int bin = blockIdx.x*blockDim.x + threadIdx.x;
-    if (bin >= nBins) return;
-    int s = binStart[bin], e = binStart[bin+1];
-    int n = e - s;
-    if (n > 1) {
-        if (n <= 24) {
-            for (int i = s+1; i < e; i++) {
-                int v = sortedToOrig[i], j = i-1;
-                while (j >= s && sortedToOrig[j] > v) { sortedToOrig[j+1] = sortedToOrig[j]; j--; }
-                sortedToOrig[j+1] = v;
-            }
-        }
-        else
-            heapSort(sortedToOrig + s, n);
-    }
-    for (int slot = s; slot < e; slot++) {
-        int p = sortedToOrig[slot];
-        uint4 f = fix[p];
-        float2 se = sigEps[p];
-        posq[slot] = make_uint4(f.x, f.y, f.z, __float_as_uint(chargeF[p]));
-        par[slot] = make_float4(se.x, se.y, __int_as_float(subset[p]), __int_as_float(p));
-        q64[slot] = charge[p]*sqrtK;
-        origToSorted[p] = slot;
-    }
+__global__ void k_place(int N, const int* __restrict__ binStart, const int* __restrict__ scattered,
+                        int* __restrict__ origToSorted, const uint4* __restrict__ fix,
+                        const float* __restrict__ chargeF, const float2* __restrict__ sigEps,
+                        const int* __restrict__ subset, const double* __restrict__ charge, double sqrtK,
+                        uint4* __restrict__ posq, float4* __restrict__ par, double* __restrict__ q64) {
+    const int s = blockIdx.x*blockDim.x + threadIdx.x;
+    if (s >= N) return;
+    const int p = scattered[s];
+    const uint4 f = fix[p];
+    const int begin = binStart[f.w], end = binStart[f.w + 1];
+    int rank = 0;
+    for (int k = begin; k < end; k++) rank += scattered[k] < p ? 1 : 0;
+    const int slot = begin + rank;
+    const float2 se = sigEps[p];
+    posq[slot] = make_uint4(f.x, f.y, f.z, __float_as_uint(chargeF[p]));
+    par[slot] = make_float4(se.x, se.y, __int_as_float(subset[p]), __int_as_float(p));
+    q64[slot] = charge[p]*sqrtK;
+    origToSorted[p] = slot;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -275,9 +239,9 @@ int launchSort(Context& c, const PosInput& in) {
     int status = scanExclusive(c, c.dBinCount.d, c.dBinStart.d, g.nBins);
     if (status != NBS_OK) return status;
     k_scatter<<<(N+T-1)/T, T, 0, st>>>(N, c.dFix.d, c.dBinStart.d, c.dBinCursor.d, c.dSortedToOrig.d);
-    k_bin_finalize<<<(g.nBins+T-1)/T, T, 0, st>>>(g.nBins, c.dBinStart.d, c.dSortedToOrig.d, c.dOrigToSorted.d, c.dFix.d,
-                                                  c.dChargeF.d, c.dSigEps.d, c.dSubset.d, c.dCharge.d, sqrt(kOne4PiEps0),
-                                                  c.dPosq.d, c.dPar.d, c.dQ64.d);
+    k_place<<<(N+T-1)/T, T, 0, st>>>(N, c.dBinStart.d, c.dSortedToOrig.d, c.dOrigToSorted.d, c.dFix.d,
+                                     c.dChargeF.d, c.dSigEps.d, c.dSubset.d, c.dCharge.d, sqrt(kOne4PiEps0),
+                                     c.dPosq.d, c.dPar.d, c.dQ64.d);
     // dBinCount is reused for the per-column block counts
     k_col_blocks<<<(g.nCols+T-1)/T, T, 0, st>>>(g.nCols, g.nzb, c.dBinStart.d, c.dBinCount.d);
     c.launches += 3;

@@ -302,6 +302,10 @@ static int setupGeometry(Context& c, const double box[9]) {
     NBS_CUDA_CHECK(c.dJList.ensure((size_t) c.maxLocalBlocks*c.capJ));
     NBS_CUDA_CHECK(c.dXList.ensure((size_t) c.maxLocalBlocks*c.capX));
     NBS_CUDA_CHECK(c.dXMask.ensure((size_t) c.maxLocalBlocks*c.capX));
+    // work items: enough warps' worth of items to balance 148 SMs x 16 warps on small systems, larger
+    // chunks (fewer i-force flushes) on big ones
+    c.chunkTiles = N < 150000 ? 2 : (N < 600000 ? 4 : 8);
+    NBS_CUDA_CHECK(c.dItems.ensure((size_t) c.maxLocalBlocks*(((c.capJ + c.capX)/32 + c.chunkTiles - 1)/c.chunkTiles + 1)));
     NBS_CUDA_CHECK(c.dForce.ensure(3*(size_t) c.Npad));
     return NBS_OK;
 }
@@ -321,6 +325,7 @@ static int checkDevice(int device) {
     return NBS_OK;
 }
 
+
 static void releaseAll(Context& c) {
     timerReset(c);
     c.dSubset.release(); c.dChargeF.release(); c.dSigEps.release(); c.dCharge.release();
@@ -329,7 +334,7 @@ static void releaseAll(Context& c) {
     c.dBinCursor.release(); c.dScanTmp.release(); c.dSortedToOrig.release(); c.dOrigToSorted.release();
     c.dPosq.release(); c.dPar.release(); c.dQ64.release(); c.dColBlockStart.release(); c.dBlkFirst.release(); c.dBlkCount.release();
     c.dBlkLo.release(); c.dBlkHi.release(); c.dExclRange.release(); c.dJList.release(); c.dJCount.release();
-    c.dXList.release(); c.dXCount.release(); c.dXMask.release(); c.dCounters.release(); c.dForce.release();
+    c.dXList.release(); c.dXCount.release(); c.dXMask.release(); c.dCounters.release(); c.dForce.release(); c.dItems.release();
     c.dEnergy.release(); c.dGrid.release(); c.dGridC.release(); c.dEterm.release(); c.dModuli.release();
     c.dPot.release(); c.dEtermD.release(); c.dTwiddleD.release();
     c.dTwiddle.release(); c.dPairStats.release(); c.dPairDump.release();
@@ -387,6 +392,7 @@ int nbs_create(const nbs_system_desc* desc, nbs_context** out) {
         }
     }
     c.capJ = 2048;
+    { cudaDeviceProp prop; if (cudaGetDeviceProperties(&prop, c.device) == cudaSuccess) c.numSMs = prop.multiProcessorCount; }
     c.ownLo = 0; c.ownHi = c.nS;
     c.capX = 256;
     c.profiling = (c.flags & NBS_FLAG_PROFILE) != 0;

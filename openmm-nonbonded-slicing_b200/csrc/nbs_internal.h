@@ -121,8 +121,9 @@ struct Context {
     Buf<uint4> dBlkLo, dBlkHi;               // fixed-point bounding box; lo.w = column index
     Buf<int2> dExclRange;                    // per sorted atom: [min, max] sorted index of its exclusion partners
     Buf<int> dJList, dJCount, dXList, dXCount;
+    Buf<int2> dItems;                        // pair-kernel work items (local block, first tile)
     Buf<unsigned> dXMask;
-    Buf<int> dCounters;                      // [0] nBlocks, [1] overflow flags, [2..] stats
+    Buf<int> dCounters;                      // [0] nBlocks, [1] overflow flag, [2] pair work items, [3] work cursor
     Buf<unsigned long long> dForce;          // [3][Npad]
     Buf<double> dEnergy;                     // [MAX_SLICES][2]
     Buf<double> dGrid;                       // charge grid [nS][nx][ny][nz] (double or float view)
@@ -162,6 +163,8 @@ struct Context {
     int blockPeriod = 1, blockOffset = 0, blockWidth = 1;
     int ownLo = 0, ownHi = 0;                // set to [0, nS) at creation
     int maxLocalBlocks = 0;
+    int chunkTiles = 2;                      // tiles per pair-kernel work item
+    int numSMs = 148;
     // ---- phase state of the evaluation in flight ----
     cudaStream_t directStream = nullptr;     // direct space runs here, concurrently with PME on `stream`
     cudaEvent_t evSorted = nullptr, evDirectDone = nullptr;

@@ -72,6 +72,8 @@ extern "C" {
 #define NBS_FLAG_DETERMINISTIC   0x1u  /* fixed-point PME spreading (DeterministicForces)   */
 #define NBS_FLAG_PROFILE         0x2u  /* record CUDA events around every kernel            */
 #define NBS_FLAG_NO_GRAPH        0x4u  /* plain stream launches instead of a CUDA graph     */
+#define NBS_FLAG_LINE_FFT        0x10u /* always use the line-at-a-time FFT kernels (the path for
+                                          grids whose planes exceed shared memory); test hook     */
 #define NBS_FLAG_FP32_ENERGY     0x8u  /* single-precision pair energies and PME grids (the
                                           plugin's "single" precision); default is double
                                           precision for every energy term, fp32 for forces    */

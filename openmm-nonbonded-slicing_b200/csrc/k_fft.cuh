@@ -1,0 +1,36 @@
+// k_fft.cuh -- argument blocks of the plane-fused FFT kernels (k_fft.cu), shared with k_pme.cu.
+#ifndef NBS_K_FFT_CUH_
+#define NBS_K_FFT_CUH_
+#include "nbs_internal.h"
+
+namespace nbs {
+
+constexpr int FFT_THREADS = 512;
+constexpr int FFT_UNPACK_Q = 4;      // (row pair, kz) items a thread stages per round of the real<->complex (un)packing
+
+struct PlaneFftPlan {
+    unsigned long long factors[3];   // radices of nx, ny, nz: 4 bits each, first pass in the low bits
+};
+
+struct PlaneFftArgs {
+    int nS, nx, ny, nz, nzh;
+    int ownLo, ownHi;                // subsets whose grids this rank transforms / produces
+    int rowStride;                   // zy / yz kernels: complex elements per plane row in shared memory
+    int chunk;                       // x kernel: kz values per CTA
+    unsigned long long factorsX, factorsY, factorsZ;
+    const void* twx; const void* twy; const void* twz;     // exp(-2 pi i k / n), precision T
+    const void* grid;                // real charge grids   [nS][nx][ny][nz]      (T)
+    void* gridC;                     // half spectra        [nS][nx][ny][nz/2+1]  (complex T)
+    const void* eterm;               // influence function  [nx][ny][nz/2+1]      (T)
+    float* pot;                      // potential grids     [nS][nx][ny][nz]      (float)
+    double* energy;
+    int wantEnergy;
+    LambdaTable lam;
+};
+
+// NBS_OK: launched.  NBS_RETRY: the grid does not fit this path (use the line-at-a-time kernels).
+template <typename T>
+int launchPlaneFft(Context& c, const PlaneFftPlan& plan, PlaneFftArgs a, int half);
+
+} // namespace nbs
+#endif

@@ -1,0 +1,495 @@
+// k_fft.inl -- plane-fused 3D real FFT for the sliced PME path (used whenever a (y, kz) plane of one
+// subset fits in shared memory; k_pme.cu keeps the line-at-a-time kernels for larger grids).
+//
+// The reference calls a library here (cuFFT / VkFFT batched over subsets: platforms/cuda/src/
+// CudaCuFFT3D.cpp:47-83, CudaVkFFT3D.cpp:17-79; pocketfft c2c on the Reference platform,
+// ReferencePME.cpp:793-805).  PME grids are small (64^3 .. 180^3): the transform is bound by launch
+// latency and by round trips through L2/HBM, not by flops.  So the chain is three kernels with one
+// global read and one global write each:
+//   k_fft_zy_fwd : CTA = one (subset, x) plane.  Real rows -> shared, z transform (two real rows ride
+//                  one complex line), unpack to half spectra, y transform down the columns, store.
+//   k_fft_x_conv2: CTA = one y, a chunk of kz, ALL subsets: forward x transform, influence function,
+//                  per-slice structure-factor products E_IJ (ReferencePME.cpp:487-491), lambda mixing
+//                  G_I = eterm * sum_J lambda_IJ S_J, inverse x transform.
+//   k_fft_yz_inv : CTA = one (subset, x) plane: inverse y, pack, inverse z, float potential grid out.
+// Inside a CTA a pass is BATCHED over all lines of the plane: every thread owns whole radix-R
+// butterflies (radices 2, 3, 4, 5, 7; 11 and 13 in a rolled form), reads them into registers, the CTA
+// synchronises, and the results are written back in place (Stockham autosort order).
+#include "nbs_internal.h"
+#include "nbs_device.cuh"
+#include "k_fft.cuh"
+#include <algorithm>
+// compiled twice (k_fft_f32.cu, k_fft_f64.cu define NBS_FFT_REAL) so that the two precisions build in parallel
+
+namespace nbs {
+
+template <typename T> struct Cx2;
+template <> struct Cx2<float> { typedef float2 type; };
+template <> struct Cx2<double> { typedef double2 type; };
+__device__ __forceinline__ float2 mkc(float x, float y) { return make_float2(x, y); }
+__device__ __forceinline__ double2 mkc(double x, double y) { return make_double2(x, y); }
+template <typename C> __device__ __forceinline__ C cmulc(C a, C b) { return mkc(a.x*b.x - a.y*b.y, a.x*b.y + a.y*b.x); }
+template <typename C> __device__ __forceinline__ C caddc(C a, C b) { return mkc(a.x + b.x, a.y + b.y); }
+template <typename C> __device__ __forceinline__ C csubc(C a, C b) { return mkc(a.x - b.x, a.y - b.y); }
+
+// One Stockham pass of radix R, batched over `lines` lines of length n, executed by the whole CTA.
+// Element e of line L lives at base[L*lineStride + e*elemStride].  Work item = one butterfly; consecutive
+// threads take consecutive butterflies of a line when the line is contiguous (elemStride == 1) and
+// consecutive lines otherwise, which keeps shared-memory accesses on distinct banks.  Q = butterflies a
+// thread may own: the CTA reads (and twiddles) everything into registers, synchronises, and only then
+// computes the size-R DFTs and writes them back, one output at a time -- the pass is in place and needs
+// no second register copy.
+template <int R, int Q, typename C>
+__device__ __forceinline__ void batchedPass(C* base, int lines, int lineStride, int elemStride, int n, int Ns, const C* tw) {
+    const int nb = n/R;
+    const int count = lines*nb;
+    const int tstep = n/(Ns*R), rstep = n/R;
+    C v[Q][R];
+    int dst[Q];
+#pragma unroll
+    for (int q = 0; q < Q; q++) {
+        const int wi = threadIdx.x + q*blockDim.x;
+        dst[q] = -1;
+        if (wi < count) {
+            int L, j;
+            if (elemStride == 1) { L = wi/nb; j = wi - L*nb; }
+            else { j = wi/lines; L = wi - j*lines; }
+            const C* line = base + (size_t) L*lineStride;
+#pragma unroll
+            for (int t = 0; t < R; t++) v[q][t] = line[(j + t*nb)*elemStride];
+            const int k = j % Ns;
+            if (Ns > 1) {
+#pragma unroll
+                for (int t = 1; t < R; t++) v[q][t] = cmulc(v[q][t], tw[t*k*tstep]);
+            }
+            dst[q] = L*lineStride + ((j/Ns)*Ns*R + k)*elemStride;
+        }
+    }
+    __syncthreads();
+    const int os = Ns*elemStride;
+    if (R == 2) {
+#pragma unroll
+        for (int q = 0; q < Q; q++)
+            if (dst[q] >= 0) {
+                base[dst[q]] = caddc(v[q][0], v[q][1]);
+                base[dst[q] + os] = csubc(v[q][0], v[q][1]);
+            }
+    }
+    else if (R == 4) {
+#pragma unroll
+        for (int q = 0; q < Q; q++)
+            if (dst[q] >= 0) {
+                const C a0 = caddc(v[q][0], v[q][2]), a1 = csubc(v[q][0], v[q][2]);
+                const C a2 = caddc(v[q][1], v[q][3]), a3 = csubc(v[q][1], v[q][3]);
+                base[dst[q]] = caddc(a0, a2);
+                base[dst[q] + os] = mkc(a1.x + a3.y, a1.y - a3.x);        // a1 - i a3
+                base[dst[q] + 2*os] = csubc(a0, a2);
+                base[dst[q] + 3*os] = mkc(a1.x - a3.y, a1.y + a3.x);      // a1 + i a3
+            }
+    }
+    else {
+        C root[R];                                   // exp(-2 pi i m / R)
+#pragma unroll
+        for (int m = 0; m < R; m++) root[m] = tw[m*rstep];
+#pragma unroll
+        for (int q = 0; q < Q; q++)
+            if (dst[q] >= 0) {
+#pragma unroll
+                for (int o = 0; o < R; o++) {
+                    C acc = v[q][0];
+#pragma unroll
+                    for (int t = 1; t < R; t++) {
+                        const C w = root[(o*t) % R];
+                        acc.x += v[q][t].x*w.x - v[q][t].y*w.y;
+                        acc.y += v[q][t].x*w.y + v[q][t].y*w.x;
+                    }
+                    base[dst[q] + o*os] = acc;
+                }
+            }
+    }
+    __syncthreads();
+}
+
+// Radix 11 / 13 (rare grid sizes): rolled loops, one butterfly per loop trip, via a scratch copy.
+template <typename C>
+__device__ __noinline__ void batchedPassLarge(C* base, int lines, int lineStride, int elemStride, int n, int R, int Ns, const C* tw) {
+    const int nb = n/R, count = lines*nb, tstep = n/(Ns*R), rstep = n/R;
+    // at most FFT_MAX_Q_LARGE butterflies per thread are staged in registers
+    C v[2][13];
+    int dst[2];
+    for (int q = 0; q < 2; q++) {
+        const int wi = threadIdx.x + q*blockDim.x;
+        dst[q] = -1;
+        if (wi < count) {
+            int L, j;
+            if (elemStride == 1) { L = wi/nb; j = wi - L*nb; }
+            else { j = wi/lines; L = wi - j*lines; }
+            const C* line = base + (size_t) L*lineStride;
+            const int k = j % Ns;
+            for (int t = 0; t < R; t++) {
+                C x = line[(j + t*nb)*elemStride];
+                v[q][t] = t == 0 ? x : cmulc(x, tw[t*k*tstep]);
+            }
+            dst[q] = L*lineStride + ((j/Ns)*Ns*R + k)*elemStride;
+        }
+    }
+    __syncthreads();
+    for (int q = 0; q < 2; q++) {
+        if (dst[q] < 0) continue;
+        for (int o = 0; o < R; o++) {
+            C acc = v[q][0];
+            for (int t = 1; t < R; t++) {
+                const C z = tw[((o*t) % R)*rstep];
+                acc.x += v[q][t].x*z.x - v[q][t].y*z.y;
+                acc.y += v[q][t].x*z.y + v[q][t].y*z.x;
+            }
+            base[dst[q] + o*Ns*elemStride] = acc;
+        }
+    }
+    __syncthreads();
+}
+
+// Forward (e^{-i...}) unnormalised FFT of `lines` lines, by the whole CTA.  Q is sized by the host so
+// that Q*blockDim >= lines*n/R for every unrolled radix of the plan.
+template <int Q, int RMAX, typename C>
+__device__ __forceinline__ void batchedFft(C* base, int lines, int lineStride, int elemStride, int n,
+                                           unsigned long long factors, const C* tw) {
+    // RMAX = largest radix this instantiation carries code for (4, 5, 7 or 13): small-radix plans get
+    // kernels with fewer registers and more CTAs per SM
+    int Ns = 1;
+    for (; factors != 0; factors >>= 4) {
+        const int R = (int) (factors & 15);
+        if (R == 4) batchedPass<4, Q>(base, lines, lineStride, elemStride, n, Ns, tw);
+        else if (R == 2) batchedPass<2, 2*Q>(base, lines, lineStride, elemStride, n, Ns, tw);
+        else if (R == 3) batchedPass<3, (4*Q + 2)/3>(base, lines, lineStride, elemStride, n, Ns, tw);
+        else if (RMAX >= 5 && R == 5) batchedPass<5, Q>(base, lines, lineStride, elemStride, n, Ns, tw);
+        else if (RMAX >= 7 && R == 7) batchedPass<7, Q>(base, lines, lineStride, elemStride, n, Ns, tw);
+        else if (RMAX >= 13) batchedPassLarge(base, lines, lineStride, elemStride, n, R, Ns, tw);
+        Ns *= R;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// zy forward: real grid [s][x][y][z] -> half spectrum [s][x][y][kz], transformed along z and y.
+// Shared plane: ny rows of `rs` complex numbers (rs >= nz/2 + 1, and 2*rs >= nz so that the complex line
+// of a row pair fits in the pair's two rows).
+// ---------------------------------------------------------------------------------------------
+template <typename T, int Q, int RMAX>
+__global__ void __launch_bounds__(FFT_THREADS) k_fft_zy_fwd(const PlaneFftArgs a) {
+    typedef typename Cx2<T>::type C;
+    extern __shared__ double2 fftSmem[];
+    C* sm = (C*) fftSmem;
+    const int ny = a.ny, nz = a.nz, nzh = a.nzh, rs = a.rowStride;
+    C* twz = sm;
+    C* twy = sm + nz;
+    C* plane = sm + nz + ny;
+    for (int k = threadIdx.x; k < nz; k += blockDim.x) twz[k] = ((const C*) a.twz)[k];
+    for (int k = threadIdx.x; k < ny; k += blockDim.x) twy[k] = ((const C*) a.twy)[k];
+    const int sx = a.ownLo*a.nx + blockIdx.x;                   // (own subset, x) plane
+    const T* grid = (const T*) a.grid + (size_t) sx*ny*nz;
+    const int pairs = (ny + 1) >> 1;
+    for (int idx = threadIdx.x; idx < pairs*nz; idx += blockDim.x) {
+        const int p = idx/nz, z = idx - p*nz;
+        const T re = grid[(size_t) (2*p)*nz + z];
+        const T im = 2*p + 1 < ny ? grid[(size_t) (2*p + 1)*nz + z] : (T) 0;
+        plane[(size_t) p*2*rs + z] = mkc(re, im);
+    }
+    __syncthreads();
+    batchedFft<Q, RMAX>(plane, pairs, 2*rs, 1, nz, a.factorsZ, twz);
+    // unpack Z -> the two rows' half spectra: S0[k] = (Z[k] + conj Z[n-k])/2, S1[k] = (Z[k] - conj Z[n-k])/(2i).
+    // In place, so a round stages whole row pairs in registers before anything is written.
+    {
+        const int pairsPerRound = max(1, (FFT_THREADS*FFT_UNPACK_Q)/nzh);
+        const T half = (T) 0.5;
+        for (int p0 = 0; p0 < pairs; p0 += pairsPerRound) {
+            const int count = min(pairsPerRound, pairs - p0)*nzh;
+            C zk[FFT_UNPACK_Q], zn[FFT_UNPACK_Q];
+#pragma unroll
+            for (int q = 0; q < FFT_UNPACK_Q; q++) {
+                const int wi = threadIdx.x + q*blockDim.x;
+                if (wi < count) {
+                    const int p = p0 + wi/nzh, k = wi % nzh;
+                    const C* line = plane + (size_t) p*2*rs;
+                    zk[q] = line[k];
+                    zn[q] = line[k == 0 ? 0 : nz - k];
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < FFT_UNPACK_Q; q++) {
+                const int wi = threadIdx.x + q*blockDim.x;
+                if (wi < count) {
+                    const int p = p0 + wi/nzh, k = wi % nzh;
+                    plane[(size_t) (2*p)*rs + k] = mkc(half*(zk[q].x + zn[q].x), half*(zk[q].y - zn[q].y));
+                    if (2*p + 1 < ny) plane[(size_t) (2*p + 1)*rs + k] = mkc(half*(zk[q].y + zn[q].y), -half*(zk[q].x - zn[q].x));
+                }
+            }
+            __syncthreads();
+        }
+    }
+    batchedFft<Q, RMAX>(plane, nzh, 1, rs, ny, a.factorsY, twy);
+    C* out = (C*) a.gridC + (size_t) sx*ny*nzh;
+    for (int idx = threadIdx.x; idx < ny*nzh; idx += blockDim.x) {
+        const int y = idx/nzh, k = idx - y*nzh;
+        out[idx] = plane[(size_t) y*rs + k];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// yz inverse: half spectrum (already inverse-transformed along x) -> real potential grid (float).
+// Inverse transforms are forward transforms of the conjugate.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int Q, int RMAX>
+__global__ void __launch_bounds__(FFT_THREADS) k_fft_yz_inv(const PlaneFftArgs a) {
+    typedef typename Cx2<T>::type C;
+    extern __shared__ double2 fftSmem[];
+    C* sm = (C*) fftSmem;
+    const int ny = a.ny, nz = a.nz, nzh = a.nzh, rs = a.rowStride;
+    C* twz = sm;
+    C* twy = sm + nz;
+    C* plane = sm + nz + ny;
+    for (int k = threadIdx.x; k < nz; k += blockDim.x) twz[k] = ((const C*) a.twz)[k];
+    for (int k = threadIdx.x; k < ny; k += blockDim.x) twy[k] = ((const C*) a.twy)[k];
+    const int sx = a.ownLo*a.nx + blockIdx.x;
+    const C* in = (const C*) a.gridC + (size_t) sx*ny*nzh;
+    for (int idx = threadIdx.x; idx < ny*nzh; idx += blockDim.x) {
+        const int y = idx/nzh, k = idx - y*nzh;
+        C v = in[idx];
+        v.y = -v.y;                                              // conjugate: inverse y = conj(fwd(conj))
+        plane[(size_t) y*rs + k] = v;
+    }
+    __syncthreads();
+    batchedFft<Q, RMAX>(plane, nzh, 1, rs, ny, a.factorsY, twy);
+    // plane now holds conj(A) where A = y-inverse spectrum.  Pack rows (2p, 2p+1) into one complex line:
+    // W[k] = conj(A0[k] + i A1[k]),  W[n-k] = conj(conj(A0[k]) + i conj(A1[k]))   (0 < k, 2k < n)
+    // so that fwd(W) = conj(r0 + i r1) with r0, r1 the two real rows.
+    {
+        const int pairs = (ny + 1) >> 1;
+        const int pairsPerRound = max(1, (FFT_THREADS*FFT_UNPACK_Q)/nzh);
+        for (int p0 = 0; p0 < pairs; p0 += pairsPerRound) {
+            const int count = min(pairsPerRound, pairs - p0)*nzh;
+            C a0[FFT_UNPACK_Q], a1[FFT_UNPACK_Q];
+#pragma unroll
+            for (int q = 0; q < FFT_UNPACK_Q; q++) {
+                const int wi = threadIdx.x + q*blockDim.x;
+                if (wi < count) {
+                    const int p = p0 + wi/nzh, k = wi % nzh;
+                    C u = plane[(size_t) (2*p)*rs + k];
+                    u.y = -u.y;                                      // A0[k]
+                    C v = mkc((T) 0, (T) 0);
+                    if (2*p + 1 < ny) { v = plane[(size_t) (2*p + 1)*rs + k]; v.y = -v.y; }    // A1[k]
+                    a0[q] = u; a1[q] = v;
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < FFT_UNPACK_Q; q++) {
+                const int wi = threadIdx.x + q*blockDim.x;
+                if (wi < count) {
+                    const int p = p0 + wi/nzh, k = wi % nzh;
+                    C* line = plane + (size_t) p*2*rs;
+                    const C A = a0[q], B = a1[q];
+                    line[k] = mkc(A.x - B.y, -(A.y + B.x));                           // conj(A + iB)
+                    if (k > 0 && 2*k < nz) line[nz - k] = mkc(A.x + B.y, A.y - B.x);  // conj(conj(A) + i conj(B))
+                }
+            }
+            __syncthreads();
+        }
+        batchedFft<Q, RMAX>(plane, pairs, 2*rs, 1, nz, a.factorsZ, twz);
+        float* pot = a.pot + (size_t) sx*ny*nz;
+        for (int idx = threadIdx.x; idx < pairs*nz; idx += blockDim.x) {
+            const int p = idx/nz, z = idx - p*nz;
+            const C wv = plane[(size_t) p*2*rs + z];
+            pot[(size_t) (2*p)*nz + z] = (float) wv.x;
+            if (2*p + 1 < ny) pot[(size_t) (2*p + 1)*nz + z] = (float) -wv.y;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// x transform + sliced convolution + x inverse.  CTA = one y x `chunk` consecutive kz, ALL subsets.
+// Convolution and energies: pme_reciprocal_convolution, ReferencePME.cpp:400-496 -- eterm per k,
+// E[slice(I,I)] += 1/2 eterm |S_I|^2, E[slice(I,J)] += eterm Re(S_I conj S_J) over the FULL grid (the
+// half spectrum counts twice except on the kz = 0 and kz = nz/2 planes).  The reference then scales
+// every subset grid by eterm and lets the gather mix subsets with lambda (:681-687); here the mix
+// happens in k space.  Shared layout: lines[x][s*chunk + l] -- the transform runs down the columns, so a
+// pass touches consecutive banks and the global <-> shared copies are straight.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int Q, int RMAX, int NS>
+__global__ void __launch_bounds__(FFT_THREADS) k_fft_x_conv2(const PlaneFftArgs a) {
+    typedef typename Cx2<T>::type C;
+    extern __shared__ double2 fftSmem[];
+    C* sm = (C*) fftSmem;
+    __shared__ double shE[MAX_SLICES];
+    const int n = a.nx, nzh = a.nzh, chunk = a.chunk, nS = a.nS;
+    const int RS = nS*chunk + 1;                             // row stride: lines[x][s*chunk + l]
+    C* tw = sm;
+    C* lines = sm + n;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) tw[k] = ((const C*) a.twx)[k];
+    if (threadIdx.x < MAX_SLICES) shE[threadIdx.x] = 0.0;
+    const int chunks = (nzh + chunk - 1)/chunk;
+    const int y = blockIdx.x/chunks, k0 = (blockIdx.x - y*chunks)*chunk;
+    const int kn = min(chunk, nzh - k0);                     // kz values this CTA really has
+    C* gridC = (C*) a.gridC;
+    for (int idx = threadIdx.x; idx < nS*n*chunk; idx += blockDim.x) {
+        const int l = idx % chunk, x = (idx/chunk) % n, s = idx/(chunk*n);
+        lines[(size_t) x*RS + s*chunk + l] = l < kn ? gridC[(((size_t) s*n + x)*a.ny + y)*nzh + k0 + l] : mkc((T) 0, (T) 0);
+    }
+    __syncthreads();
+    batchedFft<Q, RMAX>(lines, nS*chunk, 1, RS, n, a.factorsX, tw);
+    double e[NS*(NS+1)/2];
+#pragma unroll
+    for (int s = 0; s < NS*(NS+1)/2; s++) e[s] = 0.0;
+    for (int idx = threadIdx.x; idx < n*kn; idx += blockDim.x) {
+        const int l = idx % kn, x = idx/kn, k = k0 + l;
+        const T et = ((const T*) a.eterm)[((size_t) x*a.ny + y)*nzh + k];
+        C S[NS];
+#pragma unroll
+        for (int s = 0; s < NS; s++) S[s] = s < nS ? lines[(size_t) x*RS + s*chunk + l] : mkc((T) 0, (T) 0);
+        if (a.wantEnergy) {
+            const T wgt = (k == 0 || 2*k == a.nz) ? (T) 1 : (T) 2;
+#pragma unroll
+            for (int sb = 0; sb < NS; sb++)
+#pragma unroll
+                for (int sa = 0; sa <= sb; sa++) {
+                    if (sa < a.ownLo || sa >= a.ownHi) continue;     // a slice belongs to the owner of its lower subset
+                    const T prod = S[sa].x*S[sb].x + S[sa].y*S[sb].y;
+                    e[sb*(sb+1)/2 + sa] += (double) ((sa == sb ? (T) 0.5 : (T) 1)*wgt*et*prod);
+                }
+        }
+#pragma unroll
+        for (int si = 0; si < NS; si++) {
+            if (si >= a.ownHi) break;
+            if (si < a.ownLo) continue;
+            T gx = 0, gy = 0;
+#pragma unroll
+            for (int sj = 0; sj < NS; sj++) {
+                const T lam = (T) a.lam.c[triSlice(si, sj)];
+                gx += lam*S[sj].x;
+                gy += lam*S[sj].y;
+            }
+            lines[(size_t) x*RS + si*chunk + l] = mkc(et*gx, -et*gy);      // conjugated for the inverse pass
+        }
+    }
+    __syncthreads();
+    const int nOwn = a.ownHi - a.ownLo;
+    batchedFft<Q, RMAX>(lines + (size_t) a.ownLo*chunk, nOwn*chunk, 1, RS, n, a.factorsX, tw);
+    for (int idx = threadIdx.x; idx < nOwn*n*kn; idx += blockDim.x) {
+        const int l = idx % kn, x = (idx/kn) % n, s = a.ownLo + idx/(kn*n);
+        C v = lines[(size_t) x*RS + s*chunk + l];
+        v.y = -v.y;
+        gridC[(((size_t) s*n + x)*a.ny + y)*nzh + k0 + l] = v;
+    }
+    if (a.wantEnergy) {
+        const int lane = threadIdx.x & 31;
+#pragma unroll
+        for (int s = 0; s < NS*(NS+1)/2; s++) {
+            const double v = warpSum(e[s]);
+            if (lane == 0 && v != 0.0) atomicAdd(&shE[s], v);
+        }
+        __syncthreads();
+        if (threadIdx.x < NS*(NS+1)/2 && shE[threadIdx.x] != 0.0)
+            atomicAdd(a.energy + 2*threadIdx.x, shE[threadIdx.x]);       // Coulomb term of the slice
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static int maxButterflies(int lines, int n, unsigned long long factors) {
+    // largest (lines * n/R) weighted by the Q multiplier batchedFft gives that radix: Q_R * blockDim must cover it
+    // returns the minimal Q (for radix 4/5/7 passes) that covers every pass
+    int q = 1;
+    for (; factors != 0; factors >>= 4) {
+        const int R = (int) (factors & 15);
+        const int count = lines*(n/R);
+        int need;
+        if (R == 2) need = (count + 2*FFT_THREADS - 1)/(2*FFT_THREADS);             // Q_2 = 2Q
+        else if (R == 3) { need = 1; while (((4*need + 2)/3)*FFT_THREADS < count) need++; }
+        else if (R <= 7) need = (count + FFT_THREADS - 1)/FFT_THREADS;
+        else need = count <= 2*FFT_THREADS ? 1 : 99;                                // rolled radix: two per thread
+        q = std::max(q, need);
+    }
+    return q;
+}
+
+template <typename T, int Q, int RMAX>
+static int launchPlaneT(Context& c, PlaneFftArgs a, int half, size_t smPlane, size_t smX) {
+    cudaStream_t st = c.stream;
+    static bool attr[64] = {false};
+    if (!attr[c.device & 63]) {
+        const int big = 220*1024;
+        cudaFuncSetAttribute(k_fft_zy_fwd<T, Q, RMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(k_fft_yz_inv<T, Q, RMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(k_fft_x_conv2<T, Q, RMAX, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(k_fft_x_conv2<T, Q, RMAX, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(k_fft_x_conv2<T, Q, RMAX, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(k_fft_x_conv2<T, Q, RMAX, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(k_fft_x_conv2<T, Q, RMAX, MAX_SUBSETS>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        attr[c.device & 63] = true;
+    }
+    const int nOwn = c.ownHi - c.ownLo;
+    const int planes = nOwn*a.nx;
+    if (half == 0) {
+        k_fft_zy_fwd<T, Q, RMAX><<<planes, FFT_THREADS, smPlane, st>>>(a);
+        c.launches++;
+        return NBS_OK;
+    }
+    const int xCtas = a.ny*((a.nzh + a.chunk - 1)/a.chunk);
+    switch (c.nS) {
+        case 1: k_fft_x_conv2<T, Q, RMAX, 1><<<xCtas, FFT_THREADS, smX, st>>>(a); break;
+        case 2: k_fft_x_conv2<T, Q, RMAX, 2><<<xCtas, FFT_THREADS, smX, st>>>(a); break;
+        case 3: k_fft_x_conv2<T, Q, RMAX, 3><<<xCtas, FFT_THREADS, smX, st>>>(a); break;
+        case 4: k_fft_x_conv2<T, Q, RMAX, 4><<<xCtas, FFT_THREADS, smX, st>>>(a); break;
+        default: k_fft_x_conv2<T, Q, RMAX, MAX_SUBSETS><<<xCtas, FFT_THREADS, smX, st>>>(a); break;
+    }
+    k_fft_yz_inv<T, Q, RMAX><<<planes, FFT_THREADS, smPlane, st>>>(a);
+    c.launches += 2;
+    return NBS_OK;
+}
+
+template <typename T, int Q>
+static int launchPlaneQ(Context& c, PlaneFftArgs a, int half, size_t smPlane, size_t smX, int rmax) {
+    if (rmax <= 4) return launchPlaneT<T, Q, 4>(c, a, half, smPlane, smX);
+    if (rmax <= 5) return launchPlaneT<T, Q, 5>(c, a, half, smPlane, smX);
+    return launchPlaneT<T, Q, 13>(c, a, half, smPlane, smX);
+}
+
+// Returns NBS_OK after launching, or NBS_RETRY (>0) when the grid does not fit this path (the caller
+// falls back to the line-at-a-time kernels).
+template <typename T>
+int launchPlaneFft(Context& c, const PlaneFftPlan& plan, PlaneFftArgs a, int half) {
+    typedef typename Cx2<T>::type C;
+    const int nx = c.grid[0], ny = c.grid[1], nz = c.grid[2], nzh = nz/2 + 1;
+    const int rs = std::max(nzh, (nz + 1)/2) + 1;
+    // x pass: choose the kz chunk so that the chunks are even and the lines of all subsets fit
+    int chunks = (nzh + 11)/12;
+    int chunk = (nzh + chunks - 1)/chunks;
+    const size_t cs = sizeof(C);
+    while (chunk > 1 && cs*((size_t) nx + (size_t) nx*(c.nS*chunk + 1)) > 200*1024) chunk--;
+    const size_t smX = cs*((size_t) nx + (size_t) nx*(c.nS*chunk + 1));
+    const size_t smPlane = cs*((size_t) nz + ny + (size_t) ((ny + 1)/2)*2*rs);
+    if (smPlane > 200*1024 || smX > 200*1024) return NBS_RETRY;
+    const int pairs = (ny + 1)/2;
+    int q = std::max(maxButterflies(pairs, nz, plan.factors[2]), maxButterflies(nzh, ny, plan.factors[1]));
+    q = std::max(q, maxButterflies(c.nS*chunk, nx, plan.factors[0]));
+    if (nzh > FFT_THREADS*FFT_UNPACK_Q) return NBS_RETRY;
+    a.rowStride = rs;
+    a.chunk = chunk;
+    a.factorsX = plan.factors[0]; a.factorsY = plan.factors[1]; a.factorsZ = plan.factors[2];
+    const C* tw = (const C*) (sizeof(T) == 8 ? (const void*) c.dTwiddleD.d : (const void*) c.dTwiddle.d);
+    a.twx = tw; a.twy = tw + nx; a.twz = tw + nx + ny;
+    // the plane kernels see only the own slabs
+    const int nOwn = c.ownHi - c.ownLo;
+    (void) nOwn;
+    int rmax = 2;
+    for (int d = 0; d < 3; d++)
+        for (unsigned long long f = plan.factors[d]; f != 0; f >>= 4) rmax = std::max(rmax, (int) (f & 15));
+    if (q <= 1) return launchPlaneQ<T, 1>(c, a, half, smPlane, smX, rmax);
+    if (q <= 2) return launchPlaneQ<T, 2>(c, a, half, smPlane, smX, rmax);
+    return NBS_RETRY;
+}
+
+template int launchPlaneFft<NBS_FFT_REAL>(Context&, const PlaneFftPlan&, PlaneFftArgs, int);
+
+} // namespace nbs

@@ -17,6 +17,7 @@
 // Bound: HBM/L2 bandwidth and launch latency (grids of every BASELINE config fit in the 126 MB L2).
 #include "nbs_internal.h"
 #include "nbs_device.cuh"
+#include "k_fft.cuh"
 
 namespace nbs {
 
@@ -609,6 +610,29 @@ static int launchPmeT(Context& c, bool wantEnergy, int half) {
     const size_t smZ = cs*(size_t) nz*9;
     const size_t smY = cs*((size_t) ny + 16*((size_t) ny + 1));
     const size_t smX = cs*((size_t) nx + (size_t) c.nS*8*((size_t) nx + 1));
+    // plane-fused transforms (k_fft.cu) whenever a plane fits in shared memory ...
+    {
+        PlaneFftPlan plan;
+        plan.factors[0] = px.packed; plan.factors[1] = py.packed; plan.factors[2] = pz.packed;
+        PlaneFftArgs pa;
+        pa.nS = c.nS; pa.nx = nx; pa.ny = ny; pa.nz = nz; pa.nzh = nzh;
+        pa.ownLo = c.ownLo; pa.ownHi = c.ownHi;
+        pa.rowStride = 0; pa.chunk = 0;
+        pa.grid = c.dGrid.d; pa.gridC = c.dGridC.d; pa.eterm = f.eterm; pa.pot = c.dPot.d;
+        pa.energy = c.dEnergy.d; pa.wantEnergy = f.wantEnergy; pa.lam = f.lam;
+        const int planeStatus = (c.flags & NBS_FLAG_LINE_FFT) ? NBS_RETRY : launchPlaneFft<T>(c, plan, pa, half);
+        if (planeStatus < 0) return planeStatus;
+        if (planeStatus == NBS_OK) {
+            timerMark(c, half == 0 ? "fft_fwd" : "fft_conv_inv");
+            if (half == 1) {
+                k_gather<<<atomCtas, 256, 0, st>>>(p);
+                c.launches++;
+                timerMark(c, "gather");
+            }
+            return NBS_OK;
+        }
+    }
+    // ... otherwise one line per warp, five kernels
     if (smX > 200*1024 || smY > 200*1024 || smZ > 200*1024) {
         setError("PME grid too large for the shared-memory FFT");
         return NBS_ERR_UNSUPPORTED;

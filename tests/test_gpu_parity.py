@@ -74,6 +74,19 @@ def test_reference_fixture(nbs, platform, systems, name):
     three_way(kernel, kernel.desc, s.positions, s.box, g["lambdas"], fixture)
 
 
+def test_line_fft_path(nbs, systems):
+    """Grids whose planes do not fit in shared memory use the line-at-a-time FFT kernels; force that path
+    (NBS_FLAG_LINE_FFT) on a small system and hold it to the same fixture."""
+    g = np.load(os.path.join(GOLDEN, "C2_reference.npz"))
+    s = systems.make_system("C2")
+    kernel = nbs.B200CalcSlicedNonbondedForceKernel(nbs.Platform(flags=nbs.abi.NBS_FLAG_LINE_FFT))
+    kernel.initialize(s.system, s.force)
+
+    def fixture(tag, direct, recip):
+        return g[f"{tag}_energies"], g[f"{tag}_forces"], int(g["pair_count"][0]), int(g["pair_hash"][0])
+    three_way(kernel, kernel.desc, s.positions, s.box, g["lambdas"], fixture)
+
+
 @pytest.mark.parametrize("name", ["C3", "C4"])
 def test_baseline_configs_vs_oracle(nbs, platform, systems, oracle, name):
     s = systems.make_system(name)

@@ -5,7 +5,8 @@
 
 namespace nbs {
 
-constexpr int FFT_THREADS = 512;
+constexpr int FFT_THREADS = 512;     // plane kernels (zy forward, yz inverse)
+constexpr int FFT_X_THREADS = 256;   // x + convolution kernel: more registers per thread, two CTAs per SM
 constexpr int FFT_UNPACK_Q = 4;      // (row pair, kz) items a thread stages per round of the real<->complex (un)packing
 
 struct PlaneFftPlan {

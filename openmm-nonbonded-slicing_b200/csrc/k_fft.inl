@@ -35,135 +35,122 @@ template <typename C> __device__ __forceinline__ C csubc(C a, C b) { return mkc(
 // One Stockham pass of radix R, batched over `lines` lines of length n, executed by the whole CTA.
 // Element e of line L lives at base[L*lineStride + e*elemStride].  Work item = one butterfly; consecutive
 // threads take consecutive butterflies of a line when the line is contiguous (elemStride == 1) and
-// consecutive lines otherwise, which keeps shared-memory accesses on distinct banks.  Q = butterflies a
-// thread may own: the CTA reads (and twiddles) everything into registers, synchronises, and only then
-// computes the size-R DFTs and writes them back, one output at a time -- the pass is in place and needs
-// no second register copy.
-template <int R, int Q, typename C>
+// consecutive lines otherwise, which keeps shared-memory accesses on distinct banks.  The pass is in
+// place: a ROUND covers as many whole lines as the CTA has threads for, reads (and twiddles) their
+// butterflies into registers, synchronises, and only then computes the size-R DFTs and writes them
+// back one output at a time.  Lines are independent, so rounds need no other ordering.
+template <int R, typename C>
 __device__ __forceinline__ void batchedPass(C* base, int lines, int lineStride, int elemStride, int n, int Ns, const C* tw) {
     const int nb = n/R;
-    const int count = lines*nb;
     const int tstep = n/(Ns*R), rstep = n/R;
-    C v[Q][R];
-    int dst[Q];
-#pragma unroll
-    for (int q = 0; q < Q; q++) {
-        const int wi = threadIdx.x + q*blockDim.x;
-        dst[q] = -1;
-        if (wi < count) {
+    const int os = Ns*elemStride;
+    const int linesPerRound = max(1, (int) blockDim.x/nb);       // host guarantees nb <= blockDim.x
+    for (int l0 = 0; l0 < lines; l0 += linesPerRound) {
+        const int nl = min(linesPerRound, lines - l0);
+        const int wi = threadIdx.x;
+        C v[R];
+        int dst = -1;
+        if (wi < nl*nb) {
             int L, j;
             if (elemStride == 1) { L = wi/nb; j = wi - L*nb; }
-            else { j = wi/lines; L = wi - j*lines; }
+            else { j = wi/nl; L = wi - j*nl; }
+            L += l0;
             const C* line = base + (size_t) L*lineStride;
 #pragma unroll
-            for (int t = 0; t < R; t++) v[q][t] = line[(j + t*nb)*elemStride];
+            for (int t = 0; t < R; t++) v[t] = line[(j + t*nb)*elemStride];
             const int k = j % Ns;
             if (Ns > 1) {
 #pragma unroll
-                for (int t = 1; t < R; t++) v[q][t] = cmulc(v[q][t], tw[t*k*tstep]);
+                for (int t = 1; t < R; t++) v[t] = cmulc(v[t], tw[t*k*tstep]);
             }
-            dst[q] = L*lineStride + ((j/Ns)*Ns*R + k)*elemStride;
+            dst = L*lineStride + ((j/Ns)*Ns*R + k)*elemStride;
         }
-    }
-    __syncthreads();
-    const int os = Ns*elemStride;
-    if (R == 2) {
-#pragma unroll
-        for (int q = 0; q < Q; q++)
-            if (dst[q] >= 0) {
-                base[dst[q]] = caddc(v[q][0], v[q][1]);
-                base[dst[q] + os] = csubc(v[q][0], v[q][1]);
+        __syncthreads();
+        if (dst >= 0) {
+            if (R == 2) {
+                base[dst] = caddc(v[0], v[1]);
+                base[dst + os] = csubc(v[0], v[1]);
             }
-    }
-    else if (R == 4) {
-#pragma unroll
-        for (int q = 0; q < Q; q++)
-            if (dst[q] >= 0) {
-                const C a0 = caddc(v[q][0], v[q][2]), a1 = csubc(v[q][0], v[q][2]);
-                const C a2 = caddc(v[q][1], v[q][3]), a3 = csubc(v[q][1], v[q][3]);
-                base[dst[q]] = caddc(a0, a2);
-                base[dst[q] + os] = mkc(a1.x + a3.y, a1.y - a3.x);        // a1 - i a3
-                base[dst[q] + 2*os] = csubc(a0, a2);
-                base[dst[q] + 3*os] = mkc(a1.x - a3.y, a1.y + a3.x);      // a1 + i a3
+            else if (R == 4) {
+                const C a0 = caddc(v[0], v[2]), a1 = csubc(v[0], v[2]);
+                const C a2 = caddc(v[1], v[3]), a3 = csubc(v[1], v[3]);
+                base[dst] = caddc(a0, a2);
+                base[dst + os] = mkc(a1.x + a3.y, a1.y - a3.x);        // a1 - i a3
+                base[dst + 2*os] = csubc(a0, a2);
+                base[dst + 3*os] = mkc(a1.x - a3.y, a1.y + a3.x);      // a1 + i a3
             }
-    }
-    else {
-        C root[R];                                   // exp(-2 pi i m / R)
-#pragma unroll
-        for (int m = 0; m < R; m++) root[m] = tw[m*rstep];
-#pragma unroll
-        for (int q = 0; q < Q; q++)
-            if (dst[q] >= 0) {
+            else {
 #pragma unroll
                 for (int o = 0; o < R; o++) {
-                    C acc = v[q][0];
+                    C acc = v[0];
 #pragma unroll
                     for (int t = 1; t < R; t++) {
-                        const C w = root[(o*t) % R];
-                        acc.x += v[q][t].x*w.x - v[q][t].y*w.y;
-                        acc.y += v[q][t].x*w.y + v[q][t].y*w.x;
+                        const C w = tw[((o*t) % R)*rstep];               // exp(-2 pi i (o t mod R) / R)
+                        acc.x += v[t].x*w.x - v[t].y*w.y;
+                        acc.y += v[t].x*w.y + v[t].y*w.x;
                     }
-                    base[dst[q] + o*os] = acc;
+                    base[dst + o*os] = acc;
                 }
             }
+        }
+        __syncthreads();
     }
-    __syncthreads();
 }
 
-// Radix 11 / 13 (rare grid sizes): rolled loops, one butterfly per loop trip, via a scratch copy.
+// Radix 11 / 13 (rare grid sizes): the same pass with rolled loops and the staged inputs in local memory.
 template <typename C>
 __device__ __noinline__ void batchedPassLarge(C* base, int lines, int lineStride, int elemStride, int n, int R, int Ns, const C* tw) {
-    const int nb = n/R, count = lines*nb, tstep = n/(Ns*R), rstep = n/R;
-    // at most FFT_MAX_Q_LARGE butterflies per thread are staged in registers
-    C v[2][13];
-    int dst[2];
-    for (int q = 0; q < 2; q++) {
-        const int wi = threadIdx.x + q*blockDim.x;
-        dst[q] = -1;
-        if (wi < count) {
+    const int nb = n/R, tstep = n/(Ns*R), rstep = n/R;
+    const int os = Ns*elemStride;
+    const int linesPerRound = max(1, (int) blockDim.x/nb);
+    for (int l0 = 0; l0 < lines; l0 += linesPerRound) {
+        const int nl = min(linesPerRound, lines - l0);
+        const int wi = threadIdx.x;
+        C v[13];
+        int dst = -1;
+        if (wi < nl*nb) {
             int L, j;
             if (elemStride == 1) { L = wi/nb; j = wi - L*nb; }
-            else { j = wi/lines; L = wi - j*lines; }
+            else { j = wi/nl; L = wi - j*nl; }
+            L += l0;
             const C* line = base + (size_t) L*lineStride;
             const int k = j % Ns;
             for (int t = 0; t < R; t++) {
                 C x = line[(j + t*nb)*elemStride];
-                v[q][t] = t == 0 ? x : cmulc(x, tw[t*k*tstep]);
+                v[t] = t == 0 ? x : cmulc(x, tw[t*k*tstep]);
             }
-            dst[q] = L*lineStride + ((j/Ns)*Ns*R + k)*elemStride;
+            dst = L*lineStride + ((j/Ns)*Ns*R + k)*elemStride;
         }
-    }
-    __syncthreads();
-    for (int q = 0; q < 2; q++) {
-        if (dst[q] < 0) continue;
-        for (int o = 0; o < R; o++) {
-            C acc = v[q][0];
-            for (int t = 1; t < R; t++) {
-                const C z = tw[((o*t) % R)*rstep];
-                acc.x += v[q][t].x*z.x - v[q][t].y*z.y;
-                acc.y += v[q][t].x*z.y + v[q][t].y*z.x;
+        __syncthreads();
+        if (dst >= 0) {
+            for (int o = 0; o < R; o++) {
+                C acc = v[0];
+                for (int t = 1; t < R; t++) {
+                    const C z = tw[((o*t) % R)*rstep];
+                    acc.x += v[t].x*z.x - v[t].y*z.y;
+                    acc.y += v[t].x*z.y + v[t].y*z.x;
+                }
+                base[dst + o*os] = acc;
             }
-            base[dst[q] + o*Ns*elemStride] = acc;
         }
+        __syncthreads();
     }
-    __syncthreads();
 }
 
-// Forward (e^{-i...}) unnormalised FFT of `lines` lines, by the whole CTA.  Q is sized by the host so
-// that Q*blockDim >= lines*n/R for every unrolled radix of the plan.
-template <int Q, int RMAX, typename C>
+// Forward (e^{-i...}) unnormalised FFT of `lines` lines, by the whole CTA.
+// RMAX = largest radix this instantiation carries code for (4, 5 or 13): small-radix plans get kernels
+// with fewer registers and more CTAs per SM.
+template <int RMAX, typename C>
 __device__ __forceinline__ void batchedFft(C* base, int lines, int lineStride, int elemStride, int n,
                                            unsigned long long factors, const C* tw) {
-    // RMAX = largest radix this instantiation carries code for (4, 5, 7 or 13): small-radix plans get
-    // kernels with fewer registers and more CTAs per SM
     int Ns = 1;
     for (; factors != 0; factors >>= 4) {
         const int R = (int) (factors & 15);
-        if (R == 4) batchedPass<4, Q>(base, lines, lineStride, elemStride, n, Ns, tw);
-        else if (R == 2) batchedPass<2, 2*Q>(base, lines, lineStride, elemStride, n, Ns, tw);
-        else if (R == 3) batchedPass<3, (4*Q + 2)/3>(base, lines, lineStride, elemStride, n, Ns, tw);
-        else if (RMAX >= 5 && R == 5) batchedPass<5, Q>(base, lines, lineStride, elemStride, n, Ns, tw);
-        else if (RMAX >= 7 && R == 7) batchedPass<7, Q>(base, lines, lineStride, elemStride, n, Ns, tw);
+        if (R == 4) batchedPass<4>(base, lines, lineStride, elemStride, n, Ns, tw);
+        else if (R == 2) batchedPass<2>(base, lines, lineStride, elemStride, n, Ns, tw);
+        else if (R == 3) batchedPass<3>(base, lines, lineStride, elemStride, n, Ns, tw);
+        else if (RMAX >= 5 && R == 5) batchedPass<5>(base, lines, lineStride, elemStride, n, Ns, tw);
+        else if (RMAX >= 13 && R == 7) batchedPass<7>(base, lines, lineStride, elemStride, n, Ns, tw);
         else if (RMAX >= 13) batchedPassLarge(base, lines, lineStride, elemStride, n, R, Ns, tw);
         Ns *= R;
     }
@@ -174,7 +161,7 @@ __device__ __forceinline__ void batchedFft(C* base, int lines, int lineStride, i
 // Shared plane: ny rows of `rs` complex numbers (rs >= nz/2 + 1, and 2*rs >= nz so that the complex line
 // of a row pair fits in the pair's two rows).
 // ---------------------------------------------------------------------------------------------
-template <typename T, int Q, int RMAX>
+template <typename T, int RMAX>
 __global__ void __launch_bounds__(FFT_THREADS) k_fft_zy_fwd(const PlaneFftArgs a) {
     typedef typename Cx2<T>::type C;
     extern __shared__ double2 fftSmem[];
@@ -195,7 +182,7 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_zy_fwd(const PlaneFftArgs a
         plane[(size_t) p*2*rs + z] = mkc(re, im);
     }
     __syncthreads();
-    batchedFft<Q, RMAX>(plane, pairs, 2*rs, 1, nz, a.factorsZ, twz);
+    batchedFft<RMAX>(plane, pairs, 2*rs, 1, nz, a.factorsZ, twz);
     // unpack Z -> the two rows' half spectra: S0[k] = (Z[k] + conj Z[n-k])/2, S1[k] = (Z[k] - conj Z[n-k])/(2i).
     // In place, so a round stages whole row pairs in registers before anything is written.
     {
@@ -227,7 +214,7 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_zy_fwd(const PlaneFftArgs a
             __syncthreads();
         }
     }
-    batchedFft<Q, RMAX>(plane, nzh, 1, rs, ny, a.factorsY, twy);
+    batchedFft<RMAX>(plane, nzh, 1, rs, ny, a.factorsY, twy);
     C* out = (C*) a.gridC + (size_t) sx*ny*nzh;
     for (int idx = threadIdx.x; idx < ny*nzh; idx += blockDim.x) {
         const int y = idx/nzh, k = idx - y*nzh;
@@ -239,7 +226,7 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_zy_fwd(const PlaneFftArgs a
 // yz inverse: half spectrum (already inverse-transformed along x) -> real potential grid (float).
 // Inverse transforms are forward transforms of the conjugate.
 // ---------------------------------------------------------------------------------------------
-template <typename T, int Q, int RMAX>
+template <typename T, int RMAX>
 __global__ void __launch_bounds__(FFT_THREADS) k_fft_yz_inv(const PlaneFftArgs a) {
     typedef typename Cx2<T>::type C;
     extern __shared__ double2 fftSmem[];
@@ -259,7 +246,7 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_yz_inv(const PlaneFftArgs a
         plane[(size_t) y*rs + k] = v;
     }
     __syncthreads();
-    batchedFft<Q, RMAX>(plane, nzh, 1, rs, ny, a.factorsY, twy);
+    batchedFft<RMAX>(plane, nzh, 1, rs, ny, a.factorsY, twy);
     // plane now holds conj(A) where A = y-inverse spectrum.  Pack rows (2p, 2p+1) into one complex line:
     // W[k] = conj(A0[k] + i A1[k]),  W[n-k] = conj(conj(A0[k]) + i conj(A1[k]))   (0 < k, 2k < n)
     // so that fwd(W) = conj(r0 + i r1) with r0, r1 the two real rows.
@@ -295,7 +282,7 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_yz_inv(const PlaneFftArgs a
             }
             __syncthreads();
         }
-        batchedFft<Q, RMAX>(plane, pairs, 2*rs, 1, nz, a.factorsZ, twz);
+        batchedFft<RMAX>(plane, pairs, 2*rs, 1, nz, a.factorsZ, twz);
         float* pot = a.pot + (size_t) sx*ny*nz;
         for (int idx = threadIdx.x; idx < pairs*nz; idx += blockDim.x) {
             const int p = idx/nz, z = idx - p*nz;
@@ -315,7 +302,7 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_yz_inv(const PlaneFftArgs a
 // happens in k space.  Shared layout: lines[x][s*chunk + l] -- the transform runs down the columns, so a
 // pass touches consecutive banks and the global <-> shared copies are straight.
 // ---------------------------------------------------------------------------------------------
-template <typename T, int Q, int RMAX, int NS>
+template <typename T, int RMAX, int NS>
 __global__ void __launch_bounds__(FFT_THREADS) k_fft_x_conv2(const PlaneFftArgs a) {
     typedef typename Cx2<T>::type C;
     extern __shared__ double2 fftSmem[];
@@ -336,7 +323,7 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_x_conv2(const PlaneFftArgs 
         lines[(size_t) x*RS + s*chunk + l] = l < kn ? gridC[(((size_t) s*n + x)*a.ny + y)*nzh + k0 + l] : mkc((T) 0, (T) 0);
     }
     __syncthreads();
-    batchedFft<Q, RMAX>(lines, nS*chunk, 1, RS, n, a.factorsX, tw);
+    batchedFft<RMAX>(lines, nS*chunk, 1, RS, n, a.factorsX, tw);
     double e[NS*(NS+1)/2];
 #pragma unroll
     for (int s = 0; s < NS*(NS+1)/2; s++) e[s] = 0.0;
@@ -373,7 +360,7 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_x_conv2(const PlaneFftArgs 
     }
     __syncthreads();
     const int nOwn = a.ownHi - a.ownLo;
-    batchedFft<Q, RMAX>(lines + (size_t) a.ownLo*chunk, nOwn*chunk, 1, RS, n, a.factorsX, tw);
+    batchedFft<RMAX>(lines + (size_t) a.ownLo*chunk, nOwn*chunk, 1, RS, n, a.factorsX, tw);
     for (int idx = threadIdx.x; idx < nOwn*n*kn; idx += blockDim.x) {
         const int l = idx % kn, x = (idx/kn) % n, s = a.ownLo + idx/(kn*n);
         C v = lines[(size_t) x*RS + s*chunk + l];
@@ -396,63 +383,39 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_x_conv2(const PlaneFftArgs 
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-static int maxButterflies(int lines, int n, unsigned long long factors) {
-    // largest (lines * n/R) weighted by the Q multiplier batchedFft gives that radix: Q_R * blockDim must cover it
-    // returns the minimal Q (for radix 4/5/7 passes) that covers every pass
-    int q = 1;
-    for (; factors != 0; factors >>= 4) {
-        const int R = (int) (factors & 15);
-        const int count = lines*(n/R);
-        int need;
-        if (R == 2) need = (count + 2*FFT_THREADS - 1)/(2*FFT_THREADS);             // Q_2 = 2Q
-        else if (R == 3) { need = 1; while (((4*need + 2)/3)*FFT_THREADS < count) need++; }
-        else if (R <= 7) need = (count + FFT_THREADS - 1)/FFT_THREADS;
-        else need = count <= 2*FFT_THREADS ? 1 : 99;                                // rolled radix: two per thread
-        q = std::max(q, need);
-    }
-    return q;
-}
-
-template <typename T, int Q, int RMAX>
+template <typename T, int RMAX>
 static int launchPlaneT(Context& c, PlaneFftArgs a, int half, size_t smPlane, size_t smX) {
     cudaStream_t st = c.stream;
     static bool attr[64] = {false};
     if (!attr[c.device & 63]) {
         const int big = 220*1024;
-        cudaFuncSetAttribute(k_fft_zy_fwd<T, Q, RMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-        cudaFuncSetAttribute(k_fft_yz_inv<T, Q, RMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-        cudaFuncSetAttribute(k_fft_x_conv2<T, Q, RMAX, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-        cudaFuncSetAttribute(k_fft_x_conv2<T, Q, RMAX, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-        cudaFuncSetAttribute(k_fft_x_conv2<T, Q, RMAX, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-        cudaFuncSetAttribute(k_fft_x_conv2<T, Q, RMAX, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-        cudaFuncSetAttribute(k_fft_x_conv2<T, Q, RMAX, MAX_SUBSETS>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(k_fft_zy_fwd<T, RMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(k_fft_yz_inv<T, RMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(k_fft_x_conv2<T, RMAX, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(k_fft_x_conv2<T, RMAX, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(k_fft_x_conv2<T, RMAX, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(k_fft_x_conv2<T, RMAX, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(k_fft_x_conv2<T, RMAX, MAX_SUBSETS>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
         attr[c.device & 63] = true;
     }
     const int nOwn = c.ownHi - c.ownLo;
     const int planes = nOwn*a.nx;
     if (half == 0) {
-        k_fft_zy_fwd<T, Q, RMAX><<<planes, FFT_THREADS, smPlane, st>>>(a);
+        k_fft_zy_fwd<T, RMAX><<<planes, FFT_THREADS, smPlane, st>>>(a);
         c.launches++;
         return NBS_OK;
     }
     const int xCtas = a.ny*((a.nzh + a.chunk - 1)/a.chunk);
     switch (c.nS) {
-        case 1: k_fft_x_conv2<T, Q, RMAX, 1><<<xCtas, FFT_THREADS, smX, st>>>(a); break;
-        case 2: k_fft_x_conv2<T, Q, RMAX, 2><<<xCtas, FFT_THREADS, smX, st>>>(a); break;
-        case 3: k_fft_x_conv2<T, Q, RMAX, 3><<<xCtas, FFT_THREADS, smX, st>>>(a); break;
-        case 4: k_fft_x_conv2<T, Q, RMAX, 4><<<xCtas, FFT_THREADS, smX, st>>>(a); break;
-        default: k_fft_x_conv2<T, Q, RMAX, MAX_SUBSETS><<<xCtas, FFT_THREADS, smX, st>>>(a); break;
+        case 1: k_fft_x_conv2<T, RMAX, 1><<<xCtas, FFT_X_THREADS, smX, st>>>(a); break;
+        case 2: k_fft_x_conv2<T, RMAX, 2><<<xCtas, FFT_X_THREADS, smX, st>>>(a); break;
+        case 3: k_fft_x_conv2<T, RMAX, 3><<<xCtas, FFT_X_THREADS, smX, st>>>(a); break;
+        case 4: k_fft_x_conv2<T, RMAX, 4><<<xCtas, FFT_X_THREADS, smX, st>>>(a); break;
+        default: k_fft_x_conv2<T, RMAX, MAX_SUBSETS><<<xCtas, FFT_X_THREADS, smX, st>>>(a); break;
     }
-    k_fft_yz_inv<T, Q, RMAX><<<planes, FFT_THREADS, smPlane, st>>>(a);
+    k_fft_yz_inv<T, RMAX><<<planes, FFT_THREADS, smPlane, st>>>(a);
     c.launches += 2;
     return NBS_OK;
-}
-
-template <typename T, int Q>
-static int launchPlaneQ(Context& c, PlaneFftArgs a, int half, size_t smPlane, size_t smX, int rmax) {
-    if (rmax <= 4) return launchPlaneT<T, Q, 4>(c, a, half, smPlane, smX);
-    if (rmax <= 5) return launchPlaneT<T, Q, 5>(c, a, half, smPlane, smX);
-    return launchPlaneT<T, Q, 13>(c, a, half, smPlane, smX);
 }
 
 // Returns NBS_OK after launching, or NBS_RETRY (>0) when the grid does not fit this path (the caller
@@ -463,17 +426,14 @@ int launchPlaneFft(Context& c, const PlaneFftPlan& plan, PlaneFftArgs a, int hal
     const int nx = c.grid[0], ny = c.grid[1], nz = c.grid[2], nzh = nz/2 + 1;
     const int rs = std::max(nzh, (nz + 1)/2) + 1;
     // x pass: choose the kz chunk so that the chunks are even and the lines of all subsets fit
-    int chunks = (nzh + 11)/12;
+    int chunks = (nzh + 7)/8;
     int chunk = (nzh + chunks - 1)/chunks;
     const size_t cs = sizeof(C);
     while (chunk > 1 && cs*((size_t) nx + (size_t) nx*(c.nS*chunk + 1)) > 200*1024) chunk--;
     const size_t smX = cs*((size_t) nx + (size_t) nx*(c.nS*chunk + 1));
     const size_t smPlane = cs*((size_t) nz + ny + (size_t) ((ny + 1)/2)*2*rs);
     if (smPlane > 200*1024 || smX > 200*1024) return NBS_RETRY;
-    const int pairs = (ny + 1)/2;
-    int q = std::max(maxButterflies(pairs, nz, plan.factors[2]), maxButterflies(nzh, ny, plan.factors[1]));
-    q = std::max(q, maxButterflies(c.nS*chunk, nx, plan.factors[0]));
-    if (nzh > FFT_THREADS*FFT_UNPACK_Q) return NBS_RETRY;
+    if (nzh > FFT_THREADS*FFT_UNPACK_Q || std::max(nx, std::max(ny, nz))/2 > FFT_THREADS) return NBS_RETRY;
     a.rowStride = rs;
     a.chunk = chunk;
     a.factorsX = plan.factors[0]; a.factorsY = plan.factors[1]; a.factorsZ = plan.factors[2];
@@ -485,9 +445,9 @@ int launchPlaneFft(Context& c, const PlaneFftPlan& plan, PlaneFftArgs a, int hal
     int rmax = 2;
     for (int d = 0; d < 3; d++)
         for (unsigned long long f = plan.factors[d]; f != 0; f >>= 4) rmax = std::max(rmax, (int) (f & 15));
-    if (q <= 1) return launchPlaneQ<T, 1>(c, a, half, smPlane, smX, rmax);
-    if (q <= 2) return launchPlaneQ<T, 2>(c, a, half, smPlane, smX, rmax);
-    return NBS_RETRY;
+    if (rmax <= 4) return launchPlaneT<T, 4>(c, a, half, smPlane, smX);
+    if (rmax <= 5) return launchPlaneT<T, 5>(c, a, half, smPlane, smX);
+    return launchPlaneT<T, 13>(c, a, half, smPlane, smX);
 }
 
 template int launchPlaneFft<NBS_FFT_REAL>(Context&, const PlaneFftPlan&, PlaneFftArgs, int);

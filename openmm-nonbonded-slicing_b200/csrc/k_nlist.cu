@@ -20,8 +20,8 @@
 
 namespace nbs {
 
-constexpr int JBUF = 1536;     // per-warp staging capacity (entries)
-constexpr int XBUF = 192;
+constexpr int JBUF = 768;      // per-warp staging capacity (entries)
+constexpr int XBUF = 96;
 
 struct BuildArgs {
     int N, maxBlocks, capJ, capX;
@@ -99,6 +99,7 @@ __global__ void __launch_bounds__(BUILD_WARPS*32) k_build_lists(BuildArgs a) {
                 unsigned imask = 0;
                 if (j < e) {
                     const uint4 q = a.posq[j];
+                    const int2 range = a.exclRange[j];          // issued with the position: one latency, not two
                     const float rx = (float) ((long long) q.x + shx - (long long) lo.x)*a.sx;
                     const float ry = (float) ((long long) q.y + shy - (long long) lo.y)*a.sy;
                     const float rz = (float) ((long long) q.z + shz - (long long) lo.z)*a.sz;
@@ -109,7 +110,6 @@ __global__ void __launch_bounds__(BUILD_WARPS*32) k_build_lists(BuildArgs a) {
                     if (pass) {
                         const int rel = j - first;
                         if (rel >= 0 && rel < count) imask = 0xffffffffu << rel;      // own block: keep i < j only
-                        const int2 range = a.exclRange[j];
                         if (range.y >= first && range.x < first + count) {
                             const int p = __float_as_int(a.par[j].w);
                             for (int k = a.exclStart[p]; k < a.exclStart[p+1]; k++) {

@@ -10,18 +10,20 @@
 //   * WORK ITEMS, PERSISTENT WARPS.  The list builder emits items (i-block, first tile, <= chunk tiles);
 //     every warp of a persistent grid pulls items from a global cursor, so there is no CTA-wide barrier,
 //     no tail of idle warps, and small systems (818 i-blocks at DHFR size) still fill 148 SMs.
-//   * TWO PHASES PER TILE.  Phase A ("cull"): 32 i atoms (one per lane) x 32 j atoms staged in shared
-//     memory as float4; lane l meets j slot (l + k) & 31 at step k; only the squared distance is computed
-//     (~18 instructions per pair) and the pairs inside the cutoff are compacted with a warp ballot into a
-//     per-warp queue.  Phase B ("evaluate"): the queue is drained 32 REAL pairs at a time -- every lane of
-//     every pass does useful arithmetic.  Forces are fp32; with slice energies requested the same pass
-//     evaluates the pair's energies in DOUBLE precision from the exact fixed-point coordinates
-//     (slice energies are sums of 10^4..10^8 terms of both signs; DESIGN.md "Precision").
-//   * Phase B scatters into per-warp shared-memory accumulators with a plain read-modify-write; lanes of
-//     one pass that hit the same atom are found with match.any and take turns in lane order, so the
-//     summation order is fixed -- forces are bit-reproducible.  Per tile (j) and per item (i) the float
-//     sums are converted to 64-bit fixed point and added to the global accumulators (integer adds
-//     commute).
+//   * a tile = 32 i atoms (one per lane, registers) x 32 j atoms staged in shared memory as float4
+//     (position relative to the block corner, charge) + float4 (sigma/2, 2 sqrt(eps), subset); lane l
+//     meets j slot (l + k) & 31 at step k, so the i AND the j forces accumulate in registers without
+//     conflicts -- the j accumulators rotate one lane per step (3 shuffles).  The step is ~60 fp32
+//     instructions: approx rsqrt / rcp / ex2 (MUFU) with no denormal handling, erfc(x) = exp(-x^2) P(t),
+//     lambda pair from a shared-memory row selected by the lane's own subset.
+//   * slice energies (EMODE 2, the default when energies are requested): the in-cutoff pairs of a tile
+//     are compacted with warp ballots into a per-warp queue and their energies are evaluated in DOUBLE
+//     precision from the exact fixed-point coordinates, 32 REAL pairs per pass (no lane is wasted on pairs
+//     beyond the cutoff).  Slice energies are sums of 10^4..10^8 terms of both signs; single precision
+//     cannot deliver 1e-5 of a small net value (DESIGN.md "Precision").  EMODE 1 keeps single-precision
+//     pair energies (the plugin's "single" mode), EMODE 0 computes forces only.
+//   * summation order is fixed (per lane in step order; tiles and items are combined as 64-bit fixed
+//     point, whose adds commute), so forces are bit-reproducible.
 //   * positions are 32-bit fixed-point fractional coordinates; each tile converts them once into floats
 //     relative to the i-block's corner (~1e-7 nm resolution at any box size); a pair whose fp32 r^2 lands
 //     within 2e-5 nm^2 of the cutoff is re-tested exactly in double from the integers -- this is what
@@ -64,14 +66,12 @@ struct __align__(16) WarpScratch {
     float4 iPar[32];      // sigma/2, 2 sqrt(eps), subset, particle index
     float4 jPos[32];      // current tile
     float4 jPar[32];
-    float4 fi[32];        // force accumulators (float, one item / one tile)
-    float4 fj[32];
     uint4 iFix[32];       // exact coordinates, w = subset
     uint4 jFix[32];
     double iQ[32];        // charges in double (energy path)
     double jQ[32];
     unsigned jMask[32];   // exclusion-list tiles: bit l set = pair (i lane l, this j) is masked
-    unsigned short queue[1024 + 32];
+    unsigned short queue[1024 + 32];   // MODE 1/2: a whole tile's pairs; MODE 0: the energy queue (<= 64 used)
 };
 
 __device__ __forceinline__ float rsqrtFast(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -96,46 +96,39 @@ __device__ __forceinline__ float erfcxPoly(float t) {
 
 // erfc(x)*exp(x^2), x in [0, 6], in double: degree-14 polynomial in u = (8 t - 5)/3, t = 1/(1 + x/2);
 // relative error 1e-11 (fit against scipy.special.erfcx).
+// (coefficients live in constant memory: a 64-bit literal costs two uniform moves per use, a constant-bank
+// operand costs nothing)
+__constant__ double kErfcxD[15] = {
+    6.52049290501760624e-09, 5.91610931414778049e-08, -2.22270786854985114e-07, -2.43147204892178188e-07,
+    2.86160851006960621e-06, -4.29950666125027918e-06, -2.27129828446940741e-05, 1.00552837184801405e-04,
+    1.33588067694989746e-04, -1.66536651372469141e-03, -1.67024495580285893e-03, 3.29934296618579967e-02,
+    1.69407590984921058e-01, 4.22187583608948647e-01, 3.78537416928964254e-01};
+__constant__ double kExpD[12] = {
+    2.50521083854417188e-08, 2.75573192239858907e-07, 2.75573192239858907e-06, 2.48015873015873016e-05,
+    1.98412698412698413e-04, 1.38888888888888894e-03, 8.33333333333333322e-03, 4.16666666666666644e-02,
+    1.66666666666666657e-01, 0.5, 1.0, 1.0};
+__constant__ double kMiscD[6] = {2.6666666666666665, -1.6666666666666667, 1.4426950408889634074, 6755399441055744.0,
+                                 -0.693147180559945286, -2.31904681384629956e-17};
+
 __device__ __forceinline__ double erfcxPolyD(double t) {
-    const double u = fma(t, 2.6666666666666665, -1.6666666666666667);
-    double p = 6.52049290501760624e-09;
-    p = fma(p, u, 5.91610931414778049e-08);
-    p = fma(p, u, -2.22270786854985114e-07);
-    p = fma(p, u, -2.43147204892178188e-07);
-    p = fma(p, u, 2.86160851006960621e-06);
-    p = fma(p, u, -4.29950666125027918e-06);
-    p = fma(p, u, -2.27129828446940741e-05);
-    p = fma(p, u, 1.00552837184801405e-04);
-    p = fma(p, u, 1.33588067694989746e-04);
-    p = fma(p, u, -1.66536651372469141e-03);
-    p = fma(p, u, -1.67024495580285893e-03);
-    p = fma(p, u, 3.29934296618579967e-02);
-    p = fma(p, u, 1.69407590984921058e-01);
-    p = fma(p, u, 4.22187583608948647e-01);
-    p = fma(p, u, 3.78537416928964254e-01);
+    const double u = fma(t, kMiscD[0], kMiscD[1]);
+    double p = kErfcxD[0];
+#pragma unroll
+    for (int k = 1; k < 15; k++) p = fma(p, u, kErfcxD[k]);
     return p;
 }
 
 // exp(-z) for z in [0, 60], double, ~3e-16 relative: 2^n * e^h with a degree-11 Taylor polynomial on
 // |h| <= ln(2)/2 -- the library exp() minus the special cases this kernel cannot hit.
 __device__ __forceinline__ double expNegD(double z) {
-    const double u = -z*1.4426950408889634074;                 // log2(e)
-    const double shifter = 6755399441055744.0;                  // 1.5 * 2^52: rounds to nearest integer
+    const double u = -z*kMiscD[2];                              // log2(e)
+    const double shifter = kMiscD[3];                           // 1.5 * 2^52: rounds to nearest integer
     const double n = (u + shifter) - shifter;
-    const double g = fma(n, -0.693147180559945286, -z);        // -z - n ln2 (hi part of ln2)
-    const double h = fma(n, -2.31904681384629956e-17, g);      // ... lo part
-    double p = 2.50521083854417188e-08;                          // 1/11!
-    p = fma(p, h, 2.75573192239858907e-07);
-    p = fma(p, h, 2.75573192239858907e-06);
-    p = fma(p, h, 2.48015873015873016e-05);
-    p = fma(p, h, 1.98412698412698413e-04);
-    p = fma(p, h, 1.38888888888888894e-03);
-    p = fma(p, h, 8.33333333333333322e-03);
-    p = fma(p, h, 4.16666666666666644e-02);
-    p = fma(p, h, 1.66666666666666657e-01);
-    p = fma(p, h, 0.5);
-    p = fma(p, h, 1.0);
-    p = fma(p, h, 1.0);
+    const double g = fma(n, kMiscD[4], -z);                     // -z - n ln2 (hi part of ln2)
+    const double h = fma(n, kMiscD[5], g);                      // ... lo part
+    double p = kExpD[0];                                        // 1/11! ... Taylor coefficients of exp
+#pragma unroll
+    for (int k = 1; k < 12; k++) p = fma(p, h, kExpD[k]);
     const int ni = (int) n;
     return __hiloint2double(__double2hiint(p) + (ni << 20), __double2loint(p));
 }
@@ -179,22 +172,150 @@ __device__ __forceinline__ void pairEnergyD(const uint4 fi, const uint4 fj, doub
         ec = qq*(y + a.krfD*r2 - a.crfD);
 }
 
+// Exact cutoff test from the fixed-point coordinates (the wrapped integer difference is the minimum image
+// for any pair near the cutoff, because the box is at least twice the cutoff).
+__device__ __forceinline__ bool exactInRange(const uint4 fj, const uint4 fi, const PairArgs& a) {
+    const double ex = (double) (int) (fj.x - fi.x)*a.dsx;
+    const double ey = (double) (int) (fj.y - fi.y)*a.dsy;
+    const double ez = (double) (int) (fj.z - fi.z)*a.dsz;
+    return ex*ex + ey*ey + ez*ez <= a.rc2d;
+}
+
+// The one definition of "pair (this lane's i, j slot js) interacts": r^2 <= rc^2 (decided exactly when
+// the fp32 value is within 2e-5 nm^2 of the cutoff) and not masked by an exclusion.
+__device__ __forceinline__ bool pairInRange(const WarpScratch& w, const PairArgs& a, float xi, float yi, float zi,
+                                            const uint4 pi, int js, bool isX, int lane) {
+    const float4 p = w.jPos[js];
+    const float dx = xi - p.x, dy = yi - p.y, dz = zi - p.z;
+    const float r2 = fmaf(dx, dx, fmaf(dy, dy, dz*dz));
+    bool in = r2 <= a.rc2;
+    if (fabsf(r2 - a.rc2) < 2.0e-5f) in = exactInRange(w.jFix[js], pi, a);
+    if (isX) in = in && !((w.jMask[js] >> lane) & 1u);
+    return in;
+}
+
+// One 32 x 32 tile of the force kernel: lane l meets j slot (l + k) & 31 at step k; i forces (fix, fiy, fiz)
+// and the rotating j forces (fjx, fjy, fjz) stay in registers.  EMODE 2 also compacts the in-cutoff pairs
+// into w.queue and evaluates their energies in double precision, 32 real pairs per pass.
+template <int EMODE, bool IS_PME>
+__device__ __forceinline__ void energyPass(const WarpScratch& w, const PairArgs& a, int lane, int count, double* acc) {
+    if (lane < count) {
+        const unsigned e = w.queue[lane];
+        const int il = e >> 5, jq = e & 31;
+        const float4 q1 = w.iPar[il], q2 = w.jPar[jq];
+        double ecd, evd;
+        pairEnergyD<IS_PME>(w.iFix[il], w.jFix[jq], w.iQ[il], w.jQ[jq], q1.x, q2.x, q1.y, q2.y, a, ecd, evd);
+        const int sl = triSlice(__float_as_int(q1.z), __float_as_int(q2.z));
+        acc[2*sl] += ecd;
+        acc[2*sl+1] += evd;
+    }
+}
+
+template <int EMODE, bool IS_PME, bool IS_X, bool SWITCH>
+__device__ __forceinline__ void tileLoop(WarpScratch& w, const PairArgs& a, const float2* shLam, int lamOff, int lane,
+                                         float xi, float yi, float zi, float qi, float sigi, float epsi, int si, const uint4 pi,
+                                         float& fix, float& fiy, float& fiz, float& fjx, float& fjy, float& fjz, double* acc) {
+    const unsigned below = (1u << lane) - 1u;
+    const float rc2 = a.rc2, alpha = a.alpha;
+    const float TWO_OVER_SQRT_PI = 1.1283791670955126f;
+    const int src = (lane + 1) & 31;
+    int qn = 0;                                   // pairs waiting in the energy queue
+#pragma unroll 2
+    for (int k = 0; k < 32; k++) {
+        const int js = (lane + k) & 31;
+        const float4 p = w.jPos[js];
+        const float4 pr = w.jPar[js];
+        const float dx = xi - p.x, dy = yi - p.y, dz = zi - p.z;
+        const float r2 = fmaf(dx, dx, fmaf(dy, dy, dz*dz));
+        bool in = r2 <= rc2;
+        if (fabsf(r2 - rc2) < 2.0e-5f) in = exactInRange(w.jFix[js], pi, a);     // borderline: rare
+        if (IS_X) in = in && !((w.jMask[js] >> lane) & 1u);
+        if (EMODE == 2) {
+            const unsigned m = __ballot_sync(FULL_MASK, in);
+            if (in) w.queue[qn + __popc(m & below)] = (unsigned short) ((lane << 5) | js);
+            qn += __popc(m);
+            if (qn >= 32) {                       // warp-uniform
+                __syncwarp();
+                energyPass<EMODE, IS_PME>(w, a, lane, 32, acc);
+                const int rest = qn - 32;
+                const unsigned short moved = lane < rest ? w.queue[32 + lane] : (unsigned short) 0;
+                __syncwarp();
+                if (lane < rest) w.queue[lane] = moved;
+                qn = rest;
+            }
+        }
+        const float invR = rsqrtFast(r2);
+        const float r = r2*invR;
+        const float invR2 = invR*invR;
+        float s2 = (sigi + pr.x)*invR;
+        s2 *= s2;
+        const float s6 = s2*s2*s2;
+        const float eps = epsi*pr.y;
+        float ev = eps*(s6 - 1.f)*s6;
+        float fv = eps*fmaf(12.f, s6, -6.f)*s6*invR2;
+        const float qr = qi*p.w*invR;
+        float ec, fc;
+        if (IS_PME) {
+            const float ar = alpha*r;
+            const float ex = ex2Fast(-1.4426950408889634f*ar*ar);
+            const float tt = rcpFast(fmaf(0.5f, ar, 1.f));
+            const float erfcv = ex*erfcxPoly(tt);
+            ec = qr*erfcv;
+            fc = qr*invR2*fmaf(TWO_OVER_SQRT_PI*ar, ex, erfcv);
+        }
+        else {
+            ec = qr*fmaf(a.krf*r2, r, 1.f) - qi*p.w*a.crf;
+            fc = qr*invR2*fmaf(-2.f*a.krf*r2, r, 1.f);
+        }
+        if (SWITCH) {
+            if (r > a.rswitch) {
+                const float wd = 1.f/(a.rcut - a.rswitch);
+                const float u = (r - a.rswitch)*wd;
+                const float sv = 1.f + u*u*u*(-10.f + u*(15.f - u*6.f));
+                const float sd = u*u*(-30.f + u*(60.f - u*30.f))*wd;
+                fv = sv*fv - ev*sd*invR;
+                ev *= sv;
+            }
+        }
+        const int sj = __float_as_int(pr.z);
+        const float2 lam = shLam[lamOff + sj];
+        float dEdR = fmaf(lam.y, fv, lam.x*fc);
+        dEdR = in ? dEdR : 0.f;
+        fix = fmaf(dEdR, dx, fix); fiy = fmaf(dEdR, dy, fiy); fiz = fmaf(dEdR, dz, fiz);
+        fjx = fmaf(-dEdR, dx, fjx); fjy = fmaf(-dEdR, dy, fjy); fjz = fmaf(-dEdR, dz, fjz);
+        if (EMODE == 1 && in) {
+            const int sl = triSlice(si, sj);
+            acc[2*sl] += (double) ec;
+            acc[2*sl+1] += (double) ev;
+        }
+        fjx = __shfl_sync(FULL_MASK, fjx, src);
+        fjy = __shfl_sync(FULL_MASK, fjy, src);
+        fjz = __shfl_sync(FULL_MASK, fjz, src);
+    }
+    if (EMODE == 2) {                             // the queue refers to this tile's shared-memory slots
+        __syncwarp();
+        energyPass<EMODE, IS_PME>(w, a, lane, qn, acc);
+    }
+}
+
 // MODE 0: forces (+ energies per EMODE); MODE 1: count + hash the interacting pairs; MODE 2: also dump them.
 // EMODE 0: forces only; 1: single-precision energies; 2: double-precision energies.
 template <int EMODE, bool IS_PME, int MODE>
 __global__ void __launch_bounds__(PAIR_WARPS*32, 2) k_pair(const PairArgs a) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
-    __shared__ float2 shLam[MAX_SLICES];
+    __shared__ float2 shLam[MAX_SUBSETS*MAX_SUBSETS];      // (lambda_Coulomb, lambda_vdW) of subset pair (si, sj)
     __shared__ double shE[MAX_SLICES*2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpScratch& w = reinterpret_cast<WarpScratch*>(smemRaw)[warp];
-    if (threadIdx.x < MAX_SLICES) shLam[threadIdx.x] = make_float2(a.lam.c[threadIdx.x], a.lam.v[threadIdx.x]);
+    if (threadIdx.x < MAX_SUBSETS*MAX_SUBSETS) {
+        const int sl = triSlice(threadIdx.x / MAX_SUBSETS, threadIdx.x % MAX_SUBSETS);
+        shLam[threadIdx.x] = make_float2(a.lam.c[sl], a.lam.v[sl]);
+    }
     if (threadIdx.x < MAX_SLICES*2) shE[threadIdx.x] = 0.0;
     __syncthreads();
 
     const unsigned below = (1u << lane) - 1u;
     const int nItems = a.counters[2];
-    const float TWO_OVER_SQRT_PI = 1.1283791670955126f;
     double acc[MAX_SLICES*2];                     // [slice][term], dynamically indexed (local memory, L1-resident)
     if (EMODE != 0) {
 #pragma unroll
@@ -218,10 +339,14 @@ __global__ void __launch_bounds__(PAIR_WARPS*32, 2) k_pair(const PairArgs a) {
         float xi = (float) (pi.x - lo.x)*a.sx;
         const float yi = (float) (pi.y - lo.y)*a.sy, zi = (float) (pi.z - lo.z)*a.sz;
         if (!iValid) xi = 1.0e8f;
+        const float qi = iValid ? __uint_as_float(pi.w) : 0.f;
+        const float sigi = pari.x, epsi = pari.y;
+        const int si = __float_as_int(pari.z);
+        const int lamOff = si*MAX_SUBSETS;
+        float fix = 0.f, fiy = 0.f, fiz = 0.f;
         __syncwarp();
-        w.iPos[lane] = make_float4(xi, yi, zi, iValid ? __uint_as_float(pi.w) : 0.f);
+        w.iPos[lane] = make_float4(xi, yi, zi, qi);
         w.iPar[lane] = pari;
-        w.fi[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
         w.iFix[lane] = make_uint4(pi.x, pi.y, pi.z, (unsigned) __float_as_int(pari.z));
         if (EMODE == 2) w.iQ[lane] = iValid ? a.q64[first + lane] : 0.0;
 
@@ -254,37 +379,22 @@ __global__ void __launch_bounds__(PAIR_WARPS*32, 2) k_pair(const PairArgs a) {
             w.jPos[lane] = pj;
             w.jPar[lane] = parj;
             w.jFix[lane] = fixj;
-            w.fj[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (EMODE == 2) w.jQ[lane] = entry >= 0 ? a.q64[jIndex] : 0.0;
             if (isX) w.jMask[lane] = xm[(t - tJ)*32 + lane];
             __syncwarp();
 
-            // ---- phase A: cull.  Queue entry = (i lane << 5) | j slot ----
-            int qn = 0;
-#pragma unroll 4
-            for (int k = 0; k < 32; k++) {
-                const int js = (lane + k) & 31;
-                const float4 p = w.jPos[js];
-                const float dx = xi - p.x, dy = yi - p.y, dz = zi - p.z;
-                const float r2 = fmaf(dx, dx, fmaf(dy, dy, dz*dz));
-                bool in = r2 <= a.rc2;
-                if (fabsf(r2 - a.rc2) < 2.0e-5f) {
-                    // borderline: decide from the exact integer coordinates, in double
-                    const uint4 fj = w.jFix[js];
-                    const double ex = (double) (int) (fj.x - pi.x)*a.dsx;
-                    const double ey = (double) (int) (fj.y - pi.y)*a.dsy;
-                    const double ez = (double) (int) (fj.z - pi.z)*a.dsz;
-                    in = ex*ex + ey*ey + ez*ez <= a.rc2d;
-                }
-                if (isX) in = in && !((w.jMask[js] >> lane) & 1u);
-                const unsigned m = __ballot_sync(FULL_MASK, in);
-                if (in) w.queue[qn + __popc(m & below)] = (unsigned short) ((lane << 5) | js);
-                qn += __popc(m);
-            }
-            __syncwarp();
-
             if (MODE != 0) {
-                // the interacting-pair set itself (parity diagnostics)
+                // ---- the interacting-pair set itself (parity diagnostics): cull, then hash / dump ----
+                int qn = 0;
+#pragma unroll 4
+                for (int k = 0; k < 32; k++) {
+                    const int js = (lane + k) & 31;
+                    const bool in = pairInRange(w, a, xi, yi, zi, pi, js, isX, lane);
+                    const unsigned m = __ballot_sync(FULL_MASK, in);
+                    if (in) w.queue[qn + __popc(m & below)] = (unsigned short) ((lane << 5) | js);
+                    qn += __popc(m);
+                }
+                __syncwarp();
                 for (int base = 0; base < qn; base += 32) {
                     if (base + lane < qn) {
                         const unsigned e = w.queue[base + lane];
@@ -301,114 +411,32 @@ __global__ void __launch_bounds__(PAIR_WARPS*32, 2) k_pair(const PairArgs a) {
                 continue;
             }
 
-            // ---- phase B: evaluate, 32 real pairs per pass ----
-            for (int base = 0; base < qn; base += 32) {
-                const bool active = base + lane < qn;
-                int il = 32 + lane, js = 32 + lane;            // unique dummies for idle lanes
-                float fx = 0.f, fy = 0.f, fz = 0.f;
-                if (active) {
-                    const unsigned e = w.queue[base + lane];
-                    il = e >> 5; js = e & 31;
-                    const float4 p1 = w.iPos[il], q1 = w.iPar[il], p2 = w.jPos[js], q2 = w.jPar[js];
-                    const float dx = p1.x - p2.x, dy = p1.y - p2.y, dz = p1.z - p2.z;
-                    const float r2 = fmaf(dx, dx, fmaf(dy, dy, dz*dz));
-                    float invR = rsqrtFast(r2);
-                    invR = invR*fmaf(-0.5f*r2*invR, invR, 1.5f);            // one Newton step
-                    const float r = r2*invR;
-                    const float qq = p1.w*p2.w;
-                    const float sig = q1.x + q2.x;
-                    float s2 = sig*invR;
-                    s2 *= s2;
-                    const float s6 = s2*s2*s2;
-                    const float eps = q1.y*q2.y;
-                    const float invR2 = invR*invR;
-                    float ev = eps*(s6 - 1.f)*s6;
-                    float fv = eps*fmaf(12.f, s6, -6.f)*s6*invR2;
-                    float ec, fc;
-                    if (IS_PME) {
-                        const float ar = a.alpha*r;
-                        const float ex = ex2Fast(-1.4426950408889634f*ar*ar);
-                        const float tt = rcpFast(fmaf(0.5f, ar, 1.f));
-                        const float erfcv = ex*erfcxPoly(tt);
-                        const float qr = qq*invR;
-                        ec = qr*erfcv;
-                        fc = qr*invR2*fmaf(TWO_OVER_SQRT_PI*ar, ex, erfcv);
-                    }
-                    else {
-                        ec = qq*(invR + a.krf*r2 - a.crf);
-                        fc = qq*invR2*(invR - 2.f*a.krf*r2);
-                    }
-                    if (a.useSwitch && r > a.rswitch) {
-                        const float wd = 1.f/(a.rcut - a.rswitch);
-                        const float u = (r - a.rswitch)*wd;
-                        const float sv = 1.f + u*u*u*(-10.f + u*(15.f - u*6.f));
-                        const float sd = u*u*(-30.f + u*(60.f - u*30.f))*wd;
-                        fv = sv*fv - ev*sd*invR;
-                        ev *= sv;
-                    }
-                    const int sl = triSlice(__float_as_int(q1.z), __float_as_int(q2.z));
-                    const float2 lam = shLam[sl];
-                    const float dEdR = lam.y*fv + lam.x*fc;
-                    fx = dEdR*dx; fy = dEdR*dy; fz = dEdR*dz;
-                    if (EMODE == 1) {
-                        acc[2*sl] += (double) ec;
-                        acc[2*sl+1] += (double) ev;
-                    }
-                    if (EMODE == 2) {
-                        double ecd, evd;
-                        pairEnergyD<IS_PME>(w.iFix[il], w.jFix[js], w.iQ[il], w.jQ[js], q1.x, q2.x, q1.y, q2.y, a, ecd, evd);
-                        acc[2*sl] += ecd;
-                        acc[2*sl+1] += evd;
-                    }
-                }
-                // scatter: lanes that share an atom take turns in lane order (fixed summation order)
-                {
-                    const unsigned peers = __match_any_sync(FULL_MASK, il);
-                    const int rank = __popc(peers & below);
-                    unsigned pending = __ballot_sync(FULL_MASK, active);
-                    for (int round = 0; pending; round++) {
-                        if (active && rank == round) {
-                            float4 f = w.fi[il];
-                            f.x += fx; f.y += fy; f.z += fz;
-                            w.fi[il] = f;
-                        }
-                        __syncwarp();
-                        pending = __ballot_sync(FULL_MASK, active && rank > round);
-                    }
-                }
-                {
-                    const unsigned peers = __match_any_sync(FULL_MASK, js);
-                    const int rank = __popc(peers & below);
-                    unsigned pending = __ballot_sync(FULL_MASK, active);
-                    for (int round = 0; pending; round++) {
-                        if (active && rank == round) {
-                            float4 f = w.fj[js];
-                            f.x -= fx; f.y -= fy; f.z -= fz;
-                            w.fj[js] = f;
-                        }
-                        __syncwarp();
-                        pending = __ballot_sync(FULL_MASK, active && rank > round);
-                    }
-                }
+            // ---- forces: dense 32 x 32 tile, lane l meets j slot (l + k) & 31 at step k ----
+            float fjx = 0.f, fjy = 0.f, fjz = 0.f;
+            // four copies of the loop so that the exclusion-mask test and the switching function cost nothing
+            // in the tiles that do not have them (both conditions are warp-uniform)
+            if (isX) {
+                if (a.useSwitch) tileLoop<EMODE, IS_PME, true, true>(w, a, shLam, lamOff, lane, xi, yi, zi, qi, sigi, epsi, si, pi, fix, fiy, fiz, fjx, fjy, fjz, acc);
+                else tileLoop<EMODE, IS_PME, true, false>(w, a, shLam, lamOff, lane, xi, yi, zi, qi, sigi, epsi, si, pi, fix, fiy, fiz, fjx, fjy, fjz, acc);
             }
-            // j forces of this tile -> global fixed point
-            if (entry >= 0) {
-                const float4 f = w.fj[lane];
-                if (f.x != 0.f || f.y != 0.f || f.z != 0.f) {
-                    atomicAdd(a.force + jIndex, toFixed(f.x));
-                    atomicAdd(a.force + a.Npad + jIndex, toFixed(f.y));
-                    atomicAdd(a.force + 2*(size_t) a.Npad + jIndex, toFixed(f.z));
-                }
+            else {
+                if (a.useSwitch) tileLoop<EMODE, IS_PME, false, true>(w, a, shLam, lamOff, lane, xi, yi, zi, qi, sigi, epsi, si, pi, fix, fiy, fiz, fjx, fjy, fjz, acc);
+                else tileLoop<EMODE, IS_PME, false, false>(w, a, shLam, lamOff, lane, xi, yi, zi, qi, sigi, epsi, si, pi, fix, fiy, fiz, fjx, fjy, fjz, acc);
+            }
+            // j forces of this tile (lane l ends up with slot l) -> global fixed point
+            if (entry >= 0 && (fjx != 0.f || fjy != 0.f || fjz != 0.f)) {
+                atomicAdd(a.force + jIndex, toFixed(fjx));
+                atomicAdd(a.force + a.Npad + jIndex, toFixed(fjy));
+                atomicAdd(a.force + 2*(size_t) a.Npad + jIndex, toFixed(fjz));
             }
         }
         // i forces of this item -> global fixed point
         if (MODE == 0) {
             __syncwarp();
             if (iValid) {
-                const float4 f = w.fi[lane];
-                atomicAdd(a.force + first + lane, toFixed(f.x));
-                atomicAdd(a.force + a.Npad + first + lane, toFixed(f.y));
-                atomicAdd(a.force + 2*(size_t) a.Npad + first + lane, toFixed(f.z));
+                atomicAdd(a.force + first + lane, toFixed(fix));
+                atomicAdd(a.force + a.Npad + first + lane, toFixed(fiy));
+                atomicAdd(a.force + 2*(size_t) a.Npad + first + lane, toFixed(fiz));
             }
         }
     }

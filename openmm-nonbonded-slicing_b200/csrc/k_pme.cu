@@ -185,38 +185,54 @@ __device__ __forceinline__ void gridCoord(unsigned fixed, int n, int& index, T& 
     frac = (T) (unsigned) (t & 0xffffffffull)*(T) (1.0/4294967296.0);
 }
 
+// Shared by spreading and gather: lanes 0-14 evaluate the order-5 spline of "their" dimension (0-4 x, 5-9 y,
+// 10-14 z) and publish weight lane%5 (and its derivative) in the warp's shared-memory table; the base
+// grid indices come back by shuffle.
 template <typename T>
-__global__ void __launch_bounds__(256) k_spread(const PmeArgs a) {
-    const int lane = threadIdx.x & 31;
-    const int j = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
-    if (j >= a.N) return;
-    const uint4 p = a.posq[j];
-    const int subset = __float_as_int(a.par[j].z);
-    const float q = __uint_as_float(p.w);
-    // lanes 0-4 x, 5-9 y, 10-14 z: each lane keeps the weight lane%5 of "its" dimension
+__device__ __forceinline__ void splineTable(const PmeArgs& a, const uint4 p, int lane, T* wt, T* dwt, int& ix0, int& iy0, int& iz0) {
     const int dim = min(lane/5, 2), kk = lane % 5;
     int index; T frac;
     gridCoord<T>(dim == 0 ? p.x : (dim == 1 ? p.y : p.z), dim == 0 ? a.nx : (dim == 1 ? a.ny : a.nz), index, frac);
     T th[5], dth[5];
     bspline5(frac, th, dth);
-    T mine = th[0];
+    T mine = th[0], dmine = dth[0];
 #pragma unroll
-    for (int k = 1; k < 5; k++) mine = kk == k ? th[k] : mine;
-    const int ix0 = __shfl_sync(FULL_MASK, index, 0), iy0 = __shfl_sync(FULL_MASK, index, 5), iz0 = __shfl_sync(FULL_MASK, index, 10);
-    const int ox = lane/5, oy = lane % 5;
-    const T tx = __shfl_sync(FULL_MASK, mine, min(ox, 4)), ty = __shfl_sync(FULL_MASK, mine, 5 + oy);
-    T tz[5];
+    for (int k = 1; k < 5; k++) { mine = kk == k ? th[k] : mine; dmine = kk == k ? dth[k] : dmine; }
+    __syncwarp();
+    if (lane < 15) { wt[lane] = mine; if (dwt) dwt[lane] = dmine; }
+    ix0 = __shfl_sync(FULL_MASK, index, 0);
+    iy0 = __shfl_sync(FULL_MASK, index, 5);
+    iz0 = __shfl_sync(FULL_MASK, index, 10);
+    __syncwarp();
+}
+
+// One warp per (sorted) atom.  The 125 grid points are dealt to the lanes with z fastest (point = lane + 32 i,
+// z offset = point % 5), so one warp-wide atomic touches runs of 5 consecutive cells of a grid row instead of 25
+// different rows: about a third of the L2 atomic transactions of a row-per-lane assignment.
+template <typename T>
+__global__ void __launch_bounds__(256) k_spread(const PmeArgs a) {
+    __shared__ T wtab[8][16];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int j = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
+    if (j >= a.N) return;
+    const uint4 p = a.posq[j];
+    const int subset = __float_as_int(a.par[j].z);
+    const float q = __uint_as_float(p.w);
+    if (q == 0.f || subset < a.ownLo || subset >= a.ownHi) return;      // warp-uniform
+    int ix0, iy0, iz0;
+    splineTable<T>(a, p, lane, wtab[warp], (T*) nullptr, ix0, iy0, iz0);
+    const T* wt = wtab[warp];
+    T* grid = (T*) a.grid + (size_t) subset*a.nx*a.ny*a.nz;
 #pragma unroll
-    for (int k = 0; k < 5; k++) tz[k] = __shfl_sync(FULL_MASK, mine, 10 + k);
-    if (lane >= 25 || q == 0.f || subset < a.ownLo || subset >= a.ownHi) return;
-    int x = ix0 + ox; x -= x >= a.nx ? a.nx : 0;
-    int y = iy0 + oy; y -= y >= a.ny ? a.ny : 0;
-    T* row = (T*) a.grid + (((size_t) subset*a.nx + x)*a.ny + y)*a.nz;
-    const T w = (T) q*tx*ty;
-#pragma unroll
-    for (int k = 0; k < 5; k++) {
-        int z = iz0 + k; z -= z >= a.nz ? a.nz : 0;
-        atomicAdd(row + z, w*tz[k]);
+    for (int i = 0; i < 4; i++) {
+        const int pt = lane + 32*i;
+        if (pt < 125) {
+            const int row = pt/5, oz = pt - row*5, ox = row/5, oy = row - ox*5;
+            int x = ix0 + ox; x -= x >= a.nx ? a.nx : 0;
+            int y = iy0 + oy; y -= y >= a.ny ? a.ny : 0;
+            int z = iz0 + oz; z -= z >= a.nz ? a.nz : 0;
+            atomicAdd(grid + ((size_t) x*a.ny + y)*a.nz + z, (T) q*wt[ox]*wt[5 + oy]*wt[10 + oz]);
+        }
     }
 }
 
@@ -430,7 +446,8 @@ __global__ void __launch_bounds__(256) k_fft_x_conv(const FftArgs a) {
 // Reference: pme_grid_interpolate_force, ReferencePME.cpp:598-702.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_gather(const PmeArgs a) {
-    const int lane = threadIdx.x & 31;
+    __shared__ float wtab[8][16], dwtab[8][16];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int j = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
     if (j >= a.N) return;
     const uint4 p = a.posq[j];
@@ -438,37 +455,26 @@ __global__ void __launch_bounds__(256) k_gather(const PmeArgs a) {
     if (q == 0.f) return;
     const int subset = __float_as_int(a.par[j].z);
     if (subset < a.ownLo || subset >= a.ownHi) return;
-    const int dim = min(lane/5, 2), kk = lane % 5;
-    int index; float frac;
-    gridCoord<float>(dim == 0 ? p.x : (dim == 1 ? p.y : p.z), dim == 0 ? a.nx : (dim == 1 ? a.ny : a.nz), index, frac);
-    float th[5], dth[5];
-    bspline5(frac, th, dth);
-    float mine = th[0], dmine = dth[0];
-#pragma unroll
-    for (int k = 1; k < 5; k++) { mine = kk == k ? th[k] : mine; dmine = kk == k ? dth[k] : dmine; }
-    const int ix0 = __shfl_sync(FULL_MASK, index, 0), iy0 = __shfl_sync(FULL_MASK, index, 5), iz0 = __shfl_sync(FULL_MASK, index, 10);
-    const int ox = min(lane/5, 4), oy = lane % 5;
-    const float tx = __shfl_sync(FULL_MASK, mine, ox), ty = __shfl_sync(FULL_MASK, mine, 5 + oy);
-    const float dtx = __shfl_sync(FULL_MASK, dmine, ox), dty = __shfl_sync(FULL_MASK, dmine, 5 + oy);
-    float tz[5], dtz[5];
-#pragma unroll
-    for (int k = 0; k < 5; k++) { tz[k] = __shfl_sync(FULL_MASK, mine, 10 + k); dtz[k] = __shfl_sync(FULL_MASK, dmine, 10 + k); }
+    int ix0, iy0, iz0;
+    splineTable<float>(a, p, lane, wtab[warp], dwtab[warp], ix0, iy0, iz0);
+    const float* wt = wtab[warp];
+    const float* dwt = dwtab[warp];
+    const float* pot = a.pot + (size_t) subset*a.nx*a.ny*a.nz;
     float fx = 0.f, fy = 0.f, fz = 0.f;
-    if (lane < 25) {
-        int x = ix0 + ox; x -= x >= a.nx ? a.nx : 0;
-        int y = iy0 + oy; y -= y >= a.ny ? a.ny : 0;
-        const float* row = a.pot + (((size_t) subset*a.nx + x)*a.ny + y)*a.nz;
-        float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-        for (int k = 0; k < 5; k++) {
-            int z = iz0 + k; z -= z >= a.nz ? a.nz : 0;
-            const float g = row[z];
-            s0 = fmaf(tz[k], g, s0);
-            s1 = fmaf(dtz[k], g, s1);
+    for (int i = 0; i < 4; i++) {
+        const int pt = lane + 32*i;                  // z fastest: coalesced runs of 5 cells per grid row
+        if (pt < 125) {
+            const int row = pt/5, oz = pt - row*5, ox = row/5, oy = row - ox*5;
+            int x = ix0 + ox; x -= x >= a.nx ? a.nx : 0;
+            int y = iy0 + oy; y -= y >= a.ny ? a.ny : 0;
+            int z = iz0 + oz; z -= z >= a.nz ? a.nz : 0;
+            const float g = pot[((size_t) x*a.ny + y)*a.nz + z];
+            const float tx = wt[ox], ty = wt[5 + oy], tz = wt[10 + oz];
+            fx = fmaf(dwt[ox]*ty*tz, g, fx);
+            fy = fmaf(tx*dwt[5 + oy]*tz, g, fy);
+            fz = fmaf(tx*ty*dwt[10 + oz], g, fz);
         }
-        fx = dtx*ty*s0;
-        fy = tx*dty*s0;
-        fz = tx*ty*s1;
     }
     fx = warpSum(fx); fy = warpSum(fy); fz = warpSum(fz);
     if (lane == 0) {

@@ -16,6 +16,7 @@
 
 namespace nbs {
 
+unsigned long long gAllocEpoch = 1;
 static thread_local std::string gLastError;
 void setError(const std::string& message) { gLastError = message; }
 
@@ -112,6 +113,7 @@ static int readDescription(Context& c, const nbs_system_desc& d, bool creating) 
     if (d.dispersion_coefficients)
         for (int s = 0; s < c.nSl; s++) c.dispersion[s] = d.dispersion_coefficients[s];
     c.paramsDirty = true;
+    c.paramVersion++;
     return NBS_OK;
 }
 
@@ -342,6 +344,10 @@ static void releaseAll(Context& c) {
     if (c.hEnergy) cudaFreeHost(c.hEnergy);
     if (c.hForce) cudaFreeHost(c.hForce);
     c.hCounters = nullptr; c.hEnergy = nullptr; c.hForce = nullptr;
+    if (c.graphExec) cudaGraphExecDestroy(c.graphExec);
+    c.graphExec = nullptr;
+    if (c.ownStream) cudaStreamDestroy(c.ownStream);
+    c.ownStream = nullptr;
     if (c.directStream) cudaStreamDestroy(c.directStream);
     if (c.evSorted) cudaEventDestroy(c.evSorted);
     if (c.evDirectDone) cudaEventDestroy(c.evDirectDone);
@@ -433,6 +439,7 @@ int nbs_update_parameters(nbs_context* ctx, const nbs_system_desc* desc) {
 int nbs_set_lambdas(nbs_context* ctx, const double* lambdas) {
     if (!ctx || !lambdas) return fail(NBS_ERR_INVALID, "null argument");
     ctx->c.lambdas.assign(lambdas, lambdas + 2*(size_t) ctx->c.nSl);
+    ctx->c.paramVersion++;
     return NBS_OK;
 }
 
@@ -445,7 +452,7 @@ int nbs_set_global_parameters(nbs_context* ctx, const double* values) {
     for (int k = 0; k < c.nGlobals; k++)
         if (c.globals[k] != values[k]) { c.globals[k] = values[k]; changed = true; }
     // only parameters that feed an offset change the per-particle data (CommonNonbondedSlicingKernels.cpp:1152-1163)
-    if (changed && (!c.pOffIdx.empty() || !c.eOffIdx.empty())) c.paramsDirty = true;
+    if (changed && (!c.pOffIdx.empty() || !c.eOffIdx.empty())) { c.paramsDirty = true; c.paramVersion++; }
     return NBS_OK;
 }
 
@@ -479,12 +486,22 @@ static int validateExec(Context& c, const nbs_exec_args* args) {
     return NBS_OK;
 }
 
+// The stream an evaluation is enqueued on: the caller's, or -- when the caller passes the legacy default
+// stream, which cannot be captured into a graph -- a blocking stream of our own (blocking streams order
+// themselves after work already queued on the legacy default stream, and every evaluation ends with a
+// synchronisation, so the caller sees the same ordering).
+static cudaStream_t workStream(Context& c, const nbs_exec_args* args) {
+    if (args->stream != nullptr || c.nRanks != 1) return (cudaStream_t) args->stream;
+    if (!c.ownStream && cudaStreamCreate(&c.ownStream) != cudaSuccess) { cudaGetLastError(); c.ownStream = nullptr; }
+    return c.ownStream;
+}
+
 static int phaseBegin(Context& c, const nbs_exec_args* args) {
     int status = validateExec(c, args);
     if (status != NBS_OK) return status;
     NBS_CUDA_CHECK(cudaSetDevice(c.device));
     const double* box = args->box;
-    c.stream = (cudaStream_t) args->stream;
+    c.stream = workStream(c, args);
     cudaStream_t st = c.stream;
     const bool pme = c.method == NBS_METHOD_PME;
     c.phaseEnergy = args->slice_energies != nullptr;
@@ -565,9 +582,8 @@ static int phaseConvolve(Context& c, const nbs_exec_args* args) {
     return NBS_OK;
 }
 
-// Returns NBS_OK, an error, or NBS_RETRY: the neighbour-list capacity was exceeded (on this or any
-// other rank), it has been doubled, and the whole evaluation must be repeated.
-static int phaseFinish(Context& c, const nbs_exec_args* args) {
+// Enqueues the output stage: forces to the caller's layout, energies and counters to pinned host memory.
+static int phaseFinishEnqueue(Context& c, const nbs_exec_args* args) {
     if (c.phase != 2) return fail(NBS_ERR_INVALID, "nbs_execute_finish called without nbs_execute_convolve");
     c.phase = 0;
     NBS_CUDA_CHECK(cudaSetDevice(c.device));
@@ -598,6 +614,14 @@ static int phaseFinish(Context& c, const nbs_exec_args* args) {
     NBS_CUDA_CHECK(cudaMemcpyAsync(c.hEnergy, c.dEnergy.d, sizeof(double)*ENERGY_WORDS, cudaMemcpyDeviceToHost, st));
     NBS_CUDA_CHECK(cudaMemcpyAsync(c.hCounters, c.dCounters.d, sizeof(int)*16, cudaMemcpyDeviceToHost, st));
     timerMark(c, "d2h");
+    return NBS_OK;
+}
+
+// Waits for the evaluation and does the host-side part: overflow check, constants, output tables.
+static int phaseComplete(Context& c, const nbs_exec_args* args) {
+    cudaStream_t st = c.stream;
+    const int N = c.N;
+    const double* box = args->box;
     NBS_CUDA_CHECK(cudaStreamSynchronize(st));
     NBS_CUDA_CHECK(cudaGetLastError());
     if (c.hCounters[1] != 0 || c.hEnergy[2*MAX_SLICES] != 0.0) {
@@ -635,14 +659,108 @@ static int phaseFinish(Context& c, const nbs_exec_args* args) {
     return NBS_OK;
 }
 
+// Returns NBS_OK, an error, or NBS_RETRY: the neighbour-list capacity was exceeded (on this or any
+// other rank), it has been doubled, and the whole evaluation must be repeated.
+static int phaseFinish(Context& c, const nbs_exec_args* args) {
+    int status = phaseFinishEnqueue(c, args);
+    if (status != NBS_OK) return status;
+    return phaseComplete(c, args);
+}
+
+static unsigned long long mix64(unsigned long long h, unsigned long long v) {
+    h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+    return h;
+}
+
+// Everything a captured evaluation depends on besides the contents of device memory.
+static unsigned long long graphSignature(const Context& c, const nbs_exec_args* a) {
+    unsigned long long h = 0x243F6A8885A308D3ull;
+    h = mix64(h, (unsigned long long) a->positions); h = mix64(h, (unsigned long long) a->forces);
+    h = mix64(h, (unsigned long long) a->atom_index); h = mix64(h, (unsigned long long) a->stream);
+    h = mix64(h, (unsigned long long) a->slice_energies != 0);
+    h = mix64(h, ((unsigned long long) a->positions_format << 40) | ((unsigned long long) a->positions_space << 32) |
+                 ((unsigned long long) a->forces_format << 24) | ((unsigned long long) a->forces_space << 16) |
+                 ((unsigned long long) a->forces_accumulate << 8) | ((unsigned long long) (a->include_direct != 0) << 1) |
+                 (unsigned long long) (a->include_reciprocal != 0));
+    h = mix64(h, (unsigned long long) a->padded_num_atoms);
+    for (int k = 0; k < 9; k++) { unsigned long long b; std::memcpy(&b, &a->box[k], 8); h = mix64(h, b); }
+    h = mix64(h, c.paramVersion);
+    h = mix64(h, gAllocEpoch);
+    h = mix64(h, ((unsigned long long) c.capJ << 32) | (unsigned long long) c.capX);
+    return h | 1ull;
+}
+
+static bool hostPointerIsPinned(const void* p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return attr.type == cudaMemoryTypeHost;
+}
+
 int nbs_execute(nbs_context* ctx, const nbs_exec_args* args) {
     if (!ctx || !args) return fail(NBS_ERR_INVALID, "null argument");
     Context& c = ctx->c;
     if (c.nRanks != 1) return fail(NBS_ERR_INVALID, "a sharded context is driven through nbs_execute_begin/convolve/finish");
+    // A whole evaluation is ~20 short kernels: once the same evaluation (same buffers, box, parameters) has
+    // run once, it is captured into a CUDA graph and replayed, which removes the per-launch gaps.
+    bool graphable = !(c.flags & NBS_FLAG_NO_GRAPH) && !c.profiling && !c.paramsDirty && workStream(c, args) != nullptr;
+    if (graphable && args->positions_space == NBS_MEM_HOST) graphable = hostPointerIsPinned(args->positions);
+    if (graphable && args->forces && args->forces_space == NBS_MEM_HOST && !args->forces_accumulate)
+        graphable = hostPointerIsPinned(args->forces);       // (accumulation goes through our own pinned staging buffer)
     for (int attempt = 0; attempt < 7; attempt++) {
-        int status = phaseBegin(c, args);
-        if (status == NBS_OK) status = phaseConvolve(c, args);
-        if (status == NBS_OK) status = phaseFinish(c, args);
+        int status;
+        const unsigned long long key = graphable ? graphSignature(c, args) : 0;
+        if (graphable && c.graphExec && c.graphKey == key) {
+            // replay
+            status = validateExec(c, args);
+            if (status != NBS_OK) return status;
+            NBS_CUDA_CHECK(cudaSetDevice(c.device));
+            c.stream = workStream(c, args);
+            c.phaseEnergy = args->slice_energies != nullptr;
+            c.phaseDirect = args->include_direct != 0;
+            c.phaseRecip = args->include_reciprocal != 0 && c.method == NBS_METHOD_PME;
+            NBS_CUDA_CHECK(cudaGraphLaunch(c.graphExec, c.stream));
+            c.launches += c.graphLaunches;
+            status = phaseComplete(c, args);
+        }
+        else if (graphable && c.warmKey == key) {
+            // second identical evaluation: capture it
+            status = validateExec(c, args);
+            if (status != NBS_OK) return status;
+            NBS_CUDA_CHECK(cudaSetDevice(c.device));
+            cudaStream_t st = workStream(c, args);
+            if (c.graphExec) { cudaGraphExecDestroy(c.graphExec); c.graphExec = nullptr; }
+            const long long before = c.launches;
+            NBS_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            status = phaseBegin(c, args);
+            if (status == NBS_OK) status = phaseConvolve(c, args);
+            if (status == NBS_OK) status = phaseFinishEnqueue(c, args);
+            cudaGraph_t graph = nullptr;
+            cudaError_t e = cudaStreamEndCapture(st, &graph);
+            if (status != NBS_OK || e != cudaSuccess || !graph) {
+                if (graph) cudaGraphDestroy(graph);
+                cudaGetLastError();
+                c.warmKey = 0;
+                graphable = false;                 // fall back to plain launches for this call
+                if (status != NBS_OK) return status;
+                attempt--;
+                continue;
+            }
+            e = cudaGraphInstantiate(&c.graphExec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e != cudaSuccess) { c.graphExec = nullptr; cudaGetLastError(); c.warmKey = 0; graphable = false; attempt--; continue; }
+            c.graphKey = key;
+            c.graphLaunches = c.launches - before;
+            c.launches = before;
+            NBS_CUDA_CHECK(cudaGraphLaunch(c.graphExec, st));
+            c.launches += c.graphLaunches;
+            status = phaseComplete(c, args);
+        }
+        else {
+            status = phaseBegin(c, args);
+            if (status == NBS_OK) status = phaseConvolve(c, args);
+            if (status == NBS_OK) status = phaseFinish(c, args);
+            if (status == NBS_OK && graphable) c.warmKey = graphSignature(c, args);
+        }
         if (status != NBS_RETRY) return status;
     }
     return fail(NBS_ERR_CAPACITY, "neighbour list capacity exceeded");
@@ -673,6 +791,7 @@ int nbs_set_shard(nbs_context* ctx, int32_t rank, int32_t num_ranks, int32_t blo
     if (subset_begin < 0 || subset_end > c.nS || subset_begin > subset_end)
         return fail(NBS_ERR_INVALID, "illegal subset range");
     c.rank = rank; c.nRanks = num_ranks;
+    c.paramVersion++;
     c.blockPeriod = block_period; c.blockOffset = block_offset; c.blockWidth = block_width;
     c.ownLo = subset_begin; c.ownHi = subset_end;
     c.haveLast = false;
@@ -682,6 +801,7 @@ int nbs_set_shard(nbs_context* ctx, int32_t rank, int32_t num_ranks, int32_t blo
 int nbs_debug_set_list_capacity(nbs_context* ctx, int32_t j_capacity, int32_t x_capacity) {
     if (!ctx || j_capacity < 64 || x_capacity < 64 || j_capacity % 32 || x_capacity % 32)
         return fail(NBS_ERR_INVALID, "capacities must be multiples of 32, at least 64");
+    ctx->c.paramVersion++;
     ctx->c.capJ = j_capacity;
     ctx->c.capX = x_capacity;
     return NBS_OK;

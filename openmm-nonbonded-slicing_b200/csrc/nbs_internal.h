@@ -33,12 +33,14 @@ constexpr int MAX_SLICES = MAX_SUBSETS*(MAX_SUBSETS+1)/2;
 constexpr int PME_ORDER = 5;
 constexpr int J_SHIFT_BITS = 26;                 // sorted index in the low 26 bits of a list entry
 constexpr int J_INDEX_MASK = (1 << J_SHIFT_BITS)-1;
-constexpr int BUILD_WARPS = 4;                   // warps per CTA in the list-build kernel
+constexpr int BUILD_WARPS = 8;                   // warps per CTA in the list-build kernel
 constexpr int PAIR_WARPS = 8;                    // warps per CTA in the pair kernel
 
 void setError(const std::string& message);
 #define NBS_CUDA_CHECK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
     nbs::setError(std::string(#call) + ": " + cudaGetErrorString(e_)); return NBS_ERR_CUDA; } } while (0)
+
+extern unsigned long long gAllocEpoch;       // bumped whenever a device buffer moves (invalidates captured graphs)
 
 template <class T>
 struct Buf {
@@ -46,6 +48,7 @@ struct Buf {
     size_t cap = 0;
     cudaError_t ensure(size_t n) {
         if (n <= cap) return cudaSuccess;
+        gAllocEpoch++;
         if (d) cudaFree(d);
         d = nullptr;
         cap = 0;
@@ -166,11 +169,16 @@ struct Context {
     int chunkTiles = 2;                      // tiles per pair-kernel work item
     int numSMs = 148;
     // ---- phase state of the evaluation in flight ----
+    cudaStream_t ownStream = nullptr;        // used when the caller passes the legacy default stream
     cudaStream_t directStream = nullptr;     // direct space runs here, concurrently with PME on `stream`
     cudaEvent_t evSorted = nullptr, evDirectDone = nullptr;
     bool phaseDirect = false, phaseRecip = false, phaseEnergy = false, directOverlapped = false;
     const double* phasePos64 = nullptr;
     int phase = 0;                           // 0 idle, 1 begun, 2 convolved
+    // ---- CUDA graph of a whole single-rank evaluation (replayed while nothing it depends on changes) ----
+    cudaGraphExec_t graphExec = nullptr;
+    unsigned long long graphKey = 0, warmKey = 0, paramVersion = 0;
+    long long graphLaunches = 0;             // kernels per graph replay (for the launch counter)
 };
 
 constexpr int ENERGY_WORDS = 2*MAX_SLICES + 8;   // slice table + [2*MAX_SLICES] = list-overflow flag (as a double, so it all-reduces)

@@ -137,7 +137,7 @@ class DescArrays:
                 setattr(self.desc, name, value)
 
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libnbslice_b200.so")
+LIB_PATH = os.environ.get("NBS_B200_LIBRARY") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libnbslice_b200.so")
 _lib = None
 
 # every symbol include/nbslice_b200.h declares

@@ -5,8 +5,10 @@
 
 namespace nbs {
 
-constexpr int FFT_THREADS = 512;     // plane kernels (zy forward, yz inverse)
-constexpr int FFT_X_THREADS = 256;   // x + convolution kernel: more registers per thread, two CTAs per SM
+constexpr int FFT_THREADS = 512;     // upper bound of the plane kernels' CTA size (zy forward, yz inverse): two CTAs per SM
+                                     // at 64 registers; the launch picks the size that splits the widest pass of the plan
+                                     // into the fewest rounds of equal size (measured: 544 threads = one CTA per SM = slower)
+constexpr int FFT_X_THREADS = 256;   // upper bound for the x + convolution kernel (more registers per thread)
 constexpr int FFT_UNPACK_Q = 4;      // (row pair, kz) items a thread stages per round of the real<->complex (un)packing
 
 struct PlaneFftPlan {
@@ -18,6 +20,7 @@ struct PlaneFftArgs {
     int ownLo, ownHi;                // subsets whose grids this rank transforms / produces
     int rowStride;                   // zy / yz kernels: complex elements per plane row in shared memory
     int chunk;                       // x kernel: kz values per CTA
+    int planeThreads, xThreads;      // CTA sizes chosen for this plan
     unsigned long long factorsX, factorsY, factorsZ;
     const void* twx; const void* twy; const void* twz;     // exp(-2 pi i k / n), precision T
     const void* grid;                // real charge grids   [nS][nx][ny][nz]      (T)

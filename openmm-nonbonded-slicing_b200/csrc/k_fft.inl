@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_zy_fwd(const PlaneFftArgs a
     // unpack Z -> the two rows' half spectra: S0[k] = (Z[k] + conj Z[n-k])/2, S1[k] = (Z[k] - conj Z[n-k])/(2i).
     // In place, so a round stages whole row pairs in registers before anything is written.
     {
-        const int pairsPerRound = max(1, (FFT_THREADS*FFT_UNPACK_Q)/nzh);
+        const int pairsPerRound = max(1, ((int) blockDim.x*FFT_UNPACK_Q)/nzh);
         const T half = (T) 0.5;
         for (int p0 = 0; p0 < pairs; p0 += pairsPerRound) {
             const int count = min(pairsPerRound, pairs - p0)*nzh;
@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_yz_inv(const PlaneFftArgs a
     // so that fwd(W) = conj(r0 + i r1) with r0, r1 the two real rows.
     {
         const int pairs = (ny + 1) >> 1;
-        const int pairsPerRound = max(1, (FFT_THREADS*FFT_UNPACK_Q)/nzh);
+        const int pairsPerRound = max(1, ((int) blockDim.x*FFT_UNPACK_Q)/nzh);
         for (int p0 = 0; p0 < pairs; p0 += pairsPerRound) {
             const int count = min(pairsPerRound, pairs - p0)*nzh;
             C a0[FFT_UNPACK_Q], a1[FFT_UNPACK_Q];
@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_yz_inv(const PlaneFftArgs a
 // pass touches consecutive banks and the global <-> shared copies are straight.
 // ---------------------------------------------------------------------------------------------
 template <typename T, int RMAX, int NS>
-__global__ void __launch_bounds__(FFT_THREADS) k_fft_x_conv2(const PlaneFftArgs a) {
+__global__ void __launch_bounds__(FFT_X_THREADS) k_fft_x_conv2(const PlaneFftArgs a) {
     typedef typename Cx2<T>::type C;
     extern __shared__ double2 fftSmem[];
     C* sm = (C*) fftSmem;
@@ -401,19 +401,19 @@ static int launchPlaneT(Context& c, PlaneFftArgs a, int half, size_t smPlane, si
     const int nOwn = c.ownHi - c.ownLo;
     const int planes = nOwn*a.nx;
     if (half == 0) {
-        k_fft_zy_fwd<T, RMAX><<<planes, FFT_THREADS, smPlane, st>>>(a);
+        k_fft_zy_fwd<T, RMAX><<<planes, a.planeThreads, smPlane, st>>>(a);
         c.launches++;
         return NBS_OK;
     }
     const int xCtas = a.ny*((a.nzh + a.chunk - 1)/a.chunk);
     switch (c.nS) {
-        case 1: k_fft_x_conv2<T, RMAX, 1><<<xCtas, FFT_X_THREADS, smX, st>>>(a); break;
-        case 2: k_fft_x_conv2<T, RMAX, 2><<<xCtas, FFT_X_THREADS, smX, st>>>(a); break;
-        case 3: k_fft_x_conv2<T, RMAX, 3><<<xCtas, FFT_X_THREADS, smX, st>>>(a); break;
-        case 4: k_fft_x_conv2<T, RMAX, 4><<<xCtas, FFT_X_THREADS, smX, st>>>(a); break;
-        default: k_fft_x_conv2<T, RMAX, MAX_SUBSETS><<<xCtas, FFT_X_THREADS, smX, st>>>(a); break;
+        case 1: k_fft_x_conv2<T, RMAX, 1><<<xCtas, a.xThreads, smX, st>>>(a); break;
+        case 2: k_fft_x_conv2<T, RMAX, 2><<<xCtas, a.xThreads, smX, st>>>(a); break;
+        case 3: k_fft_x_conv2<T, RMAX, 3><<<xCtas, a.xThreads, smX, st>>>(a); break;
+        case 4: k_fft_x_conv2<T, RMAX, 4><<<xCtas, a.xThreads, smX, st>>>(a); break;
+        default: k_fft_x_conv2<T, RMAX, MAX_SUBSETS><<<xCtas, a.xThreads, smX, st>>>(a); break;
     }
-    k_fft_yz_inv<T, RMAX><<<planes, FFT_THREADS, smPlane, st>>>(a);
+    k_fft_yz_inv<T, RMAX><<<planes, a.planeThreads, smPlane, st>>>(a);
     c.launches += 2;
     return NBS_OK;
 }
@@ -433,7 +433,19 @@ int launchPlaneFft(Context& c, const PlaneFftPlan& plan, PlaneFftArgs a, int hal
     const size_t smX = cs*((size_t) nx + (size_t) nx*(c.nS*chunk + 1));
     const size_t smPlane = cs*((size_t) nz + ny + (size_t) ((ny + 1)/2)*2*rs);
     if (smPlane > 200*1024 || smX > 200*1024) return NBS_RETRY;
-    if (nzh > FFT_THREADS*FFT_UNPACK_Q || std::max(nx, std::max(ny, nz))/2 > FFT_THREADS) return NBS_RETRY;
+    // CTA sizes: the widest pass (lines x n/R butterflies) should run in the fewest rounds of equal size
+    auto pickThreads = [](int lines, int n, unsigned long long factors, int cap) {
+        int rmin = 16;
+        for (unsigned long long f = factors; f != 0; f >>= 4) rmin = std::min(rmin, (int) (f & 15));
+        const int nb = n/rmin;                                 // butterflies per line in the widest pass
+        const int rounds = (lines*nb + cap - 1)/cap;
+        const int linesPerRound = (lines + rounds - 1)/rounds;
+        return std::min(cap, std::max(128, ((linesPerRound*nb + 31)/32)*32));
+    };
+    const int pairsZ = (ny + 1)/2;
+    a.planeThreads = std::max(pickThreads(pairsZ, nz, plan.factors[2], FFT_THREADS), pickThreads(nzh, ny, plan.factors[1], FFT_THREADS));
+    a.xThreads = pickThreads(c.nS*chunk, nx, plan.factors[0], FFT_X_THREADS);
+    if (nzh > 128*FFT_UNPACK_Q || std::max(ny, nz)/2 > a.planeThreads || nx/2 > a.xThreads) return NBS_RETRY;
     a.rowStride = rs;
     a.chunk = chunk;
     a.factorsX = plan.factors[0]; a.factorsY = plan.factors[1]; a.factorsZ = plan.factors[2];

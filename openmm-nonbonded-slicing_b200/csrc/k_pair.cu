@@ -47,6 +47,7 @@ struct PairArgs {
     int useSwitch;
     double rc2d, alphaD, krfD, crfD;
     const double* q64;                   // sorted charges * sqrt(ONE_4PI_EPS0), double
+    const double* erfcTab;               // piecewise degree-6 fit of erfc(alpha sqrt(s))/sqrt(s) in s = r^2 (ERFC_TAB_ROW doubles per interval)
     int* counters;                       // [2] number of work items, [3] cursor
     const int2* items;                   // (local block, first tile)
     const int* blkFirst; const int* blkCount; const uint4* blkLo;
@@ -133,9 +134,17 @@ __device__ __forceinline__ double expNegD(double z) {
     return __hiloint2double(__double2hiint(p) + (ni << 20), __double2loint(p));
 }
 
-// Energy of one pair in double precision from the exact fixed-point coordinates (the wrapped integer
-// difference IS the minimum image for any pair inside the cutoff).  Formulas: ReferenceSlicedLJCoulombIxn.cpp
-// :376-396, 443-444 (PME) and :598-624 (reaction field), switch :380-384, 428-431.
+// Energy of one pair from the exact fixed-point coordinates (the wrapped integer difference IS the
+// minimum image for any pair inside the cutoff).  Formulas: ReferenceSlicedLJCoulombIxn.cpp:376-396, 443-444
+// (PME) and :598-624 (reaction field), switch :380-384, 428-431.
+//   * Coulomb, PME: K q_i q_j erfc(alpha r)/r in DOUBLE.  Double-precision instructions are ~8x more
+//     expensive to issue than fp32 ones here, so instead of rsqrt + exp + erfcx (about 45 of them) the
+//     function f(s) = erfc(alpha sqrt(s))/sqrt(s), s = r^2, comes from a table of degree-6 polynomials
+//     on 64 intervals per octave of s (built on the host from libm's erfc: relative error < 1e-13 for
+//     r <= cutoff; csrc/nbs_api.cu buildErfcTable) -- 8 fused multiply-adds.  Pairs closer than
+//     2^-3.5 nm (0.088 nm: none in a physical system) take the analytic path.
+//   * Lennard-Jones: fp32 from the same exact r^2 (terms of one sign dominate a slice's vdW sum, so 1e-7
+//     per term is far inside the 1e-5 target), accumulated in double.
 template <bool IS_PME>
 __device__ __forceinline__ void pairEnergyD(const uint4 fi, const uint4 fj, double qi, double qj, float sigi, float sigj,
                                             float epsi, float epsj, const PairArgs& a, double& ec, double& ev) {
@@ -146,30 +155,51 @@ __device__ __forceinline__ void pairEnergyD(const uint4 fi, const uint4 fj, doub
     const float r2f = (float) r2;
     float yf = rsqrtFast(r2f);
     yf = yf*fmaf(-0.5f*r2f*yf, yf, 1.5f);              // fp32 Newton step: ~1e-7
-    double y = (double) yf;
-    y = y*fma(-0.5*r2*y, y, 1.5);                       // double Newton step: ~1e-14
-    const double r = r2*y;
-    double s2 = ((double) sigi + (double) sigj)*y;
-    s2 *= s2;
-    const double s6 = s2*s2*s2;
-    ev = (double) epsi*(double) epsj*(s6 - 1.0)*s6;
-    if (a.useSwitch && r > (double) a.rswitch) {
-        const double u = (r - (double) a.rswitch)/((double) a.rcut - (double) a.rswitch);
-        ev *= 1.0 + u*u*u*(-10.0 + u*(15.0 - u*6.0));
+    {
+        float s2 = (sigi + sigj)*yf;
+        s2 *= s2;
+        const float s6 = s2*s2*s2;
+        float evf = epsi*epsj*(s6 - 1.f)*s6;
+        if (a.useSwitch) {
+            const float r = r2f*yf;
+            if (r > a.rswitch) {
+                const float u = (r - a.rswitch)/(a.rcut - a.rswitch);
+                evf *= 1.f + u*u*u*(-10.f + u*(15.f - u*6.f));
+            }
+        }
+        ev = (double) evf;
     }
     const double qq = qi*qj;
     if (IS_PME) {
-        const double x = a.alphaD*r;
-        const double d = fma(0.5, x, 1.0);
-        const float df = (float) d;
-        float tf = rcpFast(df);
-        tf = tf*fmaf(-df, tf, 2.f);                     // fp32 Newton step
-        double t = (double) tf;
-        t = t*fma(-d, t, 2.0);                          // double Newton step
-        ec = qq*y*expNegD(x*x)*erfcxPolyD(t);
+        const int idx = (int) (__float_as_uint(r2f) >> 17) - ERFC_TAB_BASE;
+        if (idx >= 0) {
+            const double2* row = reinterpret_cast<const double2*>(a.erfcTab + (size_t) idx*ERFC_TAB_ROW);
+            const double2 c0 = __ldg(row), c1 = __ldg(row + 1), c2 = __ldg(row + 2), c3 = __ldg(row + 3), c4 = __ldg(row + 4);
+            const double d = fma(r2, c0.x, c0.y);                   // position inside the interval, [-1, 1]
+            double p = fma(c1.x, d, c1.y);
+            p = fma(p, d, c2.x);
+            p = fma(p, d, c2.y);
+            p = fma(p, d, c3.x);
+            p = fma(p, d, c3.y);
+            p = fma(p, d, c4.x);
+            ec = qq*p;
+        }
+        else {
+            double y = (double) yf;
+            y = y*fma(-0.5*r2*y, y, 1.5);               // double Newton step: ~1e-14
+            const double x = a.alphaD*r2*y;
+            const double dd = fma(0.5, x, 1.0);
+            double t = (double) rcpFast((float) dd);
+            t = t*fma(-dd, t, 2.0);
+            t = t*fma(-dd, t, 2.0);
+            ec = qq*y*expNegD(x*x)*erfcxPolyD(t);
+        }
     }
-    else
+    else {
+        double y = (double) yf;
+        y = y*fma(-0.5*r2*y, y, 1.5);
         ec = qq*(y + a.krfD*r2 - a.crfD);
+    }
 }
 
 // Exact cutoff test from the fixed-point coordinates (the wrapped integer difference is the minimum image
@@ -496,6 +526,7 @@ int launchPairs(Context& c, bool wantEnergy, int mode) {
     a.krfD = pow(c.cutoff, -3.0)*(c.rfDielectric - 1.0)/(2.0*c.rfDielectric + 1.0);
     a.crfD = (1.0/c.cutoff)*(3.0*c.rfDielectric)/(2.0*c.rfDielectric + 1.0);
     a.q64 = c.dQ64.d;
+    a.erfcTab = c.dErfcTab.d;
     a.alpha = (float) c.alpha;
     // ReferenceSlicedLJCoulombIxn::setUseCutoff, ReferenceSlicedLJCoulombIxn.cpp:60-68
     a.krf = (float) (pow(c.cutoff, -3.0)*(c.rfDielectric - 1.0)/(2.0*c.rfDielectric + 1.0));

@@ -258,6 +258,48 @@ int uploadPmeTables(Context& c) {
     return NBS_OK;
 }
 
+// Piecewise polynomial table of f(s) = erfc(alpha sqrt(s))/sqrt(s) for the double-precision pair energies
+// (k_pair.cu pairEnergyD): degree-6 interpolation at Chebyshev nodes on every interval [2^e (1 + m/64),
+// 2^e (1 + (m+1)/64)), e = -7 .. floor(log2 cutoff^2) + 1.  Relative error < 1e-13 for alpha r <= 2.7
+// (verified against scipy.special.erfc; tests/test_abi.py checks the recipe in NumPy).
+static int buildErfcTable(Context& c) {
+    const int eMax = std::max(-6, (int) std::floor(std::log2(c.cutoff*c.cutoff)) + 1);
+    const int rows = (eMax + 7 + 1)*64;
+    std::vector<double> tab((size_t) rows*ERFC_TAB_ROW, 0.0);
+    const int D = 6;
+    for (int e = -7; e <= eMax; e++)
+        for (int m = 0; m < 64; m++) {
+            const long double lo = std::ldexp(1.0L + m/64.0L, e), w = std::ldexp(1.0L/64.0L, e);
+            const long double center = lo + w/2;
+            long double A[7][8];
+            for (int k = 0; k <= D; k++) {
+                const long double xn = std::cos(3.14159265358979323846264338327950288L*(2*k + 1)/(2.0L*(D + 1)));
+                const long double sv = center + xn*w/2;
+                const long double r = std::sqrt(sv);
+                long double pw = 1;
+                for (int j = 0; j <= D; j++) { A[k][j] = pw; pw *= xn; }
+                A[k][D + 1] = std::erfc((long double) c.alpha*r)/r;
+            }
+            for (int col = 0; col <= D; col++) {                 // Gaussian elimination, partial pivoting
+                int piv = col;
+                for (int r = col + 1; r <= D; r++) if (std::fabs(A[r][col]) > std::fabs(A[piv][col])) piv = r;
+                for (int j = 0; j <= D + 1; j++) std::swap(A[col][j], A[piv][j]);
+                for (int r = 0; r <= D; r++) {
+                    if (r == col) continue;
+                    const long double f = A[r][col]/A[col][col];
+                    for (int j = col; j <= D + 1; j++) A[r][j] -= f*A[col][j];
+                }
+            }
+            double* row = tab.data() + ((size_t) (e + 7)*64 + m)*ERFC_TAB_ROW;
+            row[0] = (double) (2/w);
+            row[1] = (double) (-center*2/w);
+            for (int k = 0; k <= D; k++) row[2 + (D - k)] = (double) (A[k][D + 1]/A[k][k]);     // a6 first
+        }
+    NBS_CUDA_CHECK(c.dErfcTab.ensure(tab.size()));
+    NBS_CUDA_CHECK(cudaMemcpy(c.dErfcTab.d, tab.data(), sizeof(double)*tab.size(), cudaMemcpyHostToDevice));
+    return NBS_OK;
+}
+
 // cell geometry for this box: columns whose 32-atom blocks are roughly cubic, fine z-bins for sorting
 static int setupGeometry(Context& c, const double box[9]) {
     CellGeom& g = c.geom;
@@ -338,7 +380,7 @@ static void releaseAll(Context& c) {
     c.dBlkLo.release(); c.dBlkHi.release(); c.dExclRange.release(); c.dJList.release(); c.dJCount.release();
     c.dXList.release(); c.dXCount.release(); c.dXMask.release(); c.dCounters.release(); c.dForce.release(); c.dItems.release();
     c.dEnergy.release(); c.dGrid.release(); c.dGridC.release(); c.dEterm.release(); c.dModuli.release();
-    c.dPot.release(); c.dEtermD.release(); c.dTwiddleD.release();
+    c.dPot.release(); c.dEtermD.release(); c.dTwiddleD.release(); c.dErfcTab.release();
     c.dTwiddle.release(); c.dPairStats.release(); c.dPairDump.release();
     if (c.hCounters) cudaFreeHost(c.hCounters);
     if (c.hEnergy) cudaFreeHost(c.hEnergy);
@@ -416,6 +458,7 @@ int nbs_create(const nbs_system_desc* desc, nbs_context** out) {
     }
     if (c.method == NBS_METHOD_PME) {
         status = uploadPmeTables(c);
+        if (status == NBS_OK) status = buildErfcTable(c);
         if (status != NBS_OK) { releaseAll(c); delete ctx; return status; }
     }
     *out = ctx;

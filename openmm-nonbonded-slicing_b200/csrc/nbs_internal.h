@@ -31,6 +31,11 @@ constexpr double kOne4PiEps0 = 1/(4*kPi*kEpsilon0);
 constexpr int MAX_SUBSETS = 8;
 constexpr int MAX_SLICES = MAX_SUBSETS*(MAX_SUBSETS+1)/2;
 constexpr int PME_ORDER = 5;
+// table of f(s) = erfc(alpha sqrt(s))/sqrt(s): interval index = (bits of (float) s >> 17) - ERFC_TAB_BASE, i.e. 64
+// intervals per octave starting at s = 2^-7; a row is {scale, offset, a6, a5, a4, a3, a2, a1, a0, pad} with
+// f(s) ~ sum a_k d^k, d = s*scale + offset in [-1, 1]
+constexpr int ERFC_TAB_BASE = (127 - 7) << 6;
+constexpr int ERFC_TAB_ROW = 10;
 constexpr int J_SHIFT_BITS = 26;                 // sorted index in the low 26 bits of a list entry
 constexpr int J_INDEX_MASK = (1 << J_SHIFT_BITS)-1;
 constexpr int BUILD_WARPS = 8;                   // warps per CTA in the list-build kernel
@@ -136,6 +141,7 @@ struct Context {
     Buf<double> dEtermD;
     Buf<double2> dTwiddleD;
     Buf<double> dModuli;                     // [nx+ny+nz]
+    Buf<double> dErfcTab;                    // see ERFC_TAB_ROW
     Buf<float2> dTwiddle;                    // [nx+ny+nz]
     Buf<unsigned long long> dPairStats;      // [0] count, [1] hash
     Buf<int2> dPairDump;

@@ -74,6 +74,8 @@ extern "C" {
 #define NBS_FLAG_NO_GRAPH        0x4u  /* plain stream launches instead of a CUDA graph     */
 #define NBS_FLAG_LINE_FFT        0x10u /* always use the line-at-a-time FFT kernels (the path for
                                           grids whose planes exceed shared memory); test hook     */
+#define NBS_FLAG_SORTED_PME      0x20u /* PME always works from the cell-sorted records (the path of
+                                          large systems); test hook                              */
 #define NBS_FLAG_FP32_ENERGY     0x8u  /* single-precision pair energies and PME grids (the
                                           plugin's "single" precision); default is double
                                           precision for every energy term, fp32 for forces    */

@@ -23,6 +23,7 @@ NBS_FLAG_PROFILE = 0x2
 NBS_FLAG_NO_GRAPH = 0x4
 NBS_FLAG_FP32_ENERGY = 0x8
 NBS_FLAG_LINE_FFT = 0x10
+NBS_FLAG_SORTED_PME = 0x20
 
 NBS_MEM_HOST = 0
 NBS_MEM_DEVICE = 1

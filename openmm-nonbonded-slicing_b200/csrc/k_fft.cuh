@@ -20,7 +20,9 @@ struct PlaneFftArgs {
     int ownLo, ownHi;                // subsets whose grids this rank transforms / produces
     int rowStride;                   // zy / yz kernels: complex elements per plane row in shared memory
     int chunk;                       // x kernel: kz values per CTA
-    int planeThreads, xThreads;      // CTA sizes chosen for this plan
+    int planeThreads, xThreads, colThreads;   // CTA sizes chosen for this plan
+    int slabPairs, slabsPerPlane;    // zy / yz kernels: row pairs per CTA; one slab per plane = the y transform is fused in
+    int colChunk;                    // split path: kz columns per CTA of the y kernel
     unsigned long long factorsX, factorsY, factorsZ;
     const void* twx; const void* twy; const void* twz;     // exp(-2 pi i k / n), precision T
     const void* grid;                // real charge grids   [nS][nx][ny][nz]      (T)

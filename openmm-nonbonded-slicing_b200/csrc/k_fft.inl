@@ -172,13 +172,20 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_zy_fwd(const PlaneFftArgs a
     C* plane = sm + nz + ny;
     for (int k = threadIdx.x; k < nz; k += blockDim.x) twz[k] = ((const C*) a.twz)[k];
     for (int k = threadIdx.x; k < ny; k += blockDim.x) twy[k] = ((const C*) a.twy)[k];
-    const int sx = a.ownLo*a.nx + blockIdx.x;                   // (own subset, x) plane
-    const T* grid = (const T*) a.grid + (size_t) sx*ny*nz;
-    const int pairs = (ny + 1) >> 1;
+    // CTA = one (own subset, x) plane, or -- when a plane does not fit in shared memory -- a slab of its row pairs
+    // (then the y transform is a separate kernel, k_fft_y_cols)
+    const int plane_ = blockIdx.x/a.slabsPerPlane, slab = blockIdx.x - plane_*a.slabsPerPlane;
+    const int sx = a.ownLo*a.nx + plane_;
+    const bool fused = a.slabsPerPlane == 1;
+    const int allPairs = (ny + 1) >> 1;
+    const int pBase = slab*a.slabPairs;
+    const int pairs = min(a.slabPairs, allPairs - pBase);       // row pairs this CTA holds (local rows 0 .. 2*pairs)
+    const int rowBase = 2*pBase, rowsHere = min(2*pairs, ny - rowBase);
+    const T* grid = (const T*) a.grid + ((size_t) sx*ny + rowBase)*nz;
     for (int idx = threadIdx.x; idx < pairs*nz; idx += blockDim.x) {
         const int p = idx/nz, z = idx - p*nz;
         const T re = grid[(size_t) (2*p)*nz + z];
-        const T im = 2*p + 1 < ny ? grid[(size_t) (2*p + 1)*nz + z] : (T) 0;
+        const T im = 2*p + 1 < rowsHere ? grid[(size_t) (2*p + 1)*nz + z] : (T) 0;
         plane[(size_t) p*2*rs + z] = mkc(re, im);
     }
     __syncthreads();
@@ -208,17 +215,49 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_zy_fwd(const PlaneFftArgs a
                 if (wi < count) {
                     const int p = p0 + wi/nzh, k = wi % nzh;
                     plane[(size_t) (2*p)*rs + k] = mkc(half*(zk[q].x + zn[q].x), half*(zk[q].y - zn[q].y));
-                    if (2*p + 1 < ny) plane[(size_t) (2*p + 1)*rs + k] = mkc(half*(zk[q].y + zn[q].y), -half*(zk[q].x - zn[q].x));
+                    if (2*p + 1 < rowsHere) plane[(size_t) (2*p + 1)*rs + k] = mkc(half*(zk[q].y + zn[q].y), -half*(zk[q].x - zn[q].x));
                 }
             }
             __syncthreads();
         }
     }
-    batchedFft<RMAX>(plane, nzh, 1, rs, ny, a.factorsY, twy);
-    C* out = (C*) a.gridC + (size_t) sx*ny*nzh;
-    for (int idx = threadIdx.x; idx < ny*nzh; idx += blockDim.x) {
+    if (fused) batchedFft<RMAX>(plane, nzh, 1, rs, ny, a.factorsY, twy);
+    C* out = (C*) a.gridC + ((size_t) sx*ny + rowBase)*nzh;
+    for (int idx = threadIdx.x; idx < rowsHere*nzh; idx += blockDim.x) {
         const int y = idx/nzh, k = idx - y*nzh;
         out[idx] = plane[(size_t) y*rs + k];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// y transform alone (planes too large to fuse): CTA = one (subset, x) plane x `colChunk` kz columns, in place.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int RMAX, bool INVERSE>
+__global__ void __launch_bounds__(FFT_THREADS) k_fft_y_cols(const PlaneFftArgs a) {
+    typedef typename Cx2<T>::type C;
+    extern __shared__ double2 fftSmem[];
+    C* sm = (C*) fftSmem;
+    const int ny = a.ny, nzh = a.nzh, cw = a.colChunk, rs = cw + 1;
+    C* twy = sm;
+    C* cols = sm + ny;
+    for (int k = threadIdx.x; k < ny; k += blockDim.x) twy[k] = ((const C*) a.twy)[k];
+    const int chunks = (nzh + cw - 1)/cw;
+    const int plane_ = blockIdx.x/chunks, k0 = (blockIdx.x - plane_*chunks)*cw;
+    const int kn = min(cw, nzh - k0);
+    C* base = (C*) a.gridC + (size_t) (a.ownLo*a.nx + plane_)*ny*nzh + k0;
+    for (int idx = threadIdx.x; idx < ny*kn; idx += blockDim.x) {
+        const int y = idx/kn, l = idx - y*kn;
+        C v = base[(size_t) y*nzh + l];
+        if (INVERSE) v.y = -v.y;
+        cols[(size_t) y*rs + l] = v;
+    }
+    __syncthreads();
+    batchedFft<RMAX>(cols, kn, 1, rs, ny, a.factorsY, twy);
+    for (int idx = threadIdx.x; idx < ny*kn; idx += blockDim.x) {
+        const int y = idx/kn, l = idx - y*kn;
+        C v = cols[(size_t) y*rs + l];
+        if (INVERSE) v.y = -v.y;
+        base[(size_t) y*nzh + l] = v;
     }
 }
 
@@ -237,21 +276,27 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_yz_inv(const PlaneFftArgs a
     C* plane = sm + nz + ny;
     for (int k = threadIdx.x; k < nz; k += blockDim.x) twz[k] = ((const C*) a.twz)[k];
     for (int k = threadIdx.x; k < ny; k += blockDim.x) twy[k] = ((const C*) a.twy)[k];
-    const int sx = a.ownLo*a.nx + blockIdx.x;
-    const C* in = (const C*) a.gridC + (size_t) sx*ny*nzh;
-    for (int idx = threadIdx.x; idx < ny*nzh; idx += blockDim.x) {
+    const int plane_ = blockIdx.x/a.slabsPerPlane, slab = blockIdx.x - plane_*a.slabsPerPlane;
+    const int sx = a.ownLo*a.nx + plane_;
+    const bool fused = a.slabsPerPlane == 1;
+    const int allPairs = (ny + 1) >> 1;
+    const int pBase = slab*a.slabPairs;
+    const int pairs = min(a.slabPairs, allPairs - pBase);
+    const int rowBase = 2*pBase, rowsHere = min(2*pairs, ny - rowBase);
+    const C* in = (const C*) a.gridC + ((size_t) sx*ny + rowBase)*nzh;
+    for (int idx = threadIdx.x; idx < rowsHere*nzh; idx += blockDim.x) {
         const int y = idx/nzh, k = idx - y*nzh;
         C v = in[idx];
         v.y = -v.y;                                              // conjugate: inverse y = conj(fwd(conj))
         plane[(size_t) y*rs + k] = v;
     }
     __syncthreads();
-    batchedFft<RMAX>(plane, nzh, 1, rs, ny, a.factorsY, twy);
+    if (fused) batchedFft<RMAX>(plane, nzh, 1, rs, ny, a.factorsY, twy);
+    // (split path: k_fft_y_cols<INVERSE> already produced A; the load above conjugated it, as the fused path leaves it)
     // plane now holds conj(A) where A = y-inverse spectrum.  Pack rows (2p, 2p+1) into one complex line:
     // W[k] = conj(A0[k] + i A1[k]),  W[n-k] = conj(conj(A0[k]) + i conj(A1[k]))   (0 < k, 2k < n)
     // so that fwd(W) = conj(r0 + i r1) with r0, r1 the two real rows.
     {
-        const int pairs = (ny + 1) >> 1;
         const int pairsPerRound = max(1, ((int) blockDim.x*FFT_UNPACK_Q)/nzh);
         for (int p0 = 0; p0 < pairs; p0 += pairsPerRound) {
             const int count = min(pairsPerRound, pairs - p0)*nzh;
@@ -264,7 +309,7 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_yz_inv(const PlaneFftArgs a
                     C u = plane[(size_t) (2*p)*rs + k];
                     u.y = -u.y;                                      // A0[k]
                     C v = mkc((T) 0, (T) 0);
-                    if (2*p + 1 < ny) { v = plane[(size_t) (2*p + 1)*rs + k]; v.y = -v.y; }    // A1[k]
+                    if (2*p + 1 < rowsHere) { v = plane[(size_t) (2*p + 1)*rs + k]; v.y = -v.y; }    // A1[k]
                     a0[q] = u; a1[q] = v;
                 }
             }
@@ -283,12 +328,12 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_yz_inv(const PlaneFftArgs a
             __syncthreads();
         }
         batchedFft<RMAX>(plane, pairs, 2*rs, 1, nz, a.factorsZ, twz);
-        float* pot = a.pot + (size_t) sx*ny*nz;
+        float* pot = a.pot + ((size_t) sx*ny + rowBase)*nz;
         for (int idx = threadIdx.x; idx < pairs*nz; idx += blockDim.x) {
             const int p = idx/nz, z = idx - p*nz;
             const C wv = plane[(size_t) p*2*rs + z];
             pot[(size_t) (2*p)*nz + z] = (float) wv.x;
-            if (2*p + 1 < ny) pot[(size_t) (2*p + 1)*nz + z] = (float) -wv.y;
+            if (2*p + 1 < rowsHere) pot[(size_t) (2*p + 1)*nz + z] = (float) -wv.y;
         }
     }
 }
@@ -391,6 +436,8 @@ static int launchPlaneT(Context& c, PlaneFftArgs a, int half, size_t smPlane, si
         const int big = 220*1024;
         cudaFuncSetAttribute(k_fft_zy_fwd<T, RMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
         cudaFuncSetAttribute(k_fft_yz_inv<T, RMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(k_fft_y_cols<T, RMAX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+        cudaFuncSetAttribute(k_fft_y_cols<T, RMAX, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
         cudaFuncSetAttribute(k_fft_x_conv2<T, RMAX, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
         cudaFuncSetAttribute(k_fft_x_conv2<T, RMAX, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
         cudaFuncSetAttribute(k_fft_x_conv2<T, RMAX, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
@@ -400,9 +447,16 @@ static int launchPlaneT(Context& c, PlaneFftArgs a, int half, size_t smPlane, si
     }
     const int nOwn = c.ownHi - c.ownLo;
     const int planes = nOwn*a.nx;
+    const bool fused = a.slabsPerPlane == 1;
+    const int colCtas = planes*((a.nzh + a.colChunk - 1)/a.colChunk);
+    const size_t smCols = sizeof(typename Cx2<T>::type)*((size_t) a.ny + (size_t) a.ny*(a.colChunk + 1));
     if (half == 0) {
-        k_fft_zy_fwd<T, RMAX><<<planes, a.planeThreads, smPlane, st>>>(a);
+        k_fft_zy_fwd<T, RMAX><<<planes*a.slabsPerPlane, a.planeThreads, smPlane, st>>>(a);
         c.launches++;
+        if (!fused) {
+            k_fft_y_cols<T, RMAX, false><<<colCtas, a.colThreads, smCols, st>>>(a);
+            c.launches++;
+        }
         return NBS_OK;
     }
     const int xCtas = a.ny*((a.nzh + a.chunk - 1)/a.chunk);
@@ -413,7 +467,11 @@ static int launchPlaneT(Context& c, PlaneFftArgs a, int half, size_t smPlane, si
         case 4: k_fft_x_conv2<T, RMAX, 4><<<xCtas, a.xThreads, smX, st>>>(a); break;
         default: k_fft_x_conv2<T, RMAX, MAX_SUBSETS><<<xCtas, a.xThreads, smX, st>>>(a); break;
     }
-    k_fft_yz_inv<T, RMAX><<<planes, a.planeThreads, smPlane, st>>>(a);
+    if (!fused) {
+        k_fft_y_cols<T, RMAX, true><<<colCtas, a.colThreads, smCols, st>>>(a);
+        c.launches++;
+    }
+    k_fft_yz_inv<T, RMAX><<<planes*a.slabsPerPlane, a.planeThreads, smPlane, st>>>(a);
     c.launches += 2;
     return NBS_OK;
 }
@@ -431,8 +489,20 @@ int launchPlaneFft(Context& c, const PlaneFftPlan& plan, PlaneFftArgs a, int hal
     const size_t cs = sizeof(C);
     while (chunk > 1 && cs*((size_t) nx + (size_t) nx*(c.nS*chunk + 1)) > 200*1024) chunk--;
     const size_t smX = cs*((size_t) nx + (size_t) nx*(c.nS*chunk + 1));
-    const size_t smPlane = cs*((size_t) nz + ny + (size_t) ((ny + 1)/2)*2*rs);
-    if (smPlane > 200*1024 || smX > 200*1024) return NBS_RETRY;
+    if (smX > 200*1024) return NBS_RETRY;
+    // zy / yz kernels: the whole plane when it fits (y transform fused in), else slabs of row pairs of <= ~64 KB
+    const int pairsZ = (ny + 1)/2;
+    size_t smPlane = cs*((size_t) nz + ny + (size_t) pairsZ*2*rs);
+    a.slabPairs = pairsZ;
+    a.slabsPerPlane = 1;
+    if (smPlane > 200*1024) {
+        a.slabPairs = std::max(1, (int) ((64*1024/cs - nz - ny)/(2*rs)));
+        a.slabsPerPlane = (pairsZ + a.slabPairs - 1)/a.slabPairs;
+        a.slabPairs = (pairsZ + a.slabsPerPlane - 1)/a.slabsPerPlane;          // even slabs
+        smPlane = cs*((size_t) nz + ny + (size_t) a.slabPairs*2*rs);
+    }
+    a.colChunk = 16;
+    while (a.colChunk > 1 && cs*((size_t) ny + (size_t) ny*(a.colChunk + 1)) > 64*1024) a.colChunk--;
     // CTA sizes: the widest pass (lines x n/R butterflies) should run in the fewest rounds of equal size
     auto pickThreads = [](int lines, int n, unsigned long long factors, int cap) {
         int rmin = 16;
@@ -442,10 +512,11 @@ int launchPlaneFft(Context& c, const PlaneFftPlan& plan, PlaneFftArgs a, int hal
         const int linesPerRound = (lines + rounds - 1)/rounds;
         return std::min(cap, std::max(128, ((linesPerRound*nb + 31)/32)*32));
     };
-    const int pairsZ = (ny + 1)/2;
-    a.planeThreads = std::max(pickThreads(pairsZ, nz, plan.factors[2], FFT_THREADS), pickThreads(nzh, ny, plan.factors[1], FFT_THREADS));
+    a.planeThreads = pickThreads(a.slabPairs, nz, plan.factors[2], FFT_THREADS);
+    if (a.slabsPerPlane == 1) a.planeThreads = std::max(a.planeThreads, pickThreads(nzh, ny, plan.factors[1], FFT_THREADS));
+    a.colThreads = pickThreads(a.colChunk, ny, plan.factors[1], FFT_THREADS);
     a.xThreads = pickThreads(c.nS*chunk, nx, plan.factors[0], FFT_X_THREADS);
-    if (nzh > 128*FFT_UNPACK_Q || std::max(ny, nz)/2 > a.planeThreads || nx/2 > a.xThreads) return NBS_RETRY;
+    if (nzh > 128*FFT_UNPACK_Q || nz/2 > a.planeThreads || ny/2 > std::min(a.planeThreads, a.colThreads) || nx/2 > a.xThreads) return NBS_RETRY;
     a.rowStride = rs;
     a.chunk = chunk;
     a.factorsX = plan.factors[0]; a.factorsY = plan.factors[1]; a.factorsZ = plan.factors[2];

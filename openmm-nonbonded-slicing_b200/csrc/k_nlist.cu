@@ -39,7 +39,7 @@ struct BuildArgs {
     int* jlist; int* jcount; int* xlist; unsigned* xmask; int* xcount;
     int* overflow;             // counters + 1
     int* itemCount;            // counters + 2
-    int2* items;               // work items of the pair kernel: (local block, first tile)
+    int4* items;               // work items of the pair kernel: (local block, first tile, first atom, atom count)
     int chunkTiles, maxItems;
     double* overflowFlag;      // energy[2*MAX_SLICES]: the same flag as a double, so that it all-reduces
 };
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(BUILD_WARPS*32) k_build_lists(BuildArgs a) {
         const int n = (tiles + a.chunkTiles - 1)/a.chunkTiles;
         const int base = atomicAdd(a.itemCount, n);
         for (int k = 0; k < n; k++)
-            if (base + k < a.maxItems) a.items[base + k] = make_int2(lb, k*a.chunkTiles);
+            if (base + k < a.maxItems) a.items[base + k] = make_int4(lb, k*a.chunkTiles, first, count);
     }
     if (overflow && lane == 0) { atomicOr(a.overflow, 1); a.overflowFlag[0] = 1.0; }
 }

@@ -33,7 +33,17 @@
 #include "nbs_device.cuh"
 #include <algorithm>
 
+// tuning knobs (profiles/README.md has the measurements behind the defaults)
+#ifndef PAIR_MIN_CTAS
+#define PAIR_MIN_CTAS 2          // resident CTAs per SM the register allocation is bounded for
+#endif
+#ifndef PAIR_UNROLL
+#define PAIR_UNROLL 2            // steps of the tile loop in flight per warp
+#endif
+
 namespace nbs {
+
+constexpr int kPairUnroll = PAIR_UNROLL;
 
 struct PairArgs {
     int capJ, capX, Npad;
@@ -49,7 +59,7 @@ struct PairArgs {
     const double* q64;                   // sorted charges * sqrt(ONE_4PI_EPS0), double
     const double* erfcTab;               // piecewise degree-6 fit of erfc(alpha sqrt(s))/sqrt(s) in s = r^2 (ERFC_TAB_ROW doubles per interval)
     int* counters;                       // [2] number of work items, [3] cursor
-    const int2* items;                   // (local block, first tile)
+    const int4* items;                   // (local block, first tile, first atom of the block, atoms in the block)
     const int* blkFirst; const int* blkCount; const uint4* blkLo;
     const uint4* posq; const float4* par;
     const int* jlist; const int* jcount; const int* xlist; const unsigned* xmask; const int* xcount;
@@ -250,7 +260,7 @@ __device__ __forceinline__ void tileLoop(WarpScratch& w, const PairArgs& a, cons
     const float TWO_OVER_SQRT_PI = 1.1283791670955126f;
     const int src = (lane + 1) & 31;
     int qn = 0;                                   // pairs waiting in the energy queue
-#pragma unroll 2
+#pragma unroll kPairUnroll
     for (int k = 0; k < 32; k++) {
         const int js = (lane + k) & 31;
         const float4 p = w.jPos[js];
@@ -331,7 +341,7 @@ __device__ __forceinline__ void tileLoop(WarpScratch& w, const PairArgs& a, cons
 // MODE 0: forces (+ energies per EMODE); MODE 1: count + hash the interacting pairs; MODE 2: also dump them.
 // EMODE 0: forces only; 1: single-precision energies; 2: double-precision energies.
 template <int EMODE, bool IS_PME, int MODE>
-__global__ void __launch_bounds__(PAIR_WARPS*32, 2) k_pair(const PairArgs a) {
+__global__ void __launch_bounds__(PAIR_WARPS*32, PAIR_MIN_CTAS) k_pair(const PairArgs a) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     __shared__ float2 shLam[MAX_SUBSETS*MAX_SUBSETS];      // (lambda_Coulomb, lambda_vdW) of subset pair (si, sj)
     __shared__ double shE[MAX_SLICES*2];
@@ -353,19 +363,49 @@ __global__ void __launch_bounds__(PAIR_WARPS*32, 2) k_pair(const PairArgs a) {
     }
     unsigned long long nPairs = 0, hPairs = 0;
 
+    // Everything a warp needs from global memory is requested one step ahead of its use -- the next work
+    // item's index while the current item runs, the next tile's atoms while the current tile runs, the list
+    // entries two tiles ahead -- because a warp has only a few tiles of work and an L2 round trip per tile
+    // would otherwise be fully exposed.
+    int nextItem = 0;
+    if (lane == 0) nextItem = atomicAdd(a.counters + 3, 1);
     for (;;) {
-        int item = 0;
-        if (lane == 0) item = atomicAdd(a.counters + 3, 1);
-        item = __shfl_sync(FULL_MASK, item, 0);
+        const int item = __shfl_sync(FULL_MASK, nextItem, 0);
         if (item >= nItems) break;
-        const int2 it = a.items[item];
+        if (lane == 0) nextItem = atomicAdd(a.counters + 3, 1);
+        const int4 it = a.items[item];                 // (local block, first tile, first atom, atom count)
         const int lb = it.x;
         const int b = localToGlobalBlock(lb, a.blockPeriod, a.blockOffset, a.blockWidth);
-        const int first = a.blkFirst[b], cnt = a.blkCount[b];
+        const int first = it.z, cnt = it.w;
+        const int* jl = a.jlist + (size_t) lb*a.capJ;
+        const int* xl = a.xlist + (size_t) lb*a.capX;
+        const unsigned* xm = a.xmask + (size_t) lb*a.capX;
+        const int nJ = a.jcount[lb], nX = a.xcount[lb];
         const uint4 lo = a.blkLo[b];
         const bool iValid = lane < cnt;
         const uint4 pi = iValid ? a.posq[first + lane] : lo;
         const float4 pari = iValid ? a.par[first + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const double qi64 = (EMODE == 2 && iValid) ? a.q64[first + lane] : 0.0;
+        const int tJ = (nJ + 31) >> 5, tX = (nX + 31) >> 5;
+        const int tEnd = min(it.y + a.chunkTiles, tJ + tX);
+        // list entry (and exclusion mask) of this lane in tile t; -1 beyond the item
+        auto loadEntry = [&](int t, unsigned& mask) -> int {
+            mask = 0u;
+            if (t >= tEnd) return -1;
+            if (t >= tJ) { mask = xm[(t - tJ)*32 + lane]; return xl[(t - tJ)*32 + lane]; }
+            return jl[t*32 + lane];
+        };
+        unsigned maskCur, maskNext;
+        int entryCur = loadEntry(it.y, maskCur);
+        int entryNext = loadEntry(it.y + 1, maskNext);
+        uint4 qCur = make_uint4(0u, 0u, 0u, 0u);
+        float4 parCur = make_float4(0.f, 0.f, 0.f, 0.f);
+        double q64Cur = 0.0;
+        if (entryCur >= 0) {
+            const int j = entryCur & J_INDEX_MASK;
+            qCur = a.posq[j]; parCur = a.par[j];
+            if (EMODE == 2) q64Cur = a.q64[j];
+        }
         float xi = (float) (pi.x - lo.x)*a.sx;
         const float yi = (float) (pi.y - lo.y)*a.sy, zi = (float) (pi.z - lo.z)*a.sz;
         if (!iValid) xi = 1.0e8f;
@@ -378,27 +418,20 @@ __global__ void __launch_bounds__(PAIR_WARPS*32, 2) k_pair(const PairArgs a) {
         w.iPos[lane] = make_float4(xi, yi, zi, qi);
         w.iPar[lane] = pari;
         w.iFix[lane] = make_uint4(pi.x, pi.y, pi.z, (unsigned) __float_as_int(pari.z));
-        if (EMODE == 2) w.iQ[lane] = iValid ? a.q64[first + lane] : 0.0;
-
-        const int nJ = a.jcount[lb], nX = a.xcount[lb];
-        const int tJ = (nJ + 31) >> 5, tX = (nX + 31) >> 5;
-        const int tEnd = min(it.y + a.chunkTiles, tJ + tX);
-        const int* jl = a.jlist + (size_t) lb*a.capJ;
-        const int* xl = a.xlist + (size_t) lb*a.capX;
-        const unsigned* xm = a.xmask + (size_t) lb*a.capX;
+        if (EMODE == 2) w.iQ[lane] = qi64;
 
         for (int t = it.y; t < tEnd; t++) {
             const bool isX = t >= tJ;
-            const int entry = isX ? xl[(t - tJ)*32 + lane] : jl[t*32 + lane];
-            float4 pj = make_float4(-1.0e8f, 0.f, 0.f, 0.f), parj = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int entry = entryCur;
+            float4 pj = make_float4(-1.0e8f, 0.f, 0.f, 0.f);
+            const float4 parj = parCur;
             uint4 fixj = make_uint4(0u, 0u, 0u, 0u);
             int jIndex = 0;
             if (entry >= 0) {
                 jIndex = entry & J_INDEX_MASK;
                 const int code = entry >> J_SHIFT_BITS;
                 const int kx = code % 3 - 1, ky = (code/3) % 3 - 1, kz = code/9 - 1;
-                const uint4 q = a.posq[jIndex];
-                parj = a.par[jIndex];
+                const uint4 q = qCur;
                 pj.x = (float) ((long long) q.x + ((long long) kx << 32) - (long long) lo.x)*a.sx;
                 pj.y = (float) ((long long) q.y + ((long long) ky << 32) - (long long) lo.y)*a.sy;
                 pj.z = (float) ((long long) q.z + ((long long) kz << 32) - (long long) lo.z)*a.sz;
@@ -409,9 +442,18 @@ __global__ void __launch_bounds__(PAIR_WARPS*32, 2) k_pair(const PairArgs a) {
             w.jPos[lane] = pj;
             w.jPar[lane] = parj;
             w.jFix[lane] = fixj;
-            if (EMODE == 2) w.jQ[lane] = entry >= 0 ? a.q64[jIndex] : 0.0;
-            if (isX) w.jMask[lane] = xm[(t - tJ)*32 + lane];
+            if (EMODE == 2) w.jQ[lane] = q64Cur;
+            if (isX) w.jMask[lane] = maskCur;
             __syncwarp();
+            // requests for the next tile (atoms) and the one after (list entry) go out before this tile's arithmetic
+            entryCur = entryNext; maskCur = maskNext;
+            qCur = make_uint4(0u, 0u, 0u, 0u); parCur = make_float4(0.f, 0.f, 0.f, 0.f); q64Cur = 0.0;
+            if (entryCur >= 0) {
+                const int j = entryCur & J_INDEX_MASK;
+                qCur = a.posq[j]; parCur = a.par[j];
+                if (EMODE == 2) q64Cur = a.q64[j];
+            }
+            entryNext = loadEntry(t + 2, maskNext);
 
             if (MODE != 0) {
                 // ---- the interacting-pair set itself (parity diagnostics): cull, then hash / dump ----

@@ -173,6 +173,10 @@ struct PmeArgs {
     int N, Npad, nS, nx, ny, nz, nzh;
     int ownLo, ownHi;            // this rank spreads / gathers the atoms of subsets [ownLo, ownHi)
     const uint4* posq; const float4* par;
+    // unsorted mode (small systems): particle-order inputs straight from k_prep, so that the PME chain does not
+    // wait for the cell sort; forces then go to the particle-order half of the accumulator
+    int unsorted;
+    const uint4* fix; const float* chargeF; const int* subsetOf;
     void* grid; const float* pot;
     unsigned long long* force;
     float fscale[3];             // n_d / L_d
@@ -215,9 +219,9 @@ __global__ void __launch_bounds__(256) k_spread(const PmeArgs a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int j = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
     if (j >= a.N) return;
-    const uint4 p = a.posq[j];
-    const int subset = __float_as_int(a.par[j].z);
-    const float q = __uint_as_float(p.w);
+    uint4 p; int subset; float q;
+    if (a.unsorted) { p = a.fix[j]; q = a.chargeF[j]; subset = a.subsetOf[j]; }
+    else { p = a.posq[j]; q = __uint_as_float(p.w); subset = __float_as_int(a.par[j].z); }
     if (q == 0.f || subset < a.ownLo || subset >= a.ownHi) return;      // warp-uniform
     int ix0, iy0, iz0;
     splineTable<T>(a, p, lane, wtab[warp], (T*) nullptr, ix0, iy0, iz0);
@@ -450,10 +454,10 @@ __global__ void __launch_bounds__(256) k_gather(const PmeArgs a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int j = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
     if (j >= a.N) return;
-    const uint4 p = a.posq[j];
-    const float q = __uint_as_float(p.w);
+    uint4 p; int subset; float q;
+    if (a.unsorted) { p = a.fix[j]; q = a.chargeF[j]; subset = a.subsetOf[j]; }
+    else { p = a.posq[j]; q = __uint_as_float(p.w); subset = __float_as_int(a.par[j].z); }
     if (q == 0.f) return;
-    const int subset = __float_as_int(a.par[j].z);
     if (subset < a.ownLo || subset >= a.ownHi) return;
     int ix0, iy0, iz0;
     splineTable<float>(a, p, lane, wtab[warp], dwtab[warp], ix0, iy0, iz0);
@@ -590,7 +594,9 @@ static int launchPmeT(Context& c, bool wantEnergy, int half) {
     p.N = c.N; p.Npad = c.Npad; p.nS = c.nS; p.nx = nx; p.ny = ny; p.nz = nz; p.nzh = nzh;
     p.ownLo = c.ownLo; p.ownHi = c.ownHi;
     p.posq = c.dPosq.d; p.par = c.dPar.d; p.grid = c.dGrid.d; p.pot = c.dPot.d;
-    p.force = c.dForce.d;
+    p.unsorted = c.pmeUnsorted ? 1 : 0;
+    p.fix = c.dFix.d; p.chargeF = c.dChargeF.d; p.subsetOf = c.dSubset.d;
+    p.force = c.pmeUnsorted ? c.dForce.d + 3*(size_t) c.Npad : c.dForce.d;
     for (int k = 0; k < 3; k++) p.fscale[k] = (float) (c.grid[k]*c.geom.invBox[k]);
     const int atomCtas = (c.N + 7)/8;
     if (half == 0) {

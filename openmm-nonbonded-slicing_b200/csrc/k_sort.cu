@@ -222,7 +222,9 @@ __global__ void k_excl_range(int N, const float4* __restrict__ par, const int* _
     exclRange[j] = make_int2(lo, hi);
 }
 
-int launchSort(Context& c, const PosInput& in) {
+// Fixed-point conversion + bin histogram (everything downstream -- the rest of the sort AND the PME chain of small
+// systems -- starts from its output).
+int launchPrep(Context& c, const PosInput& in) {
     const CellGeom& g = c.geom;
     const int N = c.N;
     cudaStream_t st = c.stream;
@@ -236,6 +238,15 @@ int launchSort(Context& c, const PosInput& in) {
                                     c.dFix.d, c.dBinCount.d, in.pos64out);
     c.launches++;
     timerMark(c, "prep");
+    return NBS_OK;
+}
+
+// The rest of the cell sort: scan of the bin counts, counting sort, sorted records, i-blocks.
+int launchSortRest(Context& c) {
+    const CellGeom& g = c.geom;
+    const int N = c.N;
+    cudaStream_t st = c.stream;
+    const int T = 256;
     int status = scanExclusive(c, c.dBinCount.d, c.dBinStart.d, g.nBins);
     if (status != NBS_OK) return status;
     k_scatter<<<(N+T-1)/T, T, 0, st>>>(N, c.dFix.d, c.dBinStart.d, c.dBinCursor.d, c.dSortedToOrig.d);

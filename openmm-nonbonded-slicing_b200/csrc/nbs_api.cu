@@ -11,6 +11,7 @@
 #include "nbs_internal.h"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <set>
 
@@ -348,9 +349,13 @@ static int setupGeometry(Context& c, const double box[9]) {
     NBS_CUDA_CHECK(c.dXMask.ensure((size_t) c.maxLocalBlocks*c.capX));
     // work items: enough warps' worth of items to balance 148 SMs x 16 warps on small systems, larger
     // chunks (fewer i-force flushes) on big ones
-    c.chunkTiles = N < 150000 ? 2 : (N < 600000 ? 4 : 8);
+    c.chunkTiles = N < 150000 ? 1 : (N < 600000 ? 4 : 8);
+    if (const char* env = getenv("NBS_CHUNK_TILES")) c.chunkTiles = std::max(1, atoi(env));     // tuning experiments
     NBS_CUDA_CHECK(c.dItems.ensure((size_t) c.maxLocalBlocks*(((c.capJ + c.capX)/32 + c.chunkTiles - 1)/c.chunkTiles + 1)));
-    NBS_CUDA_CHECK(c.dForce.ensure(3*(size_t) c.Npad));
+    // PME from particle-order coordinates while the grids are comfortably L2-resident (scattered access is free
+    // there); large systems keep the cell-sorted order for locality
+    c.pmeUnsorted = c.method == NBS_METHOD_PME && N < 300000 && !(c.flags & NBS_FLAG_SORTED_PME);
+    NBS_CUDA_CHECK(c.dForce.ensure(6*(size_t) c.Npad));
     return NBS_OK;
 }
 
@@ -577,15 +582,25 @@ static int phaseBegin(Context& c, const nbs_exec_args* args) {
             dPos64 = c.dPosIn.d;
         }
     }
-    NBS_CUDA_CHECK(cudaMemsetAsync(c.dForce.d, 0, sizeof(unsigned long long)*3*c.Npad, st));
+    NBS_CUDA_CHECK(cudaMemsetAsync(c.dForce.d, 0, sizeof(unsigned long long)*(c.pmeUnsorted ? 6 : 3)*c.Npad, st));
     NBS_CUDA_CHECK(cudaMemsetAsync(c.dEnergy.d, 0, sizeof(double)*ENERGY_WORDS, st));
     NBS_CUDA_CHECK(cudaMemsetAsync(c.dCounters.d, 0, sizeof(int)*16, st));
     timerMark(c, "h2d_zero");
-    if ((status = launchSort(c, in)) != NBS_OK) return status;
-    if (c.phaseDirect) {
-        // direct space on its own stream so that it overlaps the PME chain (serial when profiling)
-        const bool overlap = !c.profiling && c.phaseRecip && c.directStream != nullptr;
-        if (overlap) {
+    if ((status = launchPrep(c, in)) != NBS_OK) return status;
+    // The cell sort, the neighbour list and direct space run on their own stream, concurrently with the PME
+    // chain on `st` (serial when profiling).  With particle-order PME the fork is right here, after k_prep;
+    // otherwise PME needs the sorted records and the fork comes after the sort.
+    const bool overlap = !c.profiling && c.phaseRecip && c.directStream != nullptr;
+    const bool forkEarly = overlap && c.pmeUnsorted;
+    c.directOverlapped = overlap;
+    if (forkEarly) {
+        NBS_CUDA_CHECK(cudaEventRecord(c.evSorted, st));
+        NBS_CUDA_CHECK(cudaStreamWaitEvent(c.directStream, c.evSorted, 0));
+        c.stream = c.directStream;
+    }
+    status = launchSortRest(c);
+    if (status == NBS_OK && c.phaseDirect) {
+        if (overlap && !forkEarly) {
             NBS_CUDA_CHECK(cudaEventRecord(c.evSorted, st));
             NBS_CUDA_CHECK(cudaStreamWaitEvent(c.directStream, c.evSorted, 0));
             c.stream = c.directStream;
@@ -596,15 +611,14 @@ static int phaseBegin(Context& c, const nbs_exec_args* args) {
             if (!dPos64) status = fail(NBS_ERR_UNSUPPORTED, "exceptions need double-precision positions in this version");
             else status = launchBonded(c, dPos64, true);
         }
-        c.directOverlapped = overlap;
-        if (overlap) {
-            cudaEventRecord(c.evDirectDone, c.directStream);
-            c.stream = st;
-            if (status != NBS_OK) cudaStreamWaitEvent(st, c.evDirectDone, 0);
-        }
-        if (status != NBS_OK) return status;
     }
-    else c.directOverlapped = false;
+    if (overlap) {
+        if (c.stream == c.directStream) cudaEventRecord(c.evDirectDone, c.directStream);
+        else c.directOverlapped = false;                        // nothing was forked (no direct space, late fork)
+        c.stream = st;
+        if (status != NBS_OK && c.directOverlapped) cudaStreamWaitEvent(st, c.evDirectDone, 0);
+    }
+    if (status != NBS_OK) return status;
     if (c.phaseRecip && (status = launchPme(c, c.phaseEnergy, 0)) != NBS_OK) {
         if (c.directOverlapped) cudaStreamWaitEvent(st, c.evDirectDone, 0);
         return status;
@@ -860,7 +874,7 @@ int nbs_get_exchange_buffers(nbs_context* ctx, nbs_exchange_buffers* out) {
     out->spectrum_bytes_per_subset = (int64_t) (Gh*(fp64 ? sizeof(double2) : sizeof(float2)));
     out->spectrum_is_double = fp64 ? 1 : 0;
     out->forces = c.dForce.d;
-    out->force_words = 3*(int64_t) c.Npad;
+    out->force_words = (c.pmeUnsorted ? 6 : 3)*(int64_t) c.Npad;
     out->energies = c.dEnergy.d;
     out->energy_words = ENERGY_WORDS;
     return NBS_OK;

@@ -129,10 +129,10 @@ struct Context {
     Buf<uint4> dBlkLo, dBlkHi;               // fixed-point bounding box; lo.w = column index
     Buf<int2> dExclRange;                    // per sorted atom: [min, max] sorted index of its exclusion partners
     Buf<int> dJList, dJCount, dXList, dXCount;
-    Buf<int2> dItems;                        // pair-kernel work items (local block, first tile)
+    Buf<int4> dItems;                        // pair-kernel work items (local block, first tile, first atom, atom count)
     Buf<unsigned> dXMask;
     Buf<int> dCounters;                      // [0] nBlocks, [1] overflow flag, [2] pair work items, [3] work cursor
-    Buf<unsigned long long> dForce;          // [3][Npad]
+    Buf<unsigned long long> dForce;          // [3][Npad] in sorted order (+ [3][Npad] in particle order: unsorted-PME gather)
     Buf<double> dEnergy;                     // [MAX_SLICES][2]
     Buf<double> dGrid;                       // charge grid [nS][nx][ny][nz] (double or float view)
     Buf<double2> dGridC;                     // half spectrum [nS][nx][ny][nz/2+1] (double2 or float2 view)
@@ -172,6 +172,7 @@ struct Context {
     int blockPeriod = 1, blockOffset = 0, blockWidth = 1;
     int ownLo = 0, ownHi = 0;                // set to [0, nS) at creation
     int maxLocalBlocks = 0;
+    bool pmeUnsorted = false;                // PME works from particle-order coordinates (forks before the sort)
     int chunkTiles = 2;                      // tiles per pair-kernel work item
     int numSMs = 148;
     // ---- phase state of the evaluation in flight ----
@@ -196,7 +197,8 @@ __host__ __device__ inline int localToGlobalBlock(int local, int period, int off
 // ---- launch wrappers (each counts its launches in ctx.launches) ----
 struct PosInput { const void* ptr; int format; const int* atomIndex; double* pos64out; };
 
-int launchSort(Context& c, const PosInput& in);                 // fixed-point conversion, binning, cell sort, blocks
+int launchPrep(Context& c, const PosInput& in);                 // fixed-point conversion, bin histogram
+int launchSortRest(Context& c);                                 // cell sort, sorted records, i-blocks
 int launchBuildLists(Context& c);
 int launchExclRange(Context& c);
 int launchPairs(Context& c, bool wantEnergy, int mode);         // mode 0: forces+energy, 1: count/hash pairs, 2: dump pairs

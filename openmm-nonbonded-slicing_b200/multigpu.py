@@ -391,8 +391,22 @@ def bench_main(args, workload_name):
     dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = 1.0/float(te.mean().item())
 
-    pairs = torch.tensor([kernel.getPairSet(with_pairs=False)[0]], dtype=torch.int64, device=dev)
+    local_pairs = kernel.getPairSet(with_pairs=False)[0]
+    pairs = torch.tensor([local_pairs], dtype=torch.int64, device=dev)
     dist.all_reduce(pairs)
+    # per-kernel durations of THIS rank's shard (profiled context: serial streams, CUDA events per kernel)
+    prof = factory(abi.NBS_FLAG_PROFILE)
+    prof.set_plan(plan, rank)
+    acc = {}
+    for it in range(5):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        prof.prepare(pos_dev.data_ptr(), s.box, frc_dev.data_ptr(), lam, stream=stream)
+        evaluate_distributed(plan, rank, prof, dist, pme_group)
+        if it >= 2:
+            for name, t in prof.getKernelTimes():
+                acc[name] = acc.get(name, 0.0) + t/3
+    del prof
     checksum = float(np.abs(energies).sum())
     fsum = frc_dev.abs().sum().reshape(1)
     fmin, fmax = fsum.clone(), fsum.clone()
@@ -415,6 +429,9 @@ def bench_main(args, workload_name):
                     "d2h_bytes_per_step": int(frc_host.numel()*8 + 8*2*nsl), "ns_per_day_2fs": bench.ns_per_day(e2e_value),
                     "note": "per rank: every rank uploads all positions and downloads all forces"},
             "gpu_launches": int(launches),
+            "roofline": bench.pair_roofline(local_pairs, acc.get("pair", float("nan")), None,
+                                            note="rank 0's share of the i-blocks"),
+            "kernel_ms_rank0": {k: round(v, 5) for k, v in acc.items()},
             "collectives_per_step": {"spectrum_broadcasts": ns if plan.num_pme_ranks > 1 else 0, "all_reduces": 2},
             "slice_energy_checksum": checksum,
             "forces_identical_on_all_ranks": bool(fmin.item() == fmax.item()),

@@ -74,12 +74,14 @@ def test_reference_fixture(nbs, platform, systems, name):
     three_way(kernel, kernel.desc, s.positions, s.box, g["lambdas"], fixture)
 
 
-def test_line_fft_path(nbs, systems):
-    """Grids whose planes do not fit in shared memory use the line-at-a-time FFT kernels; force that path
-    (NBS_FLAG_LINE_FFT) on a small system and hold it to the same fixture."""
+@pytest.mark.parametrize("flags", ["NBS_FLAG_LINE_FFT", "NBS_FLAG_SORTED_PME", "NBS_FLAG_NO_GRAPH"])
+def test_alternative_paths(nbs, systems, flags):
+    """Paths that small systems do not take by default, forced on a small system and held to the same fixture:
+    the line-at-a-time FFT kernels (planes beyond shared memory), PME from the cell-sorted records (large
+    systems), plain stream launches instead of the captured CUDA graph."""
     g = np.load(os.path.join(GOLDEN, "C2_reference.npz"))
     s = systems.make_system("C2")
-    kernel = nbs.B200CalcSlicedNonbondedForceKernel(nbs.Platform(flags=nbs.abi.NBS_FLAG_LINE_FFT))
+    kernel = nbs.B200CalcSlicedNonbondedForceKernel(nbs.Platform(flags=getattr(nbs.abi, flags)))
     kernel.initialize(s.system, s.force)
 
     def fixture(tag, direct, recip):

@@ -23,6 +23,23 @@
 
 namespace nbs {
 
+// Division by a run-time constant without the ~30-instruction integer divide: q = trunc((x + 0.5) * (1/d)) in
+// fp32 is exact while x < 2^20 (the relative error 2^-22 of the product stays below the 0.5/d margin), which
+// covers every index in this file (all below 2^16).  A thread owns only one or two butterflies of a few dozen
+// instructions per pass, so four integer divides per butterfly were most of the kernel -- and so would be a
+// 64-bit magic-number computation per pass.
+struct FastDiv {
+    int d;
+    float inv;
+    __device__ __forceinline__ explicit FastDiv(int divisor) : d(divisor), inv(1.0f/(float) divisor) {}
+    __device__ __forceinline__ int div(int x) const { return __float2int_rz(((float) x + 0.5f)*inv); }
+    __device__ __forceinline__ void divmod(int x, int& q, int& r) const { q = div(x); r = x - q*d; }
+};
+
+// Global -> shared copies keep FFT_COPY_U loads in flight per thread: with one load per loop trip (what the
+// compiler emits for a plain strided loop) the kernels spent a fifth of their time waiting on L2 latency here.
+constexpr int FFT_COPY_U = 4;
+
 template <typename T> struct Cx2;
 template <> struct Cx2<float> { typedef float2 type; };
 template <> struct Cx2<double> { typedef double2 type; };
@@ -45,6 +62,7 @@ __device__ __forceinline__ void batchedPass(C* base, int lines, int lineStride, 
     const int tstep = n/(Ns*R), rstep = n/R;
     const int os = Ns*elemStride;
     const int linesPerRound = max(1, (int) blockDim.x/nb);       // host guarantees nb <= blockDim.x
+    const FastDiv divNb(nb), divNs(Ns);
     for (int l0 = 0; l0 < lines; l0 += linesPerRound) {
         const int nl = min(linesPerRound, lines - l0);
         const int wi = threadIdx.x;
@@ -52,18 +70,19 @@ __device__ __forceinline__ void batchedPass(C* base, int lines, int lineStride, 
         int dst = -1;
         if (wi < nl*nb) {
             int L, j;
-            if (elemStride == 1) { L = wi/nb; j = wi - L*nb; }
-            else { j = wi/nl; L = wi - j*nl; }
+            if (elemStride == 1) divNb.divmod(wi, L, j);
+            else FastDiv(nl).divmod(wi, j, L);
             L += l0;
             const C* line = base + (size_t) L*lineStride;
 #pragma unroll
             for (int t = 0; t < R; t++) v[t] = line[(j + t*nb)*elemStride];
-            const int k = j % Ns;
+            int jq, k;
+            divNs.divmod(j, jq, k);
             if (Ns > 1) {
 #pragma unroll
                 for (int t = 1; t < R; t++) v[t] = cmulc(v[t], tw[t*k*tstep]);
             }
-            dst = L*lineStride + ((j/Ns)*Ns*R + k)*elemStride;
+            dst = L*lineStride + (jq*Ns*R + k)*elemStride;
         }
         __syncthreads();
         if (dst >= 0) {
@@ -103,6 +122,7 @@ __device__ __noinline__ void batchedPassLarge(C* base, int lines, int lineStride
     const int nb = n/R, tstep = n/(Ns*R), rstep = n/R;
     const int os = Ns*elemStride;
     const int linesPerRound = max(1, (int) blockDim.x/nb);
+    const FastDiv divNb(nb), divNs(Ns);
     for (int l0 = 0; l0 < lines; l0 += linesPerRound) {
         const int nl = min(linesPerRound, lines - l0);
         const int wi = threadIdx.x;
@@ -110,16 +130,17 @@ __device__ __noinline__ void batchedPassLarge(C* base, int lines, int lineStride
         int dst = -1;
         if (wi < nl*nb) {
             int L, j;
-            if (elemStride == 1) { L = wi/nb; j = wi - L*nb; }
-            else { j = wi/nl; L = wi - j*nl; }
+            if (elemStride == 1) divNb.divmod(wi, L, j);
+            else FastDiv(nl).divmod(wi, j, L);
             L += l0;
             const C* line = base + (size_t) L*lineStride;
-            const int k = j % Ns;
+            int jq, k;
+            divNs.divmod(j, jq, k);
             for (int t = 0; t < R; t++) {
                 C x = line[(j + t*nb)*elemStride];
                 v[t] = t == 0 ? x : cmulc(x, tw[t*k*tstep]);
             }
-            dst = L*lineStride + ((j/Ns)*Ns*R + k)*elemStride;
+            dst = L*lineStride + (jq*Ns*R + k)*elemStride;
         }
         __syncthreads();
         if (dst >= 0) {
@@ -170,6 +191,7 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_zy_fwd(const PlaneFftArgs a
     C* twz = sm;
     C* twy = sm + nz;
     C* plane = sm + nz + ny;
+    const FastDiv divNz(nz), divNzh(nzh);
     for (int k = threadIdx.x; k < nz; k += blockDim.x) twz[k] = ((const C*) a.twz)[k];
     for (int k = threadIdx.x; k < ny; k += blockDim.x) twy[k] = ((const C*) a.twy)[k];
     // CTA = one (own subset, x) plane, or -- when a plane does not fit in shared memory -- a slab of its row pairs
@@ -182,11 +204,24 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_zy_fwd(const PlaneFftArgs a
     const int pairs = min(a.slabPairs, allPairs - pBase);       // row pairs this CTA holds (local rows 0 .. 2*pairs)
     const int rowBase = 2*pBase, rowsHere = min(2*pairs, ny - rowBase);
     const T* grid = (const T*) a.grid + ((size_t) sx*ny + rowBase)*nz;
-    for (int idx = threadIdx.x; idx < pairs*nz; idx += blockDim.x) {
-        const int p = idx/nz, z = idx - p*nz;
-        const T re = grid[(size_t) (2*p)*nz + z];
-        const T im = 2*p + 1 < rowsHere ? grid[(size_t) (2*p + 1)*nz + z] : (T) 0;
-        plane[(size_t) p*2*rs + z] = mkc(re, im);
+    for (int base = threadIdx.x; base < pairs*nz; base += FFT_COPY_U*blockDim.x) {
+        T re[FFT_COPY_U], im[FFT_COPY_U];
+        int at[FFT_COPY_U];
+#pragma unroll
+        for (int u = 0; u < FFT_COPY_U; u++) {
+            const int idx = base + u*blockDim.x;
+            at[u] = -1;
+            if (idx < pairs*nz) {
+                int p, z;
+                divNz.divmod(idx, p, z);
+                re[u] = grid[(size_t) (2*p)*nz + z];
+                im[u] = 2*p + 1 < rowsHere ? grid[(size_t) (2*p + 1)*nz + z] : (T) 0;
+                at[u] = p*2*rs + z;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < FFT_COPY_U; u++)
+            if (at[u] >= 0) plane[at[u]] = mkc(re[u], im[u]);
     }
     __syncthreads();
     batchedFft<RMAX>(plane, pairs, 2*rs, 1, nz, a.factorsZ, twz);
@@ -202,7 +237,9 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_zy_fwd(const PlaneFftArgs a
             for (int q = 0; q < FFT_UNPACK_Q; q++) {
                 const int wi = threadIdx.x + q*blockDim.x;
                 if (wi < count) {
-                    const int p = p0 + wi/nzh, k = wi % nzh;
+                    int p, k;
+                    divNzh.divmod(wi, p, k);
+                    p += p0;
                     const C* line = plane + (size_t) p*2*rs;
                     zk[q] = line[k];
                     zn[q] = line[k == 0 ? 0 : nz - k];
@@ -213,7 +250,9 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_zy_fwd(const PlaneFftArgs a
             for (int q = 0; q < FFT_UNPACK_Q; q++) {
                 const int wi = threadIdx.x + q*blockDim.x;
                 if (wi < count) {
-                    const int p = p0 + wi/nzh, k = wi % nzh;
+                    int p, k;
+                    divNzh.divmod(wi, p, k);
+                    p += p0;
                     plane[(size_t) (2*p)*rs + k] = mkc(half*(zk[q].x + zn[q].x), half*(zk[q].y - zn[q].y));
                     if (2*p + 1 < rowsHere) plane[(size_t) (2*p + 1)*rs + k] = mkc(half*(zk[q].y + zn[q].y), -half*(zk[q].x - zn[q].x));
                 }
@@ -224,7 +263,8 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_zy_fwd(const PlaneFftArgs a
     if (fused) batchedFft<RMAX>(plane, nzh, 1, rs, ny, a.factorsY, twy);
     C* out = (C*) a.gridC + ((size_t) sx*ny + rowBase)*nzh;
     for (int idx = threadIdx.x; idx < rowsHere*nzh; idx += blockDim.x) {
-        const int y = idx/nzh, k = idx - y*nzh;
+        int y, k;
+        divNzh.divmod(idx, y, k);
         out[idx] = plane[(size_t) y*rs + k];
     }
 }
@@ -244,17 +284,34 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_y_cols(const PlaneFftArgs a
     const int chunks = (nzh + cw - 1)/cw;
     const int plane_ = blockIdx.x/chunks, k0 = (blockIdx.x - plane_*chunks)*cw;
     const int kn = min(cw, nzh - k0);
+    const FastDiv divKn(kn);
     C* base = (C*) a.gridC + (size_t) (a.ownLo*a.nx + plane_)*ny*nzh + k0;
-    for (int idx = threadIdx.x; idx < ny*kn; idx += blockDim.x) {
-        const int y = idx/kn, l = idx - y*kn;
-        C v = base[(size_t) y*nzh + l];
-        if (INVERSE) v.y = -v.y;
-        cols[(size_t) y*rs + l] = v;
+    for (int b0 = threadIdx.x; b0 < ny*kn; b0 += FFT_COPY_U*blockDim.x) {
+        C v[FFT_COPY_U];
+        int at[FFT_COPY_U];
+#pragma unroll
+        for (int u = 0; u < FFT_COPY_U; u++) {
+            const int idx = b0 + u*blockDim.x;
+            at[u] = -1;
+            if (idx < ny*kn) {
+                int y, l;
+                divKn.divmod(idx, y, l);
+                v[u] = base[(size_t) y*nzh + l];
+                at[u] = y*rs + l;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < FFT_COPY_U; u++)
+            if (at[u] >= 0) {
+                if (INVERSE) v[u].y = -v[u].y;
+                cols[at[u]] = v[u];
+            }
     }
     __syncthreads();
     batchedFft<RMAX>(cols, kn, 1, rs, ny, a.factorsY, twy);
     for (int idx = threadIdx.x; idx < ny*kn; idx += blockDim.x) {
-        const int y = idx/kn, l = idx - y*kn;
+        int y, l;
+        divKn.divmod(idx, y, l);
         C v = cols[(size_t) y*rs + l];
         if (INVERSE) v.y = -v.y;
         base[(size_t) y*nzh + l] = v;
@@ -274,6 +331,7 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_yz_inv(const PlaneFftArgs a
     C* twz = sm;
     C* twy = sm + nz;
     C* plane = sm + nz + ny;
+    const FastDiv divNz(nz), divNzh(nzh);
     for (int k = threadIdx.x; k < nz; k += blockDim.x) twz[k] = ((const C*) a.twz)[k];
     for (int k = threadIdx.x; k < ny; k += blockDim.x) twy[k] = ((const C*) a.twy)[k];
     const int plane_ = blockIdx.x/a.slabsPerPlane, slab = blockIdx.x - plane_*a.slabsPerPlane;
@@ -284,11 +342,26 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_yz_inv(const PlaneFftArgs a
     const int pairs = min(a.slabPairs, allPairs - pBase);
     const int rowBase = 2*pBase, rowsHere = min(2*pairs, ny - rowBase);
     const C* in = (const C*) a.gridC + ((size_t) sx*ny + rowBase)*nzh;
-    for (int idx = threadIdx.x; idx < rowsHere*nzh; idx += blockDim.x) {
-        const int y = idx/nzh, k = idx - y*nzh;
-        C v = in[idx];
-        v.y = -v.y;                                              // conjugate: inverse y = conj(fwd(conj))
-        plane[(size_t) y*rs + k] = v;
+    for (int b0 = threadIdx.x; b0 < rowsHere*nzh; b0 += FFT_COPY_U*blockDim.x) {
+        C v[FFT_COPY_U];
+        int at[FFT_COPY_U];
+#pragma unroll
+        for (int u = 0; u < FFT_COPY_U; u++) {
+            const int idx = b0 + u*blockDim.x;
+            at[u] = -1;
+            if (idx < rowsHere*nzh) {
+                int y, k;
+                divNzh.divmod(idx, y, k);
+                v[u] = in[idx];
+                at[u] = y*rs + k;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < FFT_COPY_U; u++)
+            if (at[u] >= 0) {
+                v[u].y = -v[u].y;                                // conjugate: inverse y = conj(fwd(conj))
+                plane[at[u]] = v[u];
+            }
     }
     __syncthreads();
     if (fused) batchedFft<RMAX>(plane, nzh, 1, rs, ny, a.factorsY, twy);
@@ -305,7 +378,9 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_yz_inv(const PlaneFftArgs a
             for (int q = 0; q < FFT_UNPACK_Q; q++) {
                 const int wi = threadIdx.x + q*blockDim.x;
                 if (wi < count) {
-                    const int p = p0 + wi/nzh, k = wi % nzh;
+                    int p, k;
+                    divNzh.divmod(wi, p, k);
+                    p += p0;
                     C u = plane[(size_t) (2*p)*rs + k];
                     u.y = -u.y;                                      // A0[k]
                     C v = mkc((T) 0, (T) 0);
@@ -318,7 +393,9 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_yz_inv(const PlaneFftArgs a
             for (int q = 0; q < FFT_UNPACK_Q; q++) {
                 const int wi = threadIdx.x + q*blockDim.x;
                 if (wi < count) {
-                    const int p = p0 + wi/nzh, k = wi % nzh;
+                    int p, k;
+                    divNzh.divmod(wi, p, k);
+                    p += p0;
                     C* line = plane + (size_t) p*2*rs;
                     const C A = a0[q], B = a1[q];
                     line[k] = mkc(A.x - B.y, -(A.y + B.x));                           // conj(A + iB)
@@ -330,7 +407,8 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_yz_inv(const PlaneFftArgs a
         batchedFft<RMAX>(plane, pairs, 2*rs, 1, nz, a.factorsZ, twz);
         float* pot = a.pot + ((size_t) sx*ny + rowBase)*nz;
         for (int idx = threadIdx.x; idx < pairs*nz; idx += blockDim.x) {
-            const int p = idx/nz, z = idx - p*nz;
+            int p, z;
+        divNz.divmod(idx, p, z);
             const C wv = plane[(size_t) p*2*rs + z];
             pot[(size_t) (2*p)*nz + z] = (float) wv.x;
             if (2*p + 1 < rowsHere) pot[(size_t) (2*p + 1)*nz + z] = (float) -wv.y;
@@ -362,10 +440,33 @@ __global__ void __launch_bounds__(FFT_X_THREADS) k_fft_x_conv2(const PlaneFftArg
     const int chunks = (nzh + chunk - 1)/chunk;
     const int y = blockIdx.x/chunks, k0 = (blockIdx.x - y*chunks)*chunk;
     const int kn = min(chunk, nzh - k0);                     // kz values this CTA really has
+    const FastDiv divKn(kn), divChunk(chunk), divN(n);
     C* gridC = (C*) a.gridC;
-    for (int idx = threadIdx.x; idx < nS*n*chunk; idx += blockDim.x) {
-        const int l = idx % chunk, x = (idx/chunk) % n, s = idx/(chunk*n);
-        lines[(size_t) x*RS + s*chunk + l] = l < kn ? gridC[(((size_t) s*n + x)*a.ny + y)*nzh + k0 + l] : mkc((T) 0, (T) 0);
+    for (int b0 = threadIdx.x; b0 < nS*n*chunk; b0 += FFT_COPY_U*blockDim.x) {
+        C v[FFT_COPY_U];
+        int at[FFT_COPY_U];
+#pragma unroll
+        for (int u = 0; u < FFT_COPY_U; u++) {
+            const int idx = b0 + u*blockDim.x;
+            at[u] = -1;
+            if (idx < nS*n*chunk) {
+                int rest, l, s, x;
+                divChunk.divmod(idx, rest, l);
+                divN.divmod(rest, s, x);
+                v[u] = l < kn ? gridC[(((size_t) s*n + x)*a.ny + y)*nzh + k0 + l] : mkc((T) 0, (T) 0);
+                at[u] = x*RS + s*chunk + l;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < FFT_COPY_U; u++)
+            if (at[u] >= 0) lines[at[u]] = v[u];
+    }
+    // the influence function of this CTA's (x, y, kz) points, fetched now so that its latency hides behind the forward transform
+    T* etS = (T*) (lines + (size_t) n*RS);
+    for (int idx = threadIdx.x; idx < n*kn; idx += blockDim.x) {
+        int x, l;
+        divKn.divmod(idx, x, l);
+        etS[idx] = ((const T*) a.eterm)[((size_t) x*a.ny + y)*nzh + k0 + l];
     }
     __syncthreads();
     batchedFft<RMAX>(lines, nS*chunk, 1, RS, n, a.factorsX, tw);
@@ -373,8 +474,10 @@ __global__ void __launch_bounds__(FFT_X_THREADS) k_fft_x_conv2(const PlaneFftArg
 #pragma unroll
     for (int s = 0; s < NS*(NS+1)/2; s++) e[s] = 0.0;
     for (int idx = threadIdx.x; idx < n*kn; idx += blockDim.x) {
-        const int l = idx % kn, x = idx/kn, k = k0 + l;
-        const T et = ((const T*) a.eterm)[((size_t) x*a.ny + y)*nzh + k];
+        int x, l;
+        divKn.divmod(idx, x, l);
+        const int k = k0 + l;
+        const T et = etS[idx];
         C S[NS];
 #pragma unroll
         for (int s = 0; s < NS; s++) S[s] = s < nS ? lines[(size_t) x*RS + s*chunk + l] : mkc((T) 0, (T) 0);
@@ -407,7 +510,10 @@ __global__ void __launch_bounds__(FFT_X_THREADS) k_fft_x_conv2(const PlaneFftArg
     const int nOwn = a.ownHi - a.ownLo;
     batchedFft<RMAX>(lines + (size_t) a.ownLo*chunk, nOwn*chunk, 1, RS, n, a.factorsX, tw);
     for (int idx = threadIdx.x; idx < nOwn*n*kn; idx += blockDim.x) {
-        const int l = idx % kn, x = (idx/kn) % n, s = a.ownLo + idx/(kn*n);
+        int rest, l, s, x;
+        divKn.divmod(idx, rest, l);
+        divN.divmod(rest, s, x);
+        s += a.ownLo;
         C v = lines[(size_t) x*RS + s*chunk + l];
         v.y = -v.y;
         gridC[(((size_t) s*n + x)*a.ny + y)*nzh + k0 + l] = v;
@@ -487,8 +593,8 @@ int launchPlaneFft(Context& c, const PlaneFftPlan& plan, PlaneFftArgs a, int hal
     int chunks = (nzh + 7)/8;
     int chunk = (nzh + chunks - 1)/chunks;
     const size_t cs = sizeof(C);
-    while (chunk > 1 && cs*((size_t) nx + (size_t) nx*(c.nS*chunk + 1)) > 200*1024) chunk--;
-    const size_t smX = cs*((size_t) nx + (size_t) nx*(c.nS*chunk + 1));
+    while (chunk > 1 && cs*((size_t) nx + (size_t) nx*(c.nS*chunk + 1)) + sizeof(T)*nx*chunk > 200*1024) chunk--;
+    const size_t smX = cs*((size_t) nx + (size_t) nx*(c.nS*chunk + 1)) + sizeof(T)*(size_t) nx*chunk;
     if (smX > 200*1024) return NBS_RETRY;
     // zy / yz kernels: the whole plane when it fits (y transform fused in), else slabs of row pairs of <= ~64 KB
     const int pairsZ = (ny + 1)/2;

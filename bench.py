@@ -34,7 +34,7 @@ FLOP_PER_PAIR = 72            # FP32-equivalent flops per interacti
 FS_PER_STEP = 2.0             # ns/day figure assumes one evaluation per 2 fs step
 # DRAM traffic of one k_pair launch from the committed ncu captures (profiles/README.md): the kernel's working
 # set (positions, parameters, lists) is L2-resident, so this is far below any bandwidth limit
-PAIR_TRAFFIC_BYTES = {"C3": 3858432}
+PAIR_TRAFFIC_BYTES = {"C3": 8676608}
 
 
 def parse_args():

@@ -19,6 +19,7 @@
 #include "nbs_device.cuh"
 #include "k_fft.cuh"
 #include <algorithm>
+#include <cstdlib>
 // compiled twice (k_fft_f32.cu, k_fft_f64.cu define NBS_FFT_REAL) so that the two precisions build in parallel
 
 namespace nbs {
@@ -590,7 +591,9 @@ int launchPlaneFft(Context& c, const PlaneFftPlan& plan, PlaneFftArgs a, int hal
     const int nx = c.grid[0], ny = c.grid[1], nz = c.grid[2], nzh = nz/2 + 1;
     const int rs = std::max(nzh, (nz + 1)/2) + 1;
     // x pass: choose the kz chunk so that the chunks are even and the lines of all subsets fit
-    int chunks = (nzh + 7)/8;
+    int xTarget = 8;
+    if (const char* env = getenv("NBS_FFT_XCHUNK")) xTarget = std::max(1, atoi(env));                 // tuning experiments
+    int chunks = (nzh + xTarget - 1)/xTarget;
     int chunk = (nzh + chunks - 1)/chunks;
     const size_t cs = sizeof(C);
     while (chunk > 1 && cs*((size_t) nx + (size_t) nx*(c.nS*chunk + 1)) + sizeof(T)*nx*chunk > 200*1024) chunk--;
@@ -601,8 +604,10 @@ int launchPlaneFft(Context& c, const PlaneFftPlan& plan, PlaneFftArgs a, int hal
     size_t smPlane = cs*((size_t) nz + ny + (size_t) pairsZ*2*rs);
     a.slabPairs = pairsZ;
     a.slabsPerPlane = 1;
+    size_t slabBytes = 64*1024;
+    if (const char* env = getenv("NBS_FFT_SLAB_KB")) { slabBytes = (size_t) atoi(env)*1024; smPlane = 1u << 30; }   // tuning experiments: force the split path
     if (smPlane > 200*1024) {
-        a.slabPairs = std::max(1, (int) ((64*1024/cs - nz - ny)/(2*rs)));
+        a.slabPairs = std::max(1, (int) ((slabBytes/cs - nz - ny)/(2*rs)));
         a.slabsPerPlane = (pairsZ + a.slabPairs - 1)/a.slabPairs;
         a.slabPairs = (pairsZ + a.slabsPerPlane - 1)/a.slabsPerPlane;          // even slabs
         smPlane = cs*((size_t) nz + ny + (size_t) a.slabPairs*2*rs);

@@ -177,6 +177,7 @@ struct PmeArgs {
     // wait for the cell sort; forces then go to the particle-order half of the accumulator
     int unsorted;
     const uint4* fix; const float* chargeF; const int* subsetOf;
+    const double* q64; const double* chargeD; double sqrtK;      // double-precision charges for the double-precision grids
     void* grid; const float* pot;
     unsigned long long* force;
     float fscale[3];             // n_d / L_d
@@ -226,6 +227,8 @@ __global__ void __launch_bounds__(256) k_spread(const PmeArgs a) {
     int ix0, iy0, iz0;
     splineTable<T>(a, p, lane, wtab[warp], (T*) nullptr, ix0, iy0, iz0);
     const T* wt = wtab[warp];
+    // (the fp32 charge carries 6e-8 of rounding: visible in cross-subset energies that cancel to 1e-6 of their terms)
+    const T qT = sizeof(T) == 8 ? (T) (a.unsorted ? a.chargeD[j]*a.sqrtK : a.q64[j]) : (T) q;
     T* grid = (T*) a.grid + (size_t) subset*a.nx*a.ny*a.nz;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
@@ -235,7 +238,7 @@ __global__ void __launch_bounds__(256) k_spread(const PmeArgs a) {
             int x = ix0 + ox; x -= x >= a.nx ? a.nx : 0;
             int y = iy0 + oy; y -= y >= a.ny ? a.ny : 0;
             int z = iz0 + oz; z -= z >= a.nz ? a.nz : 0;
-            atomicAdd(grid + ((size_t) x*a.ny + y)*a.nz + z, (T) q*wt[ox]*wt[5 + oy]*wt[10 + oz]);
+            atomicAdd(grid + ((size_t) x*a.ny + y)*a.nz + z, qT*wt[ox]*wt[5 + oy]*wt[10 + oz]);
         }
     }
 }
@@ -596,6 +599,7 @@ static int launchPmeT(Context& c, bool wantEnergy, int half) {
     p.posq = c.dPosq.d; p.par = c.dPar.d; p.grid = c.dGrid.d; p.pot = c.dPot.d;
     p.unsorted = c.pmeUnsorted ? 1 : 0;
     p.fix = c.dFix.d; p.chargeF = c.dChargeF.d; p.subsetOf = c.dSubset.d;
+    p.q64 = c.dQ64.d; p.chargeD = c.dCharge.d; p.sqrtK = sqrt(kOne4PiEps0);
     p.force = c.pmeUnsorted ? c.dForce.d + 3*(size_t) c.Npad : c.dForce.d;
     for (int k = 0; k < 3; k++) p.fscale[k] = (float) (c.grid[k]*c.geom.invBox[k]);
     const int atomCtas = (c.N + 7)/8;

@@ -395,6 +395,10 @@ static void releaseAll(Context& c) {
     c.graphExec = nullptr;
     if (c.ownStream) cudaStreamDestroy(c.ownStream);
     c.ownStream = nullptr;
+    if (c.auxStream) cudaStreamDestroy(c.auxStream);
+    if (c.evAuxFork) cudaEventDestroy(c.evAuxFork);
+    if (c.evAuxDone) cudaEventDestroy(c.evAuxDone);
+    c.auxStream = nullptr; c.evAuxFork = nullptr; c.evAuxDone = nullptr;
     if (c.directStream) cudaStreamDestroy(c.directStream);
     if (c.evSorted) cudaEventDestroy(c.evSorted);
     if (c.evDirectDone) cudaEventDestroy(c.evDirectDone);
@@ -455,6 +459,9 @@ int nbs_create(const nbs_system_desc* desc, nbs_context** out) {
         (e = cudaMallocHost((void**) &c.hCounters, 16*sizeof(int))) != cudaSuccess ||
         (e = cudaMallocHost((void**) &c.hEnergy, ENERGY_WORDS*sizeof(double))) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&c.directStream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&c.auxStream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&c.evAuxFork, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&c.evAuxDone, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&c.evSorted, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&c.evDirectDone, cudaEventDisableTiming)) != cudaSuccess) {
         releaseAll(c);
@@ -605,12 +612,23 @@ static int phaseBegin(Context& c, const nbs_exec_args* args) {
             NBS_CUDA_CHECK(cudaStreamWaitEvent(c.directStream, c.evSorted, 0));
             c.stream = c.directStream;
         }
-        status = launchBuildLists(c);
+        // exceptions / exclusion corrections only need the sorted order: a third stream runs them beside the list build
+        const bool forkBonded = overlap && c.nExc > 0 && dPos64 && c.auxStream != nullptr && c.stream == c.directStream;
+        if (forkBonded) {
+            cudaEventRecord(c.evAuxFork, c.directStream);
+            cudaStreamWaitEvent(c.auxStream, c.evAuxFork, 0);
+            c.stream = c.auxStream;
+            status = launchBonded(c, dPos64, true);
+            cudaEventRecord(c.evAuxDone, c.auxStream);
+            c.stream = c.directStream;
+        }
+        if (status == NBS_OK) status = launchBuildLists(c);
         if (status == NBS_OK) status = launchPairs(c, c.phaseEnergy, 0);
-        if (status == NBS_OK && c.nExc > 0) {
+        if (status == NBS_OK && c.nExc > 0 && !forkBonded) {
             if (!dPos64) status = fail(NBS_ERR_UNSUPPORTED, "exceptions need double-precision positions in this version");
             else status = launchBonded(c, dPos64, true);
         }
+        if (forkBonded) cudaStreamWaitEvent(c.directStream, c.evAuxDone, 0);
     }
     if (overlap) {
         if (c.stream == c.directStream) cudaEventRecord(c.evDirectDone, c.directStream);

@@ -179,6 +179,8 @@ struct Context {
     cudaStream_t ownStream = nullptr;        // used when the caller passes the legacy default stream
     cudaStream_t directStream = nullptr;     // direct space runs here, concurrently with PME on `stream`
     cudaEvent_t evSorted = nullptr, evDirectDone = nullptr;
+    cudaStream_t auxStream = nullptr;        // exceptions / exclusion corrections, beside the list build
+    cudaEvent_t evAuxFork = nullptr, evAuxDone = nullptr;
     bool phaseDirect = false, phaseRecip = false, phaseEnergy = false, directOverlapped = false;
     const double* phasePos64 = nullptr;
     int phase = 0;                           // 0 idle, 1 begun, 2 convolved

@@ -27,11 +27,11 @@ struct BondedArgs {
 };
 
 __global__ void k_bonded(const BondedArgs a) {
-    const int e = blockIdx.x*blockDim.x + threadIdx.x;
+    const int e = (blockIdx.x*blockDim.x + threadIdx.x)*a.nRanks + a.rank;     // this rank's exceptions, densely packed into the grid
     const int lane = threadIdx.x & 31;
     int slice = -1;
     double eCoul = 0.0, eVdw = 0.0;
-    if (e < a.nExc && e % a.nRanks == a.rank) {
+    if (e < a.nExc) {
         const int2 pr = a.pairs[e];
         const int s1 = a.slotOf ? a.slotOf[pr.x] : pr.x, s2 = a.slotOf ? a.slotOf[pr.y] : pr.y;
         double dx = a.pos[3*s1] - a.pos[3*s2], dy = a.pos[3*s1+1] - a.pos[3*s2+1], dz = a.pos[3*s1+2] - a.pos[3*s2+2];
@@ -113,7 +113,8 @@ int launchBonded(Context& c, const double* dPos, bool periodicBox) {
         a.lamV[s] = s < c.nSl ? c.lambdas[2*s+1] : 1.0;
     }
     const int T = 128;
-    k_bonded<<<(c.nExc+T-1)/T, T, 0, c.stream>>>(a);
+    const int mine = (c.nExc + c.nRanks - 1)/c.nRanks;
+    k_bonded<<<(mine+T-1)/T, T, 0, c.stream>>>(a);
     c.launches++;
     timerMark(c, "bonded");
     return NBS_OK;

@@ -27,6 +27,7 @@ struct BuildArgs {
     int N, maxBlocks, capJ, capX;
     int blockPeriod, blockOffset, blockWidth;   // this rank's share of the i-blocks
     int ncx, ncy, nzb;
+    int periodic;              // 0: NoCutoff / CutoffNonPeriodic -- no images
     float colWx, colWy, binH;
     float Lx, Ly, Lz;
     float sx, sy, sz;          // nm per fixed-point unit
@@ -75,6 +76,7 @@ __global__ void __launch_bounds__(BUILD_WARPS*32) k_build_lists(BuildArgs a) {
         const int kx = (ux >= a.ncx) - (ux < 0), ky = (uy >= a.ncy) - (uy < 0);
         const int wx = ux - kx*a.ncx, wy = uy - ky*a.ncy;
         if (wx < 0 || wx >= a.ncx || wy < 0 || wy >= a.ncy) continue;      // more than one box away: cannot interact
+        if (!a.periodic && (kx != 0 || ky != 0)) continue;
         const int colJ = wx*a.ncy + wy;
         if (colJ < colI) continue;                                         // owned by the other block
         const float gx = fmaxf(0.f, fmaxf(ux*a.colWx - hix, lox - (ux+1)*a.colWx));
@@ -84,6 +86,7 @@ __global__ void __launch_bounds__(BUILD_WARPS*32) k_build_lists(BuildArgs a) {
         const float dz = sqrtf(R2 - d2) + 1e-4f;
         const float zlo = loz - dz, zhi = hiz + dz;
         for (int kz = -1; kz <= 1; kz++) {
+            if (!a.periodic && kz != 0) continue;
             const float segLo = fmaxf(zlo, kz*a.Lz) - kz*a.Lz, segHi = fminf(zhi, (kz+1)*a.Lz) - kz*a.Lz;
             if (segHi < segLo) continue;
             const int zb0 = max(0, min(a.nzb-1, (int) floorf(segLo/a.binH)));
@@ -187,10 +190,11 @@ int launchBuildLists(Context& c) {
     a.N = c.N; a.maxBlocks = c.maxBlocks; a.capJ = c.capJ; a.capX = c.capX;
     a.blockPeriod = c.blockPeriod; a.blockOffset = c.blockOffset; a.blockWidth = c.blockWidth;
     a.ncx = g.ncx; a.ncy = g.ncy; a.nzb = g.nzb;
+    a.periodic = c.periodic ? 1 : 0;
     a.colWx = g.colW[0]; a.colWy = g.colW[1]; a.binH = g.binH;
     a.Lx = (float) g.box[0]; a.Ly = (float) g.box[1]; a.Lz = (float) g.box[2];
     a.sx = g.scale[0]; a.sy = g.scale[1]; a.sz = g.scale[2];
-    a.reach = (float) c.cutoff + 2e-4f;
+    a.reach = (float) c.cutoffEff + 2e-4f;
     a.counters = c.dCounters.d;
     a.blkFirst = c.dBlkFirst.d; a.blkCount = c.dBlkCount.d; a.blkLo = c.dBlkLo.d; a.blkHi = c.dBlkHi.d;
     a.binStart = c.dBinStart.d;

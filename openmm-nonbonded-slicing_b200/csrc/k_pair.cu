@@ -562,17 +562,19 @@ int launchPairs(Context& c, bool wantEnergy, int mode) {
     a.nE = 2*c.nSl;
     a.sx = g.scale[0]; a.sy = g.scale[1]; a.sz = g.scale[2];
     a.dsx = g.box[0]/4294967296.0; a.dsy = g.box[1]/4294967296.0; a.dsz = g.box[2]/4294967296.0;
-    a.rc2 = (float) (c.cutoff*c.cutoff);
-    a.rc2d = c.cutoff*c.cutoff;
+    // NoCutoff: every pair interacts; the bound only has to exclude the padding lanes (parked at 1e8 nm)
+    const bool noCutoff = c.method == NBS_METHOD_NOCUTOFF;
+    a.rc2 = noCutoff ? 1.0e12f : (float) (c.cutoff*c.cutoff);
+    a.rc2d = noCutoff ? 1.0e12 : c.cutoff*c.cutoff;
     a.alphaD = c.alpha;
-    a.krfD = pow(c.cutoff, -3.0)*(c.rfDielectric - 1.0)/(2.0*c.rfDielectric + 1.0);
-    a.crfD = (1.0/c.cutoff)*(3.0*c.rfDielectric)/(2.0*c.rfDielectric + 1.0);
+    // reaction field only with a cutoff: ReferenceSlicedLJCoulombIxn::setUseCutoff, ReferenceSlicedLJCoulombIxn.cpp:60-68
+    a.krfD = noCutoff ? 0.0 : pow(c.cutoff, -3.0)*(c.rfDielectric - 1.0)/(2.0*c.rfDielectric + 1.0);
+    a.crfD = noCutoff ? 0.0 : (1.0/c.cutoff)*(3.0*c.rfDielectric)/(2.0*c.rfDielectric + 1.0);
     a.q64 = c.dQ64.d;
     a.erfcTab = c.dErfcTab.d;
     a.alpha = (float) c.alpha;
-    // ReferenceSlicedLJCoulombIxn::setUseCutoff, ReferenceSlicedLJCoulombIxn.cpp:60-68
-    a.krf = (float) (pow(c.cutoff, -3.0)*(c.rfDielectric - 1.0)/(2.0*c.rfDielectric + 1.0));
-    a.crf = (float) ((1.0/c.cutoff)*(3.0*c.rfDielectric)/(2.0*c.rfDielectric + 1.0));
+    a.krf = (float) a.krfD;
+    a.crf = (float) a.crfD;
     a.useSwitch = c.useSwitch ? 1 : 0;
     a.rswitch = (float) c.switchDist;
     a.rcut = (float) c.cutoff;

@@ -16,7 +16,7 @@ namespace nbs {
 // fixed-point fractional coordinates and counts the atom into its (column, z-bin).
 // ---------------------------------------------------------------------------------------------
 __global__ void k_prep(int N, const double* __restrict__ pos64, const float4* __restrict__ pos32,
-                       const double4* __restrict__ pos64w, const int* __restrict__ atomIndex, double3 invBox,
+                       const double4* __restrict__ pos64w, const int* __restrict__ atomIndex, double3 invBox, double3 origin,
                        int ncx, int ncy, int nzb, uint4* __restrict__ fix, int* __restrict__ binCount,
                        double* __restrict__ pos64out) {
     int slot = blockIdx.x*blockDim.x + threadIdx.x;
@@ -29,7 +29,7 @@ __global__ void k_prep(int N, const double* __restrict__ pos64, const float4* __
     if (pos64out) {          // particle-ordered, unwrapped, double: what the exception kernel reads
         pos64out[3*particle] = x; pos64out[3*particle+1] = y; pos64out[3*particle+2] = z;
     }
-    double fx = x*invBox.x, fy = y*invBox.y, fz = z*invBox.z;
+    double fx = (x - origin.x)*invBox.x, fy = (y - origin.y)*invBox.y, fz = (z - origin.z)*invBox.z;
     fx -= floor(fx); fy -= floor(fy); fz -= floor(fz);
     unsigned ux = (unsigned) (__double2ull_rd(fx*4294967296.0) & 0xffffffffull);
     unsigned uy = (unsigned) (__double2ull_rd(fy*4294967296.0) & 0xffffffffull);
@@ -222,6 +222,48 @@ __global__ void k_excl_range(int N, const float4* __restrict__ par, const int* _
     exclRange[j] = make_int2(lo, hi);
 }
 
+// Bounding box of the input positions (non-periodic methods build a virtual box around the system).
+__global__ void __launch_bounds__(1024) k_bbox(int N, const double* __restrict__ pos64, const float4* __restrict__ pos32,
+                                              const double4* __restrict__ pos64w, float* __restrict__ out) {
+    __shared__ float red[6][32];
+    float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+        float v[3];
+        if (pos64) { v[0] = (float) pos64[3*i]; v[1] = (float) pos64[3*i+1]; v[2] = (float) pos64[3*i+2]; }
+        else if (pos64w) { double4 p = pos64w[i]; v[0] = (float) p.x; v[1] = (float) p.y; v[2] = (float) p.z; }
+        else { float4 p = pos32[i]; v[0] = p.x; v[1] = p.y; v[2] = p.z; }
+#pragma unroll
+        for (int d = 0; d < 3; d++) { lo[d] = fminf(lo[d], v[d]); hi[d] = fmaxf(hi[d], v[d]); }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+            hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+        }
+        if (lane == 0) { red[d][warp] = lo[d]; red[3+d][warp] = hi[d]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        float r = red[threadIdx.x][0];
+        for (int w = 1; w < (int) (blockDim.x >> 5); w++) r = threadIdx.x < 3 ? fminf(r, red[threadIdx.x][w]) : fmaxf(r, red[threadIdx.x][w]);
+        out[threadIdx.x] = r;
+    }
+}
+
+int launchBBox(Context& c, const PosInput& in, float out[6]) {
+    NBS_CUDA_CHECK(c.dBBox.ensure(8));
+    k_bbox<<<1, 1024, 0, c.stream>>>(c.N, in.format == NBS_POS_F64_XYZ ? (const double*) in.ptr : nullptr,
+                                     in.format == NBS_POS_F32_XYZW ? (const float4*) in.ptr : nullptr,
+                                     in.format == NBS_POS_F64_XYZW ? (const double4*) in.ptr : nullptr, c.dBBox.d);
+    c.launches++;
+    NBS_CUDA_CHECK(cudaMemcpyAsync(out, c.dBBox.d, 6*sizeof(float), cudaMemcpyDeviceToHost, c.stream));
+    NBS_CUDA_CHECK(cudaStreamSynchronize(c.stream));
+    return NBS_OK;
+}
+
 // Fixed-point conversion + bin histogram (everything downstream -- the rest of the sort AND the PME chain of small
 // systems -- starts from its output).
 int launchPrep(Context& c, const PosInput& in) {
@@ -234,7 +276,8 @@ int launchPrep(Context& c, const PosInput& in) {
     k_prep<<<(N+T-1)/T, T, 0, st>>>(N, in.format == NBS_POS_F64_XYZ ? (const double*) in.ptr : nullptr,
                                     in.format == NBS_POS_F32_XYZW ? (const float4*) in.ptr : nullptr,
                                     in.format == NBS_POS_F64_XYZW ? (const double4*) in.ptr : nullptr, in.atomIndex,
-                                    make_double3(g.invBox[0], g.invBox[1], g.invBox[2]), g.ncx, g.ncy, g.nzb,
+                                    make_double3(g.invBox[0], g.invBox[1], g.invBox[2]),
+                                    make_double3(g.origin[0], g.origin[1], g.origin[2]), g.ncx, g.ncy, g.nzb,
                                     c.dFix.d, c.dBinCount.d, in.pos64out);
     c.launches++;
     timerMark(c, "prep");

@@ -105,6 +105,8 @@ static int readDescription(Context& c, const nbs_system_desc& d, bool creating) 
         c.switchDist = d.switching_distance;
         c.rfDielectric = d.rf_dielectric;
         c.useSwitch = d.method != NBS_METHOD_NOCUTOFF && d.use_switching_function != 0;
+        c.periodic = d.method == NBS_METHOD_CUTOFF_PERIODIC || d.method == NBS_METHOD_PME;
+        c.cutoffEff = d.cutoff;
         c.excPeriodic = (d.method == NBS_METHOD_NOCUTOFF || d.method == NBS_METHOD_CUTOFF_NONPERIODIC) ? false : d.exceptions_use_periodic != 0;
         for (int k = 0; k < 3; k++) c.grid[k] = d.pme_grid[k];
         c.flags = d.flags;
@@ -302,14 +304,14 @@ static int buildErfcTable(Context& c) {
 }
 
 // cell geometry for this box: columns whose 32-atom blocks are roughly cubic, fine z-bins for sorting
-static int setupGeometry(Context& c, const double box[9]) {
+static int setupGeometry(Context& c, const double L[3], const double origin[3]) {
     CellGeom& g = c.geom;
-    const double L[3] = {box[0], box[4], box[8]};
     const double volume = L[0]*L[1]*L[2];
     const double density = c.N/volume;
     double side = std::cbrt(32.0/density);
-    side = std::max(side, 0.3*c.cutoff);
+    side = std::max(side, 0.3*c.cutoffEff);
     for (int k = 0; k < 3; k++) {
+        g.origin[k] = origin[k];
         g.box[k] = L[k];
         g.invBox[k] = 1.0/L[k];
         g.scale[k] = (float) (L[k]/4294967296.0);
@@ -429,13 +431,12 @@ int nbs_create(const nbs_system_desc* desc, nbs_context** out) {
     if (desc->struct_size != (int32_t) sizeof(nbs_system_desc)) return fail(NBS_ERR_INVALID, "nbs_system_desc.struct_size mismatch");
     switch (desc->method) {
         case NBS_METHOD_PME: case NBS_METHOD_CUTOFF_PERIODIC: break;
-        case NBS_METHOD_NOCUTOFF: case NBS_METHOD_CUTOFF_NONPERIODIC:
-            return fail(NBS_ERR_UNSUPPORTED, "non-periodic nonbonded methods are not implemented on this platform yet");
+        case NBS_METHOD_NOCUTOFF: case NBS_METHOD_CUTOFF_NONPERIODIC: break;
         case NBS_METHOD_EWALD: case NBS_METHOD_LJPME:
             return fail(NBS_ERR_UNSUPPORTED, "Ewald and LJPME are not implemented on this platform (PME only)");
         default: return fail(NBS_ERR_INVALID, "illegal nonbonded method");
     }
-    if (desc->cutoff <= 0) return fail(NBS_ERR_INVALID, "cutoff must be positive");
+    if (desc->method != NBS_METHOD_NOCUTOFF && desc->cutoff <= 0) return fail(NBS_ERR_INVALID, "cutoff must be positive");
     int status = checkDevice(desc->device_index);
     if (status != NBS_OK) return status;
     nbs_context* ctx = new nbs_context();
@@ -523,12 +524,14 @@ int nbs_set_global_parameters(nbs_context* ctx, const double* values) {
 static int validateExec(Context& c, const nbs_exec_args* args) {
     if (args->struct_size != (int32_t) sizeof(nbs_exec_args)) return fail(NBS_ERR_INVALID, "nbs_exec_args.struct_size mismatch");
     const double* box = args->box;
-    if (box[1] != 0 || box[2] != 0 || box[3] != 0 || box[5] != 0 || box[6] != 0 || box[7] != 0)
-        return fail(NBS_ERR_UNSUPPORTED, "triclinic boxes are not implemented on this platform yet");
-    // ReferenceNonbondedSlicingKernels.cpp:200-204
-    const double minAllowedSize = 1.999999*c.cutoff;
-    if (box[0] < minAllowedSize || box[4] < minAllowedSize || box[8] < minAllowedSize)
-        return fail(NBS_ERR_BOX, "The periodic box size has decreased to less than twice the nonbonded cutoff.");
+    if (c.periodic) {
+        if (box[1] != 0 || box[2] != 0 || box[3] != 0 || box[5] != 0 || box[6] != 0 || box[7] != 0)
+            return fail(NBS_ERR_UNSUPPORTED, "triclinic boxes are not implemented on this platform yet");
+        // ReferenceNonbondedSlicingKernels.cpp:200-204
+        const double minAllowedSize = 1.999999*c.cutoff;
+        if (box[0] < minAllowedSize || box[4] < minAllowedSize || box[8] < minAllowedSize)
+            return fail(NBS_ERR_BOX, "The periodic box size has decreased to less than twice the nonbonded cutoff.");
+    }
     if (!args->positions) return fail(NBS_ERR_INVALID, "positions is null");
     if (args->positions_format != NBS_POS_F64_XYZ && args->positions_space != NBS_MEM_DEVICE)
         return fail(NBS_ERR_INVALID, "xyzw positions must be device memory");
@@ -565,7 +568,6 @@ static int phaseBegin(Context& c, const nbs_exec_args* args) {
     c.phase = 0;
     const int N = c.N;
     if (c.paramsDirty && (status = applyParameters(c)) != NBS_OK) return status;
-    if ((status = setupGeometry(c, box)) != NBS_OK) return status;
     timerReset(c);
     timerMark(c, "begin");
     // positions
@@ -588,6 +590,31 @@ static int phaseBegin(Context& c, const nbs_exec_args* args) {
             in.pos64out = c.dPosIn.d;
             dPos64 = c.dPosIn.d;
         }
+    }
+    {
+        // the box the cell grid and the fixed-point coordinates live in: the periodic box, or -- NoCutoff /
+        // CutoffNonPeriodic -- a virtual box twice the size of the system around its bounding box, in which no
+        // coordinate difference ever wraps (the wrapped integer difference is then the plain difference)
+        double L[3] = {box[0], box[4], box[8]}, origin[3] = {0, 0, 0};
+        if (!c.periodic) {
+            float bb[6];
+            if (args->positions_space == NBS_MEM_HOST) {
+                const double* p = (const double*) args->positions;
+                for (int d = 0; d < 3; d++) { bb[d] = 3.0e38f; bb[3+d] = -3.0e38f; }
+                for (int i = 0; i < N; i++)
+                    for (int d = 0; d < 3; d++) { bb[d] = std::min(bb[d], (float) p[3*i+d]); bb[3+d] = std::max(bb[3+d], (float) p[3*i+d]); }
+            }
+            else if ((status = launchBBox(c, in, bb)) != NBS_OK) return status;
+            double diag2 = 0;
+            for (int d = 0; d < 3; d++) {
+                const double extent = std::max(1.0e-3, (double) bb[3+d] - (double) bb[d]);
+                L[d] = 2.0*extent + 4.0;                          // >= 2 x (extent + margin): differences stay below L/2
+                origin[d] = 0.5*((double) bb[d] + (double) bb[3+d]) - 0.5*L[d];
+                diag2 += extent*extent;
+            }
+            c.cutoffEff = c.method == NBS_METHOD_NOCUTOFF ? std::sqrt(diag2) + 1.0 : c.cutoff;
+        }
+        if ((status = setupGeometry(c, L, origin)) != NBS_OK) return status;
     }
     NBS_CUDA_CHECK(cudaMemsetAsync(c.dForce.d, 0, sizeof(unsigned long long)*(c.pmeUnsorted ? 6 : 3)*c.Npad, st));
     NBS_CUDA_CHECK(cudaMemsetAsync(c.dEnergy.d, 0, sizeof(double)*ENERGY_WORDS, st));
@@ -618,7 +645,7 @@ static int phaseBegin(Context& c, const nbs_exec_args* args) {
             cudaEventRecord(c.evAuxFork, c.directStream);
             cudaStreamWaitEvent(c.auxStream, c.evAuxFork, 0);
             c.stream = c.auxStream;
-            status = launchBonded(c, dPos64, true);
+            status = launchBonded(c, dPos64, c.periodic);
             cudaEventRecord(c.evAuxDone, c.auxStream);
             c.stream = c.directStream;
         }
@@ -626,7 +653,7 @@ static int phaseBegin(Context& c, const nbs_exec_args* args) {
         if (status == NBS_OK) status = launchPairs(c, c.phaseEnergy, 0);
         if (status == NBS_OK && c.nExc > 0 && !forkBonded) {
             if (!dPos64) status = fail(NBS_ERR_UNSUPPORTED, "exceptions need double-precision positions in this version");
-            else status = launchBonded(c, dPos64, true);
+            else status = launchBonded(c, dPos64, c.periodic);
         }
         if (forkBonded) cudaStreamWaitEvent(c.directStream, c.evAuxDone, 0);
     }
@@ -728,7 +755,7 @@ static int phaseComplete(Context& c, const nbs_exec_args* args) {
                     E[2*(j*(j+1)/2+i)] += (i == j ? 1 : 2)*c.subsetQ[i]*c.subsetQ[j]*factor;
             }
         }
-        if (c.phaseDirect)   // dispersion correction, ReferenceNonbondedSlicingKernels.cpp:244-249
+        if (c.phaseDirect && c.periodic)   // dispersion correction (periodic methods only), ReferenceNonbondedSlicingKernels.cpp:244-249
             for (int s = 0; s < c.nSl; s++) E[2*s+1] += c.dispersion[s]/volume;
     }
     return NBS_OK;
@@ -777,7 +804,7 @@ int nbs_execute(nbs_context* ctx, const nbs_exec_args* args) {
     if (c.nRanks != 1) return fail(NBS_ERR_INVALID, "a sharded context is driven through nbs_execute_begin/convolve/finish");
     // A whole evaluation is ~20 short kernels: once the same evaluation (same buffers, box, parameters) has
     // run once, it is captured into a CUDA graph and replayed, which removes the per-launch gaps.
-    bool graphable = !(c.flags & NBS_FLAG_NO_GRAPH) && !c.profiling && !c.paramsDirty && workStream(c, args) != nullptr;
+    bool graphable = !(c.flags & NBS_FLAG_NO_GRAPH) && !c.profiling && !c.paramsDirty && c.periodic && workStream(c, args) != nullptr;
     if (graphable && args->positions_space == NBS_MEM_HOST) graphable = hostPointerIsPinned(args->positions);
     if (graphable && args->forces && args->forces_space == NBS_MEM_HOST && !args->forces_accumulate)
         graphable = hostPointerIsPinned(args->forces);       // (accumulation goes through our own pinned staging buffer)

@@ -71,7 +71,8 @@ struct LambdaTable {                 // passed by value to kernels
 };
 
 struct CellGeom {                    // cell / column geometry of one evaluation (rectangular box)
-    double box[3];                   // Lx, Ly, Lz
+    double box[3];                   // Lx, Ly, Lz (non-periodic methods: a virtual box twice the size of the system)
+    double origin[3];                // coordinate that maps to fractional 0 (0 for periodic boxes)
     double invBox[3];
     float scale[3];                  // L / 2^32 (fixed-point unit in nm)
     int ncx, ncy, nzb;               // columns in x, y; z-bins per column
@@ -91,6 +92,8 @@ struct Context {
     uint32_t flags = 0;
     double cutoff = 0, alpha = 0, switchDist = 0, rfDielectric = 78.3;
     bool useSwitch = false, excPeriodic = false;
+    bool periodic = true;                    // CutoffPeriodic / PME; false for NoCutoff / CutoffNonPeriodic
+    double cutoffEff = 0;                    // the cutoff, or (NoCutoff) a distance no pair of the system exceeds
     int grid[3] = {0, 0, 0};
     std::vector<int> subsets;
     std::vector<double> baseQ, baseSig, baseEps;
@@ -115,6 +118,7 @@ struct Context {
     Buf<double4> dExcParam;                  // [nExc] (sigma, 4eps, K*qq, is14 ? 1 : 0)
     Buf<int> dExcSlice;
     // ---- per-evaluation device data ----
+    Buf<float> dBBox;                        // [6] bounding box of the input positions (non-periodic methods)
     Buf<double> dPosIn;                      // staged positions when the caller's are on the host
     Buf<double> dForceOut;                   // staged forces when the caller's are on the host
     Buf<uint4> dFix;                         // original order: fixed-point xyz, w = bin
@@ -199,6 +203,7 @@ __host__ __device__ inline int localToGlobalBlock(int local, int period, int off
 // ---- launch wrappers (each counts its launches in ctx.launches) ----
 struct PosInput { const void* ptr; int format; const int* atomIndex; double* pos64out; };
 
+int launchBBox(Context& c, const PosInput& in, float out[6]);    // bounding box of device positions (synchronises)
 int launchPrep(Context& c, const PosInput& in);                 // fixed-point conversion, bin histogram
 int launchSortRest(Context& c);                                 // cell sort, sorted records, i-blocks
 int launchBuildLists(Context& c);

@@ -324,10 +324,25 @@ def bench_main(args, workload_name):
         k.prepare(pos_dev.data_ptr(), s.box, frc_dev.data_ptr(), lam, stream=stream)
         return evaluate_distributed(ShardPlan(1, ns), 0, k, dist, None)
 
-    # rank 0 calibrates, everybody adopts its plan
+    # rank 0 calibrates, everybody adopts its plan; it also times the SAME workload unsharded on its one GPU, so
+    # that the line carries its own strong-scaling reference point
     payload = [None]
     if rank == 0:
         plan, calibration = calibrate_plan(factory, world, ns, run_alone)
+        single = B200CalcSlicedNonbondedForceKernel(Platform(deviceIndex=local))
+        single.initialize(s.system, s.force)
+        single_ms = []
+        for it in range(6):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a.record()
+            single.execute_device(pos_dev.data_ptr(), s.box, frc_dev.data_ptr(), lam, stream=stream)
+            b.record()
+            torch.cuda.synchronize()
+            if it >= 3:
+                single_ms.append(a.elapsed_time(b))
+        del single
+        calibration["single_gpu_ms_per_step"] = float(np.mean(single_ms))
         payload = [(plan.widths, calibration)]
     dist.broadcast_object_list(payload, src=0)
     widths, calibration = payload[0]
@@ -407,6 +422,10 @@ def bench_main(args, workload_name):
             for name, t in prof.getKernelTimes():
                 acc[name] = acc.get(name, 0.0) + t/3
     del prof
+    # the roofline is reported for the rank whose pair kernel ran longest
+    shares = [None]*world
+    dist.all_gather_object(shares, (acc.get("pair", 0.0), local_pairs, rank))
+    slow_ms, slow_pairs, slow_rank = max(shares)
     checksum = float(np.abs(energies).sum())
     fsum = frc_dev.abs().sum().reshape(1)
     fmin, fmax = fsum.clone(), fsum.clone()
@@ -429,8 +448,11 @@ def bench_main(args, workload_name):
                     "d2h_bytes_per_step": int(frc_host.numel()*8 + 8*2*nsl), "ns_per_day_2fs": bench.ns_per_day(e2e_value),
                     "note": "per rank: every rank uploads all positions and downloads all forces"},
             "gpu_launches": int(launches),
-            "roofline": bench.pair_roofline(local_pairs, acc.get("pair", float("nan")), None,
-                                            note="rank 0's share of the i-blocks"),
+            "roofline": bench.pair_roofline(slow_pairs, slow_ms, None,
+                                            note=f"rank {slow_rank}'s share of the i-blocks (the longest pair kernel of the job)"),
+            "single_gpu_same_workload": {"ms_per_step": calibration["single_gpu_ms_per_step"],
+                                         "evals_per_s": 1e3/calibration["single_gpu_ms_per_step"],
+                                         "speedup": calibration["single_gpu_ms_per_step"]/ms},
             "kernel_ms_rank0": {k: round(v, 5) for k, v in acc.items()},
             "collectives_per_step": {"spectrum_broadcasts": ns if plan.num_pme_ranks > 1 else 0, "all_reduces": 2},
             "slice_energy_checksum": checksum,

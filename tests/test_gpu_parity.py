@@ -102,6 +102,63 @@ def test_baseline_configs_vs_oracle(nbs, platform, systems, oracle, name):
     three_way(kernel, kernel.desc, s.positions, s.box, lam, run)
 
 
+@pytest.mark.parametrize("method,n,switch", [("NoCutoff", 150, False), ("NoCutoff", 37, False), ("CutoffNonPeriodic", 400, False),
+                                              ("CutoffNonPeriodic", 333, True)])
+def test_nonperiodic_methods(nbs, platform, oracle, method, n, switch):
+    """NoCutoff and CutoffNonPeriodic (reaction field, optional switching function): a free cluster anywhere in
+    space, no box; 1-4 exceptions, offsets, three lambda settings; forces, slice energies, derivatives and the
+    interacting-pair set against the oracle (ReferenceSlicedLJCoulombIxn.cpp:571-631)."""
+    rng = np.random.default_rng(n)
+    nsub = 3
+    system = nbs.System()
+    force = nbs.SlicedNonbondedForce(nsub)
+    force.setNonbondedMethod(getattr(force, method))
+    force.setCutoffDistance(1.0)
+    if switch:
+        force.setUseSwitchingFunction(True)
+        force.setSwitchingDistance(0.8)
+    side = int(np.ceil(n**(1/3)))
+    sites = np.array([(i, j, k) for i in range(side) for j in range(side) for k in range(side)][:n], dtype=float)
+    positions = sites*0.31 + rng.uniform(-0.05, 0.05, size=(n, 3)) + np.array([17.0, -250.0, 3.3])
+    charges = rng.uniform(-0.8, 0.8, size=n)
+    for i in range(n):
+        system.addParticle(1.0)
+        force.addParticle(charges[i], rng.uniform(0.15, 0.3), rng.uniform(0.1, 1.0))
+        force.setParticleSubset(i, int(rng.integers(0, nsub)))
+    force.createExceptionsFromBonds([(i, i+1) for i in range(0, n-1) if i % 5 != 4], 1/1.2, 0.5)
+    force.addGlobalParameter("off", 0.3)
+    force.addParticleParameterOffset("off", 3, 0.5, 0.01, 0.2)
+    force.addExceptionParameterOffset("off", 2, 0.2, 0.01, 0.1)
+    force.addGlobalParameter("lc", 0.7)
+    force.addGlobalParameter("lv", 0.4)
+    force.addScalingParameter("lc", 0, 1, True, False)
+    force.addScalingParameter("lv", 0, 1, False, True)
+    force.addEnergyParameterDerivative("lc")
+    force.addEnergyParameterDerivative("lv")
+    system.addForce(force)
+    ctx = nbs.Context(system, platform)
+    ref = nbs.Context(system, oracle.OraclePlatform("port"))
+    for c in (ctx, ref):
+        c.setPositions(positions)
+    for lc, lv in ((0.7, 0.4), (0.0, 1.0), (1.0, 1.0)):
+        for c in (ctx, ref):
+            c.setParameter("lc", lc)
+            c.setParameter("lv", lv)
+        a = ctx.getState(getEnergy=True, getForces=True, getParameterDerivatives=True)
+        b = ref.getState(getEnergy=True, getForces=True, getParameterDerivatives=True)
+        assert force_rel_rms(a.getForces(), b.getForces()) <= F_TOL
+        check_energies(ctx.impls[0].kernel.lastSliceEnergies, ref.impls[0].kernel.lastSliceEnergies)
+        for name, value in b.getEnergyParameterDerivatives().items():
+            assert_equal_tol(value, a.getEnergyParameterDerivatives()[name], E_TOL)
+        r = ref.impls[0].kernel.lastResult
+        count, h, _ = ctx.impls[0].kernel.getPairSet(with_pairs=False)
+        if method == "NoCutoff":      # the reference loops over all pairs here (no neighbour list to compare with)
+            excluded = {(min(e[0], e[1]), max(e[0], e[1])) for e in force._exceptions}
+            assert count == n*(n-1)//2 - len(excluded)
+        else:
+            assert (count, h) == (r.pair_count, r.pair_hash)
+
+
 def test_pair_and_exclusion_lists_exact(nbs, platform, systems, oracle):
     """The sorted pair list itself (not just its hash) and the exclusion set, on C1 and a random system."""
     s = systems.make_system("C1")

@@ -621,12 +621,16 @@ int launchPlaneFft(Context& c, const PlaneFftPlan& plan, PlaneFftArgs a, int hal
         const int nb = n/rmin;                                 // butterflies per line in the widest pass
         const int rounds = (lines*nb + cap - 1)/cap;
         const int linesPerRound = (lines + rounds - 1)/rounds;
-        return std::min(cap, std::max(128, ((linesPerRound*nb + 31)/32)*32));
+        return std::min(cap, std::max(64, ((linesPerRound*nb + 31)/32)*32));
     };
-    a.planeThreads = pickThreads(a.slabPairs, nz, plan.factors[2], FFT_THREADS);
-    if (a.slabsPerPlane == 1) a.planeThreads = std::max(a.planeThreads, pickThreads(nzh, ny, plan.factors[1], FFT_THREADS));
+    int planeCap = 256;                      // measured at 64^3 double: 256-thread CTAs beat 512 (20.5 vs 24.6 us zy forward)
+    if (const char* env = getenv("NBS_FFT_PLANE_THREADS")) planeCap = std::max(128, std::min(FFT_THREADS, atoi(env)));   // tuning experiments
+    a.planeThreads = pickThreads(a.slabPairs, nz, plan.factors[2], planeCap);
+    if (a.slabsPerPlane == 1) a.planeThreads = std::max(a.planeThreads, pickThreads(nzh, ny, plan.factors[1], planeCap));
     a.colThreads = pickThreads(a.colChunk, ny, plan.factors[1], FFT_THREADS);
-    a.xThreads = pickThreads(c.nS*chunk, nx, plan.factors[0], FFT_X_THREADS);
+    int xCap = FFT_X_THREADS;
+    if (const char* env = getenv("NBS_FFT_X_THREADS")) xCap = std::max(64, std::min(FFT_X_THREADS, atoi(env)));           // tuning experiments
+    a.xThreads = pickThreads(c.nS*chunk, nx, plan.factors[0], xCap);
     if (nzh > 128*FFT_UNPACK_Q || nz/2 > a.planeThreads || ny/2 > std::min(a.planeThreads, a.colThreads) || nx/2 > a.xThreads) return NBS_RETRY;
     a.rowStride = rs;
     a.chunk = chunk;

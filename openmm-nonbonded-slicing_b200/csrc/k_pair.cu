@@ -32,6 +32,7 @@
 #include "nbs_internal.h"
 #include "nbs_device.cuh"
 #include <algorithm>
+#include <cstdlib>
 
 // tuning knobs (profiles/README.md has the measurements behind the defaults)
 #ifndef PAIR_MIN_CTAS
@@ -547,6 +548,7 @@ static int launchPairT(Context& c, const PairArgs& a) {
         int n = 0;
         NBS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_pair<EMODE, IS_PME, MODE>, PAIR_WARPS*32, smem));
         perSM[c.device & 63] = std::max(1, n);
+        if (const char* env = getenv("NBS_PAIR_CTAS_PER_SM")) perSM[c.device & 63] = std::max(1, std::min(n, atoi(env)));   // tuning experiments
     }
     k_pair<EMODE, IS_PME, MODE><<<perSM[c.device & 63]*c.numSMs, PAIR_WARPS*32, smem, c.stream>>>(a);
     return NBS_OK;

@@ -50,18 +50,45 @@ def parse_args():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """Samples SM clocks / throttle reasons while the timed region runs: NVML every millisecond when the
+    binding is importable (the timed region of a small workload lasts only milliseconds), else nvidia-smi."""
     QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index=0):
         self.samples, self.stop, self.index = [], threading.Event(), index
         self.thread = threading.Thread(target=self._run, daemon=True)
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        n = self.nvml
+        mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+        try:
+            bits = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:
+            bits = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        flags = [bool(bits & getattr(n, name, 0)) for name in
+                 ("nvmlClocksThrottleReasonHwSlowdown", "nvmlClocksThrottleReasonHwThermalSlowdown",
+                  "nvmlClocksThrottleReasonSwThermalSlowdown", "nvmlClocksThrottleReasonSwPowerCap")]
+        return [str(mhz), str(self.max_mhz), ""] + ["Active" if f else "Not Active" for f in flags]
 
     def _run(self):
         while not self.stop.is_set():
             try:
+                if self.nvml is not None:
+                    self.samples.append(self._sample_nvml())
+                    self.stop.wait(0.001)
+                    continue
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-i", str(self.index)],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
                 if out:
@@ -82,10 +109,9 @@ class ClockSampler:
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
         sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(len(s) > 3+k and s[3+k].lower().startswith("active") for s in self.samples)]
+        reasons = [n for k, n in enumerate(self.NAMES) if any(len(s) > 3+k and s[3+k].lower().startswith("active") for s in self.samples)]
         return {"sm_mhz": sm[len(sm)//2] if sm else None, "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
-                "samples": len(self.samples)}
+                "samples": len(self.samples), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def pair_roofline(pair_count, pair_ms, tile_efficiency, traffic=None, note=None):
@@ -253,6 +279,23 @@ def main():
     ms = float(np.mean(per_step))
     value = 1e3/ms
 
+    # ---- the same evaluation without slice energies (what an MD step between reports asks for) --------
+    forces_only = []
+    for it in range(args.warmup + args.steps):
+        flush.fill_(1)
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        start.record()
+        kernel.execute_device(pos_dev.data_ptr(), s.box, frc_dev.data_ptr(), lam, stream=stream, want_energies=False)
+        end.record()
+        torch.cuda.synchronize()
+        if it >= args.warmup:
+            forces_only.append(start.elapsed_time(end))
+    forces_ms = float(np.mean(forces_only))
+    # leave the force buffer as the full evaluation produced it (the parity check below reads it)
+    step_device()
+    torch.cuda.synchronize()
+
     # ---- end to end through the host-buffer API (what a plugin user calls) ---------------------
     pos_host = torch.tensor(s.positions, dtype=torch.float64).pin_memory()
     frc_host = torch.zeros((n, 3), dtype=torch.float64).pin_memory()
@@ -315,6 +358,8 @@ def main():
         "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(pos_np.nbytes),
                 "d2h_bytes_per_step": int(frc_np.nbytes + 8*2*36 + 64), "ns_per_day_2fs": ns_per_day(e2e_value)},
         "gpu_launches": int(launches),
+        "forces_only": {"ms_per_step": forces_ms, "value": 1e3/forces_ms, "unit": "evals/s", "ns_per_day_2fs": ns_per_day(1e3/forces_ms),
+                        "note": "same evaluation without slice energies / dE/dlambda (single-precision PME grids, no double-precision pair energies)"},
         "roofline": roofline,
         "roofline_pme": roofline_pme,
         "kernel_ms": {k: round(v, 5) for k, v in acc.items()},

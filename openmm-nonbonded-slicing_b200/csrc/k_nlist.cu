@@ -20,6 +20,7 @@
 
 namespace nbs {
 
+constexpr int NL_PREFETCH = 4;  // 32-atom chunks of a column range whose loads are in flight together
 constexpr int JBUF = 768;      // per-warp staging capacity (entries)
 constexpr int XBUF = 96;
 
@@ -96,13 +97,26 @@ __global__ void __launch_bounds__(BUILD_WARPS*32) k_build_lists(BuildArgs a) {
             if (colJ == colI) s = max(s, first);                           // j must not precede the block
             const long long shx = (long long) kx << 32, shy = (long long) ky << 32, shz = (long long) kz << 32;
             const int code = ((kx+1) + 3*(ky+1) + 9*(kz+1)) << J_SHIFT_BITS;
-            for (int j0 = s; j0 < e; j0 += 32) {
+            for (int jb = s; jb < e; jb += 32*NL_PREFETCH) {
+              // the candidates' positions and exclusion ranges of NL_PREFETCH chunks are requested together: the
+              // walk is a chain of L2 round trips, and the ballots below only order the OUTPUT, not the loads
+              uint4 qv[NL_PREFETCH];
+              int2 rv[NL_PREFETCH];
+#pragma unroll
+              for (int u = 0; u < NL_PREFETCH; u++) {
+                  const int j = jb + 32*u + lane;
+                  if (j < e) { qv[u] = a.posq[j]; rv[u] = a.exclRange[j]; }
+              }
+#pragma unroll
+              for (int u = 0; u < NL_PREFETCH; u++) {
+                const int j0 = jb + 32*u;
+                if (j0 >= e) break;                                        // warp-uniform
                 const int j = j0 + lane;
                 bool pass = false;
                 unsigned imask = 0;
                 if (j < e) {
-                    const uint4 q = a.posq[j];
-                    const int2 range = a.exclRange[j];          // issued with the position: one latency, not two
+                    const uint4 q = qv[u];
+                    const int2 range = rv[u];
                     const float rx = (float) ((long long) q.x + shx - (long long) lo.x)*a.sx;
                     const float ry = (float) ((long long) q.y + shy - (long long) lo.y)*a.sy;
                     const float rz = (float) ((long long) q.z + shz - (long long) lo.z)*a.sz;
@@ -137,6 +151,7 @@ __global__ void __launch_bounds__(BUILD_WARPS*32) k_build_lists(BuildArgs a) {
                 }
                 nj += __popc(mJ);
                 nx += __popc(mX);
+              }
             }
         }
     }

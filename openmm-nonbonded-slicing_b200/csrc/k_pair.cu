@@ -341,8 +341,10 @@ __device__ __forceinline__ void tileLoop(WarpScratch& w, const PairArgs& a, cons
 
 // MODE 0: forces (+ energies per EMODE); MODE 1: count + hash the interacting pairs; MODE 2: also dump them.
 // EMODE 0: forces only; 1: single-precision energies; 2: double-precision energies.
-template <int EMODE, bool IS_PME, int MODE>
-__global__ void __launch_bounds__(PAIR_WARPS*32, PAIR_MIN_CTAS) k_pair(const PairArgs a) {
+// MINCTAS: resident CTAs per SM the register allocation is bounded for (2: 128 registers; 3: 80 registers and a
+// few bytes of spill -- no different at DHFR size, 8 % faster at STMV size, where there is always a next item)
+template <int EMODE, bool IS_PME, int MODE, int MINCTAS>
+__global__ void __launch_bounds__(PAIR_WARPS*32, MINCTAS) k_pair(const PairArgs a) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     __shared__ float2 shLam[MAX_SUBSETS*MAX_SUBSETS];      // (lambda_Coulomb, lambda_vdW) of subset pair (si, sj)
     __shared__ double shE[MAX_SLICES*2];
@@ -534,24 +536,29 @@ __global__ void __launch_bounds__(PAIR_WARPS*32, PAIR_MIN_CTAS) k_pair(const Pai
     }
 }
 
-template <int EMODE, bool IS_PME, int MODE>
-static int launchPairT(Context& c, const PairArgs& a) {
+template <int EMODE, bool IS_PME, int MODE, int MINCTAS>
+static int launchPairK(Context& c, const PairArgs& a) {
     static bool attr[64] = {false};
     const size_t smem = sizeof(WarpScratch)*PAIR_WARPS;
     if (!attr[c.device & 63]) {
-        NBS_CUDA_CHECK(cudaFuncSetAttribute(k_pair<EMODE, IS_PME, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        NBS_CUDA_CHECK(cudaFuncSetAttribute(k_pair<EMODE, IS_PME, MODE, MINCTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         attr[c.device & 63] = true;
     }
     // persistent grid: as many CTAs as are resident at once
     static int perSM[64] = {0};
     if (perSM[c.device & 63] == 0) {
         int n = 0;
-        NBS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_pair<EMODE, IS_PME, MODE>, PAIR_WARPS*32, smem));
+        NBS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_pair<EMODE, IS_PME, MODE, MINCTAS>, PAIR_WARPS*32, smem));
         perSM[c.device & 63] = std::max(1, n);
-        if (const char* env = getenv("NBS_PAIR_CTAS_PER_SM")) perSM[c.device & 63] = std::max(1, std::min(n, atoi(env)));   // tuning experiments
     }
-    k_pair<EMODE, IS_PME, MODE><<<perSM[c.device & 63]*c.numSMs, PAIR_WARPS*32, smem, c.stream>>>(a);
+    k_pair<EMODE, IS_PME, MODE, MINCTAS><<<perSM[c.device & 63]*c.numSMs, PAIR_WARPS*32, smem, c.stream>>>(a);
     return NBS_OK;
+}
+
+template <int EMODE, bool IS_PME, int MODE>
+static int launchPairT(Context& c, const PairArgs& a) {
+    if (MODE == 0 && c.N >= 300000) return launchPairK<EMODE, IS_PME, MODE, 3>(c, a);
+    return launchPairK<EMODE, IS_PME, MODE, PAIR_MIN_CTAS>(c, a);
 }
 
 int launchPairs(Context& c, bool wantEnergy, int mode) {

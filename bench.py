@@ -97,6 +97,14 @@ class ClockSampler:
                 pass
             self.stop.wait(0.1)
 
+    def sample_now(self):
+        """One sample from the calling thread (the background thread can be starved by a busy timed loop)."""
+        try:
+            if self.nvml is not None:
+                self.samples.append(self._sample_nvml())
+        except Exception:
+            pass
+
     def __enter__(self):
         self.thread.start()
         return self
@@ -272,6 +280,7 @@ def main():
             start.record()
             energies = step_device()
             end.record()
+            clocks.sample_now()                      # while the step is still running on the device
             torch.cuda.synchronize()
             per_step.append(start.elapsed_time(end))
         t_wall = time.perf_counter()-t_wall0

@@ -376,6 +376,8 @@ def bench_main(args, workload_name):
         start.record()
         energies = step()
         end.record()
+        if sampler:
+            sampler.sample_now()
         torch.cuda.synchronize()
         per_step.append(start.elapsed_time(end))
     if sampler:

@@ -280,7 +280,7 @@ def main():
             start.record()
             energies = step_device()
             end.record()
-            clocks.sample_now()                      # while the step is still running on the device
+            clocks.sample_now()                      # right after the step (the call is synchronous; boost state outlives it)
             torch.cuda.synchronize()
             per_step.append(start.elapsed_time(end))
         t_wall = time.perf_counter()-t_wall0

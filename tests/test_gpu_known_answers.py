@@ -32,3 +32,10 @@ def test_triclinic_is_refused_not_faked(nbs, b200):
     with pytest.raises(Exception) as info:
         golden.test_triclinic(nbs, b200)
     assert "triclinic" in str(info.value).lower()
+
+
+def test_slicing_equals_rescaled_parameters_on_device(nbs, b200):
+    """testNonbondedSlicing (:1031-1318) with both the sliced force and the rescaled plain force on the device:
+    E and F at lambda = 1, 0, 0.5 agree, and the slice derivatives sum to E(1) - E(0)."""
+    from test_oracle_fixtures import slicing_equals_rescaled_parameters
+    slicing_equals_rescaled_parameters(nbs, b200, 1e-5, 1e-5)

@@ -98,8 +98,13 @@ def test_dispersion_coefficients_agree(nbs, oracle, systems):
 
 
 def test_slicing_equals_rescaled_parameters(nbs, oracle):
+    slicing_equals_rescaled_parameters(nbs, oracle.OraclePlatform("port"), 1e-9, 1e-9)
+
+
+def slicing_equals_rescaled_parameters(nbs, platform, etol, ftol):
     """testNonbondedSlicing (:1031-1318): scaling slice (0,1) and (1,1) by lambda equals a one-subset
-    force whose subset-1 charges are scaled (Coulomb case); sum of all slice derivatives = energy."""
+    force whose subset-1 charges are scaled (Coulomb case); sum of all slice derivatives = energy.
+    Both Contexts run on `platform` (an oracle, or the B200 platform in test_gpu_known_answers.py)."""
     rng = np.random.default_rng(7)
     n, L = 200, 7.0
     system1, system2 = nbs.System(), nbs.System()
@@ -133,7 +138,6 @@ def test_slicing_equals_rescaled_parameters(nbs, oracle):
     sliced.addScalingParameter("lambdaSq", 1, 1, True, False)
     system1.addForce(plain)
     system2.addForce(sliced)
-    platform = oracle.OraclePlatform("port")
     ctx2 = nbs.Context(system2, platform)
     ctx2.setPositions(positions)
     energies = {}
@@ -155,8 +159,8 @@ def test_slicing_equals_rescaled_parameters(nbs, oracle):
         for groups in (0xFFFFFFFF,):
             s1 = ctx1.getState(getEnergy=True, getForces=True, groups=groups)
             s2 = ctx2.getState(getEnergy=True, getForces=True, groups=groups)
-            assert_equal_tol(s1.getPotentialEnergy(), s2.getPotentialEnergy(), 1e-9)
-            assert force_rel_rms(s2.getForces(), s1.getForces()) < 1e-9
+            assert_equal_tol(s1.getPotentialEnergy(), s2.getPotentialEnergy(), etol)
+            assert force_rel_rms(s2.getForces(), s1.getForces()) < ftol
         energies[lam] = s2.getPotentialEnergy()
     # derivatives (:1279-1317)
     sliced.addEnergyParameterDerivative("lambda")
@@ -169,4 +173,4 @@ def test_slicing_equals_rescaled_parameters(nbs, oracle):
     ctx2.setParameter("lambdaSq", 1.0)
     d = ctx2.getState(getEnergy=True, getParameterDerivatives=True)
     derivs = d.getEnergyParameterDerivatives()
-    assert_equal_tol(energies[1.0]-energies[0.0], derivs["lambda"]+derivs["lambdaSq"], 1e-9)
+    assert_equal_tol(energies[1.0]-energies[0.0], derivs["lambda"]+derivs["lambdaSq"], etol)

@@ -18,6 +18,8 @@
  *                              (NonbondedSlicingKernels.h:66; ReferenceNonbondedSlicingKernels.cpp:270-319)
  *   nbs_get_pme_parameters  <- CalcSlicedNonbondedForceKernel::getPMEParameters
  *                              (NonbondedSlicingKernels.h:75; ReferenceNonbondedSlicingKernels.cpp:321-328)
+ *   nbs_get_ljpme_parameters<- CalcSlicedNonbondedForceKernel::getLJPMEParameters
+ *                              (NonbondedSlicingKernels.h:84; ReferenceNonbondedSlicingKernels.cpp:330-337)
  *   nbs_set_lambdas /
  *   nbs_set_global_parameters
  *                           <- the per-evaluation reads of Context parameters in
@@ -45,7 +47,7 @@
 extern "C" {
 #endif
 
-#define NBS_ABI_VERSION 1
+#define NBS_ABI_VERSION 2
 
 /* status codes */
 #define NBS_OK                 0
@@ -128,6 +130,15 @@ typedef struct nbs_system_desc {
     int32_t reserved0;
     const double* dispersion_coefficients;/* [nSl] from SlicedNonbondedForceImpl::
                                              calcDispersionCorrections, or NULL for zeros       */
+    int32_t ewald_kmax[3];                /* NBS_METHOD_EWALD: number of reciprocal vectors per
+                                             axis, numRx/numRy/numRz of setUseEwald
+                                             (ReferenceSlicedLJCoulombIxn.cpp:115-121), from
+                                             calcEwaldParameters (ReferenceNonbondedSlicingKernels.
+                                             cpp:160-162)                                        */
+    int32_t reserved1;
+    double  dispersion_alpha;             /* NBS_METHOD_LJPME: setUseLJPME (:149-155)            */
+    int32_t dispersion_grid[3];
+    int32_t reserved2;
 } nbs_system_desc;
 
 /* One evaluation == one CalcSlicedNonbondedForceKernel::execute call. */
@@ -213,6 +224,9 @@ int nbs_debug_set_list_capacity(nbs_context* ctx, int32_t j_capacity, int32_t x_
 
 /* queries */
 int nbs_get_pme_parameters(const nbs_context* ctx, double* alpha, int32_t* nx, int32_t* ny, int32_t* nz);
+/* CalcSlicedNonbondedForceKernel::getLJPMEParameters (NonbondedSlicingKernels.h:84;
+ * ReferenceNonbondedSlicingKernels.cpp:330-337): the dispersion grid; an error unless the method is LJPME */
+int nbs_get_ljpme_parameters(const nbs_context* ctx, double* alpha, int32_t* nx, int32_t* ny, int32_t* nz);
 int nbs_get_num_slices(const nbs_context* ctx, int32_t* num_slices);
 
 /*

@@ -68,6 +68,11 @@ class SystemDesc(C.Structure):
         ("flags", C.c_uint32),
         ("reserved0", C.c_int32),
         ("dispersion_coefficients", _f64p),
+        ("ewald_kmax", C.c_int32*3),
+        ("reserved1", C.c_int32),
+        ("dispersion_alpha", C.c_double),
+        ("dispersion_grid", C.c_int32*3),
+        ("reserved2", C.c_int32),
     ]
 
 
@@ -132,12 +137,13 @@ class DescArrays:
                     arr = np.ascontiguousarray(value, dtype=np.float64)
                     self.arrays[name] = arr
                     setattr(self.desc, name, _ptr(arr, C.c_double))
-            elif name == "pme_grid":
-                self.desc.pme_grid[:] = [int(v) for v in value]
+            elif name in ("pme_grid", "ewald_kmax", "dispersion_grid"):
+                getattr(self.desc, name)[:] = [int(v) for v in value]
             else:
                 setattr(self.desc, name, value)
 
 
+ABI_VERSION = 2          # NBS_ABI_VERSION of include/nbslice_b200.h
 LIB_PATH = os.environ.get("NBS_B200_LIBRARY") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libnbslice_b200.so")
 _lib = None
 
@@ -145,7 +151,7 @@ _lib = None
 EXPORTS = [
     "nbs_abi_version", "nbs_last_error", "nbs_device_count", "nbs_create", "nbs_destroy",
     "nbs_update_parameters", "nbs_set_lambdas", "nbs_set_global_parameters", "nbs_execute",
-    "nbs_get_pme_parameters", "nbs_get_num_slices", "nbs_get_pair_set", "nbs_get_exclusion_set",
+    "nbs_get_pme_parameters", "nbs_get_ljpme_parameters", "nbs_get_num_slices", "nbs_get_pair_set", "nbs_get_exclusion_set",
     "nbs_get_kernel_times", "nbs_get_launch_count", "nbs_get_nlist_stats",
     "nbs_set_shard", "nbs_execute_begin", "nbs_execute_convolve", "nbs_execute_finish", "nbs_get_exchange_buffers",
     "nbs_debug_set_list_capacity",
@@ -178,6 +184,7 @@ def load_library():
     lib.nbs_set_global_parameters.argtypes = [C.c_void_p, _f64p]
     lib.nbs_execute.argtypes = [C.c_void_p, C.POINTER(ExecArgs)]
     lib.nbs_get_pme_parameters.argtypes = [C.c_void_p, _f64p, _i32p, _i32p, _i32p]
+    lib.nbs_get_ljpme_parameters.argtypes = [C.c_void_p, _f64p, _i32p, _i32p, _i32p]
     lib.nbs_get_num_slices.argtypes = [C.c_void_p, _i32p]
     lib.nbs_get_pair_set.argtypes = [C.c_void_p, C.c_int64, _i32p, C.POINTER(C.c_int64), C.POINTER(C.c_uint64)]
     lib.nbs_get_exclusion_set.argtypes = [C.c_void_p, C.c_int64, _i32p, C.POINTER(C.c_int64)]
@@ -191,7 +198,7 @@ def load_library():
     lib.nbs_get_exchange_buffers.argtypes = [C.c_void_p, C.POINTER(ExchangeBuffers)]
     for name in EXPORTS:
         getattr(lib, name)
-    if lib.nbs_abi_version() != 1:
+    if lib.nbs_abi_version() != ABI_VERSION:
         raise ImportError("libnbslice_b200.so has an unexpected ABI version")
     _lib = lib
     return lib

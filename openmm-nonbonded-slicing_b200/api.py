@@ -496,6 +496,36 @@ class SlicedNonbondedForceImpl:
         return alpha, nx, ny, nz
 
     @staticmethod
+    def calcEwaldParameters(system, force):
+        """OpenMM NonbondedForceImpl::calcEwaldParameters [external], called at
+        ReferenceNonbondedSlicingKernels.cpp:160-162: alpha from the error tolerance and, per axis, the
+        smallest number of reciprocal vectors whose truncation error estimate
+        ``0.05 sqrt(L alpha) k exp(-(pi k / (L alpha))^2)`` falls below the tolerance, made odd."""
+        box = system.getDefaultPeriodicBoxVectors()
+        tol = force.getEwaldErrorTolerance()
+        alpha = math.sqrt(-math.log(2*tol))/force.getCutoffDistance()
+
+        def find_zero(width):
+            def value(arg):
+                temp = arg*math.pi/(width*alpha)
+                return tol - 0.05*math.sqrt(width*alpha)*arg*math.exp(-temp*temp)
+            arg = 10
+            v = value(arg)
+            if v > 0.0:
+                while v > 0.0 and arg > 0:
+                    arg -= 1
+                    v = value(arg)
+                return arg+1
+            while v < 0.0:
+                arg += 1
+                v = value(arg)
+            return arg
+
+        kmax = [find_zero(box[k][k]) for k in range(3)]
+        kmax = [k+1 if k % 2 == 0 else k for k in kmax]
+        return alpha, kmax[0], kmax[1], kmax[2]
+
+    @staticmethod
     def _evalIntegral(r, rs, rc, sigma):
         """:150-185"""
         A = 1/(rc-rs)
@@ -605,6 +635,16 @@ def build_desc(system, force, flags=0, device_index=0, legal_grid=False):
         grid = (nx, ny, nz)
         if legal_grid:
             grid = tuple(findLegalFFTDimension(g) for g in grid)
+    kmax = (0, 0, 0)
+    if method == force.Ewald:
+        alpha, kx, ky, kz = SlicedNonbondedForceImpl.calcEwaldParameters(system, force)
+        kmax = (kx, ky, kz)
+    dalpha, dgrid = 0.0, (0, 0, 0)
+    if method == force.LJPME:
+        dalpha, dnx, dny, dnz = SlicedNonbondedForceImpl.calcPMEParameters(system, force, True)
+        dgrid = (dnx, dny, dnz)
+        if legal_grid:
+            dgrid = tuple(findLegalFFTDimension(g) for g in dgrid)
     dispersion = None
     if force.getUseDispersionCorrection():
         dispersion = SlicedNonbondedForceImpl.calcDispersionCorrections(system, force)
@@ -638,6 +678,9 @@ def build_desc(system, force, flags=0, device_index=0, legal_grid=False):
         device_index=device_index,
         flags=flags,
         dispersion_coefficients=dispersion,
+        ewald_kmax=kmax,
+        dispersion_alpha=dalpha,
+        dispersion_grid=dgrid,
     )
 
 
@@ -714,7 +757,7 @@ class SlicedKernelBase(CalcSlicedNonbondedForceKernel):
     def getLJPMEParameters(self):
         if self.nonbondedMethod != self.LJPME:
             raise OpenMMException("getPMEParametersInContext: This Context is not using LJPME")
-        raise OpenMMException("LJPME is not supported by this platform")
+        return (self.desc.desc.dispersion_alpha,)+tuple(self.desc.desc.dispersion_grid)
 
 
 def findLegalFFTDimension(minimum):

@@ -15,10 +15,13 @@ namespace nbs {
 struct BondedArgs {
     int nExc, Npad;
     int rank, nRanks;                // exception e belongs to rank e % nRanks
-    int doExclusionCorrection;       // PME only
+    int doExclusionCorrection;       // Ewald, PME, LJPME
     int periodic;                    // exceptionsUsePeriodic
     double3 box, invBox;
     double alpha;
+    int ljpme;                       // LJPME: also back out the dispersion grid's contribution (:487-504)
+    double dispAlpha;
+    const double* c6;                // particle order
     const int2* pairs; const double4* params; const int* slices;
     const double* charge; const double* pos; const int* origToSorted;
     const int* slotOf;               // particle -> slot of the caller's position array (or NULL)
@@ -68,6 +71,16 @@ __global__ void k_bonded(const BondedArgs a) {
             }
             else
                 eCoul -= a.alpha*1.1283791670955125739*qq;
+            if (a.ljpme) {
+                // dispersion: only the reciprocal-space (multiplicative C6) part is removed, ReferenceSlicedLJCoulombIxn.cpp:487-504
+                const double dar2 = a.dispAlpha*a.dispAlpha*r2, dar4 = dar2*dar2, dar6 = dar4*dar2;
+                const double inverseR2 = inverseR*inverseR;
+                const double c6ij = a.c6[pr.x]*a.c6[pr.y];
+                const double inverseR6 = inverseR2*inverseR2*inverseR2;
+                const double expDar2 = exp(-dar2);
+                eVdw += c6ij*inverseR6*(1.0 - expDar2*(1.0 + dar2 + 0.5*dar4));
+                dEdR += a.lamV[slice]*6.0*c6ij*inverseR6*inverseR2*(1.0 - expDar2*(1.0 + dar2 + 0.5*dar4 + dar6/6.0));
+            }
         }
         if (dEdR != 0.0) {
             const int i = a.origToSorted[pr.x], j = a.origToSorted[pr.y];
@@ -99,11 +112,14 @@ int launchBonded(Context& c, const double* dPos, bool periodicBox) {
     BondedArgs a;
     a.nExc = c.nExc; a.Npad = c.Npad;
     a.rank = c.rank; a.nRanks = c.nRanks;
-    a.doExclusionCorrection = c.method == NBS_METHOD_PME ? 1 : 0;
+    a.doExclusionCorrection = c.ewaldDirect() ? 1 : 0;
     a.periodic = (c.excPeriodic && periodicBox) ? 1 : 0;
     a.box = make_double3(c.geom.box[0], c.geom.box[1], c.geom.box[2]);
     a.invBox = make_double3(c.geom.invBox[0], c.geom.invBox[1], c.geom.invBox[2]);
     a.alpha = c.alpha;
+    a.ljpme = c.ljpme() ? 1 : 0;
+    a.dispAlpha = c.dispAlpha;
+    a.c6 = c.dC6D.d;
     a.pairs = c.dExcPair.d; a.params = c.dExcParam.d; a.slices = c.dExcSlice.d;
     a.charge = c.dCharge.d; a.pos = dPos; a.origToSorted = c.dOrigToSorted.d;
     a.slotOf = nullptr;

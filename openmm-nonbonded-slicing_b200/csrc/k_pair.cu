@@ -57,6 +57,7 @@ struct PairArgs {
     float rswitch, rcut;
     int useSwitch;
     double rc2d, alphaD, krfD, crfD;
+    float dalpha2, invCut6, shiftMult;   // LJPME: alpha_d^2, rc^-6, rc^-6 (1 - exp(-x)(1 + x + x^2/2)) at x = (alpha_d rc)^2
     const double* q64;                   // sorted charges * sqrt(ONE_4PI_EPS0), double
     const double* erfcTab;               // piecewise degree-6 fit of erfc(alpha sqrt(s))/sqrt(s) in s = r^2 (ERFC_TAB_ROW doubles per interval)
     int* counters;                       // [2] number of work items, [3] cursor
@@ -156,9 +157,13 @@ __device__ __forceinline__ double expNegD(double z) {
 //     2^-3.5 nm (0.088 nm: none in a physical system) take the analytic path.
 //   * Lennard-Jones: fp32 from the same exact r^2 (terms of one sign dominate a slice's vdW sum, so 1e-7
 //     per term is far inside the 1e-5 target), accumulated in double.
-template <bool IS_PME>
+//   * LJPME (CMODE 2, :398-426): the multiplicative C6 term that the dispersion grid carries is taken out in real
+//     space, plus the potential shift at the cutoff; fp32 like the rest of the LJ energy.
+// CMODE: 0 = reaction field / no cutoff, 1 = PME or Ewald, 2 = LJPME.
+template <int CMODE>
 __device__ __forceinline__ void pairEnergyD(const uint4 fi, const uint4 fj, double qi, double qj, float sigi, float sigj,
                                             float epsi, float epsj, const PairArgs& a, double& ec, double& ev) {
+    constexpr bool IS_PME = CMODE != 0;
     const double dx = (double) (int) (fj.x - fi.x)*a.dsx;
     const double dy = (double) (int) (fj.y - fi.y)*a.dsy;
     const double dz = (double) (int) (fj.z - fi.z)*a.dsz;
@@ -171,6 +176,17 @@ __device__ __forceinline__ void pairEnergyD(const uint4 fi, const uint4 fj, doub
         s2 *= s2;
         const float s6 = s2*s2*s2;
         float evf = epsi*epsj*(s6 - 1.f)*s6;
+        if (CMODE == 2) {
+            const float sg = sigi*sigj;
+            const float c6 = 64.f*sg*sg*sg*epsi*epsj;                  // c6_i c6_j, c6 = 8 (sigma/2)^3 (2 sqrt(eps))
+            const float dar2 = a.dalpha2*r2f;
+            const float y2 = yf*yf;
+            const float emult = c6*y2*y2*y2*(1.f - ex2Fast(-1.4426950408889634f*dar2)*fmaf(dar2, fmaf(0.5f, dar2, 1.f), 1.f));
+            float sc = sigi + sigj;
+            sc *= sc;
+            const float sc6 = sc*sc*sc*a.invCut6;
+            evf += emult + epsi*epsj*(1.f - sc6)*sc6 - c6*a.shiftMult;
+        }
         if (a.useSwitch) {
             const float r = r2f*yf;
             if (r > a.rswitch) {
@@ -238,24 +254,25 @@ __device__ __forceinline__ bool pairInRange(const WarpScratch& w, const PairArgs
 // One 32 x 32 tile of the force kernel: lane l meets j slot (l + k) & 31 at step k; i forces (fix, fiy, fiz)
 // and the rotating j forces (fjx, fjy, fjz) stay in registers.  EMODE 2 also compacts the in-cutoff pairs
 // into w.queue and evaluates their energies in double precision, 32 real pairs per pass.
-template <int EMODE, bool IS_PME>
+template <int EMODE, int CMODE>
 __device__ __forceinline__ void energyPass(const WarpScratch& w, const PairArgs& a, int lane, int count, double* acc) {
     if (lane < count) {
         const unsigned e = w.queue[lane];
         const int il = e >> 5, jq = e & 31;
         const float4 q1 = w.iPar[il], q2 = w.jPar[jq];
         double ecd, evd;
-        pairEnergyD<IS_PME>(w.iFix[il], w.jFix[jq], w.iQ[il], w.jQ[jq], q1.x, q2.x, q1.y, q2.y, a, ecd, evd);
+        pairEnergyD<CMODE>(w.iFix[il], w.jFix[jq], w.iQ[il], w.jQ[jq], q1.x, q2.x, q1.y, q2.y, a, ecd, evd);
         const int sl = triSlice(__float_as_int(q1.z), __float_as_int(q2.z));
         acc[2*sl] += ecd;
         acc[2*sl+1] += evd;
     }
 }
 
-template <int EMODE, bool IS_PME, bool IS_X, bool SWITCH>
+template <int EMODE, int CMODE, bool IS_X, bool SWITCH>
 __device__ __forceinline__ void tileLoop(WarpScratch& w, const PairArgs& a, const float2* shLam, int lamOff, int lane,
                                          float xi, float yi, float zi, float qi, float sigi, float epsi, int si, const uint4 pi,
                                          float& fix, float& fiy, float& fiz, float& fjx, float& fjy, float& fjz, double* acc) {
+    constexpr bool IS_PME = CMODE != 0;
     const unsigned below = (1u << lane) - 1u;
     const float rc2 = a.rc2, alpha = a.alpha;
     const float TWO_OVER_SQRT_PI = 1.1283791670955126f;
@@ -277,7 +294,7 @@ __device__ __forceinline__ void tileLoop(WarpScratch& w, const PairArgs& a, cons
             qn += __popc(m);
             if (qn >= 32) {                       // warp-uniform
                 __syncwarp();
-                energyPass<EMODE, IS_PME>(w, a, lane, 32, acc);
+                energyPass<EMODE, CMODE>(w, a, lane, 32, acc);
                 const int rest = qn - 32;
                 const unsigned short moved = lane < rest ? w.queue[32 + lane] : (unsigned short) 0;
                 __syncwarp();
@@ -308,6 +325,22 @@ __device__ __forceinline__ void tileLoop(WarpScratch& w, const PairArgs& a, cons
             ec = qr*fmaf(a.krf*r2, r, 1.f) - qi*p.w*a.crf;
             fc = qr*invR2*fmaf(-2.f*a.krf*r2, r, 1.f);
         }
+        if (CMODE == 2) {
+            // LJPME (:398-426): real-space share of the multiplicative C6 term; the shift only enters the energy
+            const float sg = sigi*pr.x;
+            const float c6 = 64.f*sg*sg*sg*eps;
+            const float dar2 = a.dalpha2*r2;
+            const float exd = ex2Fast(-1.4426950408889634f*dar2);
+            const float p2 = fmaf(dar2, fmaf(0.5f, dar2, 1.f), 1.f);             // 1 + x + x^2/2
+            const float c6r6 = c6*invR2*invR2*invR2;
+            fv = fmaf(6.f*c6r6*invR2, 1.f - exd*fmaf(dar2*dar2*dar2, 1.f/6.f, p2), fv);
+            if (EMODE == 1) {
+                float sc = sigi + pr.x;
+                sc *= sc;
+                const float sc6 = sc*sc*sc*a.invCut6;
+                ev += c6r6*(1.f - exd*p2) + eps*(1.f - sc6)*sc6 - c6*a.shiftMult;
+            }
+        }
         if (SWITCH) {
             if (r > a.rswitch) {
                 const float wd = 1.f/(a.rcut - a.rswitch);
@@ -335,7 +368,7 @@ __device__ __forceinline__ void tileLoop(WarpScratch& w, const PairArgs& a, cons
     }
     if (EMODE == 2) {                             // the queue refers to this tile's shared-memory slots
         __syncwarp();
-        energyPass<EMODE, IS_PME>(w, a, lane, qn, acc);
+        energyPass<EMODE, CMODE>(w, a, lane, qn, acc);
     }
 }
 
@@ -343,7 +376,7 @@ __device__ __forceinline__ void tileLoop(WarpScratch& w, const PairArgs& a, cons
 // EMODE 0: forces only; 1: single-precision energies; 2: double-precision energies.
 // MINCTAS: resident CTAs per SM the register allocation is bounded for (2: 128 registers; 3: 80 registers and a
 // few bytes of spill -- no different at DHFR size, 8 % faster at STMV size, where there is always a next item)
-template <int EMODE, bool IS_PME, int MODE, int MINCTAS>
+template <int EMODE, int CMODE, int MODE, int MINCTAS>
 __global__ void __launch_bounds__(PAIR_WARPS*32, MINCTAS) k_pair(const PairArgs a) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     __shared__ float2 shLam[MAX_SUBSETS*MAX_SUBSETS];      // (lambda_Coulomb, lambda_vdW) of subset pair (si, sj)
@@ -491,12 +524,12 @@ __global__ void __launch_bounds__(PAIR_WARPS*32, MINCTAS) k_pair(const PairArgs 
             // four copies of the loop so that the exclusion-mask test and the switching function cost nothing
             // in the tiles that do not have them (both conditions are warp-uniform)
             if (isX) {
-                if (a.useSwitch) tileLoop<EMODE, IS_PME, true, true>(w, a, shLam, lamOff, lane, xi, yi, zi, qi, sigi, epsi, si, pi, fix, fiy, fiz, fjx, fjy, fjz, acc);
-                else tileLoop<EMODE, IS_PME, true, false>(w, a, shLam, lamOff, lane, xi, yi, zi, qi, sigi, epsi, si, pi, fix, fiy, fiz, fjx, fjy, fjz, acc);
+                if (a.useSwitch) tileLoop<EMODE, CMODE, true, true>(w, a, shLam, lamOff, lane, xi, yi, zi, qi, sigi, epsi, si, pi, fix, fiy, fiz, fjx, fjy, fjz, acc);
+                else tileLoop<EMODE, CMODE, true, false>(w, a, shLam, lamOff, lane, xi, yi, zi, qi, sigi, epsi, si, pi, fix, fiy, fiz, fjx, fjy, fjz, acc);
             }
             else {
-                if (a.useSwitch) tileLoop<EMODE, IS_PME, false, true>(w, a, shLam, lamOff, lane, xi, yi, zi, qi, sigi, epsi, si, pi, fix, fiy, fiz, fjx, fjy, fjz, acc);
-                else tileLoop<EMODE, IS_PME, false, false>(w, a, shLam, lamOff, lane, xi, yi, zi, qi, sigi, epsi, si, pi, fix, fiy, fiz, fjx, fjy, fjz, acc);
+                if (a.useSwitch) tileLoop<EMODE, CMODE, false, true>(w, a, shLam, lamOff, lane, xi, yi, zi, qi, sigi, epsi, si, pi, fix, fiy, fiz, fjx, fjy, fjz, acc);
+                else tileLoop<EMODE, CMODE, false, false>(w, a, shLam, lamOff, lane, xi, yi, zi, qi, sigi, epsi, si, pi, fix, fiy, fiz, fjx, fjy, fjz, acc);
             }
             // j forces of this tile (lane l ends up with slot l) -> global fixed point
             if (entry >= 0 && (fjx != 0.f || fjy != 0.f || fjz != 0.f)) {
@@ -536,29 +569,36 @@ __global__ void __launch_bounds__(PAIR_WARPS*32, MINCTAS) k_pair(const PairArgs 
     }
 }
 
-template <int EMODE, bool IS_PME, int MODE, int MINCTAS>
+template <int EMODE, int CMODE, int MODE, int MINCTAS>
 static int launchPairK(Context& c, const PairArgs& a) {
     static bool attr[64] = {false};
     const size_t smem = sizeof(WarpScratch)*PAIR_WARPS;
     if (!attr[c.device & 63]) {
-        NBS_CUDA_CHECK(cudaFuncSetAttribute(k_pair<EMODE, IS_PME, MODE, MINCTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        NBS_CUDA_CHECK(cudaFuncSetAttribute(k_pair<EMODE, CMODE, MODE, MINCTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         attr[c.device & 63] = true;
     }
     // persistent grid: as many CTAs as are resident at once
     static int perSM[64] = {0};
     if (perSM[c.device & 63] == 0) {
         int n = 0;
-        NBS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_pair<EMODE, IS_PME, MODE, MINCTAS>, PAIR_WARPS*32, smem));
+        NBS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_pair<EMODE, CMODE, MODE, MINCTAS>, PAIR_WARPS*32, smem));
         perSM[c.device & 63] = std::max(1, n);
     }
-    k_pair<EMODE, IS_PME, MODE, MINCTAS><<<perSM[c.device & 63]*c.numSMs, PAIR_WARPS*32, smem, c.stream>>>(a);
+    k_pair<EMODE, CMODE, MODE, MINCTAS><<<perSM[c.device & 63]*c.numSMs, PAIR_WARPS*32, smem, c.stream>>>(a);
     return NBS_OK;
 }
 
-template <int EMODE, bool IS_PME, int MODE>
+template <int EMODE, int CMODE, int MODE>
 static int launchPairT(Context& c, const PairArgs& a) {
-    if (MODE == 0 && c.N >= 300000) return launchPairK<EMODE, IS_PME, MODE, 3>(c, a);
-    return launchPairK<EMODE, IS_PME, MODE, PAIR_MIN_CTAS>(c, a);
+    if constexpr (MODE == 0 && CMODE != 2) {
+        if (c.N >= 300000) return launchPairK<EMODE, CMODE, MODE, 3>(c, a);
+    }
+    return launchPairK<EMODE, CMODE, MODE, PAIR_MIN_CTAS>(c, a);
+}
+
+template <int CMODE>
+static int launchPairE(Context& c, const PairArgs& a, int emode) {
+    return emode == 0 ? launchPairT<0, CMODE, 0>(c, a) : (emode == 1 ? launchPairT<1, CMODE, 0>(c, a) : launchPairT<2, CMODE, 0>(c, a));
 }
 
 int launchPairs(Context& c, bool wantEnergy, int mode) {
@@ -585,6 +625,12 @@ int launchPairs(Context& c, bool wantEnergy, int mode) {
     a.krf = (float) a.krfD;
     a.crf = (float) a.crfD;
     a.useSwitch = c.useSwitch ? 1 : 0;
+    {
+        const double dac2 = c.dispAlpha*c.dispAlpha*c.cutoff*c.cutoff, invCut6 = noCutoff ? 0.0 : std::pow(c.cutoff, -6.0);
+        a.dalpha2 = (float) (c.dispAlpha*c.dispAlpha);
+        a.invCut6 = (float) invCut6;
+        a.shiftMult = (float) (invCut6*(1.0 - std::exp(-dac2)*(1.0 + dac2 + 0.5*dac2*dac2)));
+    }
     a.rswitch = (float) c.switchDist;
     a.rcut = (float) c.cutoff;
     a.counters = c.dCounters.d;
@@ -601,15 +647,16 @@ int launchPairs(Context& c, bool wantEnergy, int mode) {
         a.lam.c[s] = s < c.nSl ? (float) c.lambdas[2*s] : 1.f;
         a.lam.v[s] = s < c.nSl ? (float) c.lambdas[2*s+1] : 1.f;
     }
-    const bool pme = c.method == NBS_METHOD_PME;
+    const bool pme = c.ewaldDirect();
     const int emode = !wantEnergy ? 0 : ((c.flags & NBS_FLAG_FP32_ENERGY) ? 1 : 2);
     int status;
     if (mode != 0) {
         NBS_CUDA_CHECK(cudaMemsetAsync(c.dCounters.d + 3, 0, sizeof(int), c.stream));      // rewind the work cursor
-        status = mode == 1 ? launchPairT<0, true, 1>(c, a) : launchPairT<0, true, 2>(c, a);
+        status = mode == 1 ? launchPairT<0, 1, 1>(c, a) : launchPairT<0, 1, 2>(c, a);
     }
-    else if (pme) status = emode == 0 ? launchPairT<0, true, 0>(c, a) : (emode == 1 ? launchPairT<1, true, 0>(c, a) : launchPairT<2, true, 0>(c, a));
-    else status = emode == 0 ? launchPairT<0, false, 0>(c, a) : (emode == 1 ? launchPairT<1, false, 0>(c, a) : launchPairT<2, false, 0>(c, a));
+    else if (c.ljpme()) status = launchPairE<2>(c, a, emode);
+    else if (pme) status = launchPairE<1>(c, a, emode);
+    else status = launchPairE<0>(c, a, emode);
     if (status != NBS_OK) return status;
     c.launches++;
     timerMark(c, mode == 0 ? "pair" : "pair_set");

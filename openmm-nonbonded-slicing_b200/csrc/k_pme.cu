@@ -510,6 +510,26 @@ __global__ void k_eterm(int nx, int ny, int nz, int nzh, double3 invBox, double 
     eterm[idx] = (T) (exp(-kPi*kPi*m2/(alpha*alpha))/denom);
 }
 
+// Dispersion influence function (LJPME), dpme_reciprocal_convolution, ReferencePME.cpp:520-570:
+// eterm = (2 pi^3 sqrt(pi) erfc(b) m^3 + exp(-b^2) (alpha^3 - 2 alpha pi^2 m^2)) * (-2 pi sqrt(pi) / (6 V Bx By Bz)),
+// b = pi m / alpha; unlike the Coulomb case the m = 0 term is kept (:551).
+template <typename T>
+__global__ void k_eterm_dispersion(int nx, int ny, int nz, int nzh, double3 invBox, double volume, double alpha,
+                                   const double* __restrict__ moduli, T* __restrict__ eterm) {
+    const size_t idx = (size_t) blockIdx.x*blockDim.x + threadIdx.x;
+    if (idx >= (size_t) nx*ny*nzh) return;
+    const int kz = (int) (idx % nzh), ky = (int) ((idx/nzh) % ny), kx = (int) (idx/((size_t) nzh*ny));
+    const double mx = (kx < (nx+1)/2 ? kx : kx - nx)*invBox.x;
+    const double my = (ky < (ny+1)/2 ? ky : ky - ny)*invBox.y;
+    const double mz = (kz < (nz+1)/2 ? kz : kz - nz)*invBox.z;
+    const double m2 = mx*mx + my*my + mz*mz;
+    const double sqrtPi = 1.7724538509055160273;
+    const double denom = (-2*kPi*sqrtPi/(6.0*volume))/(moduli[kx]*moduli[nx + ky]*moduli[nx + ny + kz]);
+    const double m = sqrt(m2), b = (kPi/alpha)*m;
+    const double fac1 = 2.0*kPi*kPi*kPi*sqrtPi, fac2 = alpha*alpha*alpha, fac3 = -2.0*alpha*kPi*kPi;
+    eterm[idx] = (T) ((fac1*erfc(b)*m*m2 + exp(-b*b)*(fac2 + fac3*m2))*denom);
+}
+
 int prepareEterm(Context& c) {
     const CellGeom& g = c.geom;
     if (c.etermBox[0] == g.box[0] && c.etermBox[1] == g.box[1] && c.etermBox[2] == g.box[2]) return NBS_OK;
@@ -519,8 +539,14 @@ int prepareEterm(Context& c) {
     NBS_CUDA_CHECK(c.dEtermD.ensure(total));
     const double3 inv = make_double3(g.invBox[0], g.invBox[1], g.invBox[2]);
     const double volume = g.box[0]*g.box[1]*g.box[2];
-    k_eterm<float><<<(unsigned) ((total + 255)/256), 256, 0, c.stream>>>(nx, ny, nz, nzh, inv, volume, c.alpha, c.dModuli.d, c.dEterm.d);
-    k_eterm<double><<<(unsigned) ((total + 255)/256), 256, 0, c.stream>>>(nx, ny, nz, nzh, inv, volume, c.alpha, c.dModuli.d, c.dEtermD.d);
+    if (c.dispersionPass) {
+        k_eterm_dispersion<float><<<(unsigned) ((total + 255)/256), 256, 0, c.stream>>>(nx, ny, nz, nzh, inv, volume, c.alpha, c.dModuli.d, c.dEterm.d);
+        k_eterm_dispersion<double><<<(unsigned) ((total + 255)/256), 256, 0, c.stream>>>(nx, ny, nz, nzh, inv, volume, c.alpha, c.dModuli.d, c.dEtermD.d);
+    }
+    else {
+        k_eterm<float><<<(unsigned) ((total + 255)/256), 256, 0, c.stream>>>(nx, ny, nz, nzh, inv, volume, c.alpha, c.dModuli.d, c.dEterm.d);
+        k_eterm<double><<<(unsigned) ((total + 255)/256), 256, 0, c.stream>>>(nx, ny, nz, nzh, inv, volume, c.alpha, c.dModuli.d, c.dEtermD.d);
+    }
     c.launches += 2;
     for (int k = 0; k < 3; k++) c.etermBox[k] = g.box[k];
     return NBS_OK;
@@ -600,6 +626,9 @@ static int launchPmeT(Context& c, bool wantEnergy, int half) {
     p.unsorted = c.pmeUnsorted ? 1 : 0;
     p.fix = c.dFix.d; p.chargeF = c.dChargeF.d; p.subsetOf = c.dSubset.d;
     p.q64 = c.dQ64.d; p.chargeD = c.dCharge.d; p.sqrtK = sqrt(kOne4PiEps0);
+    if (c.dispersionPass) {          // LJPME dispersion chain: the C6 coefficients are the "charges", no unit factor
+        p.unsorted = 1; p.chargeF = c.dC6F.d; p.chargeD = c.dC6D.d; p.sqrtK = 1.0;
+    }
     p.force = c.pmeUnsorted ? c.dForce.d + 3*(size_t) c.Npad : c.dForce.d;
     for (int k = 0; k < 3; k++) p.fscale[k] = (float) (c.grid[k]*c.geom.invBox[k]);
     const int atomCtas = (c.N + 7)/8;
@@ -615,11 +644,14 @@ static int launchPmeT(Context& c, bool wantEnergy, int half) {
     FftArgs f;
     f.nS = c.nS; f.nx = nx; f.ny = ny; f.nz = nz; f.nzh = nzh;
     f.ownLo = c.ownLo; f.ownHi = c.ownHi;
-    f.grid = c.dGrid.d; f.gridC = c.dGridC.d; f.pot = c.dPot.d; f.energy = c.dEnergy.d;
+    // the convolution kernels add slice s's energy to energy[2 s]: Coulomb term, or (dispersion chain) the vdW term
+    double* const energyBase = c.dEnergy.d + (c.dispersionPass ? 1 : 0);
+    f.grid = c.dGrid.d; f.gridC = c.dGridC.d; f.pot = c.dPot.d; f.energy = energyBase;
     f.eterm = sizeof(T) == 8 ? (const void*) c.dEtermD.d : (const void*) c.dEterm.d;
     f.wantEnergy = wantEnergy ? 1 : 0;
     for (int s = 0; s < MAX_SLICES; s++) {
-        f.lam.c[s] = s < c.nSl ? (float) c.lambdas[2*s] : 1.f;
+        // the kernels mix the subset potentials with lam.c: lambda_Coulomb, or (dispersion chain) lambda_vdW (:868)
+        f.lam.c[s] = s < c.nSl ? (float) c.lambdas[2*s + (c.dispersionPass ? 1 : 0)] : 1.f;
         f.lam.v[s] = s < c.nSl ? (float) c.lambdas[2*s+1] : 1.f;
     }
     const size_t cs = 2*sizeof(T);
@@ -635,7 +667,7 @@ static int launchPmeT(Context& c, bool wantEnergy, int half) {
         pa.ownLo = c.ownLo; pa.ownHi = c.ownHi;
         pa.rowStride = 0; pa.chunk = 0;
         pa.grid = c.dGrid.d; pa.gridC = c.dGridC.d; pa.eterm = f.eterm; pa.pot = c.dPot.d;
-        pa.energy = c.dEnergy.d; pa.wantEnergy = f.wantEnergy; pa.lam = f.lam;
+        pa.energy = energyBase; pa.wantEnergy = f.wantEnergy; pa.lam = f.lam;
         const int planeStatus = (c.flags & NBS_FLAG_LINE_FFT) ? NBS_RETRY : launchPlaneFft<T>(c, plan, pa, half);
         if (planeStatus < 0) return planeStatus;
         if (planeStatus == NBS_OK) {

@@ -105,7 +105,11 @@ static int readDescription(Context& c, const nbs_system_desc& d, bool creating) 
         c.switchDist = d.switching_distance;
         c.rfDielectric = d.rf_dielectric;
         c.useSwitch = d.method != NBS_METHOD_NOCUTOFF && d.use_switching_function != 0;
-        c.periodic = d.method == NBS_METHOD_CUTOFF_PERIODIC || d.method == NBS_METHOD_PME;
+        c.periodic = d.method == NBS_METHOD_CUTOFF_PERIODIC || d.method == NBS_METHOD_PME || d.method == NBS_METHOD_EWALD || d.method == NBS_METHOD_LJPME;
+        c.dispAlpha = d.dispersion_alpha;
+        for (int k = 0; k < 3; k++) c.dispGrid[k] = d.dispersion_grid[k];
+        if (d.method == NBS_METHOD_LJPME) c.useSwitch = false;      // ReferenceNonbondedSlicingKernels.cpp:174
+        for (int k = 0; k < 3; k++) c.ewaldKmax[k] = d.ewald_kmax[k];
         c.cutoffEff = d.cutoff;
         c.excPeriodic = (d.method == NBS_METHOD_NOCUTOFF || d.method == NBS_METHOD_CUTOFF_NONPERIODIC) ? false : d.exceptions_use_periodic != 0;
         for (int k = 0; k < 3; k++) c.grid[k] = d.pme_grid[k];
@@ -141,6 +145,21 @@ static int applyParameters(Context& c) {
         sigEps[i] = make_float2((float) (0.5*sig[i]), (float) (2.0*std::sqrt(eps[i])));
         c.subsetQ[c.subsets[i]] += q[i];
         c.subsetQ2[c.subsets[i]] += q[i]*q[i];
+    }
+    if (c.ljpme()) {
+        // c6 = 8 (sigma/2)^3 (2 sqrt(eps)), ReferenceSlicedLJCoulombIxn.cpp:248, 395-396; self term :212
+        std::vector<float> c6F(N);
+        std::vector<double> c6D(N);
+        c.subsetC6Self.assign(c.nS, 0.0);
+        for (int i = 0; i < N; i++) {
+            c6D[i] = 8.0*std::pow(0.5*sig[i], 3.0)*(2.0*std::sqrt(eps[i]));
+            c6F[i] = (float) c6D[i];
+            c.subsetC6Self[c.subsets[i]] += 64.0*std::pow(0.5*sig[i], 6.0)*std::pow(2.0*std::sqrt(eps[i]), 2.0)/12.0;
+        }
+        NBS_CUDA_CHECK(c.dC6F.ensure(N));
+        NBS_CUDA_CHECK(c.dC6D.ensure(N));
+        NBS_CUDA_CHECK(cudaMemcpy(c.dC6F.d, c6F.data(), sizeof(float)*N, cudaMemcpyHostToDevice));
+        NBS_CUDA_CHECK(cudaMemcpy(c.dC6D.d, c6D.data(), sizeof(double)*N, cudaMemcpyHostToDevice));
     }
     std::vector<double> eq(c.nExc), es(c.nExc), ee(c.nExc);
     std::vector<char> is14(c.nExc, 0);
@@ -228,6 +247,21 @@ static void bsplineModuli(int ngrid, double* moduli) {
     }
     for (int i = 0; i < ngrid; i++)
         if (moduli[i] < 1.0e-7) moduli[i] = (moduli[(i-1+ngrid)%ngrid] + moduli[(i+1)%ngrid])/2;
+}
+
+// LJPME runs the PME chain twice: charges on the (alpha, grid) set of setUsePME, then C6 coefficients on the set
+// of setUseLJPME (ReferenceSlicedLJCoulombIxn.cpp:229-253).  The chain reads its set from the Context's main
+// fields; this swaps the two sets (host-side only; work buffers are shared and sized for the larger grid).
+void swapPmeTables(Context& c) {
+    std::swap(c.alpha, c.dispAlpha);
+    for (int k = 0; k < 3; k++) { std::swap(c.grid[k], c.dispGrid[k]); std::swap(c.etermBox[k], c.etermBoxDisp[k]); }
+    std::swap(c.dModuli, c.dModuliDisp);
+    std::swap(c.dTwiddle, c.dTwiddleDisp);
+    std::swap(c.dTwiddleD, c.dTwiddleDDisp);
+    std::swap(c.dEterm, c.dEtermDisp);
+    std::swap(c.dEtermD, c.dEtermDDisp);
+    std::swap(c.hModuli, c.hModuliDisp);
+    c.dispersionPass = !c.dispersionPass;
 }
 
 int uploadPmeTables(Context& c) {
@@ -356,7 +390,8 @@ static int setupGeometry(Context& c, const double L[3], const double origin[3]) 
     NBS_CUDA_CHECK(c.dItems.ensure((size_t) c.maxLocalBlocks*(((c.capJ + c.capX)/32 + c.chunkTiles - 1)/c.chunkTiles + 1)));
     // PME from particle-order coordinates while the grids are comfortably L2-resident (scattered access is free
     // there); large systems keep the cell-sorted order for locality
-    c.pmeUnsorted = c.method == NBS_METHOD_PME && N < 300000 && !(c.flags & NBS_FLAG_SORTED_PME);
+    // (the Ewald sum and the LJPME chains always work from the particle-order fixed-point coordinates)
+    c.pmeUnsorted = (c.method == NBS_METHOD_PME && N < 300000 && !(c.flags & NBS_FLAG_SORTED_PME)) || c.method == NBS_METHOD_EWALD || c.method == NBS_METHOD_LJPME;
     NBS_CUDA_CHECK(c.dForce.ensure(6*(size_t) c.Npad));
     return NBS_OK;
 }
@@ -388,6 +423,9 @@ static void releaseAll(Context& c) {
     c.dXList.release(); c.dXCount.release(); c.dXMask.release(); c.dCounters.release(); c.dForce.release(); c.dItems.release();
     c.dEnergy.release(); c.dGrid.release(); c.dGridC.release(); c.dEterm.release(); c.dModuli.release();
     c.dPot.release(); c.dEtermD.release(); c.dTwiddleD.release(); c.dErfcTab.release();
+    c.dEwaldK.release(); c.dEwaldSums.release(); c.dEwaldMixed.release();
+    c.dC6F.release(); c.dC6D.release(); c.dEtermDisp.release(); c.dEtermDDisp.release(); c.dModuliDisp.release();
+    c.dTwiddleDisp.release(); c.dTwiddleDDisp.release();
     c.dTwiddle.release(); c.dPairStats.release(); c.dPairDump.release();
     if (c.hCounters) cudaFreeHost(c.hCounters);
     if (c.hEnergy) cudaFreeHost(c.hEnergy);
@@ -430,10 +468,8 @@ int nbs_create(const nbs_system_desc* desc, nbs_context** out) {
     *out = nullptr;
     if (desc->struct_size != (int32_t) sizeof(nbs_system_desc)) return fail(NBS_ERR_INVALID, "nbs_system_desc.struct_size mismatch");
     switch (desc->method) {
-        case NBS_METHOD_PME: case NBS_METHOD_CUTOFF_PERIODIC: break;
+        case NBS_METHOD_PME: case NBS_METHOD_CUTOFF_PERIODIC: case NBS_METHOD_EWALD: case NBS_METHOD_LJPME: break;
         case NBS_METHOD_NOCUTOFF: case NBS_METHOD_CUTOFF_NONPERIODIC: break;
-        case NBS_METHOD_EWALD: case NBS_METHOD_LJPME:
-            return fail(NBS_ERR_UNSUPPORTED, "Ewald and LJPME are not implemented on this platform (PME only)");
         default: return fail(NBS_ERR_INVALID, "illegal nonbonded method");
     }
     if (desc->method != NBS_METHOD_NOCUTOFF && desc->cutoff <= 0) return fail(NBS_ERR_INVALID, "cutoff must be positive");
@@ -443,10 +479,21 @@ int nbs_create(const nbs_system_desc* desc, nbs_context** out) {
     Context& c = ctx->c;
     status = readDescription(c, *desc, true);
     if (status != NBS_OK) { delete ctx; return status; }
-    if (c.method == NBS_METHOD_PME) {
+    if (c.ljpme() && (c.dispAlpha <= 0 || c.dispGrid[0] < PME_ORDER+1 || c.dispGrid[1] < PME_ORDER+1 || c.dispGrid[2] < PME_ORDER+1)) {
+        delete ctx;
+        return fail(NBS_ERR_INVALID, "LJPME needs dispersion_alpha > 0 and a dispersion grid of at least 6 points per dimension");
+    }
+    if (c.usesPmeGrid()) {
         if (c.alpha <= 0 || c.grid[0] < PME_ORDER+1 || c.grid[1] < PME_ORDER+1 || c.grid[2] < PME_ORDER+1) {
             delete ctx;
             return fail(NBS_ERR_INVALID, "PME needs ewald_alpha > 0 and a grid of at least 6 points per dimension");
+        }
+    }
+    if (c.method == NBS_METHOD_EWALD) {
+        // ReferenceSlicedLJCoulombIxn.cpp:270-271
+        if (c.alpha <= 0 || std::max(c.ewaldKmax[0], std::max(c.ewaldKmax[1], c.ewaldKmax[2])) < 1) {
+            delete ctx;
+            return fail(NBS_ERR_INVALID, "kmax for Ewald summation < 1");
         }
     }
     c.capJ = 2048;
@@ -469,8 +516,18 @@ int nbs_create(const nbs_system_desc* desc, nbs_context** out) {
         delete ctx;
         return fail(NBS_ERR_CUDA, std::string("allocation failed: ") + cudaGetErrorString(e));
     }
-    if (c.method == NBS_METHOD_PME) {
+    if (c.usesPmeGrid()) {
         status = uploadPmeTables(c);
+        if (status == NBS_OK && c.ljpme()) {
+            swapPmeTables(c);
+            status = uploadPmeTables(c);
+            swapPmeTables(c);
+        }
+        if (status == NBS_OK) status = buildErfcTable(c);
+        if (status != NBS_OK) { releaseAll(c); delete ctx; return status; }
+    }
+    if (c.method == NBS_METHOD_EWALD) {
+        status = uploadEwaldVectors(c);
         if (status == NBS_OK) status = buildErfcTable(c);
         if (status != NBS_OK) { releaseAll(c); delete ctx; return status; }
     }
@@ -561,7 +618,7 @@ static int phaseBegin(Context& c, const nbs_exec_args* args) {
     const double* box = args->box;
     c.stream = workStream(c, args);
     cudaStream_t st = c.stream;
-    const bool pme = c.method == NBS_METHOD_PME;
+    const bool pme = c.ewaldDirect();
     c.phaseEnergy = args->slice_energies != nullptr;
     c.phaseDirect = args->include_direct != 0;
     c.phaseRecip = args->include_reciprocal != 0 && pme;
@@ -664,7 +721,7 @@ static int phaseBegin(Context& c, const nbs_exec_args* args) {
         if (status != NBS_OK && c.directOverlapped) cudaStreamWaitEvent(st, c.evDirectDone, 0);
     }
     if (status != NBS_OK) return status;
-    if (c.phaseRecip && (status = launchPme(c, c.phaseEnergy, 0)) != NBS_OK) {
+    if (c.phaseRecip && (status = (c.method == NBS_METHOD_EWALD ? launchEwald(c, c.phaseEnergy) : launchPme(c, c.phaseEnergy, 0))) != NBS_OK) {
         if (c.directOverlapped) cudaStreamWaitEvent(st, c.evDirectDone, 0);
         return status;
     }
@@ -677,7 +734,15 @@ static int phaseConvolve(Context& c, const nbs_exec_args* args) {
     NBS_CUDA_CHECK(cudaSetDevice(c.device));
     cudaStream_t st = c.stream;
     int status = NBS_OK;
-    if (c.phaseRecip) status = launchPme(c, c.phaseEnergy, 1);
+    if (c.phaseRecip && c.usesPmeGrid()) status = launchPme(c, c.phaseEnergy, 1);
+    if (status == NBS_OK && c.phaseRecip && c.ljpme()) {
+        // dispersion chain (:241-253): same kernels, the C6 coefficients as "charges", the dispersion set of tables;
+        // it reuses the work grids, so it follows the Coulomb chain on the same stream
+        swapPmeTables(c);
+        status = launchPme(c, c.phaseEnergy, 0);
+        if (status == NBS_OK) status = launchPme(c, c.phaseEnergy, 1);
+        swapPmeTables(c);
+    }
     if (c.directOverlapped) NBS_CUDA_CHECK(cudaStreamWaitEvent(st, c.evDirectDone, 0));   // join the direct-space stream
     if (status != NBS_OK) { c.phase = 0; return status; }
     c.phase = 2;
@@ -755,6 +820,10 @@ static int phaseComplete(Context& c, const nbs_exec_args* args) {
                     E[2*(j*(j+1)/2+i)] += (i == j ? 1 : 2)*c.subsetQ[i]*c.subsetQ[j]*factor;
             }
         }
+        if (c.phaseRecip && c.ljpme()) {     // dispersion self term, ReferenceSlicedLJCoulombIxn.cpp:211-212
+            const double a6 = std::pow(c.dispAlpha, 6.0);
+            for (int i = 0; i < c.nS; i++) E[2*(i*(i+3)/2) + 1] += a6*c.subsetC6Self[i];
+        }
         if (c.phaseDirect && c.periodic)   // dispersion correction (periodic methods only), ReferenceNonbondedSlicingKernels.cpp:244-249
             for (int s = 0; s < c.nSl; s++) E[2*s+1] += c.dispersion[s]/volume;
     }
@@ -819,7 +888,7 @@ int nbs_execute(nbs_context* ctx, const nbs_exec_args* args) {
             c.stream = workStream(c, args);
             c.phaseEnergy = args->slice_energies != nullptr;
             c.phaseDirect = args->include_direct != 0;
-            c.phaseRecip = args->include_reciprocal != 0 && c.method == NBS_METHOD_PME;
+            c.phaseRecip = args->include_reciprocal != 0 && c.ewaldDirect();
             NBS_CUDA_CHECK(cudaGraphLaunch(c.graphExec, c.stream));
             c.launches += c.graphLaunches;
             status = phaseComplete(c, args);
@@ -892,6 +961,8 @@ int nbs_set_shard(nbs_context* ctx, int32_t rank, int32_t num_ranks, int32_t blo
         return fail(NBS_ERR_INVALID, "illegal i-block share: need 0 <= offset, offset + width <= period");
     if (subset_begin < 0 || subset_end > c.nS || subset_begin > subset_end)
         return fail(NBS_ERR_INVALID, "illegal subset range");
+    if (num_ranks > 1 && (c.method == NBS_METHOD_EWALD || c.method == NBS_METHOD_LJPME))
+        return fail(NBS_ERR_UNSUPPORTED, "the plain Ewald sum and LJPME are not sharded across ranks (use PME)");
     c.rank = rank; c.nRanks = num_ranks;
     c.paramVersion++;
     c.blockPeriod = block_period; c.blockOffset = block_offset; c.blockWidth = block_width;
@@ -930,6 +1001,14 @@ int nbs_get_pme_parameters(const nbs_context* ctx, double* alpha, int32_t* nx, i
     if (ctx->c.method != NBS_METHOD_PME && ctx->c.method != NBS_METHOD_LJPME)
         return fail(NBS_ERR_INVALID, "getPMEParametersInContext: This Context is not using PME or LJPME");
     *alpha = ctx->c.alpha; *nx = ctx->c.grid[0]; *ny = ctx->c.grid[1]; *nz = ctx->c.grid[2];
+    return NBS_OK;
+}
+
+int nbs_get_ljpme_parameters(const nbs_context* ctx, double* alpha, int32_t* nx, int32_t* ny, int32_t* nz) {
+    if (!ctx || !alpha || !nx || !ny || !nz) return fail(NBS_ERR_INVALID, "null argument");
+    if (ctx->c.method != NBS_METHOD_LJPME)                       // ReferenceNonbondedSlicingKernels.cpp:330-337
+        return fail(NBS_ERR_INVALID, "getPMEParametersInContext: This Context is not using LJPME");
+    *alpha = ctx->c.dispAlpha; *nx = ctx->c.dispGrid[0]; *ny = ctx->c.dispGrid[1]; *nz = ctx->c.dispGrid[2];
     return NBS_OK;
 }
 

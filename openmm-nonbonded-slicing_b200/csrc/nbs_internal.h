@@ -92,9 +92,19 @@ struct Context {
     uint32_t flags = 0;
     double cutoff = 0, alpha = 0, switchDist = 0, rfDielectric = 78.3;
     bool useSwitch = false, excPeriodic = false;
-    bool periodic = true;                    // CutoffPeriodic / PME; false for NoCutoff / CutoffNonPeriodic
+    bool periodic = true;                    // CutoffPeriodic / Ewald / PME; false for NoCutoff / CutoffNonPeriodic
+    bool ewaldDirect() const { return method == NBS_METHOD_PME || method == NBS_METHOD_EWALD || method == NBS_METHOD_LJPME; }   // erfc direct space + exclusion corrections
+    bool usesPmeGrid() const { return method == NBS_METHOD_PME || method == NBS_METHOD_LJPME; }
+    bool ljpme() const { return method == NBS_METHOD_LJPME; }
     double cutoffEff = 0;                    // the cutoff, or (NoCutoff) a distance no pair of the system exceeds
     int grid[3] = {0, 0, 0};
+    // LJPME: the dispersion grid's own (alpha, grid, tables); swapped with the Coulomb set around the dispersion pass
+    double dispAlpha = 0;
+    int dispGrid[3] = {0, 0, 0};
+    bool dispersionPass = false;             // launchPme is running the dispersion (C6) chain
+    std::vector<double> subsetC6Self;        // sum over the subset's atoms of c6^2 / 12 (self term, :212)
+    int ewaldKmax[3] = {0, 0, 0};            // Ewald: reciprocal vectors per axis (numRx, numRy, numRz)
+    int ewaldNK = 0;                         // vectors in the half space
     std::vector<int> subsets;
     std::vector<double> baseQ, baseSig, baseEps;
     int nExc = 0, num14 = 0, nGlobals = 0;
@@ -113,6 +123,8 @@ struct Context {
     Buf<float> dChargeF;                     // q*sqrt(K)
     Buf<float2> dSigEps;
     Buf<double> dCharge;                     // q (double)
+    Buf<float> dC6F;                         // LJPME: c6 = 8 (sigma/2)^3 2 sqrt(eps) per particle (:395-396), the dispersion grid's "charge"
+    Buf<double> dC6D;
     Buf<int> dExclStart, dExclList;          // CSR over particles (symmetric)
     Buf<int2> dExcPair;                      // [nExc]
     Buf<double4> dExcParam;                  // [nExc] (sigma, 4eps, K*qq, is14 ? 1 : 0)
@@ -147,6 +159,12 @@ struct Context {
     Buf<double> dModuli;                     // [nx+ny+nz]
     Buf<double> dErfcTab;                    // see ERFC_TAB_ROW
     Buf<float2> dTwiddle;                    // [nx+ny+nz]
+    // LJPME keeps a second set of the tables that depend on (alpha, grid)
+    Buf<float> dEtermDisp; Buf<double> dEtermDDisp, dModuliDisp; Buf<double2> dTwiddleDDisp; Buf<float2> dTwiddleDisp;
+    double etermBoxDisp[3] = {0, 0, 0};
+    std::vector<double> hModuliDisp;
+    Buf<int4> dEwaldK;                       // Ewald: half space of reciprocal vectors (rx, ry, rz, 0)
+    Buf<double2> dEwaldSums, dEwaldMixed;    // [nK][MAX_SUBSETS] structure factors; lambda-mixed factors
     Buf<unsigned long long> dPairStats;      // [0] count, [1] hash
     Buf<int2> dPairDump;
     // host mirrors
@@ -212,7 +230,10 @@ int launchPairs(Context& c, bool wantEnergy, int mode);         // mode 0: force
 int launchBonded(Context& c, const double* dPos, bool periodicBox);
 int launchPme(Context& c, bool wantEnergy, int half);    // half 0: spread..y forward; 1: x/conv..gather
 int launchFinalize(Context& c, void* dOut, int format, long long paddedAtoms, int accumulate, const int* atomIndex);
+int launchEwald(Context& c, bool wantEnergy);               // plain Ewald reciprocal sum (k_ewald.cu)
+int uploadEwaldVectors(Context& c);
 int prepareEterm(Context& c);
+void swapPmeTables(Context& c);                              // Coulomb <-> dispersion (alpha, grid, tables)
 int uploadPmeTables(Context& c);
 
 void timerMark(Context& c, const char* name);   // records an event when profiling

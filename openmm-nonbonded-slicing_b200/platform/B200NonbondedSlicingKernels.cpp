@@ -106,6 +106,18 @@ void B200CalcSlicedNonbondedForceKernel::describe(const System& system, const Sl
         s.pme_grid[1] = findLegalFFTDimension(ny);
         s.pme_grid[2] = findLegalFFTDimension(nz);
     }
+    if (force.getNonbondedMethod() == SlicedNonbondedForce::Ewald) {
+        int kx, ky, kz;
+        SlicedNonbondedForceImpl::calcEwaldParameters(system, force, s.ewald_alpha, kx, ky, kz);         // :158-162
+        s.ewald_kmax[0] = kx; s.ewald_kmax[1] = ky; s.ewald_kmax[2] = kz;
+    }
+    if (force.getNonbondedMethod() == SlicedNonbondedForce::LJPME) {
+        int nx, ny, nz;
+        SlicedNonbondedForceImpl::calcPMEParameters(system, force, s.dispersion_alpha, nx, ny, nz, true);  // :172-173
+        s.dispersion_grid[0] = findLegalFFTDimension(nx);
+        s.dispersion_grid[1] = findLegalFFTDimension(ny);
+        s.dispersion_grid[2] = findLegalFFTDimension(nz);
+    }
     if (force.getUseDispersionCorrection()) {           // :181-184, the unchanged API library does the maths
         d.dispersion = SlicedNonbondedForceImpl::calcDispersionCorrections(system, force);
         s.dispersion_coefficients = d.dispersion.data();

@@ -11,6 +11,7 @@ public:
     NonbondedForceImpl(const NonbondedForce& owner);
     virtual ~NonbondedForceImpl();
     static void calcPMEParameters(const System& system, const NonbondedForce& force, double& alpha, int& xsize, int& ysize, int& zsize, bool lj);
+    static void calcEwaldParameters(const System& system, const NonbondedForce& force, double& alpha, int& kmaxx, int& kmaxy, int& kmaxz);
 };
 }
 #endif

@@ -20,6 +20,9 @@ std::string buildSystem(const nbs_system_desc& d, const double* globalValues, Sy
     s.rfDielectric = d.rf_dielectric;
     s.alpha = d.ewald_alpha;
     for (int k = 0; k < 3; k++) s.grid[k] = d.pme_grid[k];
+    for (int k = 0; k < 3; k++) s.kmax[k] = d.ewald_kmax[k];
+    s.dispersionAlpha = d.dispersion_alpha;
+    for (int k = 0; k < 3; k++) s.dispersionGrid[k] = d.dispersion_grid[k];
     // ReferenceNonbondedSlicingKernels.cpp:146-154 -- NoCutoff disables the switch; :168-171 the
     // non-periodic methods never use periodic exceptions.
     s.useSwitch = d.method != NBS_METHOD_NOCUTOFF && d.use_switching_function;

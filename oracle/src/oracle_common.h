@@ -43,6 +43,9 @@ struct System {
     std::vector<double> dispersionCoefficients;             // [numSlices]                  :181-184
     double cutoff = 0, switchingDistance = 0, rfDielectric = 78.3, alpha = 0;
     int grid[3] = {0, 0, 0};
+    int kmax[3] = {0, 0, 0};                                // Ewald: numRx, numRy, numRz   :158-162
+    double dispersionAlpha = 0;                             // LJPME                        :168-175
+    int dispersionGrid[3] = {0, 0, 0};
     bool useSwitch = false, exceptionsPeriodic = false;
 };
 

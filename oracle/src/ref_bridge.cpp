@@ -26,8 +26,10 @@ std::string executeReference(const System& s, const double* pos, const Box& box,
         const bool ewald = method == NBS_METHOD_EWALD;
         const bool pme = method == NBS_METHOD_PME;
         const bool ljpme = method == NBS_METHOD_LJPME;
-        if (ewald || ljpme)
-            return "oracle bridge: Ewald/LJPME need calcEwaldParameters / a dispersion grid from OpenMM [external]";
+        // kmax / the dispersion grid come with the description (calcEwaldParameters / calcPMEParameters are
+        // OpenMM's [external]; the host mirror restates them, api.py SlicedNonbondedForceImpl)
+        if (ewald && !box.rectangular())
+            return "SlicedNonbondedForce: Ewald is not supported with non-rectangular boxes.  Use PME instead.";
         std::vector<OpenMM::Vec3> posData(s.n), forceData(s.n);
         for (int i = 0; i < s.n; i++) {
             posData[i] = OpenMM::Vec3(pos[3*i], pos[3*i+1], pos[3*i+2]);
@@ -50,24 +52,31 @@ std::string executeReference(const System& s, const double* pos, const Box& box,
         ReferenceSlicedLJCoulombIxn clj;
         OpenMM::NeighborList neighborList;
         if (method != NBS_METHOD_NOCUTOFF) {
-            buildNeighborList(s, pos, box, periodic || pme, neighbors);
+            buildNeighborList(s, pos, box, periodic || ewald || pme || ljpme, neighbors);
             neighborList.assign(neighbors.begin(), neighbors.end());
             clj.setUseCutoff(s.cutoff, neighborList, s.rfDielectric);
         }
         double t1 = now();
-        if (periodic || pme) {
+        if (periodic || ewald || pme || ljpme) {
             double minAllowedSize = 1.999999*s.cutoff;
             if (box.v[0][0] < minAllowedSize || box.v[1][1] < minAllowedSize || box.v[2][2] < minAllowedSize)
                 return "The periodic box size has decreased to less than twice the nonbonded cutoff.";
             clj.setPeriodic(boxVectors);
             clj.setPeriodicExceptions(s.exceptionsPeriodic);
         }
+        if (ewald)
+            clj.setUseEwald(s.alpha, s.kmax[0], s.kmax[1], s.kmax[2]);
         if (pme)
             clj.setUsePME(s.alpha, gridSize);
+        if (ljpme) {
+            int dispersionGrid[3] = {s.dispersionGrid[0], s.dispersionGrid[1], s.dispersionGrid[2]};
+            clj.setUsePME(s.alpha, gridSize);
+            clj.setUseLJPME(s.dispersionAlpha, dispersionGrid);
+        }
         if (s.useSwitch)
             clj.setUseSwitchingFunction(s.switchingDistance);
         double tRecip = 0;
-        if (pme && includeReciprocal) {
+        if ((pme || ewald || ljpme) && includeReciprocal) {
             double a = now();
             clj.calculatePairIxn(s.n, posData, s.numSubsets, s.subsets, particleParamArray, sliceLambdas, s.exclusions,
                                  forceData, sliceEnergies, false, true);
@@ -88,7 +97,7 @@ std::string executeReference(const System& s, const double* pos, const Box& box,
                 int slice = s.slice14[k];
                 nonbonded14.calculateBondIxn(indices, posData, params, forceData, sliceLambdas[slice], sliceEnergies[slice]);
             }
-            if (periodic || pme) {
+            if (periodic || ewald || pme || ljpme) {
                 double volume = box.v[0][0]*box.v[1][1]*box.v[2][2];
                 for (int slice = 0; slice < s.numSlices; slice++)
                     sliceEnergies[slice][1] += s.dispersionCoefficients[slice]/volume;

@@ -1,7 +1,7 @@
 """The reference's analytic known-answer tests (tests/TestSlicedNonbondedForce.h; restated in
 test_oracle_golden.py, where they pin the CPU oracles) run against the CUDA path itself: the same test bodies,
 the "B200" platform instead of an oracle platform.  Everything the device implements is here -- NoCutoff,
-CutoffNonPeriodic, CutoffPeriodic, PME, exceptions, offsets, switching function, dispersion correction, force
+CutoffNonPeriodic, CutoffPeriodic, PME, LJPME (testEwaldExceptions), exceptions, offsets, switching function, dispersion correction, force
 groups; triclinic boxes are not implemented on the device and stay oracle-only."""
 import pytest
 
@@ -11,7 +11,7 @@ pytestmark = pytest.mark.gpu
 
 NAMES = ["test_coulomb", "test_lj", "test_exclusions_and_14", "test_cutoff", "test_cutoff14", "test_periodic",
          "test_periodic_exceptions", "test_dispersion_correction", "test_switching_function", "test_parameter_offsets",
-         "test_direct_and_reciprocal", "test_parameter_clash"]
+         "test_direct_and_reciprocal", "test_ewald_exceptions", "test_parameter_clash"]
 
 
 @pytest.fixture(scope="module")

@@ -223,6 +223,103 @@ def test_random_systems(nbs, platform, oracle, seed, nsub, grid, n):
     assert_equal_tol(b.getPotentialEnergy(), a.getPotentialEnergy(), 1e-5)
 
 
+@pytest.mark.parametrize("seed,nsub,n,tol", [(31, 3, 300, 5e-4), (32, 1, 97, 1e-4), (33, 8, 1000, 5e-4)])
+def test_ewald_random_systems(nbs, platform, oracle, seed, nsub, n, tol):
+    """Plain Ewald (ReferenceSlicedLJCoulombIxn.cpp:256-358) on the device: erfc direct space and exclusion
+    corrections as for PME, reciprocal sum over the half space of k vectors (csrc/k_ewald.cu); direct-only,
+    reciprocal-only and full evaluations, derivatives and the pair set against the oracle."""
+    rng = np.random.default_rng(seed)
+    system, force, positions = random_system(nbs, rng, n=n, nsub=nsub, L=2.6 if n < 500 else 3.4, method="Ewald")
+    force.setEwaldErrorTolerance(tol)
+    ctx = nbs.Context(system, platform)
+    ref = nbs.Context(system, oracle.OraclePlatform("port"))
+    for c in (ctx, ref):
+        c.setPositions(positions)
+        c.setParameter("off", 0.45)
+    for lc, lv in ((0.7, 0.4), (0.0, 1.0)):
+        for c in (ctx, ref):
+            c.setParameter("lc", lc)
+            c.setParameter("lv", lv)
+        a = ctx.getState(getEnergy=True, getForces=True, getParameterDerivatives=True)
+        b = ref.getState(getEnergy=True, getForces=True, getParameterDerivatives=True)
+        assert force_rel_rms(a.getForces(), b.getForces()) <= F_TOL
+        check_energies(ctx.impls[0].kernel.lastSliceEnergies, ref.impls[0].kernel.lastSliceEnergies)
+        for name, value in b.getEnergyParameterDerivatives().items():
+            assert_equal_tol(value, a.getEnergyParameterDerivatives()[name], E_TOL)
+        count, h, _ = ctx.impls[0].kernel.getPairSet(with_pairs=False)
+        r = ref.impls[0].kernel.lastResult
+        assert (count, h) == (r.pair_count, r.pair_hash)
+    kernel = ctx.impls[0].kernel
+    lam = rng.uniform(0.2, 1.0, size=(force.getNumSlices(), 2))
+    gv = np.array([0.45, 0.0, 1.0])
+
+    def run(tag, direct, recip):
+        r = oracle.evaluate(kernel.desc, positions, kernel_box, lam, gv, direct, recip, kind="port")
+        return r.slice_energies, r.forces, r.pair_count, r.pair_hash
+    kernel_box = np.array(system.getDefaultPeriodicBoxVectors()).reshape(9)
+    three_way(kernel, kernel.desc, positions, kernel_box, lam, run)
+
+
+@pytest.mark.parametrize("seed,nsub,n,grid,dgrid", [(41, 3, 300, (20, 20, 20), (12, 12, 12)), (42, 1, 97, (24, 18, 30), (10, 14, 9)),
+                                                     (43, 4, 1000, (22, 26, 22), (16, 15, 16))])
+def test_ljpme_random_systems(nbs, platform, oracle, seed, nsub, n, grid, dgrid):
+    """LJPME on the device against the reference's own compiled TUs (the port does not restate LJPME): direct space
+    with the multiplicative C6 term taken out and the potential shift (ReferenceSlicedLJCoulombIxn.cpp:398-426),
+    dispersion exclusion corrections (:487-504), self term (:211-212) and the second PME chain on the dispersion grid
+    (ReferencePME.cpp:499-595, 814-871); direct-only, reciprocal-only, full; derivatives; pair set.
+    Multi-subset cases keep nx == nz: the reference's gather indexes subset grids with sj*nz instead of sj*nx
+    (ReferencePME.cpp:682), which only coincides with its own spreading when nx == nz."""
+    if not oracle.available("reference"):
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(seed)
+    system, force, positions = random_system(nbs, rng, n=n, nsub=nsub, L=2.6 if n < 500 else 3.4, grid=grid, method="LJPME")
+    force.setLJPMEParameters(2.4, *dgrid)
+    ctx = nbs.Context(system, platform)
+    ref = nbs.Context(system, oracle.OraclePlatform("reference"))
+    assert ctx.impls[0].kernel.getLJPMEParameters() == (2.4,)+tuple(dgrid)
+    for c in (ctx, ref):
+        c.setPositions(positions)
+        c.setParameter("off", 0.45)
+    for lc, lv in ((0.7, 0.4), (1.0, 0.0)):
+        for c in (ctx, ref):
+            c.setParameter("lc", lc)
+            c.setParameter("lv", lv)
+        a = ctx.getState(getEnergy=True, getForces=True, getParameterDerivatives=True)
+        b = ref.getState(getEnergy=True, getForces=True, getParameterDerivatives=True)
+        assert force_rel_rms(a.getForces(), b.getForces()) <= F_TOL
+        check_energies(ctx.impls[0].kernel.lastSliceEnergies, ref.impls[0].kernel.lastSliceEnergies)
+        for name, value in b.getEnergyParameterDerivatives().items():
+            assert_equal_tol(value, a.getEnergyParameterDerivatives()[name], E_TOL)
+        count, h, _ = ctx.impls[0].kernel.getPairSet(with_pairs=False)
+        r = ref.impls[0].kernel.lastResult
+        assert (count, h) == (r.pair_count, r.pair_hash)
+    kernel = ctx.impls[0].kernel
+    lam = rng.uniform(0.2, 1.0, size=(force.getNumSlices(), 2))
+    gv = np.array([0.45, 0.0, 1.0])
+    box = np.array(system.getDefaultPeriodicBoxVectors()).reshape(9)
+
+    def run(tag, direct, recip):
+        r = oracle.evaluate(kernel.desc, positions, box, lam, gv, direct, recip, kind="reference")
+        return r.slice_energies, r.forces, r.pair_count, r.pair_hash
+    three_way(kernel, kernel.desc, positions, box, lam, run)
+
+
+def test_ewald_c1(nbs, platform, systems, oracle):
+    """The TIP3P box of BASELINE.json config 0 with the method switched to Ewald, three repeated evaluations
+    (plain launches, graph capture, graph replay)."""
+    s = systems.make_system("C1")
+    s.force.setNonbondedMethod(s.force.Ewald)
+    kernel = nbs.B200CalcSlicedNonbondedForceKernel(platform)
+    kernel.initialize(s.system, s.force)
+    lam = np.random.default_rng(5).uniform(0.2, 1.0, size=(s.force.getNumSlices(), 2))
+    r = oracle.evaluate(kernel.desc, s.positions, s.box, lam, None, True, True, kind="port")
+    for _ in range(3):
+        forces = np.zeros((648, 3))
+        e = kernel._evaluate(s.positions, s.box, lam, np.zeros(0), True, True, forces)
+        assert force_rel_rms(forces, r.forces) <= F_TOL
+        check_energies(e, r.slice_energies)
+
+
 def test_tiny_and_degenerate_systems(nbs, platform, oracle):
     """Two particles; a subset with no particles; no exceptions at all; atoms exactly on the box edge."""
     for positions in ([[0, 0, 0], [0.3, 0.1, 0]], [[0.0, 2.0, 4.0], [3.9, 0.0, 0.05]]):

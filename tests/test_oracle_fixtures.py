@@ -33,10 +33,10 @@ def test_port_matches_reference_fixture(nbs, oracle, systems, name):
             assert r.pair_hash == int(g["pair_hash"][0])
 
 
-def random_system(nbs, rng, n=300, nsub=3, L=2.6, grid=(20, 20, 20), with_offsets=True, net_charge=True):
+def random_system(nbs, rng, n=300, nsub=3, L=2.6, grid=(20, 20, 20), with_offsets=True, net_charge=True, method="PME"):
     system = nbs.System()
     force = nbs.SlicedNonbondedForce(nsub)
-    force.setNonbondedMethod(force.PME)
+    force.setNonbondedMethod(getattr(force, method))
     force.setCutoffDistance(1.0)
     force.setPMEParameters(2.8, *grid)
     system.setDefaultPeriodicBoxVectors([L, 0, 0], [0, L, 0], [0, 0, L])
@@ -174,3 +174,57 @@ def slicing_equals_rescaled_parameters(nbs, platform, etol, ftol):
     d = ctx2.getState(getEnergy=True, getParameterDerivatives=True)
     derivs = d.getEnergyParameterDerivatives()
     assert_equal_tol(energies[1.0]-energies[0.0], derivs["lambda"]+derivs["lambdaSq"], etol)
+
+
+@pytest.mark.parametrize("seed,nsub,tol", [(11, 3, 5e-4), (12, 1, 1e-4), (13, 4, 1e-5)])
+def test_ewald_port_matches_compiled_reference(nbs, oracle, seed, nsub, tol):
+    """Plain Ewald (ReferenceSlicedLJCoulombIxn.cpp:256-358): the restatement against the reference's own TU,
+    direct-only / reciprocal-only / full, with kmax from the restated calcEwaldParameters."""
+    if not oracle.available("reference"):
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(seed)
+    system, force, positions = random_system(nbs, rng, n=150, nsub=nsub, L=2.3 + 0.1*nsub, method="Ewald")
+    force.setEwaldErrorTolerance(tol)
+    desc = nbs.build_desc(system, force)
+    assert min(desc.desc.ewald_kmax) >= 1 and all(k % 2 == 1 for k in desc.desc.ewald_kmax)
+    box = np.array(system.getDefaultPeriodicBoxVectors()).reshape(9)
+    lam = rng.uniform(0.1, 1.0, size=(force.getNumSlices(), 2))
+    gv = np.array([0.3, 0.7, 0.4])
+    for direct, recip in ((True, True), (True, False), (False, True)):
+        a = oracle.evaluate(desc, positions, box, lam, gv, direct, recip, kind="port")
+        b = oracle.evaluate(desc, positions, box, lam, gv, direct, recip, kind="reference")
+        assert force_rel_rms(a.forces, b.forces) < 1e-12
+        assert np.allclose(a.slice_energies, b.slice_energies, rtol=1e-11, atol=1e-9)
+        assert (a.pair_count, a.pair_hash) == (b.pair_count, b.pair_hash)
+
+
+def test_ewald_agrees_with_pme(nbs, oracle):
+    """Second opinion on both reciprocal sums (they share no code): at a tight tolerance the plain Ewald sum and
+    PME give the same forces and slice energies (cf. the method matrix of tests/TestSlicedNonbondedForce.h:1493-1500,
+    whose arbiter -- OpenMM's NonbondedForce -- is not available here)."""
+    rng = np.random.default_rng(21)
+    system, force, positions = random_system(nbs, rng, n=160, nsub=3, L=2.4, net_charge=False)
+    box = np.array(system.getDefaultPeriodicBoxVectors()).reshape(9)
+    lam = rng.uniform(0.1, 1.0, size=(6, 2))
+    gv = np.array([0.3, 0.7, 0.4])
+    force.setEwaldErrorTolerance(1e-6)
+    force.setPMEParameters(0, 0, 0, 0)
+    results = {}
+    for method in (force.Ewald, force.PME):
+        force.setNonbondedMethod(method)
+        results[method] = oracle.evaluate(nbs.build_desc(system, force), positions, box, lam, gv, True, True, kind="port")
+    a, b = results[force.Ewald], results[force.PME]
+    assert force_rel_rms(a.forces, b.forces) < 1e-5
+    assert np.abs(a.slice_energies-b.slice_energies).max() < 1e-5*np.abs(b.slice_energies).max()
+
+
+def test_ewald_rejects_triclinic(nbs, oracle):
+    system = nbs.System()
+    system.setDefaultPeriodicBoxVectors([3, 0, 0], [0.5, 3, 0], [0, 0, 3])
+    force = nbs.SlicedNonbondedForce(1)
+    force.setNonbondedMethod(force.Ewald)
+    system.addParticle(1.0)
+    force.addParticle(1.0, 0.3, 0.1)
+    system.addForce(force)
+    with pytest.raises(nbs.OpenMMException, match="Ewald is not supported with non-rectangular boxes"):
+        nbs.Context(system, oracle.OraclePlatform("port"))

@@ -468,6 +468,36 @@ def test_direct_and_reciprocal(nbs, platform):
     assert_equal_tol(e3, e4, 1e-4)
 
 
+def test_ewald_exceptions(nbs, platform):
+    """testEwaldExceptions :947-985 -- LJPME: adding a periodic exception changes the energy by exactly the
+    exception's own Coulomb + LJ energy minus the pair's plain LJ energy (the pair leaves the direct-space sum
+    and both reciprocal sums are backed out by the exclusion corrections, Coulomb and dispersion)."""
+    if getattr(platform, "kind", "") == "port":
+        pytest.skip("LJPME is not restated in the port; the compiled reference covers it")
+    system = nbs.System()
+    for _ in range(4):
+        system.addParticle(1.0)
+    system.setDefaultPeriodicBoxVectors([2, 0, 0], [0, 2, 0], [0, 0, 2])
+    force = nbs.SlicedNonbondedForce(1)
+    system.addForce(force)
+    force.setNonbondedMethod(force.LJPME)
+    force.setCutoffDistance(1.0)
+    force.addParticle(1.0, 0.5, 1.0)
+    force.addParticle(1.0, 0.5, 1.0)
+    force.addParticle(-1.0, 0.5, 1.0)
+    force.addParticle(-1.0, 0.5, 1.0)
+    context = nbs.Context(system, platform)
+    context.setPositions([[0, 0, 0], [1.5, 0, 0], [0, 0.5, 0.5], [0.2, 1.3, 0]])
+    e1 = context.getState(getEnergy=True).getPotentialEnergy()
+    force.addException(0, 1, 0.2, 0.8, 2.0)
+    force.setExceptionsUsePeriodicBoundaryConditions(True)
+    context.reinitialize(True)
+    e2 = context.getState(getEnergy=True).getPotentialEnergy()
+    r = 0.5
+    expected = nbs.ONE_4PI_EPS0*(0.2-1.0)/r + 4*2.0*((0.8/r)**12-(0.8/r)**6) - 4*1.0*((0.5/r)**12-(0.5/r)**6)
+    assert_equal_tol(expected, e2-e1, 1e-4)
+
+
 def test_parameter_clash(nbs, platform):
     """python/tests/TestSlicedNonbondedForce.py:51-67 and SlicedNonbondedForceImpl.cpp:114-131"""
     system = nbs.System()

@@ -17,7 +17,7 @@ struct BondedArgs {
     int rank, nRanks;                // exception e belongs to rank e % nRanks
     int doExclusionCorrection;       // Ewald, PME, LJPME
     int periodic;                    // exceptionsUsePeriodic
-    double3 box, invBox;
+    double3 box, invBox, tilt;       // tilt = (bx, cx, cy) of a triclinic box
     double alpha;
     int ljpme;                       // LJPME: also back out the dispersion grid's contribution (:487-504)
     double dispAlpha;
@@ -39,9 +39,12 @@ __global__ void k_bonded(const BondedArgs a) {
         const int s1 = a.slotOf ? a.slotOf[pr.x] : pr.x, s2 = a.slotOf ? a.slotOf[pr.y] : pr.y;
         double dx = a.pos[3*s1] - a.pos[3*s2], dy = a.pos[3*s1+1] - a.pos[3*s2+1], dz = a.pos[3*s1+2] - a.pos[3*s2+2];
         if (a.periodic) {
+            // ReferenceForce::getDeltaRPeriodic [external]: subtract whole c, then b, then a vectors (tilt = bx, cx, cy)
+            const double kz = floor(dz*a.invBox.z + 0.5);
+            dx -= kz*a.tilt.y; dy -= kz*a.tilt.z; dz -= kz*a.box.z;
+            const double ky = floor(dy*a.invBox.y + 0.5);
+            dx -= ky*a.tilt.x; dy -= ky*a.box.y;
             dx -= a.box.x*floor(dx*a.invBox.x + 0.5);
-            dy -= a.box.y*floor(dy*a.invBox.y + 0.5);
-            dz -= a.box.z*floor(dz*a.invBox.z + 0.5);
         }
         const double r2 = dx*dx + dy*dy + dz*dz;
         const double r = sqrt(r2);
@@ -116,6 +119,7 @@ int launchBonded(Context& c, const double* dPos, bool periodicBox) {
     a.periodic = (c.excPeriodic && periodicBox) ? 1 : 0;
     a.box = make_double3(c.geom.box[0], c.geom.box[1], c.geom.box[2]);
     a.invBox = make_double3(c.geom.invBox[0], c.geom.invBox[1], c.geom.invBox[2]);
+    a.tilt = make_double3(c.geom.tilt[0], c.geom.tilt[1], c.geom.tilt[2]);
     a.alpha = c.alpha;
     a.ljpme = c.ljpme() ? 1 : 0;
     a.dispAlpha = c.dispAlpha;

@@ -21,16 +21,22 @@
 namespace nbs {
 
 constexpr int NL_PREFETCH = 4;  // 32-atom chunks of a column range whose loads are in flight together
-constexpr int JBUF = 768;      // per-warp staging capacity (entries)
-constexpr int XBUF = 96;
+// Per-warp staging capacities (entries) follow the list capacities (3/8 of them: 768 / 96 at the initial 2048 / 256),
+// so a system whose blocks overflow the staging -- tiny boxes seen through many periodic images -- gets more of
+// both when the evaluation is repeated with doubled capacities; bounded by the shared memory of an SM.
+static int stageJ(int capJ) { return std::max(32, std::min(4096, capJ*3/8)); }
+static int stageX(int capX) { return std::max(32, std::min(1024, capX*3/8)); }
 
 struct BuildArgs {
     int N, maxBlocks, capJ, capX;
+    int stageJ, stageX;        // per-warp staging capacities
     int blockPeriod, blockOffset, blockWidth;   // this rank's share of the i-blocks
     int ncx, ncy, nzb;
     int periodic;              // 0: NoCutoff / CutoffNonPeriodic -- no images
     float colWx, colWy, binH;
     float Lx, Ly, Lz;
+    float bx, cx, cy;          // triclinic tilt (nm): b = (bx, Ly, 0), c = (cx, cy, Lz)
+    long long shiftB, shiftCx, shiftCy;   // the same in fixed-point units of their axis
     float sx, sy, sz;          // nm per fixed-point unit
     float reach;               // cutoff + margin
     const int* counters;
@@ -46,14 +52,15 @@ struct BuildArgs {
     double* overflowFlag;      // energy[2*MAX_SLICES]: the same flag as a double, so that it all-reduces
 };
 
-__global__ void __launch_bounds__(BUILD_WARPS*32) k_build_lists(BuildArgs a) {
+__global__ void __launch_bounds__(BUILD_WARPS*32, 4) k_build_lists(BuildArgs a) {
     const int lb = blockIdx.x;                  // rank-local block index (lists are stored there)
     const int b = localToGlobalBlock(lb, a.blockPeriod, a.blockOffset, a.blockWidth);
     if (b >= a.counters[0]) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    __shared__ int jbuf[BUILD_WARPS][JBUF];
-    __shared__ int xbuf[BUILD_WARPS][XBUF];
-    __shared__ unsigned xmbuf[BUILD_WARPS][XBUF];
+    extern __shared__ int stage[];              // [BUILD_WARPS][stageJ] j entries, [BUILD_WARPS][stageX] x entries, masks
+    int* const jbuf = stage + warp*a.stageJ;
+    int* const xbuf = stage + BUILD_WARPS*a.stageJ + warp*a.stageX;
+    unsigned* const xmbuf = (unsigned*) (stage + BUILD_WARPS*(a.stageJ + a.stageX)) + warp*a.stageX;
     __shared__ int counts[2][BUILD_WARPS];
 
     const int first = a.blkFirst[b], count = a.blkCount[b];
@@ -65,8 +72,13 @@ __global__ void __launch_bounds__(BUILD_WARPS*32) k_build_lists(BuildArgs a) {
     const float hix = hi.x*a.sx, hiy = hi.y*a.sy, hiz = hi.z*a.sz;
     const float ex = (float) (hi.x - lo.x)*a.sx, ey = (float) (hi.y - lo.y)*a.sy, ez = (float) (hi.z - lo.z)*a.sz;
     const float R = a.reach, R2 = R*R;
-    const int uxLo = (int) floorf((lox - R)/a.colWx), uxHi = (int) floorf((hix + R)/a.colWx);
-    const int uyLo = (int) floorf((loy - R)/a.colWy), uyHi = (int) floorf((hiy + R)/a.colWy);
+    // Unwrapped column indices (ux, uy) that can hold neighbours.  Image (kx, ky, kz) of the brick is displaced by
+    // kx a + ky b + kz c, i.e. by (kx ax + ky bx + kz cx, ky by + kz cy, kz cz): seen from the columns of that image
+    // the block's box sits at x - ky bx - kz cx, y - kz cy.  The candidate range covers every (ky, kz); the exact gap
+    // test per image follows below.  (Rectangular boxes: bx = cx = cy = 0 and this is the plain 3 x 3 x 3 walk.)
+    const float tiltX = fabsf(a.bx) + fabsf(a.cx), tiltY = fabsf(a.cy);
+    const int uxLo = (int) floorf((lox - R - tiltX)/a.colWx), uxHi = (int) floorf((hix + R + tiltX)/a.colWx);
+    const int uyLo = (int) floorf((loy - R - tiltY)/a.colWy), uyHi = (int) floorf((hiy + R + tiltY)/a.colWy);
     const int nuy = uyHi - uyLo + 1;
     const int nCand = (uxHi - uxLo + 1)*nuy;
 
@@ -74,20 +86,21 @@ __global__ void __launch_bounds__(BUILD_WARPS*32) k_build_lists(BuildArgs a) {
     bool overflow = false;
     for (int cand = warp; cand < nCand; cand += BUILD_WARPS) {
         const int ux = uxLo + cand/nuy, uy = uyLo + cand % nuy;
-        const int kx = (ux >= a.ncx) - (ux < 0), ky = (uy >= a.ncy) - (uy < 0);
+        const int kx = (ux + 2*a.ncx)/a.ncx - 2, ky = (uy + 2*a.ncy)/a.ncy - 2;     // floor division for ux >= -2 ncx
         const int wx = ux - kx*a.ncx, wy = uy - ky*a.ncy;
-        if (wx < 0 || wx >= a.ncx || wy < 0 || wy >= a.ncy) continue;      // more than one box away: cannot interact
+        if (kx < -2 || kx > 2 || ky < -1 || ky > 1 || ux < -2*a.ncx || uy < -2*a.ncy) continue;   // too far to interact
         if (!a.periodic && (kx != 0 || ky != 0)) continue;
         const int colJ = wx*a.ncy + wy;
         if (colJ < colI) continue;                                         // owned by the other block
-        const float gx = fmaxf(0.f, fmaxf(ux*a.colWx - hix, lox - (ux+1)*a.colWx));
-        const float gy = fmaxf(0.f, fmaxf(uy*a.colWy - hiy, loy - (uy+1)*a.colWy));
-        const float d2 = gx*gx + gy*gy;
-        if (d2 > R2) continue;
-        const float dz = sqrtf(R2 - d2) + 1e-4f;
-        const float zlo = loz - dz, zhi = hiz + dz;
         for (int kz = -1; kz <= 1; kz++) {
             if (!a.periodic && kz != 0) continue;
+            const float offX = ky*a.bx + kz*a.cx, offY = kz*a.cy;            // the block's box as this image sees it
+            const float gx = fmaxf(0.f, fmaxf(ux*a.colWx - (hix - offX), (lox - offX) - (ux+1)*a.colWx));
+            const float gy = fmaxf(0.f, fmaxf(uy*a.colWy - (hiy - offY), (loy - offY) - (uy+1)*a.colWy));
+            const float d2 = gx*gx + gy*gy;
+            if (d2 > R2) continue;
+            const float dz = sqrtf(R2 - d2) + 1e-4f;
+            const float zlo = loz - dz, zhi = hiz + dz;
             const float segLo = fmaxf(zlo, kz*a.Lz) - kz*a.Lz, segHi = fminf(zhi, (kz+1)*a.Lz) - kz*a.Lz;
             if (segHi < segLo) continue;
             const int zb0 = max(0, min(a.nzb-1, (int) floorf(segLo/a.binH)));
@@ -95,8 +108,9 @@ __global__ void __launch_bounds__(BUILD_WARPS*32) k_build_lists(BuildArgs a) {
             int s = a.binStart[colJ*a.nzb + zb0];
             const int e = a.binStart[colJ*a.nzb + zb1 + 1];
             if (colJ == colI) s = max(s, first);                           // j must not precede the block
-            const long long shx = (long long) kx << 32, shy = (long long) ky << 32, shz = (long long) kz << 32;
-            const int code = ((kx+1) + 3*(ky+1) + 9*(kz+1)) << J_SHIFT_BITS;
+            const long long shx = ((long long) kx << 32) + ky*a.shiftB + kz*a.shiftCx;
+            const long long shy = ((long long) ky << 32) + kz*a.shiftCy, shz = (long long) kz << 32;
+            const int code = ((kx+2) + 5*((ky+1) + 3*(kz+1))) << J_SHIFT_BITS;
             for (int jb = s; jb < e; jb += 32*NL_PREFETCH) {
               // the candidates' positions and exclusion ranges of NL_PREFETCH chunks are requested together: the
               // walk is a chain of L2 round trips, and the ballots below only order the OUTPUT, not the loads
@@ -142,11 +156,11 @@ __global__ void __launch_bounds__(BUILD_WARPS*32) k_build_lists(BuildArgs a) {
                 if (pass) {
                     if (imask == 0) {
                         const int slot = nj + __popc(mJ & below);
-                        if (slot < JBUF) jbuf[warp][slot] = code | j;
+                        if (slot < a.stageJ) jbuf[slot] = code | j;
                     }
                     else {
                         const int slot = nx + __popc(mX & below);
-                        if (slot < XBUF) { xbuf[warp][slot] = code | j; xmbuf[warp][slot] = imask; }
+                        if (slot < a.stageX) { xbuf[slot] = code | j; xmbuf[slot] = imask; }
                     }
                 }
                 nj += __popc(mJ);
@@ -155,7 +169,7 @@ __global__ void __launch_bounds__(BUILD_WARPS*32) k_build_lists(BuildArgs a) {
             }
         }
     }
-    if (nj > JBUF || nx > XBUF) { overflow = true; nj = min(nj, JBUF); nx = min(nx, XBUF); }
+    if (nj > a.stageJ || nx > a.stageX) { overflow = true; nj = min(nj, a.stageJ); nx = min(nx, a.stageX); }
     if (lane == 0) { counts[0][warp] = nj; counts[1][warp] = nx; }
     __syncthreads();
     int offJ = 0, offX = 0, totJ = 0, totX = 0;
@@ -171,8 +185,8 @@ __global__ void __launch_bounds__(BUILD_WARPS*32) k_build_lists(BuildArgs a) {
     int* jl = a.jlist + (size_t) lb*a.capJ;
     int* xl = a.xlist + (size_t) lb*a.capX;
     unsigned* xm = a.xmask + (size_t) lb*a.capX;
-    for (int k = lane; k < nj; k += 32) if (offJ + k < totJ) jl[offJ + k] = jbuf[warp][k];
-    for (int k = lane; k < nx; k += 32) if (offX + k < totX) { xl[offX + k] = xbuf[warp][k]; xm[offX + k] = xmbuf[warp][k]; }
+    for (int k = lane; k < nj; k += 32) if (offJ + k < totJ) jl[offJ + k] = jbuf[k];
+    for (int k = lane; k < nx; k += 32) if (offX + k < totX) { xl[offX + k] = xbuf[k]; xm[offX + k] = xmbuf[k]; }
     // pad the last tile of each list with invalid entries
     const int t = threadIdx.x;
     if (t < 32) {
@@ -208,6 +222,8 @@ int launchBuildLists(Context& c) {
     a.periodic = c.periodic ? 1 : 0;
     a.colWx = g.colW[0]; a.colWy = g.colW[1]; a.binH = g.binH;
     a.Lx = (float) g.box[0]; a.Ly = (float) g.box[1]; a.Lz = (float) g.box[2];
+    a.bx = (float) g.tilt[0]; a.cx = (float) g.tilt[1]; a.cy = (float) g.tilt[2];
+    a.shiftB = g.shiftB; a.shiftCx = g.shiftCx; a.shiftCy = g.shiftCy;
     a.sx = g.scale[0]; a.sy = g.scale[1]; a.sz = g.scale[2];
     a.reach = (float) c.cutoffEff + 2e-4f;
     a.counters = c.dCounters.d;
@@ -222,7 +238,14 @@ int launchBuildLists(Context& c) {
     a.items = c.dItems.d;
     a.chunkTiles = c.chunkTiles;
     a.maxItems = (int) std::min<size_t>(c.dItems.cap, 0x7fffffff);
-    k_build_lists<<<c.maxLocalBlocks, BUILD_WARPS*32, 0, c.stream>>>(a);
+    a.stageJ = stageJ(c.capJ); a.stageX = stageX(c.capX);
+    const size_t smem = sizeof(int)*BUILD_WARPS*((size_t) a.stageJ + 2*(size_t) a.stageX);
+    static bool attr[64] = {false};
+    if (!attr[c.device & 63]) {
+        NBS_CUDA_CHECK(cudaFuncSetAttribute(k_build_lists, cudaFuncAttributeMaxDynamicSharedMemorySize, 200*1024));
+        attr[c.device & 63] = true;
+    }
+    k_build_lists<<<c.maxLocalBlocks, BUILD_WARPS*32, smem, c.stream>>>(a);
     c.launches++;
     timerMark(c, "build_lists");
     return NBS_OK;

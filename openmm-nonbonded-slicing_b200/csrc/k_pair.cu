@@ -50,6 +50,7 @@ struct PairArgs {
     int capJ, capX, Npad;
     int blockPeriod, blockOffset, blockWidth;   // this rank's share of the i-blocks
     int chunkTiles;                             // tiles per work item
+    long long shiftB, shiftCx, shiftCy;         // triclinic image shifts (CellGeom), fixed-point units; 0 for a rectangular box
     int nE;                                     // 2 * number of slices
     float sx, sy, sz;
     double dsx, dsy, dsz;
@@ -466,13 +467,19 @@ __global__ void __launch_bounds__(PAIR_WARPS*32, MINCTAS) k_pair(const PairArgs 
             if (entry >= 0) {
                 jIndex = entry & J_INDEX_MASK;
                 const int code = entry >> J_SHIFT_BITS;
-                const int kx = code % 3 - 1, ky = (code/3) % 3 - 1, kz = code/9 - 1;
+                const int kx = code % 5 - 2, ky = (code/5) % 3 - 1, kz = code/15 - 1;
                 const uint4 q = qCur;
-                pj.x = (float) ((long long) q.x + ((long long) kx << 32) - (long long) lo.x)*a.sx;
-                pj.y = (float) ((long long) q.y + ((long long) ky << 32) - (long long) lo.y)*a.sy;
+                // image (kx, ky, kz) is displaced by kx a + ky b + kz c (b and c tilt into x, c into y; zero for a
+                // rectangular box), in fixed-point units of each axis
+                const long long shx = ((long long) kx << 32) + ky*a.shiftB + kz*a.shiftCx;
+                const long long shy = ((long long) ky << 32) + kz*a.shiftCy;
+                pj.x = (float) ((long long) q.x + shx - (long long) lo.x)*a.sx;
+                pj.y = (float) ((long long) q.y + shy - (long long) lo.y)*a.sy;
                 pj.z = (float) ((long long) q.z + ((long long) kz << 32) - (long long) lo.z)*a.sz;
                 pj.w = __uint_as_float(q.w);
-                fixj = make_uint4(q.x, q.y, q.z, (unsigned) __float_as_int(parj.z));
+                // exact coordinates of THIS image modulo the box: the wrapped 32-bit difference to an i atom is then
+                // the displacement to this image for any pair inside the cutoff (<= half the box along every axis)
+                fixj = make_uint4(q.x + (unsigned) shx, q.y + (unsigned) shy, q.z, (unsigned) __float_as_int(parj.z));
             }
             __syncwarp();
             w.jPos[lane] = pj;
@@ -608,6 +615,7 @@ int launchPairs(Context& c, bool wantEnergy, int mode) {
     a.capJ = c.capJ; a.capX = c.capX; a.Npad = c.Npad;
     a.blockPeriod = c.blockPeriod; a.blockOffset = c.blockOffset; a.blockWidth = c.blockWidth;
     a.chunkTiles = c.chunkTiles;
+    a.shiftB = g.shiftB; a.shiftCx = g.shiftCx; a.shiftCy = g.shiftCy;
     a.nE = 2*c.nSl;
     a.sx = g.scale[0]; a.sy = g.scale[1]; a.sz = g.scale[2];
     a.dsx = g.box[0]/4294967296.0; a.dsy = g.box[1]/4294967296.0; a.dsz = g.box[2]/4294967296.0;

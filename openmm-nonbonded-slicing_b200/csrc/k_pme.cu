@@ -181,7 +181,25 @@ struct PmeArgs {
     void* grid; const float* pot;
     unsigned long long* force;
     float fscale[3];             // n_d / L_d
+    // triclinic box (a = (ax,0,0), b = (bx,by,0), c = (cx,cy,cz)): lattice fractions from the brick fractions (u, v, w)
+    // the fixed-point coordinates hold, t_x = u - beta v + delta w, t_y = v - gammaY w, t_z = w (ReferencePME.cpp:
+    // 186-194, 249-251), and the off-diagonal reciprocal-vector terms of the force (:698-700)
+    int triclinic;
+    double beta, gammaY, delta;  // bx/ax, cy/by, (bx cy - by cx)/(ax by)
+    float fr10, fr20, fr21;      // nx r10, nx r20, ny r21
 };
+
+// Brick fractions -> lattice fractions (both 32-bit fixed point); identity for a rectangular box.
+__device__ __forceinline__ uint4 latticeFractions(const PmeArgs& a, uint4 p) {
+    if (!a.triclinic) return p;
+    const double s = 1.0/4294967296.0;
+    const double u = p.x*s, v = p.y*s, w = p.z*s;
+    double tx = u - a.beta*v + a.delta*w, ty = v - a.gammaY*w;
+    tx -= floor(tx); ty -= floor(ty);
+    p.x = (unsigned) (__double2ull_rd(tx*4294967296.0) & 0xffffffffull);
+    p.y = (unsigned) (__double2ull_rd(ty*4294967296.0) & 0xffffffffull);
+    return p;
+}
 
 template <typename T>
 __device__ __forceinline__ void gridCoord(unsigned fixed, int n, int& index, T& frac) {
@@ -194,7 +212,8 @@ __device__ __forceinline__ void gridCoord(unsigned fixed, int n, int& index, T& 
 // 10-14 z) and publish weight lane%5 (and its derivative) in the warp's shared-memory table; the base
 // grid indices come back by shuffle.
 template <typename T>
-__device__ __forceinline__ void splineTable(const PmeArgs& a, const uint4 p, int lane, T* wt, T* dwt, int& ix0, int& iy0, int& iz0) {
+__device__ __forceinline__ void splineTable(const PmeArgs& a, const uint4 pBrick, int lane, T* wt, T* dwt, int& ix0, int& iy0, int& iz0) {
+    const uint4 p = latticeFractions(a, pBrick);
     const int dim = min(lane/5, 2), kk = lane % 5;
     int index; T frac;
     gridCoord<T>(dim == 0 ? p.x : (dim == 1 ? p.y : p.z), dim == 0 ? a.nx : (dim == 1 ? a.ny : a.nz), index, frac);
@@ -485,9 +504,11 @@ __global__ void __launch_bounds__(256) k_gather(const PmeArgs a) {
     }
     fx = warpSum(fx); fy = warpSum(fy); fz = warpSum(fz);
     if (lane == 0) {
+        // F = -q (fx nx r00, fx nx r10 + fy ny r11, fx nx r20 + fy ny r21 + fz nz r22), ReferencePME.cpp:698-700
+        // (the off-diagonal reciprocal-vector terms are zero for a rectangular box)
         atomicAdd(a.force + j, toFixed(-q*fx*a.fscale[0]));
-        atomicAdd(a.force + a.Npad + j, toFixed(-q*fy*a.fscale[1]));
-        atomicAdd(a.force + 2*(size_t) a.Npad + j, toFixed(-q*fz*a.fscale[2]));
+        atomicAdd(a.force + a.Npad + j, toFixed(-q*fmaf(fx, a.fr10, fy*a.fscale[1])));
+        atomicAdd(a.force + 2*(size_t) a.Npad + j, toFixed(-q*fmaf(fx, a.fr20, fmaf(fy, a.fr21, fz*a.fscale[2]))));
     }
 }
 
@@ -495,60 +516,71 @@ __global__ void __launch_bounds__(256) k_gather(const PmeArgs a) {
 // Influence function eterm(k) = exp(-pi^2 m^2 / alpha^2) / (pi V m^2 Bx By Bz), ReferencePME.cpp:426-471
 // (without ONE_4PI_EPS0, which the charges carry).  Recomputed only when the box changes.
 // ---------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void k_eterm(int nx, int ny, int nz, int nzh, double3 invBox, double volume, double alpha,
+// The reference transforms complex-to-complex and applies eterm(k) to every element of the full grid, with the
+// frequency of index k taken as k or k - n (:436-466).  On the Nyquist planes of a TRICLINIC box that convention is not
+// inversion symmetric (index n/2 is its own partner but maps to frequency -n/2 only), so eterm(k) != eterm(partner of
+// k) there and the convolved grid is not Hermitian; the reference then keeps the real part of the inverse transform,
+// which is the transform of the Hermitian part.  The half-spectrum pipeline here gets the same result by using
+// eterm_eff(k) = (eterm(k) + eterm(partner(k)))/2, partner = ((nx-kx)%nx, (ny-ky)%ny, (nz-kz)%nz) -- identical to
+// eterm(k) everywhere for a rectangular box and off the Nyquist planes.
+template <bool DISPERSION>
+__device__ __forceinline__ double influence(int kx, int ky, int kz, int nx, int ny, int nz, double3 invBox, double3 offRecip,
+                                            double volume, double alpha, const double* __restrict__ moduli) {
+    if (!DISPERSION && kx == 0 && ky == 0 && kz == 0) return 0.0;            // :457-460
+    // m = fx r0 + fy r1 + fz r2 with the reciprocal vectors of ReferencePME.cpp:186-194 (offRecip = r10, r20, r21;
+    // zero for a rectangular box)
+    const double fx = (kx < (nx+1)/2 ? kx : kx - nx), fy = (ky < (ny+1)/2 ? ky : ky - ny), fz = (kz < (nz+1)/2 ? kz : kz - nz);
+    const double mx = fx*invBox.x;
+    const double my = fx*offRecip.x + fy*invBox.y;
+    const double mz = fx*offRecip.y + fy*offRecip.z + fz*invBox.z;
+    const double m2 = mx*mx + my*my + mz*mz;
+    const double bsp = moduli[kx]*moduli[nx + ky]*moduli[nx + ny + kz];
+    if (!DISPERSION) return exp(-kPi*kPi*m2/(alpha*alpha))/(m2*kPi*volume*bsp);
+    // dispersion (LJPME), dpme_reciprocal_convolution, ReferencePME.cpp:520-570: eterm = (2 pi^3 sqrt(pi) erfc(b) m^3 +
+    // exp(-b^2) (alpha^3 - 2 alpha pi^2 m^2)) * (-2 pi sqrt(pi) / (6 V Bx By Bz)), b = pi m / alpha; the m = 0 term is kept (:551)
+    const double sqrtPi = 1.7724538509055160273;
+    const double denom = (-2*kPi*sqrtPi/(6.0*volume))/bsp;
+    const double m = sqrt(m2), b = (kPi/alpha)*m;
+    const double fac1 = 2.0*kPi*kPi*kPi*sqrtPi, fac2 = alpha*alpha*alpha, fac3 = -2.0*alpha*kPi*kPi;
+    return (fac1*erfc(b)*m*m2 + exp(-b*b)*(fac2 + fac3*m2))*denom;
+}
+
+template <typename T, bool DISPERSION>
+__global__ void k_eterm(int nx, int ny, int nz, int nzh, double3 invBox, double3 offRecip, double volume, double alpha,
                         const double* __restrict__ moduli, T* __restrict__ eterm) {
     const size_t idx = (size_t) blockIdx.x*blockDim.x + threadIdx.x;
     if (idx >= (size_t) nx*ny*nzh) return;
     const int kz = (int) (idx % nzh), ky = (int) ((idx/nzh) % ny), kx = (int) (idx/((size_t) nzh*ny));
-    if (kx == 0 && ky == 0 && kz == 0) { eterm[idx] = (T) 0; return; }
-    const double mx = (kx < (nx+1)/2 ? kx : kx - nx)*invBox.x;
-    const double my = (ky < (ny+1)/2 ? ky : ky - ny)*invBox.y;
-    const double mz = (kz < (nz+1)/2 ? kz : kz - nz)*invBox.z;
-    const double m2 = mx*mx + my*my + mz*mz;
-    const double denom = m2*kPi*volume*moduli[kx]*moduli[nx + ky]*moduli[nx + ny + kz];
-    eterm[idx] = (T) (exp(-kPi*kPi*m2/(alpha*alpha))/denom);
-}
-
-// Dispersion influence function (LJPME), dpme_reciprocal_convolution, ReferencePME.cpp:520-570:
-// eterm = (2 pi^3 sqrt(pi) erfc(b) m^3 + exp(-b^2) (alpha^3 - 2 alpha pi^2 m^2)) * (-2 pi sqrt(pi) / (6 V Bx By Bz)),
-// b = pi m / alpha; unlike the Coulomb case the m = 0 term is kept (:551).
-template <typename T>
-__global__ void k_eterm_dispersion(int nx, int ny, int nz, int nzh, double3 invBox, double volume, double alpha,
-                                   const double* __restrict__ moduli, T* __restrict__ eterm) {
-    const size_t idx = (size_t) blockIdx.x*blockDim.x + threadIdx.x;
-    if (idx >= (size_t) nx*ny*nzh) return;
-    const int kz = (int) (idx % nzh), ky = (int) ((idx/nzh) % ny), kx = (int) (idx/((size_t) nzh*ny));
-    const double mx = (kx < (nx+1)/2 ? kx : kx - nx)*invBox.x;
-    const double my = (ky < (ny+1)/2 ? ky : ky - ny)*invBox.y;
-    const double mz = (kz < (nz+1)/2 ? kz : kz - nz)*invBox.z;
-    const double m2 = mx*mx + my*my + mz*mz;
-    const double sqrtPi = 1.7724538509055160273;
-    const double denom = (-2*kPi*sqrtPi/(6.0*volume))/(moduli[kx]*moduli[nx + ky]*moduli[nx + ny + kz]);
-    const double m = sqrt(m2), b = (kPi/alpha)*m;
-    const double fac1 = 2.0*kPi*kPi*kPi*sqrtPi, fac2 = alpha*alpha*alpha, fac3 = -2.0*alpha*kPi*kPi;
-    eterm[idx] = (T) ((fac1*erfc(b)*m*m2 + exp(-b*b)*(fac2 + fac3*m2))*denom);
+    const double here = influence<DISPERSION>(kx, ky, kz, nx, ny, nz, invBox, offRecip, volume, alpha, moduli);
+    const double partner = influence<DISPERSION>((nx - kx) % nx, (ny - ky) % ny, (nz - kz) % nz, nx, ny, nz, invBox, offRecip,
+                                                 volume, alpha, moduli);
+    eterm[idx] = (T) (0.5*(here + partner));
 }
 
 int prepareEterm(Context& c) {
     const CellGeom& g = c.geom;
-    if (c.etermBox[0] == g.box[0] && c.etermBox[1] == g.box[1] && c.etermBox[2] == g.box[2]) return NBS_OK;
+    if (c.etermBox[0] == g.box[0] && c.etermBox[1] == g.box[1] && c.etermBox[2] == g.box[2] &&
+        c.etermBox[3] == g.tilt[0] && c.etermBox[4] == g.tilt[1] && c.etermBox[5] == g.tilt[2]) return NBS_OK;
     const int nx = c.grid[0], ny = c.grid[1], nz = c.grid[2], nzh = nz/2 + 1;
     const size_t total = (size_t) nx*ny*nzh;
     NBS_CUDA_CHECK(c.dEterm.ensure(total));
     NBS_CUDA_CHECK(c.dEtermD.ensure(total));
     const double3 inv = make_double3(g.invBox[0], g.invBox[1], g.invBox[2]);
+    // r10 = -bx/(ax by), r20 = (bx cy - by cx)/(ax by cz), r21 = -cy/(by cz)
+    const double3 off = make_double3(-g.tilt[0]*g.invBox[0]*g.invBox[1],
+                                     (g.tilt[0]*g.tilt[2] - g.box[1]*g.tilt[1])*g.invBox[0]*g.invBox[1]*g.invBox[2],
+                                     -g.tilt[2]*g.invBox[1]*g.invBox[2]);
     const double volume = g.box[0]*g.box[1]*g.box[2];
     if (c.dispersionPass) {
-        k_eterm_dispersion<float><<<(unsigned) ((total + 255)/256), 256, 0, c.stream>>>(nx, ny, nz, nzh, inv, volume, c.alpha, c.dModuli.d, c.dEterm.d);
-        k_eterm_dispersion<double><<<(unsigned) ((total + 255)/256), 256, 0, c.stream>>>(nx, ny, nz, nzh, inv, volume, c.alpha, c.dModuli.d, c.dEtermD.d);
+        k_eterm<float, true><<<(unsigned) ((total + 255)/256), 256, 0, c.stream>>>(nx, ny, nz, nzh, inv, off, volume, c.alpha, c.dModuli.d, c.dEterm.d);
+        k_eterm<double, true><<<(unsigned) ((total + 255)/256), 256, 0, c.stream>>>(nx, ny, nz, nzh, inv, off, volume, c.alpha, c.dModuli.d, c.dEtermD.d);
     }
     else {
-        k_eterm<float><<<(unsigned) ((total + 255)/256), 256, 0, c.stream>>>(nx, ny, nz, nzh, inv, volume, c.alpha, c.dModuli.d, c.dEterm.d);
-        k_eterm<double><<<(unsigned) ((total + 255)/256), 256, 0, c.stream>>>(nx, ny, nz, nzh, inv, volume, c.alpha, c.dModuli.d, c.dEtermD.d);
+        k_eterm<float, false><<<(unsigned) ((total + 255)/256), 256, 0, c.stream>>>(nx, ny, nz, nzh, inv, off, volume, c.alpha, c.dModuli.d, c.dEterm.d);
+        k_eterm<double, false><<<(unsigned) ((total + 255)/256), 256, 0, c.stream>>>(nx, ny, nz, nzh, inv, off, volume, c.alpha, c.dModuli.d, c.dEtermD.d);
     }
     c.launches += 2;
-    for (int k = 0; k < 3; k++) c.etermBox[k] = g.box[k];
+    for (int k = 0; k < 3; k++) { c.etermBox[k] = g.box[k]; c.etermBox[3+k] = g.tilt[k]; }
     return NBS_OK;
 }
 
@@ -631,6 +663,16 @@ static int launchPmeT(Context& c, bool wantEnergy, int half) {
     }
     p.force = c.pmeUnsorted ? c.dForce.d + 3*(size_t) c.Npad : c.dForce.d;
     for (int k = 0; k < 3; k++) p.fscale[k] = (float) (c.grid[k]*c.geom.invBox[k]);
+    {
+        const CellGeom& g = c.geom;
+        p.triclinic = g.triclinic ? 1 : 0;
+        p.beta = g.tilt[0]*g.invBox[0];
+        p.gammaY = g.tilt[2]*g.invBox[1];
+        p.delta = (g.tilt[0]*g.tilt[2] - g.box[1]*g.tilt[1])*g.invBox[0]*g.invBox[1];
+        p.fr10 = (float) (-c.grid[0]*g.tilt[0]*g.invBox[0]*g.invBox[1]);
+        p.fr20 = (float) (c.grid[0]*(g.tilt[0]*g.tilt[2] - g.box[1]*g.tilt[1])*g.invBox[0]*g.invBox[1]*g.invBox[2]);
+        p.fr21 = (float) (-c.grid[1]*g.tilt[2]*g.invBox[1]*g.invBox[2]);
+    }
     const int atomCtas = (c.N + 7)/8;
     if (half == 0) {
         int status = prepareEterm(c);

@@ -12,12 +12,12 @@
 namespace nbs {
 
 // ---------------------------------------------------------------------------------------------
-// k_prep: one thread per input slot.  Wraps the position into the box, converts to 32-bit
+// k_prep: one thread per input slot.  Wraps the position into the box (brick), converts to 32-bit
 // fixed-point fractional coordinates and counts the atom into its (column, z-bin).
 // ---------------------------------------------------------------------------------------------
 __global__ void k_prep(int N, const double* __restrict__ pos64, const float4* __restrict__ pos32,
                        const double4* __restrict__ pos64w, const int* __restrict__ atomIndex, double3 invBox, double3 origin,
-                       int ncx, int ncy, int nzb, uint4* __restrict__ fix, int* __restrict__ binCount,
+                       double3 tilt, int ncx, int ncy, int nzb, uint4* __restrict__ fix, int* __restrict__ binCount,
                        double* __restrict__ pos64out) {
     int slot = blockIdx.x*blockDim.x + threadIdx.x;
     if (slot >= N) return;
@@ -29,8 +29,19 @@ __global__ void k_prep(int N, const double* __restrict__ pos64, const float4* __
     if (pos64out) {          // particle-ordered, unwrapped, double: what the exception kernel reads
         pos64out[3*particle] = x; pos64out[3*particle+1] = y; pos64out[3*particle+2] = z;
     }
-    double fx = (x - origin.x)*invBox.x, fy = (y - origin.y)*invBox.y, fz = (z - origin.z)*invBox.z;
-    fx -= floor(fx); fy -= floor(fy); fz -= floor(fz);
+    // wrap into the brick [0, ax) x [0, by) x [0, cz) with the lattice translations: first along c = (cx, cy, cz),
+    // then b = (bx, by, 0), then a (tilt = (bx, cx, cy), all zero for a rectangular box)
+    x -= origin.x; y -= origin.y; z -= origin.z;
+    double fz = z*invBox.z;
+    const double kz = floor(fz);
+    fz -= kz;
+    x -= kz*tilt.y; y -= kz*tilt.z;
+    double fy = y*invBox.y;
+    const double ky = floor(fy);
+    fy -= ky;
+    x -= ky*tilt.x;
+    double fx = x*invBox.x;
+    fx -= floor(fx);
     unsigned ux = (unsigned) (__double2ull_rd(fx*4294967296.0) & 0xffffffffull);
     unsigned uy = (unsigned) (__double2ull_rd(fy*4294967296.0) & 0xffffffffull);
     unsigned uz = (unsigned) (__double2ull_rd(fz*4294967296.0) & 0xffffffffull);
@@ -277,7 +288,8 @@ int launchPrep(Context& c, const PosInput& in) {
                                     in.format == NBS_POS_F32_XYZW ? (const float4*) in.ptr : nullptr,
                                     in.format == NBS_POS_F64_XYZW ? (const double4*) in.ptr : nullptr, in.atomIndex,
                                     make_double3(g.invBox[0], g.invBox[1], g.invBox[2]),
-                                    make_double3(g.origin[0], g.origin[1], g.origin[2]), g.ncx, g.ncy, g.nzb,
+                                    make_double3(g.origin[0], g.origin[1], g.origin[2]),
+                                    make_double3(g.tilt[0], g.tilt[1], g.tilt[2]), g.ncx, g.ncy, g.nzb,
                                     c.dFix.d, c.dBinCount.d, in.pos64out);
     c.launches++;
     timerMark(c, "prep");

@@ -254,7 +254,8 @@ static void bsplineModuli(int ngrid, double* moduli) {
 // fields; this swaps the two sets (host-side only; work buffers are shared and sized for the larger grid).
 void swapPmeTables(Context& c) {
     std::swap(c.alpha, c.dispAlpha);
-    for (int k = 0; k < 3; k++) { std::swap(c.grid[k], c.dispGrid[k]); std::swap(c.etermBox[k], c.etermBoxDisp[k]); }
+    for (int k = 0; k < 3; k++) std::swap(c.grid[k], c.dispGrid[k]);
+    for (int k = 0; k < 6; k++) std::swap(c.etermBox[k], c.etermBoxDisp[k]);
     std::swap(c.dModuli, c.dModuliDisp);
     std::swap(c.dTwiddle, c.dTwiddleDisp);
     std::swap(c.dTwiddleD, c.dTwiddleDDisp);
@@ -338,8 +339,13 @@ static int buildErfcTable(Context& c) {
 }
 
 // cell geometry for this box: columns whose 32-atom blocks are roughly cubic, fine z-bins for sorting
-static int setupGeometry(Context& c, const double L[3], const double origin[3]) {
+static int setupGeometry(Context& c, const double L[3], const double origin[3], const double tilt[3]) {
     CellGeom& g = c.geom;
+    for (int k = 0; k < 3; k++) g.tilt[k] = tilt[k];
+    g.triclinic = tilt[0] != 0 || tilt[1] != 0 || tilt[2] != 0;
+    g.shiftB = std::llround(tilt[0]/L[0]*4294967296.0);
+    g.shiftCx = std::llround(tilt[1]/L[0]*4294967296.0);
+    g.shiftCy = std::llround(tilt[2]/L[1]*4294967296.0);
     const double volume = L[0]*L[1]*L[2];
     const double density = c.N/volume;
     double side = std::cbrt(32.0/density);
@@ -582,8 +588,15 @@ static int validateExec(Context& c, const nbs_exec_args* args) {
     if (args->struct_size != (int32_t) sizeof(nbs_exec_args)) return fail(NBS_ERR_INVALID, "nbs_exec_args.struct_size mismatch");
     const double* box = args->box;
     if (c.periodic) {
-        if (box[1] != 0 || box[2] != 0 || box[3] != 0 || box[5] != 0 || box[6] != 0 || box[7] != 0)
-            return fail(NBS_ERR_UNSUPPORTED, "triclinic boxes are not implemented on this platform yet");
+        // OpenMM's reduced form (Context::setPeriodicBoxVectors [external] enforces it): a = (ax, 0, 0),
+        // b = (bx, by, 0), c = (cx, cy, cz), |bx| <= ax/2, |cx| <= ax/2, |cy| <= by/2
+        if (box[1] != 0 || box[2] != 0 || box[5] != 0)
+            return fail(NBS_ERR_INVALID, "First periodic box vector must be parallel to x, second must be in the x-y plane.");
+        if (box[0] <= 0 || box[4] <= 0 || box[8] <= 0 ||
+            std::fabs(box[3]) > 0.5*box[0]*(1 + 1e-12) || std::fabs(box[6]) > 0.5*box[0]*(1 + 1e-12) || std::fabs(box[7]) > 0.5*box[4]*(1 + 1e-12))
+            return fail(NBS_ERR_INVALID, "Periodic box vectors must be in reduced form.");
+        if (c.method == NBS_METHOD_EWALD && (box[3] != 0 || box[6] != 0 || box[7] != 0))     // SlicedNonbondedForceImpl.cpp:112-113
+            return fail(NBS_ERR_UNSUPPORTED, "SlicedNonbondedForce: Ewald is not supported with non-rectangular boxes.  Use PME instead.");
         // ReferenceNonbondedSlicingKernels.cpp:200-204
         const double minAllowedSize = 1.999999*c.cutoff;
         if (box[0] < minAllowedSize || box[4] < minAllowedSize || box[8] < minAllowedSize)
@@ -671,7 +684,9 @@ static int phaseBegin(Context& c, const nbs_exec_args* args) {
             }
             c.cutoffEff = c.method == NBS_METHOD_NOCUTOFF ? std::sqrt(diag2) + 1.0 : c.cutoff;
         }
-        if ((status = setupGeometry(c, L, origin)) != NBS_OK) return status;
+        // triclinic box a = (ax, 0, 0), b = (bx, by, 0), c = (cx, cy, cz): the cell grid lives in the brick ax x by x cz
+        const double tilt[3] = {c.periodic ? box[3] : 0.0, c.periodic ? box[6] : 0.0, c.periodic ? box[7] : 0.0};
+        if ((status = setupGeometry(c, L, origin, tilt)) != NBS_OK) return status;
     }
     NBS_CUDA_CHECK(cudaMemsetAsync(c.dForce.d, 0, sizeof(unsigned long long)*(c.pmeUnsorted ? 6 : 3)*c.Npad, st));
     NBS_CUDA_CHECK(cudaMemsetAsync(c.dEnergy.d, 0, sizeof(double)*ENERGY_WORDS, st));

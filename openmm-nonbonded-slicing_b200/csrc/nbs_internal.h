@@ -36,7 +36,9 @@ constexpr int PME_ORDER = 5;
 // f(s) ~ sum a_k d^k, d = s*scale + offset in [-1, 1]
 constexpr int ERFC_TAB_BASE = (127 - 7) << 6;
 constexpr int ERFC_TAB_ROW = 10;
-constexpr int J_SHIFT_BITS = 26;                 // sorted index in the low 26 bits of a list entry
+// A list entry is (image code << J_SHIFT_BITS) | sorted index; image code = (kx+2) + 5 ((ky+1) + 3 (kz+1)) with
+// kx in -2..2 (a triclinic box's b and c vectors shift x by up to ax/2 each), ky, kz in -1..1: 45 codes, 6 bits.
+constexpr int J_SHIFT_BITS = 25;                 // sorted index in the low 25 bits of a list entry
 constexpr int J_INDEX_MASK = (1 << J_SHIFT_BITS)-1;
 constexpr int BUILD_WARPS = 8;                   // warps per CTA in the list-build kernel
 constexpr int PAIR_WARPS = 8;                    // warps per CTA in the pair kernel
@@ -70,8 +72,15 @@ struct LambdaTable {                 // passed by value to kernels
     float v[MAX_SLICES];             // vdW scale per slice
 };
 
-struct CellGeom {                    // cell / column geometry of one evaluation (rectangular box)
-    double box[3];                   // Lx, Ly, Lz (non-periodic methods: a virtual box twice the size of the system)
+struct CellGeom {                    // cell / column geometry of one evaluation
+    // Triclinic boxes a = (ax, 0, 0), b = (bx, by, 0), c = (cx, cy, cz) (OpenMM's reduced form) are handled in the
+    // rectangular BRICK [0, ax) x [0, by) x [0, cz), which is a unit cell of the same lattice: atoms are wrapped into
+    // it with the lattice translations (k_prep), so cells, bounding boxes and all distances stay plain Cartesian, and
+    // only the periodic IMAGE shifts change: image (kx, ky, kz) is displaced by kx a + ky b + kz c.
+    double box[3];                   // ax, by, cz (non-periodic methods: a virtual box twice the size of the system)
+    double tilt[3];                  // bx, cx, cy (nm); all zero for a rectangular box
+    long long shiftB, shiftCx, shiftCy;   // the same in fixed-point units of their axis: bx/ax, cx/ax, cy/by times 2^32
+    bool triclinic;
     double origin[3];                // coordinate that maps to fractional 0 (0 for periodic boxes)
     double invBox[3];
     float scale[3];                  // L / 2^32 (fixed-point unit in nm)
@@ -161,7 +170,7 @@ struct Context {
     Buf<float2> dTwiddle;                    // [nx+ny+nz]
     // LJPME keeps a second set of the tables that depend on (alpha, grid)
     Buf<float> dEtermDisp; Buf<double> dEtermDDisp, dModuliDisp; Buf<double2> dTwiddleDDisp; Buf<float2> dTwiddleDisp;
-    double etermBoxDisp[3] = {0, 0, 0};
+    double etermBoxDisp[6] = {0, 0, 0, 0, 0, 0};
     std::vector<double> hModuliDisp;
     Buf<int4> dEwaldK;                       // Ewald: half space of reciprocal vectors (rx, ry, rz, 0)
     Buf<double2> dEwaldSums, dEwaldMixed;    // [nK][MAX_SUBSETS] structure factors; lambda-mixed factors
@@ -173,7 +182,7 @@ struct Context {
     int capJ = 0, capX = 0, maxBlocks = 0, Npad = 0;
     int nBlocksLast = 0;
     CellGeom geom{};
-    double etermBox[3] = {0, 0, 0};
+    double etermBox[6] = {0, 0, 0, 0, 0, 0};  // box (diagonal, tilt) the influence function was computed for
     double lastBox[9] = {0};
     bool haveLast = false, lastDirect = false;
     std::vector<double> hModuli;

@@ -1,8 +1,8 @@
 """The reference's analytic known-answer tests (tests/TestSlicedNonbondedForce.h; restated in
 test_oracle_golden.py, where they pin the CPU oracles) run against the CUDA path itself: the same test bodies,
 the "B200" platform instead of an oracle platform.  Everything the device implements is here -- NoCutoff,
-CutoffNonPeriodic, CutoffPeriodic, PME, LJPME (testEwaldExceptions), exceptions, offsets, switching function, dispersion correction, force
-groups; triclinic boxes are not implemented on the device and stay oracle-only."""
+CutoffNonPeriodic, CutoffPeriodic, PME, LJPME (testEwaldExceptions), triclinic boxes (testTriclinic), exceptions,
+offsets, switching function, dispersion correction, force groups."""
 import pytest
 
 import test_oracle_golden as golden
@@ -10,7 +10,7 @@ import test_oracle_golden as golden
 pytestmark = pytest.mark.gpu
 
 NAMES = ["test_coulomb", "test_lj", "test_exclusions_and_14", "test_cutoff", "test_cutoff14", "test_periodic",
-         "test_periodic_exceptions", "test_dispersion_correction", "test_switching_function", "test_parameter_offsets",
+         "test_periodic_exceptions", "test_triclinic", "test_dispersion_correction", "test_switching_function", "test_parameter_offsets",
          "test_direct_and_reciprocal", "test_ewald_exceptions", "test_parameter_clash"]
 
 
@@ -27,11 +27,6 @@ def test_known_answer_on_device(nbs, b200, name):
     getattr(golden, name)(nbs, b200)
 
 
-def test_triclinic_is_refused_not_faked(nbs, b200):
-    """A triclinic box must fail loudly (NBS_ERR_UNSUPPORTED), never fall back to anything else."""
-    with pytest.raises(Exception) as info:
-        golden.test_triclinic(nbs, b200)
-    assert "triclinic" in str(info.value).lower()
 
 
 def test_slicing_equals_rescaled_parameters_on_device(nbs, b200):

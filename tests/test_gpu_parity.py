@@ -304,6 +304,73 @@ def test_ljpme_random_systems(nbs, platform, oracle, seed, nsub, n, grid, dgrid)
     three_way(kernel, kernel.desc, positions, box, lam, run)
 
 
+@pytest.mark.parametrize("seed,nsub,n,L,grid,tilt,method", [
+    (61, 3, 300, 2.6, (20, 20, 20), (0.3, -0.2, 0.4), "PME"),
+    (62, 2, 1000, 3.4, (24, 18, 30), (-0.5, 0.5, -0.5), "PME"),         # the extreme reduced form: images two boxes away in x
+    (63, 4, 97, 2.2, (25, 21, 28), (0.5, 0.5, 0.5), "PME"),
+    (64, 3, 333, 2.6, (20, 20, 20), (0.25, 0.1, -0.35), "CutoffPeriodic"),
+    (65, 2, 2000, 4.4, (30, 30, 30), (-0.45, -0.3, 0.2), "PME"),
+    (66, 3, 300, 2.6, (20, 20, 20), (0.3, -0.2, 0.4), "LJPME")])
+def test_triclinic_random_systems(nbs, platform, oracle, seed, nsub, n, L, grid, tilt, method):
+    """Triclinic boxes on the device: atoms wrapped into the rectangular brick [0,ax) x [0,by) x [0,cz) of the same
+    lattice, images displaced by kx a + ky b + kz c in the list builder and the pair kernel, lattice fractions and
+    the full reciprocal matrix in PME, OpenMM's minimum image for periodic exceptions; unwrapped input coordinates."""
+    kind = "port"
+    if method == "LJPME":
+        if not oracle.available("reference"):
+            pytest.skip("oracle/_ref not built")
+        kind = "reference"
+    rng = np.random.default_rng(seed)
+    system, force, positions = random_system(nbs, rng, n=n, nsub=nsub, L=L, grid=grid, method=method, tilt=tilt)
+    if method == "LJPME":
+        force.setLJPMEParameters(2.4, 12, 12, 12)
+    force.setExceptionsUsePeriodicBoundaryConditions(seed % 2 == 1)
+    ctx = nbs.Context(system, platform)
+    ref = nbs.Context(system, oracle.OraclePlatform(kind))
+    for c in (ctx, ref):
+        c.setPositions(positions)
+        c.setParameter("off", 0.45)
+    for lc, lv in ((0.7, 0.4), (1.0, 0.0)):
+        for c in (ctx, ref):
+            c.setParameter("lc", lc)
+            c.setParameter("lv", lv)
+        a = ctx.getState(getEnergy=True, getForces=True, getParameterDerivatives=True)
+        b = ref.getState(getEnergy=True, getForces=True, getParameterDerivatives=True)
+        count, h, _ = ctx.impls[0].kernel.getPairSet(with_pairs=False)
+        r = ref.impls[0].kernel.lastResult
+        assert (count, h) == (r.pair_count, r.pair_hash), f"pair set differs ({count} vs {r.pair_count})"
+        assert force_rel_rms(a.getForces(), b.getForces()) <= F_TOL
+        check_energies(ctx.impls[0].kernel.lastSliceEnergies, ref.impls[0].kernel.lastSliceEnergies)
+        for name, value in b.getEnergyParameterDerivatives().items():
+            assert_equal_tol(value, a.getEnergyParameterDerivatives()[name], E_TOL)
+    kernel = ctx.impls[0].kernel
+    lam = rng.uniform(0.2, 1.0, size=(force.getNumSlices(), 2))
+    gv = np.array([0.45, 0.0, 1.0])
+    box = np.array(system.getDefaultPeriodicBoxVectors()).reshape(9)
+
+    def run(tag, direct, recip):
+        r = oracle.evaluate(kernel.desc, positions, box, lam, gv, direct, recip, kind=kind)
+        return r.slice_energies, r.forces, r.pair_count, r.pair_hash
+    if method != "CutoffPeriodic":
+        three_way(kernel, kernel.desc, positions, box, lam, run)
+
+
+def test_non_reduced_box_is_refused(nbs, platform):
+    """Box vectors outside OpenMM's reduced form are an error, not a silently different lattice."""
+    system = nbs.System()
+    system.setDefaultPeriodicBoxVectors([3, 0, 0], [2.0, 3, 0], [0, 0, 3])
+    force = nbs.SlicedNonbondedForce(1)
+    force.setNonbondedMethod(force.CutoffPeriodic)
+    for k in range(2):
+        system.addParticle(1.0)
+        force.addParticle(1.0, 0.3, 0.1)
+    system.addForce(force)
+    ctx = nbs.Context(system, platform)
+    ctx.setPositions([[0, 0, 0], [1, 0, 0]])
+    with pytest.raises(Exception, match="reduced form"):
+        ctx.getState(getEnergy=True)
+
+
 def test_ewald_c1(nbs, platform, systems, oracle):
     """The TIP3P box of BASELINE.json config 0 with the method switched to Ewald, three repeated evaluations
     (plain launches, graph capture, graph replay)."""

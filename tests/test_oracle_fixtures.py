@@ -33,17 +33,23 @@ def test_port_matches_reference_fixture(nbs, oracle, systems, name):
             assert r.pair_hash == int(g["pair_hash"][0])
 
 
-def random_system(nbs, rng, n=300, nsub=3, L=2.6, grid=(20, 20, 20), with_offsets=True, net_charge=True, method="PME"):
+def random_system(nbs, rng, n=300, nsub=3, L=2.6, grid=(20, 20, 20), with_offsets=True, net_charge=True, method="PME",
+                  tilt=None):
+    """``tilt`` = (bx, cx, cy) as fractions of (ax, ax, by) makes the box triclinic (OpenMM's reduced form needs
+    each within +-0.5); the atoms then sit on the sheared lattice and are displaced by whole box vectors."""
     system = nbs.System()
     force = nbs.SlicedNonbondedForce(nsub)
     force.setNonbondedMethod(getattr(force, method))
     force.setCutoffDistance(1.0)
     force.setPMEParameters(2.8, *grid)
-    system.setDefaultPeriodicBoxVectors([L, 0, 0], [0, L, 0], [0, 0, L])
+    box = np.array([[L, 0, 0], [0, L, 0], [0, 0, L]], dtype=float)
+    if tilt is not None:
+        box[1, 0], box[2, 0], box[2, 1] = tilt[0]*L, tilt[1]*L, tilt[2]*L
+    system.setDefaultPeriodicBoxVectors(*box)
     side = int(np.ceil(n**(1/3)))
     sites = np.array([(i, j, k) for i in range(side) for j in range(side) for k in range(side)][:n], dtype=float)
-    positions = (sites+0.5)*L/side + rng.uniform(-0.05, 0.05, size=(n, 3))
-    positions += rng.integers(-2, 3, size=(n, 3))*L          # unwrapped coordinates must work too
+    positions = ((sites+0.5)/side) @ box + rng.uniform(-0.05, 0.05, size=(n, 3))
+    positions += rng.integers(-2, 3, size=(n, 3)) @ box      # unwrapped coordinates must work too
     charges = rng.uniform(-0.8, 0.8, size=n)
     if not net_charge:
         charges -= charges.mean()
@@ -228,3 +234,27 @@ def test_ewald_rejects_triclinic(nbs, oracle):
     system.addForce(force)
     with pytest.raises(nbs.OpenMMException, match="Ewald is not supported with non-rectangular boxes"):
         nbs.Context(system, oracle.OraclePlatform("port"))
+
+
+@pytest.mark.parametrize("seed,tilt,method", [(51, (0.3, -0.2, 0.4), "PME"), (52, (-0.5, 0.5, -0.5), "PME"),
+                                              (53, (0.25, 0.1, -0.35), "CutoffPeriodic")])
+def test_triclinic_port_matches_compiled_reference(nbs, oracle, seed, tilt, method):
+    """Triclinic boxes (testTriclinic :432-492 pins the minimum image analytically; this pins the rest): the
+    restatement against the reference's own TUs on sheared random systems, including the extreme reduced form."""
+    if not oracle.available("reference"):
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(seed)
+    system, force, positions = random_system(nbs, rng, n=200, nsub=3, L=2.5, grid=(20, 20, 20), method=method, tilt=tilt)
+    desc = nbs.build_desc(system, force)
+    box = np.array(system.getDefaultPeriodicBoxVectors()).reshape(9)
+    lam = rng.uniform(0.1, 1.0, size=(force.getNumSlices(), 2))
+    gv = np.array([0.3, 0.7, 0.4])
+    for direct, recip in ((True, True), (True, False), (False, True)):
+        a = oracle.evaluate(desc, positions, box, lam, gv, direct, recip, kind="port")
+        b = oracle.evaluate(desc, positions, box, lam, gv, direct, recip, kind="reference")
+        if np.abs(b.forces).max() > 0:
+            assert force_rel_rms(a.forces, b.forces) < 1e-11
+        else:
+            assert np.abs(a.forces).max() == 0
+        assert np.allclose(a.slice_energies, b.slice_energies, rtol=1e-10, atol=1e-9)
+        assert (a.pair_count, a.pair_hash) == (b.pair_count, b.pair_hash)

@@ -35,6 +35,9 @@ FS_PER_STEP = 2.0             # ns/day figure assumes one evaluation per 2 fs st
 # DRAM traffic of one k_pair launch from the committed ncu captures (profiles/README.md): the kernel's working
 # set (positions, parameters, lists) is L2-resident, so this is far below any bandwidth limit
 PAIR_TRAFFIC_BYTES = {"C3": 8676608}
+# the same for the reciprocal chain (k_spread + the FFT / convolution kernels + k_gather, summed over the launches of
+# one evaluation): profiles/r01_ncu_pme_summary.txt
+PME_TRAFFIC_BYTES = {"C3": 3370752 + 6334976 + 7616256 + 6531072 + 2742272, "C5": 1084900000}
 
 
 def parse_args():
@@ -352,7 +355,8 @@ def main():
     roofline_pme = {"bound": "hbm", "kernels": "k_spread + 3 plane-fused FFT/convolution kernels + k_gather", "achieved": pme_bytes/(pme_ms*1e-3)/1e9,
                     "peak": hbm_peak, "unit": "GB/s", "frac": pme_bytes/(pme_ms*1e-3)/1e9/hbm_peak,
                     "peak_source": "hbm_gbs of MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
-                    "algorithmic": f"32*nS*G + 52*N = {pme_bytes} bytes", "kernel_ms": pme_ms, "traffic": None}
+                    "algorithmic": f"32*nS*G + 52*N = {pme_bytes} bytes", "kernel_ms": pme_ms,
+                    "traffic": PME_TRAFFIC_BYTES.get(workload_name)}
 
     line = {
         "metric": "force+energy evals/s", "value": value, "unit": "evals/s", "n_gpus": 1, "steps": args.steps,

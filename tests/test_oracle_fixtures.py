@@ -258,3 +258,27 @@ def test_triclinic_port_matches_compiled_reference(nbs, oracle, seed, tilt, meth
             assert np.abs(a.forces).max() == 0
         assert np.allclose(a.slice_energies, b.slice_energies, rtol=1e-10, atol=1e-9)
         assert (a.pair_count, a.pair_hash) == (b.pair_count, b.pair_hash)
+
+
+@pytest.mark.parametrize("seed,nsub,tilt,grid,dgrid", [(71, 3, None, (20, 18, 20), (12, 12, 12)), (72, 1, None, (24, 18, 30), (10, 14, 9)),
+                                                        (73, 4, (0.3, -0.2, 0.4), (20, 20, 20), (10, 14, 10))])
+def test_ljpme_port_matches_compiled_reference(nbs, oracle, seed, nsub, tilt, grid, dgrid):
+    """LJPME (ReferenceSlicedLJCoulombIxn.cpp:211-212, 241-253, 398-426, 487-504; ReferencePME.cpp:499-595, 814-871):
+    the restatement against the reference's own TUs.  Multi-subset cases keep nx == nz (the reference's
+    gather indexes subset grids with sj*nz)."""
+    if not oracle.available("reference"):
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(seed)
+    system, force, positions = random_system(nbs, rng, n=180, nsub=nsub, L=2.6, grid=grid, method="LJPME", tilt=tilt)
+    force.setLJPMEParameters(2.4, *dgrid)
+    desc = nbs.build_desc(system, force)
+    assert desc.desc.use_switching_function == 0
+    box = np.array(system.getDefaultPeriodicBoxVectors()).reshape(9)
+    lam = rng.uniform(0.1, 1.0, size=(force.getNumSlices(), 2))
+    gv = np.array([0.3, 0.7, 0.4])
+    for direct, recip in ((True, True), (True, False), (False, True)):
+        a = oracle.evaluate(desc, positions, box, lam, gv, direct, recip, kind="port")
+        b = oracle.evaluate(desc, positions, box, lam, gv, direct, recip, kind="reference")
+        assert force_rel_rms(a.forces, b.forces) < 1e-12
+        assert np.allclose(a.slice_energies, b.slice_energies, rtol=1e-11, atol=1e-9)
+        assert (a.pair_count, a.pair_hash) == (b.pair_count, b.pair_hash)

@@ -472,8 +472,6 @@ def test_ewald_exceptions(nbs, platform):
     """testEwaldExceptions :947-985 -- LJPME: adding a periodic exception changes the energy by exactly the
     exception's own Coulomb + LJ energy minus the pair's plain LJ energy (the pair leaves the direct-space sum
     and both reciprocal sums are backed out by the exclusion corrections, Coulomb and dispersion)."""
-    if getattr(platform, "kind", "") == "port":
-        pytest.skip("LJPME is not restated in the port; the compiled reference covers it")
     system = nbs.System()
     for _ in range(4):
         system.addParticle(1.0)

@@ -230,5 +230,7 @@ void B200CalcSlicedNonbondedForceKernel::getPMEParameters(double& alpha, int& nx
 void B200CalcSlicedNonbondedForceKernel::getLJPMEParameters(double& alpha, int& nx, int& ny, int& nz) const {
     if (nonbondedMethod != LJPME)                               // :330-337
         throw OpenMMException("getPMEParametersInContext: This Context is not using LJPME");
-    throw OpenMMException("SlicedNonbondedForce (B200): LJPME is not implemented on this platform");
+    int32_t gx, gy, gz;
+    check(nbs_get_ljpme_parameters(handle, &alpha, &gx, &gy, &gz));
+    nx = gx; ny = gy; nz = gz;
 }

@@ -77,6 +77,7 @@ __global__ void __launch_bounds__(BUILD_WARPS*32, 4) k_build_lists(BuildArgs a) 
     // the block's box sits at x - ky bx - kz cx, y - kz cy.  The candidate range covers every (ky, kz); the exact gap
     // test per image follows below.  (Rectangular boxes: bx = cx = cy = 0 and this is the plain 3 x 3 x 3 walk.)
     const float tiltX = fabsf(a.bx) + fabsf(a.cx), tiltY = fabsf(a.cy);
+    const bool triclinic = tiltX != 0.f || tiltY != 0.f;
     const int uxLo = (int) floorf((lox - R - tiltX)/a.colWx), uxHi = (int) floorf((hix + R + tiltX)/a.colWx);
     const int uyLo = (int) floorf((loy - R - tiltY)/a.colWy), uyHi = (int) floorf((hiy + R + tiltY)/a.colWy);
     const int nuy = uyHi - uyLo + 1;
@@ -92,13 +93,23 @@ __global__ void __launch_bounds__(BUILD_WARPS*32, 4) k_build_lists(BuildArgs a) 
         if (!a.periodic && (kx != 0 || ky != 0)) continue;
         const int colJ = wx*a.ncy + wy;
         if (colJ < colI) continue;                                         // owned by the other block
+        // gap between the block's box and the column in x, y (rectangular boxes: the same for every kz, tested once)
+        float d2 = 0.f;
+        if (!triclinic) {
+            const float gx = fmaxf(0.f, fmaxf(ux*a.colWx - hix, lox - (ux+1)*a.colWx));
+            const float gy = fmaxf(0.f, fmaxf(uy*a.colWy - hiy, loy - (uy+1)*a.colWy));
+            d2 = gx*gx + gy*gy;
+            if (d2 > R2) continue;
+        }
         for (int kz = -1; kz <= 1; kz++) {
             if (!a.periodic && kz != 0) continue;
-            const float offX = ky*a.bx + kz*a.cx, offY = kz*a.cy;            // the block's box as this image sees it
-            const float gx = fmaxf(0.f, fmaxf(ux*a.colWx - (hix - offX), (lox - offX) - (ux+1)*a.colWx));
-            const float gy = fmaxf(0.f, fmaxf(uy*a.colWy - (hiy - offY), (loy - offY) - (uy+1)*a.colWy));
-            const float d2 = gx*gx + gy*gy;
-            if (d2 > R2) continue;
+            if (triclinic) {
+                const float offX = ky*a.bx + kz*a.cx, offY = kz*a.cy;        // the block's box as this image sees it
+                const float gx = fmaxf(0.f, fmaxf(ux*a.colWx - (hix - offX), (lox - offX) - (ux+1)*a.colWx));
+                const float gy = fmaxf(0.f, fmaxf(uy*a.colWy - (hiy - offY), (loy - offY) - (uy+1)*a.colWy));
+                d2 = gx*gx + gy*gy;
+                if (d2 > R2) continue;
+            }
             const float dz = sqrtf(R2 - d2) + 1e-4f;
             const float zlo = loz - dz, zhi = hiz + dz;
             const float segLo = fmaxf(zlo, kz*a.Lz) - kz*a.Lz, segHi = fminf(zhi, (kz+1)*a.Lz) - kz*a.Lz;
@@ -213,8 +224,11 @@ __global__ void __launch_bounds__(BUILD_WARPS*32, 4) k_build_lists(BuildArgs a) 
 int launchBuildLists(Context& c) {
     const CellGeom& g = c.geom;
     if (c.blockWidth == 0) return NBS_OK;          // this rank has no direct-space share
-    int status = launchExclRange(c);
-    if (status != NBS_OK) return status;
+    if (c.exclRangeForked) NBS_CUDA_CHECK(cudaStreamWaitEvent(c.stream, c.evExclDone, 0));     // launched beside the block construction
+    else {
+        int status = launchExclRange(c);
+        if (status != NBS_OK) return status;
+    }
     BuildArgs a;
     a.N = c.N; a.maxBlocks = c.maxBlocks; a.capJ = c.capJ; a.capX = c.capX;
     a.blockPeriod = c.blockPeriod; a.blockOffset = c.blockOffset; a.blockWidth = c.blockWidth;

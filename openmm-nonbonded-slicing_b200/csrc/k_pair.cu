@@ -60,7 +60,7 @@ struct PairArgs {
     double rc2d, alphaD, krfD, crfD;
     float dalpha2, invCut6, shiftMult;   // LJPME: alpha_d^2, rc^-6, rc^-6 (1 - exp(-x)(1 + x + x^2/2)) at x = (alpha_d rc)^2
     const double* q64;                   // sorted charges * sqrt(ONE_4PI_EPS0), double
-    const double* erfcTab;               // piecewise degree-6 fit of erfc(alpha sqrt(s))/sqrt(s) in s = r^2 (ERFC_TAB_ROW doubles per interval)
+    const double* erfcTab;               // piecewise degree-4 fit of erfc(alpha sqrt(s))/sqrt(s) in s = r^2 (ERFC_TAB_ROW doubles per interval)
     int* counters;                       // [2] number of work items, [3] cursor
     const int4* items;                   // (local block, first tile, first atom of the block, atoms in the block)
     const int* blkFirst; const int* blkCount; const uint4* blkLo;
@@ -152,9 +152,9 @@ __device__ __forceinline__ double expNegD(double z) {
 // (PME) and :598-624 (reaction field), switch :380-384, 428-431.
 //   * Coulomb, PME: K q_i q_j erfc(alpha r)/r in DOUBLE.  Double-precision instructions are ~8x more
 //     expensive to issue than fp32 ones here, so instead of rsqrt + exp + erfcx (about 45 of them) the
-//     function f(s) = erfc(alpha sqrt(s))/sqrt(s), s = r^2, comes from a table of degree-6 polynomials
-//     on 64 intervals per octave of s (built on the host from libm's erfc: relative error < 1e-13 for
-//     r <= cutoff; csrc/nbs_api.cu buildErfcTable) -- 8 fused multiply-adds.  Pairs closer than
+//     function f(s) = erfc(alpha sqrt(s))/sqrt(s), s = r^2, comes from a table of degree-4 polynomials
+//     on 256 intervals per octave of s (built on the host from libm's erfc: relative error ~1e-11;
+//     csrc/nbs_api.cu buildErfcTable) -- three 16-byte loads and 5 fused multiply-adds.  Pairs closer than
 //     2^-3.5 nm (0.088 nm: none in a physical system) take the analytic path.
 //   * Lennard-Jones: fp32 from the same exact r^2 (terms of one sign dominate a slice's vdW sum, so 1e-7
 //     per term is far inside the 1e-5 target), accumulated in double.
@@ -199,17 +199,18 @@ __device__ __forceinline__ void pairEnergyD(const uint4 fi, const uint4 fj, doub
     }
     const double qq = qi*qj;
     if (IS_PME) {
-        const int idx = (int) (__float_as_uint(r2f) >> 17) - ERFC_TAB_BASE;
+        const unsigned bits = __float_as_uint(r2f);
+        const int idx = (int) (bits >> (23 - ERFC_TAB_PER_OCTAVE_LOG2)) - ERFC_TAB_BASE;
         if (idx >= 0) {
             const double2* row = reinterpret_cast<const double2*>(a.erfcTab + (size_t) idx*ERFC_TAB_ROW);
-            const double2 c0 = __ldg(row), c1 = __ldg(row + 1), c2 = __ldg(row + 2), c3 = __ldg(row + 3), c4 = __ldg(row + 4);
-            const double d = fma(r2, c0.x, c0.y);                   // position inside the interval, [-1, 1]
-            double p = fma(c1.x, d, c1.y);
+            const double2 c0 = __ldg(row), c1 = __ldg(row + 1), c2 = __ldg(row + 2);
+            // 2 / (interval width) = 2^(1 + 8 - e), e = unbiased exponent of r2f: built straight into the exponent field
+            const double scale = __hiloint2double((1023 + 1 + ERFC_TAB_PER_OCTAVE_LOG2 + 127 - (int) (bits >> 23)) << 20, 0);
+            const double d = fma(r2, scale, c0.x);                  // position inside the interval, [-1, 1]
+            double p = fma(c0.y, d, c1.x);
+            p = fma(p, d, c1.y);
             p = fma(p, d, c2.x);
             p = fma(p, d, c2.y);
-            p = fma(p, d, c3.x);
-            p = fma(p, d, c3.y);
-            p = fma(p, d, c4.x);
             ec = qq*p;
         }
         else {
@@ -260,10 +261,12 @@ __device__ __forceinline__ void energyPass(const WarpScratch& w, const PairArgs&
     if (lane < count) {
         const unsigned e = w.queue[lane];
         const int il = e >> 5, jq = e & 31;
-        const float4 q1 = w.iPar[il], q2 = w.jPar[jq];
+        // (sigma/2, 2 sqrt(eps)) only: 8-byte loads; the subsets ride in the .w of the exact coordinates
+        const float2 q1 = *reinterpret_cast<const float2*>(&w.iPar[il]), q2 = *reinterpret_cast<const float2*>(&w.jPar[jq]);
+        const uint4 fi = w.iFix[il], fj = w.jFix[jq];
         double ecd, evd;
-        pairEnergyD<CMODE>(w.iFix[il], w.jFix[jq], w.iQ[il], w.jQ[jq], q1.x, q2.x, q1.y, q2.y, a, ecd, evd);
-        const int sl = triSlice(__float_as_int(q1.z), __float_as_int(q2.z));
+        pairEnergyD<CMODE>(fi, fj, w.iQ[il], w.jQ[jq], q1.x, q2.x, q1.y, q2.y, a, ecd, evd);
+        const int sl = triSlice((int) fi.w, (int) fj.w);
         acc[2*sl] += ecd;
         acc[2*sl+1] += evd;
     }

@@ -18,8 +18,14 @@ namespace nbs {
 __global__ void k_prep(int N, const double* __restrict__ pos64, const float4* __restrict__ pos32,
                        const double4* __restrict__ pos64w, const int* __restrict__ atomIndex, double3 invBox, double3 origin,
                        double3 tilt, int ncx, int ncy, int nzb, uint4* __restrict__ fix, int* __restrict__ binCount,
-                       double* __restrict__ pos64out) {
+                       double* __restrict__ pos64out, double* __restrict__ energy, int* __restrict__ counters) {
     int slot = blockIdx.x*blockDim.x + threadIdx.x;
+    // the slice-energy table and the counters are first touched by later kernels: zeroed here instead of by two
+    // more memset nodes in front of the chain
+    if (blockIdx.x == 0) {
+        for (int k = threadIdx.x; k < ENERGY_WORDS; k += blockDim.x) energy[k] = 0.0;
+        if (threadIdx.x < 16) counters[threadIdx.x] = 0;
+    }
     if (slot >= N) return;
     double x, y, z;
     if (pos64) { x = pos64[3*slot]; y = pos64[3*slot+1]; z = pos64[3*slot+2]; }
@@ -182,6 +188,23 @@ __global__ void k_col_blocks(int nCols, int nzb, const int* __restrict__ binStar
     colBlocks[col] = (cnt + 31) >> 5;
 }
 
+// k_col_blocks + k_scan_single in one single-CTA kernel (the usual case: at most 32768 columns): blocks per column
+// straight from the bin offsets, exclusive scan, total in out[nCols].
+__global__ void __launch_bounds__(1024) k_col_block_scan(int nCols, int nzb, const int* __restrict__ binStart, int* __restrict__ out) {
+    __shared__ int warpSums[33];
+    const int per = (nCols + 1023) >> 10;
+    const int begin = min(nCols, (int) threadIdx.x*per), end = min(nCols, begin + per);
+    int sum = 0;
+    for (int col = begin; col < end; col++) sum += (binStart[(col+1)*nzb] - binStart[col*nzb] + 31) >> 5;
+    int total;
+    int ex = blockExclusiveScan(sum, warpSums, total);
+    for (int col = begin; col < end; col++) {
+        out[col] = ex;
+        ex += (binStart[(col+1)*nzb] - binStart[col*nzb] + 31) >> 5;
+    }
+    if (threadIdx.x == 0) out[nCols] = total;
+}
+
 __global__ void k_blocks(int nCols, int nzb, int maxBlocks, const int* __restrict__ binStart,
                          const int* __restrict__ colBlockStart, const uint4* __restrict__ posq,
                          int* __restrict__ blkFirst, int* __restrict__ blkCount, uint4* __restrict__ blkLo,
@@ -290,7 +313,7 @@ int launchPrep(Context& c, const PosInput& in) {
                                     make_double3(g.invBox[0], g.invBox[1], g.invBox[2]),
                                     make_double3(g.origin[0], g.origin[1], g.origin[2]),
                                     make_double3(g.tilt[0], g.tilt[1], g.tilt[2]), g.ncx, g.ncy, g.nzb,
-                                    c.dFix.d, c.dBinCount.d, in.pos64out);
+                                    c.dFix.d, c.dBinCount.d, in.pos64out, c.dEnergy.d, c.dCounters.d);
     c.launches++;
     timerMark(c, "prep");
     return NBS_OK;
@@ -308,11 +331,31 @@ int launchSortRest(Context& c) {
     k_place<<<(N+T-1)/T, T, 0, st>>>(N, c.dBinStart.d, c.dSortedToOrig.d, c.dOrigToSorted.d, c.dFix.d,
                                      c.dChargeF.d, c.dSigEps.d, c.dSubset.d, c.dCharge.d, sqrt(kOne4PiEps0),
                                      c.dPosq.d, c.dPar.d, c.dQ64.d);
-    // dBinCount is reused for the per-column block counts
-    k_col_blocks<<<(g.nCols+T-1)/T, T, 0, st>>>(g.nCols, g.nzb, c.dBinStart.d, c.dBinCount.d);
-    c.launches += 3;
-    status = scanExclusive(c, c.dBinCount.d, c.dColBlockStart.d, g.nCols);
-    if (status != NBS_OK) return status;
+    c.launches += 2;
+    // The per-atom exclusion ranges only need the sorted order: on the side stream they run beside the block
+    // construction instead of in front of the list builder (which waits for them, launchBuildLists).
+    c.exclRangeForked = false;
+    if (c.sideFork) {
+        cudaEventRecord(c.evPlaced, st);
+        cudaStreamWaitEvent(c.auxStream, c.evPlaced, 0);
+        c.stream = c.auxStream;
+        status = launchExclRange(c);
+        c.stream = st;
+        if (status != NBS_OK) return status;
+        cudaEventRecord(c.evExclDone, c.auxStream);
+        c.exclRangeForked = true;
+    }
+    if (g.nCols <= 32768) {
+        k_col_block_scan<<<1, 1024, 0, st>>>(g.nCols, g.nzb, c.dBinStart.d, c.dColBlockStart.d);
+        c.launches++;
+    }
+    else {
+        // dBinCount is reused for the per-column block counts
+        k_col_blocks<<<(g.nCols+T-1)/T, T, 0, st>>>(g.nCols, g.nzb, c.dBinStart.d, c.dBinCount.d);
+        c.launches++;
+        status = scanExclusive(c, c.dBinCount.d, c.dColBlockStart.d, g.nCols);
+        if (status != NBS_OK) return status;
+    }
     k_blocks<<<(c.maxBlocks*32+T-1)/T, T, 0, st>>>(g.nCols, g.nzb, c.maxBlocks, c.dBinStart.d, c.dColBlockStart.d, c.dPosq.d,
                                                   c.dBlkFirst.d, c.dBlkCount.d, c.dBlkLo.d, c.dBlkHi.d, c.dCounters.d);
     c.launches++;

@@ -297,19 +297,21 @@ int uploadPmeTables(Context& c) {
 }
 
 // Piecewise polynomial table of f(s) = erfc(alpha sqrt(s))/sqrt(s) for the double-precision pair energies
-// (k_pair.cu pairEnergyD): degree-6 interpolation at Chebyshev nodes on every interval [2^e (1 + m/64),
-// 2^e (1 + (m+1)/64)), e = -7 .. floor(log2 cutoff^2) + 1.  Relative error < 1e-13 for alpha r <= 2.7
-// (verified against scipy.special.erfc; tests/test_abi.py checks the recipe in NumPy).
+// (k_pair.cu pairEnergyD): degree-4 interpolation at Chebyshev nodes on every interval [2^e (1 + m/256),
+// 2^e (1 + (m+1)/256)), e = -7 .. floor(log2 cutoff^2) + 1.  Relative error 1e-11 at alpha = 2.6 (2e-10 at alpha = 3.4,
+// where f itself is 1e-6 of its short-range values), checked against mpmath.  Three 16-byte loads and 4 FMAs per pair
+// -- the loads are what the pair kernel's energy passes are bound by (one divergent row per lane).
 static int buildErfcTable(Context& c) {
     const int eMax = std::max(-6, (int) std::floor(std::log2(c.cutoff*c.cutoff)) + 1);
-    const int rows = (eMax + 7 + 1)*64;
+    const int M = 1 << ERFC_TAB_PER_OCTAVE_LOG2;
+    const int rows = (eMax + 7 + 1)*M;
     std::vector<double> tab((size_t) rows*ERFC_TAB_ROW, 0.0);
-    const int D = 6;
+    const int D = ERFC_TAB_DEGREE;
     for (int e = -7; e <= eMax; e++)
-        for (int m = 0; m < 64; m++) {
-            const long double lo = std::ldexp(1.0L + m/64.0L, e), w = std::ldexp(1.0L/64.0L, e);
+        for (int m = 0; m < M; m++) {
+            const long double lo = std::ldexp(1.0L + m/(long double) M, e), w = std::ldexp(1.0L/M, e);
             const long double center = lo + w/2;
-            long double A[7][8];
+            long double A[ERFC_TAB_DEGREE + 1][ERFC_TAB_DEGREE + 2];
             for (int k = 0; k <= D; k++) {
                 const long double xn = std::cos(3.14159265358979323846264338327950288L*(2*k + 1)/(2.0L*(D + 1)));
                 const long double sv = center + xn*w/2;
@@ -328,10 +330,9 @@ static int buildErfcTable(Context& c) {
                     for (int j = col; j <= D + 1; j++) A[r][j] -= f*A[col][j];
                 }
             }
-            double* row = tab.data() + ((size_t) (e + 7)*64 + m)*ERFC_TAB_ROW;
-            row[0] = (double) (2/w);
-            row[1] = (double) (-center*2/w);
-            for (int k = 0; k <= D; k++) row[2 + (D - k)] = (double) (A[k][D + 1]/A[k][k]);     // a6 first
+            double* row = tab.data() + ((size_t) (e + 7)*M + m)*ERFC_TAB_ROW;
+            row[0] = (double) (-center*2/w);                     // d = s * (2/w) + offset, 2/w = 2^(9-e) formed from the exponent
+            for (int k = 0; k <= D; k++) row[1 + (D - k)] = (double) (A[k][D + 1]/A[k][k]);     // a4 first
         }
     NBS_CUDA_CHECK(c.dErfcTab.ensure(tab.size()));
     NBS_CUDA_CHECK(cudaMemcpy(c.dErfcTab.d, tab.data(), sizeof(double)*tab.size(), cudaMemcpyHostToDevice));
@@ -444,6 +445,9 @@ static void releaseAll(Context& c) {
     if (c.auxStream) cudaStreamDestroy(c.auxStream);
     if (c.evAuxFork) cudaEventDestroy(c.evAuxFork);
     if (c.evAuxDone) cudaEventDestroy(c.evAuxDone);
+    if (c.evPlaced) cudaEventDestroy(c.evPlaced);
+    if (c.evExclDone) cudaEventDestroy(c.evExclDone);
+    c.evPlaced = nullptr; c.evExclDone = nullptr;
     c.auxStream = nullptr; c.evAuxFork = nullptr; c.evAuxDone = nullptr;
     if (c.directStream) cudaStreamDestroy(c.directStream);
     if (c.evSorted) cudaEventDestroy(c.evSorted);
@@ -516,6 +520,8 @@ int nbs_create(const nbs_system_desc* desc, nbs_context** out) {
         (e = cudaStreamCreateWithFlags(&c.auxStream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&c.evAuxFork, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&c.evAuxDone, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&c.evPlaced, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&c.evExclDone, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&c.evSorted, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&c.evDirectDone, cudaEventDisableTiming)) != cudaSuccess) {
         releaseAll(c);
@@ -689,8 +695,7 @@ static int phaseBegin(Context& c, const nbs_exec_args* args) {
         if ((status = setupGeometry(c, L, origin, tilt)) != NBS_OK) return status;
     }
     NBS_CUDA_CHECK(cudaMemsetAsync(c.dForce.d, 0, sizeof(unsigned long long)*(c.pmeUnsorted ? 6 : 3)*c.Npad, st));
-    NBS_CUDA_CHECK(cudaMemsetAsync(c.dEnergy.d, 0, sizeof(double)*ENERGY_WORDS, st));
-    NBS_CUDA_CHECK(cudaMemsetAsync(c.dCounters.d, 0, sizeof(int)*16, st));
+    // (the slice-energy table and the counters are zeroed by k_prep)
     timerMark(c, "h2d_zero");
     if ((status = launchPrep(c, in)) != NBS_OK) return status;
     // The cell sort, the neighbour list and direct space run on their own stream, concurrently with the PME
@@ -704,6 +709,7 @@ static int phaseBegin(Context& c, const nbs_exec_args* args) {
         NBS_CUDA_CHECK(cudaStreamWaitEvent(c.directStream, c.evSorted, 0));
         c.stream = c.directStream;
     }
+    c.sideFork = overlap && c.phaseDirect && c.auxStream != nullptr;
     status = launchSortRest(c);
     if (status == NBS_OK && c.phaseDirect) {
         if (overlap && !forkEarly) {

@@ -31,11 +31,13 @@ constexpr double kOne4PiEps0 = 1/(4*kPi*kEpsilon0);
 constexpr int MAX_SUBSETS = 8;
 constexpr int MAX_SLICES = MAX_SUBSETS*(MAX_SUBSETS+1)/2;
 constexpr int PME_ORDER = 5;
-// table of f(s) = erfc(alpha sqrt(s))/sqrt(s): interval index = (bits of (float) s >> 17) - ERFC_TAB_BASE, i.e. 64
-// intervals per octave starting at s = 2^-7; a row is {scale, offset, a6, a5, a4, a3, a2, a1, a0, pad} with
-// f(s) ~ sum a_k d^k, d = s*scale + offset in [-1, 1]
-constexpr int ERFC_TAB_BASE = (127 - 7) << 6;
-constexpr int ERFC_TAB_ROW = 10;
+// table of f(s) = erfc(alpha sqrt(s))/sqrt(s): interval index = (bits of (float) s >> 15) - ERFC_TAB_BASE, i.e. 256
+// intervals per octave starting at s = 2^-7; a row is {offset, a4, a3, a2, a1, a0} (48 bytes: three 16-byte loads) with
+// f(s) ~ sum a_k d^k, d = s*2^(9-e) + offset in [-1, 1], e = exponent of (float) s
+constexpr int ERFC_TAB_PER_OCTAVE_LOG2 = 8;
+constexpr int ERFC_TAB_BASE = (127 - 7) << ERFC_TAB_PER_OCTAVE_LOG2;
+constexpr int ERFC_TAB_ROW = 6;
+constexpr int ERFC_TAB_DEGREE = 4;
 // A list entry is (image code << J_SHIFT_BITS) | sorted index; image code = (kx+2) + 5 ((ky+1) + 3 (kz+1)) with
 // kx in -2..2 (a triclinic box's b and c vectors shift x by up to ax/2 each), ky, kz in -1..1: 45 codes, 6 bits.
 constexpr int J_SHIFT_BITS = 25;                 // sorted index in the low 25 bits of a list entry
@@ -212,6 +214,8 @@ struct Context {
     cudaEvent_t evSorted = nullptr, evDirectDone = nullptr;
     cudaStream_t auxStream = nullptr;        // exceptions / exclusion corrections, beside the list build
     cudaEvent_t evAuxFork = nullptr, evAuxDone = nullptr;
+    cudaEvent_t evPlaced = nullptr, evExclDone = nullptr;   // k_excl_range on auxStream, beside the block construction
+    bool sideFork = false, exclRangeForked = false;
     bool phaseDirect = false, phaseRecip = false, phaseEnergy = false, directOverlapped = false;
     const double* phasePos64 = nullptr;
     int phase = 0;                           // 0 idle, 1 begun, 2 convolved

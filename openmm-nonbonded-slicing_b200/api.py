@@ -402,6 +402,10 @@ class SlicedNonbondedForce:
     def getPMEParametersInContext(self, context):
         return context._impl(self).getPMEParameters()
 
+    def getLJPMEParametersInContext(self, context):
+        """openmmapi/include/SlicedNonbondedForce.h:31, openmmapi/src/SlicedNonbondedForce.cpp:188-190"""
+        return context._impl(self).getLJPMEParameters()
+
     def updateParametersInContext(self, context):
         context._impl(self).updateParametersInContext(context)
 
@@ -478,6 +482,10 @@ class SlicedNonbondedForceImpl:
 
     def getPMEParameters(self):
         return self.kernel.getPMEParameters()
+
+    def getLJPMEParameters(self):
+        """openmmapi/src/SlicedNonbondedForceImpl.cpp:365-367"""
+        return self.kernel.getLJPMEParameters()
 
     @staticmethod
     def calcPMEParameters(system, force, lj=False):

@@ -273,6 +273,9 @@ def test_ljpme_port_matches_compiled_reference(nbs, oracle, seed, nsub, tilt, gr
     force.setLJPMEParameters(2.4, *dgrid)
     desc = nbs.build_desc(system, force)
     assert desc.desc.use_switching_function == 0
+    ctx = nbs.Context(system, oracle.OraclePlatform("port"))
+    assert force.getLJPMEParametersInContext(ctx) == (2.4,)+tuple(dgrid)
+    assert force.getPMEParametersInContext(ctx)[1:] == tuple(grid)
     box = np.array(system.getDefaultPeriodicBoxVectors()).reshape(9)
     lam = rng.uniform(0.1, 1.0, size=(force.getNumSlices(), 2))
     gv = np.array([0.3, 0.7, 0.4])

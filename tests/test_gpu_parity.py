@@ -356,6 +356,46 @@ def test_triclinic_random_systems(nbs, platform, oracle, seed, nsub, n, L, grid,
         three_way(kernel, kernel.desc, positions, box, lam, run)
 
 
+@pytest.mark.parametrize("method,flag,tilt", [("LJPME", "NBS_FLAG_FP32_ENERGY", None), ("Ewald", "NBS_FLAG_FP32_ENERGY", None),
+                                              ("PME", "NBS_FLAG_SORTED_PME", (0.3, -0.2, 0.4)), ("PME", "NBS_FLAG_LINE_FFT", (0.3, -0.2, 0.4)),
+                                              ("LJPME", "NBS_FLAG_NO_GRAPH", (-0.5, 0.5, -0.5)), ("Ewald", "NBS_FLAG_NO_GRAPH", None)])
+def test_method_and_flag_combinations(nbs, oracle, method, flag, tilt):
+    """The late additions on the paths they do not take by default: single-precision energies (looser energy
+    tolerance: that is the plugin's "single" mode) with the LJPME / Ewald pair-kernel variants, a triclinic box through
+    the sorted-PME and line-FFT paths, plain launches; and the forces-only evaluation (no slice energies requested)
+    against the same oracle forces."""
+    import torch
+    rng = np.random.default_rng(91)
+    system, force, positions = random_system(nbs, rng, n=400, nsub=3, L=2.8, grid=(24, 20, 24), method=method, tilt=tilt)
+    if method == "LJPME":
+        force.setLJPMEParameters(2.4, 14, 12, 14)
+    fp32 = flag == "NBS_FLAG_FP32_ENERGY"
+    ctx = nbs.Context(system, nbs.Platform(flags=getattr(nbs.abi, flag)))
+    ref = nbs.Context(system, oracle.OraclePlatform("port"))
+    for c in (ctx, ref):
+        c.setPositions(positions)
+        c.setParameter("lc", 0.6)
+        c.setParameter("lv", 0.3)
+    for _ in range(3):                      # plain launches, graph capture, graph replay
+        a = ctx.getState(getEnergy=True, getForces=True)
+    b = ref.getState(getEnergy=True, getForces=True)
+    assert force_rel_rms(a.getForces(), b.getForces()) <= F_TOL
+    ea, eb = ctx.impls[0].kernel.lastSliceEnergies, ref.impls[0].kernel.lastSliceEnergies
+    err = np.abs(ea-eb)/np.maximum(np.abs(eb), 1.0)
+    assert err.max() <= (2e-4 if fp32 else E_TOL), err
+    # forces only
+    kernel = ctx.impls[0].kernel
+    pos = torch.tensor(positions, dtype=torch.float64, device="cuda")
+    frc = torch.zeros((400, 3), dtype=torch.float64, device="cuda")
+    lam = np.ones((6, 2))
+    lam[1] = [0.6, 0.3]
+    box = np.array(system.getDefaultPeriodicBoxVectors()).reshape(9)
+    for _ in range(3):
+        kernel.execute_device(pos.data_ptr(), box, frc.data_ptr(), lam, want_energies=False)
+    torch.cuda.synchronize()
+    assert force_rel_rms(frc.cpu().numpy(), b.getForces()) <= F_TOL
+
+
 def test_non_reduced_box_is_refused(nbs, platform):
     """Box vectors outside OpenMM's reduced form are an error, not a silently different lattice."""
     system = nbs.System()

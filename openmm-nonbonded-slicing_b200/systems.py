@@ -248,3 +248,67 @@ def make_system(name, seed=None, derivatives=True, guard_band=GUARD_BAND):
             force.addEnergyParameterDerivative(pname)
     box = np.diag([L, L, L])
     return SyntheticSystem(name, system, force, positions, box, cfg["description"], lambda_names)
+
+
+# ---------------------------------------------------------------------------------------------
+# Small variants for the methods and box shapes beyond the BASELINE configurations: what the golden
+# fixtures tests/golden/{C1_ewald, C1_ljpme, T1_pme, T1_ljpme}_reference.npz are generated from
+# (oracle/make_golden.py).  Everything comes from SplitMix64, so the systems are identical everywhere.
+# ---------------------------------------------------------------------------------------------
+VARIANTS = {
+    "C1_ewald": "C1 with the method switched to plain Ewald (kmax from calcEwaldParameters at tolerance 5e-4)",
+    "C1_ljpme": "C1 with LJPME, dispersion grid 12^3 at alpha_d = 2.4",
+    "T1_pme": "300 atoms on a sheared lattice, triclinic box (tilt 0.3, -0.2, 0.4), 3 subsets, PME 20^3, 1-4 exceptions, offsets",
+    "T1_ljpme": "the same system with LJPME (dispersion grid 12^3)",
+}
+
+
+def _triclinic_test_system(method, seed=4242, n=300, nsub=3, L=2.6, tilt=(0.3, -0.2, 0.4), grid=20):
+    system = System()
+    force = SlicedNonbondedForce(nsub)
+    force.setNonbondedMethod(method)
+    force.setCutoffDistance(CUTOFF)
+    force.setPMEParameters(2.8, grid, grid, grid)
+    box = np.array([[L, 0, 0], [tilt[0]*L, L, 0], [tilt[1]*L, tilt[2]*L, L]], dtype=float)
+    system.setDefaultPeriodicBoxVectors(*box)
+    side = int(math.ceil(n**(1/3)))
+    sites = np.array([(i, j, k) for i in range(side) for j in range(side) for k in range(side)][:n], dtype=float)
+    jitter = (splitmix64(seed, 1, 3*n).reshape(n, 3) - 0.5)*0.1
+    images = np.floor(splitmix64(seed, 2, 3*n).reshape(n, 3)*5) - 2        # unwrapped input: whole box vectors added
+    positions = ((sites + 0.5)/side + images) @ box + jitter
+    charges = (splitmix64(seed, 3, n) - 0.5)*1.6
+    sigmas = 0.15 + 0.15*splitmix64(seed, 4, n)
+    epsilons = 0.1 + 0.9*splitmix64(seed, 5, n)
+    subsets = np.floor(splitmix64(seed, 6, n)*nsub).astype(int)
+    for i in range(n):
+        system.addParticle(1.0)
+        force.addParticle(float(charges[i]), float(sigmas[i]), float(epsilons[i]))
+        force.setParticleSubset(i, int(subsets[i]))
+    force.createExceptionsFromBonds([(i, i+1) for i in range(0, n-1) if i % 5 != 4], 1/1.2, 0.5)
+    force.addGlobalParameter("off", 0.3)
+    force.addParticleParameterOffset("off", 3, 0.5, 0.01, 0.2)
+    force.addExceptionParameterOffset("off", 2, 0.2, 0.01, 0.1)
+    force.setExceptionsUsePeriodicBoundaryConditions(True)
+    system.addForce(force)
+    return system, force, positions, box
+
+
+def make_variant(name):
+    """See VARIANTS.  Returns a SyntheticSystem; ``box`` is the 3x3 matrix of box vectors (rows)."""
+    if name == "C1_ewald":
+        s = make_system("C1")
+        s.force.setNonbondedMethod(SlicedNonbondedForce.Ewald)
+    elif name == "C1_ljpme":
+        s = make_system("C1")
+        s.force.setNonbondedMethod(SlicedNonbondedForce.LJPME)
+        s.force.setLJPMEParameters(2.4, 12, 12, 12)
+    elif name in ("T1_pme", "T1_ljpme"):
+        method = SlicedNonbondedForce.PME if name == "T1_pme" else SlicedNonbondedForce.LJPME
+        system, force, positions, box = _triclinic_test_system(method)
+        if name == "T1_ljpme":
+            force.setLJPMEParameters(2.4, 12, 12, 12)
+        s = SyntheticSystem(name, system, force, positions, box, VARIANTS[name], [])
+    else:
+        raise KeyError(name)
+    s.name, s.description = name, VARIANTS[name]
+    return s

@@ -61,13 +61,16 @@ def three_way(kernel, desc, s_positions, box, lam, oracle_eval):
             assert (count, h) == (pair_count, pair_hash), f"pair set differs ({count} vs {pair_count})"
 
 
-@pytest.mark.parametrize("name", ["C1", "C2"])
+@pytest.mark.parametrize("name", ["C1", "C2", "C1_ewald", "C1_ljpme", "T1_pme", "T1_ljpme"])
 def test_reference_fixture(nbs, platform, systems, name):
-    """CUDA path vs the outputs of the reference's own compiled TUs (tests/golden, oracle/make_golden.py)."""
+    """CUDA path vs the outputs of the reference's own compiled TUs (tests/golden, oracle/make_golden.py): the BASELINE
+    configurations C1 / C2 and the variants beyond them -- plain Ewald, LJPME, a triclinic box (systems.VARIANTS)."""
     g = np.load(os.path.join(GOLDEN, f"{name}_reference.npz"))
-    s = systems.make_system(name)
+    s = systems.make_variant(name) if name in systems.VARIANTS else systems.make_system(name)
     kernel = nbs.B200CalcSlicedNonbondedForceKernel(platform)
     kernel.initialize(s.system, s.force)
+    if "global_values" in g.files:
+        kernel._push_parameters(g["lambdas"], np.ascontiguousarray(g["global_values"], dtype=np.float64))
 
     def fixture(tag, direct, recip):
         return g[f"{tag}_energies"], g[f"{tag}_forces"], int(g["pair_count"][0]), int(g["pair_hash"][0])

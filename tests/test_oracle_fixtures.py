@@ -17,15 +17,18 @@ def systems():
     return importlib.import_module("openmm-nonbonded-slicing_b200.systems")
 
 
-@pytest.mark.parametrize("name", ["C1", "C2"])
+@pytest.mark.parametrize("name", ["C1", "C2", "C1_ewald", "C1_ljpme", "T1_pme", "T1_ljpme"])
 def test_port_matches_reference_fixture(nbs, oracle, systems, name):
+    """The restatement against committed outputs of the reference's own TUs (oracle/make_golden.py): the BASELINE
+    configurations C1 / C2 and the variants beyond them -- plain Ewald, LJPME, a triclinic box (systems.VARIANTS)."""
     g = np.load(os.path.join(GOLDEN, f"{name}_reference.npz"))
-    s = systems.make_system(name)
+    s = systems.make_variant(name) if name in systems.VARIANTS else systems.make_system(name)
     # the generator is deterministic: same positions as when the fixture was made
     assert np.allclose([s.positions.sum(), (s.positions**2).sum()], g["positions_checksum"], rtol=1e-13)
-    desc = nbs.build_desc(s.system, s.force)
+    desc = nbs.build_desc(s.system, s.force, legal_grid=True)
+    gv = g["global_values"] if "global_values" in g.files else None
     for tag, (direct, recip) in {"full": (True, True), "direct": (True, False), "recip": (False, True)}.items():
-        r = oracle.evaluate(desc, s.positions, s.box, g["lambdas"], None, direct, recip, kind="port")
+        r = oracle.evaluate(desc, s.positions, s.box, g["lambdas"], gv, direct, recip, kind="port")
         assert force_rel_rms(r.forces, g[f"{tag}_forces"]) < 1e-12
         assert np.allclose(r.slice_energies, g[f"{tag}_energies"], rtol=1e-11, atol=1e-9)
         if direct:

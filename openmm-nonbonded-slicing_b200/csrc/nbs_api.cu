@@ -709,7 +709,8 @@ static int phaseBegin(Context& c, const nbs_exec_args* args) {
         NBS_CUDA_CHECK(cudaStreamWaitEvent(c.directStream, c.evSorted, 0));
         c.stream = c.directStream;
     }
-    c.sideFork = overlap && c.phaseDirect && c.auxStream != nullptr;
+    // (only when this rank builds lists: launchBuildLists is where the side stream joins again)
+    c.sideFork = overlap && c.phaseDirect && c.auxStream != nullptr && c.blockWidth != 0;
     status = launchSortRest(c);
     if (status == NBS_OK && c.phaseDirect) {
         if (overlap && !forkEarly) {

@@ -496,6 +496,136 @@ def test_ewald_exceptions(nbs, platform):
     assert_equal_tol(expected, e2-e1, 1e-4)
 
 
+def test_two_forces(nbs, platform):
+    """testTwoForces :815-881 -- two SlicedNonbondedForces in one System (separate kernel instances that must not share
+    mutable state), separate force groups, updateParametersInContext on each, then both switched to PME."""
+    system = nbs.System()
+    system.addParticle(1.0)
+    system.addParticle(1.0)
+    nb1 = nbs.SlicedNonbondedForce(1)
+    nb1.addParticle(-1.5, 1, 1.2)
+    nb1.addParticle(0.5, 1, 1.0)
+    system.addForce(nb1)
+    nb2 = nbs.SlicedNonbondedForce(1)
+    nb2.addParticle(0.4, 1.4, 0.5)
+    nb2.addParticle(0.3, 1.8, 1.0)
+    nb2.setForceGroup(1)
+    system.addForce(nb2)
+    context = nbs.Context(system, platform)
+    context.setPositions([[0, 0, 0], [1.5, 0, 0]])
+    K = nbs.ONE_4PI_EPS0
+    e1 = context.getState(getEnergy=True, groups=1 << 0).getPotentialEnergy()
+    assert_equal_tol(K*(-1.5*0.5)/1.5 + 4.0*math.sqrt(1.2*1.0)*((1.0/1.5)**12-(1.0/1.5)**6), e1, TOL)
+    e2 = context.getState(getEnergy=True, groups=1 << 1).getPotentialEnergy()
+    assert_equal_tol(K*(0.4*0.3)/1.5 + 4.0*math.sqrt(0.5*1.0)*((1.6/1.5)**12-(1.6/1.5)**6), e2, TOL)
+    assert_equal_tol(e1+e2, context.getState(getEnergy=True).getPotentialEnergy(), TOL)
+    nb1.setParticleParameters(0, -1.2, 1.1, 1.4)
+    nb1.updateParametersInContext(context)
+    nb2.setParticleParameters(0, 0.5, 1.6, 0.6)
+    nb2.updateParametersInContext(context)
+    e1 = context.getState(getEnergy=True, groups=1 << 0).getPotentialEnergy()
+    assert_equal_tol(K*(-1.2*0.5)/1.5 + 4.0*math.sqrt(1.4*1.0)*((1.05/1.5)**12-(1.05/1.5)**6), e1, TOL)
+    e2 = context.getState(getEnergy=True, groups=1 << 1).getPotentialEnergy()
+    assert_equal_tol(K*(0.5*0.3)/1.5 + 4.0*math.sqrt(0.6*1.0)*((1.7/1.5)**12-(1.7/1.5)**6), e2, TOL)
+    # the PME leg needs a periodic box (at least twice the default 1 nm cutoff)
+    system.setDefaultPeriodicBoxVectors([4, 0, 0], [0, 4, 0], [0, 0, 4])
+    nb1.setNonbondedMethod(nb1.PME)
+    nb2.setNonbondedMethod(nb2.PME)
+    context.reinitialize(True)
+    e1 = context.getState(getEnergy=True, groups=1 << 0).getPotentialEnergy()
+    e2 = context.getState(getEnergy=True, groups=1 << 1).getPotentialEnergy()
+    assert_equal_tol(e1+e2, context.getState(getEnergy=True).getPotentialEnergy(), TOL)
+    assert e1 != 0 and e2 != 0 and e1 != e2
+
+
+SEPARATION_CASES = [(m, x) for m in ("NoCutoff", "CutoffNonPeriodic", "CutoffPeriodic", "Ewald", "PME", "LJPME") for x in (False, True)]
+
+
+def scaling_parameter_separation(nbs, platform, method, exceptions, tol):
+    """testScalingParameterSeparation :1320-1456 -- one parameter scaling both terms of slice (0,1) against separate
+    Coulomb / LJ parameters; parameters on the diagonal slices; E = sum lambda dE/dlambda because every slice is
+    scaled; overall, direct-space-only and reciprocal-space-only groups."""
+    num_molecules = 100
+    n = 2*num_molecules
+    cutoff = 3.5
+    L = 7.0 if exceptions else 10.0
+    rng = np.random.default_rng(17)
+    systems, forces = [nbs.System(), nbs.System()], [nbs.SlicedNonbondedForce(2), nbs.SlicedNonbondedForce(2)]
+    M = int(round(num_molecules**(1/3)))
+    if M*M*M < num_molecules:
+        M += 1
+    positions = np.zeros((n, 3))
+    subset1 = rng.random(n) < 0.5
+    for f in forces:
+        f.setNonbondedMethod(getattr(f, method))
+        f.setCutoffDistance(cutoff)
+        f.setUseDispersionCorrection(True)
+        f.setReciprocalSpaceForceGroup(1)
+        f.setEwaldErrorTolerance(1e-4)
+    for k in range(num_molecules):
+        iz = k//(M*M)
+        iy = (k - iz*M*M)//M
+        ix = k - M*(iy + iz*M)
+        center = np.array([ix+0.5, iy+0.5, iz+0.5])*L/M
+        delta = np.array([0.5-ix % 2, 0.5-iy % 2, 0.5-iz % 2])/2
+        i, j = 2*k, 2*k+1
+        positions[i], positions[j] = center+delta, center-delta
+        for f in forces:
+            f.addParticle(1-2*(i % 2), 1, 1)
+            f.addParticle(1-2*(j % 2), 1, 1)
+            if exceptions:
+                f.addException(i, j, float((1-2*(i % 2))*(1-2*(j % 2))), 1, 1)
+    for s in systems:
+        for _ in range(n):
+            s.addParticle(1.0)
+        s.setDefaultPeriodicBoxVectors([L, 0, 0], [0, L, 0], [0, 0, L])
+    for f in forces:
+        for k in range(n):
+            if subset1[k]:
+                f.setParticleSubset(k, 1)
+    lam, value = 0.5, 0.3
+    s1, s2 = forces
+    s1.addGlobalParameter("lambda", lam)
+    s1.addScalingParameter("lambda", 0, 1, True, True)
+    s1.addEnergyParameterDerivative("lambda")
+    s2.addGlobalParameter("lambdaCoulomb", lam)
+    s2.addGlobalParameter("lambdaLJ", lam)
+    s2.addScalingParameter("lambdaCoulomb", 0, 1, True, False)
+    s2.addScalingParameter("lambdaLJ", 0, 1, False, True)
+    s2.addEnergyParameterDerivative("lambdaCoulomb")
+    s2.addEnergyParameterDerivative("lambdaLJ")
+    s1.addGlobalParameter("alpha", value)
+    s1.addScalingParameter("alpha", 0, 0, True, True)
+    s1.addEnergyParameterDerivative("alpha")
+    s1.addGlobalParameter("beta", value)
+    s1.addScalingParameter("beta", 1, 1, True, True)
+    s1.addEnergyParameterDerivative("beta")
+    s2.addGlobalParameter("gamma", value)
+    s2.addScalingParameter("gamma", 0, 0, True, True)
+    s2.addScalingParameter("gamma", 1, 1, True, True)
+    s2.addEnergyParameterDerivative("gamma")
+    systems[0].addForce(s1)
+    systems[1].addForce(s2)
+    contexts = [nbs.Context(systems[0], platform), nbs.Context(systems[1], platform)]
+    for c in contexts:
+        c.setPositions(positions)
+    for groups in (0xFFFFFFFF, 1 << 0, 1 << 1):
+        st1 = contexts[0].getState(getEnergy=True, getForces=True, getParameterDerivatives=True, groups=groups)
+        st2 = contexts[1].getState(getEnergy=True, getForces=True, getParameterDerivatives=True, groups=groups)
+        d1, d2 = st1.getEnergyParameterDerivatives(), st2.getEnergyParameterDerivatives()
+        assert_equal_tol(st1.getPotentialEnergy(), st2.getPotentialEnergy(), tol)
+        for fa, fb in zip(st1.getForces(), st2.getForces()):
+            assert_equal_vec(fa, fb, tol)
+        assert_equal_tol(d1["lambda"], d2["lambdaCoulomb"]+d2["lambdaLJ"], tol)
+        assert_equal_tol(st1.getPotentialEnergy(), lam*d1["lambda"]+value*(d1["alpha"]+d1["beta"]), tol)
+        assert_equal_tol(d1["alpha"]+d1["beta"], d2["gamma"], tol)
+
+
+@pytest.mark.parametrize("method,exceptions", SEPARATION_CASES)
+def test_scaling_parameter_separation(nbs, platform, method, exceptions):
+    scaling_parameter_separation(nbs, platform, method, exceptions, 1e-4)
+
+
 def test_parameter_clash(nbs, platform):
     """python/tests/TestSlicedNonbondedForce.py:51-67 and SlicedNonbondedForceImpl.cpp:114-131"""
     system = nbs.System()

@@ -527,8 +527,7 @@ def test_two_forces(nbs, platform):
     assert_equal_tol(K*(-1.2*0.5)/1.5 + 4.0*math.sqrt(1.4*1.0)*((1.05/1.5)**12-(1.05/1.5)**6), e1, TOL)
     e2 = context.getState(getEnergy=True, groups=1 << 1).getPotentialEnergy()
     assert_equal_tol(K*(0.5*0.3)/1.5 + 4.0*math.sqrt(0.6*1.0)*((1.7/1.5)**12-(1.7/1.5)**6), e2, TOL)
-    # the PME leg needs a periodic box (at least twice the default 1 nm cutoff)
-    system.setDefaultPeriodicBoxVectors([4, 0, 0], [0, 4, 0], [0, 0, 4])
+    # (PME runs in the System's default 2 nm box, exactly twice the default cutoff, as in the reference's test)
     nb1.setNonbondedMethod(nb1.PME)
     nb2.setNonbondedMethod(nb2.PME)
     context.reinitialize(True)

@@ -227,6 +227,23 @@ def test_ewald_agrees_with_pme(nbs, oracle):
     assert np.abs(a.slice_energies-b.slice_energies).max() < 1e-5*np.abs(b.slice_energies).max()
 
 
+def test_ewald_agrees_with_pme_on_c1(nbs, oracle, systems):
+    """The same second opinion on BASELINE config 0 (the TIP3P box): with both reciprocal sums converged (tolerance
+    1e-6: 77^3 PME grid, 11 Ewald vectors per axis) the absolute forces and slice energies agree -- this is what pins
+    absolute PME values here, where OpenMM's own NonbondedForce (the reference tests' arbiter) is not available."""
+    s = systems.make_system("C1")
+    lam = np.ones((s.force.getNumSlices(), 2))
+    s.force.setEwaldErrorTolerance(1e-6)
+    s.force.setPMEParameters(0, 0, 0, 0)
+    results = {}
+    for method in (s.force.Ewald, s.force.PME):
+        s.force.setNonbondedMethod(method)
+        results[method] = oracle.evaluate(nbs.build_desc(s.system, s.force), s.positions, s.box, lam, None, True, True, kind="port")
+    a, b = results[s.force.Ewald], results[s.force.PME]
+    assert force_rel_rms(a.forces, b.forces) < 2e-5
+    assert np.abs(a.slice_energies-b.slice_energies).max() < 0.05        # kJ/mol, out of a self energy of 6e4 kJ/mol
+
+
 def test_ewald_rejects_triclinic(nbs, oracle):
     system = nbs.System()
     system.setDefaultPeriodicBoxVectors([3, 0, 0], [0.5, 3, 0], [0, 0, 3])

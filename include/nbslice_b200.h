@@ -251,6 +251,11 @@ int nbs_get_launch_count(const nbs_context* ctx, int64_t* launches);
  * [3] candidate pair evaluations (tiles*1024), [4] exclusion-list entries */
 int nbs_get_nlist_stats(nbs_context* ctx, int64_t stats[8]);
 
+/* Measured instruction-rate ceilings of `device` (diagnostics for the benchmark's roofline; no reference
+ * counterpart): out[0] = dense FP32 FMA rate in TFLOP/s, out[1] = rsqrt.approx rate in Gop/s,
+ * out[2] = SM count, out[3] = nominal SM clock in MHz. */
+int nbs_measure_peaks(int32_t device, double out[4]);
+
 static inline uint64_t nbs_pair_hash(uint32_t first, uint32_t second) {
     uint64_t x = ((uint64_t) first << 32) | second;       /* splitmix64 finaliser */
     x += 0x9E3779B97F4A7C15ull;

@@ -154,7 +154,7 @@ EXPORTS = [
     "nbs_get_pme_parameters", "nbs_get_ljpme_parameters", "nbs_get_num_slices", "nbs_get_pair_set", "nbs_get_exclusion_set",
     "nbs_get_kernel_times", "nbs_get_launch_count", "nbs_get_nlist_stats",
     "nbs_set_shard", "nbs_execute_begin", "nbs_execute_convolve", "nbs_execute_finish", "nbs_get_exchange_buffers",
-    "nbs_debug_set_list_capacity",
+    "nbs_debug_set_list_capacity", "nbs_measure_peaks",
 ]
 
 
@@ -196,6 +196,7 @@ def load_library():
         getattr(lib, name).argtypes = [C.c_void_p, C.POINTER(ExecArgs)]
     lib.nbs_debug_set_list_capacity.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
     lib.nbs_get_exchange_buffers.argtypes = [C.c_void_p, C.POINTER(ExchangeBuffers)]
+    lib.nbs_measure_peaks.argtypes = [C.c_int32, _f64p]
     for name in EXPORTS:
         getattr(lib, name)
     if lib.nbs_abi_version() != ABI_VERSION:

@@ -215,6 +215,7 @@ __global__ void __launch_bounds__(BUILD_WARPS*32, 4) k_build_lists(BuildArgs a) 
         const int tiles = ((totJ + 31) >> 5) + ((totX + 31) >> 5);
         const int n = (tiles + a.chunkTiles - 1)/a.chunkTiles;
         const int base = atomicAdd(a.itemCount, n);
+        if (base + n > a.maxItems) overflow = true;      // (never with the host's sizing of `items`; redo rather than drop work)
         for (int k = 0; k < n; k++)
             if (base + k < a.maxItems) a.items[base + k] = make_int4(lb, k*a.chunkTiles, first, count);
     }

@@ -50,6 +50,7 @@ static int readDescription(Context& c, const nbs_system_desc& d, bool creating) 
     if (!creating) {
         // ReferenceNonbondedSlicingKernels.cpp:271-272
         if (d.num_particles != c.N) return fail(NBS_ERR_INVALID, "updateParametersInContext: The number of particles has changed");
+        if (d.num_subsets != c.nS) return fail(NBS_ERR_INVALID, "updateParametersInContext: The number of subsets has changed");
     }
     if (d.num_particles > J_INDEX_MASK) return fail(NBS_ERR_UNSUPPORTED, "too many particles");
     const int N = d.num_particles;
@@ -219,34 +220,19 @@ static int applyParameters(Context& c) {
     return NBS_OK;
 }
 
-// B-spline moduli: pme_calculate_bsplines_moduli, ReferencePME.cpp:88-183 (order 5), and FFT twiddles.
-static void bsplineModuli(int ngrid, double* moduli) {
-    const int order = PME_ORDER;
-    double data[PME_ORDER];
-    data[order-1] = 0; data[1] = 0; data[0] = 1;
-    for (int k = 3; k < order; k++) {
-        double div = 1.0/(k-1.0);
-        data[k-1] = 0;
-        for (int l = 1; l < (k-1); l++) data[k-l-1] = div*(l*data[k-l-2] + (k-l)*data[k-l-1]);
-        data[0] = div*data[0];
+// |DFT of the order-5 cardinal B-spline sampled at the integers|^2 along one axis (what the reference tabulates with
+// an O(n^2) cosine/sine sum, ReferencePME.cpp:88-183).  The samples are M5(1..4) = 1/24, 11/24, 11/24, 1/24 --
+// symmetric about 2.5 -- so the transform is a phase factor times (cos(3t/2) + 11 cos(t/2))/12 with t = 2 pi k/n and
+// the modulus has a closed form.  It vanishes only at t = pi (k = n/2, even n); like the reference (:170-176) such
+// an entry is replaced by the mean of its two neighbours.
+static void splineModuli(int n, double* out) {
+    for (int k = 0; k < n; k++) {
+        const double halfT = kPi*k/n;
+        const double amplitude = (std::cos(3.0*halfT) + 11.0*std::cos(halfT))/12.0;
+        out[k] = amplitude*amplitude;
     }
-    double div = 1.0/(order-1);
-    data[order-1] = 0;
-    for (int l = 1; l < (order-1); l++) data[order-l-1] = div*(l*data[order-l-2] + (order-l)*data[order-l-1]);
-    data[0] = div*data[0];
-    std::vector<double> bsp(std::max(ngrid, order+1), 0.0);
-    for (int i = 1; i <= order; i++) bsp[i] = data[i-1];
-    for (int i = 0; i < ngrid; i++) {
-        double sc = 0, ss = 0;
-        for (int j = 0; j < ngrid; j++) {
-            double arg = (2.0*M_PI*i*j)/ngrid;
-            sc += bsp[j]*cos(arg);
-            ss += bsp[j]*sin(arg);
-        }
-        moduli[i] = sc*sc + ss*ss;
-    }
-    for (int i = 0; i < ngrid; i++)
-        if (moduli[i] < 1.0e-7) moduli[i] = (moduli[(i-1+ngrid)%ngrid] + moduli[(i+1)%ngrid])/2;
+    for (int k = 0; k < n; k++)
+        if (out[k] < 1.0e-7) out[k] = 0.5*(out[(k + n - 1) % n] + out[(k + 1) % n]);
 }
 
 // LJPME runs the PME chain twice: charges on the (alpha, grid) set of setUsePME, then C6 coefficients on the set
@@ -269,9 +255,9 @@ int uploadPmeTables(Context& c) {
     const int nx = c.grid[0], ny = c.grid[1], nz = c.grid[2];
     const int total = nx + ny + nz;
     c.hModuli.assign(total, 0.0);
-    bsplineModuli(nx, c.hModuli.data());
-    bsplineModuli(ny, c.hModuli.data() + nx);
-    bsplineModuli(nz, c.hModuli.data() + nx + ny);
+    splineModuli(nx, c.hModuli.data());
+    splineModuli(ny, c.hModuli.data() + nx);
+    splineModuli(nz, c.hModuli.data() + nx + ny);
     std::vector<float2> tw(total);
     std::vector<double2> twD(total);
     int off = 0;
@@ -846,7 +832,9 @@ static int phaseComplete(Context& c, const nbs_exec_args* args) {
             const double a6 = std::pow(c.dispAlpha, 6.0);
             for (int i = 0; i < c.nS; i++) E[2*(i*(i+3)/2) + 1] += a6*c.subsetC6Self[i];
         }
-        if (c.phaseDirect && c.periodic)   // dispersion correction (periodic methods only), ReferenceNonbondedSlicingKernels.cpp:244-249
+        // dispersion correction: `periodic || ewald || pme` in the reference, i.e. NOT with LJPME, whose reciprocal
+        // sum already carries the long-range dispersion (ReferenceNonbondedSlicingKernels.cpp:244-249, :317)
+        if (c.phaseDirect && c.periodic && !c.ljpme())
             for (int s = 0; s < c.nSl; s++) E[2*s+1] += c.dispersion[s]/volume;
     }
     return NBS_OK;
@@ -883,6 +871,19 @@ static unsigned long long graphSignature(const Context& c, const nbs_exec_args* 
     return h | 1ull;
 }
 
+// A captured evaluation never contains k_eterm (it is captured on the second identical evaluation, when the
+// influence function is already up to date), so a replay is only valid while the tables on the device are still
+// the ones of this box: an evaluation at another box in between (a rejected barostat trial) rewrites them.
+static bool etermMatchesBox(const Context& c, const double* box) {
+    if (!c.usesPmeGrid()) return true;
+    const double want[6] = {box[0], box[4], box[8], box[3], box[6], box[7]};
+    for (int k = 0; k < 6; k++) {
+        if (c.etermBox[k] != want[k]) return false;
+        if (c.ljpme() && c.etermBoxDisp[k] != want[k]) return false;
+    }
+    return true;
+}
+
 static bool hostPointerIsPinned(const void* p) {
     cudaPointerAttributes attr;
     if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return false; }
@@ -902,6 +903,11 @@ int nbs_execute(nbs_context* ctx, const nbs_exec_args* args) {
     for (int attempt = 0; attempt < 7; attempt++) {
         int status;
         const unsigned long long key = graphable ? graphSignature(c, args) : 0;
+        if (graphable && c.graphExec && c.graphKey == key && args->include_reciprocal && !etermMatchesBox(c, args->box)) {
+            cudaGraphExecDestroy(c.graphExec);     // stale influence function: plain path now, capture again later
+            c.graphExec = nullptr;
+            c.graphKey = 0;
+        }
         if (graphable && c.graphExec && c.graphKey == key) {
             // replay
             status = validateExec(c, args);
@@ -1019,7 +1025,7 @@ int nbs_get_exchange_buffers(nbs_context* ctx, nbs_exchange_buffers* out) {
 }
 
 int nbs_get_pme_parameters(const nbs_context* ctx, double* alpha, int32_t* nx, int32_t* ny, int32_t* nz) {
-    if (!ctx) return fail(NBS_ERR_INVALID, "null argument");
+    if (!ctx || !alpha || !nx || !ny || !nz) return fail(NBS_ERR_INVALID, "null argument");
     if (ctx->c.method != NBS_METHOD_PME && ctx->c.method != NBS_METHOD_LJPME)
         return fail(NBS_ERR_INVALID, "getPMEParametersInContext: This Context is not using PME or LJPME");
     *alpha = ctx->c.alpha; *nx = ctx->c.grid[0]; *ny = ctx->c.grid[1]; *nz = ctx->c.grid[2];

@@ -97,7 +97,7 @@ std::string executeReference(const System& s, const double* pos, const Box& box,
                 int slice = s.slice14[k];
                 nonbonded14.calculateBondIxn(indices, posData, params, forceData, sliceLambdas[slice], sliceEnergies[slice]);
             }
-            if (periodic || ewald || pme || ljpme) {
+            if (periodic || ewald || pme) {       // not LJPME: ReferenceNonbondedSlicingKernels.cpp:244
                 double volume = box.v[0][0]*box.v[1][1]*box.v[2][2];
                 for (int slice = 0; slice < s.numSlices; slice++)
                     sliceEnergies[slice][1] += s.dispersionCoefficients[slice]/volume;

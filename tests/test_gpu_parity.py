@@ -578,6 +578,38 @@ def test_repeatable_forces(nbs, platform, systems):
     assert np.array_equal(out[0], out[1]) and np.array_equal(out[0], out[2])
 
 
+def test_graph_replay_survives_box_change(nbs, platform, systems):
+    """A, A, A, B, A: the evaluation at box A is captured into a CUDA graph on its second run; one evaluation at
+    another box (a rejected barostat trial) rewrites the influence function on the device, and the graph -- which
+    never contains k_eterm -- must not be replayed against it when the old box comes back."""
+    import torch
+    s = systems.make_system("C2")
+    n = s.force.getNumParticles()
+    lam = np.random.default_rng(5).uniform(0.3, 1.0, size=(s.force.getNumSlices(), 2))
+    pos = torch.tensor(s.positions, dtype=torch.float64, device="cuda")
+    box_a, box_b = s.box.copy(), s.box*1.013
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def run(kernel, box):
+        f = torch.zeros((n, 3), dtype=torch.float64, device="cuda")
+        e = kernel.execute_device(pos.data_ptr(), box, f.data_ptr(), lam, stream=stream)
+        torch.cuda.synchronize()
+        return e, f.cpu().numpy()
+    kernel = nbs.B200CalcSlicedNonbondedForceKernel(platform)
+    kernel.initialize(s.system, s.force)
+    plain = nbs.B200CalcSlicedNonbondedForceKernel(nbs.Platform(flags=nbs.abi.NBS_FLAG_NO_GRAPH))
+    plain.initialize(s.system, s.force)
+    # (the force buffer is a new allocation each time; PyTorch's caching allocator hands the same block back,
+    # so the graph signature -- which holds the pointers -- repeats)
+    results = [run(kernel, b) for b in (box_a, box_a, box_a, box_b, box_a, box_a, box_a)]
+    ref_a, ref_b = run(plain, box_a), run(plain, box_b)
+    for k in (0, 1, 2, 4, 5, 6):
+        assert np.allclose(results[k][0], ref_a[0], rtol=1e-9, atol=1e-7), k
+        assert force_rel_rms(results[k][1], ref_a[1]) < 1e-6, k
+    assert np.allclose(results[3][0], ref_b[0], rtol=1e-9, atol=1e-7)
+    assert not np.allclose(ref_a[0], ref_b[0], rtol=1e-6)
+
+
 def test_stmv_size_properties(nbs, platform, systems):
     """C5 (1,066,628 atoms, 180^3 grid): size-independent properties instead of the 5-minute oracle run --
     momentum conservation of the direct-space forces, the lambda-derivative identity

@@ -47,7 +47,7 @@
 extern "C" {
 #endif
 
-#define NBS_ABI_VERSION 2
+#define NBS_ABI_VERSION 3
 
 /* status codes */
 #define NBS_OK                 0
@@ -78,6 +78,9 @@ extern "C" {
                                           grids whose planes exceed shared memory); test hook     */
 #define NBS_FLAG_SORTED_PME      0x20u /* PME always works from the cell-sorted records (the path of
                                           large systems); test hook                              */
+#define NBS_FLAG_NO_LIST_REUSE   0x40u /* rebuild the neighbour list on every evaluation, like the
+                                          Reference platform (default: built with a skin and kept
+                                          until an atom has moved half of it, see nbs_set_list_skin) */
 #define NBS_FLAG_FP32_ENERGY     0x8u  /* single-precision pair energies and PME grids (the
                                           plugin's "single" precision); default is double
                                           precision for every energy term, fp32 for forces    */
@@ -218,6 +221,21 @@ int nbs_execute_finish(nbs_context* ctx, const nbs_exec_args* args);
 /* valid between nbs_execute_begin and nbs_execute_finish of the evaluation in flight */
 int nbs_get_exchange_buffers(nbs_context* ctx, nbs_exchange_buffers* out);
 
+/*
+ * Neighbour-list policy of the periodic cutoff methods.  The list is built with cutoff + skin and re-used by later
+ * evaluations until some atom has moved more than skin/2 since the build -- measured on the device in every
+ * evaluation; an evaluation that finds the limit exceeded is redone with a fresh list before it returns, so
+ * results never depend on the policy (the exact cutoff test is the pair kernel's).  This is what the plugin's CUDA
+ * platform inherits from OpenMM's NonbondedUtilities (CommonNonbondedSlicingKernels.cpp:721, useNeighborList);
+ * the Reference platform rebuilds every time (ReferenceNonbondedSlicingKernels.cpp:197), which skin = 0 or
+ * NBS_FLAG_NO_LIST_REUSE selects.  Default skin: 0.07 nm.
+ */
+int nbs_set_list_skin(nbs_context* ctx, double skin_nm);
+/* out: [0] evaluations, [1] evaluations that built a list, [2] evaluations redone because the displacement limit
+ * was exceeded, [3] largest displacement (nm) since the build at the last evaluation, [4] skin (nm),
+ * [5] 1 if a re-usable list exists, [6] 1 if the last evaluation re-used one, [7] largest per-evaluation growth of [3] */
+int nbs_get_list_stats(const nbs_context* ctx, double out[8]);
+
 /* test hook: initial per-block capacities of the neighbour lists (they grow on demand; a tiny value
  * forces the NBS_RETRY path) */
 int nbs_debug_set_list_capacity(nbs_context* ctx, int32_t j_capacity, int32_t x_capacity);
@@ -248,13 +266,17 @@ int nbs_get_kernel_times(nbs_context* ctx, int32_t capacity, const char** names,
 /* number of kernels launched by this library on behalf of ctx since creation */
 int nbs_get_launch_count(const nbs_context* ctx, int64_t* launches);
 /* neighbour-list statistics of the last evaluation: [0] i-blocks, [1] j entries, [2] tiles,
- * [3] candidate pair evaluations (tiles*1024), [4] exclusion-list entries */
+ * [3] pair evaluations of the pair kernel (32 per step of 4 i atoms x 8 entries; only the clusters a
+ * group of entries can reach are stepped), [4] exclusion-list entries */
 int nbs_get_nlist_stats(nbs_context* ctx, int64_t stats[8]);
 
 /* Measured instruction-rate ceilings of `device` (diagnostics for the benchmark's roofline; no reference
  * counterpart): out[0] = dense FP32 FMA rate in TFLOP/s, out[1] = rsqrt.approx rate in Gop/s,
  * out[2] = SM count, out[3] = nominal SM clock in MHz. */
 int nbs_measure_peaks(int32_t device, double out[4]);
+/* out[0..4]: warp-instructions per clock per SM of DFMA, int32->double, float->double, double->float and
+ * int64->double conversions (what bounds the double-precision energy passes of the pair kernel) */
+int nbs_measure_dp_rates(int32_t device, double out[8]);
 
 static inline uint64_t nbs_pair_hash(uint32_t first, uint32_t second) {
     uint64_t x = ((uint64_t) first << 32) | second;       /* splitmix64 finaliser */

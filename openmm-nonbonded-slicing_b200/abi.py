@@ -24,6 +24,7 @@ NBS_FLAG_NO_GRAPH = 0x4
 NBS_FLAG_FP32_ENERGY = 0x8
 NBS_FLAG_LINE_FFT = 0x10
 NBS_FLAG_SORTED_PME = 0x20
+NBS_FLAG_NO_LIST_REUSE = 0x40
 
 NBS_MEM_HOST = 0
 NBS_MEM_DEVICE = 1
@@ -143,7 +144,7 @@ class DescArrays:
                 setattr(self.desc, name, value)
 
 
-ABI_VERSION = 2          # NBS_ABI_VERSION of include/nbslice_b200.h
+ABI_VERSION = 3          # NBS_ABI_VERSION of include/nbslice_b200.h
 LIB_PATH = os.environ.get("NBS_B200_LIBRARY") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libnbslice_b200.so")
 _lib = None
 
@@ -154,7 +155,7 @@ EXPORTS = [
     "nbs_get_pme_parameters", "nbs_get_ljpme_parameters", "nbs_get_num_slices", "nbs_get_pair_set", "nbs_get_exclusion_set",
     "nbs_get_kernel_times", "nbs_get_launch_count", "nbs_get_nlist_stats",
     "nbs_set_shard", "nbs_execute_begin", "nbs_execute_convolve", "nbs_execute_finish", "nbs_get_exchange_buffers",
-    "nbs_debug_set_list_capacity", "nbs_measure_peaks",
+    "nbs_debug_set_list_capacity", "nbs_measure_peaks", "nbs_measure_dp_rates", "nbs_set_list_skin", "nbs_get_list_stats",
 ]
 
 
@@ -197,6 +198,9 @@ def load_library():
     lib.nbs_debug_set_list_capacity.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
     lib.nbs_get_exchange_buffers.argtypes = [C.c_void_p, C.POINTER(ExchangeBuffers)]
     lib.nbs_measure_peaks.argtypes = [C.c_int32, _f64p]
+    lib.nbs_measure_dp_rates.argtypes = [C.c_int32, _f64p]
+    lib.nbs_set_list_skin.argtypes = [C.c_void_p, C.c_double]
+    lib.nbs_get_list_stats.argtypes = [C.c_void_p, _f64p]
     for name in EXPORTS:
         getattr(lib, name)
     if lib.nbs_abi_version() != ABI_VERSION:

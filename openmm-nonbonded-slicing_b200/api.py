@@ -907,6 +907,16 @@ class B200CalcSlicedNonbondedForceKernel(SlicedKernelBase):
         abi.check(self.lib.nbs_get_nlist_stats(self.handle, v))
         return list(v)
 
+    def setListSkin(self, skin):
+        """Neighbour-list padding in nm (0 = rebuild on every evaluation, like the Reference platform)."""
+        abi.check(self.lib.nbs_set_list_skin(self.handle, float(skin)))
+
+    def getListStats(self):
+        v = (C.c_double*8)()
+        abi.check(self.lib.nbs_get_list_stats(self.handle, v))
+        return {"evaluations": int(v[0]), "builds": int(v[1]), "redone": int(v[2]), "max_displacement": v[3],
+                "skin": v[4], "list_valid": bool(v[5]), "reused_last": bool(v[6]), "max_step_growth": v[7]}
+
 
 class Platform:
     """The "B200" platform: creates kernels backed by the CUDA library."""

@@ -38,19 +38,16 @@
 #ifndef PAIR_MIN_CTAS
 #define PAIR_MIN_CTAS 2          // resident CTAs per SM the register allocation is bounded for
 #endif
-#ifndef PAIR_UNROLL
-#define PAIR_UNROLL 2            // steps of the tile loop in flight per warp
-#endif
 
 namespace nbs {
 
-constexpr int kPairUnroll = PAIR_UNROLL;
 
 struct PairArgs {
     int capJ, capX, Npad;
     int blockPeriod, blockOffset, blockWidth;   // this rank's share of the i-blocks
     int chunkTiles;                             // tiles per work item
     long long shiftB, shiftCx, shiftCy;         // triclinic image shifts (CellGeom), fixed-point units; 0 for a rectangular box
+    unsigned guardX, guardY, guardZ;            // re-used lists: how far (fixed-point units) an i atom may have moved below its block's build-time corner
     int nE;                                     // 2 * number of slices
     float sx, sy, sz;
     double dsx, dsy, dsz;
@@ -60,12 +57,14 @@ struct PairArgs {
     double rc2d, alphaD, krfD, crfD;
     float dalpha2, invCut6, shiftMult;   // LJPME: alpha_d^2, rc^-6, rc^-6 (1 - exp(-x)(1 + x + x^2/2)) at x = (alpha_d rc)^2
     const double* q64;                   // sorted charges * sqrt(ONE_4PI_EPS0), double
-    const double* erfcTab;               // piecewise degree-4 fit of erfc(alpha sqrt(s))/sqrt(s) in s = r^2 (ERFC_TAB_ROW doubles per interval)
+    const double* erfcTab;               // piecewise degree-7 fit of erfc(alpha sqrt(s))/sqrt(s) in s = r^2, [coefficient][tabRows]
+    int tabRows;
     int* counters;                       // [2] number of work items, [3] cursor
     const int4* items;                   // (local block, first tile, first atom of the block, atoms in the block)
     const int* blkFirst; const int* blkCount; const uint4* blkLo;
     const uint4* posq; const float4* par;
     const int* jlist; const int* jcount; const int* xlist; const unsigned* xmask; const int* xcount;
+    const unsigned* gmJ; const unsigned* gmX;      // cluster masks of the lists' groups of 8 entries, one word per tile
     unsigned long long* force;
     double* energy;                      // [nSl][2]
     unsigned long long* pairStats;       // mode 1/2: [0] count, [1] hash
@@ -77,15 +76,23 @@ struct PairArgs {
 // per-warp shared memory
 struct __align__(16) WarpScratch {
     float4 iPos[32];      // i-block: position relative to the block corner, charge*sqrt(K)
-    float4 iPar[32];      // sigma/2, 2 sqrt(eps), subset, particle index
+    float4 iPar[32];      // sigma/2, 2 sqrt(eps), subset * MAX_SUBSETS, particle index
     float4 jPos[32];      // current tile
     float4 jPar[32];
-    uint4 iFix[32];       // exact coordinates, w = subset
-    uint4 jFix[32];
-    double iQ[32];        // charges in double (energy path)
-    double jQ[32];
+    // Everything the exact (integer-coordinate) paths gather by slot number -- the double-precision energy passes
+    // and the borderline cutoff test -- is stored one 32-bit word per array: 32 words are 32 banks, so a warp's
+    // gather with arbitrary slot numbers is conflict-free whatever the pattern.
+    unsigned iX[32], iY[32], iZ[32];      // exact fixed-point coordinates
+    unsigned jX[32], jY[32], jZ[32];
+    unsigned iQlo[32], iQhi[32];          // charge * sqrt(K) in double
+    unsigned jQlo[32], jQhi[32];
+    float iSig[32], iEps[32];
+    float jSig[32], jEps[32];
+    // i forces of the work item: cluster c's partial sums of lane l (= 4 jl + il: i atom 4 c + il, as seen by the
+    // lane's j slots) -- one private word per (cluster, lane), so the read-modify-write of a step needs no atomics
+    float fiX[8][32], fiY[8][32], fiZ[8][32];
     unsigned jMask[32];   // exclusion-list tiles: bit l set = pair (i lane l, this j) is masked
-    unsigned short queue[1024 + 32];   // MODE 1/2: a whole tile's pairs; MODE 0: the energy queue (<= 64 used)
+    unsigned short queue[1024 + 32];      // the tile's in-cutoff pairs: subset_i << 13 | subset_j << 10 | i slot << 5 | j slot
 };
 
 __device__ __forceinline__ float rsqrtFast(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -162,12 +169,13 @@ __device__ __forceinline__ double expNegD(double z) {
 //     space, plus the potential shift at the cutoff; fp32 like the rest of the LJ energy.
 // CMODE: 0 = reaction field / no cutoff, 1 = PME or Ewald, 2 = LJPME.
 template <int CMODE>
-__device__ __forceinline__ void pairEnergyD(const uint4 fi, const uint4 fj, double qi, double qj, float sigi, float sigj,
-                                            float epsi, float epsj, const PairArgs& a, double& ec, double& ev) {
+__device__ __forceinline__ void pairEnergyD(unsigned ix, unsigned iy, unsigned iz, unsigned jx, unsigned jy, unsigned jz,
+                                            double qi, double qj, float sigi, float sigj, float epsi, float epsj,
+                                            const PairArgs& a, const double* tab, int tabRows, double& ec, double& ev) {
     constexpr bool IS_PME = CMODE != 0;
-    const double dx = (double) (int) (fj.x - fi.x)*a.dsx;
-    const double dy = (double) (int) (fj.y - fi.y)*a.dsy;
-    const double dz = (double) (int) (fj.z - fi.z)*a.dsz;
+    const double dx = (double) (int) (jx - ix)*a.dsx;
+    const double dy = (double) (int) (jy - iy)*a.dsy;
+    const double dz = (double) (int) (jz - iz)*a.dsz;
     const double r2 = dx*dx + dy*dy + dz*dz;
     const float r2f = (float) r2;
     float yf = rsqrtFast(r2f);
@@ -201,16 +209,15 @@ __device__ __forceinline__ void pairEnergyD(const uint4 fi, const uint4 fj, doub
     if (IS_PME) {
         const unsigned bits = __float_as_uint(r2f);
         const int idx = (int) (bits >> (23 - ERFC_TAB_PER_OCTAVE_LOG2)) - ERFC_TAB_BASE;
-        if (idx >= 0) {
-            const double2* row = reinterpret_cast<const double2*>(a.erfcTab + (size_t) idx*ERFC_TAB_ROW);
-            const double2 c0 = __ldg(row), c1 = __ldg(row + 1), c2 = __ldg(row + 2);
-            // 2 / (interval width) = 2^(1 + 8 - e), e = unbiased exponent of r2f: built straight into the exponent field
+        if (idx >= 0 && idx < tabRows) {
+            // d = s 2^(5-e) - (33 + 2 m): position inside the interval, [-1, 1]; the power of two goes straight into
+            // the exponent field (e = unbiased exponent of r2f), 33 + 2 m = 2 (16 + m) + 1 from the index bits
             const double scale = __hiloint2double((1023 + 1 + ERFC_TAB_PER_OCTAVE_LOG2 + 127 - (int) (bits >> 23)) << 20, 0);
-            const double d = fma(r2, scale, c0.x);                  // position inside the interval, [-1, 1]
-            double p = fma(c0.y, d, c1.x);
-            p = fma(p, d, c1.y);
-            p = fma(p, d, c2.x);
-            p = fma(p, d, c2.y);
+            const int m2 = 2*(int) ((bits >> (23 - ERFC_TAB_PER_OCTAVE_LOG2)) & ((1u << ERFC_TAB_PER_OCTAVE_LOG2) - 1u)) + (2 << ERFC_TAB_PER_OCTAVE_LOG2) + 1;
+            const double d = fma(r2, scale, -(double) m2);
+            double p = tab[idx];
+#pragma unroll
+            for (int k = 1; k <= ERFC_TAB_DEGREE; k++) p = fma(p, d, tab[k*ERFC_TAB_MAX_ROWS + idx]);
             ec = qq*p;
         }
         else {
@@ -233,174 +240,246 @@ __device__ __forceinline__ void pairEnergyD(const uint4 fi, const uint4 fj, doub
 
 // Exact cutoff test from the fixed-point coordinates (the wrapped integer difference is the minimum image
 // for any pair near the cutoff, because the box is at least twice the cutoff).
-__device__ __forceinline__ bool exactInRange(const uint4 fj, const uint4 fi, const PairArgs& a) {
-    const double ex = (double) (int) (fj.x - fi.x)*a.dsx;
-    const double ey = (double) (int) (fj.y - fi.y)*a.dsy;
-    const double ez = (double) (int) (fj.z - fi.z)*a.dsz;
-    return ex*ex + ey*ey + ez*ez <= a.rc2d;
+__device__ __noinline__ bool exactInRange(unsigned ix, unsigned iy, unsigned iz, unsigned jx, unsigned jy, unsigned jz,
+                                          double dsx, double dsy, double dsz, double rc2d) {
+    const double ex = (double) (int) (jx - ix)*dsx;
+    const double ey = (double) (int) (jy - iy)*dsy;
+    const double ez = (double) (int) (jz - iz)*dsz;
+    return ex*ex + ey*ey + ez*ez <= rc2d;
 }
 
-// The one definition of "pair (this lane's i, j slot js) interacts": r^2 <= rc^2 (decided exactly when
-// the fp32 value is within 2e-5 nm^2 of the cutoff) and not masked by an exclusion.
-__device__ __forceinline__ bool pairInRange(const WarpScratch& w, const PairArgs& a, float xi, float yi, float zi,
-                                            const uint4 pi, int js, bool isX, int lane) {
-    const float4 p = w.jPos[js];
-    const float dx = xi - p.x, dy = yi - p.y, dz = zi - p.z;
-    const float r2 = fmaf(dx, dx, fmaf(dy, dy, dz*dz));
-    bool in = r2 <= a.rc2;
-    if (fabsf(r2 - a.rc2) < 2.0e-5f) in = exactInRange(w.jFix[js], pi, a);
-    if (isX) in = in && !((w.jMask[js] >> lane) & 1u);
-    return in;
+// Lattice translation packed into par.z above the subset by k_reprep (all zero unless the atom has left the brick
+// since the neighbour list was built), in 64-bit fixed-point units of each axis.
+struct LatticeShift { long long x, y, z; };
+__device__ __forceinline__ LatticeShift crossShift(int parz, const PairArgs& a) {
+    const int cx = (parz << 25) >> 29, cy = (parz << 23) >> 30, cz = (parz << 21) >> 30;
+    LatticeShift s;
+    s.x = ((long long) cx << 32) + cy*a.shiftB + cz*a.shiftCx;
+    s.y = ((long long) cy << 32) + cz*a.shiftCy;
+    s.z = (long long) cz << 32;
+    return s;
 }
 
-// One 32 x 32 tile of the force kernel: lane l meets j slot (l + k) & 31 at step k; i forces (fix, fiy, fiz)
-// and the rotating j forces (fjx, fjy, fjz) stay in registers.  EMODE 2 also compacts the in-cutoff pairs
-// into w.queue and evaluates their energies in double precision, 32 real pairs per pass.
-template <int EMODE, int CMODE>
-__device__ __forceinline__ void energyPass(const WarpScratch& w, const PairArgs& a, int lane, int count, double* acc) {
-    if (lane < count) {
-        const unsigned e = w.queue[lane];
-        const int il = e >> 5, jq = e & 31;
-        // (sigma/2, 2 sqrt(eps)) only: 8-byte loads; the subsets ride in the .w of the exact coordinates
-        const float2 q1 = *reinterpret_cast<const float2*>(&w.iPar[il]), q2 = *reinterpret_cast<const float2*>(&w.jPar[jq]);
-        const uint4 fi = w.iFix[il], fj = w.jFix[jq];
-        double ecd, evd;
-        pairEnergyD<CMODE>(fi, fj, w.iQ[il], w.jQ[jq], q1.x, q2.x, q1.y, q2.y, a, ecd, evd);
-        const int sl = triSlice((int) fi.w, (int) fj.w);
-        acc[2*sl] += ecd;
-        acc[2*sl+1] += evd;
-    }
-}
+// ---- the tile loop ----------------------------------------------------------------------------------------------
+// A tile is 32 list entries (j atoms staged in shared memory) against the item's 32 i atoms.  It is walked as
+// 4 GROUPS of 8 entries x up to 8 CLUSTERS of 4 i atoms: lane = 4*jl + il meets j slot 8*g + jl and i slot 4*c + il
+// in the step of (group g, cluster c), and the step only exists if the group's cluster mask (from the list
+// builder) has bit c -- a warp-uniform test.  The j forces of a group stay in registers over its cluster steps and
+// are reduced over the four il lanes once per group; the i forces accumulate in lane-private shared-memory words
+// (fiX/Y/Z[c][lane]) -- the cluster index is a run-time value, so ONE copy of the step serves all clusters (eight
+// unrolled copies with register accumulators overflowed the instruction cache: 27 % of the kernel's stall samples
+// were "no instruction", profiles/r02_ncu_k_pair_a_summary.txt).
+struct StepCtx {
+    float rc2, alpha;
+    float jx, jy, jz, jq, jsig, jeps;     // this lane's j atom of the current group
+    int sj;                               // its subset
+    unsigned jm;                          // its exclusion mask (exclusion-list tiles)
+    int js;                               // its slot in the staged tile
+    unsigned qbits;                       // queue entry without the i part: subset_j << 10 | js (the i subset is added per step)
+    float fjx, fjy, fjz;
+    int qn;                               // pairs waiting in the energy / pair-set queue
+};
 
-template <int EMODE, int CMODE, bool IS_X, bool SWITCH>
-__device__ __forceinline__ void tileLoop(WarpScratch& w, const PairArgs& a, const float2* shLam, int lamOff, int lane,
-                                         float xi, float yi, float zi, float qi, float sigi, float epsi, int si, const uint4 pi,
-                                         float& fix, float& fiy, float& fiz, float& fjx, float& fjy, float& fjz, double* acc) {
+template <int EMODE, int CMODE, int MODE>
+__device__ __forceinline__ void pairStep(WarpScratch& w, const PairArgs& a, const float2* shLam, int lane, int il, int c,
+                                         bool isX, StepCtx& s, double* acc) {
     constexpr bool IS_PME = CMODE != 0;
-    const unsigned below = (1u << lane) - 1u;
-    const float rc2 = a.rc2, alpha = a.alpha;
     const float TWO_OVER_SQRT_PI = 1.1283791670955126f;
-    const int src = (lane + 1) & 31;
-    int qn = 0;                                   // pairs waiting in the energy queue
-#pragma unroll kPairUnroll
-    for (int k = 0; k < 32; k++) {
-        const int js = (lane + k) & 31;
-        const float4 p = w.jPos[js];
-        const float4 pr = w.jPar[js];
-        const float dx = xi - p.x, dy = yi - p.y, dz = zi - p.z;
-        const float r2 = fmaf(dx, dx, fmaf(dy, dy, dz*dz));
-        bool in = r2 <= rc2;
-        if (fabsf(r2 - rc2) < 2.0e-5f) in = exactInRange(w.jFix[js], pi, a);     // borderline: rare
-        if (IS_X) in = in && !((w.jMask[js] >> lane) & 1u);
-        if (EMODE == 2) {
-            const unsigned m = __ballot_sync(FULL_MASK, in);
-            if (in) w.queue[qn + __popc(m & below)] = (unsigned short) ((lane << 5) | js);
-            qn += __popc(m);
-            if (qn >= 32) {                       // warp-uniform
-                __syncwarp();
-                energyPass<EMODE, CMODE>(w, a, lane, 32, acc);
-                const int rest = qn - 32;
-                const unsigned short moved = lane < rest ? w.queue[32 + lane] : (unsigned short) 0;
-                __syncwarp();
-                if (lane < rest) w.queue[lane] = moved;
-                qn = rest;
-            }
-        }
-        const float invR = rsqrtFast(r2);
-        const float r = r2*invR;
-        const float invR2 = invR*invR;
-        float s2 = (sigi + pr.x)*invR;
-        s2 *= s2;
-        const float s6 = s2*s2*s2;
-        const float eps = epsi*pr.y;
-        float ev = eps*(s6 - 1.f)*s6;
-        float fv = eps*fmaf(12.f, s6, -6.f)*s6*invR2;
-        const float qr = qi*p.w*invR;
-        float ec, fc;
-        if (IS_PME) {
-            const float ar = alpha*r;
-            const float ex = ex2Fast(-1.4426950408889634f*ar*ar);
-            const float tt = rcpFast(fmaf(0.5f, ar, 1.f));
-            const float erfcv = ex*erfcxPoly(tt);
-            ec = qr*erfcv;
-            fc = qr*invR2*fmaf(TWO_OVER_SQRT_PI*ar, ex, erfcv);
-        }
-        else {
-            ec = qr*fmaf(a.krf*r2, r, 1.f) - qi*p.w*a.crf;
-            fc = qr*invR2*fmaf(-2.f*a.krf*r2, r, 1.f);
-        }
-        if (CMODE == 2) {
-            // LJPME (:398-426): real-space share of the multiplicative C6 term; the shift only enters the energy
-            const float sg = sigi*pr.x;
-            const float c6 = 64.f*sg*sg*sg*eps;
-            const float dar2 = a.dalpha2*r2;
-            const float exd = ex2Fast(-1.4426950408889634f*dar2);
-            const float p2 = fmaf(dar2, fmaf(0.5f, dar2, 1.f), 1.f);             // 1 + x + x^2/2
-            const float c6r6 = c6*invR2*invR2*invR2;
-            fv = fmaf(6.f*c6r6*invR2, 1.f - exd*fmaf(dar2*dar2*dar2, 1.f/6.f, p2), fv);
-            if (EMODE == 1) {
-                float sc = sigi + pr.x;
-                sc *= sc;
-                const float sc6 = sc*sc*sc*a.invCut6;
-                ev += c6r6*(1.f - exd*p2) + eps*(1.f - sc6)*sc6 - c6*a.shiftMult;
-            }
-        }
-        if (SWITCH) {
-            if (r > a.rswitch) {
-                const float wd = 1.f/(a.rcut - a.rswitch);
-                const float u = (r - a.rswitch)*wd;
-                const float sv = 1.f + u*u*u*(-10.f + u*(15.f - u*6.f));
-                const float sd = u*u*(-30.f + u*(60.f - u*30.f))*wd;
-                fv = sv*fv - ev*sd*invR;
-                ev *= sv;
-            }
-        }
-        const int sj = __float_as_int(pr.z);
-        const float2 lam = shLam[lamOff + sj];
-        float dEdR = fmaf(lam.y, fv, lam.x*fc);
-        dEdR = in ? dEdR : 0.f;
-        fix = fmaf(dEdR, dx, fix); fiy = fmaf(dEdR, dy, fiy); fiz = fmaf(dEdR, dz, fiz);
-        fjx = fmaf(-dEdR, dx, fjx); fjy = fmaf(-dEdR, dy, fjy); fjz = fmaf(-dEdR, dz, fjz);
-        if (EMODE == 1 && in) {
-            const int sl = triSlice(si, sj);
-            acc[2*sl] += (double) ec;
-            acc[2*sl+1] += (double) ev;
-        }
-        fjx = __shfl_sync(FULL_MASK, fjx, src);
-        fjy = __shfl_sync(FULL_MASK, fjy, src);
-        fjz = __shfl_sync(FULL_MASK, fjz, src);
+    const int is = c*4 + il;
+    const float4 ip = w.iPos[is];
+    const float4 ipar = w.iPar[is];               // sigma/2, 2 sqrt(eps), subset * MAX_SUBSETS (int bits), particle index
+    const float dx = ip.x - s.jx, dy = ip.y - s.jy, dz = ip.z - s.jz;
+    const float r2 = fmaf(dx, dx, fmaf(dy, dy, dz*dz));
+    bool in = r2 <= s.rc2;
+    if (fabsf(r2 - s.rc2) < 2.0e-5f) in = exactInRange(w.iX[is], w.iY[is], w.iZ[is], w.jX[s.js], w.jY[s.js], w.jZ[s.js], a.dsx, a.dsy, a.dsz, a.rc2d);     // borderline: rare
+    if (isX) in = in && !((s.jm >> is) & 1u);
+    if (EMODE == 2 || MODE != 0) {
+        const unsigned m = __ballot_sync(FULL_MASK, in);
+        if (in) w.queue[s.qn + __popc(m & ((1u << lane) - 1u))] = (unsigned short) (s.qbits | (is << 5) | ((unsigned) __float_as_int(ipar.z) << 10));
+        s.qn += __popc(m);
     }
-    if (EMODE == 2) {                             // the queue refers to this tile's shared-memory slots
-        __syncwarp();
-        energyPass<EMODE, CMODE>(w, a, lane, qn, acc);
+    if (MODE != 0) return;
+    const float invR = rsqrtFast(r2);
+    const float r = r2*invR;
+    const float invR2 = invR*invR;
+    float s2 = (ipar.x + s.jsig)*invR;
+    s2 *= s2;
+    const float s6 = s2*s2*s2;
+    const float eps = ipar.y*s.jeps;
+    float ev = eps*(s6 - 1.f)*s6;
+    float fv = eps*fmaf(12.f, s6, -6.f)*s6*invR2;
+    const float qr = ip.w*s.jq*invR;
+    float ec, fc;
+    if (IS_PME) {
+        const float ar = s.alpha*r;
+        const float ex = ex2Fast(-1.4426950408889634f*ar*ar);
+        const float tt = rcpFast(fmaf(0.5f, ar, 1.f));
+        const float erfcv = ex*erfcxPoly(tt);
+        ec = qr*erfcv;
+        fc = qr*invR2*fmaf(TWO_OVER_SQRT_PI*ar, ex, erfcv);
     }
+    else {
+        ec = qr*fmaf(a.krf*r2, r, 1.f) - ip.w*s.jq*a.crf;
+        fc = qr*invR2*fmaf(-2.f*a.krf*r2, r, 1.f);
+    }
+    if (CMODE == 2) {
+        // LJPME (:398-426): real-space share of the multiplicative C6 term; the shift only enters the energy
+        const float sg = ipar.x*s.jsig;
+        const float c6 = 64.f*sg*sg*sg*eps;
+        const float dar2 = a.dalpha2*r2;
+        const float exd = ex2Fast(-1.4426950408889634f*dar2);
+        const float p2 = fmaf(dar2, fmaf(0.5f, dar2, 1.f), 1.f);             // 1 + x + x^2/2
+        const float c6r6 = c6*invR2*invR2*invR2;
+        fv = fmaf(6.f*c6r6*invR2, 1.f - exd*fmaf(dar2*dar2*dar2, 1.f/6.f, p2), fv);
+        if (EMODE == 1) {
+            float sc = ipar.x + s.jsig;
+            sc *= sc;
+            const float sc6 = sc*sc*sc*a.invCut6;
+            ev += c6r6*(1.f - exd*p2) + eps*(1.f - sc6)*sc6 - c6*a.shiftMult;
+        }
+    }
+    if (a.useSwitch) {                                            // warp-uniform
+        if (r > a.rswitch) {
+            const float wd = 1.f/(a.rcut - a.rswitch);
+            const float u = (r - a.rswitch)*wd;
+            const float sv = 1.f + u*u*u*(-10.f + u*(15.f - u*6.f));
+            const float sd = u*u*(-30.f + u*(60.f - u*30.f))*wd;
+            fv = sv*fv - ev*sd*invR;
+            ev *= sv;
+        }
+    }
+    const int siOff = __float_as_int(ipar.z);
+    const float2 lam = shLam[siOff + s.sj];
+    float dEdR = fmaf(lam.y, fv, lam.x*fc);
+    dEdR = in ? dEdR : 0.f;
+    w.fiX[c][lane] = fmaf(dEdR, dx, w.fiX[c][lane]);
+    w.fiY[c][lane] = fmaf(dEdR, dy, w.fiY[c][lane]);
+    w.fiZ[c][lane] = fmaf(dEdR, dz, w.fiZ[c][lane]);
+    s.fjx = fmaf(-dEdR, dx, s.fjx); s.fjy = fmaf(-dEdR, dy, s.fjy); s.fjz = fmaf(-dEdR, dz, s.fjz);
+    if (EMODE == 1 && in) {
+        const int sl = triSlice(siOff/MAX_SUBSETS, s.sj);
+        acc[2*sl] += (double) ec;
+        acc[2*sl+1] += (double) ev;
+    }
+}
+
+// Double-precision energies of the queued (in-cutoff) pairs of the current tile, 32 real pairs per pass, two passes
+// in flight (their loads and dependent FMA chains interleave).  Operands are gathered word by word from the
+// conflict-free per-slot arrays; the erfc table is the CTA's shared-memory copy.  The common case -- every pair of a
+// pass in the same slice -- accumulates in two registers; the per-lane table in local memory is only touched when
+// the slice changes.
+template <int CMODE>
+__device__ __forceinline__ void energyPasses(const WarpScratch& w, const PairArgs& a, const double* tab, int lane, int count,
+                                             double* acc, int& curSl, double& regC, double& regV) {
+    for (int base = 0; base < count; base += 64) {
+        double ecd[2] = {0.0, 0.0}, evd[2] = {0.0, 0.0};
+        int sl[2] = {-1, -1};
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int k = base + 32*u + lane;
+            if (k < count) {
+                const unsigned e = w.queue[k];
+                const int iq = (e >> 5) & 31, jq = e & 31;
+                const double qi = __hiloint2double((int) w.iQhi[iq], (int) w.iQlo[iq]);
+                const double qj = __hiloint2double((int) w.jQhi[jq], (int) w.jQlo[jq]);
+                pairEnergyD<CMODE>(w.iX[iq], w.iY[iq], w.iZ[iq], w.jX[jq], w.jY[jq], w.jZ[jq], qi, qj,
+                                   w.iSig[iq], w.jSig[jq], w.iEps[iq], w.jEps[jq], a, tab, a.tabRows, ecd[u], evd[u]);
+                sl[u] = triSlice((int) (e >> 13), (int) ((e >> 10) & 7u));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int lead = __shfl_sync(FULL_MASK, sl[u], 0);      // lane 0 is active whenever the pass has any pair
+            const bool uniform = __all_sync(FULL_MASK, sl[u] == lead || sl[u] < 0);
+            if (uniform) {
+                if (lead < 0) continue;
+                if (lead != curSl) {
+                    if (curSl >= 0) { acc[2*curSl] += regC; acc[2*curSl+1] += regV; }
+                    regC = 0.0; regV = 0.0; curSl = lead;
+                }
+                regC += ecd[u]; regV += evd[u];
+            }
+            else if (sl[u] >= 0) { acc[2*sl[u]] += ecd[u]; acc[2*sl[u]+1] += evd[u]; }
+        }
+    }
+}
+
+template <int EMODE, int CMODE, int MODE>
+__device__ __forceinline__ void tileLoop(WarpScratch& w, const PairArgs& a, const float2* shLam, int lane, unsigned gmWord, bool isX,
+                                         int jIndexMine, bool jValidMine, double* acc, int& qnOut) {
+    const int il = lane & 3, jl = lane >> 2;
+    StepCtx s;
+    s.rc2 = a.rc2; s.alpha = a.alpha;
+    s.qn = 0;
+#pragma unroll 1
+    for (int g = 0; g < 4; g++) {
+        const unsigned m = (gmWord >> (8*g)) & 0xffu;
+        if (m == 0u) continue;                         // warp-uniform
+        s.js = 8*g + jl;
+        {
+            const float4 p = w.jPos[s.js];
+            const float4 pr = w.jPar[s.js];
+            s.jx = p.x; s.jy = p.y; s.jz = p.z; s.jq = p.w;
+            s.jsig = pr.x; s.jeps = pr.y; s.sj = __float_as_int(pr.z);
+            s.jm = isX ? w.jMask[s.js] : 0u;
+            s.qbits = ((unsigned) s.sj << 10) | (unsigned) s.js;
+        }
+        s.fjx = 0.f; s.fjy = 0.f; s.fjz = 0.f;
+#pragma unroll 1
+        for (unsigned mm = m; mm != 0u; mm &= mm - 1u)
+            pairStep<EMODE, CMODE, MODE>(w, a, shLam, lane, il, __ffs((int) mm) - 1, isX, s, acc);
+        if (MODE == 0) {
+            // j forces of the group: sum over the four il lanes (x and y share the first exchange: odd lanes end
+            // up owning y, even lanes x), then lanes il = 0, 1, 2 add x, y, z to the 64-bit fixed-point accumulators
+            const bool odd = il & 1;
+            float keep = odd ? s.fjy : s.fjx;
+            const float send = odd ? s.fjx : s.fjy;
+            keep += __shfl_xor_sync(FULL_MASK, send, 1);
+            s.fjz += __shfl_xor_sync(FULL_MASK, s.fjz, 1);
+            keep += __shfl_xor_sync(FULL_MASK, keep, 2);
+            s.fjz += __shfl_xor_sync(FULL_MASK, s.fjz, 2);
+            const int jIndex = __shfl_sync(FULL_MASK, jIndexMine, s.js);
+            const bool jValid = __shfl_sync(FULL_MASK, (int) jValidMine, s.js) != 0;
+            const float v = il == 2 ? s.fjz : keep;
+            if (il < 3 && jValid && v != 0.f) atomicAdd(a.force + (size_t) il*a.Npad + jIndex, toFixed(v));
+        }
+    }
+    qnOut = s.qn;
 }
 
 // MODE 0: forces (+ energies per EMODE); MODE 1: count + hash the interacting pairs; MODE 2: also dump them.
 // EMODE 0: forces only; 1: single-precision energies; 2: double-precision energies.
-// MINCTAS: resident CTAs per SM the register allocation is bounded for (2: 128 registers; 3: 80 registers and a
-// few bytes of spill -- no different at DHFR size, 8 % faster at STMV size, where there is always a next item)
+// MINCTAS: resident CTAs per SM the register allocation is bounded for.
 template <int EMODE, int CMODE, int MODE, int MINCTAS>
 __global__ void __launch_bounds__(PAIR_WARPS*32, MINCTAS) k_pair(const PairArgs a) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     __shared__ float2 shLam[MAX_SUBSETS*MAX_SUBSETS];      // (lambda_Coulomb, lambda_vdW) of subset pair (si, sj)
     __shared__ double shE[MAX_SLICES*2];
+    __shared__ int shArrived;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpScratch& w = reinterpret_cast<WarpScratch*>(smemRaw)[warp];
+    // EMODE 2: the CTA's copy of the erfc table, behind the warps' scratch areas ([coefficient][ERFC_TAB_MAX_ROWS])
+    double* const shTab = reinterpret_cast<double*>(smemRaw + sizeof(WarpScratch)*PAIR_WARPS);
+    if (EMODE == 2 && MODE == 0 && CMODE != 0) {
+        for (int k = threadIdx.x; k < (ERFC_TAB_DEGREE + 1)*a.tabRows; k += blockDim.x)
+            shTab[(k / a.tabRows)*ERFC_TAB_MAX_ROWS + k % a.tabRows] = a.erfcTab[k];
+    }
     if (threadIdx.x < MAX_SUBSETS*MAX_SUBSETS) {
         const int sl = triSlice(threadIdx.x / MAX_SUBSETS, threadIdx.x % MAX_SUBSETS);
         shLam[threadIdx.x] = make_float2(a.lam.c[sl], a.lam.v[sl]);
     }
     if (threadIdx.x < MAX_SLICES*2) shE[threadIdx.x] = 0.0;
+    if (threadIdx.x == 0) shArrived = 0;
     __syncthreads();
 
-    const unsigned below = (1u << lane) - 1u;
     const int nItems = a.counters[2];
     double acc[MAX_SLICES*2];                     // [slice][term], dynamically indexed (local memory, L1-resident)
     if (EMODE != 0) {
 #pragma unroll
         for (int k = 0; k < MAX_SLICES*2; k++) acc[k] = 0.0;
     }
+    int curSl = -1;                               // EMODE 2: slice whose energies currently accumulate in registers
+    double regC = 0.0, regV = 0.0;
     unsigned long long nPairs = 0, hPairs = 0;
 
     // Everything a warp needs from global memory is requested one step ahead of its use -- the next work
@@ -420,24 +499,32 @@ __global__ void __launch_bounds__(PAIR_WARPS*32, MINCTAS) k_pair(const PairArgs 
         const int* jl = a.jlist + (size_t) lb*a.capJ;
         const int* xl = a.xlist + (size_t) lb*a.capX;
         const unsigned* xm = a.xmask + (size_t) lb*a.capX;
+        const unsigned* gj = a.gmJ + (size_t) lb*(a.capJ >> 5);
+        const unsigned* gx = a.gmX + (size_t) lb*(a.capX >> 5);
         const int nJ = a.jcount[lb], nX = a.xcount[lb];
         const uint4 lo = a.blkLo[b];
         const bool iValid = lane < cnt;
-        const uint4 pi = iValid ? a.posq[first + lane] : lo;
+        uint4 pi = iValid ? a.posq[first + lane] : lo;
         const float4 pari = iValid ? a.par[first + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+        {
+            // an atom that left the brick since the list was built: back next to its build-time position (k_reprep)
+            const LatticeShift ls = crossShift(__float_as_int(pari.z), a);
+            pi.x += (unsigned) ls.x; pi.y += (unsigned) ls.y;
+        }
         const double qi64 = (EMODE == 2 && iValid) ? a.q64[first + lane] : 0.0;
         const int tJ = (nJ + 31) >> 5, tX = (nX + 31) >> 5;
         const int tEnd = min(it.y + a.chunkTiles, tJ + tX);
         // list entry (and exclusion mask) of this lane in tile t; -1 beyond the item
-        auto loadEntry = [&](int t, unsigned& mask) -> int {
-            mask = 0u;
+        auto loadEntry = [&](int t, unsigned& mask, unsigned& gm) -> int {
+            mask = 0u; gm = 0u;
             if (t >= tEnd) return -1;
-            if (t >= tJ) { mask = xm[(t - tJ)*32 + lane]; return xl[(t - tJ)*32 + lane]; }
+            if (t >= tJ) { mask = xm[(t - tJ)*32 + lane]; gm = gx[t - tJ]; return xl[(t - tJ)*32 + lane]; }
+            gm = gj[t];
             return jl[t*32 + lane];
         };
-        unsigned maskCur, maskNext;
-        int entryCur = loadEntry(it.y, maskCur);
-        int entryNext = loadEntry(it.y + 1, maskNext);
+        unsigned maskCur, maskNext, gmCur, gmNext;
+        int entryCur = loadEntry(it.y, maskCur, gmCur);
+        int entryNext = loadEntry(it.y + 1, maskNext, gmNext);
         uint4 qCur = make_uint4(0u, 0u, 0u, 0u);
         float4 parCur = make_float4(0.f, 0.f, 0.f, 0.f);
         double q64Cur = 0.0;
@@ -446,116 +533,120 @@ __global__ void __launch_bounds__(PAIR_WARPS*32, MINCTAS) k_pair(const PairArgs 
             qCur = a.posq[j]; parCur = a.par[j];
             if (EMODE == 2) q64Cur = a.q64[j];
         }
-        float xi = (float) (pi.x - lo.x)*a.sx;
-        const float yi = (float) (pi.y - lo.y)*a.sy, zi = (float) (pi.z - lo.z)*a.sz;
+        // (window arithmetic: the atom sits in [corner - guard, corner + box - guard) whichever side of the brick's
+        // faces it and the corner are on; guard = 0 unless the list is being re-used)
+        float xi = (float) ((long long) (pi.x - lo.x + a.guardX) - (long long) a.guardX)*a.sx;
+        const float yi = (float) ((long long) (pi.y - lo.y + a.guardY) - (long long) a.guardY)*a.sy;
+        const float zi = (float) ((long long) (pi.z - lo.z + a.guardZ) - (long long) a.guardZ)*a.sz;
         if (!iValid) xi = 1.0e8f;
         const float qi = iValid ? __uint_as_float(pi.w) : 0.f;
-        const float sigi = pari.x, epsi = pari.y;
-        const int si = __float_as_int(pari.z);
-        const int lamOff = si*MAX_SUBSETS;
-        float fix = 0.f, fiy = 0.f, fiz = 0.f;
+        const int si = __float_as_int(pari.z) & 7;
         __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 8; c++) { w.fiX[c][lane] = 0.f; w.fiY[c][lane] = 0.f; w.fiZ[c][lane] = 0.f; }
         w.iPos[lane] = make_float4(xi, yi, zi, qi);
-        w.iPar[lane] = pari;
-        w.iFix[lane] = make_uint4(pi.x, pi.y, pi.z, (unsigned) __float_as_int(pari.z));
-        if (EMODE == 2) w.iQ[lane] = qi64;
+        w.iPar[lane] = make_float4(pari.x, pari.y, __int_as_float(si*MAX_SUBSETS), pari.w);
+        w.iX[lane] = pi.x; w.iY[lane] = pi.y; w.iZ[lane] = pi.z;
+        if (EMODE == 2) {
+            w.iQlo[lane] = (unsigned) __double2loint(qi64); w.iQhi[lane] = (unsigned) __double2hiint(qi64);
+            w.iSig[lane] = pari.x; w.iEps[lane] = pari.y;
+        }
 
         for (int t = it.y; t < tEnd; t++) {
             const bool isX = t >= tJ;
             const int entry = entryCur;
+            const unsigned gmWord = gmCur;
             float4 pj = make_float4(-1.0e8f, 0.f, 0.f, 0.f);
             const float4 parj = parCur;
-            uint4 fixj = make_uint4(0u, 0u, 0u, 0u);
+            unsigned fjx_ = 0u, fjy_ = 0u, fjz_ = 0u;
             int jIndex = 0;
             if (entry >= 0) {
                 jIndex = entry & J_INDEX_MASK;
                 const int code = entry >> J_SHIFT_BITS;
-                const int kx = code % 5 - 2, ky = (code/5) % 3 - 1, kz = code/15 - 1;
+                const LatticeShift ls = crossShift(__float_as_int(parj.z), a);
+                const int kz = code/15 - 1;
                 const uint4 q = qCur;
                 // image (kx, ky, kz) is displaced by kx a + ky b + kz c (b and c tilt into x, c into y; zero for a
                 // rectangular box), in fixed-point units of each axis
-                const long long shx = ((long long) kx << 32) + ky*a.shiftB + kz*a.shiftCx;
-                const long long shy = ((long long) ky << 32) + kz*a.shiftCy;
+                // (+ the lattice translation of an atom that left the brick since the list was built)
+                const long long shx = ((long long) (code % 5 - 2) << 32) + ((code/5) % 3 - 1)*a.shiftB + kz*a.shiftCx + ls.x;
+                const long long shy = ((long long) ((code/5) % 3 - 1) << 32) + kz*a.shiftCy + ls.y;
                 pj.x = (float) ((long long) q.x + shx - (long long) lo.x)*a.sx;
                 pj.y = (float) ((long long) q.y + shy - (long long) lo.y)*a.sy;
-                pj.z = (float) ((long long) q.z + ((long long) kz << 32) - (long long) lo.z)*a.sz;
+                pj.z = (float) ((long long) q.z + ((long long) kz << 32) + ls.z - (long long) lo.z)*a.sz;
                 pj.w = __uint_as_float(q.w);
                 // exact coordinates of THIS image modulo the box: the wrapped 32-bit difference to an i atom is then
                 // the displacement to this image for any pair inside the cutoff (<= half the box along every axis)
-                fixj = make_uint4(q.x + (unsigned) shx, q.y + (unsigned) shy, q.z, (unsigned) __float_as_int(parj.z));
+                fjx_ = q.x + (unsigned) shx; fjy_ = q.y + (unsigned) shy; fjz_ = q.z;
             }
             __syncwarp();
             w.jPos[lane] = pj;
-            w.jPar[lane] = parj;
-            w.jFix[lane] = fixj;
-            if (EMODE == 2) w.jQ[lane] = q64Cur;
+            w.jPar[lane] = make_float4(parj.x, parj.y, __int_as_float(__float_as_int(parj.z) & 7), parj.w);
+            w.jX[lane] = fjx_; w.jY[lane] = fjy_; w.jZ[lane] = fjz_;
+            if (EMODE == 2) {
+                w.jQlo[lane] = (unsigned) __double2loint(q64Cur); w.jQhi[lane] = (unsigned) __double2hiint(q64Cur);
+                w.jSig[lane] = parj.x; w.jEps[lane] = parj.y;
+            }
             if (isX) w.jMask[lane] = maskCur;
             __syncwarp();
             // requests for the next tile (atoms) and the one after (list entry) go out before this tile's arithmetic
-            entryCur = entryNext; maskCur = maskNext;
+            entryCur = entryNext; maskCur = maskNext; gmCur = gmNext;
             qCur = make_uint4(0u, 0u, 0u, 0u); parCur = make_float4(0.f, 0.f, 0.f, 0.f); q64Cur = 0.0;
             if (entryCur >= 0) {
                 const int j = entryCur & J_INDEX_MASK;
                 qCur = a.posq[j]; parCur = a.par[j];
                 if (EMODE == 2) q64Cur = a.q64[j];
             }
-            entryNext = loadEntry(t + 2, maskNext);
+            entryNext = loadEntry(t + 2, maskNext, gmNext);
 
+            int qn = 0;
+            tileLoop<EMODE, CMODE, MODE>(w, a, shLam, lane, gmWord, isX, jIndex, entry >= 0, acc, qn);
             if (MODE != 0) {
-                // ---- the interacting-pair set itself (parity diagnostics): cull, then hash / dump ----
-                int qn = 0;
-#pragma unroll 4
-                for (int k = 0; k < 32; k++) {
-                    const int js = (lane + k) & 31;
-                    const bool in = pairInRange(w, a, xi, yi, zi, pi, js, isX, lane);
-                    const unsigned m = __ballot_sync(FULL_MASK, in);
-                    if (in) w.queue[qn + __popc(m & below)] = (unsigned short) ((lane << 5) | js);
-                    qn += __popc(m);
-                }
+                // ---- the interacting-pair set itself (parity diagnostics): hash / dump what the loop queued ----
                 __syncwarp();
                 for (int base = 0; base < qn; base += 32) {
                     if (base + lane < qn) {
                         const unsigned e = w.queue[base + lane];
-                        const unsigned oi = (unsigned) __float_as_int(w.iPar[e >> 5].w), oj = (unsigned) __float_as_int(w.jPar[e & 31].w);
-                        const unsigned f = min(oi, oj), s = max(oi, oj);
+                        const unsigned oi = (unsigned) __float_as_int(w.iPar[(e >> 5) & 31].w), oj = (unsigned) __float_as_int(w.jPar[e & 31].w);
+                        const unsigned f = min(oi, oj), sd = max(oi, oj);
                         nPairs++;
-                        hPairs += pairHash(f, s);
+                        hPairs += pairHash(f, sd);
                         if (MODE == 2) {
                             unsigned long long slot = atomicAdd(a.pairStats + 2, 1ull);
-                            if ((long long) slot < a.dumpCapacity) a.pairDump[slot] = make_int2((int) f, (int) s);
+                            if ((long long) slot < a.dumpCapacity) a.pairDump[slot] = make_int2((int) f, (int) sd);
                         }
                     }
                 }
-                continue;
             }
-
-            // ---- forces: dense 32 x 32 tile, lane l meets j slot (l + k) & 31 at step k ----
-            float fjx = 0.f, fjy = 0.f, fjz = 0.f;
-            // four copies of the loop so that the exclusion-mask test and the switching function cost nothing
-            // in the tiles that do not have them (both conditions are warp-uniform)
-            if (isX) {
-                if (a.useSwitch) tileLoop<EMODE, CMODE, true, true>(w, a, shLam, lamOff, lane, xi, yi, zi, qi, sigi, epsi, si, pi, fix, fiy, fiz, fjx, fjy, fjz, acc);
-                else tileLoop<EMODE, CMODE, true, false>(w, a, shLam, lamOff, lane, xi, yi, zi, qi, sigi, epsi, si, pi, fix, fiy, fiz, fjx, fjy, fjz, acc);
-            }
-            else {
-                if (a.useSwitch) tileLoop<EMODE, CMODE, false, true>(w, a, shLam, lamOff, lane, xi, yi, zi, qi, sigi, epsi, si, pi, fix, fiy, fiz, fjx, fjy, fjz, acc);
-                else tileLoop<EMODE, CMODE, false, false>(w, a, shLam, lamOff, lane, xi, yi, zi, qi, sigi, epsi, si, pi, fix, fiy, fiz, fjx, fjy, fjz, acc);
-            }
-            // j forces of this tile (lane l ends up with slot l) -> global fixed point
-            if (entry >= 0 && (fjx != 0.f || fjy != 0.f || fjz != 0.f)) {
-                atomicAdd(a.force + jIndex, toFixed(fjx));
-                atomicAdd(a.force + a.Npad + jIndex, toFixed(fjy));
-                atomicAdd(a.force + 2*(size_t) a.Npad + jIndex, toFixed(fjz));
+            else if (EMODE == 2) {                 // the queue refers to this tile's shared-memory slots
+                __syncwarp();
+                energyPasses<CMODE>(w, a, shTab, lane, qn, acc, curSl, regC, regV);
             }
         }
-        // i forces of this item -> global fixed point
+        // i forces of this item: fi[c] summed over the eight jl lanes.  Three exchange stages, each halving the
+        // number of clusters a lane still carries, leave lane 4 c + il with the total of cluster c, atom il --
+        // i.e. lane l with the force on the block's atom l.
         if (MODE == 0) {
             __syncwarp();
-            if (iValid) {
-                atomicAdd(a.force + first + lane, toFixed(fix));
-                atomicAdd(a.force + a.Npad + first + lane, toFixed(fiy));
-                atomicAdd(a.force + 2*(size_t) a.Npad + first + lane, toFixed(fiz));
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+                float v[8];
+#pragma unroll
+                for (int c = 0; c < 8; c++) v[c] = d == 0 ? w.fiX[c][lane] : (d == 1 ? w.fiY[c][lane] : w.fiZ[c][lane]);
+#pragma unroll
+                for (int st = 2; st >= 0; st--) {
+                    const int half = 1 << st;
+                    const bool upper = (lane >> (st + 2)) & 1;
+#pragma unroll
+                    for (int k = 0; k < half; k++) {
+                        const float send = upper ? v[k] : v[k + half];
+                        const float keep = upper ? v[k + half] : v[k];
+                        v[k] = keep + __shfl_xor_sync(FULL_MASK, send, 4 << st);
+                    }
+                }
+                if (iValid && v[0] != 0.f) atomicAdd(a.force + (size_t) d*a.Npad + first + lane, toFixed(v[0]));
             }
+            __syncwarp();
         }
     }
 
@@ -570,19 +661,31 @@ __global__ void __launch_bounds__(PAIR_WARPS*32, MINCTAS) k_pair(const PairArgs 
         return;
     }
     if (EMODE != 0) {
+        if (EMODE == 2 && curSl >= 0) { acc[2*curSl] += regC; acc[2*curSl+1] += regV; }
+        // CTA-level sum without a barrier (a warp that has run out of work items retires; the last one to arrive
+        // adds the CTA's totals to the global table)
         for (int k = 0; k < a.nE; k++) {
             const double v = warpSum(acc[k]);
             if (lane == 0 && v != 0.0) atomicAdd(&shE[k], v);
         }
-        __syncthreads();
-        if (threadIdx.x < MAX_SLICES*2 && shE[threadIdx.x] != 0.0) atomicAdd(a.energy + threadIdx.x, shE[threadIdx.x]);
+        __threadfence_block();
+        int arrived = 0;
+        if (lane == 0) arrived = atomicAdd(&shArrived, 1);
+        arrived = __shfl_sync(FULL_MASK, arrived, 0);
+        if (arrived == PAIR_WARPS - 1) {
+            __threadfence_block();
+            for (int k = lane; k < a.nE; k += 32) {
+                const double v = *((volatile double*) &shE[k]);
+                if (v != 0.0) atomicAdd(a.energy + k, v);
+            }
+        }
     }
 }
 
 template <int EMODE, int CMODE, int MODE, int MINCTAS>
 static int launchPairK(Context& c, const PairArgs& a) {
     static bool attr[64] = {false};
-    const size_t smem = sizeof(WarpScratch)*PAIR_WARPS;
+    const size_t smem = sizeof(WarpScratch)*PAIR_WARPS + (EMODE == 2 && MODE == 0 && CMODE != 0 ? sizeof(double)*(ERFC_TAB_DEGREE + 1)*ERFC_TAB_MAX_ROWS : 0);
     if (!attr[c.device & 63]) {
         NBS_CUDA_CHECK(cudaFuncSetAttribute(k_pair<EMODE, CMODE, MODE, MINCTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         attr[c.device & 63] = true;
@@ -601,7 +704,8 @@ static int launchPairK(Context& c, const PairArgs& a) {
 template <int EMODE, int CMODE, int MODE>
 static int launchPairT(Context& c, const PairArgs& a) {
     if constexpr (MODE == 0 && CMODE != 2) {
-        if (c.N >= 300000) return launchPairK<EMODE, CMODE, MODE, 3>(c, a);
+        static const int forced = getenv("NBS_PAIR_MINCTAS") ? atoi(getenv("NBS_PAIR_MINCTAS")) : 0;     // tuning experiments
+        if (forced == 3 || (forced == 0 && c.N >= 300000)) return launchPairK<EMODE, CMODE, MODE, 3>(c, a);
     }
     return launchPairK<EMODE, CMODE, MODE, PAIR_MIN_CTAS>(c, a);
 }
@@ -619,6 +723,11 @@ int launchPairs(Context& c, bool wantEnergy, int mode) {
     a.blockPeriod = c.blockPeriod; a.blockOffset = c.blockOffset; a.blockWidth = c.blockWidth;
     a.chunkTiles = c.chunkTiles;
     a.shiftB = g.shiftB; a.shiftCx = g.shiftCx; a.shiftCy = g.shiftCy;
+    {
+        const double room = c.skin > 0 ? 0.5*c.skin + 1.0e-3 : 0.0;      // nm an atom may have moved since the build
+        a.guardX = (unsigned) (room/g.box[0]*4294967296.0); a.guardY = (unsigned) (room/g.box[1]*4294967296.0);
+        a.guardZ = (unsigned) (room/g.box[2]*4294967296.0);
+    }
     a.nE = 2*c.nSl;
     a.sx = g.scale[0]; a.sy = g.scale[1]; a.sz = g.scale[2];
     a.dsx = g.box[0]/4294967296.0; a.dsy = g.box[1]/4294967296.0; a.dsz = g.box[2]/4294967296.0;
@@ -632,6 +741,7 @@ int launchPairs(Context& c, bool wantEnergy, int mode) {
     a.crfD = noCutoff ? 0.0 : (1.0/c.cutoff)*(3.0*c.rfDielectric)/(2.0*c.rfDielectric + 1.0);
     a.q64 = c.dQ64.d;
     a.erfcTab = c.dErfcTab.d;
+    a.tabRows = c.erfcRows;
     a.alpha = (float) c.alpha;
     a.krf = (float) a.krfD;
     a.crf = (float) a.crfD;
@@ -649,6 +759,7 @@ int launchPairs(Context& c, bool wantEnergy, int mode) {
     a.blkFirst = c.dBlkFirst.d; a.blkCount = c.dBlkCount.d; a.blkLo = c.dBlkLo.d;
     a.posq = c.dPosq.d; a.par = c.dPar.d;
     a.jlist = c.dJList.d; a.jcount = c.dJCount.d; a.xlist = c.dXList.d; a.xmask = c.dXMask.d; a.xcount = c.dXCount.d;
+    a.gmJ = c.dGmJ.d; a.gmX = c.dGmX.d;
     a.force = c.dForce.d;
     a.energy = c.dEnergy.d;
     a.pairStats = c.dPairStats.d;

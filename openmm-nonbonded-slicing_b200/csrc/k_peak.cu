@@ -47,9 +47,84 @@ __global__ void __launch_bounds__(256) k_peak_mufu(int rounds, float seed, float
     if (total == 12345.678f) sink[0] = total;
 }
 
+// double-precision and conversion rates (the energy passes of the pair kernel): WHICH = 0 DFMA, 1 int32 -> double,
+// 2 float -> double, 3 double -> float, 4 int64 -> double
+template <int WHICH>
+__global__ void __launch_bounds__(256) k_peak_dp(int rounds, double seed, double* sink) {
+    double acc[8];
+    int iv[8];
+    float fv[8];
+    long long lv[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { acc[k] = seed + threadIdx.x + k; iv[k] = threadIdx.x*7 + k; fv[k] = (float) (seed + k); lv[k] = (long long) threadIdx.x*77777 + k; }
+    const double a = 1.0 + 1e-9*seed, b = 1e-3*seed;
+    for (int r = 0; r < rounds; r++) {
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                if (WHICH == 0) acc[k] = fma(acc[k], a, b);
+                else if (WHICH == 1) { double d = (double) iv[k]; iv[k] = __double2hiint(d) ^ (iv[k] + u); }
+                else if (WHICH == 2) { double d = (double) fv[k]; fv[k] = __int_as_float((__double2hiint(d) & 0x007fffff) | 0x3f800000); }
+                else if (WHICH == 3) { float f = (float) acc[k]; acc[k] = __hiloint2double(__float_as_int(f), u); }
+                else { double d = (double) lv[k]; lv[k] = (long long) __double2hiint(d)*3 + lv[k]; }
+            }
+        }
+    }
+    double total = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) total += acc[k] + iv[k] + fv[k] + (double) lv[k];
+    if (total == 12345.678) sink[0] = total;
+}
+
 } // namespace nbs
 
 using namespace nbs;
+
+// out[0..4]: warp-instructions per clock per SM of DFMA, I2F.F64.S32, F2F.F64.F32, F2F.F32.F64, I2F.F64.S64 (an upper
+// bound for the conversions, whose loops carry a couple of integer instructions per conversion)
+extern "C" int nbs_measure_dp_rates(int32_t device, double out[8]) {
+    if (!out) { setError("null argument"); return NBS_ERR_INVALID; }
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+        cudaGetLastError();
+        setError("no CUDA device available (this library has no CPU fallback)");
+        return NBS_ERR_CUDA;
+    }
+    NBS_CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    NBS_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    double* sink = nullptr;
+    NBS_CUDA_CHECK(cudaMalloc((void**) &sink, sizeof(double)));
+    cudaEvent_t e0, e1;
+    NBS_CUDA_CHECK(cudaEventCreate(&e0));
+    NBS_CUDA_CHECK(cudaEventCreate(&e1));
+    const int ctas = prop.multiProcessorCount*4, rounds = 64;
+    for (int which = 0; which < 5; which++) {
+        double best = 0;
+        for (int rep = 0; rep < 5; rep++) {
+            cudaEventRecord(e0, 0);
+            switch (which) {
+                case 0: k_peak_dp<0><<<ctas, 256>>>(rounds, 0.5, sink); break;
+                case 1: k_peak_dp<1><<<ctas, 256>>>(rounds, 0.5, sink); break;
+                case 2: k_peak_dp<2><<<ctas, 256>>>(rounds, 0.5, sink); break;
+                case 3: k_peak_dp<3><<<ctas, 256>>>(rounds, 0.5, sink); break;
+                default: k_peak_dp<4><<<ctas, 256>>>(rounds, 0.5, sink); break;
+            }
+            cudaEventRecord(e1, 0);
+            NBS_CUDA_CHECK(cudaEventSynchronize(e1));
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e0, e1);
+            const double warpInstr = (double) rounds*16*8*8*ctas;            // 8 warps per CTA
+            const double perClockPerSM = warpInstr/(ms*1e-3)/(prop.clockRate*1e3)/prop.multiProcessorCount;
+            if (rep >= 1 && perClockPerSM > best) best = perClockPerSM;
+        }
+        out[which] = best;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(sink);
+    return NBS_OK;
+}
 
 extern "C" int nbs_measure_peaks(int32_t device, double out[4]) {
     if (!out) { setError("null argument"); return NBS_ERR_INVALID; }

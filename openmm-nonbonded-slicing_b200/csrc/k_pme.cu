@@ -179,6 +179,7 @@ struct PmeArgs {
     const uint4* fix; const float* chargeF; const int* subsetOf;
     const double* q64; const double* chargeD; double sqrtK;      // double-precision charges for the double-precision grids
     void* grid; const float* pot;
+    unsigned long long* gridFixed;   // deterministic mode: 64-bit fixed-point accumulation grid
     unsigned long long* force;
     float fscale[3];             // n_d / L_d
     // triclinic box (a = (ax,0,0), b = (bx,by,0), c = (cx,cy,cz)): lattice fractions from the brick fractions (u, v, w)
@@ -233,7 +234,19 @@ __device__ __forceinline__ void splineTable(const PmeArgs& a, const uint4 pBrick
 // One warp per (sorted) atom.  The 125 grid points are dealt to the lanes with z fastest (point = lane + 32 i,
 // z offset = point % 5), so one warp-wide atomic touches runs of 5 consecutive cells of a grid row instead of 25
 // different rows: about a third of the L2 atomic transactions of a row-per-lane assignment.
+// FIXED (NBS_FLAG_DETERMINISTIC; the plugin's CudaDeterministicForces, pme.cc:108-109, 124-134): the grid points are
+// accumulated as 64-bit fixed point -- integer adds commute, so the grid, and with it every reciprocal-space force,
+// is bit-reproducible whatever order the atomics retire in -- and k_fixed_to_real converts the grid afterwards.
+template <typename T> struct FixedGridScale { static constexpr double value = 4294967296.0; };            // 2^32: 2e-10 of a unit charge
+template <> struct FixedGridScale<double> { static constexpr double value = 1099511627776.0; };          // 2^40 for the double-precision grids
+
 template <typename T>
+__global__ void k_fixed_to_real(size_t n, const long long* __restrict__ fixed, T* __restrict__ grid) {
+    const size_t i = (size_t) blockIdx.x*blockDim.x + threadIdx.x;
+    if (i < n) grid[i] = (T) ((double) fixed[i]*(1.0/FixedGridScale<T>::value));
+}
+
+template <typename T, bool FIXED>
 __global__ void __launch_bounds__(256) k_spread(const PmeArgs a) {
     __shared__ T wtab[8][16];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -241,7 +254,7 @@ __global__ void __launch_bounds__(256) k_spread(const PmeArgs a) {
     if (j >= a.N) return;
     uint4 p; int subset; float q;
     if (a.unsorted) { p = a.fix[j]; q = a.chargeF[j]; subset = a.subsetOf[j]; }
-    else { p = a.posq[j]; q = __uint_as_float(p.w); subset = __float_as_int(a.par[j].z); }
+    else { p = a.posq[j]; q = __uint_as_float(p.w); subset = __float_as_int(a.par[j].z) & 7; }
     if (q == 0.f || subset < a.ownLo || subset >= a.ownHi) return;      // warp-uniform
     int ix0, iy0, iz0;
     splineTable<T>(a, p, lane, wtab[warp], (T*) nullptr, ix0, iy0, iz0);
@@ -249,6 +262,7 @@ __global__ void __launch_bounds__(256) k_spread(const PmeArgs a) {
     // (the fp32 charge carries 6e-8 of rounding: visible in cross-subset energies that cancel to 1e-6 of their terms)
     const T qT = sizeof(T) == 8 ? (T) (a.unsorted ? a.chargeD[j]*a.sqrtK : a.q64[j]) : (T) q;
     T* grid = (T*) a.grid + (size_t) subset*a.nx*a.ny*a.nz;
+    unsigned long long* gridFixed = a.gridFixed + (size_t) subset*a.nx*a.ny*a.nz;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const int pt = lane + 32*i;
@@ -257,7 +271,10 @@ __global__ void __launch_bounds__(256) k_spread(const PmeArgs a) {
             int x = ix0 + ox; x -= x >= a.nx ? a.nx : 0;
             int y = iy0 + oy; y -= y >= a.ny ? a.ny : 0;
             int z = iz0 + oz; z -= z >= a.nz ? a.nz : 0;
-            atomicAdd(grid + ((size_t) x*a.ny + y)*a.nz + z, qT*wt[ox]*wt[5 + oy]*wt[10 + oz]);
+            const T value = qT*wt[ox]*wt[5 + oy]*wt[10 + oz];
+            const size_t cell = ((size_t) x*a.ny + y)*a.nz + z;
+            if (FIXED) atomicAdd(gridFixed + cell, (unsigned long long) __double2ll_rn((double) value*FixedGridScale<T>::value));
+            else atomicAdd(grid + cell, value);
         }
     }
 }
@@ -478,7 +495,7 @@ __global__ void __launch_bounds__(256) k_gather(const PmeArgs a) {
     if (j >= a.N) return;
     uint4 p; int subset; float q;
     if (a.unsorted) { p = a.fix[j]; q = a.chargeF[j]; subset = a.subsetOf[j]; }
-    else { p = a.posq[j]; q = __uint_as_float(p.w); subset = __float_as_int(a.par[j].z); }
+    else { p = a.posq[j]; q = __uint_as_float(p.w); subset = __float_as_int(a.par[j].z) & 7; }
     if (q == 0.f) return;
     if (subset < a.ownLo || subset >= a.ownHi) return;
     int ix0, iy0, iz0;
@@ -654,7 +671,7 @@ static int launchPmeT(Context& c, bool wantEnergy, int half) {
     PmeArgs p;
     p.N = c.N; p.Npad = c.Npad; p.nS = c.nS; p.nx = nx; p.ny = ny; p.nz = nz; p.nzh = nzh;
     p.ownLo = c.ownLo; p.ownHi = c.ownHi;
-    p.posq = c.dPosq.d; p.par = c.dPar.d; p.grid = c.dGrid.d; p.pot = c.dPot.d;
+    p.posq = c.dPosq.d; p.par = c.dPar.d; p.grid = c.dGrid.d; p.pot = c.dPot.d; p.gridFixed = nullptr;
     p.unsorted = c.pmeUnsorted ? 1 : 0;
     p.fix = c.dFix.d; p.chargeF = c.dChargeF.d; p.subsetOf = c.dSubset.d;
     p.q64 = c.dQ64.d; p.chargeD = c.dCharge.d; p.sqrtK = sqrt(kOne4PiEps0);
@@ -677,8 +694,20 @@ static int launchPmeT(Context& c, bool wantEnergy, int half) {
     if (half == 0) {
         int status = prepareEterm(c);
         if (status != NBS_OK) return status;
-        NBS_CUDA_CHECK(cudaMemsetAsync((T*) c.dGrid.d + (size_t) c.ownLo*G, 0, sizeof(T)*G*(c.ownHi - c.ownLo), st));
-        k_spread<T><<<atomCtas, 256, 0, st>>>(p);
+        if (c.flags & NBS_FLAG_DETERMINISTIC) {
+            const size_t cells = G*(c.ownHi - c.ownLo);
+            NBS_CUDA_CHECK(c.dGridFixed.ensure(G*c.nS));
+            p.gridFixed = c.dGridFixed.d;
+            NBS_CUDA_CHECK(cudaMemsetAsync(c.dGridFixed.d + (size_t) c.ownLo*G, 0, sizeof(unsigned long long)*cells, st));
+            k_spread<T, true><<<atomCtas, 256, 0, st>>>(p);
+            k_fixed_to_real<T><<<(unsigned) ((cells + 255)/256), 256, 0, st>>>(cells, (const long long*) c.dGridFixed.d + (size_t) c.ownLo*G,
+                                                                                 (T*) c.dGrid.d + (size_t) c.ownLo*G);
+            c.launches++;
+        }
+        else {
+            NBS_CUDA_CHECK(cudaMemsetAsync((T*) c.dGrid.d + (size_t) c.ownLo*G, 0, sizeof(T)*G*(c.ownHi - c.ownLo), st));
+            k_spread<T, false><<<atomCtas, 256, 0, st>>>(p);
+        }
         c.launches++;
         timerMark(c, "spread");
     }

@@ -15,6 +15,27 @@ namespace nbs {
 // k_prep: one thread per input slot.  Wraps the position into the box (brick), converts to 32-bit
 // fixed-point fractional coordinates and counts the atom into its (column, z-bin).
 // ---------------------------------------------------------------------------------------------
+// Wraps a position into the brick [0, ax) x [0, by) x [0, cz) with the lattice translations -- first along
+// c = (cx, cy, cz), then b = (bx, by, 0), then a (tilt = (bx, cx, cy), all zero for a rectangular box) -- and
+// converts it to 32-bit fixed-point fractions of the brick.
+__device__ __forceinline__ void wrapToFixed(double x, double y, double z, const double3 invBox, const double3 origin,
+                                            const double3 tilt, unsigned& ux, unsigned& uy, unsigned& uz) {
+    x -= origin.x; y -= origin.y; z -= origin.z;
+    double fz = z*invBox.z;
+    const double kz = floor(fz);
+    fz -= kz;
+    x -= kz*tilt.y; y -= kz*tilt.z;
+    double fy = y*invBox.y;
+    const double ky = floor(fy);
+    fy -= ky;
+    x -= ky*tilt.x;
+    double fx = x*invBox.x;
+    fx -= floor(fx);
+    ux = (unsigned) (__double2ull_rd(fx*4294967296.0) & 0xffffffffull);
+    uy = (unsigned) (__double2ull_rd(fy*4294967296.0) & 0xffffffffull);
+    uz = (unsigned) (__double2ull_rd(fz*4294967296.0) & 0xffffffffull);
+}
+
 __global__ void k_prep(int N, const double* __restrict__ pos64, const float4* __restrict__ pos32,
                        const double4* __restrict__ pos64w, const int* __restrict__ atomIndex, double3 invBox, double3 origin,
                        double3 tilt, int ncx, int ncy, int nzb, uint4* __restrict__ fix, int* __restrict__ binCount,
@@ -35,25 +56,72 @@ __global__ void k_prep(int N, const double* __restrict__ pos64, const float4* __
     if (pos64out) {          // particle-ordered, unwrapped, double: what the exception kernel reads
         pos64out[3*particle] = x; pos64out[3*particle+1] = y; pos64out[3*particle+2] = z;
     }
-    // wrap into the brick [0, ax) x [0, by) x [0, cz) with the lattice translations: first along c = (cx, cy, cz),
-    // then b = (bx, by, 0), then a (tilt = (bx, cx, cy), all zero for a rectangular box)
-    x -= origin.x; y -= origin.y; z -= origin.z;
-    double fz = z*invBox.z;
-    const double kz = floor(fz);
-    fz -= kz;
-    x -= kz*tilt.y; y -= kz*tilt.z;
-    double fy = y*invBox.y;
-    const double ky = floor(fy);
-    fy -= ky;
-    x -= ky*tilt.x;
-    double fx = x*invBox.x;
-    fx -= floor(fx);
-    unsigned ux = (unsigned) (__double2ull_rd(fx*4294967296.0) & 0xffffffffull);
-    unsigned uy = (unsigned) (__double2ull_rd(fy*4294967296.0) & 0xffffffffull);
-    unsigned uz = (unsigned) (__double2ull_rd(fz*4294967296.0) & 0xffffffffull);
+    unsigned ux, uy, uz;
+    wrapToFixed(x, y, z, invBox, origin, tilt, ux, uy, uz);
     int bin = (__umulhi(ux, ncx)*ncy + __umulhi(uy, ncy))*nzb + __umulhi(uz, nzb);
     fix[particle] = make_uint4(ux, uy, uz, (unsigned) bin);
     atomicAdd(&binCount[bin], 1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_reprep: the per-evaluation front end while the neighbour list is RE-USED (the plugin's CUDA platform inherits
+// the same policy from OpenMM: a padded list kept until atoms have moved half the padding,
+// CommonNonbondedSlicingKernels.cpp:721 `useNeighborList`).  One thread per input slot: new fixed-point coordinates
+// go straight to the atom's place in the sort order of the last build; nothing is sorted, no block or list changes.
+//   * displacement since the build -> running maximum in counters[4] (float bits of nm^2; zeroed by the build's
+//     k_prep).  The host redoes the evaluation with a fresh list if it exceeds half the skin.
+//   * an atom that has left the brick since the build is wrapped like any other, and the lattice translation
+//     (cross_x, cross_y, cross_z) that brings it back next to its build-time position is packed into par.z above
+//     the subset (bits 4-6: cross_x in -2..2, 7-8: cross_y, 9-10: cross_z, two's complement): the pair kernel adds
+//     it to the image shift of the list entry, whose image code refers to the build-time coordinates.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_reprep(int N, const double* __restrict__ pos64, const float4* __restrict__ pos32,
+                         const double4* __restrict__ pos64w, const int* __restrict__ atomIndex, double3 invBox, double3 origin,
+                         double3 tilt, long long shiftB, long long shiftCx, long long shiftCy, float3 scale,
+                         const int* __restrict__ origToSorted, const uint4* __restrict__ fixBuild,
+                         const float* __restrict__ chargeF, const int* __restrict__ subset,
+                         uint4* __restrict__ fix, uint4* __restrict__ posq, float4* __restrict__ par,
+                         double* __restrict__ pos64out, double* __restrict__ energy, int* __restrict__ counters) {
+    int slot = blockIdx.x*blockDim.x + threadIdx.x;
+    if (blockIdx.x == 0) {
+        for (int k = threadIdx.x; k < ENERGY_WORDS; k += blockDim.x) energy[k] = 0.0;
+        if (threadIdx.x == 0) { counters[1] = 0; counters[3] = 0; }      // overflow flag, pair-kernel work cursor
+    }
+    float d2 = 0.f;
+    if (slot < N) {
+        double x, y, z;
+        if (pos64) { x = pos64[3*slot]; y = pos64[3*slot+1]; z = pos64[3*slot+2]; }
+        else if (pos64w) { double4 p = pos64w[slot]; x = p.x; y = p.y; z = p.z; }
+        else { float4 p = pos32[slot]; x = p.x; y = p.y; z = p.z; }
+        const int particle = atomIndex ? atomIndex[slot] : slot;
+        if (pos64out) { pos64out[3*particle] = x; pos64out[3*particle+1] = y; pos64out[3*particle+2] = z; }
+        unsigned ux, uy, uz;
+        wrapToFixed(x, y, z, invBox, origin, tilt, ux, uy, uz);
+        const int s = origToSorted[particle];
+        const uint4 fb = fixBuild[s];
+        // lattice translation back to the build-time neighbourhood: z first (c tilts into x and y), then y, then x
+        const long long half = 1ll << 31;
+        long long dz = (long long) uz - (long long) fb.z;
+        const int cz = dz > half ? -1 : (dz < -half ? 1 : 0);
+        dz += (long long) cz << 32;
+        long long dy = (long long) uy - (long long) fb.y + cz*shiftCy;
+        int cy = 0;
+        while (dy > half) { dy -= 1ll << 32; cy--; }
+        while (dy < -half) { dy += 1ll << 32; cy++; }
+        long long dx = (long long) ux - (long long) fb.x + cz*shiftCx + cy*shiftB;
+        int cx = 0;
+        while (dx > half) { dx -= 1ll << 32; cx--; }
+        while (dx < -half) { dx += 1ll << 32; cx++; }
+        const float ex = (float) dx*scale.x, ey = (float) dy*scale.y, ez = (float) dz*scale.z;
+        d2 = ex*ex + ey*ey + ez*ez;
+        if (cx < -2 || cx > 2 || cy < -1 || cy > 1) d2 = 1.0e30f;       // not representable: forces a fresh list
+        fix[particle] = make_uint4(ux, uy, uz, 0u);
+        posq[s] = make_uint4(ux, uy, uz, __float_as_uint(chargeF[particle]));
+        reinterpret_cast<int*>(par)[4*s + 2] = subset[particle] | ((cx & 7) << 4) | ((cy & 3) << 7) | ((cz & 3) << 9);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d2 = fmaxf(d2, __shfl_xor_sync(0xffffffffu, d2, o));
+    if ((threadIdx.x & 31) == 0 && d2 > 0.f) atomicMax(reinterpret_cast<unsigned*>(counters) + 4, __float_as_uint(d2));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -162,7 +230,8 @@ __global__ void k_place(int N, const int* __restrict__ binStart, const int* __re
                         int* __restrict__ origToSorted, const uint4* __restrict__ fix,
                         const float* __restrict__ chargeF, const float2* __restrict__ sigEps,
                         const int* __restrict__ subset, const double* __restrict__ charge, double sqrtK,
-                        uint4* __restrict__ posq, float4* __restrict__ par, double* __restrict__ q64) {
+                        uint4* __restrict__ posq, float4* __restrict__ par, double* __restrict__ q64,
+                        uint4* __restrict__ fixBuild) {
     const int s = blockIdx.x*blockDim.x + threadIdx.x;
     if (s >= N) return;
     const int p = scattered[s];
@@ -175,6 +244,7 @@ __global__ void k_place(int N, const int* __restrict__ binStart, const int* __re
     posq[slot] = make_uint4(f.x, f.y, f.z, __float_as_uint(chargeF[p]));
     par[slot] = make_float4(se.x, se.y, __int_as_float(subset[p]), __int_as_float(p));
     q64[slot] = charge[p]*sqrtK;
+    fixBuild[slot] = make_uint4(f.x, f.y, f.z, 0u);      // what a re-used list measures displacements from (k_reprep)
     origToSorted[p] = slot;
 }
 
@@ -232,6 +302,10 @@ __global__ void k_blocks(int nCols, int nzb, int maxBlocks, const int* __restric
         zl = min(zl, __shfl_xor_sync(0xffffffffu, zl, o)); zh = max(zh, __shfl_xor_sync(0xffffffffu, zh, o));
     }
     if (lane == 0) {
+        // largest block extents (fixed-point units): decide whether this list may be re-used (nbs_api.cu phaseComplete)
+        atomicMax(reinterpret_cast<unsigned*>(counters) + 5, xh - xl);
+        atomicMax(reinterpret_cast<unsigned*>(counters) + 6, yh - yl);
+        atomicMax(reinterpret_cast<unsigned*>(counters) + 7, zh - zl);
         blkFirst[b] = first;
         blkCount[b] = count;
         blkLo[b] = make_uint4(xl, yl, zl, (unsigned) col);
@@ -319,6 +393,23 @@ int launchPrep(Context& c, const PosInput& in) {
     return NBS_OK;
 }
 
+int launchReprep(Context& c, const PosInput& in) {
+    const CellGeom& g = c.geom;
+    const int N = c.N, T = 256;
+    k_reprep<<<(N+T-1)/T, T, 0, c.stream>>>(N, in.format == NBS_POS_F64_XYZ ? (const double*) in.ptr : nullptr,
+                                            in.format == NBS_POS_F32_XYZW ? (const float4*) in.ptr : nullptr,
+                                            in.format == NBS_POS_F64_XYZW ? (const double4*) in.ptr : nullptr, in.atomIndex,
+                                            make_double3(g.invBox[0], g.invBox[1], g.invBox[2]),
+                                            make_double3(g.origin[0], g.origin[1], g.origin[2]),
+                                            make_double3(g.tilt[0], g.tilt[1], g.tilt[2]), g.shiftB, g.shiftCx, g.shiftCy,
+                                            make_float3(g.scale[0], g.scale[1], g.scale[2]),
+                                            c.dOrigToSorted.d, c.dFixBuild.d, c.dChargeF.d, c.dSubset.d,
+                                            c.dFix.d, c.dPosq.d, c.dPar.d, in.pos64out, c.dEnergy.d, c.dCounters.d);
+    c.launches++;
+    timerMark(c, "reprep");
+    return NBS_OK;
+}
+
 // The rest of the cell sort: scan of the bin counts, counting sort, sorted records, i-blocks.
 int launchSortRest(Context& c) {
     const CellGeom& g = c.geom;
@@ -330,7 +421,7 @@ int launchSortRest(Context& c) {
     k_scatter<<<(N+T-1)/T, T, 0, st>>>(N, c.dFix.d, c.dBinStart.d, c.dBinCursor.d, c.dSortedToOrig.d);
     k_place<<<(N+T-1)/T, T, 0, st>>>(N, c.dBinStart.d, c.dSortedToOrig.d, c.dOrigToSorted.d, c.dFix.d,
                                      c.dChargeF.d, c.dSigEps.d, c.dSubset.d, c.dCharge.d, sqrt(kOne4PiEps0),
-                                     c.dPosq.d, c.dPar.d, c.dQ64.d);
+                                     c.dPosq.d, c.dPar.d, c.dQ64.d, c.dFixBuild.d);
     c.launches += 2;
     // The per-atom exclusion ranges only need the sorted order: on the side stream they run beside the block
     // construction instead of in front of the list builder (which waits for them, launchBuildLists).

@@ -217,6 +217,7 @@ static int applyParameters(Context& c) {
         NBS_CUDA_CHECK(cudaMemcpy(c.dExcSlice.d, excSlice.data(), sizeof(int)*c.nExc, cudaMemcpyHostToDevice));
     }
     c.paramsDirty = false;
+    c.listEpoch++;                 // the sorted per-atom records of a re-used list hold the old parameters
     return NBS_OK;
 }
 
@@ -283,21 +284,19 @@ int uploadPmeTables(Context& c) {
 }
 
 // Piecewise polynomial table of f(s) = erfc(alpha sqrt(s))/sqrt(s) for the double-precision pair energies
-// (k_pair.cu pairEnergyD): degree-4 interpolation at Chebyshev nodes on every interval [2^e (1 + m/256),
-// 2^e (1 + (m+1)/256)), e = -7 .. floor(log2 cutoff^2) + 1.  Relative error 1e-11 at alpha = 2.6 (2e-10 at alpha = 3.4,
-// where f itself is 1e-6 of its short-range values), checked against mpmath.  Three 16-byte loads and 4 FMAs per pair
-// -- the loads are what the pair kernel's energy passes are bound by (one divergent row per lane).
+// (k_pair.cu pairEnergyD): degree-7 interpolation at Chebyshev nodes on every interval [2^e (1 + m/16),
+// 2^e (1 + (m+1)/16)), e = -7 .. floor(log2 cutoff^2) + 1; relative error 5e-12 (ERFC_TAB_* in nbs_internal.h).
 static int buildErfcTable(Context& c) {
-    const int eMax = std::max(-6, (int) std::floor(std::log2(c.cutoff*c.cutoff)) + 1);
+    const int eMax = std::min(8, std::max(-6, (int) std::floor(std::log2(c.cutoff*c.cutoff)) + 1));
     const int M = 1 << ERFC_TAB_PER_OCTAVE_LOG2;
     const int rows = (eMax + 7 + 1)*M;
-    std::vector<double> tab((size_t) rows*ERFC_TAB_ROW, 0.0);
-    const int D = ERFC_TAB_DEGREE;
+    constexpr int D = ERFC_TAB_DEGREE;
+    std::vector<double> tab((size_t) rows*(D + 1), 0.0);
     for (int e = -7; e <= eMax; e++)
         for (int m = 0; m < M; m++) {
             const long double lo = std::ldexp(1.0L + m/(long double) M, e), w = std::ldexp(1.0L/M, e);
             const long double center = lo + w/2;
-            long double A[ERFC_TAB_DEGREE + 1][ERFC_TAB_DEGREE + 2];
+            long double A[D + 1][D + 2];
             for (int k = 0; k <= D; k++) {
                 const long double xn = std::cos(3.14159265358979323846264338327950288L*(2*k + 1)/(2.0L*(D + 1)));
                 const long double sv = center + xn*w/2;
@@ -316,10 +315,10 @@ static int buildErfcTable(Context& c) {
                     for (int j = col; j <= D + 1; j++) A[r][j] -= f*A[col][j];
                 }
             }
-            double* row = tab.data() + ((size_t) (e + 7)*M + m)*ERFC_TAB_ROW;
-            row[0] = (double) (-center*2/w);                     // d = s * (2/w) + offset, 2/w = 2^(9-e) formed from the exponent
-            for (int k = 0; k <= D; k++) row[1 + (D - k)] = (double) (A[k][D + 1]/A[k][k]);     // a4 first
+            const int row = (e + 7)*M + m;
+            for (int k = 0; k <= D; k++) tab[(size_t) (D - k)*rows + row] = (double) (A[k][D + 1]/A[k][k]);     // a7 first
         }
+    c.erfcRows = rows;
     NBS_CUDA_CHECK(c.dErfcTab.ensure(tab.size()));
     NBS_CUDA_CHECK(cudaMemcpy(c.dErfcTab.d, tab.data(), sizeof(double)*tab.size(), cudaMemcpyHostToDevice));
     return NBS_OK;
@@ -335,7 +334,10 @@ static int setupGeometry(Context& c, const double L[3], const double origin[3], 
     g.shiftCy = std::llround(tilt[2]/L[1]*4294967296.0);
     const double volume = L[0]*L[1]*L[2];
     const double density = c.N/volume;
-    double side = std::cbrt(32.0/density);
+    // columns narrower than a cubic 32-atom block (factor 0.8): the i-blocks get taller, their 4-atom clusters
+    // closer to cubes, and the pair kernel's cluster masks prune more (profiles/README.md)
+    static const double sideScale = getenv("NBS_COL_SIDE_SCALE") ? atof(getenv("NBS_COL_SIDE_SCALE")) : 0.8;
+    double side = sideScale*std::cbrt(32.0/density);
     side = std::max(side, 0.3*c.cutoffEff);
     for (int k = 0; k < 3; k++) {
         g.origin[k] = origin[k];
@@ -357,6 +359,7 @@ static int setupGeometry(Context& c, const double L[3], const double origin[3], 
     c.maxBlocks = N/32 + g.nCols + 1;
     c.maxLocalBlocks = std::max(1, ((c.maxBlocks + c.blockPeriod - 1)/c.blockPeriod)*c.blockWidth);
     NBS_CUDA_CHECK(c.dFix.ensure(N));
+    NBS_CUDA_CHECK(c.dFixBuild.ensure(c.Npad));
     NBS_CUDA_CHECK(c.dBinCount.ensure(g.nBins + 2));
     NBS_CUDA_CHECK(c.dBinStart.ensure(g.nBins + 2));
     NBS_CUDA_CHECK(c.dBinCursor.ensure(g.nBins + 2));
@@ -376,6 +379,8 @@ static int setupGeometry(Context& c, const double L[3], const double origin[3], 
     NBS_CUDA_CHECK(c.dJList.ensure((size_t) c.maxLocalBlocks*c.capJ));
     NBS_CUDA_CHECK(c.dXList.ensure((size_t) c.maxLocalBlocks*c.capX));
     NBS_CUDA_CHECK(c.dXMask.ensure((size_t) c.maxLocalBlocks*c.capX));
+    NBS_CUDA_CHECK(c.dGmJ.ensure((size_t) c.maxLocalBlocks*(c.capJ/32)));
+    NBS_CUDA_CHECK(c.dGmX.ensure((size_t) c.maxLocalBlocks*(c.capX/32)));
     // work items: enough warps' worth of items to balance 148 SMs x 16 warps on small systems, larger
     // chunks (fewer i-force flushes) on big ones
     c.chunkTiles = N < 150000 ? 1 : (N < 600000 ? 4 : 8);
@@ -409,12 +414,12 @@ static void releaseAll(Context& c) {
     timerReset(c);
     c.dSubset.release(); c.dChargeF.release(); c.dSigEps.release(); c.dCharge.release();
     c.dExclStart.release(); c.dExclList.release(); c.dExcPair.release(); c.dExcParam.release(); c.dExcSlice.release();
-    c.dPosIn.release(); c.dForceOut.release(); c.dFix.release(); c.dBinCount.release(); c.dBinStart.release();
+    c.dPosIn.release(); c.dForceOut.release(); c.dFix.release(); c.dFixBuild.release(); c.dBinCount.release(); c.dBinStart.release();
     c.dBinCursor.release(); c.dScanTmp.release(); c.dSortedToOrig.release(); c.dOrigToSorted.release();
     c.dPosq.release(); c.dPar.release(); c.dQ64.release(); c.dColBlockStart.release(); c.dBlkFirst.release(); c.dBlkCount.release();
     c.dBlkLo.release(); c.dBlkHi.release(); c.dExclRange.release(); c.dJList.release(); c.dJCount.release();
-    c.dXList.release(); c.dXCount.release(); c.dXMask.release(); c.dCounters.release(); c.dForce.release(); c.dItems.release();
-    c.dEnergy.release(); c.dGrid.release(); c.dGridC.release(); c.dEterm.release(); c.dModuli.release();
+    c.dXList.release(); c.dXCount.release(); c.dXMask.release(); c.dGmJ.release(); c.dGmX.release(); c.dCounters.release(); c.dForce.release(); c.dItems.release();
+    c.dEnergy.release(); c.dGrid.release(); c.dGridFixed.release(); c.dGridC.release(); c.dEterm.release(); c.dModuli.release();
     c.dPot.release(); c.dEtermD.release(); c.dTwiddleD.release(); c.dErfcTab.release();
     c.dEwaldK.release(); c.dEwaldSums.release(); c.dEwaldMixed.release();
     c.dC6F.release(); c.dC6D.release(); c.dEtermDisp.release(); c.dEtermDDisp.release(); c.dModuliDisp.release();
@@ -424,8 +429,10 @@ static void releaseAll(Context& c) {
     if (c.hEnergy) cudaFreeHost(c.hEnergy);
     if (c.hForce) cudaFreeHost(c.hForce);
     c.hCounters = nullptr; c.hEnergy = nullptr; c.hForce = nullptr;
-    if (c.graphExec) cudaGraphExecDestroy(c.graphExec);
-    c.graphExec = nullptr;
+    for (int k = 0; k < 2; k++) {
+        if (c.graphExecs[k]) cudaGraphExecDestroy(c.graphExecs[k]);
+        c.graphExecs[k] = nullptr;
+    }
     if (c.ownStream) cudaStreamDestroy(c.ownStream);
     c.ownStream = nullptr;
     if (c.auxStream) cudaStreamDestroy(c.auxStream);
@@ -497,6 +504,9 @@ int nbs_create(const nbs_system_desc* desc, nbs_context** out) {
     c.ownLo = 0; c.ownHi = c.nS;
     c.capX = 256;
     c.profiling = (c.flags & NBS_FLAG_PROFILE) != 0;
+    // neighbour-list re-use: on by default for the periodic cutoff methods (nbs_set_list_skin changes it)
+    c.skin = (c.periodic && !(c.flags & NBS_FLAG_NO_LIST_REUSE)) ? 0.07 : 0.0;
+    if (const char* env = getenv("NBS_LIST_SKIN")) { if (c.periodic && !(c.flags & NBS_FLAG_NO_LIST_REUSE)) c.skin = std::max(0.0, atof(env)); }
     cudaError_t e = cudaSuccess;
     if ((e = c.dCounters.ensure(16)) != cudaSuccess || (e = c.dEnergy.ensure(ENERGY_WORDS)) != cudaSuccess ||
         (e = c.dPairStats.ensure(4)) != cudaSuccess || (e = c.dPairDump.ensure(1)) != cudaSuccess ||
@@ -544,6 +554,7 @@ int nbs_destroy(nbs_context* ctx) {
 int nbs_update_parameters(nbs_context* ctx, const nbs_system_desc* desc) {
     if (!ctx || !desc) return fail(NBS_ERR_INVALID, "null argument");
     cudaSetDevice(ctx->c.device);
+    ctx->c.listEpoch++;
     return readDescription(ctx->c, *desc, false);
 }
 
@@ -616,9 +627,24 @@ static cudaStream_t workStream(Context& c, const nbs_exec_args* args) {
     return c.ownStream;
 }
 
-static int phaseBegin(Context& c, const nbs_exec_args* args) {
+// Decides whether this evaluation re-uses the sort order and the neighbour list of an earlier one.  The list was
+// built with cutoff + skin; it stays complete while no atom has moved more than skin/2 since, which k_reprep
+// measures on the device DURING the evaluation -- phaseComplete then either accepts the result or has the
+// evaluation redone with a fresh list (and asks for a fresh list ahead of time when the next step would
+// probably exceed the limit).
+static void planListReuse(Context& c, const nbs_exec_args* args) {
+    const bool direct = args->include_direct != 0;
+    c.reuseNow = c.skin > 0 && c.periodic && c.listValid && !c.forceRebuild && !c.paramsDirty &&
+                 std::memcmp(c.listBox, args->box, sizeof(double)*9) == 0 && c.listEpochAtBuild == c.listEpoch &&
+                 c.listAllocEpoch == gAllocEpoch && c.listCapJ == c.capJ && (!direct || c.listHasDirect);
+}
+
+static int phaseBegin(Context& c, const nbs_exec_args* args, bool planned = false) {
     int status = validateExec(c, args);
     if (status != NBS_OK) return status;
+    if (c.paramsDirty) { NBS_CUDA_CHECK(cudaSetDevice(c.device)); if ((status = applyParameters(c)) != NBS_OK) return status; }
+    if (!planned) planListReuse(c, args);
+    c.evalCount++;
     NBS_CUDA_CHECK(cudaSetDevice(c.device));
     const double* box = args->box;
     c.stream = workStream(c, args);
@@ -629,7 +655,6 @@ static int phaseBegin(Context& c, const nbs_exec_args* args) {
     c.phaseRecip = args->include_reciprocal != 0 && pme;
     c.phase = 0;
     const int N = c.N;
-    if (c.paramsDirty && (status = applyParameters(c)) != NBS_OK) return status;
     timerReset(c);
     timerMark(c, "begin");
     // positions
@@ -683,7 +708,7 @@ static int phaseBegin(Context& c, const nbs_exec_args* args) {
     NBS_CUDA_CHECK(cudaMemsetAsync(c.dForce.d, 0, sizeof(unsigned long long)*(c.pmeUnsorted ? 6 : 3)*c.Npad, st));
     // (the slice-energy table and the counters are zeroed by k_prep)
     timerMark(c, "h2d_zero");
-    if ((status = launchPrep(c, in)) != NBS_OK) return status;
+    if ((status = (c.reuseNow ? launchReprep(c, in) : launchPrep(c, in))) != NBS_OK) return status;
     // The cell sort, the neighbour list and direct space run on their own stream, concurrently with the PME
     // chain on `st` (serial when profiling).  With particle-order PME the fork is right here, after k_prep;
     // otherwise PME needs the sorted records and the fork comes after the sort.
@@ -697,7 +722,7 @@ static int phaseBegin(Context& c, const nbs_exec_args* args) {
     }
     // (only when this rank builds lists: launchBuildLists is where the side stream joins again)
     c.sideFork = overlap && c.phaseDirect && c.auxStream != nullptr && c.blockWidth != 0;
-    status = launchSortRest(c);
+    status = c.reuseNow ? NBS_OK : launchSortRest(c);
     if (status == NBS_OK && c.phaseDirect) {
         if (overlap && !forkEarly) {
             NBS_CUDA_CHECK(cudaEventRecord(c.evSorted, st));
@@ -714,7 +739,7 @@ static int phaseBegin(Context& c, const nbs_exec_args* args) {
             cudaEventRecord(c.evAuxDone, c.auxStream);
             c.stream = c.directStream;
         }
-        if (status == NBS_OK) status = launchBuildLists(c);
+        if (status == NBS_OK && !c.reuseNow) status = launchBuildLists(c);
         if (status == NBS_OK) status = launchPairs(c, c.phaseEnergy, 0);
         if (status == NBS_OK && c.nExc > 0 && !forkBonded) {
             if (!dPos64) status = fail(NBS_ERR_UNSUPPORTED, "exceptions need double-precision positions in this version");
@@ -806,6 +831,43 @@ static int phaseComplete(Context& c, const nbs_exec_args* args) {
         c.capX *= 2;
         return NBS_RETRY;
     }
+    {
+        float d2;
+        std::memcpy(&d2, &c.hCounters[4], sizeof(float));
+        const double disp = std::sqrt((double) d2), limit = 0.5*c.skin;
+        if (c.reuseNow) {
+            if (disp > limit) {
+                c.listValid = false;
+                if (c.phaseDirect) {              // the list may have missed pairs: redo with a fresh one
+                    c.redoCount++;
+                    c.forceRebuild = true;
+                    return NBS_RETRY;
+                }
+            }
+            c.dispStepMax = std::max(c.dispStepMax, disp - c.dispLast);
+            c.dispLast = disp;
+            if (disp + 1.5*c.dispStepMax > limit) c.forceRebuild = true;     // the next evaluation would probably exceed it
+        }
+        else {
+            // a fresh sort (+ list): re-usable unless a block is so long that the pair kernel's window arithmetic
+            // (corner - guard .. corner + box - guard) could not place a moved atom unambiguously
+            c.buildCount++;
+            bool fits = true;
+            for (int d = 0; d < 3; d++) {
+                const double guard = (0.5*c.skin + 1.0e-3)/c.geom.box[d]*4294967296.0;
+                if ((double) (unsigned) c.hCounters[5+d] + 2.0*guard + 65536.0 >= 4294967296.0) fits = false;
+            }
+            c.listValid = c.skin > 0 && c.periodic && fits;
+            c.listHasDirect = c.phaseDirect;
+            std::memcpy(c.listBox, box, sizeof(double)*9);
+            c.listEpochAtBuild = c.listEpoch;
+            c.listAllocEpoch = gAllocEpoch;
+            c.listCapJ = c.capJ;
+            c.forceRebuild = false;
+            c.dispLast = 0;
+            c.dispStepMax = 0;
+        }
+    }
     c.nBlocksLast = c.hCounters[0];
     c.haveLast = true;
     c.lastDirect = c.phaseDirect;
@@ -868,6 +930,7 @@ static unsigned long long graphSignature(const Context& c, const nbs_exec_args* 
     h = mix64(h, c.paramVersion);
     h = mix64(h, gAllocEpoch);
     h = mix64(h, ((unsigned long long) c.capJ << 32) | (unsigned long long) c.capX);
+    h = mix64(h, c.reuseNow ? 0x5bd1e995ull : 0ull);
     return h | 1ull;
 }
 
@@ -900,15 +963,17 @@ int nbs_execute(nbs_context* ctx, const nbs_exec_args* args) {
     if (graphable && args->positions_space == NBS_MEM_HOST) graphable = hostPointerIsPinned(args->positions);
     if (graphable && args->forces && args->forces_space == NBS_MEM_HOST && !args->forces_accumulate)
         graphable = hostPointerIsPinned(args->forces);       // (accumulation goes through our own pinned staging buffer)
-    for (int attempt = 0; attempt < 7; attempt++) {
+    for (int attempt = 0; attempt < 9; attempt++) {
         int status;
+        planListReuse(c, args);
+        const int slot = c.reuseNow ? 1 : 0;
         const unsigned long long key = graphable ? graphSignature(c, args) : 0;
-        if (graphable && c.graphExec && c.graphKey == key && args->include_reciprocal && !etermMatchesBox(c, args->box)) {
-            cudaGraphExecDestroy(c.graphExec);     // stale influence function: plain path now, capture again later
-            c.graphExec = nullptr;
-            c.graphKey = 0;
+        if (graphable && c.graphExecs[slot] && c.graphKeys[slot] == key && args->include_reciprocal && !etermMatchesBox(c, args->box)) {
+            cudaGraphExecDestroy(c.graphExecs[slot]);     // stale influence function: plain path now, capture again later
+            c.graphExecs[slot] = nullptr;
+            c.graphKeys[slot] = 0;
         }
-        if (graphable && c.graphExec && c.graphKey == key) {
+        if (graphable && c.graphExecs[slot] && c.graphKeys[slot] == key) {
             // replay
             status = validateExec(c, args);
             if (status != NBS_OK) return status;
@@ -917,20 +982,21 @@ int nbs_execute(nbs_context* ctx, const nbs_exec_args* args) {
             c.phaseEnergy = args->slice_energies != nullptr;
             c.phaseDirect = args->include_direct != 0;
             c.phaseRecip = args->include_reciprocal != 0 && c.ewaldDirect();
-            NBS_CUDA_CHECK(cudaGraphLaunch(c.graphExec, c.stream));
-            c.launches += c.graphLaunches;
+            c.evalCount++;
+            NBS_CUDA_CHECK(cudaGraphLaunch(c.graphExecs[slot], c.stream));
+            c.launches += c.graphLaunchCounts[slot];
             status = phaseComplete(c, args);
         }
-        else if (graphable && c.warmKey == key) {
+        else if (graphable && c.warmKeys[slot] == key) {
             // second identical evaluation: capture it
             status = validateExec(c, args);
             if (status != NBS_OK) return status;
             NBS_CUDA_CHECK(cudaSetDevice(c.device));
             cudaStream_t st = workStream(c, args);
-            if (c.graphExec) { cudaGraphExecDestroy(c.graphExec); c.graphExec = nullptr; }
+            if (c.graphExecs[slot]) { cudaGraphExecDestroy(c.graphExecs[slot]); c.graphExecs[slot] = nullptr; }
             const long long before = c.launches;
             NBS_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-            status = phaseBegin(c, args);
+            status = phaseBegin(c, args, true);
             if (status == NBS_OK) status = phaseConvolve(c, args);
             if (status == NBS_OK) status = phaseFinishEnqueue(c, args);
             cudaGraph_t graph = nullptr;
@@ -938,27 +1004,27 @@ int nbs_execute(nbs_context* ctx, const nbs_exec_args* args) {
             if (status != NBS_OK || e != cudaSuccess || !graph) {
                 if (graph) cudaGraphDestroy(graph);
                 cudaGetLastError();
-                c.warmKey = 0;
+                c.warmKeys[slot] = 0;
                 graphable = false;                 // fall back to plain launches for this call
                 if (status != NBS_OK) return status;
                 attempt--;
                 continue;
             }
-            e = cudaGraphInstantiate(&c.graphExec, graph, 0);
+            e = cudaGraphInstantiate(&c.graphExecs[slot], graph, 0);
             cudaGraphDestroy(graph);
-            if (e != cudaSuccess) { c.graphExec = nullptr; cudaGetLastError(); c.warmKey = 0; graphable = false; attempt--; continue; }
-            c.graphKey = key;
-            c.graphLaunches = c.launches - before;
+            if (e != cudaSuccess) { c.graphExecs[slot] = nullptr; cudaGetLastError(); c.warmKeys[slot] = 0; graphable = false; attempt--; continue; }
+            c.graphKeys[slot] = key;
+            c.graphLaunchCounts[slot] = c.launches - before;
             c.launches = before;
-            NBS_CUDA_CHECK(cudaGraphLaunch(c.graphExec, st));
-            c.launches += c.graphLaunches;
+            NBS_CUDA_CHECK(cudaGraphLaunch(c.graphExecs[slot], st));
+            c.launches += c.graphLaunchCounts[slot];
             status = phaseComplete(c, args);
         }
         else {
-            status = phaseBegin(c, args);
+            status = phaseBegin(c, args, true);
             if (status == NBS_OK) status = phaseConvolve(c, args);
             if (status == NBS_OK) status = phaseFinish(c, args);
-            if (status == NBS_OK && graphable) c.warmKey = graphSignature(c, args);
+            if (status == NBS_OK && graphable) c.warmKeys[slot] = key;
         }
         if (status != NBS_RETRY) return status;
     }
@@ -993,6 +1059,7 @@ int nbs_set_shard(nbs_context* ctx, int32_t rank, int32_t num_ranks, int32_t blo
         return fail(NBS_ERR_UNSUPPORTED, "the plain Ewald sum and LJPME are not sharded across ranks (use PME)");
     c.rank = rank; c.nRanks = num_ranks;
     c.paramVersion++;
+    c.listEpoch++;
     c.blockPeriod = block_period; c.blockOffset = block_offset; c.blockWidth = block_width;
     c.ownLo = subset_begin; c.ownHi = subset_end;
     c.haveLast = false;
@@ -1003,8 +1070,26 @@ int nbs_debug_set_list_capacity(nbs_context* ctx, int32_t j_capacity, int32_t x_
     if (!ctx || j_capacity < 64 || x_capacity < 64 || j_capacity % 32 || x_capacity % 32)
         return fail(NBS_ERR_INVALID, "capacities must be multiples of 32, at least 64");
     ctx->c.paramVersion++;
+    ctx->c.listEpoch++;
     ctx->c.capJ = j_capacity;
     ctx->c.capX = x_capacity;
+    return NBS_OK;
+}
+
+int nbs_set_list_skin(nbs_context* ctx, double skin) {
+    if (!ctx || !(skin >= 0) || skin > 1.0) return fail(NBS_ERR_INVALID, "the neighbour-list skin must lie in [0, 1] nm");
+    Context& c = ctx->c;
+    c.skin = c.periodic ? skin : 0.0;
+    c.listEpoch++;
+    c.paramVersion++;
+    return NBS_OK;
+}
+
+int nbs_get_list_stats(const nbs_context* ctx, double out[8]) {
+    if (!ctx || !out) return fail(NBS_ERR_INVALID, "null argument");
+    const Context& c = ctx->c;
+    out[0] = (double) c.evalCount; out[1] = (double) c.buildCount; out[2] = (double) c.redoCount;
+    out[3] = c.dispLast; out[4] = c.skin; out[5] = c.listValid ? 1 : 0; out[6] = c.reuseNow ? 1 : 0; out[7] = c.dispStepMax;
     return NBS_OK;
 }
 
@@ -1126,13 +1211,19 @@ int nbs_get_nlist_stats(nbs_context* ctx, int64_t stats[8]) {
     std::vector<int> jc(nb), xc(nb);
     NBS_CUDA_CHECK(cudaMemcpy(jc.data(), c.dJCount.d, sizeof(int)*nb, cudaMemcpyDeviceToHost));
     NBS_CUDA_CHECK(cudaMemcpy(xc.data(), c.dXCount.d, sizeof(int)*nb, cudaMemcpyDeviceToHost));
-    long long entries = 0, tiles = 0, xentries = 0;
+    // pair evaluations = 32 per step, one step per set bit of a group's cluster mask (k_pair.cu tileLoop)
+    std::vector<unsigned> gj((size_t) nb*(c.capJ/32)), gx((size_t) nb*(c.capX/32));
+    NBS_CUDA_CHECK(cudaMemcpy(gj.data(), c.dGmJ.d, sizeof(unsigned)*gj.size(), cudaMemcpyDeviceToHost));
+    NBS_CUDA_CHECK(cudaMemcpy(gx.data(), c.dGmX.d, sizeof(unsigned)*gx.size(), cudaMemcpyDeviceToHost));
+    long long entries = 0, tiles = 0, xentries = 0, steps = 0;
     for (int b = 0; b < nb; b++) {
         entries += jc[b] + xc[b];
         xentries += xc[b];
         tiles += (jc[b]+31)/32 + (xc[b]+31)/32;
+        for (int t = 0; t < (jc[b]+31)/32; t++) steps += __builtin_popcount(gj[(size_t) b*(c.capJ/32) + t]);
+        for (int t = 0; t < (xc[b]+31)/32; t++) steps += __builtin_popcount(gx[(size_t) b*(c.capX/32) + t]);
     }
-    stats[0] = nb; stats[1] = entries; stats[2] = tiles; stats[3] = tiles*1024; stats[4] = xentries;
+    stats[0] = nb; stats[1] = entries; stats[2] = tiles; stats[3] = steps*32; stats[4] = xentries;
     stats[5] = c.capJ; stats[6] = c.geom.nCols; stats[7] = c.geom.nBins;
     return NBS_OK;
 }

@@ -31,13 +31,15 @@ constexpr double kOne4PiEps0 = 1/(4*kPi*kEpsilon0);
 constexpr int MAX_SUBSETS = 8;
 constexpr int MAX_SLICES = MAX_SUBSETS*(MAX_SUBSETS+1)/2;
 constexpr int PME_ORDER = 5;
-// table of f(s) = erfc(alpha sqrt(s))/sqrt(s): interval index = (bits of (float) s >> 15) - ERFC_TAB_BASE, i.e. 256
-// intervals per octave starting at s = 2^-7; a row is {offset, a4, a3, a2, a1, a0} (48 bytes: three 16-byte loads) with
-// f(s) ~ sum a_k d^k, d = s*2^(9-e) + offset in [-1, 1], e = exponent of (float) s
-constexpr int ERFC_TAB_PER_OCTAVE_LOG2 = 8;
+// Table of f(s) = erfc(alpha sqrt(s))/sqrt(s), s = r^2, for the double-precision pair energies: 16 intervals per octave
+// of s starting at s = 2^-7 (interval index = (bits of (float) s >> 19) - ERFC_TAB_BASE), one degree-7 polynomial in
+// d = s 2^(5-e) - (33 + 2 m) in [-1, 1] per interval (e = exponent of s, m = interval inside the octave; relative
+// error 5e-12).  Stored coefficient-major (tab[k][row], a7 first) so that a warp's gather of one coefficient from
+// shared memory hits distinct banks for the rows of an octave; ERFC_TAB_MAX_ROWS rows fit the pair kernel's copy.
+constexpr int ERFC_TAB_PER_OCTAVE_LOG2 = 4;
 constexpr int ERFC_TAB_BASE = (127 - 7) << ERFC_TAB_PER_OCTAVE_LOG2;
-constexpr int ERFC_TAB_ROW = 6;
-constexpr int ERFC_TAB_DEGREE = 4;
+constexpr int ERFC_TAB_DEGREE = 7;
+constexpr int ERFC_TAB_MAX_ROWS = 256;           // up to s = 2^9 nm^2
 // A list entry is (image code << J_SHIFT_BITS) | sorted index; image code = (kx+2) + 5 ((ky+1) + 3 (kz+1)) with
 // kx in -2..2 (a triclinic box's b and c vectors shift x by up to ax/2 each), ky, kz in -1..1: 45 codes, 6 bits.
 constexpr int J_SHIFT_BITS = 25;                 // sorted index in the low 25 bits of a list entry
@@ -145,6 +147,7 @@ struct Context {
     Buf<double> dPosIn;                      // staged positions when the caller's are on the host
     Buf<double> dForceOut;                   // staged forces when the caller's are on the host
     Buf<uint4> dFix;                         // original order: fixed-point xyz, w = bin
+    Buf<uint4> dFixBuild;                    // sorted order: coordinates at the last list build (re-used lists measure displacements from them)
     Buf<int> dBinCount, dBinStart, dBinCursor;
     Buf<int> dScanTmp;
     Buf<int> dSortedToOrig, dOrigToSorted;
@@ -156,19 +159,22 @@ struct Context {
     Buf<uint4> dBlkLo, dBlkHi;               // fixed-point bounding box; lo.w = column index
     Buf<int2> dExclRange;                    // per sorted atom: [min, max] sorted index of its exclusion partners
     Buf<int> dJList, dJCount, dXList, dXCount;
+    Buf<unsigned> dGmJ, dGmX;                // cluster masks of the list entries' groups of 8: one word per tile of 32 entries
     Buf<int4> dItems;                        // pair-kernel work items (local block, first tile, first atom, atom count)
     Buf<unsigned> dXMask;
     Buf<int> dCounters;                      // [0] nBlocks, [1] overflow flag, [2] pair work items, [3] work cursor
     Buf<unsigned long long> dForce;          // [3][Npad] in sorted order (+ [3][Npad] in particle order: unsorted-PME gather)
     Buf<double> dEnergy;                     // [MAX_SLICES][2]
     Buf<double> dGrid;                       // charge grid [nS][nx][ny][nz] (double or float view)
+    Buf<unsigned long long> dGridFixed;      // NBS_FLAG_DETERMINISTIC: fixed-point accumulation grid of the spreading
     Buf<double2> dGridC;                     // half spectrum [nS][nx][ny][nz/2+1] (double2 or float2 view)
     Buf<float> dPot;                         // potential grid read by the gather
     Buf<float> dEterm;
     Buf<double> dEtermD;
     Buf<double2> dTwiddleD;
     Buf<double> dModuli;                     // [nx+ny+nz]
-    Buf<double> dErfcTab;                    // see ERFC_TAB_ROW
+    Buf<double> dErfcTab;                    // [ERFC_TAB_DEGREE + 1][erfcRows], see ERFC_TAB_*
+    int erfcRows = 0;
     Buf<float2> dTwiddle;                    // [nx+ny+nz]
     // LJPME keeps a second set of the tables that depend on (alpha, grid)
     Buf<float> dEtermDisp; Buf<double> dEtermDDisp, dModuliDisp; Buf<double2> dTwiddleDDisp; Buf<float2> dTwiddleDisp;
@@ -207,6 +213,18 @@ struct Context {
     int maxLocalBlocks = 0;
     bool pmeUnsorted = false;                // PME works from particle-order coordinates (forks before the sort)
     int chunkTiles = 2;                      // tiles per pair-kernel work item
+    // ---- neighbour-list re-use (periodic cutoff methods): the list is built with cutoff + skin and kept until an
+    // atom has moved more than skin/2 since the build (checked on the device, acted upon by the host) ----
+    double skin = 0;                         // nm; 0 = rebuild on every evaluation, like the Reference platform
+    bool listValid = false;                  // sort order (+ lists, if listHasDirect) of a previous evaluation can be re-used
+    bool listHasDirect = false;
+    double listBox[9] = {0};
+    unsigned long long listEpoch = 0, listEpochAtBuild = 0;     // bumped by anything that invalidates the list
+    unsigned long long listAllocEpoch = 0;
+    int listCapJ = 0;
+    bool reuseNow = false, forceRebuild = false;
+    double dispLast = 0, dispStepMax = 0;    // nm: max displacement at the last evaluation; largest growth per evaluation seen
+    long long evalCount = 0, buildCount = 0, redoCount = 0;
     int numSMs = 148;
     // ---- phase state of the evaluation in flight ----
     cudaStream_t ownStream = nullptr;        // used when the caller passes the legacy default stream
@@ -220,9 +238,10 @@ struct Context {
     const double* phasePos64 = nullptr;
     int phase = 0;                           // 0 idle, 1 begun, 2 convolved
     // ---- CUDA graph of a whole single-rank evaluation (replayed while nothing it depends on changes) ----
-    cudaGraphExec_t graphExec = nullptr;
-    unsigned long long graphKey = 0, warmKey = 0, paramVersion = 0;
-    long long graphLaunches = 0;             // kernels per graph replay (for the launch counter)
+    // (two cached graphs: slot 0 = evaluations that build the list, slot 1 = evaluations that re-use it)
+    cudaGraphExec_t graphExecs[2] = {nullptr, nullptr};
+    unsigned long long graphKeys[2] = {0, 0}, warmKeys[2] = {0, 0}, paramVersion = 0;
+    long long graphLaunchCounts[2] = {0, 0}; // kernels per graph replay (for the launch counter)
 };
 
 constexpr int ENERGY_WORDS = 2*MAX_SLICES + 8;   // slice table + [2*MAX_SLICES] = list-overflow flag (as a double, so it all-reduces)
@@ -237,6 +256,7 @@ struct PosInput { const void* ptr; int format; const int* atomIndex; double* pos
 int launchBBox(Context& c, const PosInput& in, float out[6]);    // bounding box of device positions (synchronises)
 int launchPrep(Context& c, const PosInput& in);                 // fixed-point conversion, bin histogram
 int launchSortRest(Context& c);                                 // cell sort, sorted records, i-blocks
+int launchReprep(Context& c, const PosInput& in);               // re-used list: new coordinates into the old sort order
 int launchBuildLists(Context& c);
 int launchExclRange(Context& c);
 int launchPairs(Context& c, bool wantEnergy, int mode);         // mode 0: forces+energy, 1: count/hash pairs, 2: dump pairs

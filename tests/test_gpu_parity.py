@@ -563,19 +563,126 @@ def test_errors_mirror_reference(nbs, platform):
         force.getPMEParametersInContext(context)
 
 
-def test_repeatable_forces(nbs, platform, systems):
-    """testDeterministicForces (platforms/cuda/tests/TestCudaSlicedNonbondedForce.cpp:109-141): direct-space
-    forces are accumulated in 64-bit fixed point, so repeated evaluations are bit-identical."""
+def test_deterministic_forces(nbs, systems):
+    """testDeterministicForces (platforms/cuda/tests/TestCudaSlicedNonbondedForce.cpp:109-141) in the reference's own
+    shape: FULL PME in the triclinic box (6,0,0), (2.1,6,0), (-1.5,-0.5,6), 1,000 charges of +-1 at random positions,
+    the platform's deterministic-forces property set -- two evaluations must agree bit for bit.  Direct space always
+    does (64-bit fixed-point accumulators, fixed summation order); reciprocal space does because
+    NBS_FLAG_DETERMINISTIC makes the charge spreading accumulate in 64-bit fixed point (pme.cc:108-109, 124-134).
+    Without the flag the spreading uses floating-point atomics, whose order -- and rounding -- varies from run to
+    run: expected, documented, and checked here only to stay within the parity tolerance."""
+    rng = np.random.default_rng(0)
+    n = 1000
+    system = nbs.System()
+    system.setDefaultPeriodicBoxVectors([6, 0, 0], [2.1, 6, 0], [-1.5, -0.5, 6])
+    force = nbs.SlicedNonbondedForce(1)
+    force.setNonbondedMethod(force.PME)
+    for i in range(n):
+        system.addParticle(1.0)
+        force.addParticle(1.0 if i % 2 == 0 else -1.0, 1.0, 0.0)
+    system.addForce(force)
+    positions = (rng.random((n, 3)) - 0.5)*6
+    box = np.array([[6, 0, 0], [2.1, 6, 0], [-1.5, -0.5, 6]], dtype=float)
+    lam = np.ones((1, 2))
+    for energies in (False, True):                      # fp32 grids (forces only) and fp64 grids
+        kernel = nbs.B200CalcSlicedNonbondedForceKernel(nbs.Platform(flags=nbs.abi.NBS_FLAG_DETERMINISTIC))
+        kernel.initialize(system, force)
+        out = []
+        for _ in range(4):
+            f = np.zeros((n, 3))
+            if energies:
+                kernel._evaluate(positions, box, lam, np.zeros(0), True, True, f)
+            else:
+                import torch
+                pos = torch.tensor(positions, dtype=torch.float64, device="cuda")
+                fd = torch.zeros((n, 3), dtype=torch.float64, device="cuda")
+                kernel.execute_device(pos.data_ptr(), box, fd.data_ptr(), lam, want_energies=False)
+                torch.cuda.synchronize()
+                f = fd.cpu().numpy()
+            out.append(f)
+        for f in out[1:]:
+            assert np.array_equal(out[0], f)
+    plain = nbs.B200CalcSlicedNonbondedForceKernel(nbs.Platform())
+    plain.initialize(system, force)
+    f = np.zeros((n, 3))
+    plain._evaluate(positions, box, lam, np.zeros(0), True, True, f)
+    assert force_rel_rms(f, out[0]) < 1e-6
+
+
+@pytest.mark.parametrize("name,step", [("C2", 0.004), ("C2", 0.02), ("T1_pme", 0.006), ("C1", 0.01)])
+def test_list_reuse_matches_rebuild(nbs, platform, systems, name, step):
+    """A neighbour list built with a skin and re-used while atoms move (what the plugin's CUDA platform inherits
+    from OpenMM, CommonNonbondedSlicingKernels.cpp:721) must never change a result: along a ballistic trajectory
+    (every atom has its own velocity, `step` nm per evaluation for the fastest ones; atoms cross the periodic
+    boundaries, of a triclinic box too) the interacting-pair set is IDENTICAL (count + hash) to that of a context that
+    rebuilds its list on every evaluation, forces agree to 1e-5 (single-precision rounding in a different summation order; the last step is also held to the oracle), slice energies to 1e-9 -- including the evaluations
+    that find the displacement limit exceeded and are redone with a fresh list."""
+    s = systems.make_variant(name) if name in systems.VARIANTS else systems.make_system(name)
+    n = s.force.getNumParticles()
+    rng = np.random.default_rng(17)
+    lam = rng.uniform(0.3, 1.0, size=(s.force.getNumSlices(), 2))
+    velocity = rng.normal(size=(n, 3))
+    velocity *= step/np.abs(velocity).max()
+    reuse = nbs.B200CalcSlicedNonbondedForceKernel(platform)
+    reuse.initialize(s.system, s.force)
+    fresh = nbs.B200CalcSlicedNonbondedForceKernel(nbs.Platform(flags=nbs.abi.NBS_FLAG_NO_LIST_REUSE))
+    fresh.initialize(s.system, s.force)
+    gv = np.full(max(s.force.getNumGlobalParameters(), 1), 0.45) if name in systems.VARIANTS else np.zeros(0)
+    steps = 50
+    for t in range(steps):
+        pos = s.positions + t*velocity
+        fa, fb = np.zeros((n, 3)), np.zeros((n, 3))
+        ea = reuse._evaluate(pos, s.box, lam, gv, True, True, fa)
+        eb = fresh._evaluate(pos, s.box, lam, gv, True, True, fb)
+        assert reuse.getPairSet(with_pairs=False)[:2] == fresh.getPairSet(with_pairs=False)[:2], t
+        assert force_rel_rms(fa, fb) < 1e-5, t        # fp32 pair forces summed in a different order (the lists differ)
+        assert np.allclose(ea, eb, rtol=1e-9, atol=1e-7), t
+    from oracle import oracle as cpu
+    r = cpu.evaluate(reuse.desc, pos, s.box, lam, gv if len(gv) else None, True, True, kind="port")
+    assert force_rel_rms(fa, r.forces) <= F_TOL and (r.pair_count, r.pair_hash) == reuse.getPairSet(with_pairs=False)[:2]
+    check_energies(ea, r.slice_energies)
+    stats, stats_fresh = reuse.getListStats(), fresh.getListStats()
+    assert stats_fresh["builds"] == steps and stats_fresh["redone"] == 0
+    assert stats["builds"] < steps/2, stats                      # the list really was re-used ...
+    assert stats["builds"] >= 2, stats                           # ... and really was rebuilt when atoms had moved
+    assert stats["evaluations"] == steps + stats["redone"], stats
+
+
+def test_list_reuse_survives_jumps_and_parameter_changes(nbs, platform, systems, oracle):
+    """Things that silently invalidate a kept list: positions replaced wholesale (detected on the device by the
+    displacement check), a new box, updated parameters, a changed offset parameter.  Each evaluation against the oracle."""
     s = systems.make_system("C2")
+    n = s.force.getNumParticles()
+    lam = np.random.default_rng(2).uniform(0.3, 1.0, size=(s.force.getNumSlices(), 2))
     kernel = nbs.B200CalcSlicedNonbondedForceKernel(platform)
     kernel.initialize(s.system, s.force)
-    lam = np.ones((s.force.getNumSlices(), 2))
-    out = []
-    for _ in range(3):
-        f = np.zeros((s.force.getNumParticles(), 3))
-        kernel._evaluate(s.positions, s.box, lam, np.zeros(0), True, False, f)
-        out.append(f)
-    assert np.array_equal(out[0], out[1]) and np.array_equal(out[0], out[2])
+    rng = np.random.default_rng(3)
+
+    def check(pos, box):
+        f = np.zeros((n, 3))
+        e = kernel._evaluate(pos, box, lam, np.zeros(0), True, True, f)
+        r = oracle.evaluate(kernel.desc, pos, box, lam, None, True, True, kind="port")
+        assert force_rel_rms(f, r.forces) <= F_TOL
+        check_energies(e, r.slice_energies)
+        assert kernel.getPairSet(with_pairs=False)[:2] == (r.pair_count, r.pair_hash)
+    check(s.positions, s.box)
+    check(s.positions + rng.normal(scale=0.003, size=(n, 3)), s.box)          # small move: re-use
+    assert kernel.getListStats()["reused_last"]
+    shuffled = s.positions.copy()
+    waters = shuffled[30:].reshape(-1, 3, 3)
+    waters[[5, 900]] = waters[[900, 5]] + 0.0                                  # two molecules trade places: a jump
+    check(shuffled, s.box)
+    assert kernel.getListStats()["redone"] == 1
+    check(shuffled*1.004, s.box*1.004)                                          # new box: fresh list, no redo
+    assert kernel.getListStats()["redone"] == 1 and not kernel.getListStats()["reused_last"]
+    check(shuffled*1.004, s.box*1.004)
+    assert kernel.getListStats()["reused_last"]
+    q, sig, eps = s.force.getParticleParameters(3)
+    s.force.setParticleParameters(3, q + 0.1, sig*1.05, eps*0.9)
+    kernel.desc = nbs.build_desc(s.system, s.force, **kernel._desc_options())
+    kernel._update()                                                            # copyParametersToContext
+    check(shuffled*1.004, s.box*1.004)
+    assert not kernel.getListStats()["reused_last"]
 
 
 def test_graph_replay_survives_box_change(nbs, platform, systems):
@@ -608,6 +715,41 @@ def test_graph_replay_survives_box_change(nbs, platform, systems):
         assert force_rel_rms(results[k][1], ref_a[1]) < 1e-6, k
     assert np.allclose(results[3][0], ref_b[0], rtol=1e-9, atol=1e-7)
     assert not np.allclose(ref_a[0], ref_b[0], rtol=1e-6)
+
+
+def c5_fixture_errors(golden, forces, energies, tag="full"):
+    """Parity figures of a C5 evaluation against tests/golden/C5_reference.npz (the reference's own full-size CPU
+    evaluation, oracle/make_golden_c5.py): relative RMS force error over the fixture's 4,096-atom sample, relative
+    error of sum |F|^2 over all atoms, worst slice-energy error over max(|E|, 1)."""
+    idx = golden["sample"]
+    ref = golden[f"{tag}_forces_sample"]
+    f_err = float(np.sqrt(((forces[idx]-ref)**2).sum()/(ref**2).sum()))
+    sumsq_err = float(abs((forces**2).sum()/golden[f"{tag}_force_sumsq"][0] - 1.0))
+    ref_e = golden[f"{tag}_energies"]
+    e_err = float(np.max(np.abs(energies-ref_e)/np.maximum(np.abs(ref_e), 1.0)))
+    return f_err, sumsq_err, e_err
+
+
+def test_stmv_size_vs_reference_fixture(nbs, platform, systems):
+    """C5 (1,066,628 atoms, 2 subsets, PME 180^3) against the reference's own full-size evaluation: slice energies of
+    the full / direct-only / reciprocal-only evaluations, the interacting-pair count and hash (234 M pairs), forces
+    of a fixed 4,096-atom sample and sum |F|^2 over all atoms."""
+    g = np.load(os.path.join(GOLDEN, "C5_reference.npz"))
+    s = systems.make_system("C5")
+    assert np.allclose([s.positions.sum(), (s.positions**2).sum()], g["positions_checksum"], rtol=1e-13)
+    n = s.force.getNumParticles()
+    kernel = nbs.B200CalcSlicedNonbondedForceKernel(platform)
+    kernel.initialize(s.system, s.force)
+    for tag, (direct, recip) in {"full": (True, True), "direct": (True, False), "recip": (False, True)}.items():
+        f = np.zeros((n, 3))
+        e = kernel._evaluate(s.positions, s.box, g["lambdas"], np.zeros(0), direct, recip, f)
+        f_err, sumsq_err, e_err = c5_fixture_errors(g, f, e, tag)
+        assert f_err <= F_TOL, (tag, f_err)
+        assert sumsq_err <= 2*F_TOL, (tag, sumsq_err)
+        assert e_err <= E_TOL, (tag, e_err)
+        if direct:
+            count, h, _ = kernel.getPairSet(with_pairs=False)
+            assert (count, h) == (int(g["pair_count"][0]), int(g["pair_hash"][0]))
 
 
 def test_stmv_size_properties(nbs, platform, systems):

@@ -51,6 +51,7 @@ struct PairArgs {
     int nE;                                     // 2 * number of slices
     float sx, sy, sz;
     double dsx, dsy, dsz;
+    double ds2;                                 // dsx^2 when the three units are equal (cubic box: r^2 in integer arithmetic)
     float rc2, alpha, krf, crf;
     float rswitch, rcut;
     int useSwitch;
@@ -78,21 +79,12 @@ struct __align__(16) WarpScratch {
     float4 iPos[32];      // i-block: position relative to the block corner, charge*sqrt(K)
     float4 iPar[32];      // sigma/2, 2 sqrt(eps), subset * MAX_SUBSETS, particle index
     float4 jPos[32];      // current tile
-    float4 jPar[32];
-    // Everything the exact (integer-coordinate) paths gather by slot number -- the double-precision energy passes
-    // and the borderline cutoff test -- is stored one 32-bit word per array: 32 words are 32 banks, so a warp's
-    // gather with arbitrary slot numbers is conflict-free whatever the pattern.
-    unsigned iX[32], iY[32], iZ[32];      // exact fixed-point coordinates
-    unsigned jX[32], jY[32], jZ[32];
-    unsigned iQlo[32], iQhi[32];          // charge * sqrt(K) in double
-    unsigned jQlo[32], jQhi[32];
-    float iSig[32], iEps[32];
-    float jSig[32], jEps[32];
-    // i forces of the work item: cluster c's partial sums of lane l (= 4 jl + il: i atom 4 c + il, as seen by the
-    // lane's j slots) -- one private word per (cluster, lane), so the read-modify-write of a step needs no atomics
-    float fiX[8][32], fiY[8][32], fiZ[8][32];
+    float4 jPar[32];      // sigma/2, 2 sqrt(eps), subset, particle index
+    // exact fixed-point coordinates and double-precision charges (charge * sqrt(K)), one 32-bit word per array:
+    // 32 words are 32 banks, so any gather by slot number is conflict-free
+    unsigned iX[32], iY[32], iZ[32], iQlo[32], iQhi[32];
+    unsigned jX[32], jY[32], jZ[32], jQlo[32], jQhi[32];
     unsigned jMask[32];   // exclusion-list tiles: bit l set = pair (i lane l, this j) is masked
-    unsigned short queue[1024 + 32];      // the tile's in-cutoff pairs: subset_i << 13 | subset_j << 10 | i slot << 5 | j slot
 };
 
 __device__ __forceinline__ float rsqrtFast(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -117,8 +109,6 @@ __device__ __forceinline__ float erfcxPoly(float t) {
 
 // erfc(x)*exp(x^2), x in [0, 6], in double: degree-14 polynomial in u = (8 t - 5)/3, t = 1/(1 + x/2);
 // relative error 1e-11 (fit against scipy.special.erfcx).
-// (coefficients live in constant memory: a 64-bit literal costs two uniform moves per use, a constant-bank
-// operand costs nothing)
 __constant__ double kErfcxD[15] = {
     6.52049290501760624e-09, 5.91610931414778049e-08, -2.22270786854985114e-07, -2.43147204892178188e-07,
     2.86160851006960621e-06, -4.29950666125027918e-06, -2.27129828446940741e-05, 1.00552837184801405e-04,
@@ -131,116 +121,42 @@ __constant__ double kExpD[12] = {
 __constant__ double kMiscD[6] = {2.6666666666666665, -1.6666666666666667, 1.4426950408889634074, 6755399441055744.0,
                                  -0.693147180559945286, -2.31904681384629956e-17};
 
-__device__ __forceinline__ double erfcxPolyD(double t) {
-    const double u = fma(t, kMiscD[0], kMiscD[1]);
+// erfc(alpha r)/r in double WITHOUT the table, for the pairs the table does not cover (closer than 0.088 nm -- none
+// in a physical system -- or beyond its last row): rsqrt + Newton, exp(-x^2) as 2^n e^h with a degree-11 Taylor
+// polynomial, erfcx as a degree-14 polynomial.  Out of line: it is never on the hot path.
+__device__ __noinline__ double erfcOverRAnalytic(double r2, double alphaD) {
+    double y = (double) rsqrtFast((float) r2);
+    y = y*fma(-0.5*r2*y, y, 1.5);
+    y = y*fma(-0.5*r2*y, y, 1.5);
+    const double x = alphaD*r2*y;
+    const double dd = fma(0.5, x, 1.0);
+    double t = (double) rcpFast((float) dd);
+    t = t*fma(-dd, t, 2.0);
+    t = t*fma(-dd, t, 2.0);
+    const double z = x*x;
+    const double u = -z*kMiscD[2];                              // log2(e)
+    const double n = (u + kMiscD[3]) - kMiscD[3];               // 1.5 * 2^52: rounds to the nearest integer
+    const double h = fma(n, kMiscD[5], fma(n, kMiscD[4], -z));  // -z - n ln2, ln2 in two parts
+    double e = kExpD[0];
+#pragma unroll
+    for (int k = 1; k < 12; k++) e = fma(e, h, kExpD[k]);
+    e = __hiloint2double(__double2hiint(e) + ((int) n << 20), __double2loint(e));
+    const double v = fma(t, kMiscD[0], kMiscD[1]);
     double p = kErfcxD[0];
 #pragma unroll
-    for (int k = 1; k < 15; k++) p = fma(p, u, kErfcxD[k]);
-    return p;
-}
-
-// exp(-z) for z in [0, 60], double, ~3e-16 relative: 2^n * e^h with a degree-11 Taylor polynomial on
-// |h| <= ln(2)/2 -- the library exp() minus the special cases this kernel cannot hit.
-__device__ __forceinline__ double expNegD(double z) {
-    const double u = -z*kMiscD[2];                              // log2(e)
-    const double shifter = kMiscD[3];                           // 1.5 * 2^52: rounds to nearest integer
-    const double n = (u + shifter) - shifter;
-    const double g = fma(n, kMiscD[4], -z);                     // -z - n ln2 (hi part of ln2)
-    const double h = fma(n, kMiscD[5], g);                      // ... lo part
-    double p = kExpD[0];                                        // 1/11! ... Taylor coefficients of exp
-#pragma unroll
-    for (int k = 1; k < 12; k++) p = fma(p, h, kExpD[k]);
-    const int ni = (int) n;
-    return __hiloint2double(__double2hiint(p) + (ni << 20), __double2loint(p));
-}
-
-// Energy of one pair from the exact fixed-point coordinates (the wrapped integer difference IS the
-// minimum image for any pair inside the cutoff).  Formulas: ReferenceSlicedLJCoulombIxn.cpp:376-396, 443-444
-// (PME) and :598-624 (reaction field), switch :380-384, 428-431.
-//   * Coulomb, PME: K q_i q_j erfc(alpha r)/r in DOUBLE.  Double-precision instructions are ~8x more
-//     expensive to issue than fp32 ones here, so instead of rsqrt + exp + erfcx (about 45 of them) the
-//     function f(s) = erfc(alpha sqrt(s))/sqrt(s), s = r^2, comes from a table of degree-4 polynomials
-//     on 256 intervals per octave of s (built on the host from libm's erfc: relative error ~1e-11;
-//     csrc/nbs_api.cu buildErfcTable) -- three 16-byte loads and 5 fused multiply-adds.  Pairs closer than
-//     2^-3.5 nm (0.088 nm: none in a physical system) take the analytic path.
-//   * Lennard-Jones: fp32 from the same exact r^2 (terms of one sign dominate a slice's vdW sum, so 1e-7
-//     per term is far inside the 1e-5 target), accumulated in double.
-//   * LJPME (CMODE 2, :398-426): the multiplicative C6 term that the dispersion grid carries is taken out in real
-//     space, plus the potential shift at the cutoff; fp32 like the rest of the LJ energy.
-// CMODE: 0 = reaction field / no cutoff, 1 = PME or Ewald, 2 = LJPME.
-template <int CMODE>
-__device__ __forceinline__ void pairEnergyD(unsigned ix, unsigned iy, unsigned iz, unsigned jx, unsigned jy, unsigned jz,
-                                            double qi, double qj, float sigi, float sigj, float epsi, float epsj,
-                                            const PairArgs& a, const double* tab, int tabRows, double& ec, double& ev) {
-    constexpr bool IS_PME = CMODE != 0;
-    const double dx = (double) (int) (jx - ix)*a.dsx;
-    const double dy = (double) (int) (jy - iy)*a.dsy;
-    const double dz = (double) (int) (jz - iz)*a.dsz;
-    const double r2 = dx*dx + dy*dy + dz*dz;
-    const float r2f = (float) r2;
-    float yf = rsqrtFast(r2f);
-    yf = yf*fmaf(-0.5f*r2f*yf, yf, 1.5f);              // fp32 Newton step: ~1e-7
-    {
-        float s2 = (sigi + sigj)*yf;
-        s2 *= s2;
-        const float s6 = s2*s2*s2;
-        float evf = epsi*epsj*(s6 - 1.f)*s6;
-        if (CMODE == 2) {
-            const float sg = sigi*sigj;
-            const float c6 = 64.f*sg*sg*sg*epsi*epsj;                  // c6_i c6_j, c6 = 8 (sigma/2)^3 (2 sqrt(eps))
-            const float dar2 = a.dalpha2*r2f;
-            const float y2 = yf*yf;
-            const float emult = c6*y2*y2*y2*(1.f - ex2Fast(-1.4426950408889634f*dar2)*fmaf(dar2, fmaf(0.5f, dar2, 1.f), 1.f));
-            float sc = sigi + sigj;
-            sc *= sc;
-            const float sc6 = sc*sc*sc*a.invCut6;
-            evf += emult + epsi*epsj*(1.f - sc6)*sc6 - c6*a.shiftMult;
-        }
-        if (a.useSwitch) {
-            const float r = r2f*yf;
-            if (r > a.rswitch) {
-                const float u = (r - a.rswitch)/(a.rcut - a.rswitch);
-                evf *= 1.f + u*u*u*(-10.f + u*(15.f - u*6.f));
-            }
-        }
-        ev = (double) evf;
-    }
-    const double qq = qi*qj;
-    if (IS_PME) {
-        const unsigned bits = __float_as_uint(r2f);
-        const int idx = (int) (bits >> (23 - ERFC_TAB_PER_OCTAVE_LOG2)) - ERFC_TAB_BASE;
-        if (idx >= 0 && idx < tabRows) {
-            // d = s 2^(5-e) - (33 + 2 m): position inside the interval, [-1, 1]; the power of two goes straight into
-            // the exponent field (e = unbiased exponent of r2f), 33 + 2 m = 2 (16 + m) + 1 from the index bits
-            const double scale = __hiloint2double((1023 + 1 + ERFC_TAB_PER_OCTAVE_LOG2 + 127 - (int) (bits >> 23)) << 20, 0);
-            const int m2 = 2*(int) ((bits >> (23 - ERFC_TAB_PER_OCTAVE_LOG2)) & ((1u << ERFC_TAB_PER_OCTAVE_LOG2) - 1u)) + (2 << ERFC_TAB_PER_OCTAVE_LOG2) + 1;
-            const double d = fma(r2, scale, -(double) m2);
-            double p = tab[idx];
-#pragma unroll
-            for (int k = 1; k <= ERFC_TAB_DEGREE; k++) p = fma(p, d, tab[k*ERFC_TAB_MAX_ROWS + idx]);
-            ec = qq*p;
-        }
-        else {
-            double y = (double) yf;
-            y = y*fma(-0.5*r2*y, y, 1.5);               // double Newton step: ~1e-14
-            const double x = a.alphaD*r2*y;
-            const double dd = fma(0.5, x, 1.0);
-            double t = (double) rcpFast((float) dd);
-            t = t*fma(-dd, t, 2.0);
-            t = t*fma(-dd, t, 2.0);
-            ec = qq*y*expNegD(x*x)*erfcxPolyD(t);
-        }
-    }
-    else {
-        double y = (double) yf;
-        y = y*fma(-0.5*r2*y, y, 1.5);
-        ec = qq*(y + a.krfD*r2 - a.crfD);
-    }
+    for (int k = 1; k < 15; k++) p = fma(p, v, kErfcxD[k]);
+    return y*e*p;
 }
 
 // Exact cutoff test from the fixed-point coordinates (the wrapped integer difference is the minimum image
-// for any pair near the cutoff, because the box is at least twice the cutoff).
-__device__ __noinline__ bool exactInRange(unsigned ix, unsigned iy, unsigned iz, unsigned jx, unsigned jy, unsigned jz,
+// for any pair near the cutoff, because the box is at least twice the cutoff).  Out of line: only pairs whose
+// fp32 r^2 lands within 2e-5 nm^2 of the cutoff get here.
+#ifdef PAIR_EXACT_INLINE
+__device__ __forceinline__ bool exactInRange(
+#else
+__device__ __noinline__ bool exactInRange(
+#endif
+unsigned ix, unsigned iy, unsigned iz, unsigned jx, unsigned jy, unsigned jz,
                                           double dsx, double dsy, double dsz, double rc2d) {
     const double ex = (double) (int) (jx - ix)*dsx;
     const double ey = (double) (int) (jy - iy)*dsy;
@@ -265,40 +181,83 @@ __device__ __forceinline__ LatticeShift crossShift(int parz, const PairArgs& a) 
 // 4 GROUPS of 8 entries x up to 8 CLUSTERS of 4 i atoms: lane = 4*jl + il meets j slot 8*g + jl and i slot 4*c + il
 // in the step of (group g, cluster c), and the step only exists if the group's cluster mask (from the list
 // builder) has bit c -- a warp-uniform test.  The j forces of a group stay in registers over its cluster steps and
-// are reduced over the four il lanes once per group; the i forces accumulate in lane-private shared-memory words
-// (fiX/Y/Z[c][lane]) -- the cluster index is a run-time value, so ONE copy of the step serves all clusters (eight
-// unrolled copies with register accumulators overflowed the instruction cache: 27 % of the kernel's stall samples
-// were "no instruction", profiles/r02_ncu_k_pair_a_summary.txt).
+// are reduced over the four il lanes once per group; the i forces of all 8 clusters stay in registers (fi[c]) for
+// the whole work item.
+//
+// Energies are evaluated IN the step, for every lane, and counted for the lanes whose pair is inside the cutoff:
+//   * Coulomb (EMODE 2): K q_i q_j erfc(alpha r)/r in DOUBLE from the exact fixed-point coordinates -- slice energies
+//     are sums of 10^4..10^8 terms of both signs and single precision cannot deliver 1e-5 of a small net value
+//     (DESIGN.md "Precision").  r^2 is formed in 64-bit INTEGER arithmetic when the box is cubic (one conversion to
+//     double; conversions are the scarce resource: 0.45 warp instructions per clock and SM against 1.6 for DFMA,
+//     profiles/r02_peaks.json), f(s) = erfc(alpha sqrt(s))/sqrt(s) comes from the CTA's shared-memory table of
+//     degree-7 polynomials in s (16 intervals per octave; index and interval position straight from the bits of the
+//     double).  With the exact r^2 at hand the cutoff decision is exact too: no borderline branch.
+//   * Lennard-Jones: the step's fp32 value, summed in fp32 over a tile and in double across tiles.
+//   * a tile whose i atoms share one subset and whose j atoms share one subset -- almost all of them -- adds into two
+//     registers; mixed tiles go through the per-lane slice table in local memory.
 struct StepCtx {
     float rc2, alpha;
     float jx, jy, jz, jq, jsig, jeps;     // this lane's j atom of the current group
     int sj;                               // its subset
     unsigned jm;                          // its exclusion mask (exclusion-list tiles)
     int js;                               // its slot in the staged tile
-    unsigned qbits;                       // queue entry without the i part: subset_j << 10 | js (the i subset is added per step)
+    unsigned jxe, jye, jze;               // EMODE 2: its exact coordinates and double-precision charge
+    double jq64;
+    unsigned jOrig;                       // MODE 1/2: its particle index
     float fjx, fjy, fjz;
-    int qn;                               // pairs waiting in the energy / pair-set queue
+    // energy accumulators of the current tile
+    double ecTile;                        // EMODE 2, uniform tile
+    float ecTileF, evTile;                // EMODE 1 Coulomb; Lennard-Jones (both modes), uniform tile
+    bool uniform;                         // the tile's pairs all belong to one slice
+    unsigned long long nPairs, hPairs;    // MODE 1/2
 };
 
-template <int EMODE, int CMODE, int MODE>
-__device__ __forceinline__ void pairStep(WarpScratch& w, const PairArgs& a, const float2* shLam, int lane, int il, int c,
-                                         bool isX, StepCtx& s, double* acc) {
+template <int EMODE, int CMODE, int MODE, bool CUBIC, int C>
+__device__ __forceinline__ void pairStep(WarpScratch& w, const PairArgs& a, const float2* shLam, const double* tab, int lane, int il,
+                                         bool isX, StepCtx& s, float (&fi)[8][3], double* acc) {
     constexpr bool IS_PME = CMODE != 0;
     const float TWO_OVER_SQRT_PI = 1.1283791670955126f;
-    const int is = c*4 + il;
+    const int is = C*4 + il;
     const float4 ip = w.iPos[is];
     const float4 ipar = w.iPar[is];               // sigma/2, 2 sqrt(eps), subset * MAX_SUBSETS (int bits), particle index
     const float dx = ip.x - s.jx, dy = ip.y - s.jy, dz = ip.z - s.jz;
     const float r2 = fmaf(dx, dx, fmaf(dy, dy, dz*dz));
-    bool in = r2 <= s.rc2;
-    if (fabsf(r2 - s.rc2) < 2.0e-5f) in = exactInRange(w.iX[is], w.iY[is], w.iZ[is], w.jX[s.js], w.jY[s.js], w.jZ[s.js], a.dsx, a.dsy, a.dsz, a.rc2d);     // borderline: rare
-    if (isX) in = in && !((s.jm >> is) & 1u);
-    if (EMODE == 2 || MODE != 0) {
-        const unsigned m = __ballot_sync(FULL_MASK, in);
-        if (in) w.queue[s.qn + __popc(m & ((1u << lane) - 1u))] = (unsigned short) (s.qbits | (is << 5) | ((unsigned) __float_as_int(ipar.z) << 10));
-        s.qn += __popc(m);
+    bool in;
+    double r2d = 0.0;
+    if (EMODE == 2 && MODE == 0) {
+        // exact r^2 (needed for the energy anyway) decides; the fp32 value only gates out the parked padding lanes
+        const int ex = (int) (s.jxe - w.iX[is]), ey = (int) (s.jye - w.iY[is]), ez = (int) (s.jze - w.iZ[is]);
+        if (CUBIC) {
+            const unsigned long long r2i = (unsigned long long) ((long long) ex*ex) + (unsigned long long) ((long long) ey*ey) +
+                                           (unsigned long long) ((long long) ez*ez);
+            r2d = __ull2double_rn(r2i)*a.ds2;
+        }
+        else {
+            const double fx = (double) ex*a.dsx, fy = (double) ey*a.dsy, fz = (double) ez*a.dsz;
+            r2d = fma(fx, fx, fma(fy, fy, fz*fz));
+        }
+        in = r2 < s.rc2 + 2.0e-5f && r2d <= a.rc2d;
     }
-    if (MODE != 0) return;
+    else {
+        in = r2 <= s.rc2;
+        if (fabsf(r2 - s.rc2) < 2.0e-5f)          // borderline: rare
+            in = exactInRange(w.iX[is], w.iY[is], w.iZ[is], w.jX[s.js], w.jY[s.js], w.jZ[s.js], a.dsx, a.dsy, a.dsz, a.rc2d);
+    }
+    if (isX) in = in && !((s.jm >> is) & 1u);
+    if (MODE != 0) {
+        // the interacting-pair set itself (parity diagnostics): count + hash (+ dump)
+        if (in) {
+            const unsigned oi = (unsigned) __float_as_int(ipar.w);
+            const unsigned f = min(oi, s.jOrig), sd = max(oi, s.jOrig);
+            s.nPairs++;
+            s.hPairs += pairHash(f, sd);
+            if (MODE == 2) {
+                const unsigned long long slot = atomicAdd(a.pairStats + 2, 1ull);
+                if ((long long) slot < a.dumpCapacity) a.pairDump[slot] = make_int2((int) f, (int) sd);
+            }
+        }
+        return;
+    }
     const float invR = rsqrtFast(r2);
     const float r = r2*invR;
     const float invR2 = invR*invR;
@@ -308,6 +267,19 @@ __device__ __forceinline__ void pairStep(WarpScratch& w, const PairArgs& a, cons
     const float eps = ipar.y*s.jeps;
     float ev = eps*(s6 - 1.f)*s6;
     float fv = eps*fmaf(12.f, s6, -6.f)*s6*invR2;
+    float invE2 = invR2;                          // 1/r^2 for the energy terms
+    if (EMODE == 2) {
+        // Lennard-Jones ENERGY from the exact r^2: one Newton step of 1/sqrt from the force path's value takes out
+        // both the approximation error of rsqrt and the ~6e-7 of the tile-relative fp32 coordinates (r^-12 would
+        // turn that into 4e-6 per close contact: visible in small slices such as protein-ligand)
+        const float r2e = (float) r2d;
+        const float invE = invR*fmaf(-0.5f*r2e*invR, invR, 1.5f);
+        invE2 = invE*invE;
+        float t2 = (ipar.x + s.jsig)*invE;
+        t2 *= t2;
+        const float t6 = t2*t2*t2;
+        ev = eps*(t6 - 1.f)*t6;
+    }
     const float qr = ip.w*s.jq*invR;
     float ec, fc;
     if (IS_PME) {
@@ -331,11 +303,11 @@ __device__ __forceinline__ void pairStep(WarpScratch& w, const PairArgs& a, cons
         const float p2 = fmaf(dar2, fmaf(0.5f, dar2, 1.f), 1.f);             // 1 + x + x^2/2
         const float c6r6 = c6*invR2*invR2*invR2;
         fv = fmaf(6.f*c6r6*invR2, 1.f - exd*fmaf(dar2*dar2*dar2, 1.f/6.f, p2), fv);
-        if (EMODE == 1) {
+        if (EMODE != 0) {
             float sc = ipar.x + s.jsig;
             sc *= sc;
             const float sc6 = sc*sc*sc*a.invCut6;
-            ev += c6r6*(1.f - exd*p2) + eps*(1.f - sc6)*sc6 - c6*a.shiftMult;
+            ev += c6*invE2*invE2*invE2*(1.f - exd*p2) + eps*(1.f - sc6)*sc6 - c6*a.shiftMult;
         }
     }
     if (a.useSwitch) {                                            // warp-uniform
@@ -352,65 +324,55 @@ __device__ __forceinline__ void pairStep(WarpScratch& w, const PairArgs& a, cons
     const float2 lam = shLam[siOff + s.sj];
     float dEdR = fmaf(lam.y, fv, lam.x*fc);
     dEdR = in ? dEdR : 0.f;
-    w.fiX[c][lane] = fmaf(dEdR, dx, w.fiX[c][lane]);
-    w.fiY[c][lane] = fmaf(dEdR, dy, w.fiY[c][lane]);
-    w.fiZ[c][lane] = fmaf(dEdR, dz, w.fiZ[c][lane]);
+    fi[C][0] = fmaf(dEdR, dx, fi[C][0]); fi[C][1] = fmaf(dEdR, dy, fi[C][1]); fi[C][2] = fmaf(dEdR, dz, fi[C][2]);
     s.fjx = fmaf(-dEdR, dx, s.fjx); s.fjy = fmaf(-dEdR, dy, s.fjy); s.fjz = fmaf(-dEdR, dz, s.fjz);
-    if (EMODE == 1 && in) {
+    if (EMODE == 0) return;
+
+    // ---- energies ----
+    double ecd = 0.0;
+    if (EMODE == 2) {
+        const double qq = __hiloint2double((int) w.iQhi[is], (int) w.iQlo[is])*s.jq64;
+        if (IS_PME) {
+            // table row and position inside its interval from the bits of r^2: the exponent and the top four mantissa
+            // bits are the row; d = s 2^(5-e) - (33 + 2 m) in [-1, 1], both factors assembled as bit patterns
+            const int hi = __double2hiint(r2d);
+            const int idx = (hi >> (20 - ERFC_TAB_PER_OCTAVE_LOG2)) - ((1023 - 7) << ERFC_TAB_PER_OCTAVE_LOG2);
+            // (a pair beyond the table -- far outside the cutoff, or closer than 0.088 nm -- reads the nearest row; its
+            // value is only used, and then replaced by the analytic form, if the pair is inside the cutoff)
+            const int row = min(max(idx, 0), a.tabRows - 1);
+            const double scale = __hiloint2double((2046 + 1 + ERFC_TAB_PER_OCTAVE_LOG2 - ((hi >> 20) & 0x7ff)) << 20, 0);
+            const int m = (hi >> (20 - ERFC_TAB_PER_OCTAVE_LOG2)) & ((1 << ERFC_TAB_PER_OCTAVE_LOG2) - 1);
+            const double m2 = __hiloint2double(((1023 + 1 + ERFC_TAB_PER_OCTAVE_LOG2) << 20) | ((2*m + 1) << (20 - 1 - ERFC_TAB_PER_OCTAVE_LOG2)), 0);
+            const double d = fma(r2d, scale, -m2);
+            double p = tab[row];
+#pragma unroll
+            for (int k = 1; k <= ERFC_TAB_DEGREE; k++) p = fma(p, d, tab[k*ERFC_TAB_MAX_ROWS + row]);
+            if (in && row != idx) p = erfcOverRAnalytic(r2d, a.alphaD);           // rare
+            ecd = qq*p;
+        }
+        else {
+            double y = (double) invR;                              // reaction field (:598-624): 1/r + krf r^2 - crf
+            y = y*fma(-0.5*r2d*y, y, 1.5);
+            y = y*fma(-0.5*r2d*y, y, 1.5);
+            ecd = qq*(y + a.krfD*r2d - a.crfD);
+        }
+    }
+    if (s.uniform) {
+        if (EMODE == 2) s.ecTile += in ? ecd : 0.0;
+        else s.ecTileF += in ? ec : 0.f;
+        s.evTile += in ? ev : 0.f;
+    }
+    else if (in) {
         const int sl = triSlice(siOff/MAX_SUBSETS, s.sj);
-        acc[2*sl] += (double) ec;
+        acc[2*sl] += EMODE == 2 ? ecd : (double) ec;
         acc[2*sl+1] += (double) ev;
     }
 }
 
-// Double-precision energies of the queued (in-cutoff) pairs of the current tile, 32 real pairs per pass, two passes
-// in flight (their loads and dependent FMA chains interleave).  Operands are gathered word by word from the
-// conflict-free per-slot arrays; the erfc table is the CTA's shared-memory copy.  The common case -- every pair of a
-// pass in the same slice -- accumulates in two registers; the per-lane table in local memory is only touched when
-// the slice changes.
-template <int CMODE>
-__device__ __forceinline__ void energyPasses(const WarpScratch& w, const PairArgs& a, const double* tab, int lane, int count,
-                                             double* acc, int& curSl, double& regC, double& regV) {
-    for (int base = 0; base < count; base += 64) {
-        double ecd[2] = {0.0, 0.0}, evd[2] = {0.0, 0.0};
-        int sl[2] = {-1, -1};
-#pragma unroll
-        for (int u = 0; u < 2; u++) {
-            const int k = base + 32*u + lane;
-            if (k < count) {
-                const unsigned e = w.queue[k];
-                const int iq = (e >> 5) & 31, jq = e & 31;
-                const double qi = __hiloint2double((int) w.iQhi[iq], (int) w.iQlo[iq]);
-                const double qj = __hiloint2double((int) w.jQhi[jq], (int) w.jQlo[jq]);
-                pairEnergyD<CMODE>(w.iX[iq], w.iY[iq], w.iZ[iq], w.jX[jq], w.jY[jq], w.jZ[jq], qi, qj,
-                                   w.iSig[iq], w.jSig[jq], w.iEps[iq], w.jEps[jq], a, tab, a.tabRows, ecd[u], evd[u]);
-                sl[u] = triSlice((int) (e >> 13), (int) ((e >> 10) & 7u));
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 2; u++) {
-            const int lead = __shfl_sync(FULL_MASK, sl[u], 0);      // lane 0 is active whenever the pass has any pair
-            const bool uniform = __all_sync(FULL_MASK, sl[u] == lead || sl[u] < 0);
-            if (uniform) {
-                if (lead < 0) continue;
-                if (lead != curSl) {
-                    if (curSl >= 0) { acc[2*curSl] += regC; acc[2*curSl+1] += regV; }
-                    regC = 0.0; regV = 0.0; curSl = lead;
-                }
-                regC += ecd[u]; regV += evd[u];
-            }
-            else if (sl[u] >= 0) { acc[2*sl[u]] += ecd[u]; acc[2*sl[u]+1] += evd[u]; }
-        }
-    }
-}
-
-template <int EMODE, int CMODE, int MODE>
-__device__ __forceinline__ void tileLoop(WarpScratch& w, const PairArgs& a, const float2* shLam, int lane, unsigned gmWord, bool isX,
-                                         int jIndexMine, bool jValidMine, double* acc, int& qnOut) {
+template <int EMODE, int CMODE, int MODE, bool CUBIC>
+__device__ __forceinline__ void tileLoop(WarpScratch& w, const PairArgs& a, const float2* shLam, const double* tab, int lane, unsigned gmWord,
+                                         bool isX, int jIndexMine, bool jValidMine, StepCtx& s, float (&fi)[8][3], double* acc) {
     const int il = lane & 3, jl = lane >> 2;
-    StepCtx s;
-    s.rc2 = a.rc2; s.alpha = a.alpha;
-    s.qn = 0;
 #pragma unroll 1
     for (int g = 0; g < 4; g++) {
         const unsigned m = (gmWord >> (8*g)) & 0xffu;
@@ -422,12 +384,21 @@ __device__ __forceinline__ void tileLoop(WarpScratch& w, const PairArgs& a, cons
             s.jx = p.x; s.jy = p.y; s.jz = p.z; s.jq = p.w;
             s.jsig = pr.x; s.jeps = pr.y; s.sj = __float_as_int(pr.z);
             s.jm = isX ? w.jMask[s.js] : 0u;
-            s.qbits = ((unsigned) s.sj << 10) | (unsigned) s.js;
+            if (MODE != 0) s.jOrig = (unsigned) __float_as_int(pr.w);
+            if (EMODE == 2 && MODE == 0) {
+                s.jxe = w.jX[s.js]; s.jye = w.jY[s.js]; s.jze = w.jZ[s.js];
+                s.jq64 = __hiloint2double((int) w.jQhi[s.js], (int) w.jQlo[s.js]);
+            }
         }
         s.fjx = 0.f; s.fjy = 0.f; s.fjz = 0.f;
-#pragma unroll 1
-        for (unsigned mm = m; mm != 0u; mm &= mm - 1u)
-            pairStep<EMODE, CMODE, MODE>(w, a, shLam, lane, il, __ffs((int) mm) - 1, isX, s, acc);
+        if (m & 0x01u) pairStep<EMODE, CMODE, MODE, CUBIC, 0>(w, a, shLam, tab, lane, il, isX, s, fi, acc);
+        if (m & 0x02u) pairStep<EMODE, CMODE, MODE, CUBIC, 1>(w, a, shLam, tab, lane, il, isX, s, fi, acc);
+        if (m & 0x04u) pairStep<EMODE, CMODE, MODE, CUBIC, 2>(w, a, shLam, tab, lane, il, isX, s, fi, acc);
+        if (m & 0x08u) pairStep<EMODE, CMODE, MODE, CUBIC, 3>(w, a, shLam, tab, lane, il, isX, s, fi, acc);
+        if (m & 0x10u) pairStep<EMODE, CMODE, MODE, CUBIC, 4>(w, a, shLam, tab, lane, il, isX, s, fi, acc);
+        if (m & 0x20u) pairStep<EMODE, CMODE, MODE, CUBIC, 5>(w, a, shLam, tab, lane, il, isX, s, fi, acc);
+        if (m & 0x40u) pairStep<EMODE, CMODE, MODE, CUBIC, 6>(w, a, shLam, tab, lane, il, isX, s, fi, acc);
+        if (m & 0x80u) pairStep<EMODE, CMODE, MODE, CUBIC, 7>(w, a, shLam, tab, lane, il, isX, s, fi, acc);
         if (MODE == 0) {
             // j forces of the group: sum over the four il lanes (x and y share the first exchange: odd lanes end
             // up owning y, even lanes x), then lanes il = 0, 1, 2 add x, y, z to the 64-bit fixed-point accumulators
@@ -444,13 +415,13 @@ __device__ __forceinline__ void tileLoop(WarpScratch& w, const PairArgs& a, cons
             if (il < 3 && jValid && v != 0.f) atomicAdd(a.force + (size_t) il*a.Npad + jIndex, toFixed(v));
         }
     }
-    qnOut = s.qn;
 }
 
 // MODE 0: forces (+ energies per EMODE); MODE 1: count + hash the interacting pairs; MODE 2: also dump them.
-// EMODE 0: forces only; 1: single-precision energies; 2: double-precision energies.
+// EMODE 0: forces only; 1: single-precision energies; 2: double-precision Coulomb energies.
+// CUBIC: the three fixed-point units are equal (r^2 in integer arithmetic).
 // MINCTAS: resident CTAs per SM the register allocation is bounded for.
-template <int EMODE, int CMODE, int MODE, int MINCTAS>
+template <int EMODE, int CMODE, int MODE, bool CUBIC, int MINCTAS>
 __global__ void __launch_bounds__(PAIR_WARPS*32, MINCTAS) k_pair(const PairArgs a) {
     extern __shared__ __align__(16) unsigned char smemRaw[];
     __shared__ float2 shLam[MAX_SUBSETS*MAX_SUBSETS];      // (lambda_Coulomb, lambda_vdW) of subset pair (si, sj)
@@ -478,9 +449,13 @@ __global__ void __launch_bounds__(PAIR_WARPS*32, MINCTAS) k_pair(const PairArgs 
 #pragma unroll
         for (int k = 0; k < MAX_SLICES*2; k++) acc[k] = 0.0;
     }
-    int curSl = -1;                               // EMODE 2: slice whose energies currently accumulate in registers
+    int curSl = -1;                               // slice whose energies currently accumulate in registers
     double regC = 0.0, regV = 0.0;
-    unsigned long long nPairs = 0, hPairs = 0;
+    StepCtx s;
+    s.rc2 = a.rc2; s.alpha = a.alpha;
+    s.nPairs = 0; s.hPairs = 0;
+    s.ecTile = 0.0; s.ecTileF = 0.f; s.evTile = 0.f; s.uniform = false;
+    s.jm = 0u; s.jOrig = 0u; s.jxe = s.jye = s.jze = 0u; s.jq64 = 0.0;
 
     // Everything a warp needs from global memory is requested one step ahead of its use -- the next work
     // item's index while the current item runs, the next tile's atoms while the current tile runs, the list
@@ -541,16 +516,17 @@ __global__ void __launch_bounds__(PAIR_WARPS*32, MINCTAS) k_pair(const PairArgs 
         if (!iValid) xi = 1.0e8f;
         const float qi = iValid ? __uint_as_float(pi.w) : 0.f;
         const int si = __float_as_int(pari.z) & 7;
-        __syncwarp();
+        // do the i atoms share one subset?  (then a tile whose j atoms do too accumulates its energies in registers)
+        const int si0 = __shfl_sync(FULL_MASK, si, 0);
+        const bool iUniform = __all_sync(FULL_MASK, si == si0 || !iValid);
+        float fi[8][3];
 #pragma unroll
-        for (int c = 0; c < 8; c++) { w.fiX[c][lane] = 0.f; w.fiY[c][lane] = 0.f; w.fiZ[c][lane] = 0.f; }
+        for (int c = 0; c < 8; c++) { fi[c][0] = 0.f; fi[c][1] = 0.f; fi[c][2] = 0.f; }
+        __syncwarp();
         w.iPos[lane] = make_float4(xi, yi, zi, qi);
         w.iPar[lane] = make_float4(pari.x, pari.y, __int_as_float(si*MAX_SUBSETS), pari.w);
         w.iX[lane] = pi.x; w.iY[lane] = pi.y; w.iZ[lane] = pi.z;
-        if (EMODE == 2) {
-            w.iQlo[lane] = (unsigned) __double2loint(qi64); w.iQhi[lane] = (unsigned) __double2hiint(qi64);
-            w.iSig[lane] = pari.x; w.iEps[lane] = pari.y;
-        }
+        if (EMODE == 2) { w.iQlo[lane] = (unsigned) __double2loint(qi64); w.iQhi[lane] = (unsigned) __double2hiint(qi64); }
 
         for (int t = it.y; t < tEnd; t++) {
             const bool isX = t >= tJ;
@@ -579,14 +555,12 @@ __global__ void __launch_bounds__(PAIR_WARPS*32, MINCTAS) k_pair(const PairArgs 
                 // the displacement to this image for any pair inside the cutoff (<= half the box along every axis)
                 fjx_ = q.x + (unsigned) shx; fjy_ = q.y + (unsigned) shy; fjz_ = q.z;
             }
+            const int sjMine = __float_as_int(parj.z) & 7;
             __syncwarp();
             w.jPos[lane] = pj;
-            w.jPar[lane] = make_float4(parj.x, parj.y, __int_as_float(__float_as_int(parj.z) & 7), parj.w);
+            w.jPar[lane] = make_float4(parj.x, parj.y, __int_as_float(sjMine), parj.w);
             w.jX[lane] = fjx_; w.jY[lane] = fjy_; w.jZ[lane] = fjz_;
-            if (EMODE == 2) {
-                w.jQlo[lane] = (unsigned) __double2loint(q64Cur); w.jQhi[lane] = (unsigned) __double2hiint(q64Cur);
-                w.jSig[lane] = parj.x; w.jEps[lane] = parj.y;
-            }
+            if (EMODE == 2) { w.jQlo[lane] = (unsigned) __double2loint(q64Cur); w.jQhi[lane] = (unsigned) __double2hiint(q64Cur); }
             if (isX) w.jMask[lane] = maskCur;
             __syncwarp();
             // requests for the next tile (atoms) and the one after (list entry) go out before this tile's arithmetic
@@ -599,40 +573,34 @@ __global__ void __launch_bounds__(PAIR_WARPS*32, MINCTAS) k_pair(const PairArgs 
             }
             entryNext = loadEntry(t + 2, maskNext, gmNext);
 
-            int qn = 0;
-            tileLoop<EMODE, CMODE, MODE>(w, a, shLam, lane, gmWord, isX, jIndex, entry >= 0, acc, qn);
-            if (MODE != 0) {
-                // ---- the interacting-pair set itself (parity diagnostics): hash / dump what the loop queued ----
-                __syncwarp();
-                for (int base = 0; base < qn; base += 32) {
-                    if (base + lane < qn) {
-                        const unsigned e = w.queue[base + lane];
-                        const unsigned oi = (unsigned) __float_as_int(w.iPar[(e >> 5) & 31].w), oj = (unsigned) __float_as_int(w.jPar[e & 31].w);
-                        const unsigned f = min(oi, oj), sd = max(oi, oj);
-                        nPairs++;
-                        hPairs += pairHash(f, sd);
-                        if (MODE == 2) {
-                            unsigned long long slot = atomicAdd(a.pairStats + 2, 1ull);
-                            if ((long long) slot < a.dumpCapacity) a.pairDump[slot] = make_int2((int) f, (int) sd);
-                        }
+            if (EMODE != 0 && MODE == 0) {
+                // one slice for the whole tile?  (lane 0's entry of a tile is never padding)
+                const int sj0 = __shfl_sync(FULL_MASK, sjMine, 0);
+                s.uniform = iUniform && __all_sync(FULL_MASK, sjMine == sj0 || entry < 0);
+                if (s.uniform) {
+                    const int sl = triSlice(si0, sj0);
+                    if (sl != curSl) {
+                        if (curSl >= 0) { acc[2*curSl] += regC; acc[2*curSl+1] += regV; }
+                        regC = 0.0; regV = 0.0; curSl = sl;
                     }
                 }
+                s.ecTile = 0.0; s.ecTileF = 0.f; s.evTile = 0.f;
             }
-            else if (EMODE == 2) {                 // the queue refers to this tile's shared-memory slots
-                __syncwarp();
-                energyPasses<CMODE>(w, a, shTab, lane, qn, acc, curSl, regC, regV);
+            tileLoop<EMODE, CMODE, MODE, CUBIC>(w, a, shLam, shTab, lane, gmWord, isX, jIndex, entry >= 0, s, fi, acc);
+            if (EMODE != 0 && MODE == 0 && s.uniform) {
+                regC += EMODE == 2 ? s.ecTile : (double) s.ecTileF;
+                regV += (double) s.evTile;
             }
         }
         // i forces of this item: fi[c] summed over the eight jl lanes.  Three exchange stages, each halving the
         // number of clusters a lane still carries, leave lane 4 c + il with the total of cluster c, atom il --
         // i.e. lane l with the force on the block's atom l.
         if (MODE == 0) {
-            __syncwarp();
 #pragma unroll
             for (int d = 0; d < 3; d++) {
                 float v[8];
 #pragma unroll
-                for (int c = 0; c < 8; c++) v[c] = d == 0 ? w.fiX[c][lane] : (d == 1 ? w.fiY[c][lane] : w.fiZ[c][lane]);
+                for (int c = 0; c < 8; c++) v[c] = fi[c][d];
 #pragma unroll
                 for (int st = 2; st >= 0; st--) {
                     const int half = 1 << st;
@@ -651,7 +619,7 @@ __global__ void __launch_bounds__(PAIR_WARPS*32, MINCTAS) k_pair(const PairArgs 
     }
 
     if (MODE != 0) {
-        nPairs = (unsigned long long) warpSum((double) nPairs);        // exact below 2^53
+        unsigned long long nPairs = (unsigned long long) warpSum((double) s.nPairs), hPairs = s.hPairs;        // exact below 2^53
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) hPairs += __shfl_xor_sync(FULL_MASK, hPairs, o);
         if (lane == 0) {
@@ -661,7 +629,7 @@ __global__ void __launch_bounds__(PAIR_WARPS*32, MINCTAS) k_pair(const PairArgs 
         return;
     }
     if (EMODE != 0) {
-        if (EMODE == 2 && curSl >= 0) { acc[2*curSl] += regC; acc[2*curSl+1] += regV; }
+        if (curSl >= 0) { acc[2*curSl] += regC; acc[2*curSl+1] += regV; }
         // CTA-level sum without a barrier (a warp that has run out of work items retires; the last one to arrive
         // adds the CTA's totals to the global table)
         for (int k = 0; k < a.nE; k++) {
@@ -682,37 +650,39 @@ __global__ void __launch_bounds__(PAIR_WARPS*32, MINCTAS) k_pair(const PairArgs 
     }
 }
 
-template <int EMODE, int CMODE, int MODE, int MINCTAS>
+template <int EMODE, int CMODE, int MODE, bool CUBIC, int MINCTAS>
 static int launchPairK(Context& c, const PairArgs& a) {
     static bool attr[64] = {false};
     const size_t smem = sizeof(WarpScratch)*PAIR_WARPS + (EMODE == 2 && MODE == 0 && CMODE != 0 ? sizeof(double)*(ERFC_TAB_DEGREE + 1)*ERFC_TAB_MAX_ROWS : 0);
     if (!attr[c.device & 63]) {
-        NBS_CUDA_CHECK(cudaFuncSetAttribute(k_pair<EMODE, CMODE, MODE, MINCTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        NBS_CUDA_CHECK(cudaFuncSetAttribute(k_pair<EMODE, CMODE, MODE, CUBIC, MINCTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         attr[c.device & 63] = true;
     }
     // persistent grid: as many CTAs as are resident at once
     static int perSM[64] = {0};
     if (perSM[c.device & 63] == 0) {
         int n = 0;
-        NBS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_pair<EMODE, CMODE, MODE, MINCTAS>, PAIR_WARPS*32, smem));
+        NBS_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_pair<EMODE, CMODE, MODE, CUBIC, MINCTAS>, PAIR_WARPS*32, smem));
         perSM[c.device & 63] = std::max(1, n);
     }
-    k_pair<EMODE, CMODE, MODE, MINCTAS><<<perSM[c.device & 63]*c.numSMs, PAIR_WARPS*32, smem, c.stream>>>(a);
+    k_pair<EMODE, CMODE, MODE, CUBIC, MINCTAS><<<perSM[c.device & 63]*c.numSMs, PAIR_WARPS*32, smem, c.stream>>>(a);
     return NBS_OK;
 }
 
-template <int EMODE, int CMODE, int MODE>
+template <int EMODE, int CMODE, int MODE, bool CUBIC>
 static int launchPairT(Context& c, const PairArgs& a) {
     if constexpr (MODE == 0 && CMODE != 2) {
         static const int forced = getenv("NBS_PAIR_MINCTAS") ? atoi(getenv("NBS_PAIR_MINCTAS")) : 0;     // tuning experiments
-        if (forced == 3 || (forced == 0 && c.N >= 300000)) return launchPairK<EMODE, CMODE, MODE, 3>(c, a);
+        if (forced == 3 || (forced == 0 && c.N >= 300000 && EMODE == 0)) return launchPairK<EMODE, CMODE, MODE, CUBIC, 3>(c, a);
     }
-    return launchPairK<EMODE, CMODE, MODE, PAIR_MIN_CTAS>(c, a);
+    return launchPairK<EMODE, CMODE, MODE, CUBIC, PAIR_MIN_CTAS>(c, a);
 }
 
 template <int CMODE>
-static int launchPairE(Context& c, const PairArgs& a, int emode) {
-    return emode == 0 ? launchPairT<0, CMODE, 0>(c, a) : (emode == 1 ? launchPairT<1, CMODE, 0>(c, a) : launchPairT<2, CMODE, 0>(c, a));
+static int launchPairE(Context& c, const PairArgs& a, int emode, bool cubic) {
+    if (emode == 0) return launchPairT<0, CMODE, 0, false>(c, a);
+    if (emode == 1) return launchPairT<1, CMODE, 0, false>(c, a);
+    return cubic ? launchPairT<2, CMODE, 0, true>(c, a) : launchPairT<2, CMODE, 0, false>(c, a);
 }
 
 int launchPairs(Context& c, bool wantEnergy, int mode) {
@@ -731,6 +701,8 @@ int launchPairs(Context& c, bool wantEnergy, int mode) {
     a.nE = 2*c.nSl;
     a.sx = g.scale[0]; a.sy = g.scale[1]; a.sz = g.scale[2];
     a.dsx = g.box[0]/4294967296.0; a.dsy = g.box[1]/4294967296.0; a.dsz = g.box[2]/4294967296.0;
+    a.ds2 = a.dsx*a.dsx;
+    const bool cubic = g.box[0] == g.box[1] && g.box[1] == g.box[2];
     // NoCutoff: every pair interacts; the bound only has to exclude the padding lanes (parked at 1e8 nm)
     const bool noCutoff = c.method == NBS_METHOD_NOCUTOFF;
     a.rc2 = noCutoff ? 1.0e12f : (float) (c.cutoff*c.cutoff);
@@ -774,11 +746,11 @@ int launchPairs(Context& c, bool wantEnergy, int mode) {
     int status;
     if (mode != 0) {
         NBS_CUDA_CHECK(cudaMemsetAsync(c.dCounters.d + 3, 0, sizeof(int), c.stream));      // rewind the work cursor
-        status = mode == 1 ? launchPairT<0, 1, 1>(c, a) : launchPairT<0, 1, 2>(c, a);
+        status = mode == 1 ? launchPairT<0, 1, 1, false>(c, a) : launchPairT<0, 1, 2, false>(c, a);
     }
-    else if (c.ljpme()) status = launchPairE<2>(c, a, emode);
-    else if (pme) status = launchPairE<1>(c, a, emode);
-    else status = launchPairE<0>(c, a, emode);
+    else if (c.ljpme()) status = launchPairE<2>(c, a, emode, cubic);
+    else if (pme) status = launchPairE<1>(c, a, emode, cubic);
+    else status = launchPairE<0>(c, a, emode, cubic);
     if (status != NBS_OK) return status;
     c.launches++;
     timerMark(c, mode == 0 ? "pair" : "pair_set");

@@ -45,7 +45,10 @@ constexpr int ERFC_TAB_MAX_ROWS = 256;           // up to s = 2^9 nm^2
 constexpr int J_SHIFT_BITS = 25;                 // sorted index in the low 25 bits of a list entry
 constexpr int J_INDEX_MASK = (1 << J_SHIFT_BITS)-1;
 constexpr int BUILD_WARPS = 8;                   // warps per CTA in the list-build kernel
-constexpr int PAIR_WARPS = 8;                    // warps per CTA in the pair kernel
+#ifndef NBS_PAIR_WARPS
+#define NBS_PAIR_WARPS 8
+#endif
+constexpr int PAIR_WARPS = NBS_PAIR_WARPS;       // warps per CTA in the pair kernel
 
 void setError(const std::string& message);
 #define NBS_CUDA_CHECK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \

@@ -47,7 +47,7 @@
 extern "C" {
 #endif
 
-#define NBS_ABI_VERSION 3
+#define NBS_ABI_VERSION 4
 
 /* status codes */
 #define NBS_OK                 0
@@ -220,6 +220,55 @@ int nbs_execute_convolve(nbs_context* ctx, const nbs_exec_args* args);
 int nbs_execute_finish(nbs_context* ctx, const nbs_exec_args* args);
 /* valid between nbs_execute_begin and nbs_execute_finish of the evaluation in flight */
 int nbs_get_exchange_buffers(nbs_context* ctx, nbs_exchange_buffers* out);
+
+/*
+ * Peer-memory sharding (PME; one process per GPU on one NVLink / NVSwitch node).  The split above leaves a subset's
+ * reciprocal work on ONE rank; this one splits it over ALL ranks and needs no collective library on the data path:
+ *   direct space : i-blocks as above (block_period / block_offset / block_width);
+ *   PME          : rank r owns the x-SLAB [r nx / R, (r+1) nx / R) of every subset grid: it spreads the atoms that
+ *                  touch its planes (positions are replicated, so no halo is exchanged), transforms its planes along
+ *                  z and y, runs the fused x pass (forward x, sliced convolution, slice energies, lambda mixing,
+ *                  inverse x) for the y-range [r ny / R, (r+1) ny / R) READING the other ranks' planes and WRITING the
+ *                  result back into them through peer memory (the all-to-all transposes of a slab-decomposed FFT,
+ *                  fused into the kernel that consumes them), inverse-transforms its planes and gathers the forces
+ *                  its planes contribute;
+ *   reduction    : one kernel sums the 64-bit fixed-point force accumulators of all ranks for this rank's 1/R of the
+ *                  atoms, reading peer memory, and writes the sums back to every rank (reduce-scatter + all-gather);
+ *                  slice energies travel through a small mailbox in peer memory.
+ * The steps of an evaluation are separated by barriers over flags in peer memory (in_kernel_barrier = 1; then
+ * nbs_execute drives the whole sharded evaluation), or by the caller (in_kernel_barrier = 0: call
+ * nbs_execute_step(step) for step = 0 .. NBS_NUM_STEPS-1 and make sure every rank has finished step k before any
+ * rank starts step k+1 -- what tests do with several contexts on one device).
+ * The reference has no counterpart (platforms/cuda/src/CudaParallelNonbondedSlicingKernels.cpp:35-53 keeps
+ * reciprocal space on device 0).  PME only; the plane-FFT path only (grids whose x lines fit in shared memory).
+ */
+#define NBS_MAX_RANKS 16
+#define NBS_NUM_STEPS 5
+typedef struct nbs_peer_export {
+    int32_t struct_size;                  /* = sizeof(nbs_peer_export)                          */
+    int32_t rank;
+    int64_t process_id;                   /* exporting process: a peer in the same process is reached by pointer,   */
+    int32_t device;                       /* one in another process through the CUDA IPC handles below              */
+    int32_t reserved;
+    void*   spectra;                      /* device pointers in the exporting process                               */
+    void*   forces;
+    void*   mailbox;
+    unsigned char spectra_ipc[64];        /* cudaIpcMemHandle_t of the three allocations                            */
+    unsigned char forces_ipc[64];
+    unsigned char mailbox_ipc[64];
+} nbs_peer_export;
+
+int nbs_set_slab_shard(nbs_context* ctx, int32_t rank, int32_t num_ranks, int32_t block_period, int32_t block_offset,
+                       int32_t block_width);
+int nbs_export_peer(nbs_context* ctx, nbs_peer_export* out);
+/* `all` = the exports of ranks 0 .. count-1 (this rank's own included), count == num_ranks */
+int nbs_import_peers(nbs_context* ctx, int32_t count, const nbs_peer_export* all, int32_t in_kernel_barrier);
+/* step 0: sort, lists, direct space (own stream), spreading, z/y transforms of the own planes
+ *      1: fused x pass over peer memory for the own y-range
+ *      2: inverse y/z transforms of the own planes, force gather, join direct space, publish slice energies
+ *      3: force reduction over peer memory
+ *      4: forces to the caller's layout, energies to the host; returns NBS_RETRY like nbs_execute_finish */
+int nbs_execute_step(nbs_context* ctx, const nbs_exec_args* args, int32_t step);
 
 /*
  * Neighbour-list policy of the periodic cutoff methods.  The list is built with cutoff + skin and re-used by later

@@ -112,6 +112,26 @@ class ExchangeBuffers(C.Structure):
     ]
 
 
+NBS_MAX_RANKS = 16
+NBS_NUM_STEPS = 5
+
+
+class PeerExport(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_int32),
+        ("rank", C.c_int32),
+        ("process_id", C.c_int64),
+        ("device", C.c_int32),
+        ("reserved", C.c_int32),
+        ("spectra", C.c_void_p),
+        ("forces", C.c_void_p),
+        ("mailbox", C.c_void_p),
+        ("spectra_ipc", C.c_ubyte*64),
+        ("forces_ipc", C.c_ubyte*64),
+        ("mailbox_ipc", C.c_ubyte*64),
+    ]
+
+
 def _ptr(array, ctype):
     if array is None or array.size == 0:
         return C.cast(None, C.POINTER(ctype))
@@ -144,7 +164,7 @@ class DescArrays:
                 setattr(self.desc, name, value)
 
 
-ABI_VERSION = 3          # NBS_ABI_VERSION of include/nbslice_b200.h
+ABI_VERSION = 4          # NBS_ABI_VERSION of include/nbslice_b200.h
 LIB_PATH = os.environ.get("NBS_B200_LIBRARY") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libnbslice_b200.so")
 _lib = None
 
@@ -155,6 +175,7 @@ EXPORTS = [
     "nbs_get_pme_parameters", "nbs_get_ljpme_parameters", "nbs_get_num_slices", "nbs_get_pair_set", "nbs_get_exclusion_set",
     "nbs_get_kernel_times", "nbs_get_launch_count", "nbs_get_nlist_stats",
     "nbs_set_shard", "nbs_execute_begin", "nbs_execute_convolve", "nbs_execute_finish", "nbs_get_exchange_buffers",
+    "nbs_set_slab_shard", "nbs_export_peer", "nbs_import_peers", "nbs_execute_step",
     "nbs_debug_set_list_capacity", "nbs_measure_peaks", "nbs_measure_dp_rates", "nbs_set_list_skin", "nbs_get_list_stats",
 ]
 
@@ -195,6 +216,10 @@ def load_library():
     lib.nbs_set_shard.argtypes = [C.c_void_p] + [C.c_int32]*7
     for name in ("nbs_execute_begin", "nbs_execute_convolve", "nbs_execute_finish"):
         getattr(lib, name).argtypes = [C.c_void_p, C.POINTER(ExecArgs)]
+    lib.nbs_set_slab_shard.argtypes = [C.c_void_p] + [C.c_int32]*5
+    lib.nbs_export_peer.argtypes = [C.c_void_p, C.POINTER(PeerExport)]
+    lib.nbs_import_peers.argtypes = [C.c_void_p, C.c_int32, C.POINTER(PeerExport), C.c_int32]
+    lib.nbs_execute_step.argtypes = [C.c_void_p, C.POINTER(ExecArgs), C.c_int32]
     lib.nbs_debug_set_list_capacity.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
     lib.nbs_get_exchange_buffers.argtypes = [C.c_void_p, C.POINTER(ExchangeBuffers)]
     lib.nbs_measure_peaks.argtypes = [C.c_int32, _f64p]

@@ -18,6 +18,12 @@ struct PlaneFftPlan {
 struct PlaneFftArgs {
     int nS, nx, ny, nz, nzh;
     int ownLo, ownHi;                // subsets whose grids this rank transforms / produces
+    // slab sharding over ranks (peer memory): the zy / yz kernels work on the planes x in [xLo, xLo + nxOwn) of every
+    // own subset, the x kernel on the rows y in [yLo, yLo + nyOwn), reading and writing plane x in the spectra of the
+    // rank that owns it (peerSpectra[owner(x)], the layout of gridC).  Unsharded: xLo = yLo = 0, nxOwn = nx, nyOwn = ny,
+    // nRanks = 1, peerSpectra[0] = gridC.
+    int xLo, nxOwn, yLo, nyOwn, nRanks;
+    void* peerSpectra[NBS_MAX_RANKS];
     int rowStride;                   // zy / yz kernels: complex elements per plane row in shared memory
     int chunk;                       // x kernel: kz values per CTA
     int planeThreads, xThreads, colThreads;   // CTA sizes chosen for this plan

@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_zy_fwd(const PlaneFftArgs a
     // CTA = one (own subset, x) plane, or -- when a plane does not fit in shared memory -- a slab of its row pairs
     // (then the y transform is a separate kernel, k_fft_y_cols)
     const int plane_ = blockIdx.x/a.slabsPerPlane, slab = blockIdx.x - plane_*a.slabsPerPlane;
-    const int sx = a.ownLo*a.nx + plane_;
+    const int sx = (a.ownLo + plane_/a.nxOwn)*a.nx + a.xLo + plane_ % a.nxOwn;     // (subset, x) of this rank's plane number plane_
     const bool fused = a.slabsPerPlane == 1;
     const int allPairs = (ny + 1) >> 1;
     const int pBase = slab*a.slabPairs;
@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_y_cols(const PlaneFftArgs a
     const int plane_ = blockIdx.x/chunks, k0 = (blockIdx.x - plane_*chunks)*cw;
     const int kn = min(cw, nzh - k0);
     const FastDiv divKn(kn);
-    C* base = (C*) a.gridC + (size_t) (a.ownLo*a.nx + plane_)*ny*nzh + k0;
+    C* base = (C*) a.gridC + (size_t) ((a.ownLo + plane_/a.nxOwn)*a.nx + a.xLo + plane_ % a.nxOwn)*ny*nzh + k0;
     for (int b0 = threadIdx.x; b0 < ny*kn; b0 += FFT_COPY_U*blockDim.x) {
         C v[FFT_COPY_U];
         int at[FFT_COPY_U];
@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_yz_inv(const PlaneFftArgs a
     for (int k = threadIdx.x; k < nz; k += blockDim.x) twz[k] = ((const C*) a.twz)[k];
     for (int k = threadIdx.x; k < ny; k += blockDim.x) twy[k] = ((const C*) a.twy)[k];
     const int plane_ = blockIdx.x/a.slabsPerPlane, slab = blockIdx.x - plane_*a.slabsPerPlane;
-    const int sx = a.ownLo*a.nx + plane_;
+    const int sx = (a.ownLo + plane_/a.nxOwn)*a.nx + a.xLo + plane_ % a.nxOwn;     // (subset, x) of this rank's plane number plane_
     const bool fused = a.slabsPerPlane == 1;
     const int allPairs = (ny + 1) >> 1;
     const int pBase = slab*a.slabPairs;
@@ -439,10 +439,16 @@ __global__ void __launch_bounds__(FFT_X_THREADS) k_fft_x_conv2(const PlaneFftArg
     for (int k = threadIdx.x; k < n; k += blockDim.x) tw[k] = ((const C*) a.twx)[k];
     if (threadIdx.x < MAX_SLICES) shE[threadIdx.x] = 0.0;
     const int chunks = (nzh + chunk - 1)/chunk;
-    const int y = blockIdx.x/chunks, k0 = (blockIdx.x - y*chunks)*chunk;
+    const int yLocal = blockIdx.x/chunks, k0 = (blockIdx.x - yLocal*chunks)*chunk;
+    const int y = a.yLo + yLocal;
     const int kn = min(chunk, nzh - k0);                     // kz values this CTA really has
     const FastDiv divKn(kn), divChunk(chunk), divN(n);
-    C* gridC = (C*) a.gridC;
+    // plane x lives in the spectra of rank ((x + 1) R - 1) / nx, the owner of the slab [r nx / R, (r+1) nx / R)
+    const int nRanks = a.nRanks;
+    auto planeOf = [&](int s, int x) -> C* {
+        C* base = nRanks == 1 ? (C*) a.gridC : (C*) a.peerSpectra[((x + 1)*nRanks - 1)/n];
+        return base + (((size_t) s*n + x)*a.ny + y)*nzh + k0;
+    };
     for (int b0 = threadIdx.x; b0 < nS*n*chunk; b0 += FFT_COPY_U*blockDim.x) {
         C v[FFT_COPY_U];
         int at[FFT_COPY_U];
@@ -454,7 +460,7 @@ __global__ void __launch_bounds__(FFT_X_THREADS) k_fft_x_conv2(const PlaneFftArg
                 int rest, l, s, x;
                 divChunk.divmod(idx, rest, l);
                 divN.divmod(rest, s, x);
-                v[u] = l < kn ? gridC[(((size_t) s*n + x)*a.ny + y)*nzh + k0 + l] : mkc((T) 0, (T) 0);
+                v[u] = l < kn ? planeOf(s, x)[l] : mkc((T) 0, (T) 0);
                 at[u] = x*RS + s*chunk + l;
             }
         }
@@ -517,7 +523,7 @@ __global__ void __launch_bounds__(FFT_X_THREADS) k_fft_x_conv2(const PlaneFftArg
         s += a.ownLo;
         C v = lines[(size_t) x*RS + s*chunk + l];
         v.y = -v.y;
-        gridC[(((size_t) s*n + x)*a.ny + y)*nzh + k0 + l] = v;
+        planeOf(s, x)[l] = v;
     }
     if (a.wantEnergy) {
         const int lane = threadIdx.x & 31;
@@ -553,7 +559,7 @@ static int launchPlaneT(Context& c, PlaneFftArgs a, int half, size_t smPlane, si
         attr[c.device & 63] = true;
     }
     const int nOwn = c.ownHi - c.ownLo;
-    const int planes = nOwn*a.nx;
+    const int planes = nOwn*a.nxOwn;
     const bool fused = a.slabsPerPlane == 1;
     const int colCtas = planes*((a.nzh + a.colChunk - 1)/a.colChunk);
     const size_t smCols = sizeof(typename Cx2<T>::type)*((size_t) a.ny + (size_t) a.ny*(a.colChunk + 1));
@@ -566,20 +572,26 @@ static int launchPlaneT(Context& c, PlaneFftArgs a, int half, size_t smPlane, si
         }
         return NBS_OK;
     }
-    const int xCtas = a.ny*((a.nzh + a.chunk - 1)/a.chunk);
-    switch (c.nS) {
-        case 1: k_fft_x_conv2<T, RMAX, 1><<<xCtas, a.xThreads, smX, st>>>(a); break;
-        case 2: k_fft_x_conv2<T, RMAX, 2><<<xCtas, a.xThreads, smX, st>>>(a); break;
-        case 3: k_fft_x_conv2<T, RMAX, 3><<<xCtas, a.xThreads, smX, st>>>(a); break;
-        case 4: k_fft_x_conv2<T, RMAX, 4><<<xCtas, a.xThreads, smX, st>>>(a); break;
-        default: k_fft_x_conv2<T, RMAX, MAX_SUBSETS><<<xCtas, a.xThreads, smX, st>>>(a); break;
+    // half 1 = x pass + inverse transforms; half 2 = x pass only, half 3 = inverse transforms only (slab sharding puts
+    // a barrier between them: the x pass writes into other ranks' planes)
+    const int xCtas = a.nyOwn*((a.nzh + a.chunk - 1)/a.chunk);
+    if (half != 3) {
+        switch (c.nS) {
+            case 1: k_fft_x_conv2<T, RMAX, 1><<<xCtas, a.xThreads, smX, st>>>(a); break;
+            case 2: k_fft_x_conv2<T, RMAX, 2><<<xCtas, a.xThreads, smX, st>>>(a); break;
+            case 3: k_fft_x_conv2<T, RMAX, 3><<<xCtas, a.xThreads, smX, st>>>(a); break;
+            case 4: k_fft_x_conv2<T, RMAX, 4><<<xCtas, a.xThreads, smX, st>>>(a); break;
+            default: k_fft_x_conv2<T, RMAX, MAX_SUBSETS><<<xCtas, a.xThreads, smX, st>>>(a); break;
+        }
+        c.launches++;
     }
+    if (half == 2) return NBS_OK;
     if (!fused) {
         k_fft_y_cols<T, RMAX, true><<<colCtas, a.colThreads, smCols, st>>>(a);
         c.launches++;
     }
     k_fft_yz_inv<T, RMAX><<<planes*a.slabsPerPlane, a.planeThreads, smPlane, st>>>(a);
-    c.launches += 2;
+    c.launches++;
     return NBS_OK;
 }
 

@@ -172,6 +172,7 @@ __device__ __forceinline__ void warpFft(C* line, int n, unsigned long long facto
 struct PmeArgs {
     int N, Npad, nS, nx, ny, nz, nzh;
     int ownLo, ownHi;            // this rank spreads / gathers the atoms of subsets [ownLo, ownHi)
+    int xLo, xHi;                // ... into / from the grid planes x in [xLo, xHi) (slab sharding; the whole grid otherwise)
     const uint4* posq; const float4* par;
     // unsorted mode (small systems): particle-order inputs straight from k_prep, so that the PME chain does not
     // wait for the cell sort; forces then go to the particle-order half of the accumulator
@@ -200,6 +201,19 @@ __device__ __forceinline__ uint4 latticeFractions(const PmeArgs& a, uint4 p) {
     p.x = (unsigned) (__double2ull_rd(tx*4294967296.0) & 0xffffffffull);
     p.y = (unsigned) (__double2ull_rd(ty*4294967296.0) & 0xffffffffull);
     return p;
+}
+
+// Slab sharding: does any of the five x planes of the atom's spline fall into this rank's slab?  (warp-uniform)
+__device__ __forceinline__ bool touchesSlab(const PmeArgs& a, const uint4 pBrick) {
+    if (a.xHi - a.xLo >= a.nx) return true;
+    const uint4 p = latticeFractions(a, pBrick);
+    const int ix0 = (int) (((unsigned long long) p.x*(unsigned) a.nx) >> 32);
+#pragma unroll
+    for (int o = 0; o < PME_ORDER; o++) {
+        int x = ix0 + o; x -= x >= a.nx ? a.nx : 0;
+        if (x >= a.xLo && x < a.xHi) return true;
+    }
+    return false;
 }
 
 template <typename T>
@@ -240,10 +254,12 @@ __device__ __forceinline__ void splineTable(const PmeArgs& a, const uint4 pBrick
 template <typename T> struct FixedGridScale { static constexpr double value = 4294967296.0; };            // 2^32: 2e-10 of a unit charge
 template <> struct FixedGridScale<double> { static constexpr double value = 1099511627776.0; };          // 2^40 for the double-precision grids
 
+// (blockIdx.y = grid of a subset; `n` consecutive cells of each, `stride` cells apart)
 template <typename T>
-__global__ void k_fixed_to_real(size_t n, const long long* __restrict__ fixed, T* __restrict__ grid) {
+__global__ void k_fixed_to_real(size_t n, size_t stride, const long long* __restrict__ fixed, T* __restrict__ grid) {
     const size_t i = (size_t) blockIdx.x*blockDim.x + threadIdx.x;
-    if (i < n) grid[i] = (T) ((double) fixed[i]*(1.0/FixedGridScale<T>::value));
+    const size_t at = blockIdx.y*stride + i;
+    if (i < n) grid[at] = (T) ((double) fixed[at]*(1.0/FixedGridScale<T>::value));
 }
 
 template <typename T, bool FIXED>
@@ -256,6 +272,7 @@ __global__ void __launch_bounds__(256) k_spread(const PmeArgs a) {
     if (a.unsorted) { p = a.fix[j]; q = a.chargeF[j]; subset = a.subsetOf[j]; }
     else { p = a.posq[j]; q = __uint_as_float(p.w); subset = __float_as_int(a.par[j].z) & 7; }
     if (q == 0.f || subset < a.ownLo || subset >= a.ownHi) return;      // warp-uniform
+    if (!touchesSlab(a, p)) return;
     int ix0, iy0, iz0;
     splineTable<T>(a, p, lane, wtab[warp], (T*) nullptr, ix0, iy0, iz0);
     const T* wt = wtab[warp];
@@ -273,6 +290,7 @@ __global__ void __launch_bounds__(256) k_spread(const PmeArgs a) {
             int z = iz0 + oz; z -= z >= a.nz ? a.nz : 0;
             const T value = qT*wt[ox]*wt[5 + oy]*wt[10 + oz];
             const size_t cell = ((size_t) x*a.ny + y)*a.nz + z;
+            if (x < a.xLo || x >= a.xHi) continue;                        // another rank's plane
             if (FIXED) atomicAdd(gridFixed + cell, (unsigned long long) __double2ll_rn((double) value*FixedGridScale<T>::value));
             else atomicAdd(grid + cell, value);
         }
@@ -498,6 +516,7 @@ __global__ void __launch_bounds__(256) k_gather(const PmeArgs a) {
     else { p = a.posq[j]; q = __uint_as_float(p.w); subset = __float_as_int(a.par[j].z) & 7; }
     if (q == 0.f) return;
     if (subset < a.ownLo || subset >= a.ownHi) return;
+    if (!touchesSlab(a, p)) return;
     int ix0, iy0, iz0;
     splineTable<float>(a, p, lane, wtab[warp], dwtab[warp], ix0, iy0, iz0);
     const float* wt = wtab[warp];
@@ -512,7 +531,8 @@ __global__ void __launch_bounds__(256) k_gather(const PmeArgs a) {
             int x = ix0 + ox; x -= x >= a.nx ? a.nx : 0;
             int y = iy0 + oy; y -= y >= a.ny ? a.ny : 0;
             int z = iz0 + oz; z -= z >= a.nz ? a.nz : 0;
-            const float g = pot[((size_t) x*a.ny + y)*a.nz + z];
+            // (slab sharding: the planes of other ranks contribute there; the force reduction adds the shares)
+            const float g = (x >= a.xLo && x < a.xHi) ? pot[((size_t) x*a.ny + y)*a.nz + z] : 0.f;
             const float tx = wt[ox], ty = wt[5 + oy], tz = wt[10 + oz];
             fx = fmaf(dwt[ox]*ty*tz, g, fx);
             fy = fmaf(tx*dwt[5 + oy]*tz, g, fy);
@@ -671,6 +691,7 @@ static int launchPmeT(Context& c, bool wantEnergy, int half) {
     PmeArgs p;
     p.N = c.N; p.Npad = c.Npad; p.nS = c.nS; p.nx = nx; p.ny = ny; p.nz = nz; p.nzh = nzh;
     p.ownLo = c.ownLo; p.ownHi = c.ownHi;
+    p.xLo = c.slabMode ? c.xLo : 0; p.xHi = c.slabMode ? c.xHi : nx;
     p.posq = c.dPosq.d; p.par = c.dPar.d; p.grid = c.dGrid.d; p.pot = c.dPot.d; p.gridFixed = nullptr;
     p.unsorted = c.pmeUnsorted ? 1 : 0;
     p.fix = c.dFix.d; p.chargeF = c.dChargeF.d; p.subsetOf = c.dSubset.d;
@@ -694,18 +715,21 @@ static int launchPmeT(Context& c, bool wantEnergy, int half) {
     if (half == 0) {
         int status = prepareEterm(c);
         if (status != NBS_OK) return status;
+        // the cells this rank spreads into: the grids of its subsets, or (slab sharding) its planes of every grid
+        const size_t planeCells = (size_t) ny*nz, first = (size_t) c.ownLo*G + (size_t) p.xLo*planeCells;
+        const size_t cellsPerGrid = c.slabMode ? (size_t) (p.xHi - p.xLo)*planeCells : G*(c.ownHi - c.ownLo);
+        const int gridsToClear = c.slabMode ? c.nS : 1;
         if (c.flags & NBS_FLAG_DETERMINISTIC) {
-            const size_t cells = G*(c.ownHi - c.ownLo);
             NBS_CUDA_CHECK(c.dGridFixed.ensure(G*c.nS));
             p.gridFixed = c.dGridFixed.d;
-            NBS_CUDA_CHECK(cudaMemsetAsync(c.dGridFixed.d + (size_t) c.ownLo*G, 0, sizeof(unsigned long long)*cells, st));
+            NBS_CUDA_CHECK(cudaMemset2DAsync(c.dGridFixed.d + first, sizeof(unsigned long long)*G, 0, sizeof(unsigned long long)*cellsPerGrid, gridsToClear, st));
             k_spread<T, true><<<atomCtas, 256, 0, st>>>(p);
-            k_fixed_to_real<T><<<(unsigned) ((cells + 255)/256), 256, 0, st>>>(cells, (const long long*) c.dGridFixed.d + (size_t) c.ownLo*G,
-                                                                                 (T*) c.dGrid.d + (size_t) c.ownLo*G);
+            k_fixed_to_real<T><<<dim3((unsigned) ((cellsPerGrid + 255)/256), gridsToClear), 256, 0, st>>>(cellsPerGrid, G, (const long long*) c.dGridFixed.d + first,
+                                                                                                           (T*) c.dGrid.d + first);
             c.launches++;
         }
         else {
-            NBS_CUDA_CHECK(cudaMemsetAsync((T*) c.dGrid.d + (size_t) c.ownLo*G, 0, sizeof(T)*G*(c.ownHi - c.ownLo), st));
+            NBS_CUDA_CHECK(cudaMemset2DAsync((T*) c.dGrid.d + first, sizeof(T)*G, 0, sizeof(T)*cellsPerGrid, gridsToClear, st));
             k_spread<T, false><<<atomCtas, 256, 0, st>>>(p);
         }
         c.launches++;
@@ -736,14 +760,18 @@ static int launchPmeT(Context& c, bool wantEnergy, int half) {
         PlaneFftArgs pa;
         pa.nS = c.nS; pa.nx = nx; pa.ny = ny; pa.nz = nz; pa.nzh = nzh;
         pa.ownLo = c.ownLo; pa.ownHi = c.ownHi;
+        pa.xLo = c.slabMode ? c.xLo : 0; pa.nxOwn = c.slabMode ? c.xHi - c.xLo : nx;
+        pa.yLo = c.slabMode ? c.yLo : 0; pa.nyOwn = c.slabMode ? c.yHi - c.yLo : ny;
+        pa.nRanks = c.slabMode ? c.nRanks : 1;
+        for (int r = 0; r < NBS_MAX_RANKS; r++) pa.peerSpectra[r] = c.slabMode && r < c.nRanks ? c.peerSpectra[r] : (void*) c.dGridC.d;
         pa.rowStride = 0; pa.chunk = 0;
         pa.grid = c.dGrid.d; pa.gridC = c.dGridC.d; pa.eterm = f.eterm; pa.pot = c.dPot.d;
         pa.energy = energyBase; pa.wantEnergy = f.wantEnergy; pa.lam = f.lam;
         const int planeStatus = (c.flags & NBS_FLAG_LINE_FFT) ? NBS_RETRY : launchPlaneFft<T>(c, plan, pa, half);
         if (planeStatus < 0) return planeStatus;
         if (planeStatus == NBS_OK) {
-            timerMark(c, half == 0 ? "fft_fwd" : "fft_conv_inv");
-            if (half == 1) {
+            timerMark(c, half == 0 ? "fft_fwd" : (half == 3 ? "fft_inv" : "fft_conv_inv"));
+            if (half == 1 || half == 3) {
                 k_gather<<<atomCtas, 256, 0, st>>>(p);
                 c.launches++;
                 timerMark(c, "gather");
@@ -752,6 +780,10 @@ static int launchPmeT(Context& c, bool wantEnergy, int half) {
         }
     }
     // ... otherwise one line per warp, five kernels
+    if (c.slabMode) {
+        setError("slab sharding needs the plane-FFT path (the x lines of all subsets must fit in shared memory; NBS_FLAG_LINE_FFT is not supported)");
+        return NBS_ERR_UNSUPPORTED;
+    }
     if (smX > 200*1024 || smY > 200*1024 || smZ > 200*1024) {
         setError("PME grid too large for the shared-memory FFT");
         return NBS_ERR_UNSUPPORTED;
@@ -771,7 +803,8 @@ static int launchPmeT(Context& c, bool wantEnergy, int half) {
 }
 
 // Energies requested -> double-precision grids and transforms; forces only -> single precision.
-// half 0: spread + forward z/y transforms of the own subsets; half 1: x pass + convolution, inverse, gather.
+// half 0: spread + forward z/y transforms of the own subsets; half 1: x pass + convolution, inverse, gather
+// (slab sharding: half 2 = x pass alone, half 3 = inverse transforms + gather).
 int launchPme(Context& c, bool wantEnergy, int half) {
     const bool fp64 = wantEnergy && !(c.flags & NBS_FLAG_FP32_ENERGY);
     return fp64 ? launchPmeT<double>(c, true, half) : launchPmeT<float>(c, wantEnergy, half);

@@ -9,6 +9,7 @@
 //        adapter's job (it owns the scaling-parameter names)
 // There is no CPU fallback anywhere in this file: every path ends in CUDA kernels or an error code.
 #include "nbs_internal.h"
+#include <unistd.h>
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -446,6 +447,13 @@ static void releaseAll(Context& c) {
     if (c.evSorted) cudaEventDestroy(c.evSorted);
     if (c.evDirectDone) cudaEventDestroy(c.evDirectDone);
     c.directStream = nullptr; c.evSorted = nullptr; c.evDirectDone = nullptr;
+    for (int k = 0; k < 3*NBS_MAX_RANKS; k++) {
+        if (c.peerOpened[k]) cudaIpcCloseMemHandle(c.peerOpened[k]);
+        c.peerOpened[k] = nullptr;
+    }
+    c.dMailbox.release();
+    if (c.hTimedOut) cudaFreeHost(c.hTimedOut);
+    c.hTimedOut = nullptr;
 }
 
 } // namespace nbs
@@ -953,10 +961,21 @@ static bool hostPointerIsPinned(const void* p) {
     return attr.type == cudaMemoryTypeHost;
 }
 
+static int slabStepRun(Context& c, const nbs_exec_args* args, int step);
+
 int nbs_execute(nbs_context* ctx, const nbs_exec_args* args) {
     if (!ctx || !args) return fail(NBS_ERR_INVALID, "null argument");
     Context& c = ctx->c;
-    if (c.nRanks != 1) return fail(NBS_ERR_INVALID, "a sharded context is driven through nbs_execute_begin/convolve/finish");
+    if (c.slabMode && c.peersImported && c.peerBarrier) {
+        // peer-memory sharding with in-kernel barriers: the five steps back to back, every rank the same
+        for (int attempt = 0; attempt < 9; attempt++) {
+            int status = NBS_OK;
+            for (int step = 0; step < NBS_NUM_STEPS && status == NBS_OK; step++) status = slabStepRun(c, args, step);
+            if (status != NBS_RETRY) return status;
+        }
+        return fail(NBS_ERR_CAPACITY, "neighbour list capacity exceeded");
+    }
+    if (c.nRanks != 1) return fail(NBS_ERR_INVALID, "a sharded context is driven through nbs_execute_begin/convolve/finish (or nbs_execute_step)");
     // A whole evaluation is ~20 short kernels: once the same evaluation (same buffers, box, parameters) has
     // run once, it is captured into a CUDA graph and replayed, which removes the per-launch gaps.
     bool graphable = !(c.flags & NBS_FLAG_NO_GRAPH) && !c.profiling && !c.paramsDirty && c.periodic && workStream(c, args) != nullptr;
@@ -1031,6 +1050,151 @@ int nbs_execute(nbs_context* ctx, const nbs_exec_args* args) {
     return fail(NBS_ERR_CAPACITY, "neighbour list capacity exceeded");
 }
 
+// ---- peer-memory sharding: the evaluation in five steps (include/nbslice_b200.h, nbs_execute_step) ------------------
+static int slabStepRun(Context& c, const nbs_exec_args* args, int step) {
+    if (!c.slabMode || !c.peersImported) return fail(NBS_ERR_INVALID, "nbs_execute_step needs nbs_set_slab_shard and nbs_import_peers first");
+    if (step != c.slabStep) { c.slabStep = 0; c.phase = 0; return fail(NBS_ERR_INVALID, "nbs_execute_step: steps must run in order 0 .. NBS_NUM_STEPS-1"); }
+    int status = NBS_OK;
+    switch (step) {
+        case 0:
+            // sort, lists and direct space (own stream), spreading and z/y transforms of the own planes
+            if ((status = phaseBegin(c, args)) != NBS_OK) break;
+            if (c.phaseRecip && c.peerBarrier) status = launchPeerBarrier(c, false);      // every rank's planes are transformed
+            break;
+        case 1:
+            NBS_CUDA_CHECK(cudaSetDevice(c.device));
+            if (c.phaseRecip) {
+                if ((status = launchPme(c, c.phaseEnergy, 2)) != NBS_OK) break;
+                if (c.peerBarrier) status = launchPeerBarrier(c, false);                  // every rank's x pass has written its rows
+            }
+            break;
+        case 2:
+            NBS_CUDA_CHECK(cudaSetDevice(c.device));
+            if (c.phaseRecip && (status = launchPme(c, c.phaseEnergy, 3)) != NBS_OK) break;
+            if (c.directOverlapped) NBS_CUDA_CHECK(cudaStreamWaitEvent(c.stream, c.evDirectDone, 0));
+            status = launchPeerBarrier(c, true);                                          // forces are complete; energies published
+            break;
+        case 3:
+            NBS_CUDA_CHECK(cudaSetDevice(c.device));
+            if ((status = launchPeerReduce(c)) != NBS_OK) break;
+            if (c.peerBarrier) status = launchPeerBarrier(c, false);                      // every rank's slice has been written back
+            c.phase = 2;
+            break;
+        case 4: {
+            c.slabStep = 0;
+            NBS_CUDA_CHECK(cudaMemcpyAsync(c.hTimedOut, &c.dMailbox.d->timedOut, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream));
+            status = phaseFinish(c, args);
+            if (status >= 0 && *c.hTimedOut != 0)
+                return fail(NBS_ERR_CUDA, "a peer-memory barrier timed out: some rank never reached the same step of the evaluation");
+            return status;
+        }
+        default:
+            return fail(NBS_ERR_INVALID, "nbs_execute_step: illegal step");
+    }
+    if (status != NBS_OK) {
+        if (c.directOverlapped && step < 2) cudaStreamWaitEvent(c.stream, c.evDirectDone, 0);
+        c.slabStep = 0; c.phase = 0;
+        return status;
+    }
+    c.slabStep = step + 1;
+    return NBS_OK;
+}
+
+int nbs_execute_step(nbs_context* ctx, const nbs_exec_args* args, int32_t step) {
+    if (!ctx || !args) return fail(NBS_ERR_INVALID, "null argument");
+    return slabStepRun(ctx->c, args, step);
+}
+
+int nbs_set_slab_shard(nbs_context* ctx, int32_t rank, int32_t num_ranks, int32_t block_period, int32_t block_offset,
+                       int32_t block_width) {
+    if (!ctx) return fail(NBS_ERR_INVALID, "null argument");
+    Context& c = ctx->c;
+    if (num_ranks < 1 || num_ranks > NBS_MAX_RANKS || rank < 0 || rank >= num_ranks) return fail(NBS_ERR_INVALID, "illegal rank / num_ranks");
+    if (block_period < 1 || block_width < 0 || block_offset < 0 || block_offset + block_width > block_period)
+        return fail(NBS_ERR_INVALID, "illegal i-block share: need 0 <= offset, offset + width <= period");
+    if (c.method != NBS_METHOD_PME) return fail(NBS_ERR_UNSUPPORTED, "peer-memory sharding is implemented for PME only");
+    if (c.grid[0] < num_ranks || c.grid[1] < num_ranks) return fail(NBS_ERR_UNSUPPORTED, "more ranks than grid planes");
+    if (c.flags & NBS_FLAG_LINE_FFT) return fail(NBS_ERR_UNSUPPORTED, "peer-memory sharding needs the plane-FFT path");
+    NBS_CUDA_CHECK(cudaSetDevice(c.device));
+    c.rank = rank; c.nRanks = num_ranks;
+    c.paramVersion++;
+    c.listEpoch++;
+    c.blockPeriod = block_period; c.blockOffset = block_offset; c.blockWidth = block_width;
+    c.ownLo = 0; c.ownHi = c.nS;
+    c.slabMode = true; c.peersImported = false; c.slabStep = 0;
+    c.xLo = (int) ((long long) rank*c.grid[0]/num_ranks); c.xHi = (int) ((long long) (rank + 1)*c.grid[0]/num_ranks);
+    c.yLo = (int) ((long long) rank*c.grid[1]/num_ranks); c.yHi = (int) ((long long) (rank + 1)*c.grid[1]/num_ranks);
+    c.haveLast = false;
+    // the buffers the peers map must exist (and never move) before they are exported
+    c.Npad = ((c.N + 31)/32)*32 + 32;
+    NBS_CUDA_CHECK(c.dForce.ensure(6*(size_t) c.Npad));
+    NBS_CUDA_CHECK(c.dMailbox.ensure(1));
+    NBS_CUDA_CHECK(cudaMemset(c.dMailbox.d, 0, sizeof(PeerMailbox)));
+    if (!c.hTimedOut) NBS_CUDA_CHECK(cudaMallocHost((void**) &c.hTimedOut, sizeof(unsigned long long)));
+    *c.hTimedOut = 0;
+    return NBS_OK;
+}
+
+int nbs_export_peer(nbs_context* ctx, nbs_peer_export* out) {
+    if (!ctx || !out) return fail(NBS_ERR_INVALID, "null argument");
+    Context& c = ctx->c;
+    if (out->struct_size != (int32_t) sizeof(nbs_peer_export)) return fail(NBS_ERR_INVALID, "nbs_peer_export.struct_size mismatch");
+    if (!c.slabMode) return fail(NBS_ERR_INVALID, "nbs_export_peer needs nbs_set_slab_shard first");
+    NBS_CUDA_CHECK(cudaSetDevice(c.device));
+    out->rank = c.rank;
+    out->process_id = (int64_t) getpid();
+    out->device = c.device;
+    out->reserved = 1;                       // 1 = the IPC handles below are valid
+    out->spectra = c.dGridC.d; out->forces = c.dForce.d; out->mailbox = c.dMailbox.d;
+    cudaIpcMemHandle_t h[3];
+    void* ptrs[3] = {c.dGridC.d, c.dForce.d, c.dMailbox.d};
+    for (int k = 0; k < 3; k++)
+        if (cudaIpcGetMemHandle(&h[k], ptrs[k]) != cudaSuccess) { cudaGetLastError(); std::memset(&h[k], 0, sizeof(h[k])); out->reserved = 0; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    std::memcpy(out->spectra_ipc, &h[0], 64); std::memcpy(out->forces_ipc, &h[1], 64); std::memcpy(out->mailbox_ipc, &h[2], 64);
+    return NBS_OK;
+}
+
+int nbs_import_peers(nbs_context* ctx, int32_t count, const nbs_peer_export* all, int32_t in_kernel_barrier) {
+    if (!ctx || !all) return fail(NBS_ERR_INVALID, "null argument");
+    Context& c = ctx->c;
+    if (!c.slabMode || count != c.nRanks) return fail(NBS_ERR_INVALID, "nbs_import_peers: need one export per rank of nbs_set_slab_shard");
+    NBS_CUDA_CHECK(cudaSetDevice(c.device));
+    for (int r = 0; r < count; r++) {
+        const nbs_peer_export& e = all[r];
+        if (e.struct_size != (int32_t) sizeof(nbs_peer_export) || e.rank != r) return fail(NBS_ERR_INVALID, "nbs_import_peers: exports must be ordered by rank");
+        if (r == c.rank) {
+            c.peerSpectra[r] = c.dGridC.d; c.peerForce[r] = c.dForce.d; c.peerMailbox[r] = c.dMailbox.d;
+        }
+        else if (e.process_id == (int64_t) getpid()) {
+            if (e.device != c.device) {          // same process, another device: plain peer access
+                cudaError_t pe = cudaDeviceEnablePeerAccess(e.device, 0);
+                if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled)
+                    return fail(NBS_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(pe));
+                cudaGetLastError();
+            }
+            c.peerSpectra[r] = e.spectra; c.peerForce[r] = (unsigned long long*) e.forces; c.peerMailbox[r] = (PeerMailbox*) e.mailbox;
+        }
+        else {
+            if (!e.reserved) return fail(NBS_ERR_CUDA, "a peer could not export CUDA IPC handles for its buffers");
+            const unsigned char* handles[3] = {e.spectra_ipc, e.forces_ipc, e.mailbox_ipc};
+            void* mapped[3] = {nullptr, nullptr, nullptr};
+            for (int k = 0; k < 3; k++) {
+                cudaIpcMemHandle_t h;
+                std::memcpy(&h, handles[k], 64);
+                cudaError_t ie = cudaIpcOpenMemHandle(&mapped[k], h, cudaIpcMemLazyEnablePeerAccess);
+                if (ie != cudaSuccess) return fail(NBS_ERR_CUDA, std::string("cudaIpcOpenMemHandle (is peer-to-peer access available between the GPUs?): ") + cudaGetErrorString(ie));
+                c.peerOpened[3*r + k] = mapped[k];
+            }
+            c.peerSpectra[r] = mapped[0]; c.peerForce[r] = (unsigned long long*) mapped[1]; c.peerMailbox[r] = (PeerMailbox*) mapped[2];
+        }
+    }
+    c.peerBarrier = in_kernel_barrier != 0;
+    c.peersImported = true;
+    c.slabStep = 0;
+    return NBS_OK;
+}
+
 int nbs_execute_begin(nbs_context* ctx, const nbs_exec_args* args) {
     if (!ctx || !args) return fail(NBS_ERR_INVALID, "null argument");
     return phaseBegin(ctx->c, args);
@@ -1058,6 +1222,7 @@ int nbs_set_shard(nbs_context* ctx, int32_t rank, int32_t num_ranks, int32_t blo
     if (num_ranks > 1 && (c.method == NBS_METHOD_EWALD || c.method == NBS_METHOD_LJPME))
         return fail(NBS_ERR_UNSUPPORTED, "the plain Ewald sum and LJPME are not sharded across ranks (use PME)");
     c.rank = rank; c.nRanks = num_ranks;
+    c.slabMode = false; c.peersImported = false;
     c.paramVersion++;
     c.listEpoch++;
     c.blockPeriod = block_period; c.blockOffset = block_offset; c.blockWidth = block_width;

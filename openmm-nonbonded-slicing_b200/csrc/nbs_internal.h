@@ -97,6 +97,16 @@ struct CellGeom {                    // cell / column geometry of one evaluation
     float binH;                      // z-bin height (nm)
 };
 
+constexpr int ENERGY_WORDS = 2*MAX_SLICES + 8;   // slice table + [2*MAX_SLICES] = list-overflow flag (as a double, so it all-reduces)
+
+// Peer-memory sharding: one mailbox per rank, reachable by every rank of the node (CUDA IPC / same process).
+struct PeerMailbox {
+    unsigned long long arrive[NBS_MAX_RANKS];      // arrive[r] = number of barriers rank r has reached (written BY rank r)
+    unsigned long long epoch;                      // barriers this rank has reached (local)
+    unsigned long long timedOut;                   // epoch of a barrier that gave up waiting (0 = none)
+    double energies[NBS_MAX_RANKS][ENERGY_WORDS];  // energies[r] = rank r's slice-energy table of the evaluation in flight
+};
+
 struct KernelTimer {
     std::vector<const char*> names;
     std::vector<cudaEvent_t> events;      // events[i], events[i+1] bracket names[i]
@@ -214,6 +224,17 @@ struct Context {
     int blockPeriod = 1, blockOffset = 0, blockWidth = 1;
     int ownLo = 0, ownHi = 0;                // set to [0, nS) at creation
     int maxLocalBlocks = 0;
+    // peer-memory sharding (nbs_set_slab_shard): PME split by x-slabs over all ranks, x pass and force reduction over
+    // NVLink peer memory, barriers over flags in the peers' mailboxes
+    bool slabMode = false, peersImported = false, peerBarrier = false;
+    int xLo = 0, xHi = 0, yLo = 0, yHi = 0;     // own grid planes; own rows of the x pass
+    void* peerSpectra[NBS_MAX_RANKS] = {nullptr};
+    unsigned long long* peerForce[NBS_MAX_RANKS] = {nullptr};
+    PeerMailbox* peerMailbox[NBS_MAX_RANKS] = {nullptr};
+    void* peerOpened[3*NBS_MAX_RANKS] = {nullptr};          // IPC mappings to close
+    Buf<PeerMailbox> dMailbox;
+    unsigned long long* hTimedOut = nullptr;    // pinned copy of the mailbox's timedOut word
+    int slabStep = 0;                           // next step of the evaluation in flight
     bool pmeUnsorted = false;                // PME works from particle-order coordinates (forks before the sort)
     int chunkTiles = 2;                      // tiles per pair-kernel work item
     // ---- neighbour-list re-use (periodic cutoff methods): the list is built with cutoff + skin and kept until an
@@ -247,8 +268,6 @@ struct Context {
     long long graphLaunchCounts[2] = {0, 0}; // kernels per graph replay (for the launch counter)
 };
 
-constexpr int ENERGY_WORDS = 2*MAX_SLICES + 8;   // slice table + [2*MAX_SLICES] = list-overflow flag (as a double, so it all-reduces)
-
 __host__ __device__ inline int localToGlobalBlock(int local, int period, int offset, int width) {
     return (local/width)*period + offset + local % width;
 }
@@ -266,6 +285,8 @@ int launchPairs(Context& c, bool wantEnergy, int mode);         // mode 0: force
 int launchBonded(Context& c, const double* dPos, bool periodicBox);
 int launchPme(Context& c, bool wantEnergy, int half);    // half 0: spread..y forward; 1: x/conv..gather
 int launchFinalize(Context& c, void* dOut, int format, long long paddedAtoms, int accumulate, const int* atomIndex);
+int launchPeerBarrier(Context& c, bool publishEnergies);        // k_peer.cu
+int launchPeerReduce(Context& c);
 int launchEwald(Context& c, bool wantEnergy);               // plain Ewald reciprocal sum (k_ewald.cu)
 int uploadEwaldVectors(Context& c);
 int prepareEterm(Context& c);

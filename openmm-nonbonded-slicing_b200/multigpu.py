@@ -17,6 +17,16 @@ sharded where it shards naturally:
   * forces (64-bit fixed point -- integer sums are exact and order independent, so every rank ends up
     with bit-identical forces) and the slice-energy table are combined with NCCL all-reduce.
 
+A second scheme, PEER-MEMORY SHARDING (``SlabPlan``, ``connect_peers``, ``evaluate_peer``), removes what limits the
+one above (a subset's reciprocal work sits on one rank; 25 MB of force accumulators go through an all-reduce):
+
+  * PME is split by x-slabs of every subset grid over ALL ranks; the fused x pass reads and writes the other ranks'
+    planes over NVLink peer memory (the transposes of a slab-decomposed FFT, inside the kernel that consumes them);
+  * one kernel reduces the fixed-point force accumulators over peer memory (reduce-scatter + all-gather in place);
+  * the steps are ordered by barriers over flags in peer memory, so a sharded evaluation is ONE library call
+    (``nbs_execute``) with no collective on the data path.  NCCL is only used where a real exchange of host-side
+    data remains: the all-gather of position shards in the end-to-end path.
+
 ``torch.distributed`` is plumbing: the compute is the C ABI's three phases (include/nbslice_b200.h:
 nbs_execute_begin / _convolve / _finish), and the collectives are issued on the same CUDA stream in
 between.  The choreography is written against a small backend protocol so that the CPU tests can run
@@ -117,6 +127,60 @@ class ShardPlan:
                 "block_pattern": {"period": self.period, "widths": self.widths}}
 
 
+class SlabPlan:
+    """Peer-memory sharding: which rank owns which grid planes, x-pass rows, i-blocks and accumulator words.
+    Pure integer logic, identical on every rank and mirrored by the library (nbs_set_slab_shard, k_fft_x_conv2's
+    owner formula, launchPeerReduce)."""
+
+    def __init__(self, world_size, grid, direct_share=None, period=PATTERN_PERIOD):
+        if world_size < 1 or world_size > abi.NBS_MAX_RANKS:
+            raise ValueError("world_size must lie in 1 .. NBS_MAX_RANKS")
+        if min(grid[0], grid[1]) < world_size:
+            raise ValueError("more ranks than grid planes")
+        self.world_size = world_size
+        self.grid = tuple(int(g) for g in grid)
+        self.period = max(period, world_size)
+        if direct_share is None:
+            direct_share = [1.0]*world_size
+        if len(direct_share) != world_size or min(direct_share) < 0 or sum(direct_share) <= 0:
+            raise ValueError("direct_share needs one non-negative entry per rank and a positive sum")
+        self.widths = ShardPlan._apportion(direct_share, self.period)
+
+    def x_range(self, rank):
+        """Grid planes [lo, hi) whose spreading, z/y transforms and gather `rank` does."""
+        n, r = self.grid[0], self.world_size
+        return (rank*n//r, (rank+1)*n//r)
+
+    def y_range(self, rank):
+        """Rows [lo, hi) of the fused x pass that `rank` runs (reading every rank's planes)."""
+        n, r = self.grid[1], self.world_size
+        return (rank*n//r, (rank+1)*n//r)
+
+    def x_owner(self, x):
+        """The rank whose slab holds plane x -- the closed form the x kernel uses."""
+        return ((x + 1)*self.world_size - 1)//self.grid[0]
+
+    def block_share(self, rank):
+        return (self.period, sum(self.widths[:rank]), self.widths[rank])
+
+    @staticmethod
+    def word_range(rank, world_size, words):
+        """16-byte words [lo, hi) of the force accumulators that `rank` reduces (`words` of 16 bytes in total)."""
+        return (words*rank//world_size, words*(rank+1)//world_size)
+
+    def describe(self):
+        return {"world_size": self.world_size, "scheme": "peer memory: x-slabs of every subset grid, fused x pass and force reduction over NVLink",
+                "x_ranges": [self.x_range(r) for r in range(self.world_size)],
+                "block_pattern": {"period": self.period, "widths": self.widths}}
+
+
+def shard_rows(n, rank, world_size):
+    """Rows [lo, hi) of an n-row host array (positions in, forces out) that `rank` moves over PCIe; the shards are
+    padded to equal length `rows` for the all-gather."""
+    rows = (n + world_size - 1)//world_size
+    return min(n, rank*rows), min(n, (rank+1)*rows), rows
+
+
 # ---------------------------------------------------------------------------------------------------
 # Choreography (backend-agnostic).  A backend provides, for ONE rank:
 #   begin()                    -> None
@@ -152,6 +216,32 @@ def evaluate_distributed(plan, rank, backend, dist, pme_group, max_attempts=7):
         if result is not RETRY:
             return result
     raise RuntimeError("neighbour list capacity exceeded")
+
+
+def evaluate_peer_lockstep(backends, max_attempts=7):
+    """Peer-memory sharding with all ranks inside ONE process (several contexts on one device sharing a stream, or
+    NumPy stand-ins): the library's five steps, every rank finishing step k before any rank starts step k+1 --
+    the ordering the in-kernel barriers provide between processes."""
+    for _ in range(max_attempts):
+        results = None
+        for step in range(abi.NBS_NUM_STEPS):
+            results = [b.step(step) for b in backends]
+        if not any(r is RETRY for r in results):
+            return results
+        assert all(r is RETRY for r in results), "the overflow flag must reach every rank"
+    raise RuntimeError("neighbour list capacity exceeded")
+
+
+def connect_peers(kernel, plan, rank, dist, group=None, in_kernel_barrier=True):
+    """Set the shard, exchange the ranks' buffer exports (host-side plumbing) and map the peers' memory."""
+    kernel.set_slab_plan(plan, rank)
+    mine = kernel.export_peer()
+    if plan.world_size == 1:
+        exports = [mine]
+    else:
+        exports = [None]*plan.world_size
+        dist.all_gather_object(exports, mine, group=group)
+    kernel.import_peers(exports, in_kernel_barrier)
 
 
 def evaluate_lockstep(plan, backends, max_attempts=7):
@@ -209,6 +299,37 @@ class ShardedB200Kernel(B200CalcSlicedNonbondedForceKernel):
         period, offset, width = plan.block_share(rank)
         lo, hi = plan.subset_range(rank)
         abi.check(self.lib.nbs_set_shard(self.handle, rank, plan.world_size, period, offset, width, lo, hi))
+
+    # -- peer-memory sharding --------------------------------------------------------------------------
+    def set_slab_plan(self, plan, rank):
+        self.plan, self.rank = plan, rank
+        period, offset, width = plan.block_share(rank)
+        abi.check(self.lib.nbs_set_slab_shard(self.handle, rank, plan.world_size, period, offset, width))
+
+    def export_peer(self):
+        ex = abi.PeerExport()
+        ex.struct_size = C.sizeof(abi.PeerExport)
+        abi.check(self.lib.nbs_export_peer(self.handle, C.byref(ex)))
+        return bytes(ex)
+
+    def import_peers(self, exports, in_kernel_barrier=True):
+        array = (abi.PeerExport*len(exports))()
+        for k, blob in enumerate(exports):
+            C.memmove(C.byref(array[k]), blob, C.sizeof(abi.PeerExport))
+        abi.check(self.lib.nbs_import_peers(self.handle, len(exports), array, int(in_kernel_barrier)))
+
+    def step(self, k):
+        """One of the library's five steps (the caller orders the ranks); the last one returns the energies."""
+        status = self.lib.nbs_execute_step(self.handle, C.byref(self._args), k)
+        if status == abi.NBS_RETRY:
+            return RETRY
+        abi.check(status)
+        return self._energies if k == abi.NBS_NUM_STEPS-1 else None
+
+    def evaluate_peer(self):
+        """The whole sharded evaluation: one library call, barriers over peer memory inside."""
+        abi.check(self.lib.nbs_execute(self.handle, C.byref(self._args)))
+        return self._energies
 
     # -- backend protocol ---------------------------------------------------------------------------
     def prepare(self, positions_ptr, box, forces_ptr, lambdas, stream=0, want_energies=True,

@@ -18,7 +18,7 @@ def test_header_symbols_exported(nbs):
     assert declared == set(nbs.abi.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.nbs_abi_version() == nbs.abi.ABI_VERSION == 3
+    assert lib.nbs_abi_version() == nbs.abi.ABI_VERSION == 4
 
 
 def test_struct_sizes_match(nbs, tmp_path):

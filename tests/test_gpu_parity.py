@@ -636,8 +636,10 @@ def test_list_reuse_matches_rebuild(nbs, platform, systems, name, step):
         eb = fresh._evaluate(pos, s.box, lam, gv, True, True, fb)
         assert reuse.getPairSet(with_pairs=False)[:2] == fresh.getPairSet(with_pairs=False)[:2], t
         assert force_rel_rms(fa, fb) < 1e-5, t        # fp32 pair forces summed in a different order (the lists differ)
-        # (Coulomb terms are double precision: 1e-9; Lennard-Jones terms are fp32 sums per tile, whose order differs)
-        assert np.allclose(ea[:, 0], eb[:, 0], rtol=1e-9, atol=1e-7) and np.allclose(ea[:, 1], eb[:, 1], rtol=2e-7, atol=1e-6), t
+        # (Coulomb terms are double precision: 1e-9; Lennard-Jones terms are fp32 values summed in fp32 over a tile, and
+        # the tiles of a skin-padded list differ from those of a fresh one: measured up to 7e-7, held to 2e-6 -- a fifth
+        # of the parity tolerance against the oracle, which the last step is also held to below)
+        assert np.allclose(ea[:, 0], eb[:, 0], rtol=1e-9, atol=1e-7) and np.allclose(ea[:, 1], eb[:, 1], rtol=2e-6, atol=1e-6), t
     from oracle import oracle as cpu
     r = cpu.evaluate(reuse.desc, pos, s.box, lam, gv if len(gv) else None, True, True, kind="port")
     assert force_rel_rms(fa, r.forces) <= F_TOL and (r.pair_count, r.pair_hash) == reuse.getPairSet(with_pairs=False)[:2]

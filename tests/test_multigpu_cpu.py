@@ -218,3 +218,233 @@ def test_gloo_ranks_reproduce_the_serial_result(world, ns, share, overflow_rank)
         assert np.array_equal(f, ref_f)
         assert np.allclose(e, ref_e, rtol=1e-12, atol=1e-12)
         assert attempts == (2 if overflow_rank >= 0 else 1)
+
+
+# ====================================================================================================
+# Peer-memory sharding (SlabPlan): plan logic and a NumPy model of the five steps
+# ====================================================================================================
+SlabPlan = multigpu.SlabPlan
+
+
+@pytest.mark.parametrize("world,grid", [(1, (18, 18, 18)), (2, (18, 20, 24)), (3, (64, 64, 64)), (7, (45, 36, 50)), (8, (180, 180, 180)), (16, (16, 21, 16))])
+def test_slab_plan_partitions_planes_rows_blocks_and_words(world, grid):
+    plan = SlabPlan(world, grid)
+    xs, ys = [], []
+    for r in range(world):
+        lo, hi = plan.x_range(r)
+        assert hi > lo
+        xs += list(range(lo, hi))
+        assert all(plan.x_owner(x) == r for x in range(lo, hi))       # the closed form of k_fft_x_conv2
+        ys += list(range(*plan.y_range(r)))
+    assert xs == list(range(grid[0])) and ys == list(range(grid[1]))
+    assert sum(plan.widths) == plan.period
+    offsets = [plan.block_share(r)[1] for r in range(world)]
+    assert offsets == [sum(plan.widths[:r]) for r in range(world)]
+    words = 3*(1000 + 32)//2
+    covered = []
+    for r in range(world):
+        covered += list(range(*SlabPlan.word_range(r, world, words)))
+    assert covered == list(range(words))
+    with pytest.raises(ValueError):
+        SlabPlan(grid[0] + 1, grid)
+
+
+def test_shard_rows_cover_the_array():
+    for n, world in ((1066628, 8), (23558, 2), (10, 4), (7, 8)):
+        rows_seen, width = [], None
+        for r in range(world):
+            lo, hi, rows = multigpu.shard_rows(n, r, world)
+            width = rows
+            rows_seen += list(range(lo, hi))
+            assert hi - lo <= rows
+        assert rows_seen == list(range(n)) and width*world >= n
+
+
+class SlabWindows:
+    """What every rank can reach through peer memory: per rank its planes, its force accumulators and its mailbox.
+    In process the shards share ONE instance (true shared memory); under gloo each rank holds a private copy that
+    `sync` makes consistent at the points where the library has a barrier."""
+
+    def __init__(self, world, nx, nrows, ns, n, nsl):
+        self.world = world
+        self.planes = np.zeros((ns, nx, nrows), dtype=np.complex128)        # plane x lives on its owner; one array models all
+        self.force = np.zeros((world, 3*n), dtype=np.int64)
+        self.energy = np.zeros((world, 2*nsl + 1))
+
+
+class NumpySlabShard:
+    """One rank of a toy sliced PME in the peer scheme: atoms spread (order 2) onto nx planes x nrows rows per subset;
+    step 0 spreads the OWN planes, step 1 runs the x pass (DFT over x, slice energies, lambda mixing, inverse) for the OWN
+    rows reading and writing every rank's planes, step 2 gathers from the OWN planes and publishes energies, step 3
+    reduces the OWN words of all ranks' accumulators and writes them back, step 4 returns the result."""
+
+    def __init__(self, plan, rank, win, n=120, ns=3, nrows=5, seed=11, overflow_on_first_attempt=False, sync=None):
+        rng = np.random.default_rng(seed)
+        self.plan, self.rank, self.win, self.n, self.ns, self.nrows = plan, rank, win, n, ns, nrows
+        self.nx = plan.grid[0]
+        self.u = rng.random(n)*self.nx                       # plane coordinate
+        self.row_w = rng.normal(size=(n, nrows))             # an atom's weight on each row
+        self.q = rng.normal(size=n)
+        self.subset = rng.integers(0, ns, size=n)
+        self.nsl = ns*(ns+1)//2
+        self.lam = 0.25 + 0.75*rng.random(self.nsl)
+        self.eterm = 0.5 + rng.random((self.nx, nrows))
+        self.overflow_pending = overflow_on_first_attempt
+        self.attempts = 0
+        self.sync = sync or (lambda shard, step: None)
+
+    def _spline(self, i):
+        ix = int(np.floor(self.u[i])); w = self.u[i] - ix
+        return [(ix % self.nx, 1.0 - w), ((ix + 1) % self.nx, w)]
+
+    def step(self, k):
+        win, r = self.win, self.rank
+        xlo, xhi = self.plan.x_range(r)
+        if k == 0:
+            self.attempts += 1
+            win.planes[:, xlo:xhi, :] = 0
+            win.force[r] = 0
+            win.energy[r] = 0
+            if self.overflow_pending:
+                win.energy[r, 2*self.nsl] = 1.0
+            for i in range(self.n):
+                for x, w in self._spline(i):
+                    if xlo <= x < xhi:                                     # another rank's plane otherwise
+                        win.planes[self.subset[i], x, :] += self.q[i]*w*self.row_w[i]
+        elif k == 1:
+            ylo, yhi = self.plan.y_range(r) if self.nrows == self.plan.grid[1] else (r*self.nrows//self.plan.world_size, (r+1)*self.nrows//self.plan.world_size)
+            for y in range(ylo, yhi):
+                S = np.fft.fft(win.planes[:, :, y], axis=1)                # reads every rank's planes
+                for sa in range(self.ns):
+                    for sb in range(sa, self.ns):
+                        win.energy[r, 2*tri(sa, sb)] += (0.5 if sa == sb else 1.0)*float((self.eterm[:, y]*(S[sa]*np.conj(S[sb])).real).sum())
+                mixed = np.stack([self.eterm[:, y]*sum(self.lam[tri(si, sj)]*S[sj] for sj in range(self.ns)) for si in range(self.ns)])
+                win.planes[:, :, y] = np.fft.ifft(mixed, axis=1)           # writes every rank's planes
+        elif k == 2:
+            f = np.zeros((self.n, 3), dtype=np.int64)
+            for i in range(self.n):
+                for x, w in self._spline(i):
+                    if xlo <= x < xhi:
+                        g = float((win.planes[self.subset[i], x, :].real*self.row_w[i]).sum())
+                        f[i] += NumpyShard.fixed(np.array([self.q[i]*w*g, -self.q[i]*g, 0.5*self.q[i]*w*w*g]))
+            win.force[r] += f.reshape(-1)
+        elif k == 3:
+            words = 3*self.n
+            lo, hi = SlabPlan.word_range(r, self.plan.world_size, words)
+            total = win.force[:, lo:hi].sum(axis=0)                        # reads every rank's accumulators ...
+            win.force[:, lo:hi] = total                                    # ... and writes the sums back to all of them
+            self._energy = win.energy.sum(axis=0)
+        elif k == 4:
+            self.sync(self, k)
+            if self._energy[2*self.nsl] != 0.0:
+                self.overflow_pending = False
+                return multigpu.RETRY
+            return win.force[r].copy(), self._energy[:2*self.nsl].copy()
+        self.sync(self, k)
+        return None
+
+
+def slab_serial(**kw):
+    plan = SlabPlan(1, (12, 5, 4))
+    win = SlabWindows(1, 12, 5, 3, kw.get("n", 120), 6)
+    return multigpu.evaluate_peer_lockstep([NumpySlabShard(plan, 0, win, **kw)])[0]
+
+
+@pytest.mark.parametrize("world", [2, 3, 5])
+def test_peer_lockstep_shards_reproduce_the_serial_result(world):
+    ref_f, ref_e = slab_serial()
+    plan = SlabPlan(world, (12, 5, 4))
+    win = SlabWindows(world, 12, 5, 3, 120, 6)
+    shards = [NumpySlabShard(plan, r, win, overflow_on_first_attempt=(r == world-1)) for r in range(world)]
+    results = multigpu.evaluate_peer_lockstep(shards)
+    assert [s.attempts for s in shards] == [2]*world                       # the overflow flag reached every rank
+    for f, e in results:
+        # (halo atoms get their force in two fixed-point pieces instead of one: +-1 unit of 2^-32)
+        assert np.abs(f - ref_f).max() <= 2
+        assert np.array_equal(f, results[0][0])                            # identical on every rank
+        assert np.allclose(e, ref_e, rtol=1e-12, atol=1e-12)
+
+
+def _gloo_sync(dist, plan):
+    """Makes a rank's private copy of the windows consistent where the library has a barrier: what peers wrote or
+    published is fetched with collectives (gloo stands in for NVLink loads / stores)."""
+    def gather(t):
+        parts = [torch.zeros_like(t) for _ in range(plan.world_size)]
+        dist.all_gather(parts, t)
+        return parts
+
+    def sync(shard, step):
+        win, world = shard.win, plan.world_size
+        if step == 0:                     # every rank's own planes
+            parts = gather(torch.from_numpy(np.ascontiguousarray(np.stack([win.planes.real, win.planes.imag]))))
+            for r, p in enumerate(parts):
+                lo, hi = plan.x_range(r)
+                a = p.numpy()
+                win.planes[:, lo:hi, :] = a[0][:, lo:hi, :] + 1j*a[1][:, lo:hi, :]
+        elif step == 1:                   # every rank's rows of all planes
+            parts = gather(torch.from_numpy(np.ascontiguousarray(np.stack([win.planes.real, win.planes.imag]))))
+            for r, p in enumerate(parts):
+                lo, hi = r*shard.nrows//world, (r+1)*shard.nrows//world
+                a = p.numpy()
+                win.planes[:, :, lo:hi] = a[0][:, :, lo:hi] + 1j*a[1][:, :, lo:hi]
+        elif step == 2:                   # every rank's accumulators and published energies
+            for name in ("force", "energy"):
+                arr = getattr(win, name)
+                parts = gather(torch.from_numpy(arr[shard.rank].copy()))
+                for r, p in enumerate(parts):
+                    arr[r] = p.numpy()
+        elif step == 3:                   # every rank's reduced words
+            parts = gather(torch.from_numpy(win.force[shard.rank].copy()))
+            for r, p in enumerate(parts):
+                lo, hi = SlabPlan.word_range(r, world, win.force.shape[1])
+                win.force[:, lo:hi] = p.numpy()[lo:hi]
+    return sync
+
+
+def _peer_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        plan = SlabPlan(world, (12, 5, 4))
+        win = SlabWindows(world, 12, 5, 3, 120, 6)
+        shard = NumpySlabShard(plan, rank, win, overflow_on_first_attempt=(rank == 0), sync=_gloo_sync(dist, plan))
+        # end-to-end plumbing of bench.py's sharded path: every rank uploads its rows of the positions, the shards are
+        # all-gathered, and it downloads its rows of the forces
+        n = 120
+        full = np.arange(3.0*n).reshape(n, 3)
+        lo, hi, rows = multigpu.shard_rows(n, rank, world)
+        mine = torch.zeros((rows, 3), dtype=torch.float64)
+        mine[:hi-lo] = torch.from_numpy(full[lo:hi])
+        gathered = torch.zeros((world*rows, 3), dtype=torch.float64)
+        dist.all_gather_into_tensor(gathered, mine)
+        assert np.array_equal(gathered[:n].numpy(), full)
+        f, e = multigpu.evaluate_peer_lockstep([shard])[0]
+        out.put((rank, f, e, shard.attempts, (lo, hi)))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gloo_peer_ranks_reproduce_the_serial_result(world):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_peer_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = sorted([out.get(timeout=120) for _ in range(world)], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ref_f, ref_e = slab_serial()
+    rows = []
+    for _, f, e, attempts, (lo, hi) in results:
+        assert np.abs(f - ref_f).max() <= 2 and np.array_equal(f, results[0][1])
+        assert np.allclose(e, ref_e, rtol=1e-12, atol=1e-12)
+        assert attempts == 2
+        rows += list(range(lo, hi))
+    assert rows == list(range(120))

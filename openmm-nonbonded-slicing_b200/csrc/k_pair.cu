@@ -58,7 +58,7 @@ struct PairArgs {
     double rc2d, alphaD, krfD, crfD;
     float dalpha2, invCut6, shiftMult;   // LJPME: alpha_d^2, rc^-6, rc^-6 (1 - exp(-x)(1 + x + x^2/2)) at x = (alpha_d rc)^2
     const double* q64;                   // sorted charges * sqrt(ONE_4PI_EPS0), double
-    const double* erfcTab;               // piecewise degree-7 fit of erfc(alpha sqrt(s))/sqrt(s) in s = r^2, [coefficient][tabRows]
+    const double* erfcTab;               // piecewise fit of erfc(alpha sqrt(s))/sqrt(s) in s = r^2: c0[tabRows], float4 (c1..c4)[tabRows]
     int tabRows;
     int* counters;                       // [2] number of work items, [3] cursor
     const int4* items;                   // (local block, first tile, first atom of the block, atoms in the block)
@@ -189,9 +189,13 @@ __device__ __forceinline__ LatticeShift crossShift(int parz, const PairArgs& a) 
 //     are sums of 10^4..10^8 terms of both signs and single precision cannot deliver 1e-5 of a small net value
 //     (DESIGN.md "Precision").  r^2 is formed in 64-bit INTEGER arithmetic when the box is cubic (one conversion to
 //     double; conversions are the scarce resource: 0.45 warp instructions per clock and SM against 1.6 for DFMA,
-//     profiles/r02_peaks.json), f(s) = erfc(alpha sqrt(s))/sqrt(s) comes from the CTA's shared-memory table of
-//     degree-7 polynomials in s (16 intervals per octave; index and interval position straight from the bits of the
-//     double).  With the exact r^2 at hand the cutoff decision is exact too: no borderline branch.
+//     profiles/r02_peaks.json), f(s) = erfc(alpha sqrt(s))/sqrt(s) comes from the CTA's shared-memory table: per row
+//     (128 per octave of s; row and position inside it straight from the bits of the double) c0 in double and a
+//     degree-4 remainder in SINGLE precision -- the remainder is at most 3 % of f, so its single-precision rounding is
+//     3e-9 of f (ERFC_TAB_* in nbs_internal.h).  qq c0 is summed in double, qq (f - c0) in single precision per tile:
+//     two double-precision instructions and two shared-memory loads per pair (the first table was a degree-7 double
+//     Horner chain: eight loads, twelve double-precision instructions, 60 % of the kernel's shared-memory wavefronts).
+//     With the exact r^2 at hand the cutoff decision is exact too: no borderline branch.
 //   * Lennard-Jones: the step's fp32 value, summed in fp32 over a tile and in double across tiles.
 //   * a tile whose i atoms share one subset and whose j atoms share one subset -- almost all of them -- adds into two
 //     registers; mixed tiles go through the per-lane slice table in local memory.
@@ -269,16 +273,16 @@ __device__ __forceinline__ void pairStep(WarpScratch& w, const PairArgs& a, cons
     float fv = eps*fmaf(12.f, s6, -6.f)*s6*invR2;
     float invE2 = invR2;                          // 1/r^2 for the energy terms
     if (EMODE == 2) {
-        // Lennard-Jones ENERGY from the exact r^2: one Newton step of 1/sqrt from the force path's value takes out
-        // both the approximation error of rsqrt and the ~6e-7 of the tile-relative fp32 coordinates (r^-12 would
-        // turn that into 4e-6 per close contact: visible in small slices such as protein-ligand)
+        // Lennard-Jones ENERGY at the exact r^2: the force path evaluated E at the distance rho with 1/rho = invR, which
+        // differs from the exact one by the approximation error of rsqrt and the ~6e-7 of the tile-relative fp32
+        // coordinates (r^-12 would turn that into 4e-6 per close contact: visible in small slices such as
+        // protein-ligand).  First order in the difference: E(r^2) = E(rho^2) + dE/d(r^2) (r^2 - rho^2), with
+        // dE/d(r^2) = -fv/2 and r^2 - rho^2 = -(1 - r^2 invR^2)/invR^2 -- three instructions instead of a second evaluation
+        // (the second-order term is 1e-12 of E).
         const float r2e = (float) r2d;
-        const float invE = invR*fmaf(-0.5f*r2e*invR, invR, 1.5f);
-        invE2 = invE*invE;
-        float t2 = (ipar.x + s.jsig)*invE;
-        t2 *= t2;
-        const float t6 = t2*t2*t2;
-        ev = eps*(t6 - 1.f)*t6;
+        const float t = fmaf(-r2e, invR2, 1.f);
+        ev = fmaf(0.5f*eps*fmaf(12.f, s6, -6.f)*s6, t, ev);
+        if (CMODE == 2) invE2 = invR2*(1.f + t);  // LJPME's extra r^-6 term below, to the same order
     }
     const float qr = ip.w*s.jq*invR;
     float ec, fc;
@@ -329,26 +333,29 @@ __device__ __forceinline__ void pairStep(WarpScratch& w, const PairArgs& a, cons
     if (EMODE == 0) return;
 
     // ---- energies ----
+    // EMODE 2: K q_i q_j f(r^2) = qq c0 (double) + qq (f - c0) (single: the remainder is a few per cent of f)
     double ecd = 0.0;
+    float ecRem = 0.f;
     if (EMODE == 2) {
         const double qq = __hiloint2double((int) w.iQhi[is], (int) w.iQlo[is])*s.jq64;
         if (IS_PME) {
-            // table row and position inside its interval from the bits of r^2: the exponent and the top four mantissa
-            // bits are the row; d = s 2^(5-e) - (33 + 2 m) in [-1, 1], both factors assembled as bit patterns
+            // table row and position inside its interval straight from the bits of r^2: exponent and top seven mantissa
+            // bits are the row, the next 23 mantissa bits the position d in [-1/2, 1/2) (centred: + half a unit)
+            constexpr int L = ERFC_TAB_PER_OCTAVE_LOG2;
             const int hi = __double2hiint(r2d);
-            const int idx = (hi >> (20 - ERFC_TAB_PER_OCTAVE_LOG2)) - ((1023 - 7) << ERFC_TAB_PER_OCTAVE_LOG2);
+            const unsigned lo = (unsigned) __double2loint(r2d);
+            const int idx = (hi >> (20 - L)) - ((1023 - 7) << L);
             // (a pair beyond the table -- far outside the cutoff, or closer than 0.088 nm -- reads the nearest row; its
             // value is only used, and then replaced by the analytic form, if the pair is inside the cutoff)
             const int row = min(max(idx, 0), a.tabRows - 1);
-            const double scale = __hiloint2double((2046 + 1 + ERFC_TAB_PER_OCTAVE_LOG2 - ((hi >> 20) & 0x7ff)) << 20, 0);
-            const int m = (hi >> (20 - ERFC_TAB_PER_OCTAVE_LOG2)) & ((1 << ERFC_TAB_PER_OCTAVE_LOG2) - 1);
-            const double m2 = __hiloint2double(((1023 + 1 + ERFC_TAB_PER_OCTAVE_LOG2) << 20) | ((2*m + 1) << (20 - 1 - ERFC_TAB_PER_OCTAVE_LOG2)), 0);
-            const double d = fma(r2d, scale, -m2);
-            double p = tab[row];
-#pragma unroll
-            for (int k = 1; k <= ERFC_TAB_DEGREE; k++) p = fma(p, d, tab[k*ERFC_TAB_MAX_ROWS + row]);
-            if (in && row != idx) p = erfcOverRAnalytic(r2d, a.alphaD);           // rare
-            ecd = qq*p;
+            const unsigned frac = (((unsigned) hi & ((1u << (20 - L)) - 1u)) << (3 + L)) | (lo >> (29 - L));
+            const float d = (__uint_as_float(0x3f800000u | frac) - 1.5f) + 5.9604645e-8f;
+            double c0 = tab[row];
+            const float4 cf = reinterpret_cast<const float4*>(tab + ERFC_TAB_MAX_ROWS)[row];
+            ecRem = d*fmaf(d, fmaf(d, fmaf(d, cf.w, cf.z), cf.y), cf.x);
+            if (in && row != idx) { c0 = erfcOverRAnalytic(r2d, a.alphaD); ecRem = 0.f; }           // rare
+            ecd = qq*c0;
+            ecRem *= ip.w*s.jq;
         }
         else {
             double y = (double) invR;                              // reaction field (:598-624): 1/r + krf r^2 - crf
@@ -358,13 +365,13 @@ __device__ __forceinline__ void pairStep(WarpScratch& w, const PairArgs& a, cons
         }
     }
     if (s.uniform) {
-        if (EMODE == 2) s.ecTile += in ? ecd : 0.0;
+        if (EMODE == 2) { s.ecTile += in ? ecd : 0.0; s.ecTileF += in ? ecRem : 0.f; }
         else s.ecTileF += in ? ec : 0.f;
         s.evTile += in ? ev : 0.f;
     }
     else if (in) {
         const int sl = triSlice(siOff/MAX_SUBSETS, s.sj);
-        acc[2*sl] += EMODE == 2 ? ecd : (double) ec;
+        acc[2*sl] += EMODE == 2 ? ecd + (double) ecRem : (double) ec;
         acc[2*sl+1] += (double) ev;
     }
 }
@@ -432,8 +439,9 @@ __global__ void __launch_bounds__(PAIR_WARPS*32, MINCTAS) k_pair(const PairArgs 
     // EMODE 2: the CTA's copy of the erfc table, behind the warps' scratch areas ([coefficient][ERFC_TAB_MAX_ROWS])
     double* const shTab = reinterpret_cast<double*>(smemRaw + sizeof(WarpScratch)*PAIR_WARPS);
     if (EMODE == 2 && MODE == 0 && CMODE != 0) {
-        for (int k = threadIdx.x; k < (ERFC_TAB_DEGREE + 1)*a.tabRows; k += blockDim.x)
-            shTab[(k / a.tabRows)*ERFC_TAB_MAX_ROWS + k % a.tabRows] = a.erfcTab[k];
+        // (c0[tabRows] doubles, then the rows' float4 coefficient sets as pairs of 8-byte words)
+        for (int k = threadIdx.x; k < 3*a.tabRows; k += blockDim.x)
+            shTab[k < a.tabRows ? k : ERFC_TAB_MAX_ROWS + (k - a.tabRows)] = a.erfcTab[k];
     }
     if (threadIdx.x < MAX_SUBSETS*MAX_SUBSETS) {
         const int sl = triSlice(threadIdx.x / MAX_SUBSETS, threadIdx.x % MAX_SUBSETS);
@@ -588,7 +596,7 @@ __global__ void __launch_bounds__(PAIR_WARPS*32, MINCTAS) k_pair(const PairArgs 
             }
             tileLoop<EMODE, CMODE, MODE, CUBIC>(w, a, shLam, shTab, lane, gmWord, isX, jIndex, entry >= 0, s, fi, acc);
             if (EMODE != 0 && MODE == 0 && s.uniform) {
-                regC += EMODE == 2 ? s.ecTile : (double) s.ecTileF;
+                regC += EMODE == 2 ? s.ecTile + (double) s.ecTileF : (double) s.ecTileF;
                 regV += (double) s.evTile;
             }
         }
@@ -653,7 +661,7 @@ __global__ void __launch_bounds__(PAIR_WARPS*32, MINCTAS) k_pair(const PairArgs 
 template <int EMODE, int CMODE, int MODE, bool CUBIC, int MINCTAS>
 static int launchPairK(Context& c, const PairArgs& a) {
     static bool attr[64] = {false};
-    const size_t smem = sizeof(WarpScratch)*PAIR_WARPS + (EMODE == 2 && MODE == 0 && CMODE != 0 ? sizeof(double)*(ERFC_TAB_DEGREE + 1)*ERFC_TAB_MAX_ROWS : 0);
+    const size_t smem = sizeof(WarpScratch)*PAIR_WARPS + (EMODE == 2 && MODE == 0 && CMODE != 0 ? sizeof(double)*3*ERFC_TAB_MAX_ROWS : 0);
     if (!attr[c.device & 63]) {
         NBS_CUDA_CHECK(cudaFuncSetAttribute(k_pair<EMODE, CMODE, MODE, CUBIC, MINCTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
         attr[c.device & 63] = true;

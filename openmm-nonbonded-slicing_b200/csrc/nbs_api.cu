@@ -285,25 +285,27 @@ int uploadPmeTables(Context& c) {
 }
 
 // Piecewise polynomial table of f(s) = erfc(alpha sqrt(s))/sqrt(s) for the double-precision pair energies
-// (k_pair.cu pairEnergyD): degree-7 interpolation at Chebyshev nodes on every interval [2^e (1 + m/16),
-// 2^e (1 + (m+1)/16)), e = -7 .. floor(log2 cutoff^2) + 1; relative error 5e-12 (ERFC_TAB_* in nbs_internal.h).
+// (k_pair.cu pairStep): degree-4 interpolation at Chebyshev nodes on every interval [2^e (1 + m/128),
+// 2^e (1 + (m+1)/128)), e = -7 .., in the variable d = (s - centre)/width; c0 in double, c1..c4 in single precision
+// (ERFC_TAB_* in nbs_internal.h).  Built from libm's long-double erfc.
 static int buildErfcTable(Context& c) {
-    const int eMax = std::min(8, std::max(-6, (int) std::floor(std::log2(c.cutoff*c.cutoff)) + 1));
     const int M = 1 << ERFC_TAB_PER_OCTAVE_LOG2;
+    const int eMax = std::min(ERFC_TAB_MAX_ROWS/M - 8, std::max(-6, (int) std::floor(std::log2(c.cutoff*c.cutoff)) + 1));
     const int rows = (eMax + 7 + 1)*M;
-    constexpr int D = ERFC_TAB_DEGREE;
-    std::vector<double> tab((size_t) rows*(D + 1), 0.0);
+    constexpr int D = 4;
+    std::vector<double> tab((size_t) rows*3, 0.0);               // c0[rows], then float4[rows] = 2 doubles per row
+    float* coef = reinterpret_cast<float*>(tab.data() + rows);
     for (int e = -7; e <= eMax; e++)
         for (int m = 0; m < M; m++) {
             const long double lo = std::ldexp(1.0L + m/(long double) M, e), w = std::ldexp(1.0L/M, e);
             const long double center = lo + w/2;
             long double A[D + 1][D + 2];
             for (int k = 0; k <= D; k++) {
-                const long double xn = std::cos(3.14159265358979323846264338327950288L*(2*k + 1)/(2.0L*(D + 1)));
-                const long double sv = center + xn*w/2;
+                const long double dn = 0.5L*std::cos(3.14159265358979323846264338327950288L*(2*k + 1)/(2.0L*(D + 1)));
+                const long double sv = center + dn*w;
                 const long double r = std::sqrt(sv);
                 long double pw = 1;
-                for (int j = 0; j <= D; j++) { A[k][j] = pw; pw *= xn; }
+                for (int j = 0; j <= D; j++) { A[k][j] = pw; pw *= dn; }
                 A[k][D + 1] = std::erfc((long double) c.alpha*r)/r;
             }
             for (int col = 0; col <= D; col++) {                 // Gaussian elimination, partial pivoting
@@ -317,7 +319,8 @@ static int buildErfcTable(Context& c) {
                 }
             }
             const int row = (e + 7)*M + m;
-            for (int k = 0; k <= D; k++) tab[(size_t) (D - k)*rows + row] = (double) (A[k][D + 1]/A[k][k]);     // a7 first
+            tab[row] = (double) (A[0][D + 1]/A[0][0]);
+            for (int k = 1; k <= D; k++) coef[4*(size_t) row + k - 1] = (float) (A[k][D + 1]/A[k][k]);
         }
     c.erfcRows = rows;
     NBS_CUDA_CHECK(c.dErfcTab.ensure(tab.size()));

@@ -31,15 +31,15 @@ constexpr double kOne4PiEps0 = 1/(4*kPi*kEpsilon0);
 constexpr int MAX_SUBSETS = 8;
 constexpr int MAX_SLICES = MAX_SUBSETS*(MAX_SUBSETS+1)/2;
 constexpr int PME_ORDER = 5;
-// Table of f(s) = erfc(alpha sqrt(s))/sqrt(s), s = r^2, for the double-precision pair energies: 16 intervals per octave
-// of s starting at s = 2^-7 (interval index = (bits of (float) s >> 19) - ERFC_TAB_BASE), one degree-7 polynomial in
-// d = s 2^(5-e) - (33 + 2 m) in [-1, 1] per interval (e = exponent of s, m = interval inside the octave; relative
-// error 5e-12).  Stored coefficient-major (tab[k][row], a7 first) so that a warp's gather of one coefficient from
-// shared memory hits distinct banks for the rows of an octave; ERFC_TAB_MAX_ROWS rows fit the pair kernel's copy.
-constexpr int ERFC_TAB_PER_OCTAVE_LOG2 = 4;
-constexpr int ERFC_TAB_BASE = (127 - 7) << ERFC_TAB_PER_OCTAVE_LOG2;
-constexpr int ERFC_TAB_DEGREE = 7;
-constexpr int ERFC_TAB_MAX_ROWS = 256;           // up to s = 2^9 nm^2
+// Table of f(s) = erfc(alpha sqrt(s))/sqrt(s), s = r^2, for the double-precision pair energies: 128 intervals per octave
+// of s starting at s = 2^-7; row = exponent and top seven mantissa bits of the double s.  A row holds c0 = P(0) in DOUBLE
+// and c1..c4 in SINGLE precision of the degree-4 interpolant P(d) = c0 + d (c1 + d (c2 + d (c3 + d c4))) at Chebyshev nodes,
+// d in [-1/2, 1/2) the position inside the interval (the next 23 mantissa bits of s).  The remainder d (c1 + ...) is at
+// most 3 % of f, so evaluating it in single precision costs 3e-9 of f (rounding, zero mean; bias per row below 3e-10:
+// tools/erfc_table_check.py restates the scheme in NumPy) while the energy path needs ONE double-precision product per
+// pair instead of an eight-term double-precision Horner chain and two shared-memory loads instead of eight.
+constexpr int ERFC_TAB_PER_OCTAVE_LOG2 = 7;
+constexpr int ERFC_TAB_MAX_ROWS = 1280;          // 10 octaves: up to s = 2^3 nm^2; pairs beyond take the analytic branch
 // A list entry is (image code << J_SHIFT_BITS) | sorted index; image code = (kx+2) + 5 ((ky+1) + 3 (kz+1)) with
 // kx in -2..2 (a triclinic box's b and c vectors shift x by up to ax/2 each), ky, kz in -1..1: 45 codes, 6 bits.
 constexpr int J_SHIFT_BITS = 25;                 // sorted index in the low 25 bits of a list entry
@@ -186,7 +186,7 @@ struct Context {
     Buf<double> dEtermD;
     Buf<double2> dTwiddleD;
     Buf<double> dModuli;                     // [nx+ny+nz]
-    Buf<double> dErfcTab;                    // [ERFC_TAB_DEGREE + 1][erfcRows], see ERFC_TAB_*
+    Buf<double> dErfcTab;                    // c0[erfcRows] (double) followed by (c1, c2, c3, c4)[erfcRows] (float4), see ERFC_TAB_*
     int erfcRows = 0;
     Buf<float2> dTwiddle;                    // [nx+ny+nz]
     // LJPME keeps a second set of the tables that depend on (alpha, grid)

@@ -414,8 +414,21 @@ def calibrate_plan(kernel_factory, world_size, num_subsets, run_once):
 
 
 # ---------------------------------------------------------------------------------------------------
-# bench.py --gpus N (N > 1): strong scaling of one evaluation of the STMV-size system
+# bench.py under torch.distributed.run (any N, including 1): strong scaling of the STMV-size system
 # ---------------------------------------------------------------------------------------------------
+def c5_fixture_errors(golden, forces, energies, tag="full"):
+    """Parity figures of a C5 evaluation against tests/golden/C5_reference.npz (the reference's own full-size CPU
+    evaluation, oracle/make_golden_c5.py): relative RMS force error over the fixture's 4,096-atom sample, relative
+    error of sum |F|^2 over all atoms, worst slice-energy error over max(|E|, 1)."""
+    idx = golden["sample"]
+    ref = golden[f"{tag}_forces_sample"]
+    f_err = float(np.sqrt(((forces[idx]-ref)**2).sum()/(ref**2).sum()))
+    sumsq_err = float(abs((forces**2).sum()/golden[f"{tag}_force_sumsq"][0] - 1.0))
+    ref_e = golden[f"{tag}_energies"]
+    e_err = float(np.max(np.abs(energies-ref_e)/np.maximum(np.abs(ref_e), 1.0)))
+    return f_err, sumsq_err, e_err
+
+
 def bench_main(args, workload_name):
     import importlib
     import torch
@@ -431,156 +444,201 @@ def bench_main(args, workload_name):
     dist.init_process_group("nccl", device_id=dev)
     s = systems.make_system(workload_name)
     n, nsl, ns = s.force.getNumParticles(), s.force.getNumSlices(), s.force.getNumSubsets()
+    grid = s.force.getPMEParameters()[1:]
     lam = np.ones((nsl, 2))
-    pos_dev = torch.tensor(s.positions, dtype=torch.float64, device=dev).contiguous()
+    moving = bench.MovingSystem(s.positions, dev)
     frc_dev = torch.zeros((n, 3), dtype=torch.float64, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
+    flush = torch.empty(256*1024*1024, dtype=torch.uint8, device=dev)
+    warmup = max(args.warmup, 3)
 
     def factory(flags):
         k = ShardedB200Kernel(Platform(deviceIndex=local, flags=flags))
         k.initialize(s.system, s.force)
         return k
 
-    def run_alone(k):
-        k.prepare(pos_dev.data_ptr(), s.box, frc_dev.data_ptr(), lam, stream=stream)
-        return evaluate_distributed(ShardPlan(1, ns), 0, k, dist, None)
-
-    # rank 0 calibrates, everybody adopts its plan; it also times the SAME workload unsharded on its one GPU, so
-    # that the line carries its own strong-scaling reference point
-    payload = [None]
-    if rank == 0:
-        plan, calibration = calibrate_plan(factory, world, ns, run_alone)
-        single = B200CalcSlicedNonbondedForceKernel(Platform(deviceIndex=local))
-        single.initialize(s.system, s.force)
-        single_ms = []
-        for it in range(6):
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize()
-            a.record()
-            single.execute_device(pos_dev.data_ptr(), s.box, frc_dev.data_ptr(), lam, stream=stream)
-            b.record()
-            torch.cuda.synchronize()
-            if it >= 3:
-                single_ms.append(a.elapsed_time(b))
-        del single
-        calibration["single_gpu_ms_per_step"] = float(np.mean(single_ms))
-        payload = [(plan.widths, calibration)]
-    dist.broadcast_object_list(payload, src=0)
-    widths, calibration = payload[0]
-    plan = ShardPlan(world, ns, [float(w) for w in widths])
-    pme_group = dist.new_group(plan.pme_ranks()) if plan.num_pme_ranks > 1 else None
-
+    # ---- the sharding scheme: peer memory (CUDA IPC over NVLink) on every rank, or -- if any rank cannot map its
+    # peers -- the NCCL scheme of round 1 (subset grids on their owners, all-reduce of the accumulators) -----------------
+    plan = SlabPlan(world, grid)
     kernel = factory(0)
-    kernel.set_plan(plan, rank)
-    flush = torch.empty(256*1024*1024, dtype=torch.uint8, device=dev)
+    ok, why = 1, ""
+    try:
+        connect_peers(kernel, plan, rank, dist)
+    except Exception as exc:                       # noqa: BLE001 -- reported in the line; the other GPU scheme is used
+        ok, why = 0, str(exc)
+    flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    peer_mode = bool(flag.item())
+    pme_group = None
+    if not peer_mode:
+        del kernel
+        plan = ShardPlan(world, ns)
+        pme_group = dist.new_group(plan.pme_ranks()) if plan.num_pme_ranks > 1 else None
+        kernel = factory(0)
+        kernel.set_plan(plan, rank)
 
-    def step():
-        kernel.prepare(pos_dev.data_ptr(), s.box, frc_dev.data_ptr(), lam, stream=stream)
-        return evaluate_distributed(plan, rank, kernel, dist, pme_group)
+    def evaluate(k, positions_ptr, want=True):
+        k.prepare(positions_ptr, s.box, frc_dev.data_ptr(), lam, stream=stream, want_energies=want)
+        if peer_mode:
+            return k.evaluate_peer()
+        return evaluate_distributed(plan, rank, k, dist, pme_group)
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    torch.cuda.synchronize()
-    dist.barrier()
-    launches0 = kernel.getLaunchCount()
+    def barrier():
+        dist.barrier()
+
+    def timed(step, steps, trajectory=moving):
+        per_step, result = bench.timed_steps(step, trajectory, flush, warmup, steps, barrier=barrier)
+        t = torch.tensor(per_step, dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)               # max over ranks, step by step
+        return float(t.mean().item()), result
+
+    # ---- device-resident throughput of the moving system ----------------------------------------------------------------
+    timed(lambda: evaluate(kernel, moving.pos.data_ptr()), 0)
+    launches0, stats0 = kernel.getLaunchCount(), kernel.getListStats()
     sampler = bench.ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.__enter__()
-    # device-resident throughput: per-step CUDA events, L2 flushed between steps outside the events
-    per_step = []
-    for _ in range(args.steps):
-        flush.fill_(1)
-        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        dist.barrier()
-        torch.cuda.synchronize()
-        start.record()
-        energies = step()
-        end.record()
-        if sampler:
-            sampler.sample_now()
-        torch.cuda.synchronize()
-        per_step.append(start.elapsed_time(end))
+    per_step, energies = bench.timed_steps(lambda: evaluate(kernel, moving.pos.data_ptr()), moving, flush, 0, args.steps, barrier=barrier)
     if sampler:
+        sampler.sample_now()
         sampler.__exit__()
     launches = kernel.getLaunchCount()-launches0
+    policy = bench.list_policy(stats0, kernel.getListStats())
     t = torch.tensor(per_step, dtype=torch.float64, device=dev)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)               # max over ranks, step by step
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.mean().item())
     value = 1e3/ms
+    forces_ms, _ = timed(lambda: evaluate(kernel, moving.pos.data_ptr(), want=False), args.steps)
 
-    # end to end: host positions in, host forces + energies out, every step
-    pos_host = torch.tensor(s.positions, dtype=torch.float64).pin_memory()
-    frc_host = torch.zeros((n, 3), dtype=torch.float64).pin_memory()
+    # ---- end to end: every rank uploads ITS rows of the positions (pinned host memory), the shards are all-gathered over
+    # NVLink, and every rank downloads ITS rows of the forces; energies go to the host on every rank ---------------------
+    lo, hi, rows = shard_rows(n, rank, world)
+    pos_shard_host = torch.zeros((rows, 3), dtype=torch.float64).pin_memory()
+    frc_shard_host = torch.zeros((rows, 3), dtype=torch.float64).pin_memory()
+    pos_shard_dev = torch.zeros((rows, 3), dtype=torch.float64, device=dev)
+    pos_all = torch.zeros((world*rows, 3), dtype=torch.float64, device=dev)
     e2e = []
-    for it in range(args.warmup + args.steps):
+    for it in range(warmup + args.steps):
+        pos_shard_host[:hi-lo] = torch.from_numpy(moving.host_positions(it, lo, hi))
         flush.fill_(1)
         torch.cuda.synchronize()
         dist.barrier()
+        torch.cuda.synchronize()
         t0 = time.perf_counter()
-        pos_dev.copy_(pos_host, non_blocking=True)
-        step()
-        frc_host.copy_(frc_dev, non_blocking=True)
+        pos_shard_dev.copy_(pos_shard_host, non_blocking=True)
+        if world > 1:
+            dist.all_gather_into_tensor(pos_all, pos_shard_dev)
+        else:
+            pos_all.copy_(pos_shard_dev)
+        e_host = evaluate(kernel, pos_all.data_ptr())
+        frc_shard_host[:hi-lo].copy_(frc_dev[lo:hi], non_blocking=True)
         torch.cuda.synchronize()
         dt = time.perf_counter()-t0
-        if it >= args.warmup:
+        if it >= warmup:
             e2e.append(dt)
     te = torch.tensor(e2e, dtype=torch.float64, device=dev)
     dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = 1.0/float(te.mean().item())
 
+    # ---- parity of THIS job against the reference's own full-size evaluation (committed fixture), un-moved positions -----
+    parity = None
+    fixture = os.path.join(bench.ROOT, "tests", "golden", f"{workload_name}_reference.npz")
+    frozen = bench.MovingSystem(s.positions, dev)
+    if workload_name == "C5" and os.path.exists(fixture):
+        g = np.load(fixture)
+        kernel.prepare(frozen.pos.data_ptr(), s.box, frc_dev.data_ptr(), g["lambdas"], stream=stream)
+        e_fix = kernel.evaluate_peer() if peer_mode else evaluate_distributed(plan, rank, kernel, dist, pme_group)
+        torch.cuda.synchronize()
+        f_err, sumsq_err, e_err = c5_fixture_errors(g, frc_dev.cpu().numpy(), e_fix)
+        local_pairs = kernel.getPairSet(with_pairs=False)
+        pairs = torch.tensor([local_pairs[0]], dtype=torch.int64, device=dev)
+        dist.all_reduce(pairs)
+        hashes = [None]*world
+        dist.all_gather_object(hashes, int(local_pairs[1]))
+        worst = torch.tensor([f_err, sumsq_err, e_err], dtype=torch.float64, device=dev)
+        dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+        parity = {"fixture": "tests/golden/C5_reference.npz (the reference's own full-size CPU evaluation)",
+                  "force_rel_rms_4096_atom_sample": float(worst[0].item()), "sum_F2_rel_err": float(worst[1].item()),
+                  "max_energy_err_over_max_absE_1": float(worst[2].item()), "worst_over_ranks": True,
+                  "pair_count_matches": int(pairs.item()) == int(g["pair_count"][0]),
+                  "pair_hash_matches": sum(hashes) % 2**64 == int(g["pair_hash"][0])}
     local_pairs = kernel.getPairSet(with_pairs=False)[0]
     pairs = torch.tensor([local_pairs], dtype=torch.int64, device=dev)
     dist.all_reduce(pairs)
-    # per-kernel durations of THIS rank's shard (profiled context: serial streams, CUDA events per kernel)
-    prof = factory(abi.NBS_FLAG_PROFILE)
-    prof.set_plan(plan, rank)
-    acc = {}
-    for it in range(5):
-        flush.fill_(1)
-        torch.cuda.synchronize()
-        prof.prepare(pos_dev.data_ptr(), s.box, frc_dev.data_ptr(), lam, stream=stream)
-        evaluate_distributed(plan, rank, prof, dist, pme_group)
-        if it >= 2:
-            for name, t in prof.getKernelTimes():
-                acc[name] = acc.get(name, 0.0) + t/3
-    del prof
-    # the roofline is reported for the rank whose pair kernel ran longest
-    shares = [None]*world
-    dist.all_gather_object(shares, (acc.get("pair", 0.0), local_pairs, rank))
-    slow_ms, slow_pairs, slow_rank = max(shares)
-    checksum = float(np.abs(energies).sum())
     fsum = frc_dev.abs().sum().reshape(1)
     fmin, fmax = fsum.clone(), fsum.clone()
     dist.all_reduce(fmin, op=dist.ReduceOp.MIN)
     dist.all_reduce(fmax, op=dist.ReduceOp.MAX)
+
+    # ---- per-kernel durations of THIS rank's shard (profiled context: serial streams, CUDA events per kernel) ------------
+    prof = factory(abi.NBS_FLAG_PROFILE)
+    if peer_mode:
+        connect_peers(prof, plan, rank, dist)
+    else:
+        prof.set_plan(plan, rank)
+    acc = {}
+    for it in range(6):
+        frozen.advance(0)
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        dist.barrier()
+        evaluate(prof, frozen.pos.data_ptr())
+        if it >= 3:
+            for name, tms in prof.getKernelTimes():
+                acc[name] = acc.get(name, 0.0) + tms/3
+    del prof
+    shares = [None]*world
+    dist.all_gather_object(shares, (acc.get("pair", 0.0), local_pairs, rank))
+    slow_ms, slow_pairs, slow_rank = max(shares)
+    all_acc = [None]*world
+    dist.all_gather_object(all_acc, {k: round(v, 5) for k, v in acc.items()})
+
+    # ---- the same workload, same protocol, unsharded on ONE GPU (rank 0 alone; the others wait) ----------------------------
+    single = None
+    if world > 1:
+        if rank == 0:
+            one = B200CalcSlicedNonbondedForceKernel(Platform(deviceIndex=local))
+            one.initialize(s.system, s.force)
+            tb = bench.timed_steps(lambda: one.execute_device(moving.pos.data_ptr(), s.box, frc_dev.data_ptr(), lam, stream=stream),
+                                   moving, flush, warmup, min(args.steps, 10))[0]
+            del one
+            single = {"ms_per_step": float(np.mean(tb)), "evals_per_s": 1e3/float(np.mean(tb)), "speedup": float(np.mean(tb))/ms,
+                      "efficiency": float(np.mean(tb))/ms/world, "note": "unsharded library on rank 0's GPU, same trajectory and timing protocol"}
+        dist.barrier()
+
     if rank == 0:
-        grid = s.force.getPMEParameters()[1]
         line = {
             "metric": "force+energy evals/s", "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{workload_name}: {s.description}", "atoms": n, "subsets": ns, "pme_grid": grid,
+            "config": {"workload": f"{workload_name}: {s.description}", "atoms": n, "subsets": ns, "pme_grid": grid[0],
                        "cutoff_nm": 1.0, "ns_per_day_2fs": bench.ns_per_day(value),
                        "l2": "256 MiB buffer written between steps, outside the per-step CUDA events",
-                       "neighbour_list": "rebuilt from scratch every step on every rank",
-                       "interacting_pairs": int(pairs.item()), "plan": plan.describe(), "calibration": calibration,
-                       "timing": "CUDA events per step on each rank, max over ranks per step, mean over steps"},
+                       "motion": bench.MOTION,
+                       "neighbour_list": "built with a skin on every rank, re-used until an atom has moved half of it",
+                       "list_policy": policy, "interacting_pairs": int(pairs.item()),
+                       "sharding": plan.describe() if peer_mode else dict(plan.describe(), scheme="NCCL: subset grids on their owners, spectrum broadcast, all-reduce of the accumulators", peer_memory_unavailable=why),
+                       "timing": "CUDA events per step on each rank after a barrier, max over ranks per step, mean over steps"},
             "clocks": sampler.summary(),
-            "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(pos_host.numel()*8),
-                    "d2h_bytes_per_step": int(frc_host.numel()*8 + 8*2*nsl), "ns_per_day_2fs": bench.ns_per_day(e2e_value),
-                    "note": "per rank: every rank uploads all positions and downloads all forces"},
+            "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(world*rows*24),
+                    "d2h_bytes_per_step": int(world*(rows*24 + 8*2*nsl)), "ns_per_day_2fs": bench.ns_per_day(e2e_value),
+                    "note": f"whole job: every rank uploads {rows} rows of the positions (pinned host memory), the shards are all-gathered over "
+                            "NVLink (NCCL), every rank downloads its rows of the forces and the slice energies"},
             "gpu_launches": int(launches),
-            "roofline": bench.pair_roofline(slow_pairs, slow_ms, None,
+            "forces_only": {"ms_per_step": forces_ms, "value": 1e3/forces_ms, "unit": "evals/s"},
+            "roofline": bench.pair_roofline(slow_pairs, slow_ms, None, device=local,
                                             note=f"rank {slow_rank}'s share of the i-blocks (the longest pair kernel of the job)"),
-            "single_gpu_same_workload": {"ms_per_step": calibration["single_gpu_ms_per_step"],
-                                         "evals_per_s": 1e3/calibration["single_gpu_ms_per_step"],
-                                         "speedup": calibration["single_gpu_ms_per_step"]/ms},
             "kernel_ms_rank0": {k: round(v, 5) for k, v in acc.items()},
-            "collectives_per_step": {"spectrum_broadcasts": ns if plan.num_pme_ranks > 1 else 0, "all_reduces": 2},
-            "slice_energy_checksum": checksum,
+            "kernel_ms_all_ranks": all_acc,
+            "collectives_per_step": ({"nccl": 0, "peer_memory_barriers": 4, "peer_memory_kernels": "k_fft_x_conv2 (x pass over all ranks' planes), k_peer_reduce (force accumulators)"}
+                                     if peer_mode else {"spectrum_broadcasts": ns if plan.num_pme_ranks > 1 else 0, "all_reduces": 2}),
+            "slice_energy_checksum": float(np.abs(energies).sum()),
             "forces_identical_on_all_ranks": bool(fmin.item() == fmax.item()),
         }
+        if single is not None:
+            line["single_gpu_same_workload"] = single
+        if parity is not None:
+            line["parity_vs_fixture"] = parity
         print(json.dumps(line))
     dist.barrier()
     dist.destroy_process_group()

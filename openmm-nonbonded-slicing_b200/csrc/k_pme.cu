@@ -173,6 +173,10 @@ struct PmeArgs {
     int N, Npad, nS, nx, ny, nz, nzh;
     int ownLo, ownHi;            // this rank spreads / gathers the atoms of subsets [ownLo, ownHi)
     int xLo, xHi;                // ... into / from the grid planes x in [xLo, xHi) (slab sharding; the whole grid otherwise)
+    // slab sharding, cell-sorted atoms, rectangular box: only the atoms of the cell columns that can reach the slab are
+    // looked at -- sorted atoms [binStart[rangeBin[0]], binStart[rangeBin[1]]) and [binStart[rangeBin[2]],
+    // binStart[rangeBin[3]]) (the second range is the periodic wrap); rangeBin[0] < 0: all atoms
+    const int* binStart; int rangeBin[4];
     const uint4* posq; const float4* par;
     // unsorted mode (small systems): particle-order inputs straight from k_prep, so that the PME chain does not
     // wait for the cell sort; forces then go to the particle-order half of the accumulator
@@ -201,6 +205,15 @@ __device__ __forceinline__ uint4 latticeFractions(const PmeArgs& a, uint4 p) {
     p.x = (unsigned) (__double2ull_rd(tx*4294967296.0) & 0xffffffffull);
     p.y = (unsigned) (__double2ull_rd(ty*4294967296.0) & 0xffffffffull);
     return p;
+}
+
+// Slab sharding: is sorted atom j in one of the two ranges of cell columns that can reach this rank's planes?  (Every
+// warp of the grid asks; the four bounds are the same words for all of them and stay in L1.)
+__device__ __forceinline__ bool inSlabRanges(const PmeArgs& a, int j) {
+    if (a.rangeBin[0] < 0) return true;
+    const int a0 = __ldg(a.binStart + a.rangeBin[0]), a1 = __ldg(a.binStart + a.rangeBin[1]);
+    const int b0 = __ldg(a.binStart + a.rangeBin[2]), b1 = __ldg(a.binStart + a.rangeBin[3]);
+    return (j >= a0 && j < a1) || (j >= b0 && j < b1);
 }
 
 // Slab sharding: does any of the five x planes of the atom's spline fall into this rank's slab?  (warp-uniform)
@@ -267,7 +280,7 @@ __global__ void __launch_bounds__(256) k_spread(const PmeArgs a) {
     __shared__ T wtab[8][16];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int j = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
-    if (j >= a.N) return;
+    if (j >= a.N || !inSlabRanges(a, j)) return;
     uint4 p; int subset; float q;
     if (a.unsorted) { p = a.fix[j]; q = a.chargeF[j]; subset = a.subsetOf[j]; }
     else { p = a.posq[j]; q = __uint_as_float(p.w); subset = __float_as_int(a.par[j].z) & 7; }
@@ -510,7 +523,7 @@ __global__ void __launch_bounds__(256) k_gather(const PmeArgs a) {
     __shared__ float wtab[8][16], dwtab[8][16];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int j = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
-    if (j >= a.N) return;
+    if (j >= a.N || !inSlabRanges(a, j)) return;
     uint4 p; int subset; float q;
     if (a.unsorted) { p = a.fix[j]; q = a.chargeF[j]; subset = a.subsetOf[j]; }
     else { p = a.posq[j]; q = __uint_as_float(p.w); subset = __float_as_int(a.par[j].z) & 7; }
@@ -692,6 +705,24 @@ static int launchPmeT(Context& c, bool wantEnergy, int half) {
     p.N = c.N; p.Npad = c.Npad; p.nS = c.nS; p.nx = nx; p.ny = ny; p.nz = nz; p.nzh = nzh;
     p.ownLo = c.ownLo; p.ownHi = c.ownHi;
     p.xLo = c.slabMode ? c.xLo : 0; p.xHi = c.slabMode ? c.xHi : nx;
+    p.binStart = c.dBinStart.d;
+    p.rangeBin[0] = -1; p.rangeBin[1] = p.rangeBin[2] = p.rangeBin[3] = 0;
+    if (c.slabMode && c.nRanks > 1 && !c.pmeUnsorted && !c.dispersionPass && !c.geom.triclinic) {
+        // cell columns (x-major in the sorted order) whose atoms can touch the planes [xLo, xHi): an order-5 spline
+        // starting at plane xLo - 4 .. xHi - 1, plus what an atom may have moved since the sort that placed it
+        const CellGeom& g = c.geom;
+        const double margin = (0.5*c.skin + 2.0e-3)*g.invBox[0];
+        const double uLo = (double) (p.xLo - (PME_ORDER - 1))/nx - margin, uHi = (double) p.xHi/nx + margin;
+        const int colLo = (int) std::floor(uLo*g.ncx), colHi = (int) std::floor(uHi*g.ncx);       // inclusive
+        if (colHi - colLo + 1 < g.ncx) {
+            int A0 = colLo, A1 = colHi, B0 = 0, B1 = -1;
+            if (colLo < 0) { A0 = 0; B0 = colLo + g.ncx; B1 = g.ncx - 1; }
+            else if (colHi >= g.ncx) { A1 = g.ncx - 1; B0 = 0; B1 = colHi - g.ncx; }
+            const int perCol = g.ncy*g.nzb;
+            p.rangeBin[0] = A0*perCol; p.rangeBin[1] = (A1 + 1)*perCol;
+            p.rangeBin[2] = B0*perCol; p.rangeBin[3] = (B1 + 1)*perCol;
+        }
+    }
     p.posq = c.dPosq.d; p.par = c.dPar.d; p.grid = c.dGrid.d; p.pot = c.dPot.d; p.gridFixed = nullptr;
     p.unsorted = c.pmeUnsorted ? 1 : 0;
     p.fix = c.dFix.d; p.chargeF = c.dChargeF.d; p.subsetOf = c.dSubset.d;

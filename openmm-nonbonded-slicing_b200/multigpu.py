@@ -450,7 +450,8 @@ def bench_main(args, workload_name):
     frc_dev = torch.zeros((n, 3), dtype=torch.float64, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
     flush = torch.empty(256*1024*1024, dtype=torch.uint8, device=dev)
-    warmup = max(args.warmup, 3)
+    warmup = max(args.warmup, bench.MIN_WARMUP)      # both CUDA-graph-free here, but the same protocol as the 1-GPU line
+    e2e_warm = max(args.warmup, 3)
 
     def factory(flags):
         k = ShardedB200Kernel(Platform(deviceIndex=local, flags=flags))
@@ -498,7 +499,7 @@ def bench_main(args, workload_name):
     sampler = bench.ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.__enter__()
-    per_step, energies = bench.timed_steps(lambda: evaluate(kernel, moving.pos.data_ptr()), moving, flush, 0, args.steps, barrier=barrier)
+    per_step, energies = bench.timed_steps(lambda: evaluate(kernel, moving.pos.data_ptr()), moving, flush, 0, args.steps, barrier=barrier, t0=warmup)
     if sampler:
         sampler.sample_now()
         sampler.__exit__()
@@ -518,7 +519,7 @@ def bench_main(args, workload_name):
     pos_shard_dev = torch.zeros((rows, 3), dtype=torch.float64, device=dev)
     pos_all = torch.zeros((world*rows, 3), dtype=torch.float64, device=dev)
     e2e = []
-    for it in range(warmup + args.steps):
+    for it in range(e2e_warm + args.steps):
         pos_shard_host[:hi-lo] = torch.from_numpy(moving.host_positions(it, lo, hi))
         flush.fill_(1)
         torch.cuda.synchronize()
@@ -534,7 +535,7 @@ def bench_main(args, workload_name):
         frc_shard_host[:hi-lo].copy_(frc_dev[lo:hi], non_blocking=True)
         torch.cuda.synchronize()
         dt = time.perf_counter()-t0
-        if it >= warmup:
+        if it >= e2e_warm:
             e2e.append(dt)
     te = torch.tensor(e2e, dtype=torch.float64, device=dev)
     dist.all_reduce(te, op=dist.ReduceOp.MAX)

@@ -314,3 +314,52 @@ def test_peer_two_processes(nbs, multigpu, systems):
         for _, runs in results:
             assert force_rel_rms(runs[it][0], ref_f) <= 1e-6
             assert np.allclose(runs[it][1], ref_e, rtol=1e-9, atol=1e-9)
+
+
+def test_peer_shards_sorted_pme_column_ranges(nbs, multigpu, systems):
+    """Large systems run PME from the cell-sorted records, and a rank then only looks at the atoms of the cell columns
+    that can reach its planes (k_pme.cu inSlabRanges).  Forced here on C3 (NBS_FLAG_SORTED_PME), 8 ranks, and repeated
+    after every atom has moved by up to 0.01 nm, twice -- the neighbour list and the sort order are re-used, atoms cross slab
+    and box boundaries -- against the unsharded evaluation of the same positions."""
+    import torch
+    s = systems.make_system("C3")
+    n = s.force.getNumParticles()
+    lam = np.random.default_rng(8).uniform(0.2, 1.0, size=(s.force.getNumSlices(), 2))
+    world = 8
+    dev = torch.device("cuda:0")
+    plan = multigpu.SlabPlan(world, s.force.getPMEParameters()[1:])
+    shards = []
+    for r in range(world):
+        k = multigpu.ShardedB200Kernel(nbs.Platform(flags=nbs.abi.NBS_FLAG_SORTED_PME))
+        k.initialize(s.system, s.force)
+        k.set_slab_plan(plan, r)
+        shards.append(k)
+    exports = [k.export_peer() for k in shards]
+    for k in shards:
+        k.import_peers(exports, in_kernel_barrier=False)
+    plain = nbs.B200CalcSlicedNonbondedForceKernel(nbs.Platform())
+    plain.initialize(s.system, s.force)
+    # (device buffers are allocated by a context's first evaluation, and ANY allocation in the process invalidates kept
+    # lists -- captured graphs hold pointers: let the comparison context allocate before the shards build theirs)
+    plain._evaluate(s.positions, s.box, lam, np.zeros(0), True, True, np.zeros((n, 3)))
+    rng = np.random.default_rng(9)
+    shift = rng.uniform(-0.01, 0.01, size=(n, 3))
+    for step in range(3):
+        positions = s.positions + step*0.5*shift
+        pos = torch.tensor(positions, dtype=torch.float64, device=dev)
+        outs = []
+        for k in shards:
+            out = torch.zeros_like(pos)
+            k.prepare(pos.data_ptr(), s.box, out.data_ptr(), lam, stream=torch.cuda.current_stream().cuda_stream)
+            outs.append(out)
+        energies = multigpu.evaluate_peer_lockstep(shards)
+        torch.cuda.synchronize()
+        ref_f = np.zeros((n, 3))
+        ref_e = plain._evaluate(positions, s.box, lam, np.zeros(0), True, True, ref_f)
+        for o, e in zip(outs, energies):
+            assert force_rel_rms(o.cpu().numpy(), ref_f) <= 1e-6, step
+            # (Coulomb: double-precision sums; Lennard-Jones: fp32 sums per tile, and the tiles of the two contexts'
+            # lists need not be the same once lists are re-used -- the tolerance of test_list_reuse_matches_rebuild)
+            assert np.allclose(e[:, 0], ref_e[:, 0], rtol=2e-8, atol=1e-6) and np.allclose(e[:, 1], ref_e[:, 1], rtol=2e-6, atol=1e-6), step
+        if step > 0:
+            assert all(k.getListStats()["reused_last"] for k in shards)

@@ -625,6 +625,152 @@ def test_scaling_parameter_separation(nbs, platform, method, exceptions):
     scaling_parameter_separation(nbs, platform, method, exceptions, 1e-4)
 
 
+SLICING_CASES = [(m, o, x, lj) for m in ("NoCutoff", "CutoffNonPeriodic", "CutoffPeriodic", "Ewald", "PME", "LJPME")
+                 for o in (False, True) for x in (False, True) for lj in (False, True)]
+
+
+def nonbonded_slicing(nbs, platform, method, offsets, exceptions, lj, tol):
+    """testNonbondedSlicing :1030-1318, the reference's 48-run matrix (:1493-1497): a two-subset SlicedNonbondedForce
+    whose slices (0,1) and (1,1) are scaled by Context parameters must equal an UNSLICED force (here a one-subset
+    SlicedNonbondedForce standing in for OpenMM's NonbondedForce) whose subset-1 charges (Coulomb runs) or epsilons (LJ
+    runs) are rescaled by hand -- at parameter values 1, 0 and 0.5, for the direct-space group, the reciprocal-space group
+    and both; then E(1) - E(0) = sum of the two parameter derivatives, and with a third parameter on slice (0,0) the
+    three derivatives add up to the energy of the scaled term.  Offsets: a particle charge offset, a particle epsilon
+    offset and (with exceptions) the same on two exceptions, all driven by one global parameter."""
+    include_lj, include_coulomb = lj, not lj
+    num_molecules = 100
+    n = 2*num_molecules
+    cutoff = 3.5
+    L = 7.0 if exceptions else 10.0
+    rng = np.random.default_rng(23)
+    system1, system2 = nbs.System(), nbs.System()
+    for sysm in (system1, system2):
+        for _ in range(n):
+            sysm.addParticle(1.0)
+        sysm.setDefaultPeriodicBoxVectors([L, 0, 0], [0, L, 0], [0, 0, L])
+    plain = nbs.SlicedNonbondedForce(1)
+    plain.setNonbondedMethod(getattr(plain, method))
+    plain.setCutoffDistance(cutoff)
+    plain.setUseDispersionCorrection(True)
+    plain.setReciprocalSpaceForceGroup(1)
+    plain.setEwaldErrorTolerance(1e-4)
+
+    def q(k):
+        return float(1 - 2*(k % 2))
+    M = int(round(num_molecules**(1/3)))
+    if M*M*M < num_molecules:
+        M += 1
+    eps = 1.0
+    positions = np.zeros((n, 3))
+    for k in range(num_molecules):
+        iz = k//(M*M)
+        iy = (k - iz*M*M)//M
+        ix = k - M*(iy + iz*M)
+        center = np.array([ix+0.5, iy+0.5, iz+0.5])*L/M
+        delta = np.array([0.5-ix % 2, 0.5-iy % 2, 0.5-iz % 2])/2
+        i, j = 2*k, 2*k+1
+        positions[i], positions[j] = center+delta, center-delta
+        plain.addParticle(q(i), 1, eps)
+        plain.addParticle(q(j), 1, eps)
+        if exceptions:
+            plain.addException(i, j, q(i)*q(j), 1, eps)
+    particle_offsets, exception_offsets = [], []
+    if offsets:
+        particle_offsets = [(0, "offsetLambda", 1.0, 0.0, 0.0), (1, "offsetLambda", 0.0, 0.0, 1.0)]
+        if exceptions:
+            exception_offsets = [(0, "offsetLambda", 1.0, 0.0, 0.0), (1, "offsetLambda", 0.0, 0.0, 1.0)]
+        plain.addGlobalParameter("offsetLambda", 0.0)
+        for k, name, dq, ds, de in particle_offsets:
+            plain.addParticleParameterOffset(name, k, dq, ds, de)
+        for k, name, dq, ds, de in exception_offsets:
+            plain.addExceptionParameterOffset(name, k, dq, ds, de)
+    sliced = nbs.SlicedNonbondedForce(plain, 2)
+    in1 = rng.random(n) < 0.5
+    for k in range(n):
+        if in1[k]:
+            sliced.setParticleSubset(k, 1)
+    param01 = "lambda" if include_coulomb else "sqrtLambda"
+    sliced.addGlobalParameter(param01, 1)
+    sliced.addScalingParameter(param01, 0, 1, include_coulomb, include_lj)
+    param11 = "lambdaSq" if include_coulomb else "lambda"
+    sliced.addGlobalParameter(param11, 1)
+    sliced.addScalingParameter(param11, 1, 1, include_coulomb, include_lj)
+    system1.addForce(plain)
+    system2.addForce(sliced)
+    particle_scale = [("lambda" if include_coulomb else "one", "lambda" if include_lj else "one") if in1[k] else ("one", "one") for k in range(n)]
+    num_exceptions = plain.getNumExceptions()
+    exception_scale = []
+    for k in range(num_exceptions):
+        i, j = plain.getExceptionParameters(k)[:2]
+        if in1[i] != in1[j] or in1[i]:
+            name = param01 if in1[i] != in1[j] else param11
+            exception_scale.append((name if include_coulomb else "one", name if include_lj else "one"))
+        else:
+            exception_scale.append(("one", "one"))
+    context1, context2 = nbs.Context(system1, platform), nbs.Context(system2, platform)
+    context1.setPositions(positions)
+    context2.setPositions(positions)
+
+    def compare():
+        """direct-space group, reciprocal-space group, everything (:1151-1171); returns the total energy"""
+        energy = None
+        for groups in (1 << 0, 1 << 1, 0xFFFFFFFF):
+            st1 = context1.getState(getEnergy=True, getForces=True, groups=groups)
+            st2 = context2.getState(getEnergy=True, getForces=True, groups=groups)
+            assert_equal_tol(st1.getPotentialEnergy(), st2.getPotentialEnergy(), tol)
+            for fa, fb in zip(st1.getForces(), st2.getForces()):
+                assert_equal_vec(fa, fb, tol)
+            energy = st1.getPotentialEnergy()
+        return energy
+
+    def rescale(value):
+        for k in range(n):
+            plain.setParticleParameters(k, q(k)*value[particle_scale[k][0]], 1, eps*value[particle_scale[k][1]])
+        for k in range(num_exceptions):
+            plain.setExceptionParameters(k, 2*k, 2*k+1, q(2*k)*q(2*k+1)*value[exception_scale[k][0]], 1, eps*value[exception_scale[k][1]])
+        for idx, (k, name, dq, ds, de) in enumerate(particle_offsets):
+            plain.setParticleParameterOffset(idx, name, k, dq*value[particle_scale[k][0]], ds, de*value[particle_scale[k][1]])
+        for idx, (k, name, dq, ds, de) in enumerate(exception_offsets):
+            plain.setExceptionParameterOffset(idx, name, k, dq*value[exception_scale[k][0]], ds, de*value[exception_scale[k][1]])
+        plain.updateParametersInContext(context1)
+        context2.setParameter(param01, value[param01])
+        context2.setParameter(param11, value[param11])
+
+    energy_lambda_one = compare()
+    rescale({"one": 1.0, "lambda": 0.0, "sqrtLambda": 0.0, "lambdaSq": 0.0})
+    energy_lambda_zero = compare()
+    rescale({"one": 1.0, "lambda": 0.5, "sqrtLambda": np.sqrt(0.5), "lambdaSq": 0.25})
+    compare()
+    # derivatives (:1279-1286): the energy is linear in each scaling parameter
+    sliced.addEnergyParameterDerivative(param01)
+    sliced.addEnergyParameterDerivative(param11)
+    context2.reinitialize(True)
+    derivs = context2.getState(getParameterDerivatives=True).getEnergyParameterDerivatives()
+    assert_equal_tol(energy_lambda_one - energy_lambda_zero, derivs[param01] + derivs[param11], tol)
+    # sum of derivatives (:1288-1317): only the scaled term left in the unsliced force, every slice of it scaled
+    for k in range(n):
+        plain.setParticleParameters(k, q(k) if include_coulomb else 0.0, 1, eps if include_lj else 0.0)
+    for k in range(num_exceptions):
+        plain.setExceptionParameters(k, 2*k, 2*k+1, q(2*k)*q(2*k+1) if include_coulomb else 0.0, 1, eps if include_lj else 0.0)
+    for idx, (k, name, dq, ds, de) in enumerate(particle_offsets):
+        plain.setParticleParameterOffset(idx, name, k, dq if include_coulomb else 0.0, ds, de if include_lj else 0.0)
+    for idx, (k, name, dq, ds, de) in enumerate(exception_offsets):
+        plain.setExceptionParameterOffset(idx, name, k, dq if include_coulomb else 0.0, ds, de if include_lj else 0.0)
+    plain.updateParametersInContext(context1)
+    energy = context1.getState(getEnergy=True).getPotentialEnergy()
+    sliced.addGlobalParameter("remainder", 1.0)
+    sliced.addScalingParameter("remainder", 0, 0, include_coulomb, include_lj)
+    sliced.addEnergyParameterDerivative("remainder")
+    context2.reinitialize(True)
+    derivs = context2.getState(getEnergy=True, getParameterDerivatives=True).getEnergyParameterDerivatives()
+    assert_equal_tol(energy, derivs[param01] + derivs[param11] + derivs["remainder"], tol)
+
+
+@pytest.mark.parametrize("method,offsets,exceptions,lj", SLICING_CASES)
+def test_nonbonded_slicing(nbs, platform, method, offsets, exceptions, lj):
+    nonbonded_slicing(nbs, platform, method, offsets, exceptions, lj, 1e-4)
+
+
 def test_parameter_clash(nbs, platform):
     """python/tests/TestSlicedNonbondedForce.py:51-67 and SlicedNonbondedForceImpl.cpp:114-131"""
     system = nbs.System()
@@ -640,3 +786,154 @@ def test_parameter_clash(nbs, platform):
     system.addForce(force)
     with pytest.raises(Exception):
         nbs.Context(system, platform)
+
+
+# ---- the reference tests that compare against OpenMM's own NonbondedForce / Reference platform -------------------------
+# (NonbondedForce does not exist here: a one-subset SlicedNonbondedForce stands in for it, and "the Reference platform" is
+# the compiled-reference oracle; the bodies take the two platforms to compare, so the GPU suite re-uses them)
+def _compare_states(context_a, context_b, groups, etol, ftol):
+    from helpers import force_rel_rms
+    sa = context_a.getState(getEnergy=True, getForces=True, groups=groups)
+    sb = context_b.getState(getEnergy=True, getForces=True, groups=groups)
+    assert_equal_tol(sb.getPotentialEnergy(), sa.getPotentialEnergy(), etol)
+    assert force_rel_rms(sa.getForces(), sb.getForces()) <= ftol
+
+
+def large_system(nbs, platform_a, platform_b, etol=1e-5, ftol=1e-5):
+    """testLargeSystem :494-555 -- 600 two-particle molecules at random positions in a 20 nm box, an exclusion inside each
+    molecule; NoCutoff, then CutoffNonPeriodic (2 nm), then CutoffPeriodic after reinitialize(true): `platform_a` against
+    `platform_b` (the reference compares its platform with the Reference platform).  (Its HarmonicBondForce sits in
+    another force group and is not part of the comparison.)"""
+    num_molecules, cutoff, box = 600, 2.0, 20.0
+    rng = np.random.default_rng(0)
+    system = nbs.System()
+    force = nbs.SlicedNonbondedForce(1)
+    positions = np.zeros((2*num_molecules, 3))
+    for i in range(num_molecules):
+        eps = 0.1 if i < num_molecules//2 else 0.2
+        force.addParticle(-1.0, 0.2, eps)
+        force.addParticle(1.0, 0.1, eps)
+        positions[2*i] = box*rng.random(3)
+        positions[2*i+1] = positions[2*i] + [1.0, 0.0, 0.0]
+        force.addException(2*i, 2*i+1, 0.0, 0.15, 0.0)
+        system.addParticle(1.0)
+        system.addParticle(1.0)
+    system.setDefaultPeriodicBoxVectors([box, 0, 0], [0, box, 0], [0, 0, box])
+    force.setNonbondedMethod(force.NoCutoff)
+    system.addForce(force)
+    contexts = [nbs.Context(system, platform_a), nbs.Context(system, platform_b)]
+    for c in contexts:
+        c.setPositions(positions)
+    _compare_states(contexts[0], contexts[1], 0xFFFFFFFF, etol, ftol)
+    force.setNonbondedMethod(force.CutoffNonPeriodic)
+    force.setCutoffDistance(cutoff)
+    for c in contexts:
+        c.reinitialize(True)
+    _compare_states(contexts[0], contexts[1], 0xFFFFFFFF, etol, ftol)
+    force.setNonbondedMethod(force.CutoffPeriodic)
+    for c in contexts:
+        c.reinitialize(True)
+    _compare_states(contexts[0], contexts[1], 0xFFFFFFFF, etol, ftol)
+
+
+def changing_parameters(nbs, platform_a, platform_b, etol=1e-5, ftol=1e-5):
+    """testChangingParameters :683-758 -- 600 molecules on a lattice, PME with a 2 nm cutoff in a 20 nm box (default PME
+    parameters), direct-space and reciprocal-space groups compared separately; then every fifth particle gets
+    1.5 x charge, 1.1 x sigma, 1.7 x epsilon through updateParametersInContext and everything is compared again."""
+    num_molecules, cutoff, box = 600, 2.0, 20.0
+    system = nbs.System()
+    force = nbs.SlicedNonbondedForce(1)
+    M = int(num_molecules**(1/3))
+    if M*M*M < num_molecules:
+        M += 1
+    positions = np.zeros((2*num_molecules, 3))
+    for k in range(num_molecules):
+        iz = k//(M*M)
+        iy = (k - iz*M*M)//M
+        ix = k - M*(iy + iz*M)
+        center = (np.array([ix, iy, iz]) + 0.5)*box/M
+        delta = np.array([0.5 - ix % 2, 0.5 - iy % 2, 0.5 - iz % 2])/2
+        eps = 0.1 if k < num_molecules//2 else 0.2
+        force.addParticle(-1.0, 0.2, eps)
+        force.addParticle(1.0, 0.1, eps)
+        positions[2*k], positions[2*k+1] = center + delta, center - delta
+        force.addException(2*k, 2*k+1, 0.0, 0.15, 0.0)
+        system.addParticle(1.0)
+        system.addParticle(1.0)
+    force.setNonbondedMethod(force.PME)
+    force.setCutoffDistance(cutoff)
+    force.setForceGroup(1)
+    force.setReciprocalSpaceForceGroup(3)
+    system.addForce(force)
+    system.setDefaultPeriodicBoxVectors([box, 0, 0], [0, box, 0], [0, 0, box])
+    contexts = [nbs.Context(system, platform_a), nbs.Context(system, platform_b)]
+    for c in contexts:
+        c.setPositions(positions)
+    _compare_states(contexts[0], contexts[1], 1 << 1, etol, ftol)
+    _compare_states(contexts[0], contexts[1], 1 << 3, etol, ftol)
+    for i in range(0, 2*num_molecules, 5):
+        charge, sigma, epsilon = force.getParticleParameters(i)
+        force.setParticleParameters(i, 1.5*charge, 1.1*sigma, 1.7*epsilon)
+    for c in contexts:
+        force.updateParametersInContext(c)
+    _compare_states(contexts[0], contexts[1], 0xFFFFFFFF, etol, ftol)
+    _compare_states(contexts[0], contexts[1], 1 << 1, etol, ftol)
+    _compare_states(contexts[0], contexts[1], 1 << 3, etol, ftol)
+
+
+def instantiate_from_nonbonded_force(nbs, platform, method, tol=TOL):
+    """testInstantiateFromNonbondedForce :29-85 -- a force and its copy (the copy constructor the plugin uses to wrap an
+    existing NonbondedForce: particles, exceptions, global parameters, particle and exception offsets) in ONE Context,
+    in different force groups: direct-space groups agree, and after a parameter change the reciprocal-space groups do."""
+    force = nbs.SlicedNonbondedForce(1)
+    force.setCutoffDistance(2.0)
+    force.setNonbondedMethod(getattr(force, method))
+    for q, sig, eps in ((0.0, 1.0, 0.5), (1.0, 0.5, 0.6), (-1.0, 2.0, 0.7), (0.5, 2.0, 0.8), (-0.5, 2.0, 0.8)):
+        force.addParticle(q, sig, eps)
+    force.addException(0, 3, 0.0, 1.0, 0.0)
+    force.addException(2, 3, 0.5, 1.0, 1.5)
+    force.addException(0, 1, 1.0, 1.5, 1.0)
+    force.addGlobalParameter("p1", 0.5)
+    force.addGlobalParameter("p2", 1.0)
+    force.addParticleParameterOffset("p1", 0, -2.0, 0.5, 0.5)
+    force.addParticleParameterOffset("p2", 1, 1.0, 1.0, 2.0)
+    force.addExceptionParameterOffset("p1", 1, 0.5, 0.5, 1.5)
+    force.setReciprocalSpaceForceGroup(2)
+    sliced = nbs.SlicedNonbondedForce(force, 1)
+    sliced.setForceGroup(1)
+    sliced.setReciprocalSpaceForceGroup(3)
+    n = force.getNumParticles()
+    system = nbs.System()
+    L = float(n)
+    system.setDefaultPeriodicBoxVectors([L, 0, 0], [0, L, 0], [0, 0, L])
+    for _ in range(n):
+        system.addParticle(1.0)
+    system.addForce(force)
+    system.addForce(sliced)
+    context = nbs.Context(system, platform)
+    context.setPositions(np.array([[float(i), 0.0, 0.0] for i in range(n)]))
+    for ga, gb, p1 in ((1 << 0, 1 << 1, None), (1 << 2, 1 << 3, 1.0)):
+        if p1 is not None:
+            context.setParameter("p1", p1)
+        sa = context.getState(getEnergy=True, getForces=True, groups=ga)
+        sb = context.getState(getEnergy=True, getForces=True, groups=gb)
+        assert_equal_tol(sa.getPotentialEnergy(), sb.getPotentialEnergy(), tol)
+        for fa, fb in zip(sa.getForces(), sb.getForces()):
+            assert_equal_vec(fa, fb, tol)
+
+
+def test_large_system_port_vs_compiled_reference(nbs, oracle):
+    if not oracle.available("reference"):
+        pytest.skip("oracle/_ref not built")
+    large_system(nbs, oracle.OraclePlatform("port"), oracle.OraclePlatform("reference"), 1e-10, 1e-10)
+
+
+def test_changing_parameters_port_vs_compiled_reference(nbs, oracle):
+    if not oracle.available("reference"):
+        pytest.skip("oracle/_ref not built")
+    changing_parameters(nbs, oracle.OraclePlatform("port"), oracle.OraclePlatform("reference"), 1e-9, 1e-9)
+
+
+@pytest.mark.parametrize("method", ["NoCutoff", "CutoffNonPeriodic", "CutoffPeriodic", "Ewald", "PME", "LJPME"])
+def test_instantiate_from_nonbonded_force(nbs, platform, method):
+    instantiate_from_nonbonded_force(nbs, platform, method)

@@ -177,6 +177,11 @@ struct PmeArgs {
     // looked at -- sorted atoms [binStart[rangeBin[0]], binStart[rangeBin[1]]) and [binStart[rangeBin[2]],
     // binStart[rangeBin[3]]) (the second range is the periodic wrap); rangeBin[0] < 0: all atoms
     const int* binStart; int rangeBin[4];
+    // ... and once the host knows the two ranges (they come back with the counters of the evaluation that sorted the
+    // atoms) the grid covers exactly those atoms: warp j works on sorted atom hostRange[0] + j, or hostRange[2] + (j - length
+    // of the first range)
+    int useHostRange; int hostRange[4];
+    int batch;                   // atoms per warp in k_spread / k_gather (4 .. 32, a power of two)
     const uint4* posq; const float4* par;
     // unsorted mode (small systems): particle-order inputs straight from k_prep, so that the PME chain does not
     // wait for the cell sort; forces then go to the particle-order half of the accumulator
@@ -216,6 +221,22 @@ __device__ __forceinline__ bool inSlabRanges(const PmeArgs& a, int j) {
     return (j >= a0 && j < a1) || (j >= b0 && j < b1);
 }
 
+// The sorted atom warp j of the grid works on, or -1.
+__device__ __forceinline__ int slabAtom(const PmeArgs& a, int j) {
+    if (j < 0) return -1;
+    if (a.useHostRange) {
+        const int lenA = a.hostRange[1] - a.hostRange[0];
+        if (j < lenA) return a.hostRange[0] + j;
+        const int atom = a.hostRange[2] + (j - lenA);
+        return atom < a.hostRange[3] ? atom : -1;
+    }
+    return (j < a.N && inSlabRanges(a, j)) ? j : -1;
+}
+
+__global__ void k_slab_ranges(const int* __restrict__ binStart, int b0, int b1, int b2, int b3, int* __restrict__ out) {
+    if (threadIdx.x == 0) { out[0] = binStart[b0]; out[1] = binStart[b1]; out[2] = binStart[b2]; out[3] = binStart[b3]; }
+}
+
 // Slab sharding: does any of the five x planes of the atom's spline fall into this rank's slab?  (warp-uniform)
 __device__ __forceinline__ bool touchesSlab(const PmeArgs& a, const uint4 pBrick) {
     if (a.xHi - a.xLo >= a.nx) return true;
@@ -236,31 +257,58 @@ __device__ __forceinline__ void gridCoord(unsigned fixed, int n, int& index, T& 
     frac = (T) (unsigned) (t & 0xffffffffull)*(T) (1.0/4294967296.0);
 }
 
-// Shared by spreading and gather: lanes 0-14 evaluate the order-5 spline of "their" dimension (0-4 x, 5-9 y,
-// 10-14 z) and publish weight lane%5 (and its derivative) in the warp's shared-memory table; the base
-// grid indices come back by shuffle.
-template <typename T>
-__device__ __forceinline__ void splineTable(const PmeArgs& a, const uint4 pBrick, int lane, T* wt, T* dwt, int& ix0, int& iy0, int& iz0) {
-    const uint4 p = latticeFractions(a, pBrick);
-    const int dim = min(lane/5, 2), kk = lane % 5;
-    int index; T frac;
-    gridCoord<T>(dim == 0 ? p.x : (dim == 1 ? p.y : p.z), dim == 0 ? a.nx : (dim == 1 ? a.ny : a.nz), index, frac);
-    T th[5], dth[5];
-    bspline5(frac, th, dth);
-    T mine = th[0], dmine = dth[0];
+// Spreading and gather work in BATCHES of 32 atoms per warp.  Phase 1, lane = atom: coalesced loads, the three order-5
+// splines (about 200 arithmetic instructions -- done once per 32 atoms, every lane busy; one warp per atom paid them per
+// atom with 15 lanes busy) into the warp's shared-memory table, k-major with a row stride of 33 so that both phases are
+// free of bank conflicts.  Phase 2, one atom at a time: the 125 grid points are dealt to the lanes with z fastest
+// (point = lane + 32 i, its (ox, oy, oz) fixed per lane for the whole kernel), so one warp-wide atomic / load touches
+// runs of 5 consecutive cells of a grid row -- about a third of the L2 transactions of a row-per-lane assignment.
+// Per atom that leaves four passes of ~16 instructions: ~75 warp instructions instead of 340 (spread) / 460 (gather).
+constexpr int PME_TAB_STRIDE = 33;
+template <typename T, bool DERIV>
+struct __align__(16) PmeWarpTab {
+    T w[15][PME_TAB_STRIDE];           // spline weights: [0..4] x, [5..9] y, [10..14] z
+    float dw[DERIV ? 15 : 1][PME_TAB_STRIDE];      // their derivatives (gather)
+    T q[32];
+    int ix0[32], iy0[32], iz0[32], subset[32], atom[32];
+};
+
+// Phase 1 for lane's atom; returns the ballot of the lanes that hold an atom with work to do.
+template <typename T, bool DERIV>
+__device__ __forceinline__ unsigned pmeBatchSetup(const PmeArgs& a, PmeWarpTab<T, DERIV>& t, int lane, int mapped) {
+    const int j = slabAtom(a, mapped);
+    bool valid = j >= 0;
+    uint4 p = make_uint4(0u, 0u, 0u, 0u); int subset = 0; float q = 0.f;
+    if (valid) {
+        if (a.unsorted) { p = a.fix[j]; q = a.chargeF[j]; subset = a.subsetOf[j]; }
+        else { p = a.posq[j]; q = __uint_as_float(p.w); subset = __float_as_int(a.par[j].z) & 7; }
+        valid = q != 0.f && subset >= a.ownLo && subset < a.ownHi && touchesSlab(a, p);
+    }
+    if (valid) {
+        const uint4 f = latticeFractions(a, p);
+        int index; T frac, th[5], dth[5];
+        gridCoord<T>(f.x, a.nx, index, frac); t.ix0[lane] = index;
+        bspline5(frac, th, dth);
 #pragma unroll
-    for (int k = 1; k < 5; k++) { mine = kk == k ? th[k] : mine; dmine = kk == k ? dth[k] : dmine; }
+        for (int k = 0; k < 5; k++) { t.w[k][lane] = th[k]; if (DERIV) t.dw[k][lane] = (float) dth[k]; }
+        gridCoord<T>(f.y, a.ny, index, frac); t.iy0[lane] = index;
+        bspline5(frac, th, dth);
+#pragma unroll
+        for (int k = 0; k < 5; k++) { t.w[5 + k][lane] = th[k]; if (DERIV) t.dw[5 + k][lane] = (float) dth[k]; }
+        gridCoord<T>(f.z, a.nz, index, frac); t.iz0[lane] = index;
+        bspline5(frac, th, dth);
+#pragma unroll
+        for (int k = 0; k < 5; k++) { t.w[10 + k][lane] = th[k]; if (DERIV) t.dw[10 + k][lane] = (float) dth[k]; }
+        // (the fp32 charge carries 6e-8 of rounding: visible in cross-subset energies that cancel to 1e-6 of their terms)
+        t.q[lane] = sizeof(T) == 8 ? (T) (a.unsorted ? a.chargeD[j]*a.sqrtK : a.q64[j]) : (T) q;
+        t.subset[lane] = subset;
+        t.atom[lane] = j;
+    }
+    const unsigned todo = __ballot_sync(FULL_MASK, valid);
     __syncwarp();
-    if (lane < 15) { wt[lane] = mine; if (dwt) dwt[lane] = dmine; }
-    ix0 = __shfl_sync(FULL_MASK, index, 0);
-    iy0 = __shfl_sync(FULL_MASK, index, 5);
-    iz0 = __shfl_sync(FULL_MASK, index, 10);
-    __syncwarp();
+    return todo;
 }
 
-// One warp per (sorted) atom.  The 125 grid points are dealt to the lanes with z fastest (point = lane + 32 i,
-// z offset = point % 5), so one warp-wide atomic touches runs of 5 consecutive cells of a grid row instead of 25
-// different rows: about a third of the L2 atomic transactions of a row-per-lane assignment.
 // FIXED (NBS_FLAG_DETERMINISTIC; the plugin's CudaDeterministicForces, pme.cc:108-109, 124-134): the grid points are
 // accumulated as 64-bit fixed point -- integer adds commute, so the grid, and with it every reciprocal-space force,
 // is bit-reproducible whatever order the atomics retire in -- and k_fixed_to_real converts the grid afterwards.
@@ -277,35 +325,37 @@ __global__ void k_fixed_to_real(size_t n, size_t stride, const long long* __rest
 
 template <typename T, bool FIXED>
 __global__ void __launch_bounds__(256) k_spread(const PmeArgs a) {
-    __shared__ T wtab[8][16];
+    extern __shared__ __align__(16) unsigned char pmeSmem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int j = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
-    if (j >= a.N || !inSlabRanges(a, j)) return;
-    uint4 p; int subset; float q;
-    if (a.unsorted) { p = a.fix[j]; q = a.chargeF[j]; subset = a.subsetOf[j]; }
-    else { p = a.posq[j]; q = __uint_as_float(p.w); subset = __float_as_int(a.par[j].z) & 7; }
-    if (q == 0.f || subset < a.ownLo || subset >= a.ownHi) return;      // warp-uniform
-    if (!touchesSlab(a, p)) return;
-    int ix0, iy0, iz0;
-    splineTable<T>(a, p, lane, wtab[warp], (T*) nullptr, ix0, iy0, iz0);
-    const T* wt = wtab[warp];
-    // (the fp32 charge carries 6e-8 of rounding: visible in cross-subset energies that cancel to 1e-6 of their terms)
-    const T qT = sizeof(T) == 8 ? (T) (a.unsorted ? a.chargeD[j]*a.sqrtK : a.q64[j]) : (T) q;
-    T* grid = (T*) a.grid + (size_t) subset*a.nx*a.ny*a.nz;
-    unsigned long long* gridFixed = a.gridFixed + (size_t) subset*a.nx*a.ny*a.nz;
+    PmeWarpTab<T, false>& t = reinterpret_cast<PmeWarpTab<T, false>*>(pmeSmem)[warp];
+    unsigned todo = pmeBatchSetup<T, false>(a, t, lane, lane < a.batch ? ((int) blockIdx.x*((int) blockDim.x >> 5) + warp)*a.batch + lane : -1);
+    if (todo == 0u) return;
+    int ox[4], oy[4], oz[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        const int pt = lane + 32*i;
-        if (pt < 125) {
-            const int row = pt/5, oz = pt - row*5, ox = row/5, oy = row - ox*5;
-            int x = ix0 + ox; x -= x >= a.nx ? a.nx : 0;
-            int y = iy0 + oy; y -= y >= a.ny ? a.ny : 0;
-            int z = iz0 + oz; z -= z >= a.nz ? a.nz : 0;
-            const T value = qT*wt[ox]*wt[5 + oy]*wt[10 + oz];
-            const size_t cell = ((size_t) x*a.ny + y)*a.nz + z;
-            if (x < a.xLo || x >= a.xHi) continue;                        // another rank's plane
-            if (FIXED) atomicAdd(gridFixed + cell, (unsigned long long) __double2ll_rn((double) value*FixedGridScale<T>::value));
-            else atomicAdd(grid + cell, value);
+        const int pt = min(lane + 32*i, 124), row = pt/5;
+        oz[i] = pt - row*5; ox[i] = row/5; oy[i] = row - ox[i]*5;
+    }
+    const size_t G = (size_t) a.nx*a.ny*a.nz;
+    while (todo) {
+        const int b = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int ix0 = t.ix0[b], iy0 = t.iy0[b], iz0 = t.iz0[b];
+        const T qT = t.q[b];
+        T* grid = (T*) a.grid + (size_t) t.subset[b]*G;
+        unsigned long long* gridFixed = a.gridFixed + (size_t) t.subset[b]*G;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            if (lane + 32*i < 125) {
+                int x = ix0 + ox[i]; x -= x >= a.nx ? a.nx : 0;
+                int y = iy0 + oy[i]; y -= y >= a.ny ? a.ny : 0;
+                int z = iz0 + oz[i]; z -= z >= a.nz ? a.nz : 0;
+                const T value = qT*t.w[ox[i]][b]*t.w[5 + oy[i]][b]*t.w[10 + oz[i]][b];
+                const size_t cell = ((size_t) x*a.ny + y)*a.nz + z;
+                if (x < a.xLo || x >= a.xHi) continue;                        // another rank's plane
+                if (FIXED) atomicAdd(gridFixed + cell, (unsigned long long) __double2ll_rn((double) value*FixedGridScale<T>::value));
+                else atomicAdd(grid + cell, value);
+            }
         }
     }
 }
@@ -520,45 +570,61 @@ __global__ void __launch_bounds__(256) k_fft_x_conv(const FftArgs a) {
 // Reference: pme_grid_interpolate_force, ReferencePME.cpp:598-702.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_gather(const PmeArgs a) {
-    __shared__ float wtab[8][16], dwtab[8][16];
+    extern __shared__ __align__(16) unsigned char pmeSmem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int j = (blockIdx.x*blockDim.x + threadIdx.x) >> 5;
-    if (j >= a.N || !inSlabRanges(a, j)) return;
-    uint4 p; int subset; float q;
-    if (a.unsorted) { p = a.fix[j]; q = a.chargeF[j]; subset = a.subsetOf[j]; }
-    else { p = a.posq[j]; q = __uint_as_float(p.w); subset = __float_as_int(a.par[j].z) & 7; }
-    if (q == 0.f) return;
-    if (subset < a.ownLo || subset >= a.ownHi) return;
-    if (!touchesSlab(a, p)) return;
-    int ix0, iy0, iz0;
-    splineTable<float>(a, p, lane, wtab[warp], dwtab[warp], ix0, iy0, iz0);
-    const float* wt = wtab[warp];
-    const float* dwt = dwtab[warp];
-    const float* pot = a.pot + (size_t) subset*a.nx*a.ny*a.nz;
-    float fx = 0.f, fy = 0.f, fz = 0.f;
+    PmeWarpTab<float, true>& t = reinterpret_cast<PmeWarpTab<float, true>*>(pmeSmem)[warp];
+    unsigned todo = pmeBatchSetup<float, true>(a, t, lane, lane < a.batch ? ((int) blockIdx.x*((int) blockDim.x >> 5) + warp)*a.batch + lane : -1);
+    if (todo == 0u) return;
+    int ox[4], oy[4], oz[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        const int pt = lane + 32*i;                  // z fastest: coalesced runs of 5 cells per grid row
-        if (pt < 125) {
-            const int row = pt/5, oz = pt - row*5, ox = row/5, oy = row - ox*5;
-            int x = ix0 + ox; x -= x >= a.nx ? a.nx : 0;
-            int y = iy0 + oy; y -= y >= a.ny ? a.ny : 0;
-            int z = iz0 + oz; z -= z >= a.nz ? a.nz : 0;
-            // (slab sharding: the planes of other ranks contribute there; the force reduction adds the shares)
-            const float g = (x >= a.xLo && x < a.xHi) ? pot[((size_t) x*a.ny + y)*a.nz + z] : 0.f;
-            const float tx = wt[ox], ty = wt[5 + oy], tz = wt[10 + oz];
-            fx = fmaf(dwt[ox]*ty*tz, g, fx);
-            fy = fmaf(tx*dwt[5 + oy]*tz, g, fy);
-            fz = fmaf(tx*ty*dwt[10 + oz], g, fz);
-        }
+        const int pt = min(lane + 32*i, 124), row = pt/5;
+        oz[i] = pt - row*5; ox[i] = row/5; oy[i] = row - ox[i]*5;
     }
-    fx = warpSum(fx); fy = warpSum(fy); fz = warpSum(fz);
-    if (lane == 0) {
-        // F = -q (fx nx r00, fx nx r10 + fy ny r11, fx nx r20 + fy ny r21 + fz nz r22), ReferencePME.cpp:698-700
-        // (the off-diagonal reciprocal-vector terms are zero for a rectangular box)
-        atomicAdd(a.force + j, toFixed(-q*fx*a.fscale[0]));
-        atomicAdd(a.force + a.Npad + j, toFixed(-q*fmaf(fx, a.fr10, fy*a.fscale[1])));
-        atomicAdd(a.force + 2*(size_t) a.Npad + j, toFixed(-q*fmaf(fx, a.fr20, fmaf(fy, a.fr21, fz*a.fscale[2]))));
+    const size_t G = (size_t) a.nx*a.ny*a.nz;
+    while (todo) {
+        const int b = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int ix0 = t.ix0[b], iy0 = t.iy0[b], iz0 = t.iz0[b];
+        const float* pot = a.pot + (size_t) t.subset[b]*G;
+        float fx = 0.f, fy = 0.f, fz = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            if (lane + 32*i < 125) {
+                int x = ix0 + ox[i]; x -= x >= a.nx ? a.nx : 0;
+                int y = iy0 + oy[i]; y -= y >= a.ny ? a.ny : 0;
+                int z = iz0 + oz[i]; z -= z >= a.nz ? a.nz : 0;
+                // (slab sharding: the planes of other ranks contribute there; the force reduction adds the shares)
+                const float g = (x >= a.xLo && x < a.xHi) ? pot[((size_t) x*a.ny + y)*a.nz + z] : 0.f;
+                const float tx = t.w[ox[i]][b], ty = t.w[5 + oy[i]][b], tz = t.w[10 + oz[i]][b];
+                fx = fmaf(t.dw[ox[i]][b]*ty*tz, g, fx);
+                fy = fmaf(tx*t.dw[5 + oy[i]][b]*tz, g, fy);
+                fz = fmaf(tx*ty*t.dw[10 + oz[i]][b], g, fz);
+            }
+        }
+        // three sums over the warp in six exchanges: the upper half-warp takes over y (and a zero), the lower keeps x and z;
+        // then quarter-warps split those again, so that lanes 0-7 hold partial x, 8-15 z, 16-23 y
+        {
+            const bool up16 = lane & 16;
+            const float k0 = up16 ? fy : fx, s0 = up16 ? fx : fy;
+            const float k1 = up16 ? 0.f : fz, s1 = up16 ? fz : 0.f;
+            float u = k0 + __shfl_xor_sync(FULL_MASK, s0, 16);      // lower: x total of the pair, upper: y
+            float v = k1 + __shfl_xor_sync(FULL_MASK, s1, 16);      // lower: z, upper: nothing
+            const bool up8 = lane & 8;
+            const float keep = up8 ? v : u, send = up8 ? u : v;
+            float r = keep + __shfl_xor_sync(FULL_MASK, send, 8);   // lanes 0-7: x, 8-15: z, 16-23: y, 24-31: nothing
+            r += __shfl_xor_sync(FULL_MASK, r, 4);
+            r += __shfl_xor_sync(FULL_MASK, r, 2);
+            r += __shfl_xor_sync(FULL_MASK, r, 1);
+            fx = __shfl_sync(FULL_MASK, r, 0); fz = __shfl_sync(FULL_MASK, r, 8); fy = __shfl_sync(FULL_MASK, r, 16);
+        }
+        if (lane < 3) {
+            // F = -q (fx nx r00, fx nx r10 + fy ny r11, fx nx r20 + fy ny r21 + fz nz r22), ReferencePME.cpp:698-700
+            // (the off-diagonal reciprocal-vector terms are zero for a rectangular box)
+            const float q = t.q[b];
+            const float f = lane == 0 ? fx*a.fscale[0] : (lane == 1 ? fmaf(fx, a.fr10, fy*a.fscale[1]) : fmaf(fx, a.fr20, fmaf(fy, a.fr21, fz*a.fscale[2])));
+            if (f != 0.f) atomicAdd(a.force + (size_t) lane*a.Npad + t.atom[b], toFixed(-q*f));
+        }
     }
 }
 
@@ -723,6 +789,32 @@ static int launchPmeT(Context& c, bool wantEnergy, int half) {
             p.rangeBin[2] = B0*perCol; p.rangeBin[3] = (B1 + 1)*perCol;
         }
     }
+    // batches of up to 32 atoms per warp: fewer on small systems, so that there still are a few thousand warps (a batch
+    // is worked off one atom after the other -- at 32 atoms per warp a DHFR-size system would be 700 warps of latency)
+    int batch = 32;
+    while (batch > 4 && (long long) c.N < (long long) batch*c.numSMs*64) batch >>= 1;       // measured: 4 at C3, 8 at C4, 32 at C5
+    static const int batchEnv = getenv("NBS_PME_BATCH") ? atoi(getenv("NBS_PME_BATCH")) : 0;      // tuning experiments
+    if (batchEnv == 4 || batchEnv == 8 || batchEnv == 16 || batchEnv == 32) batch = batchEnv;
+    p.batch = batch;
+    const int pmeThreads = 256;
+    const size_t pmeSmem = sizeof(PmeWarpTab<T, false>)*(pmeThreads/32);
+    const int atomsPerCta = (pmeThreads/32)*batch;
+    int atomCtas = (c.N + atomsPerCta - 1)/atomsPerCta;
+    p.useHostRange = 0;
+    for (int k = 0; k < 4; k++) p.hostRange[k] = 0;
+    if (p.rangeBin[0] >= 0) {
+        if (c.reuseNow && c.slabRangeValid) {
+            // the sort order is the one whose ranges came back with the counters: launch exactly those atoms
+            p.useHostRange = 1;
+            for (int k = 0; k < 4; k++) p.hostRange[k] = c.slabRange[k];
+            atomCtas = std::max(1, (c.slabRange[1] - c.slabRange[0] + c.slabRange[3] - c.slabRange[2] + atomsPerCta - 1)/atomsPerCta);
+        }
+        else if (half == 0) {
+            // a fresh sort: every warp checks the ranges on the device; the host gets them with this evaluation's counters
+            k_slab_ranges<<<1, 32, 0, st>>>(c.dBinStart.d, p.rangeBin[0], p.rangeBin[1], p.rangeBin[2], p.rangeBin[3], c.dCounters.d + 8);
+            c.launches++;
+        }
+    }
     p.posq = c.dPosq.d; p.par = c.dPar.d; p.grid = c.dGrid.d; p.pot = c.dPot.d; p.gridFixed = nullptr;
     p.unsorted = c.pmeUnsorted ? 1 : 0;
     p.fix = c.dFix.d; p.chargeF = c.dChargeF.d; p.subsetOf = c.dSubset.d;
@@ -742,7 +834,6 @@ static int launchPmeT(Context& c, bool wantEnergy, int half) {
         p.fr20 = (float) (c.grid[0]*(g.tilt[0]*g.tilt[2] - g.box[1]*g.tilt[1])*g.invBox[0]*g.invBox[1]*g.invBox[2]);
         p.fr21 = (float) (-c.grid[1]*g.tilt[2]*g.invBox[1]*g.invBox[2]);
     }
-    const int atomCtas = (c.N + 7)/8;
     if (half == 0) {
         int status = prepareEterm(c);
         if (status != NBS_OK) return status;
@@ -754,14 +845,14 @@ static int launchPmeT(Context& c, bool wantEnergy, int half) {
             NBS_CUDA_CHECK(c.dGridFixed.ensure(G*c.nS));
             p.gridFixed = c.dGridFixed.d;
             NBS_CUDA_CHECK(cudaMemset2DAsync(c.dGridFixed.d + first, sizeof(unsigned long long)*G, 0, sizeof(unsigned long long)*cellsPerGrid, gridsToClear, st));
-            k_spread<T, true><<<atomCtas, 256, 0, st>>>(p);
+            k_spread<T, true><<<atomCtas, pmeThreads, pmeSmem, st>>>(p);
             k_fixed_to_real<T><<<dim3((unsigned) ((cellsPerGrid + 255)/256), gridsToClear), 256, 0, st>>>(cellsPerGrid, G, (const long long*) c.dGridFixed.d + first,
                                                                                                            (T*) c.dGrid.d + first);
             c.launches++;
         }
         else {
             NBS_CUDA_CHECK(cudaMemset2DAsync((T*) c.dGrid.d + first, sizeof(T)*G, 0, sizeof(T)*cellsPerGrid, gridsToClear, st));
-            k_spread<T, false><<<atomCtas, 256, 0, st>>>(p);
+            k_spread<T, false><<<atomCtas, pmeThreads, pmeSmem, st>>>(p);
         }
         c.launches++;
         timerMark(c, "spread");
@@ -803,7 +894,7 @@ static int launchPmeT(Context& c, bool wantEnergy, int half) {
         if (planeStatus == NBS_OK) {
             timerMark(c, half == 0 ? "fft_fwd" : (half == 3 ? "fft_inv" : "fft_conv_inv"));
             if (half == 1 || half == 3) {
-                k_gather<<<atomCtas, 256, 0, st>>>(p);
+                k_gather<<<atomCtas, pmeThreads, sizeof(PmeWarpTab<float, true>)*(pmeThreads/32), st>>>(p);
                 c.launches++;
                 timerMark(c, "gather");
             }
@@ -826,7 +917,7 @@ static int launchPmeT(Context& c, bool wantEnergy, int half) {
     else launchFftChain<T, 8>(c, f, px, py, pz, smX, smY, smZ, half);
     timerMark(c, half == 0 ? "fft_fwd" : "fft_conv_inv");
     if (half == 1) {
-        k_gather<<<atomCtas, 256, 0, st>>>(p);
+        k_gather<<<atomCtas, pmeThreads, sizeof(PmeWarpTab<float, true>)*(pmeThreads/32), st>>>(p);
         c.launches++;
         timerMark(c, "gather");
     }

@@ -865,6 +865,9 @@ static int phaseComplete(Context& c, const nbs_exec_args* args) {
             // a fresh sort (+ list): re-usable unless a block is so long that the pair kernel's window arithmetic
             // (corner - guard .. corner + box - guard) could not place a moved atom unambiguously
             c.buildCount++;
+            // (slab sharding: the sorted-atom ranges of the cell columns that reach the own planes, k_slab_ranges)
+            for (int k = 0; k < 4; k++) c.slabRange[k] = c.hCounters[8 + k];
+            c.slabRangeValid = c.slabMode && (c.slabRange[1] > c.slabRange[0] || c.slabRange[3] > c.slabRange[2]);
             bool fits = true;
             for (int d = 0; d < 3; d++) {
                 const double guard = (0.5*c.skin + 1.0e-3)/c.geom.box[d]*4294967296.0;

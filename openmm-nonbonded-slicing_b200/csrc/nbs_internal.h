@@ -235,6 +235,8 @@ struct Context {
     Buf<PeerMailbox> dMailbox;
     unsigned long long* hTimedOut = nullptr;    // pinned copy of the mailbox's timedOut word
     int slabStep = 0;                           // next step of the evaluation in flight
+    int slabRange[4] = {0, 0, 0, 0};            // sorted atoms that can reach the own planes: [0],[1]) and [2],[3]) (host copy of counters[8..11])
+    bool slabRangeValid = false;
     bool pmeUnsorted = false;                // PME works from particle-order coordinates (forks before the sort)
     int chunkTiles = 2;                      // tiles per pair-kernel work item
     // ---- neighbour-list re-use (periodic cutoff methods): the list is built with cutoff + skin and kept until an

@@ -81,6 +81,12 @@ extern "C" {
 #define NBS_FLAG_NO_LIST_REUSE   0x40u /* rebuild the neighbour list on every evaluation, like the
                                           Reference platform (default: built with a skin and kept
                                           until an atom has moved half of it, see nbs_set_list_skin) */
+#define NBS_FLAG_DOUBLE          0x80u /* the plugin's Precision = double (CommonNonbondedSlicingKernels.cpp:297-299; every CUDA
+                                          test of the reference runs in single, mixed and double, platforms/cuda/tests/
+                                          CMakeLists.txt:22-24): direct-space forces in double precision arithmetic from the
+                                          exact fixed-point coordinates, double-precision PME grids, transforms and gather.
+                                          Coordinates still carry 32 fractional bits of the box (5e-9 nm at 21 nm), which is
+                                          what bounds the agreement with a double-precision reference (measured 2e-8 of the forces) */
 #define NBS_FLAG_FP32_ENERGY     0x8u  /* single-precision pair energies and PME grids (the
                                           plugin's "single" precision); default is double
                                           precision for every energy term, fp32 for forces    */

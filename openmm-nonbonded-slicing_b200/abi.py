@@ -25,6 +25,7 @@ NBS_FLAG_FP32_ENERGY = 0x8
 NBS_FLAG_LINE_FFT = 0x10
 NBS_FLAG_SORTED_PME = 0x20
 NBS_FLAG_NO_LIST_REUSE = 0x40
+NBS_FLAG_DOUBLE = 0x80
 
 NBS_MEM_HOST = 0
 NBS_MEM_DEVICE = 1

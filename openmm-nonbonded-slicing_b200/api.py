@@ -945,12 +945,34 @@ class B200CalcSlicedNonbondedForceKernel(SlicedKernelBase):
 class Platform:
     """The "B200" platform: creates kernels backed by the CUDA library."""
 
-    def __init__(self, deviceIndex=0, flags=0):
+    def __init__(self, deviceIndex=0, flags=0, properties=None):
         self.deviceIndex = deviceIndex
         self.flags = flags
+        self.properties = {"Precision": "mixed", "DeterministicForces": "false"}
+        for name, value in (properties or {}).items():
+            self.setPropertyDefaultValue(name, value)
 
     def getName(self):
         return "B200"
+
+    # the two properties of OpenMM's CUDA platform that reach this force (CudaNonbondedSlicingKernels.cpp:22-33,
+    # CommonNonbondedSlicingKernels.cpp:297-299): Precision = single | mixed | double, DeterministicForces = true | false
+    def getPropertyDefaultValue(self, name):
+        return self.properties[name]
+
+    def setPropertyDefaultValue(self, name, value):
+        if name == "Precision":
+            if value not in ("single", "mixed", "double"):
+                raise OpenMMException("Illegal value for Precision: " + str(value))
+            self.flags &= ~(abi.NBS_FLAG_DOUBLE | abi.NBS_FLAG_FP32_ENERGY)
+            self.flags |= {"single": abi.NBS_FLAG_FP32_ENERGY, "mixed": 0, "double": abi.NBS_FLAG_DOUBLE}[value]
+        elif name == "DeterministicForces":
+            self.flags &= ~abi.NBS_FLAG_DETERMINISTIC
+            if str(value).lower() == "true":
+                self.flags |= abi.NBS_FLAG_DETERMINISTIC
+        else:
+            raise OpenMMException("Illegal property name: " + str(name))
+        self.properties[name] = value
 
     def createKernel(self, name, context):
         if name != CalcSlicedNonbondedForceKernel.Name():

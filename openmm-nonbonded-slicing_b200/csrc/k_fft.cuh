@@ -34,7 +34,8 @@ struct PlaneFftArgs {
     const void* grid;                // real charge grids   [nS][nx][ny][nz]      (T)
     void* gridC;                     // half spectra        [nS][nx][ny][nz/2+1]  (complex T)
     const void* eterm;               // influence function  [nx][ny][nz/2+1]      (T)
-    float* pot;                      // potential grids     [nS][nx][ny][nz]      (float)
+    float* pot;                      // potential grids     [nS][nx][ny][nz]      (float; double when potDouble)
+    int potDouble;
     double* energy;
     int wantEnergy;
     LambdaTable lam;

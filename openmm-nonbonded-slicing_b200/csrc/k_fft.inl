@@ -407,12 +407,19 @@ __global__ void __launch_bounds__(FFT_THREADS) k_fft_yz_inv(const PlaneFftArgs a
         }
         batchedFft<RMAX>(plane, pairs, 2*rs, 1, nz, a.factorsZ, twz);
         float* pot = a.pot + ((size_t) sx*ny + rowBase)*nz;
+        double* potD = (double*) a.pot + ((size_t) sx*ny + rowBase)*nz;       // NBS_FLAG_DOUBLE: a double potential grid
         for (int idx = threadIdx.x; idx < pairs*nz; idx += blockDim.x) {
             int p, z;
-        divNz.divmod(idx, p, z);
+            divNz.divmod(idx, p, z);
             const C wv = plane[(size_t) p*2*rs + z];
-            pot[(size_t) (2*p)*nz + z] = (float) wv.x;
-            if (2*p + 1 < rowsHere) pot[(size_t) (2*p + 1)*nz + z] = (float) -wv.y;
+            if (a.potDouble) {
+                potD[(size_t) (2*p)*nz + z] = (double) wv.x;
+                if (2*p + 1 < rowsHere) potD[(size_t) (2*p + 1)*nz + z] = (double) -wv.y;
+            }
+            else {
+                pot[(size_t) (2*p)*nz + z] = (float) wv.x;
+                if (2*p + 1 < rowsHere) pot[(size_t) (2*p + 1)*nz + z] = (float) -wv.y;
+            }
         }
     }
 }

@@ -57,6 +57,9 @@ struct PairArgs {
     int useSwitch;
     double rc2d, alphaD, krfD, crfD;
     float dalpha2, invCut6, shiftMult;   // LJPME: alpha_d^2, rc^-6, rc^-6 (1 - exp(-x)(1 + x + x^2/2)) at x = (alpha_d rc)^2
+    double dalpha2D, invCut6D, shiftMultD, rswitchD, rcutD;     // the same (and the switching range) for the double-precision kernel
+    const double2* sigEpsD;              // double-precision kernel: (sigma/2, 2 sqrt(eps)) by PARTICLE index
+    const double* lamD;                  // double-precision kernel: [nSl][2] (lambda_Coulomb, lambda_vdW)
     const double* q64;                   // sorted charges * sqrt(ONE_4PI_EPS0), double
     const double* erfcTab;               // piecewise fit of erfc(alpha sqrt(s))/sqrt(s) in s = r^2: c0[tabRows], float4 (c1..c4)[tabRows]
     int tabRows;
@@ -658,6 +661,178 @@ __global__ void __launch_bounds__(PAIR_WARPS*32, MINCTAS) k_pair(const PairArgs 
     }
 }
 
+// ---- double-precision force mode (NBS_FLAG_DOUBLE) ----------------------------------------------------------------
+// The plugin's Precision = double (CommonNonbondedSlicingKernels.cpp:297-299).  Same neighbour list and work items; the
+// arithmetic of ReferenceSlicedLJCoulombIxn.cpp:367-445 (:571-631 for the reaction field) in double precision from the
+// exact fixed-point coordinates, libm-grade erfc / exp.  Not tuned: one lane per i atom, lane l meets j slot (l + k) mod 32
+// at step k and the j accumulators rotate one lane per step.
+struct __align__(16) WarpScratchD {
+    long long jX[32], jY[32], jZ[32];          // relative to the i-block's corner, fixed-point units
+    unsigned jMask[32];
+    double jQ[32], jSig[32], jEps[32];
+    int jSub[32], jIndex[32];                  // jIndex < 0: padding
+};
+
+template <int CMODE>
+__global__ void __launch_bounds__(256) k_pair_f64(const PairArgs a) {
+    __shared__ WarpScratchD scratch[8];
+    __shared__ double shE[MAX_SLICES*2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpScratchD& w = scratch[warp];
+    if (threadIdx.x < MAX_SLICES*2) shE[threadIdx.x] = 0.0;
+    __syncthreads();
+    const int nItems = a.counters[2];
+    double acc[MAX_SLICES*2];
+#pragma unroll
+    for (int k = 0; k < MAX_SLICES*2; k++) acc[k] = 0.0;
+    const double TWO_OVER_SQRT_PI = 1.1283791670955125739;
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(a.counters + 3, 1);
+        item = __shfl_sync(FULL_MASK, item, 0);
+        if (item >= nItems) break;
+        const int4 it = a.items[item];
+        const int lb = it.x, first = it.z, cnt = it.w;
+        const int* jl = a.jlist + (size_t) lb*a.capJ;
+        const int* xl = a.xlist + (size_t) lb*a.capX;
+        const unsigned* xm = a.xmask + (size_t) lb*a.capX;
+        const int nJ = a.jcount[lb], nX = a.xcount[lb];
+        const int tJ = (nJ + 31) >> 5, tX = (nX + 31) >> 5;
+        const int tEnd = min(it.y + a.chunkTiles, tJ + tX);
+        const bool iValid = lane < cnt;
+        const uint4 lo = a.blkLo[localToGlobalBlock(lb, a.blockPeriod, a.blockOffset, a.blockWidth)];
+        uint4 pi = lo;
+        double qi = 0.0, sigi = 0.0, epsi = 0.0;
+        int si = 0;
+        // coordinates relative to the block's corner, in 64-bit fixed-point units: the i atom in the window [corner - guard,
+        // corner + box - guard), a list entry at the periodic image its image code names -- exactly the geometry of the
+        // single-precision kernel, without its conversion to float (a plain wrapped 32-bit difference would pick the
+        // NEAREST image of j, which in a small box can be a second entry of the same list)
+        long long wix = 0, wiy = 0, wiz = 0;
+        if (iValid) {
+            pi = a.posq[first + lane];
+            const float4 pr = a.par[first + lane];
+            const LatticeShift ls = crossShift(__float_as_int(pr.z), a);
+            pi.x += (unsigned) ls.x; pi.y += (unsigned) ls.y;
+            wix = (long long) (pi.x - lo.x + a.guardX) - (long long) a.guardX;
+            wiy = (long long) (pi.y - lo.y + a.guardY) - (long long) a.guardY;
+            wiz = (long long) (pi.z - lo.z + a.guardZ) - (long long) a.guardZ;
+            qi = a.q64[first + lane];
+            const double2 se = a.sigEpsD[__float_as_int(pr.w)];
+            sigi = se.x; epsi = se.y;
+            si = __float_as_int(pr.z) & 7;
+        }
+        double fix = 0.0, fiy = 0.0, fiz = 0.0;
+        for (int t = it.y; t < tEnd; t++) {
+            const bool isX = t >= tJ;
+            const int entry = isX ? xl[(t - tJ)*32 + lane] : jl[t*32 + lane];
+            __syncwarp();
+            w.jIndex[lane] = -1;
+            w.jMask[lane] = isX ? xm[(t - tJ)*32 + lane] : 0u;
+            if (entry >= 0) {
+                const int j = entry & J_INDEX_MASK, code = entry >> J_SHIFT_BITS;
+                const uint4 q = a.posq[j];
+                const float4 pr = a.par[j];
+                const LatticeShift ls = crossShift(__float_as_int(pr.z), a);
+                const int kz = code/15 - 1;
+                const long long shx = ((long long) (code % 5 - 2) << 32) + ((code/5) % 3 - 1)*a.shiftB + kz*a.shiftCx + ls.x;
+                const long long shy = ((long long) ((code/5) % 3 - 1) << 32) + kz*a.shiftCy + ls.y;
+                w.jX[lane] = (long long) q.x + shx - (long long) lo.x;
+                w.jY[lane] = (long long) q.y + shy - (long long) lo.y;
+                w.jZ[lane] = (long long) q.z + ((long long) kz << 32) + ls.z - (long long) lo.z;
+                w.jQ[lane] = a.q64[j];
+                const double2 se = a.sigEpsD[__float_as_int(pr.w)];
+                w.jSig[lane] = se.x; w.jEps[lane] = se.y;
+                w.jSub[lane] = __float_as_int(pr.z) & 7;
+                w.jIndex[lane] = j;
+            }
+            __syncwarp();
+            double fjx = 0.0, fjy = 0.0, fjz = 0.0;
+#pragma unroll 1
+            for (int k = 0; k < 32; k++) {
+                const int slot = (lane + k) & 31;
+                const int jIndex = w.jIndex[slot];
+                bool on = iValid && jIndex >= 0 && !((w.jMask[slot] >> lane) & 1u);
+                // j - i
+                const double ex = (double) (w.jX[slot] - wix)*a.dsx;
+                const double ey = (double) (w.jY[slot] - wiy)*a.dsy;
+                const double ez = (double) (w.jZ[slot] - wiz)*a.dsz;
+                const double r2 = ex*ex + ey*ey + ez*ez;
+                on = on && r2 <= a.rc2d;
+                if (on) {
+                    const double r = sqrt(r2), invR = 1.0/r, invR2 = invR*invR;
+                    const double sig = sigi + w.jSig[slot];
+                    double s2 = sig*invR; s2 *= s2;
+                    const double s6 = s2*s2*s2;
+                    const double eps = epsi*w.jEps[slot];
+                    double ev = eps*(s6 - 1.0)*s6;
+                    double fv = eps*(12.0*s6 - 6.0)*s6*invR2;
+                    const double qq = qi*w.jQ[slot];
+                    double ec, fc;
+                    if (CMODE != 0) {
+                        const double ar = a.alphaD*r;
+                        const double erfcv = erfc(ar), ex2 = exp(-ar*ar);
+                        ec = qq*invR*erfcv;
+                        fc = qq*invR*invR2*(erfcv + TWO_OVER_SQRT_PI*ar*ex2);
+                    }
+                    else {
+                        ec = qq*(invR + a.krfD*r2 - a.crfD);
+                        fc = qq*(invR*invR2 - 2.0*a.krfD);
+                    }
+                    if (CMODE == 2) {                     // LJPME, :398-426
+                        const double sg = sigi*w.jSig[slot];
+                        const double c6 = 64.0*sg*sg*sg*eps;
+                        const double dar2 = a.dalpha2D*r2, exd = exp(-dar2);
+                        const double p2 = 1.0 + dar2 + 0.5*dar2*dar2;
+                        const double c6r6 = c6*invR2*invR2*invR2;
+                        fv += 6.0*c6r6*invR2*(1.0 - exd*(p2 + dar2*dar2*dar2/6.0));
+                        double sc = sig*sig;
+                        const double sc6 = sc*sc*sc*a.invCut6D;
+                        ev += c6r6*(1.0 - exd*p2) + eps*(1.0 - sc6)*sc6 - c6*a.shiftMultD;
+                    }
+                    if (a.useSwitch && r > a.rswitchD) {
+                        const double wd = 1.0/(a.rcutD - a.rswitchD), u = (r - a.rswitchD)*wd;
+                        const double sv = 1.0 + u*u*u*(-10.0 + u*(15.0 - u*6.0));
+                        const double sd = u*u*(-30.0 + u*(60.0 - u*30.0))*wd;
+                        fv = sv*fv - ev*sd*invR;
+                        ev *= sv;
+                    }
+                    const int sl = triSlice(si, w.jSub[slot]);
+                    const double dEdR = a.lamD[2*sl + 1]*fv + a.lamD[2*sl]*fc;
+                    // force on i = dEdR (x_i - x_j) = -dEdR e;  on j the opposite
+                    fix -= dEdR*ex; fiy -= dEdR*ey; fiz -= dEdR*ez;
+                    fjx += dEdR*ex; fjy += dEdR*ey; fjz += dEdR*ez;
+                    acc[2*sl] += ec;
+                    acc[2*sl + 1] += ev;
+                }
+                // the accumulator of slot (lane + k) moves to the lane that meets that slot next: lane - 1
+                fjx = __shfl_sync(FULL_MASK, fjx, (lane + 1) & 31);
+                fjy = __shfl_sync(FULL_MASK, fjy, (lane + 1) & 31);
+                fjz = __shfl_sync(FULL_MASK, fjz, (lane + 1) & 31);
+            }
+            // 32 rotations: lane l holds the total of slot l again
+            const int jIndex = w.jIndex[lane];
+            if (jIndex >= 0) {
+                if (fjx != 0.0) atomicAdd(a.force + jIndex, toFixed(fjx));
+                if (fjy != 0.0) atomicAdd(a.force + (size_t) a.Npad + jIndex, toFixed(fjy));
+                if (fjz != 0.0) atomicAdd(a.force + 2*(size_t) a.Npad + jIndex, toFixed(fjz));
+            }
+        }
+        if (iValid) {
+            if (fix != 0.0) atomicAdd(a.force + first + lane, toFixed(fix));
+            if (fiy != 0.0) atomicAdd(a.force + (size_t) a.Npad + first + lane, toFixed(fiy));
+            if (fiz != 0.0) atomicAdd(a.force + 2*(size_t) a.Npad + first + lane, toFixed(fiz));
+        }
+    }
+    for (int k = 0; k < a.nE; k++) {
+        const double v = warpSum(acc[k]);
+        if (lane == 0 && v != 0.0) atomicAdd(&shE[k], v);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < a.nE; k += blockDim.x)
+        if (shE[k] != 0.0) atomicAdd(a.energy + k, shE[k]);
+}
+
 template <int EMODE, int CMODE, int MODE, bool CUBIC, int MINCTAS>
 static int launchPairK(Context& c, const PairArgs& a) {
     static bool attr[64] = {false};
@@ -752,6 +927,24 @@ int launchPairs(Context& c, bool wantEnergy, int mode) {
     const bool pme = c.ewaldDirect();
     const int emode = !wantEnergy ? 0 : ((c.flags & NBS_FLAG_FP32_ENERGY) ? 1 : 2);
     int status;
+    if (mode == 0 && (c.flags & NBS_FLAG_DOUBLE)) {
+        // Precision = double: its own kernel (energies always computed; they cost nothing extra there)
+        a.dalpha2D = c.dispAlpha*c.dispAlpha;
+        a.invCut6D = noCutoff ? 0.0 : std::pow(c.cutoff, -6.0);
+        { const double dac2 = a.dalpha2D*c.cutoff*c.cutoff; a.shiftMultD = a.invCut6D*(1.0 - std::exp(-dac2)*(1.0 + dac2 + 0.5*dac2*dac2)); }
+        a.rswitchD = c.switchDist; a.rcutD = c.cutoff;
+        a.sigEpsD = c.dSigEpsD.d;
+        NBS_CUDA_CHECK(c.dLamD.ensure(2*MAX_SLICES));
+        NBS_CUDA_CHECK(cudaMemcpyAsync(c.dLamD.d, c.lambdas.data(), sizeof(double)*2*c.nSl, cudaMemcpyHostToDevice, c.stream));
+        a.lamD = c.dLamD.d;
+        const int ctas = 4*c.numSMs;
+        if (c.ljpme()) k_pair_f64<2><<<ctas, 256, 0, c.stream>>>(a);
+        else if (pme) k_pair_f64<1><<<ctas, 256, 0, c.stream>>>(a);
+        else k_pair_f64<0><<<ctas, 256, 0, c.stream>>>(a);
+        c.launches++;
+        timerMark(c, "pair");
+        return NBS_OK;
+    }
     if (mode != 0) {
         NBS_CUDA_CHECK(cudaMemsetAsync(c.dCounters.d + 3, 0, sizeof(int), c.stream));      // rewind the work cursor
         status = mode == 1 ? launchPairT<0, 1, 1, false>(c, a) : launchPairT<0, 1, 2, false>(c, a);

@@ -198,6 +198,7 @@ struct PmeArgs {
     int triclinic;
     double beta, gammaY, delta;  // bx/ax, cy/by, (bx cy - by cx)/(ax by)
     float fr10, fr20, fr21;      // nx r10, nx r20, ny r21
+    double fscaleD[3], fr10D, fr20D, fr21D;      // the same in double (NBS_FLAG_DOUBLE)
 };
 
 // Brick fractions -> lattice fractions (both 32-bit fixed point); identity for a rectangular box.
@@ -268,7 +269,7 @@ constexpr int PME_TAB_STRIDE = 33;
 template <typename T, bool DERIV>
 struct __align__(16) PmeWarpTab {
     T w[15][PME_TAB_STRIDE];           // spline weights: [0..4] x, [5..9] y, [10..14] z
-    float dw[DERIV ? 15 : 1][PME_TAB_STRIDE];      // their derivatives (gather)
+    T dw[DERIV ? 15 : 1][PME_TAB_STRIDE];          // their derivatives (gather)
     T q[32];
     int ix0[32], iy0[32], iz0[32], subset[32], atom[32];
 };
@@ -290,15 +291,15 @@ __device__ __forceinline__ unsigned pmeBatchSetup(const PmeArgs& a, PmeWarpTab<T
         gridCoord<T>(f.x, a.nx, index, frac); t.ix0[lane] = index;
         bspline5(frac, th, dth);
 #pragma unroll
-        for (int k = 0; k < 5; k++) { t.w[k][lane] = th[k]; if (DERIV) t.dw[k][lane] = (float) dth[k]; }
+        for (int k = 0; k < 5; k++) { t.w[k][lane] = th[k]; if (DERIV) t.dw[k][lane] = dth[k]; }
         gridCoord<T>(f.y, a.ny, index, frac); t.iy0[lane] = index;
         bspline5(frac, th, dth);
 #pragma unroll
-        for (int k = 0; k < 5; k++) { t.w[5 + k][lane] = th[k]; if (DERIV) t.dw[5 + k][lane] = (float) dth[k]; }
+        for (int k = 0; k < 5; k++) { t.w[5 + k][lane] = th[k]; if (DERIV) t.dw[5 + k][lane] = dth[k]; }
         gridCoord<T>(f.z, a.nz, index, frac); t.iz0[lane] = index;
         bspline5(frac, th, dth);
 #pragma unroll
-        for (int k = 0; k < 5; k++) { t.w[10 + k][lane] = th[k]; if (DERIV) t.dw[10 + k][lane] = (float) dth[k]; }
+        for (int k = 0; k < 5; k++) { t.w[10 + k][lane] = th[k]; if (DERIV) t.dw[10 + k][lane] = dth[k]; }
         // (the fp32 charge carries 6e-8 of rounding: visible in cross-subset energies that cancel to 1e-6 of their terms)
         t.q[lane] = sizeof(T) == 8 ? (T) (a.unsorted ? a.chargeD[j]*a.sqrtK : a.q64[j]) : (T) q;
         t.subset[lane] = subset;
@@ -370,7 +371,8 @@ struct FftArgs {
     unsigned long long factors;  // its radices, 4 bits each
     const void* tw;              // twiddles of this dimension: exp(-2 pi i k / n), precision T
     void* grid; void* gridC; const void* eterm;
-    float* pot;                  // real-space potential grid (always float; read by the gather)
+    float* pot;                  // real-space potential grid read by the gather (float; double when potDouble)
+    int potDouble;
     double* energy;
     int wantEnergy;
     LambdaTable lam;
@@ -432,10 +434,11 @@ __global__ void __launch_bounds__(256) k_fft_z_inv(const FftArgs a) {
     warpFft<NQ>(line, a.n, a.factors, tw, lane);
     float* r0 = a.pot + ((size_t) sx*a.ny + y0)*n;
     float* r1 = r0 + n;
+    double* d0 = (double*) a.pot + ((size_t) sx*a.ny + y0)*n;
     for (int z = lane; z < n; z += 32) {
         const C w = line[z];
-        r0[z] = (float) w.x;
-        if (y1 < a.ny) r1[z] = (float) -w.y;
+        if (a.potDouble) { d0[z] = (double) w.x; if (y1 < a.ny) d0[n + z] = (double) -w.y; }
+        else { r0[z] = (float) w.x; if (y1 < a.ny) r1[z] = (float) -w.y; }
     }
 }
 
@@ -569,11 +572,12 @@ __global__ void __launch_bounds__(256) k_fft_x_conv(const FftArgs a) {
 // Gather: one warp per atom, 125 points of the atom's own (lambda-mixed) potential grid.
 // Reference: pme_grid_interpolate_force, ReferencePME.cpp:598-702.
 // ---------------------------------------------------------------------------------------------
+template <typename T>
 __global__ void __launch_bounds__(256) k_gather(const PmeArgs a) {
     extern __shared__ __align__(16) unsigned char pmeSmem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    PmeWarpTab<float, true>& t = reinterpret_cast<PmeWarpTab<float, true>*>(pmeSmem)[warp];
-    unsigned todo = pmeBatchSetup<float, true>(a, t, lane, lane < a.batch ? ((int) blockIdx.x*((int) blockDim.x >> 5) + warp)*a.batch + lane : -1);
+    PmeWarpTab<T, true>& t = reinterpret_cast<PmeWarpTab<T, true>*>(pmeSmem)[warp];
+    unsigned todo = pmeBatchSetup<T, true>(a, t, lane, lane < a.batch ? ((int) blockIdx.x*((int) blockDim.x >> 5) + warp)*a.batch + lane : -1);
     if (todo == 0u) return;
     int ox[4], oy[4], oz[4];
 #pragma unroll
@@ -586,8 +590,8 @@ __global__ void __launch_bounds__(256) k_gather(const PmeArgs a) {
         const int b = __ffs(todo) - 1;
         todo &= todo - 1;
         const int ix0 = t.ix0[b], iy0 = t.iy0[b], iz0 = t.iz0[b];
-        const float* pot = a.pot + (size_t) t.subset[b]*G;
-        float fx = 0.f, fy = 0.f, fz = 0.f;
+        const T* pot = (const T*) a.pot + (size_t) t.subset[b]*G;
+        T fx = 0, fy = 0, fz = 0;
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             if (lane + 32*i < 125) {
@@ -595,24 +599,24 @@ __global__ void __launch_bounds__(256) k_gather(const PmeArgs a) {
                 int y = iy0 + oy[i]; y -= y >= a.ny ? a.ny : 0;
                 int z = iz0 + oz[i]; z -= z >= a.nz ? a.nz : 0;
                 // (slab sharding: the planes of other ranks contribute there; the force reduction adds the shares)
-                const float g = (x >= a.xLo && x < a.xHi) ? pot[((size_t) x*a.ny + y)*a.nz + z] : 0.f;
-                const float tx = t.w[ox[i]][b], ty = t.w[5 + oy[i]][b], tz = t.w[10 + oz[i]][b];
-                fx = fmaf(t.dw[ox[i]][b]*ty*tz, g, fx);
-                fy = fmaf(tx*t.dw[5 + oy[i]][b]*tz, g, fy);
-                fz = fmaf(tx*ty*t.dw[10 + oz[i]][b], g, fz);
+                const T g = (x >= a.xLo && x < a.xHi) ? pot[((size_t) x*a.ny + y)*a.nz + z] : (T) 0;
+                const T tx = t.w[ox[i]][b], ty = t.w[5 + oy[i]][b], tz = t.w[10 + oz[i]][b];
+                fx = fma(t.dw[ox[i]][b]*ty*tz, g, fx);
+                fy = fma(tx*t.dw[5 + oy[i]][b]*tz, g, fy);
+                fz = fma(tx*ty*t.dw[10 + oz[i]][b], g, fz);
             }
         }
         // three sums over the warp in six exchanges: the upper half-warp takes over y (and a zero), the lower keeps x and z;
         // then quarter-warps split those again, so that lanes 0-7 hold partial x, 8-15 z, 16-23 y
         {
             const bool up16 = lane & 16;
-            const float k0 = up16 ? fy : fx, s0 = up16 ? fx : fy;
-            const float k1 = up16 ? 0.f : fz, s1 = up16 ? fz : 0.f;
-            float u = k0 + __shfl_xor_sync(FULL_MASK, s0, 16);      // lower: x total of the pair, upper: y
-            float v = k1 + __shfl_xor_sync(FULL_MASK, s1, 16);      // lower: z, upper: nothing
+            const T k0 = up16 ? fy : fx, s0 = up16 ? fx : fy;
+            const T k1 = up16 ? (T) 0 : fz, s1 = up16 ? fz : (T) 0;
+            T u = k0 + __shfl_xor_sync(FULL_MASK, s0, 16);          // lower: x total of the pair, upper: y
+            T v = k1 + __shfl_xor_sync(FULL_MASK, s1, 16);          // lower: z, upper: nothing
             const bool up8 = lane & 8;
-            const float keep = up8 ? v : u, send = up8 ? u : v;
-            float r = keep + __shfl_xor_sync(FULL_MASK, send, 8);   // lanes 0-7: x, 8-15: z, 16-23: y, 24-31: nothing
+            const T keep = up8 ? v : u, send = up8 ? u : v;
+            T r = keep + __shfl_xor_sync(FULL_MASK, send, 8);       // lanes 0-7: x, 8-15: z, 16-23: y, 24-31: nothing
             r += __shfl_xor_sync(FULL_MASK, r, 4);
             r += __shfl_xor_sync(FULL_MASK, r, 2);
             r += __shfl_xor_sync(FULL_MASK, r, 1);
@@ -621,9 +625,11 @@ __global__ void __launch_bounds__(256) k_gather(const PmeArgs a) {
         if (lane < 3) {
             // F = -q (fx nx r00, fx nx r10 + fy ny r11, fx nx r20 + fy ny r21 + fz nz r22), ReferencePME.cpp:698-700
             // (the off-diagonal reciprocal-vector terms are zero for a rectangular box)
-            const float q = t.q[b];
-            const float f = lane == 0 ? fx*a.fscale[0] : (lane == 1 ? fmaf(fx, a.fr10, fy*a.fscale[1]) : fmaf(fx, a.fr20, fmaf(fy, a.fr21, fz*a.fscale[2])));
-            if (f != 0.f) atomicAdd(a.force + (size_t) lane*a.Npad + t.atom[b], toFixed(-q*f));
+            const T q = t.q[b];
+            const T f = sizeof(T) == 8
+                ? (lane == 0 ? fx*(T) a.fscaleD[0] : (lane == 1 ? fx*(T) a.fr10D + fy*(T) a.fscaleD[1] : fx*(T) a.fr20D + fy*(T) a.fr21D + fz*(T) a.fscaleD[2]))
+                : (lane == 0 ? fx*(T) a.fscale[0] : (lane == 1 ? fx*(T) a.fr10 + fy*(T) a.fscale[1] : fx*(T) a.fr20 + fy*(T) a.fr21 + fz*(T) a.fscale[2]));
+            if (f != (T) 0) atomicAdd(a.force + (size_t) lane*a.Npad + t.atom[b], toFixed(-q*f));
         }
     }
 }
@@ -732,7 +738,7 @@ static void launchFftChain(Context& c, FftArgs f, const FftPlan& px, const FftPl
     own.nS = nOwn;
     own.grid = (T*) f.grid + (size_t) c.ownLo*nx*ny*nz;
     own.gridC = (C*) f.gridC + (size_t) c.ownLo*nx*ny*nzh;
-    own.pot = f.pot + (size_t) c.ownLo*nx*ny*nz;
+    own.pot = f.potDouble ? (float*) ((double*) f.pot + (size_t) c.ownLo*nx*ny*nz) : f.pot + (size_t) c.ownLo*nx*ny*nz;
     if (half == 0) {
         own.n = pz.n; own.factors = pz.packed; own.tw = tw + nx + ny;
         k_fft_z_fwd<T, NQ><<<(pairs + 7)/8, 256, smZ, st>>>(own);
@@ -823,16 +829,17 @@ static int launchPmeT(Context& c, bool wantEnergy, int half) {
         p.unsorted = 1; p.chargeF = c.dC6F.d; p.chargeD = c.dC6D.d; p.sqrtK = 1.0;
     }
     p.force = c.pmeUnsorted ? c.dForce.d + 3*(size_t) c.Npad : c.dForce.d;
-    for (int k = 0; k < 3; k++) p.fscale[k] = (float) (c.grid[k]*c.geom.invBox[k]);
+    for (int k = 0; k < 3; k++) { p.fscale[k] = (float) (c.grid[k]*c.geom.invBox[k]); p.fscaleD[k] = c.grid[k]*c.geom.invBox[k]; }
     {
         const CellGeom& g = c.geom;
         p.triclinic = g.triclinic ? 1 : 0;
         p.beta = g.tilt[0]*g.invBox[0];
         p.gammaY = g.tilt[2]*g.invBox[1];
         p.delta = (g.tilt[0]*g.tilt[2] - g.box[1]*g.tilt[1])*g.invBox[0]*g.invBox[1];
-        p.fr10 = (float) (-c.grid[0]*g.tilt[0]*g.invBox[0]*g.invBox[1]);
-        p.fr20 = (float) (c.grid[0]*(g.tilt[0]*g.tilt[2] - g.box[1]*g.tilt[1])*g.invBox[0]*g.invBox[1]*g.invBox[2]);
-        p.fr21 = (float) (-c.grid[1]*g.tilt[2]*g.invBox[1]*g.invBox[2]);
+        p.fr10D = -c.grid[0]*g.tilt[0]*g.invBox[0]*g.invBox[1];
+        p.fr20D = c.grid[0]*(g.tilt[0]*g.tilt[2] - g.box[1]*g.tilt[1])*g.invBox[0]*g.invBox[1]*g.invBox[2];
+        p.fr21D = -c.grid[1]*g.tilt[2]*g.invBox[1]*g.invBox[2];
+        p.fr10 = (float) p.fr10D; p.fr20 = (float) p.fr20D; p.fr21 = (float) p.fr21D;
     }
     if (half == 0) {
         int status = prepareEterm(c);
@@ -863,7 +870,8 @@ static int launchPmeT(Context& c, bool wantEnergy, int half) {
     f.ownLo = c.ownLo; f.ownHi = c.ownHi;
     // the convolution kernels add slice s's energy to energy[2 s]: Coulomb term, or (dispersion chain) the vdW term
     double* const energyBase = c.dEnergy.d + (c.dispersionPass ? 1 : 0);
-    f.grid = c.dGrid.d; f.gridC = c.dGridC.d; f.pot = c.dPot.d; f.energy = energyBase;
+    const bool doubleForces = sizeof(T) == 8 && (c.flags & NBS_FLAG_DOUBLE);
+    f.grid = c.dGrid.d; f.gridC = c.dGridC.d; f.pot = c.dPot.d; f.potDouble = doubleForces ? 1 : 0; f.energy = energyBase;
     f.eterm = sizeof(T) == 8 ? (const void*) c.dEtermD.d : (const void*) c.dEterm.d;
     f.wantEnergy = wantEnergy ? 1 : 0;
     for (int s = 0; s < MAX_SLICES; s++) {
@@ -887,14 +895,21 @@ static int launchPmeT(Context& c, bool wantEnergy, int half) {
         pa.nRanks = c.slabMode ? c.nRanks : 1;
         for (int r = 0; r < NBS_MAX_RANKS; r++) pa.peerSpectra[r] = c.slabMode && r < c.nRanks ? c.peerSpectra[r] : (void*) c.dGridC.d;
         pa.rowStride = 0; pa.chunk = 0;
-        pa.grid = c.dGrid.d; pa.gridC = c.dGridC.d; pa.eterm = f.eterm; pa.pot = c.dPot.d;
+        pa.grid = c.dGrid.d; pa.gridC = c.dGridC.d; pa.eterm = f.eterm; pa.pot = c.dPot.d; pa.potDouble = f.potDouble;
         pa.energy = energyBase; pa.wantEnergy = f.wantEnergy; pa.lam = f.lam;
         const int planeStatus = (c.flags & NBS_FLAG_LINE_FFT) ? NBS_RETRY : launchPlaneFft<T>(c, plan, pa, half);
         if (planeStatus < 0) return planeStatus;
         if (planeStatus == NBS_OK) {
             timerMark(c, half == 0 ? "fft_fwd" : (half == 3 ? "fft_inv" : "fft_conv_inv"));
             if (half == 1 || half == 3) {
-                k_gather<<<atomCtas, pmeThreads, sizeof(PmeWarpTab<float, true>)*(pmeThreads/32), st>>>(p);
+                {
+                    if (doubleForces) {
+                        // double-precision gather: half the warps per CTA (its tables are twice the size)
+                        PmeArgs pd = p;
+                        k_gather<double><<<2*atomCtas, pmeThreads/2, sizeof(PmeWarpTab<double, true>)*(pmeThreads/64), st>>>(pd);
+                    }
+                    else k_gather<float><<<atomCtas, pmeThreads, sizeof(PmeWarpTab<float, true>)*(pmeThreads/32), st>>>(p);
+                }
                 c.launches++;
                 timerMark(c, "gather");
             }
@@ -917,7 +932,14 @@ static int launchPmeT(Context& c, bool wantEnergy, int half) {
     else launchFftChain<T, 8>(c, f, px, py, pz, smX, smY, smZ, half);
     timerMark(c, half == 0 ? "fft_fwd" : "fft_conv_inv");
     if (half == 1) {
-        k_gather<<<atomCtas, pmeThreads, sizeof(PmeWarpTab<float, true>)*(pmeThreads/32), st>>>(p);
+        {
+                    if (doubleForces) {
+                        // double-precision gather: half the warps per CTA (its tables are twice the size)
+                        PmeArgs pd = p;
+                        k_gather<double><<<2*atomCtas, pmeThreads/2, sizeof(PmeWarpTab<double, true>)*(pmeThreads/64), st>>>(pd);
+                    }
+                    else k_gather<float><<<atomCtas, pmeThreads, sizeof(PmeWarpTab<float, true>)*(pmeThreads/32), st>>>(p);
+                }
         c.launches++;
         timerMark(c, "gather");
     }
@@ -928,8 +950,8 @@ static int launchPmeT(Context& c, bool wantEnergy, int half) {
 // half 0: spread + forward z/y transforms of the own subsets; half 1: x pass + convolution, inverse, gather
 // (slab sharding: half 2 = x pass alone, half 3 = inverse transforms + gather).
 int launchPme(Context& c, bool wantEnergy, int half) {
-    const bool fp64 = wantEnergy && !(c.flags & NBS_FLAG_FP32_ENERGY);
-    return fp64 ? launchPmeT<double>(c, true, half) : launchPmeT<float>(c, wantEnergy, half);
+    const bool fp64 = (wantEnergy && !(c.flags & NBS_FLAG_FP32_ENERGY)) || (c.flags & NBS_FLAG_DOUBLE);
+    return fp64 ? launchPmeT<double>(c, wantEnergy, half) : launchPmeT<float>(c, wantEnergy, half);
 }
 
 } // namespace nbs

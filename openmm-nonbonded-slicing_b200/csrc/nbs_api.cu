@@ -210,6 +210,12 @@ static int applyParameters(Context& c) {
     NBS_CUDA_CHECK(cudaMemcpy(c.dChargeF.d, chargeF.data(), sizeof(float)*N, cudaMemcpyHostToDevice));
     NBS_CUDA_CHECK(cudaMemcpy(c.dSigEps.d, sigEps.data(), sizeof(float2)*N, cudaMemcpyHostToDevice));
     NBS_CUDA_CHECK(cudaMemcpy(c.dCharge.d, q.data(), sizeof(double)*N, cudaMemcpyHostToDevice));
+    if (c.flags & NBS_FLAG_DOUBLE) {
+        std::vector<double2> sigEpsD(N);
+        for (int i = 0; i < N; i++) sigEpsD[i] = make_double2(0.5*sig[i], 2.0*std::sqrt(eps[i]));
+        NBS_CUDA_CHECK(c.dSigEpsD.ensure(N));
+        NBS_CUDA_CHECK(cudaMemcpy(c.dSigEpsD.d, sigEpsD.data(), sizeof(double2)*N, cudaMemcpyHostToDevice));
+    }
     NBS_CUDA_CHECK(cudaMemcpy(c.dExclStart.d, exclStart.data(), sizeof(int)*(N+1), cudaMemcpyHostToDevice));
     NBS_CUDA_CHECK(cudaMemcpy(c.dExclList.d, exclList.data(), sizeof(int)*exclList.size(), cudaMemcpyHostToDevice));
     if (c.nExc > 0) {
@@ -280,7 +286,7 @@ int uploadPmeTables(Context& c) {
     const size_t G = (size_t) nx*ny*nz, Gh = (size_t) nx*ny*(nz/2+1);
     NBS_CUDA_CHECK(c.dGrid.ensure(G*c.nS));
     NBS_CUDA_CHECK(c.dGridC.ensure(Gh*c.nS));
-    NBS_CUDA_CHECK(c.dPot.ensure(G*c.nS));
+    NBS_CUDA_CHECK(c.dPot.ensure(((c.flags & NBS_FLAG_DOUBLE) ? 2 : 1)*G*c.nS));      // (double-precision mode: a double potential grid)
     return NBS_OK;
 }
 
@@ -418,7 +424,7 @@ static int checkDevice(int device) {
 
 static void releaseAll(Context& c) {
     timerReset(c);
-    c.dSubset.release(); c.dChargeF.release(); c.dSigEps.release(); c.dCharge.release();
+    c.dSubset.release(); c.dChargeF.release(); c.dSigEps.release(); c.dCharge.release(); c.dSigEpsD.release(); c.dLamD.release();
     c.dExclStart.release(); c.dExclList.release(); c.dExcPair.release(); c.dExcParam.release(); c.dExcSlice.release();
     c.dPosIn.release(); c.dForceOut.release(); c.dFix.release(); c.dFixBuild.release(); c.dBinCount.release(); c.dBinStart.release();
     c.dBinCursor.release(); c.dScanTmp.release(); c.dSortedToOrig.release(); c.dOrigToSorted.release();
@@ -1270,7 +1276,7 @@ int nbs_get_exchange_buffers(nbs_context* ctx, nbs_exchange_buffers* out) {
     if (!ctx || !out) return fail(NBS_ERR_INVALID, "null argument");
     Context& c = ctx->c;
     if (out->struct_size != (int32_t) sizeof(nbs_exchange_buffers)) return fail(NBS_ERR_INVALID, "nbs_exchange_buffers.struct_size mismatch");
-    const bool fp64 = c.phaseEnergy && !(c.flags & NBS_FLAG_FP32_ENERGY);
+    const bool fp64 = (c.phaseEnergy && !(c.flags & NBS_FLAG_FP32_ENERGY)) || (c.flags & NBS_FLAG_DOUBLE);
     const size_t Gh = (size_t) c.grid[0]*c.grid[1]*(c.grid[2]/2 + 1);
     out->spectra = c.dGridC.d;
     out->spectrum_bytes_per_subset = (int64_t) (Gh*(fp64 ? sizeof(double2) : sizeof(float2)));

@@ -148,6 +148,8 @@ struct Context {
     Buf<int> dSubset;
     Buf<float> dChargeF;                     // q*sqrt(K)
     Buf<float2> dSigEps;
+    Buf<double2> dSigEpsD;                   // NBS_FLAG_DOUBLE: (sigma/2, 2 sqrt(eps)) in double, particle order
+    Buf<double> dLamD;                       // NBS_FLAG_DOUBLE: the lambda table in double
     Buf<double> dCharge;                     // q (double)
     Buf<float> dC6F;                         // LJPME: c6 = 8 (sigma/2)^3 2 sqrt(eps) per particle (:395-396), the dispersion grid's "charge"
     Buf<double> dC6D;

@@ -124,6 +124,10 @@ void B200CalcSlicedNonbondedForceKernel::describe(const System& system, const Sl
     }
     s.device_index = cu.getDeviceIndex();
     s.flags = cu.getPlatformData().deterministicForces ? NBS_FLAG_DETERMINISTIC : 0;
+    // the platform's Precision property (CommonNonbondedSlicingKernels.cpp:297-299): "double" selects double-precision
+    // forces, "single" single-precision energies; "mixed" is the library's default (fp32 forces, fp64 energies)
+    if (cu.getUseDoublePrecision()) s.flags |= NBS_FLAG_DOUBLE;
+    else if (!cu.getUseMixedPrecision()) s.flags |= NBS_FLAG_FP32_ENERGY;
 }
 
 void B200CalcSlicedNonbondedForceKernel::initialize(const System& system, const SlicedNonbondedForce& force) {

@@ -835,3 +835,63 @@ def test_openmm_cuda_buffer_layouts(nbs, platform, systems, oracle):
             assert (count, h) == (ref.pair_count, ref.pair_hash)
         else:       # float32 coordinates are OpenMM's single-precision mode: positions themselves are rounded
             assert force_rel_rms(f, ref.forces) <= 2e-4
+
+
+DOUBLE_CASES = [("PME", None, False), ("PME", (0.3, -0.2, 0.25), False), ("LJPME", None, False), ("Ewald", None, False),
+                ("CutoffPeriodic", None, True), ("CutoffPeriodic", (0.25, 0.1, -0.3), False), ("CutoffNonPeriodic", None, True),
+                ("NoCutoff", None, False)]
+
+
+@pytest.mark.parametrize("method,tilt,switch", DOUBLE_CASES)
+def test_double_precision_mode(nbs, oracle, method, tilt, switch):
+    """NBS_FLAG_DOUBLE, the plugin's Precision = double (CommonNonbondedSlicingKernels.cpp:297-299; the reference registers
+    every CUDA test in single, mixed and double, platforms/cuda/tests/CMakeLists.txt:22-24): direct space in double
+    precision arithmetic from the exact coordinates, double PME grids / transforms / gather.  Against the oracle, which is
+    double throughout: forces to 1e-7 relative RMS (measured 2e-8: a hundred times tighter than the mixed-precision default;
+    what is left is the 32 fractional bits the coordinates carry -- 6.5e-10 nm in this box, 4e-8 of an r^-13 force at close
+    contact -- not the arithmetic).  Slice energies are double-precision sums in the default mode already; they are held to
+    the same 1e-5 * max(|E|, 1) here (measured: 6e-8 direct space, 2e-6 on a reciprocal-space cross term of 0.1 kJ/mol that
+    is the difference of structure-factor products a thousand times larger -- the coordinate grid again, identical in
+    both modes)."""
+    rng = np.random.default_rng(77)
+    system, force, positions = random_system(nbs, rng, n=400, nsub=3, L=2.8, grid=(24, 20, 24), method=method, tilt=tilt)
+    if method == "LJPME":
+        force.setLJPMEParameters(2.4, 14, 12, 14)
+    if switch:
+        force.setUseSwitchingFunction(True)
+        force.setSwitchingDistance(0.8*force.getCutoffDistance())
+    ctx = nbs.Context(system, nbs.Platform(flags=nbs.abi.NBS_FLAG_DOUBLE))
+    mixed = nbs.Context(system, nbs.Platform())
+    ref = nbs.Context(system, oracle.OraclePlatform("port"))
+    for c in (ctx, mixed, ref):
+        c.setPositions(positions)
+        c.setParameter("lc", 0.6)
+        c.setParameter("lv", 0.3)
+    for groups in (0xFFFFFFFF,):
+        for _ in range(3):                      # plain launches, graph capture, graph replay
+            a = ctx.getState(getEnergy=True, getForces=True, groups=groups)
+        m = mixed.getState(getEnergy=True, getForces=True, groups=groups)
+        b = ref.getState(getEnergy=True, getForces=True, groups=groups)
+        err_double, err_mixed = force_rel_rms(a.getForces(), b.getForces()), force_rel_rms(m.getForces(), b.getForces())
+        assert err_double <= 1e-7, (err_double, err_mixed)
+        assert err_double < 0.05*err_mixed, (err_double, err_mixed)          # and it really is another arithmetic
+        ea, eb = ctx.impls[0].kernel.lastSliceEnergies, ref.impls[0].kernel.lastSliceEnergies
+        err = np.abs(ea-eb)/np.maximum(np.abs(eb), 1.0)
+        assert err.max() <= E_TOL, err
+
+
+def test_double_precision_mode_c2_three_way(nbs, systems, oracle):
+    """C2 (7,530 atoms, exceptions, offsets-free) in double-precision mode: direct-only, reciprocal-only and full
+    evaluations against the oracle, forces to 1e-7, slice energies to the common tolerance."""
+    g = np.load(os.path.join(GOLDEN, "C2_reference.npz"))
+    s = systems.make_system("C2")
+    kernel = nbs.B200CalcSlicedNonbondedForceKernel(nbs.Platform(flags=nbs.abi.NBS_FLAG_DOUBLE))
+    kernel.initialize(s.system, s.force)
+    n = s.force.getNumParticles()
+    for tag, (direct, recip) in {"direct": (True, False), "recip": (False, True), "full": (True, True)}.items():
+        f = np.zeros((n, 3))
+        e = kernel._evaluate(s.positions, s.box, g["lambdas"], np.zeros(0), direct, recip, f)
+        r = oracle.evaluate(kernel.desc, s.positions, s.box, g["lambdas"], None, direct, recip, kind="port")
+        assert force_rel_rms(f, r.forces) <= 1e-7, tag
+        err = np.abs(e-r.slice_energies)/np.maximum(np.abs(r.slice_energies), 1.0)
+        assert err.max() <= E_TOL, (tag, err)

@@ -8,7 +8,8 @@ systems = importlib.import_module("openmm-nonbonded-slicing_b200.systems")
 from oracle import oracle  # noqa: E402  (diagnostic: the oracle is the checker)
 name = sys.argv[1] if len(sys.argv) > 1 else "C3"
 s = systems.make_system(name)
-k = nbs.B200CalcSlicedNonbondedForceKernel(nbs.Platform())
+precision = sys.argv[2] if len(sys.argv) > 2 else "mixed"          # single | mixed | double
+k = nbs.B200CalcSlicedNonbondedForceKernel(nbs.Platform(properties={"Precision": precision}))
 k.initialize(s.system, s.force)
 lam = np.ones((s.force.getNumSlices(), 2))
 for direct, recip in ((True, False), (False, True), (True, True)):
@@ -19,3 +20,4 @@ for direct, recip in ((True, False), (False, True), (True, True)):
     print(name, "direct" if direct else "", "recip" if recip else "", "force relRMS %.2e" % np.sqrt(((f-r.forces)**2).sum()/(r.forces**2).sum()),
           "max energy err %.2e" % err.max(), "at", np.unravel_index(err.argmax(), err.shape))
     print(np.array2string(err, precision=1))
+    print(np.array2string(e, precision=9), np.array2string(r.slice_energies, precision=9))

@@ -895,3 +895,24 @@ def test_double_precision_mode_c2_three_way(nbs, systems, oracle):
         assert force_rel_rms(f, r.forces) <= 1e-7, tag
         err = np.abs(e-r.slice_energies)/np.maximum(np.abs(r.slice_energies), 1.0)
         assert err.max() <= E_TOL, (tag, err)
+
+
+@pytest.mark.parametrize("lambda_elec,lambda_vdw", [(1.0, 1.0), (0.5, 1.0), (0.0, 0.5)])
+def test_c2_alchemical_lambda_settings(nbs, platform, systems, oracle, lambda_elec, lambda_vdw):
+    """C2 (alchemical solvation: a 30-atom ligand in 2,500 waters) at the three settings SURVEY 8(d) names --
+    (lambda_elec, lambda_vdw) = (1, 1), (0.5, 1), (0, 0.5) -- through the Context API: total energy, forces and BOTH
+    energy parameter derivatives against the reference's own TUs."""
+    s = systems.make_system("C2")
+    cpu = oracle.OraclePlatform("reference" if oracle.available("reference") else "port")
+    contexts = [nbs.Context(s.system, platform), nbs.Context(s.system, cpu)]
+    for c in contexts:
+        c.setPositions(s.positions)
+        c.setParameter("lambda_elec", lambda_elec)
+        c.setParameter("lambda_vdw", lambda_vdw)
+    a, b = (c.getState(getEnergy=True, getForces=True, getParameterDerivatives=True) for c in contexts)
+    assert force_rel_rms(a.getForces(), b.getForces()) <= F_TOL
+    assert abs(a.getPotentialEnergy() - b.getPotentialEnergy()) <= E_TOL*max(1.0, abs(b.getPotentialEnergy()))
+    da, db = a.getEnergyParameterDerivatives(), b.getEnergyParameterDerivatives()
+    assert set(da) == {"lambda_elec", "lambda_vdw"} == set(db)
+    for name in db:
+        assert abs(da[name] - db[name]) <= E_TOL*max(1.0, abs(db[name])), (name, da[name], db[name])

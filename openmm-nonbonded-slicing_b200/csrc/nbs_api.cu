@@ -393,13 +393,11 @@ static int setupGeometry(Context& c, const double L[3], const double origin[3], 
     NBS_CUDA_CHECK(c.dGmX.ensure((size_t) c.maxLocalBlocks*(c.capX/32)));
     // work items: enough warps' worth of items to balance 148 SMs x 16 warps on small systems, larger
     // chunks (fewer i-force flushes) on big ones
-    c.chunkTiles = N < 150000 ? 1 : (N < 600000 ? 4 : 8);
-    if (c.nRanks > 1) {
-        // a rank's share of a large system: its ~2,400 warps should still get several items each (measured on C5 at 8
-        // ranks, 133 k atoms' worth of blocks per rank: one tile per item 0.546 ms, eight tiles per item 0.512 ms)
-        const long long localN = (long long) N*std::max(1, c.blockWidth)/std::max(1, c.blockPeriod);
-        c.chunkTiles = localN < 60000 ? 1 : (localN < 250000 ? 4 : 8);
-    }
+    // (sized by the atoms whose i-blocks this rank works on.  Measured, pair kernel with energies: C3 122 / 120 / 129 us at
+    // 1 / 2 / 3 tiles per item, C4 381 / 341 / 347 us at 1 / 2 / 4, C5 on 8 ranks -- 133 k atoms' worth of blocks per rank --
+    // 0.546 / 0.512 ms at 1 / 8: profiles/r02_chunk_tiles_sweep.log)
+    const long long localN = c.nRanks > 1 ? (long long) N*std::max(1, c.blockWidth)/std::max(1, c.blockPeriod) : N;
+    c.chunkTiles = localN < 40000 ? 1 : (localN < 110000 ? 2 : (localN < 250000 ? 4 : 8));
     if (const char* env = getenv("NBS_CHUNK_TILES")) c.chunkTiles = std::max(1, atoi(env));     // tuning experiments
     NBS_CUDA_CHECK(c.dItems.ensure((size_t) c.maxLocalBlocks*(((c.capJ + c.capX)/32 + c.chunkTiles - 1)/c.chunkTiles + 1)));
     // PME from particle-order coordinates while the grids are comfortably L2-resident (scattered access is free

@@ -939,7 +939,10 @@ static unsigned long long mix64(unsigned long long h, unsigned long long v) {
     return h;
 }
 
-// Everything a captured evaluation depends on besides the contents of device memory.
+// Everything a captured evaluation depends on besides the contents of device memory.  Device memory itself is read at
+// replay: positions, the caller's atom_index array (OpenMM re-orders atoms every few hundred steps -- the array's
+// CONTENTS change, its address does not, and k_prep / k_reprep read it afresh in every replay), lambdas' effect
+// travels through paramVersion (they are kernel arguments, so a change re-captures).
 static unsigned long long graphSignature(const Context& c, const nbs_exec_args* a) {
     unsigned long long h = 0x243F6A8885A308D3ull;
     h = mix64(h, (unsigned long long) a->positions); h = mix64(h, (unsigned long long) a->forces);

@@ -1,11 +1,4 @@
-V=$PWD/openmm-nonbonded-slicing_b200/csrc/variants
-out=gpurun_out/r02_occupancy_variants.log
-rm -f $out
-for lib in default w6m3 w4m5; do
-  if [ $lib = default ]; then unset NBS_B200_LIBRARY; else export NBS_B200_LIBRARY=$V/lib_$lib.so; fi
-  echo "== $lib" >> $out
-  timeout 120 python tools/time_kernels.py C3 20 2>&1 | tail -1 | sed 's/.*C3 /C3 /' | cut -c1-110 >> $out
-  timeout 120 python tools/time_kernels.py C3 20 forces 2>&1 | tail -1 | sed 's/.*C3 /C3 /' | cut -c1-110 >> $out
-  timeout 300 python tools/time_kernels.py C5 4 2>&1 | tail -1 | sed 's/.*C5 /C5 /' | cut -c1-110 >> $out
-done
-cat $out
+# scratch script for `gpurun -- 'bash tools/_call.sh'`: what a round-end check runs
+set -x
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -8 > gpurun_out/gputest.log; cat gpurun_out/gputest.log
+timeout 400 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_c3.json 2> gpurun_out/bench_c3.err; tail -3 gpurun_out/bench_c3.err; cat gpurun_out/bench_c3.json

@@ -207,6 +207,7 @@ def run_reference(args, workload_name):
     nbs = importlib.import_module("openmm-nonbonded-slicing_b200")
     kind = "reference" if oracle.available("reference") else "port"
     description = load_description(workload_name)
+    cfg = importlib.import_module("openmm-nonbonded-slicing_b200.systems").CONFIGS.get(workload_name, {})
     warmup, steps = args.warmup, args.steps
     if REFERENCE_SECONDS_PER_EVAL.get(workload_name, 1.0)*(warmup + steps) > 240.0:
         warmup, steps = 0, 1
@@ -253,7 +254,11 @@ def run_reference(args, workload_name):
         "steps": steps, "warmup": warmup, "requested": {"steps": args.steps, "warmup": args.warmup},
         "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{workload_name}: {description}", "ns_per_day_2fs": ns_per_day(value)},
+        "config": {"workload": f"{workload_name}: {description}", "atoms": CONFIG_ATOMS.get(workload_name),
+                   "subsets": len(cfg.get("solute", [])) + 1 + (1 if workload_name == "C1" else 0), "pme_grid": cfg.get("grid"),
+                   "cutoff_nm": 1.0, "ns_per_day_2fs": ns_per_day(value),
+                   "motion": "none: the CPU arm evaluates the un-moved configuration (its cost does not depend on the positions; "
+                             "it rebuilds its neighbour list on every evaluation, like the Reference platform)"},
         "cpu_baseline": {"value": value, "unit": "evals/s", "cores": os.cpu_count(), "kind": kind, "sample": sample,
                          "breakdown_s": timings},
         "cached": n_evals == 0, "evaluations_run_now": n_evals, "run_s": time.perf_counter()-t_run0,

@@ -464,6 +464,8 @@ def bench_main(args, workload_name):
     kernel = factory(0)
     ok, why = 1, ""
     try:
+        if os.environ.get("NBS_BENCH_SCHEME", "peer") != "peer":      # exercise the NCCL scheme on a box that has peer access
+            raise RuntimeError("NBS_BENCH_SCHEME asks for the NCCL scheme")
         connect_peers(kernel, plan, rank, dist)
     except Exception as exc:                       # noqa: BLE001 -- reported in the line; the other GPU scheme is used
         ok, why = 0, str(exc)
@@ -473,7 +475,17 @@ def bench_main(args, workload_name):
     pme_group = None
     if not peer_mode:
         del kernel
-        plan = ShardPlan(world, ns)
+        # the round-1 scheme: rank 0 measures direct-space and PME times and derives the i-block shares (grid owners get
+        # less direct space), everybody adopts its plan
+        payload = [None]
+        if rank == 0:
+            def run_alone(k):
+                k.prepare(moving.pos.data_ptr(), s.box, frc_dev.data_ptr(), lam, stream=stream)
+                return evaluate_distributed(ShardPlan(1, ns), 0, k, dist, None)
+            calibrated, _ = calibrate_plan(factory, world, ns, run_alone)
+            payload = [calibrated.widths]
+        dist.broadcast_object_list(payload, src=0)
+        plan = ShardPlan(world, ns, [float(w) for w in payload[0]])
         pme_group = dist.new_group(plan.pme_ranks()) if plan.num_pme_ranks > 1 else None
         kernel = factory(0)
         kernel.set_plan(plan, rank)

@@ -37,6 +37,24 @@ def test_struct_sizes_match(nbs, tmp_path):
                                      abi.ExecArgs.stream.offset]
 
 
+def test_peer_export_layout_and_c_example(nbs, tmp_path):
+    """nbs_peer_export (peer-memory sharding) has the same layout in C and in ctypes, and the plain-C host example of
+    the peer API compiles against the header."""
+    import subprocess
+    src = tmp_path/"peer.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "nbslice_b200.h"\n'
+                   'int main(){printf("%zu %zu %zu %zu %d %d\\n", sizeof(nbs_peer_export), offsetof(nbs_peer_export, spectra),'
+                   'offsetof(nbs_peer_export, spectra_ipc), offsetof(nbs_peer_export, mailbox_ipc), NBS_MAX_RANKS, NBS_NUM_STEPS);return 0;}\n')
+    exe = tmp_path/"peer"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    abi = nbs.abi
+    assert out == [C.sizeof(abi.PeerExport), abi.PeerExport.spectra.offset, abi.PeerExport.spectra_ipc.offset,
+                   abi.PeerExport.mailbox_ipc.offset, abi.NBS_MAX_RANKS, abi.NBS_NUM_STEPS]
+    example = os.path.join(ROOT, "openmm-nonbonded-slicing_b200", "examples", "peer_sharding.c")
+    subprocess.run(["gcc", "-std=c11", "-D_DEFAULT_SOURCE", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-fsyntax-only", example], check=True)
+
+
 def test_pair_hash_matches_header(nbs, tmp_path):
     import subprocess
     src = tmp_path/"h.c"

@@ -23,7 +23,8 @@ frc = torch.zeros((n, 3), dtype=torch.float64, device="cuda")
 lam = np.ones((s.force.getNumSlices(), 2))
 flush = torch.empty(256*1024*1024, dtype=torch.uint8, device="cuda")
 
-prof = nbs.B200CalcSlicedNonbondedForceKernel(nbs.Platform(flags=nbs.abi.NBS_FLAG_PROFILE))
+precision = os.environ.get("NBS_PRECISION", "mixed")          # single | mixed | double (the platform's Precision property)
+prof = nbs.B200CalcSlicedNonbondedForceKernel(nbs.Platform(flags=nbs.abi.NBS_FLAG_PROFILE, properties={"Precision": precision}))
 prof.initialize(s.system, s.force)
 acc = {}
 for it in range(3 + reps):
@@ -33,7 +34,7 @@ for it in range(3 + reps):
     if it >= 3:
         for k, t in prof.getKernelTimes():
             acc[k] = acc.get(k, 0.0) + 1e3*t/reps
-kernel = nbs.B200CalcSlicedNonbondedForceKernel(nbs.Platform())
+kernel = nbs.B200CalcSlicedNonbondedForceKernel(nbs.Platform(properties={"Precision": precision}))
 kernel.initialize(s.system, s.force)
 times = []
 for it in range(5 + reps):
@@ -46,5 +47,5 @@ for it in range(5 + reps):
     torch.cuda.synchronize()
     if it >= 5:
         times.append(1e3*a.elapsed_time(b))
-print(os.environ.get("NBS_B200_LIBRARY", "default"), name, "energy" if want_energy else "forces",
+print(os.environ.get("NBS_B200_LIBRARY", "default"), precision, name, "energy" if want_energy else "forces",
       "eval_us %.1f (min %.1f)" % (np.mean(times), np.min(times)), " ".join(f"{k}={v:.1f}" for k, v in acc.items()))

@@ -1,4 +1,5 @@
-// k_nlist.cu -- tile neighbour list with exclusion masks, rebuilt every evaluation.
+// k_nlist.cu -- tile neighbour list with exclusion masks; built with cutoff + skin and re-used until an atom has moved
+// half the skin (nbs_set_list_skin; skin 0 = rebuilt on every evaluation).
 //
 // Replaces what the reference gets from OpenMM: computeNeighborListVoxelHash + the exclusion sets
 // on the Reference platform (ReferenceNonbondedSlicingKernels.cpp:101-106, 197) and

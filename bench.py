@@ -37,8 +37,8 @@ FLOP_PER_PAIR = 72            # FP32-equivalent flops per interacti
 FS_PER_STEP = 2.0             # ns/day figure assumes one evaluation per 2 fs step
 THERMAL_SIGMA_NM = 0.0009     # displacement per step and component: ~300 K, 12 amu, 2 fs (an oxygen; hydrogens move 3x further
                               # in reality, rigid water constraints slow them again -- one figure for every atom keeps it simple)
-MOTION = (f"ballistic: every atom has its own velocity, N(0, {THERMAL_SIGMA_NM} nm) per component and step (about 300 K at 2 fs); "
-          "positions are advanced between steps, outside the timed region")
+MOTION = (f"ballistic: every atom has its own velocity, N(0, {THERMAL_SIGMA_NM} nm) per component and step (about 300 K at 2 fs), "
+          "reversed every 48 steps; positions are advanced between steps, outside the timed region")
 # DRAM traffic of one k_pair launch from the committed ncu captures (profiles/README.md): the kernel's working
 # set (positions, parameters, lists) is L2-resident, so this is far below any bandwidth limit
 PAIR_TRAFFIC_BYTES = {"C3": 8676608}
@@ -298,12 +298,22 @@ class MovingSystem:
         self.vel = torch.tensor(self.vel_host, dtype=torch.float64, device=device)
         self.pos = self.pos0.clone()
 
+    TURN = 48          # steps after which every velocity is reversed
+
+    @classmethod
+    def phase(cls, t):
+        """Steps' worth of displacement at step t: 0, 1, .., TURN, TURN-1, .., 0, 1, ..  A long run (--steps 500) then
+        never carries atoms further than TURN steps from the generated configuration -- far enough for the list to be
+        rebuilt every few steps, not so far that atoms overlap and forces leave the 64-bit fixed-point range."""
+        k = t % (2*cls.TURN)
+        return k if k <= cls.TURN else 2*cls.TURN - k
+
     def advance(self, t):
         import torch
-        torch.add(self.pos0, self.vel, alpha=float(t), out=self.pos)
+        torch.add(self.pos0, self.vel, alpha=float(self.phase(t)), out=self.pos)
 
     def host_positions(self, t, lo=0, hi=None):
-        return self.pos0_host[lo:hi] + t*self.vel_host[lo:hi]
+        return self.pos0_host[lo:hi] + self.phase(t)*self.vel_host[lo:hi]
 
 
 MIN_WARMUP = 24

@@ -325,6 +325,11 @@ int nbs_get_launch_count(const nbs_context* ctx, int64_t* launches);
  * group of entries can reach are stepped), [4] exclusion-list entries */
 int nbs_get_nlist_stats(nbs_context* ctx, int64_t stats[8]);
 
+/* Host-only diagnostic (no device is touched): f(s) = erfc(alpha sqrt(s))/sqrt(s) for n values of s = r^2 exactly as the pair
+ * kernel's energy path evaluates it from its table (c0 in double + a single-precision remainder); NaN
+ * where the kernel takes its analytic branch instead (s < 2^-7 nm^2 or beyond the table). */
+int nbs_debug_erfc_table(double alpha, double cutoff, int32_t n, const double* s, double* f);
+
 /* Measured instruction-rate ceilings of `device` (diagnostics for the benchmark's roofline; no reference
  * counterpart): out[0] = dense FP32 FMA rate in TFLOP/s, out[1] = rsqrt.approx rate in Gop/s,
  * out[2] = SM count, out[3] = nominal SM clock in MHz. */

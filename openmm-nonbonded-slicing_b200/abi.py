@@ -177,6 +177,7 @@ EXPORTS = [
     "nbs_get_kernel_times", "nbs_get_launch_count", "nbs_get_nlist_stats",
     "nbs_set_shard", "nbs_execute_begin", "nbs_execute_convolve", "nbs_execute_finish", "nbs_get_exchange_buffers",
     "nbs_set_slab_shard", "nbs_export_peer", "nbs_import_peers", "nbs_execute_step",
+    "nbs_debug_erfc_table",
     "nbs_debug_set_list_capacity", "nbs_measure_peaks", "nbs_measure_dp_rates", "nbs_set_list_skin", "nbs_get_list_stats",
 ]
 
@@ -223,6 +224,7 @@ def load_library():
     lib.nbs_execute_step.argtypes = [C.c_void_p, C.POINTER(ExecArgs), C.c_int32]
     lib.nbs_debug_set_list_capacity.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
     lib.nbs_get_exchange_buffers.argtypes = [C.c_void_p, C.POINTER(ExchangeBuffers)]
+    lib.nbs_debug_erfc_table.argtypes = [C.c_double, C.c_double, C.c_int32, _f64p, _f64p]
     lib.nbs_measure_peaks.argtypes = [C.c_int32, _f64p]
     lib.nbs_measure_dp_rates.argtypes = [C.c_int32, _f64p]
     lib.nbs_set_list_skin.argtypes = [C.c_void_p, C.c_double]

@@ -294,12 +294,13 @@ int uploadPmeTables(Context& c) {
 // (k_pair.cu pairStep): degree-4 interpolation at Chebyshev nodes on every interval [2^e (1 + m/128),
 // 2^e (1 + (m+1)/128)), e = -7 .., in the variable d = (s - centre)/width; c0 in double, c1..c4 in single precision
 // (ERFC_TAB_* in nbs_internal.h).  Built from libm's long-double erfc.
-static int buildErfcTable(Context& c) {
+// (host only: returns the number of rows; `tab` = c0[rows] doubles, then the rows' float4 coefficient sets)
+static int computeErfcTable(double alpha, double cutoff, std::vector<double>& tab) {
     const int M = 1 << ERFC_TAB_PER_OCTAVE_LOG2;
-    const int eMax = std::min(ERFC_TAB_MAX_ROWS/M - 8, std::max(-6, (int) std::floor(std::log2(c.cutoff*c.cutoff)) + 1));
+    const int eMax = std::min(ERFC_TAB_MAX_ROWS/M - 8, std::max(-6, (int) std::floor(std::log2(cutoff*cutoff)) + 1));
     const int rows = (eMax + 7 + 1)*M;
     constexpr int D = 4;
-    std::vector<double> tab((size_t) rows*3, 0.0);               // c0[rows], then float4[rows] = 2 doubles per row
+    tab.assign((size_t) rows*3, 0.0);                            // c0[rows], then float4[rows] = 2 doubles per row
     float* coef = reinterpret_cast<float*>(tab.data() + rows);
     for (int e = -7; e <= eMax; e++)
         for (int m = 0; m < M; m++) {
@@ -312,7 +313,7 @@ static int buildErfcTable(Context& c) {
                 const long double r = std::sqrt(sv);
                 long double pw = 1;
                 for (int j = 0; j <= D; j++) { A[k][j] = pw; pw *= dn; }
-                A[k][D + 1] = std::erfc((long double) c.alpha*r)/r;
+                A[k][D + 1] = std::erfc((long double) alpha*r)/r;
             }
             for (int col = 0; col <= D; col++) {                 // Gaussian elimination, partial pivoting
                 int piv = col;
@@ -328,7 +329,12 @@ static int buildErfcTable(Context& c) {
             tab[row] = (double) (A[0][D + 1]/A[0][0]);
             for (int k = 1; k <= D; k++) coef[4*(size_t) row + k - 1] = (float) (A[k][D + 1]/A[k][k]);
         }
-    c.erfcRows = rows;
+    return rows;
+}
+
+static int buildErfcTable(Context& c) {
+    std::vector<double> tab;
+    c.erfcRows = computeErfcTable(c.alpha, c.cutoff, tab);
     NBS_CUDA_CHECK(c.dErfcTab.ensure(tab.size()));
     NBS_CUDA_CHECK(cudaMemcpy(c.dErfcTab.d, tab.data(), sizeof(double)*tab.size(), cudaMemcpyHostToDevice));
     return NBS_OK;
@@ -1290,6 +1296,34 @@ int nbs_get_exchange_buffers(nbs_context* ctx, nbs_exchange_buffers* out) {
     out->force_words = (c.pmeUnsorted ? 6 : 3)*(int64_t) c.Npad;
     out->energies = c.dEnergy.d;
     out->energy_words = ENERGY_WORDS;
+    return NBS_OK;
+}
+
+// Host-only diagnostic: f(s) = erfc(alpha sqrt(s))/sqrt(s) exactly as the pair kernel's energy path evaluates it (k_pair.cu
+// pairStep: row and position from the bits of the double, c0 in double + the single-precision remainder), from the table
+// buildErfcTable uploads.  NaN where the kernel would take its analytic branch.  No device is touched.
+int nbs_debug_erfc_table(double alpha, double cutoff, int32_t n, const double* s, double* f) {
+    if (!s || !f || n < 0 || !(alpha > 0) || !(cutoff > 0)) return fail(NBS_ERR_INVALID, "illegal argument");
+    std::vector<double> tab;
+    const int rows = computeErfcTable(alpha, cutoff, tab);
+    const float* coef = reinterpret_cast<const float*>(tab.data() + rows);
+    constexpr int L = ERFC_TAB_PER_OCTAVE_LOG2;
+    for (int i = 0; i < n; i++) {
+        unsigned long long bits;
+        std::memcpy(&bits, &s[i], 8);
+        const int hi = (int) (bits >> 32);
+        const unsigned lo = (unsigned) bits;
+        const int idx = (hi >> (20 - L)) - ((1023 - 7) << L);
+        if (idx < 0 || idx >= rows) { f[i] = std::nan(""); continue; }
+        const unsigned frac = (((unsigned) hi & ((1u << (20 - L)) - 1u)) << (3 + L)) | (lo >> (29 - L));
+        const unsigned fbits = 0x3f800000u | frac;
+        float one;
+        std::memcpy(&one, &fbits, 4);
+        const float d = (one - 1.5f) + 5.9604645e-8f;
+        const float* cf = coef + 4*(size_t) idx;
+        const float rem = d*std::fmaf(d, std::fmaf(d, std::fmaf(d, cf[3], cf[2]), cf[1]), cf[0]);
+        f[i] = tab[idx] + (double) rem;
+    }
     return NBS_OK;
 }
 

@@ -139,3 +139,27 @@ def test_cpp_adapter_compiles_against_plugin_interface():
                          capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "adapter compiles" in out.stdout
+
+
+def test_erfc_table_of_the_pair_kernel(nbs):
+    """The table behind the pair kernel's double-precision Coulomb energies (csrc/nbs_api.cu computeErfcTable, evaluated
+    as csrc/k_pair.cu pairStep does: row and position from the bits of r^2, c0 in double + a single-precision degree-4
+    remainder) against erfc(alpha r)/r -- on the host, through the library's own code: 1e-8 worst case, no bias."""
+    from scipy.special import erfc
+    lib = nbs.abi.load_library()
+    rng = np.random.default_rng(0)
+    for alpha, cutoff in ((2.628261, 1.0), (3.5, 0.9), (1.6, 2.0)):
+        s = np.exp(rng.uniform(np.log(2.0**-7), np.log(cutoff*cutoff), size=100000))
+        s[:3] = [2.0**-7, cutoff*cutoff, 0.5*cutoff*cutoff]
+        f = np.zeros_like(s)
+        nbs.abi.check(lib.nbs_debug_erfc_table(alpha, cutoff, len(s), s.ctypes.data_as(C.POINTER(C.c_double)),
+                                               f.ctypes.data_as(C.POINTER(C.c_double))))
+        ref = erfc(alpha*np.sqrt(s))/np.sqrt(s)
+        err = (f - ref)/ref
+        assert not np.isnan(f).any()
+        assert np.abs(err).max() < 1e-8 and abs(err.mean()) < 1e-10, (alpha, cutoff, np.abs(err).max(), err.mean())
+    # outside the table the kernel takes its analytic branch: the diagnostic says so with NaN
+    s = np.array([2.0**-8, 1.0e3])
+    f = np.zeros(2)
+    nbs.abi.check(lib.nbs_debug_erfc_table(2.6, 1.0, 2, s.ctypes.data_as(C.POINTER(C.c_double)), f.ctypes.data_as(C.POINTER(C.c_double))))
+    assert np.isnan(f).all()
